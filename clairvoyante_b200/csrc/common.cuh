@@ -1,0 +1,57 @@
+// common.cuh -- shared device helpers for libcvb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifndef __CUDA_ARCH_FEAT_SM100_ALL
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ != 1000)
+#error "libcvb200 is written for sm_100a only"
+#endif
+#endif
+
+namespace cvb {
+
+// reference clairvoyante/selu.py:23-24
+__device__ __forceinline__ float selu_f(float x) {
+  const float alpha = 1.6732632423543772848170429916717f;
+  const float scale = 1.0507009873554804934193349852946f;
+  // scale * where(x >= 0, x, alpha * (exp(x) - 1))   (selu.py:25)
+  float neg = alpha * (__expf(fminf(x, 0.f)) - 1.0f);
+  return scale * (x >= 0.f ? x : neg);
+}
+// d selu / dx expressed through the OUTPUT y = selu(x):  x>=0 -> scale ; x<0 -> y + scale*alpha
+__device__ __forceinline__ float selu_grad_from_out(float y) {
+  const float alpha = 1.6732632423543772848170429916717f;
+  const float scale = 1.0507009873554804934193349852946f;
+  return y >= 0.f ? scale : (y + scale * alpha);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
+}
+// 16-byte async copy that zero-fills when !pred (src must still be a valid address)
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool pred) {
+  int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+// streaming 128-bit global load that does not allocate in L1 (input tensors are read once)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 max4(float4 a, float4 b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+
+}  // namespace cvb

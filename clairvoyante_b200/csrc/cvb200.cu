@@ -1,0 +1,453 @@
+// cvb200.cu -- C ABI of libcvb200.so (see include/cvb200.h for the contract and the
+// reference call sites each entry point replaces).
+#include "../../include/cvb200.h"
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "fwd_simt.cuh"
+#include "train_simt.cuh"
+
+using namespace cvb;
+
+// ------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) return fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" const char* cvb_last_error(void) { return g_err; }
+extern "C" int cvb_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------
+struct VarInfo {
+  std::string name;
+  int ndim;
+  int64_t dims[4];
+  int64_t numel, offset;
+};
+
+static const int CHUNK = 16384;  // sites per device pass (bounds the intermediates)
+
+struct cvb_model {
+  int variant = 0, device = 0, compute_mode = CVB_COMPUTE_FP32, num_sms = 148;
+  std::vector<VarInfo> vars;
+  int64_t nparams = 0, step = 0;
+  float *d_params = nullptr, *d_m = nullptr, *d_v = nullptr, *d_grad = nullptr;
+  // forward work buffers
+  float *d_p2 = nullptr, *d_p3 = nullptr, *d_h4 = nullptr;
+  int64_t p2_site = 0, p3_site = 0, h4_site = 0;
+  // host path: 2 slots
+  float *d_x[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr}, *d_lg[2] = {nullptr, nullptr};
+  float *h_x[2] = {nullptr, nullptr}, *h_out[2] = {nullptr, nullptr}, *h_lg[2] = {nullptr, nullptr};
+  cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t e_h2d[2], e_comp[2], e_d2h[2];
+  bool events = false;
+  int64_t launches = 0;
+  TrainWork* train = nullptr;
+  const float* var(const char* n) const {
+    for (auto& v : vars)
+      if (v.name == n) return d_params + v.offset;
+    return nullptr;
+  }
+  const VarInfo* info(const char* n) const {
+    for (auto& v : vars)
+      if (v.name == n) return &v;
+    return nullptr;
+  }
+};
+
+static void add_var(cvb_model* m, const std::string& name, std::initializer_list<int64_t> dims) {
+  VarInfo v;
+  v.name = name;
+  v.ndim = (int)dims.size();
+  v.numel = 1;
+  int i = 0;
+  for (auto d : dims) { v.dims[i++] = d; v.numel *= d; }
+  for (; i < 4; ++i) v.dims[i] = 1;
+  v.offset = m->nparams;
+  m->nparams += (v.numel + 3) / 4 * 4;  // keep every variable 16-byte aligned
+  m->vars.push_back(v);
+}
+
+static void build_vars(cvb_model* m) {
+  // names/shapes: jupyter_nb/visualization.ipynb:100-121; clairvoyante_v3_slim.py:9-11
+  if (m->variant == CVB_V3) {
+    add_var(m, "conv1/kernel", {1, 4, 4, 16});   add_var(m, "conv1/bias", {16});
+    add_var(m, "conv2/kernel", {2, 4, 16, 32});  add_var(m, "conv2/bias", {32});
+    add_var(m, "conv3/kernel", {3, 4, 32, 48});  add_var(m, "conv3/bias", {48});
+    add_var(m, "fc4/kernel", {4608, 336});       add_var(m, "fc4/bias", {336});
+    add_var(m, "fc5/kernel", {336, 168});        add_var(m, "fc5/bias", {168});
+    add_var(m, "YBaseChangeSigmoid/kernel", {336, 4}); add_var(m, "YBaseChangeSigmoid/bias", {4});
+    add_var(m, "YZygosityFC/kernel", {168, 2});        add_var(m, "YZygosityFC/bias", {2});
+    add_var(m, "YVarTypeFC/kernel", {168, 4});         add_var(m, "YVarTypeFC/bias", {4});
+    add_var(m, "YIndelLengthFC/kernel", {168, 6});     add_var(m, "YIndelLengthFC/bias", {6});
+    m->p2_site = 28 * 128; m->p3_site = 4608; m->h4_site = 336;
+  } else {
+    add_var(m, "conv1/kernel", {1, 4, 4, 8});    add_var(m, "conv1/bias", {8});
+    add_var(m, "conv2/kernel", {3, 4, 8, 16});   add_var(m, "conv2/bias", {16});
+    add_var(m, "conv3/kernel", {5, 4, 16, 32});  add_var(m, "conv3/bias", {32});
+    add_var(m, "fc4/kernel", {4224, 36});        add_var(m, "fc4/bias", {36});
+    add_var(m, "fc5/kernel", {36, 18});          add_var(m, "fc5/bias", {18});
+    add_var(m, "YBaseChangeSigmoid/kernel", {36, 4}); add_var(m, "YBaseChangeSigmoid/bias", {4});
+    add_var(m, "YZygosityFC/kernel", {18, 2});        add_var(m, "YZygosityFC/bias", {2});
+    add_var(m, "YVarTypeFC/kernel", {18, 4});         add_var(m, "YVarTypeFC/bias", {4});
+    add_var(m, "YIndelLengthFC/kernel", {18, 6});     add_var(m, "YIndelLengthFC/bias", {6});
+    m->p2_site = 37 * 64; m->p3_site = 4224; m->h4_site = 36;
+  }
+}
+
+extern "C" int cvb_create(int variant, int device, cvb_model** out) {
+  if (!out) return fail("cvb_create: out is NULL");
+  if (variant != CVB_V3 && variant != CVB_V3_SLIM) return fail("cvb_create: unknown variant %d", variant);
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail("cvb_create: device %d not in [0,%d)", device, ndev);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail("cvb_create: libcvb200 needs an sm_100 GPU, device %d is sm_%d%d", device, prop.major, prop.minor);
+  cvb_model* m = new cvb_model();
+  m->variant = variant;
+  m->device = device;
+  m->num_sms = prop.multiProcessorCount;
+  build_vars(m);
+  const size_t pb = (size_t)m->nparams * 4;
+  CK(cudaMalloc(&m->d_params, pb)); CK(cudaMemset(m->d_params, 0, pb));
+  CK(cudaMalloc(&m->d_m, pb));      CK(cudaMemset(m->d_m, 0, pb));
+  CK(cudaMalloc(&m->d_v, pb));      CK(cudaMemset(m->d_v, 0, pb));
+  CK(cudaMalloc(&m->d_grad, pb + 64)); CK(cudaMemset(m->d_grad, 0, pb + 64));
+  CK(cudaMalloc(&m->d_p2, (size_t)CHUNK * m->p2_site * 4)); CK(cudaMemset(m->d_p2, 0, (size_t)CHUNK * m->p2_site * 4));
+  CK(cudaMalloc(&m->d_p3, (size_t)CHUNK * m->p3_site * 4));
+  CK(cudaMalloc(&m->d_h4, (size_t)CHUNK * m->h4_site * 4));
+  CK(cudaStreamCreateWithFlags(&m->s_comp, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&m->s_h2d, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreateWithFlags(&m->e_h2d[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->e_comp[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->e_d2h[i], cudaEventDisableTiming));
+  }
+  m->events = true;
+  *out = m;
+  return 0;
+}
+
+extern "C" int cvb_destroy(cvb_model* m) {
+  if (!m) return 0;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  train_work_free(m->train);
+  cudaFree(m->d_params); cudaFree(m->d_m); cudaFree(m->d_v); cudaFree(m->d_grad);
+  cudaFree(m->d_p2); cudaFree(m->d_p3); cudaFree(m->d_h4);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(m->d_x[i]); cudaFree(m->d_out[i]); cudaFree(m->d_lg[i]);
+    cudaFreeHost(m->h_x[i]); cudaFreeHost(m->h_out[i]); cudaFreeHost(m->h_lg[i]);
+    if (m->events) { cudaEventDestroy(m->e_h2d[i]); cudaEventDestroy(m->e_comp[i]); cudaEventDestroy(m->e_d2h[i]); }
+  }
+  if (m->s_comp) cudaStreamDestroy(m->s_comp);
+  if (m->s_h2d) cudaStreamDestroy(m->s_h2d);
+  if (m->s_d2h) cudaStreamDestroy(m->s_d2h);
+  delete m;
+  return 0;
+}
+
+extern "C" int cvb_num_variables(const cvb_model* m) { return m ? (int)m->vars.size() : 0; }
+extern "C" int64_t cvb_num_parameters(const cvb_model* m) {
+  int64_t t = 0;
+  if (m) for (auto& v : m->vars) t += v.numel;
+  return t;
+}
+extern "C" int cvb_variable_info(const cvb_model* m, int idx, char* name, int name_cap, int64_t* numel, int* ndim,
+                                 int64_t dims[4]) {
+  if (!m || idx < 0 || idx >= (int)m->vars.size()) return fail("cvb_variable_info: bad index %d", idx);
+  const VarInfo& v = m->vars[idx];
+  if (name && name_cap > 0) { strncpy(name, v.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (numel) *numel = v.numel;
+  if (ndim) *ndim = v.ndim;
+  if (dims) for (int i = 0; i < 4; ++i) dims[i] = v.dims[i];
+  return 0;
+}
+
+static float* slot_ptr(cvb_model* m, int slot) {
+  return slot == 0 ? m->d_params : slot == 1 ? m->d_m : slot == 2 ? m->d_v : nullptr;
+}
+extern "C" int cvb_set_variable(cvb_model* m, const char* name, int slot, const float* host, int64_t n) {
+  if (!m || !name || !host) return fail("cvb_set_variable: NULL argument");
+  const VarInfo* v = m->info(name);
+  if (!v) return fail("cvb_set_variable: no variable named '%s'", name);
+  if (n != v->numel) return fail("cvb_set_variable: '%s' has %lld elements, got %lld", name, (long long)v->numel, (long long)n);
+  float* base = slot_ptr(m, slot);
+  if (!base) return fail("cvb_set_variable: bad slot %d", slot);
+  CK(cudaSetDevice(m->device));
+  CK(cudaMemcpy(base + v->offset, host, (size_t)n * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+extern "C" int cvb_get_variable(cvb_model* m, const char* name, int slot, float* host, int64_t n) {
+  if (!m || !name || !host) return fail("cvb_get_variable: NULL argument");
+  const VarInfo* v = m->info(name);
+  if (!v) return fail("cvb_get_variable: no variable named '%s'", name);
+  if (n != v->numel) return fail("cvb_get_variable: '%s' has %lld elements, got %lld", name, (long long)v->numel, (long long)n);
+  float* base = slot_ptr(m, slot);
+  if (!base) return fail("cvb_get_variable: bad slot %d", slot);
+  CK(cudaSetDevice(m->device));
+  CK(cudaStreamSynchronize(m->s_comp));
+  CK(cudaMemcpy(host, base + v->offset, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int cvb_set_step(cvb_model* m, int64_t t) { if (!m) return fail("NULL model"); m->step = t; return 0; }
+extern "C" int cvb_get_step(const cvb_model* m, int64_t* t) { if (!m || !t) return fail("NULL argument"); *t = m->step; return 0; }
+extern "C" int cvb_set_compute_mode(cvb_model* m, int mode) {
+  if (!m) return fail("NULL model");
+  if (mode != CVB_COMPUTE_FP32) return fail("cvb_set_compute_mode: mode %d is not built into this library yet", mode);
+  m->compute_mode = mode;
+  return 0;
+}
+extern "C" int64_t cvb_kernel_launches(const cvb_model* m) { return m ? m->launches : 0; }
+
+// ------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------
+template <class K>
+static cudaError_t set_smem(K kernel, int bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+static HeadPtrs head_ptrs(const cvb_model* m) {
+  HeadPtrs h;
+  h.w5 = m->var("fc5/kernel"); h.b5 = m->var("fc5/bias");
+  h.wb = m->var("YBaseChangeSigmoid/kernel"); h.bb = m->var("YBaseChangeSigmoid/bias");
+  h.wz = m->var("YZygosityFC/kernel"); h.bz = m->var("YZygosityFC/bias");
+  h.wt = m->var("YVarTypeFC/kernel"); h.bt = m->var("YVarTypeFC/bias");
+  h.wl = m->var("YIndelLengthFC/kernel"); h.bl = m->var("YIndelLengthFC/bias");
+  return h;
+}
+
+// one chunk (n <= CHUNK) of the forward pass on `st`
+static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, float* logits16, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int sms = m->num_sms;
+  if (m->variant == CVB_V3) {
+    {
+      using F = FrontV3<4>;
+      auto k = k_v3_front<4>;
+      CK(set_smem(k, F::SMEM_BYTES));
+      int64_t tiles = (n + 3) / 4;
+      int grid = (int)std::min<int64_t>(tiles, 2 * sms);
+      k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
+                                          m->var("conv2/bias"), m->d_p2);
+      CK(cudaGetLastError());
+    }
+    {
+      using C = ConvCfg<32, 48, 3, 26, 3, 8, 8>;
+      using L = ConvLayerSmem<C, 3>;
+      auto k = k_conv_layer<C, 3, 256>;
+      CK(set_smem(k, L::SMEM_BYTES));
+      int64_t tiles = (n + C::S - 1) / C::S;
+      int grid = (int)std::min<int64_t>(tiles, sms);
+      k<<<grid, 256, L::SMEM_BYTES, st>>>(m->d_p2, n, m->var("conv3/kernel"), m->var("conv3/bias"), m->d_p3);
+      CK(cudaGetLastError());
+    }
+    {
+      using F = FcCfg<336, 21, 16, 12, 8>;
+      auto k = k_fc4<F>;
+      CK(set_smem(k, F::SMEM_BYTES));
+      int grid = (int)((n + F::M - 1) / F::M);
+      k<<<grid, 256, F::SMEM_BYTES, st>>>(m->d_p3, n, 4608, m->var("fc4/kernel"), m->var("fc4/bias"), m->d_h4);
+      CK(cudaGetLastError());
+    }
+    {
+      int grid = (int)((n + 15) / 16);
+      k_tail<336, 168, 16><<<grid, 256, 0, st>>>(m->d_h4, n, head_ptrs(m), out16, logits16);
+      CK(cudaGetLastError());
+    }
+    m->launches += 4;
+  } else {
+    {
+      using F = FrontSlim<6>;
+      auto k = k_slim_front<6>;
+      CK(set_smem(k, F::SMEM_BYTES));
+      int64_t tiles = (n + 5) / 6;
+      int grid = (int)std::min<int64_t>(tiles, 4 * sms);
+      k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
+                                          m->var("conv2/bias"), m->d_p2);
+      CK(cudaGetLastError());
+    }
+    {
+      using C = ConvCfg<16, 32, 5, 33, 3, 8, 8>;
+      using L = ConvLayerSmem<C, 1>;
+      auto k = k_conv_layer<C, 1, 256>;
+      CK(set_smem(k, L::SMEM_BYTES));
+      int64_t tiles = (n + C::S - 1) / C::S;
+      int grid = (int)std::min<int64_t>(tiles, sms);
+      k<<<grid, 256, L::SMEM_BYTES, st>>>(m->d_p2, n, m->var("conv3/kernel"), m->var("conv3/bias"), m->d_p3);
+      CK(cudaGetLastError());
+    }
+    {
+      using F = FcCfg<36, 9, 4, 28, 8>;
+      auto k = k_fc4<F>;
+      CK(set_smem(k, F::SMEM_BYTES));
+      int grid = (int)((n + F::M - 1) / F::M);
+      k<<<grid, 256, F::SMEM_BYTES, st>>>(m->d_p3, n, 4224, m->var("fc4/kernel"), m->var("fc4/bias"), m->d_h4);
+      CK(cudaGetLastError());
+    }
+    {
+      int grid = (int)((n + 15) / 16);
+      k_tail<36, 18, 16><<<grid, 256, 0, st>>>(m->d_h4, n, head_ptrs(m), out16, logits16);
+      CK(cudaGetLastError());
+    }
+    m->launches += 4;
+  }
+  return 0;
+}
+
+extern "C" int cvb_predict_device(cvb_model* m, const float* x, int64_t n, float* out16, float* logits16, void* stream) {
+  if (!m) return fail("cvb_predict_device: NULL model");
+  if (n < 0) return fail("cvb_predict_device: negative n");
+  if (n == 0) return 0;
+  if (!x || !out16) return fail("cvb_predict_device: NULL buffer");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : m->s_comp;
+  for (int64_t s = 0; s < n; s += CHUNK) {
+    int64_t c = std::min<int64_t>(CHUNK, n - s);
+    if (forward_chunk(m, x + s * 528, c, out16 + s * 16, logits16 ? logits16 + s * 16 : nullptr, st)) return 1;
+  }
+  return 0;
+}
+
+static int ensure_host_slots(cvb_model* m) {
+  if (m->d_x[0]) return 0;
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaMalloc(&m->d_x[i], (size_t)CHUNK * 528 * 4));
+    CK(cudaMalloc(&m->d_out[i], (size_t)CHUNK * 16 * 4));
+    CK(cudaMalloc(&m->d_lg[i], (size_t)CHUNK * 16 * 4));
+    CK(cudaMallocHost(&m->h_x[i], (size_t)CHUNK * 528 * 4));
+    CK(cudaMallocHost(&m->h_out[i], (size_t)CHUNK * 16 * 4));
+    CK(cudaMallocHost(&m->h_lg[i], (size_t)CHUNK * 16 * 4));
+  }
+  return 0;
+}
+
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+extern "C" int cvb_predict_host(cvb_model* m, const float* x, int64_t n, float* out16, float* logits16) {
+  if (!m) return fail("cvb_predict_host: NULL model");
+  if (n < 0) return fail("cvb_predict_host: negative n");
+  if (n == 0) return 0;
+  if (!x || !out16) return fail("cvb_predict_host: NULL buffer");
+  CK(cudaSetDevice(m->device));
+  if (ensure_host_slots(m)) return 1;
+  const bool pinned_in = is_pinned(x);
+  const int64_t nchunks = (n + CHUNK - 1) / CHUNK;
+  // software pipeline over chunks: H2D(c+1) || kernels(c) || D2H(c-1)
+  for (int64_t c = 0; c <= nchunks; ++c) {
+    if (c < nchunks) {
+      const int sl = (int)(c & 1);
+      const int64_t s0 = c * CHUNK, cn = std::min<int64_t>(CHUNK, n - s0);
+      const float* src = x + s0 * 528;
+      if (!pinned_in) {
+        if (c >= 2) CK(cudaEventSynchronize(m->e_h2d[sl]));  // staging buffer free again
+        memcpy(m->h_x[sl], src, (size_t)cn * 528 * 4);
+        src = m->h_x[sl];
+      }
+      if (c >= 2) CK(cudaStreamWaitEvent(m->s_h2d, m->e_comp[sl], 0));  // d_x[sl] consumed
+      CK(cudaMemcpyAsync(m->d_x[sl], src, (size_t)cn * 528 * 4, cudaMemcpyHostToDevice, m->s_h2d));
+      CK(cudaEventRecord(m->e_h2d[sl], m->s_h2d));
+      CK(cudaStreamWaitEvent(m->s_comp, m->e_h2d[sl], 0));
+      if (c >= 2) CK(cudaStreamWaitEvent(m->s_comp, m->e_d2h[sl], 0));  // d_out[sl] drained
+      if (forward_chunk(m, m->d_x[sl], cn, m->d_out[sl], logits16 ? m->d_lg[sl] : nullptr, m->s_comp)) return 1;
+      CK(cudaEventRecord(m->e_comp[sl], m->s_comp));
+      CK(cudaStreamWaitEvent(m->s_d2h, m->e_comp[sl], 0));
+      CK(cudaMemcpyAsync(m->h_out[sl], m->d_out[sl], (size_t)cn * 64, cudaMemcpyDeviceToHost, m->s_d2h));
+      if (logits16) CK(cudaMemcpyAsync(m->h_lg[sl], m->d_lg[sl], (size_t)cn * 64, cudaMemcpyDeviceToHost, m->s_d2h));
+      CK(cudaEventRecord(m->e_d2h[sl], m->s_d2h));
+    }
+    if (c >= 1) {
+      const int64_t p = c - 1;
+      const int sl = (int)(p & 1);
+      const int64_t s0 = p * CHUNK, cn = std::min<int64_t>(CHUNK, n - s0);
+      CK(cudaEventSynchronize(m->e_d2h[sl]));
+      memcpy(out16 + s0 * 16, m->h_out[sl], (size_t)cn * 64);
+      if (logits16) memcpy(logits16 + s0 * 16, m->h_lg[sl], (size_t)cn * 64);
+    }
+  }
+  return 0;
+}
+
+extern "C" int cvb_debug_read(cvb_model* m, int which, float* host, int64_t n) {
+  if (!m || !host) return fail("cvb_debug_read: NULL argument");
+  const float* src = which == 0 ? m->d_p2 : which == 1 ? m->d_p3 : which == 2 ? m->d_h4 : nullptr;
+  const int64_t per = which == 0 ? m->p2_site : which == 1 ? m->p3_site : m->h4_site;
+  if (!src) return fail("cvb_debug_read: bad selector %d", which);
+  if (n < 0 || n > (int64_t)CHUNK * per) return fail("cvb_debug_read: n out of range");
+  CK(cudaSetDevice(m->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(host, src, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int cvb_alloc_pinned(int64_t bytes, void** out) {
+  if (!out || bytes <= 0) return fail("cvb_alloc_pinned: bad argument");
+  CK(cudaMallocHost(out, (size_t)bytes));
+  return 0;
+}
+extern "C" int cvb_free_pinned(void* p) {
+  if (p) CK(cudaFreeHost(p));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// loss / training (train_simt.cuh)
+// ------------------------------------------------------------------------------------
+extern "C" int cvb_loss_host(cvb_model* m, const float* x, const float* y, int64_t n, float* loss) {
+  if (!m || !loss) return fail("cvb_loss_host: NULL argument");
+  return fail("cvb_loss_host: not built yet");
+}
+extern "C" int cvb_train_step_host(cvb_model* m, const float* x, const float* y, int64_t n, float lr, float l2,
+                                   float drop4, uint64_t dropout_seed, int apply_update, float* loss5) {
+  if (!m) return fail("cvb_train_step_host: NULL model");
+  return fail("cvb_train_step_host: not built yet");
+}
+extern "C" int cvb_grad_buffer(cvb_model* m, void** dev_ptr, int64_t* numel) {
+  if (!m || !dev_ptr || !numel) return fail("cvb_grad_buffer: NULL argument");
+  *dev_ptr = m->d_grad;
+  *numel = m->nparams + 8;
+  return 0;
+}
+extern "C" int cvb_get_gradient(cvb_model* m, const char* name, float* host, int64_t n) {
+  if (!m || !name || !host) return fail("cvb_get_gradient: NULL argument");
+  const VarInfo* v = m->info(name);
+  if (!v) return fail("cvb_get_gradient: no variable named '%s'", name);
+  if (n != v->numel) return fail("cvb_get_gradient: size mismatch for '%s'", name);
+  CK(cudaSetDevice(m->device));
+  CK(cudaStreamSynchronize(m->s_comp));
+  CK(cudaMemcpy(host, m->d_grad + v->offset, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int cvb_apply_adam(cvb_model* m, float lr, float l2) {
+  if (!m) return fail("cvb_apply_adam: NULL model");
+  return fail("cvb_apply_adam: not built yet");
+}

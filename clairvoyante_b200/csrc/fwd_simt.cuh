@@ -1,0 +1,477 @@
+// fwd_simt.cuh -- fp32 SIMT forward kernels (CVB_COMPUTE_FP32).
+//
+// v3 pipeline (clairvoyante_v3.py:54-138), three device stages with L2/HBM-staged
+// intermediates (see DESIGN.md for why the whole net cannot sit in one CTA's smem at
+// fp32-equivalent precision):
+//   k_v3_front : x -> conv1+SELU -> pool1 -> conv2+SELU -> pool2            -> p2 [n][28][128]
+//   k_conv3    : p2 -> conv3+SELU -> pool3                                    -> p3 [n][4608]
+//   k_fc4      : p3 @ W4 + b4 -> SELU                                         -> h4 [n][336]
+//   k_tail     : h4 -> FC5+SELU -> 4 heads -> sigmoid / softmax               -> out16, logits16
+// p2 carries one zero row above and below the 26 pooled rows (conv3's SAME padding).
+#pragma once
+#include "conv_simt.cuh"
+
+namespace cvb {
+
+// ------------------------------------------------------------------------------------
+// k_v3_front
+// ------------------------------------------------------------------------------------
+template <int S>
+struct FrontV3 {
+  using C1 = ConvCfg<4, 16, 1, 33, S, 8, 8>;   // in: x tile  [S][33][20]
+  using C2 = ConvCfg<16, 32, 2, 29, S, 8, 8>;  // in: p1 tile [S][30][68] (row 29 = zeros)
+  static constexpr int THREADS = 256;
+  static_assert(C1::THREADS <= THREADS && C2::THREADS <= THREADS, "tile does not fit the CTA");
+  static constexpr int C1S_ROWS = 33, C1S_RS = 68;   // conv1 output (pre-pool)
+  static constexpr int C2S_ROWS = 29, C2S_RS = 132;  // conv2 output (pre-pool)
+  // smem map (floats).  xs and c1s alias the c2s region: both are dead before conv2 writes it.
+  static constexpr int W1 = 0;
+  static constexpr int B1 = W1 + C1::W_FLOATS;
+  static constexpr int W2 = B1 + 16;
+  static constexpr int B2 = W2 + C2::W_FLOATS;
+  static constexpr int P1S = B2 + 32;
+  static constexpr int C2S = P1S + C2::IN_FLOATS;
+  static constexpr int C2S_FLOATS = S * C2S_ROWS * C2S_RS;
+  static constexpr int C1S = C2S;                          // alias
+  static constexpr int C1S_FLOATS = S * C1S_ROWS * C1S_RS;
+  static constexpr int XS = C1S + C1S_FLOATS;              // alias (after c1s)
+  static_assert(C1S_FLOATS + C1::IN_FLOATS <= C2S_FLOATS, "alias region too small");
+  static constexpr int SMEM_FLOATS = C2S + C2S_FLOATS;
+  static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
+};
+
+template <int S>
+__global__ void __launch_bounds__(256, 2)
+k_v3_front(const float* __restrict__ x, int64_t n, const float* __restrict__ w1g, const float* __restrict__ b1g,
+           const float* __restrict__ w2g, const float* __restrict__ b2g, float* __restrict__ p2) {
+  using F = FrontV3<S>;
+  using C1 = typename F::C1;
+  using C2 = typename F::C2;
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  float* w1s = smem + F::W1;
+  float* b1s = smem + F::B1;
+  float* w2s = smem + F::W2;
+  float* b2s = smem + F::B2;
+  float* p1s = smem + F::P1S;
+  float* c2s = smem + F::C2S;
+  float* c1s = smem + F::C1S;
+  float* xs = smem + F::XS;
+
+  for (int i = tid; i < C1::W_FLOATS; i += 256) w1s[i] = w1g[i];
+  for (int i = tid; i < C2::W_FLOATS; i += 256) w2s[i] = w2g[i];
+  if (tid < 16) b1s[tid] = b1g[tid];
+  if (tid < 32) b2s[tid] = b2g[tid];
+  // zero row 29 of every site in p1s (conv2's bottom SAME pad); never overwritten
+  for (int i = tid; i < S * C2::RS; i += 256) {
+    int s = i / C2::RS, c = i - s * C2::RS;
+    p1s[(s * C2::ROWS + 29) * C2::RS + c] = 0.f;
+  }
+  const ConvThread<C1> th1(tid);
+  const ConvThread<C2> th2(tid);
+  const int64_t ntiles = (n + S - 1) / S;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t site0 = tile * S;
+    __syncthreads();  // previous tile's pool2 readers are done with c2s (xs/c1s alias it)
+    // ---- load x tile: S*33 rows of 4 float4 -> xs[site][33][20]
+    for (int i = tid; i < S * 33 * 4; i += 256) {
+      int s = i / 132, r = i - s * 132;
+      int h = r >> 2, q = r & 3;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (site0 + s < n) v = ldg_stream(reinterpret_cast<const float4*>(x + (site0 + s) * 528) + r);
+      *reinterpret_cast<float4*>(xs + (s * C1::ROWS + h) * C1::RS + q * 4) = v;
+    }
+    __syncthreads();
+    // ---- conv1 + SELU -> c1s
+    {
+      float acc[C1::TM][C1::TN];
+      conv_compute<C1>(xs, w1s, th1, acc);
+      conv_store_selu_smem<C1, F::C1S_ROWS, F::C1S_RS, 0>(acc, b1s, th1, c1s);
+    }
+    __syncthreads();
+    // ---- pool1 (5,1) -> p1s rows 0..28
+    for (int i = tid; i < S * 29 * 16; i += 256) {
+      int s = i / (29 * 16), r = i - s * (29 * 16);
+      int h = r >> 4, q = r & 15;
+      const float* src = c1s + (s * F::C1S_ROWS + h) * F::C1S_RS + q * 4;
+      float4 v = *reinterpret_cast<const float4*>(src);
+#pragma unroll
+      for (int j = 1; j < 5; ++j) v = max4(v, *reinterpret_cast<const float4*>(src + j * F::C1S_RS));
+      *reinterpret_cast<float4*>(p1s + (s * C2::ROWS + h) * C2::RS + q * 4) = v;
+    }
+    __syncthreads();
+    // ---- conv2 + SELU -> c2s
+    {
+      float acc[C2::TM][C2::TN];
+      conv_compute<C2>(p1s, w2s, th2, acc);
+      conv_store_selu_smem<C2, F::C2S_ROWS, F::C2S_RS, 0>(acc, b2s, th2, c2s);
+    }
+    __syncthreads();
+    // ---- pool2 (4,1) -> global p2[site][1+h][128]
+    for (int i = tid; i < S * 26 * 32; i += 256) {
+      int s = i / (26 * 32), r = i - s * (26 * 32);
+      int h = r >> 5, q = r & 31;
+      if (site0 + s >= n) continue;
+      const float* src = c2s + (s * F::C2S_ROWS + h) * F::C2S_RS + q * 4;
+      float4 v = *reinterpret_cast<const float4*>(src);
+#pragma unroll
+      for (int j = 1; j < 4; ++j) v = max4(v, *reinterpret_cast<const float4*>(src + j * F::C2S_RS));
+      *reinterpret_cast<float4*>(p2 + ((site0 + s) * 28 + 1 + h) * 128 + q * 4) = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// k_slim_front (clairvoyante_v3_slim.py:54-70): x -> conv1(1x4,8)+SELU -> conv2(3x4,16)+SELU
+//   -> p2 [n][37][64] (two zero rows above and below the 33 rows: conv3 is 5x4 SAME)
+// ------------------------------------------------------------------------------------
+template <int S>
+struct FrontSlim {
+  using C1 = ConvCfg<4, 8, 1, 33, S, 8, 8>;   // in: x tile  [S][33][20]
+  using C2 = ConvCfg<8, 16, 3, 33, S, 8, 8>;  // in: c1 tile [S][35][36] (rows 0 and 34 zero)
+  static constexpr int THREADS = 256;
+  static_assert(C1::THREADS <= THREADS && C2::THREADS <= THREADS, "tile does not fit the CTA");
+  static constexpr int W1 = 0;
+  static constexpr int B1 = W1 + C1::W_FLOATS;
+  static constexpr int W2 = B1 + 8;
+  static constexpr int B2 = W2 + C2::W_FLOATS;
+  static constexpr int XS = B2 + 16;
+  static constexpr int C1S = XS + C1::IN_FLOATS;
+  static constexpr int SMEM_FLOATS = C1S + C2::IN_FLOATS;
+  static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
+};
+
+template <int S>
+__global__ void __launch_bounds__(256, 2)
+k_slim_front(const float* __restrict__ x, int64_t n, const float* __restrict__ w1g, const float* __restrict__ b1g,
+             const float* __restrict__ w2g, const float* __restrict__ b2g, float* __restrict__ p2) {
+  using F = FrontSlim<S>;
+  using C1 = typename F::C1;
+  using C2 = typename F::C2;
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  float* w1s = smem + F::W1;
+  float* b1s = smem + F::B1;
+  float* w2s = smem + F::W2;
+  float* b2s = smem + F::B2;
+  float* xs = smem + F::XS;
+  float* c1s = smem + F::C1S;
+  for (int i = tid; i < C1::W_FLOATS; i += 256) w1s[i] = w1g[i];
+  for (int i = tid; i < C2::W_FLOATS; i += 256) w2s[i] = w2g[i];
+  if (tid < 8) b1s[tid] = b1g[tid];
+  if (tid < 16) b2s[tid] = b2g[tid];
+  for (int i = tid; i < S * 2 * C2::RS; i += 256) {  // zero pad rows 0 and 34
+    int s = i / (2 * C2::RS), r = i - s * (2 * C2::RS);
+    int row = r < C2::RS ? 0 : 34, c = r < C2::RS ? r : r - C2::RS;
+    c1s[(s * C2::ROWS + row) * C2::RS + c] = 0.f;
+  }
+  const ConvThread<C1> th1(tid);
+  const ConvThread<C2> th2(tid);
+  const int64_t ntiles = (n + S - 1) / S;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t site0 = tile * S;
+    __syncthreads();
+    for (int i = tid; i < S * 33 * 4; i += 256) {
+      int s = i / 132, r = i - s * 132;
+      int h = r >> 2, q = r & 3;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (site0 + s < n) v = ldg_stream(reinterpret_cast<const float4*>(x + (site0 + s) * 528) + r);
+      *reinterpret_cast<float4*>(xs + (s * C1::ROWS + h) * C1::RS + q * 4) = v;
+    }
+    __syncthreads();
+    {
+      float acc[C1::TM][C1::TN];
+      conv_compute<C1>(xs, w1s, th1, acc);
+      conv_store_selu_smem<C1, C2::ROWS, C2::RS, 1>(acc, b1s, th1, c1s);
+    }
+    __syncthreads();
+    {
+      float acc[C2::TM][C2::TN];
+      conv_compute<C2>(c1s, w2s, th2, acc);
+      int nsites = (int)((n - site0) < S ? (n - site0) : S);
+      conv_store_selu_global<C2, 37, 64, 2>(acc, b2s, th2, p2 + site0 * (37 * 64), nsites);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// k_conv3: generic "one conv layer from a padded global tile" kernel.
+//   in  : [n][ROWS][4*CIN]  (zero pad rows included)      out : [n][HOUT-POOL+1][4*COUT]
+// Input tiles are double-buffered with cp.async; the SELU output is written back over
+// the (dead) input tile and max-pooled from there on its way to global memory.
+// ------------------------------------------------------------------------------------
+template <class C, int POOL>
+struct ConvLayerSmem {
+  static constexpr int ORS = 4 * C::COUT + 4;  // stride of the pre-pool output rows in smem
+  static constexpr int OUT_FLOATS = C::S * C::HOUT * ORS;
+  static constexpr int BUF = (C::IN_FLOATS > OUT_FLOATS ? C::IN_FLOATS : OUT_FLOATS);
+  static constexpr int WS = 0;
+  static constexpr int BS = WS + C::W_FLOATS;
+  static constexpr int BUF0 = BS + ((C::COUT + 3) / 4) * 4;
+  static constexpr int SMEM_FLOATS = BUF0 + 2 * BUF;
+  static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
+  static constexpr int HP = C::HOUT - POOL + 1;
+};
+
+template <class C>
+__device__ __forceinline__ void conv_tile_load_async(float* __restrict__ buf, const float* __restrict__ in,
+                                                     int64_t site0, int64_t n, int tid, int nthreads) {
+  constexpr int ROWF4 = C::CIN;  // float4 per row = 4*CIN/4
+  for (int i = tid; i < C::S * C::ROWS * ROWF4; i += nthreads) {
+    int s = i / (C::ROWS * ROWF4), r = i - s * (C::ROWS * ROWF4);
+    int row = r / ROWF4, q = r - row * ROWF4;
+    bool ok = site0 + s < n;
+    const float* src = in + ((ok ? site0 + s : 0) * C::ROWS + row) * (4 * C::CIN) + q * 4;
+    cp_async16_zfill(buf + (s * C::ROWS + row) * C::RS + q * 4, src, ok);
+  }
+}
+
+template <class C, int POOL, int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_conv_layer(const float* __restrict__ in, int64_t n, const float* __restrict__ wg, const float* __restrict__ bg,
+             float* __restrict__ out) {
+  using L = ConvLayerSmem<C, POOL>;
+  static_assert(C::THREADS <= NTHREADS, "tile does not fit the CTA");
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  float* ws = smem + L::WS;
+  float* bs = smem + L::BS;
+  float* bufs[2] = {smem + L::BUF0, smem + L::BUF0 + L::BUF};
+  const int64_t ntiles = (n + C::S - 1) / C::S;
+  for (int i = tid; i < C::W_FLOATS / 4; i += NTHREADS) cp_async16(ws + i * 4, wg + i * 4);
+  if (tid < C::COUT) bs[tid] = bg[tid];
+  int64_t tile = blockIdx.x;
+  if (tile < ntiles) conv_tile_load_async<C>(bufs[0], in, tile * C::S, n, tid, NTHREADS);
+  cp_async_commit();
+  const ConvThread<C> th(tid);
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    float* cur = bufs[it & 1];
+    const int64_t next = tile + gridDim.x;
+    if (next < ntiles) conv_tile_load_async<C>(bufs[(it & 1) ^ 1], in, next * C::S, n, tid, NTHREADS);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    float acc[C::TM][C::TN];
+    conv_compute<C>(cur, ws, th, acc);
+    __syncthreads();  // every thread is done reading the input tile
+    conv_store_selu_smem<C, C::HOUT, L::ORS, 0>(acc, bs, th, cur);
+    __syncthreads();
+    const int64_t site0 = tile * C::S;
+    constexpr int OF4 = C::COUT;  // float4 per output row
+    for (int i = tid; i < C::S * L::HP * OF4; i += NTHREADS) {
+      int s = i / (L::HP * OF4), r = i - s * (L::HP * OF4);
+      int h = r / OF4, q = r - h * OF4;
+      if (site0 + s >= n) continue;
+      const float* src = cur + (s * C::HOUT + h) * L::ORS + q * 4;
+      float4 v = *reinterpret_cast<const float4*>(src);
+#pragma unroll
+      for (int j = 1; j < POOL; ++j) v = max4(v, *reinterpret_cast<const float4*>(src + j * L::ORS));
+      *reinterpret_cast<float4*>(out + ((site0 + s) * L::HP + h) * (4 * C::COUT) + q * 4) = v;
+    }
+    __syncthreads();  // pooled reads done before the next-next tile load lands in `cur`
+  }
+  cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------
+// k_fc4: h4 = SELU(A @ W + b),  A [n][K] row-major, W [K][N] row-major (TF dense kernel).
+// CTA tile = (RT*TMS) sites x N columns, thread tile TMS sites x CPT columns, 3-stage
+// cp.async pipeline over K in chunks of KC.
+// ------------------------------------------------------------------------------------
+template <int N_, int CT_, int CPT_, int RT_, int TMS_>
+struct FcCfg {
+  static constexpr int N = N_, CT = CT_, CPT = CPT_, RT = RT_, TMS = TMS_;
+  static constexpr int KC = 16, STAGES = 3;
+  static constexpr int M = RT * TMS;
+  static constexpr int LDA = KC + 4;
+  static constexpr int A_FLOATS = M * LDA;
+  static constexpr int B_FLOATS = KC * N;
+  static constexpr int STAGE_FLOATS = A_FLOATS + B_FLOATS;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_FLOATS * 4;
+  static constexpr int THREADS = 256;
+  static_assert(CT * CPT == N && CPT % 4 == 0 && CT * RT <= THREADS, "fc tile shape");
+};
+
+template <class F>
+__device__ __forceinline__ void fc_chunk_load(float* __restrict__ st, const float* __restrict__ A,
+                                              const float* __restrict__ W, int64_t site0, int64_t n, int K, int k0,
+                                              int tid) {
+  float* as = st;
+  float* bs = st + F::A_FLOATS;
+  for (int i = tid; i < F::M * (F::KC / 4); i += F::THREADS) {
+    int s = i / (F::KC / 4), q = i - s * (F::KC / 4);
+    bool ok = site0 + s < n;
+    cp_async16_zfill(as + s * F::LDA + q * 4, A + (ok ? site0 + s : 0) * (int64_t)K + k0 + q * 4, ok);
+  }
+  for (int i = tid; i < F::KC * F::N / 4; i += F::THREADS) cp_async16(bs + i * 4, W + (int64_t)k0 * F::N + i * 4);
+}
+
+template <class F>
+__global__ void __launch_bounds__(256, 1)
+k_fc4(const float* __restrict__ A, int64_t n, int K, const float* __restrict__ W, const float* __restrict__ bias,
+      float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  const int ct = tid % F::CT, rt = tid / F::CT;
+  const bool active = rt < F::RT;
+  const int64_t site0 = (int64_t)blockIdx.x * F::M;
+  const int nchunks = K / F::KC;
+  float acc[F::TMS][F::CPT];
+#pragma unroll
+  for (int i = 0; i < F::TMS; ++i)
+#pragma unroll
+    for (int j = 0; j < F::CPT; ++j) acc[i][j] = 0.f;
+#pragma unroll
+  for (int s = 0; s < F::STAGES - 1; ++s) {
+    if (s < nchunks) fc_chunk_load<F>(smem + s * F::STAGE_FLOATS, A, W, site0, n, K, s * F::KC, tid);
+    cp_async_commit();
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait<F::STAGES - 2>();
+    __syncthreads();  // chunk c landed; everyone finished chunk c-1 (its stage is refilled below)
+    {
+      int cn = c + F::STAGES - 1;
+      if (cn < nchunks) fc_chunk_load<F>(smem + (cn % F::STAGES) * F::STAGE_FLOATS, A, W, site0, n, K, cn * F::KC, tid);
+      cp_async_commit();
+    }
+    if (active) {
+      const float* as = smem + (c % F::STAGES) * F::STAGE_FLOATS;
+      const float* bs = as + F::A_FLOATS;
+#pragma unroll
+      for (int k4 = 0; k4 < F::KC / 4; ++k4) {
+        float4 a[F::TMS];
+#pragma unroll
+        for (int i = 0; i < F::TMS; ++i) a[i] = *reinterpret_cast<const float4*>(as + (rt + F::RT * i) * F::LDA + k4 * 4);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          float4 b[F::CPT / 4];
+#pragma unroll
+          for (int j = 0; j < F::CPT / 4; ++j)
+            b[j] = *reinterpret_cast<const float4*>(bs + (k4 * 4 + kk) * F::N + (ct + F::CT * j) * 4);
+#pragma unroll
+          for (int i = 0; i < F::TMS; ++i) {
+            const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+#pragma unroll
+            for (int j = 0; j < F::CPT / 4; ++j) {
+              acc[i][j * 4 + 0] = fmaf(av, b[j].x, acc[i][j * 4 + 0]);
+              acc[i][j * 4 + 1] = fmaf(av, b[j].y, acc[i][j * 4 + 1]);
+              acc[i][j * 4 + 2] = fmaf(av, b[j].z, acc[i][j * 4 + 2]);
+              acc[i][j * 4 + 3] = fmaf(av, b[j].w, acc[i][j * 4 + 3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  if (!active) return;
+#pragma unroll
+  for (int j = 0; j < F::CPT / 4; ++j) {
+    const int col = (ct + F::CT * j) * 4;
+    const float4 bv = *reinterpret_cast<const float4*>(bias + col);
+#pragma unroll
+    for (int i = 0; i < F::TMS; ++i) {
+      const int64_t site = site0 + rt + F::RT * i;
+      if (site >= n) continue;
+      float4 v;
+      v.x = selu_f(acc[i][j * 4 + 0] + bv.x);
+      v.y = selu_f(acc[i][j * 4 + 1] + bv.y);
+      v.z = selu_f(acc[i][j * 4 + 2] + bv.z);
+      v.w = selu_f(acc[i][j * 4 + 3] + bv.w);
+      *reinterpret_cast<float4*>(out + site * F::N + col) = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// k_tail: FC5 + SELU, the four heads, sigmoid / softmax (clairvoyante_v3.py:114-137).
+// One CTA = TS sites.  h4 tile in smem; W5 streamed from L2 (each element read once per CTA).
+// ------------------------------------------------------------------------------------
+struct HeadPtrs {
+  const float *w5, *b5, *wb, *bb, *wz, *bz, *wt, *bt, *wl, *bl;
+};
+
+template <int N4, int N5, int TS>
+__global__ void __launch_bounds__(256, 2)
+k_tail(const float* __restrict__ h4, int64_t n, HeadPtrs hp, float* __restrict__ out16, float* __restrict__ logits16) {
+  constexpr int L4 = N4 + 4, L5 = N5 + 4;
+  __shared__ __align__(16) float h4s[TS * L4];
+  __shared__ __align__(16) float h5s[TS * L5];
+  __shared__ float lg[TS * 16];
+  const int tid = threadIdx.x;
+  const int64_t site0 = (int64_t)blockIdx.x * TS;
+  for (int i = tid; i < TS * (N4 / 4); i += 256) {
+    int s = i / (N4 / 4), q = i - s * (N4 / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (site0 + s < n) v = *reinterpret_cast<const float4*>(h4 + (site0 + s) * N4 + q * 4);
+    *reinterpret_cast<float4*>(h4s + s * L4 + q * 4) = v;
+  }
+  __syncthreads();
+  // FC5: thread j owns output column j for all TS sites
+  for (int j = tid; j < N5; j += 256) {
+    float acc[TS];
+#pragma unroll
+    for (int s = 0; s < TS; ++s) acc[s] = 0.f;
+    for (int k = 0; k < N4; k += 4) {
+      const float w0 = hp.w5[(k + 0) * N5 + j], w1 = hp.w5[(k + 1) * N5 + j];
+      const float w2 = hp.w5[(k + 2) * N5 + j], w3 = hp.w5[(k + 3) * N5 + j];
+#pragma unroll
+      for (int s = 0; s < TS; ++s) {
+        const float4 a = *reinterpret_cast<const float4*>(h4s + s * L4 + k);
+        acc[s] = fmaf(a.x, w0, acc[s]);
+        acc[s] = fmaf(a.y, w1, acc[s]);
+        acc[s] = fmaf(a.z, w2, acc[s]);
+        acc[s] = fmaf(a.w, w3, acc[s]);
+      }
+    }
+    const float b = hp.b5[j];
+#pragma unroll
+    for (int s = 0; s < TS; ++s) h5s[s * L5 + j] = selu_f(acc[s] + b);
+  }
+  __syncthreads();
+  // heads: 16 dot products per site
+  for (int i = tid; i < TS * 16; i += 256) {
+    const int s = i >> 4, o = i & 15;
+    float acc = 0.f;
+    if (o < 4) {  // base change: input is the FC4 branch (clairvoyante_v3.py:125)
+      for (int k = 0; k < N4; ++k) acc = fmaf(h4s[s * L4 + k], hp.wb[k * 4 + o], acc);
+      acc += hp.bb[o];
+    } else {
+      const float* w;
+      int ld, col;
+      float b;
+      if (o < 6) { w = hp.wz; ld = 2; col = o - 4; b = hp.bz[col]; }
+      else if (o < 10) { w = hp.wt; ld = 4; col = o - 6; b = hp.bt[col]; }
+      else { w = hp.wl; ld = 6; col = o - 10; b = hp.bl[col]; }
+      for (int k = 0; k < N5; ++k) acc = fmaf(h5s[s * L5 + k], w[k * ld + col], acc);
+      acc = selu_f(acc + b) + 1e-10f;  // clairvoyante_v3.py:127-128
+    }
+    lg[i] = acc;
+  }
+  __syncthreads();
+  if (tid < TS && site0 + tid < n) {
+    const float* l = lg + tid * 16;
+    float o[16];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = 1.f / (1.f + __expf(-l[k]));
+    auto sm = [&](int a, int b) {
+      float m = l[a];
+      for (int k = a + 1; k < b; ++k) m = fmaxf(m, l[k]);
+      float sum = 0.f;
+      for (int k = a; k < b; ++k) { o[k] = __expf(l[k] - m); sum += o[k]; }
+      const float inv = 1.f / sum;
+      for (int k = a; k < b; ++k) o[k] *= inv;
+    };
+    sm(4, 6); sm(6, 10); sm(10, 16);
+    float4* d = reinterpret_cast<float4*>(out16 + (site0 + tid) * 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+    if (logits16) {
+      float4* dl = reinterpret_cast<float4*>(logits16 + (site0 + tid) * 16);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dl[k] = make_float4(l[4 * k], l[4 * k + 1], l[4 * k + 2], l[4 * k + 3]);
+    }
+  }
+}
+
+}  // namespace cvb

@@ -1,0 +1,319 @@
+"""`Clairvoyante` model object: the reference's seam (clairvoyante/clairvoyante_v3.py:5-283,
+clairvoyante_v3_slim.py:5-260) re-implemented on libcvb200.so.
+
+Same constructor kwargs, public attributes and method names as the reference class, so
+callVar.py / train.py / evaluate.py drive it unchanged.  Every method that was a
+`session.run(...)` is one C-ABI call (include/cvb200.h); NumPy arrays go in and fresh
+NumPy arrays come out (the reference returns new arrays per call and the drivers rely on
+that: callVar.py:199-205).  ctypes releases the GIL during the call, so the drivers'
+`Thread(target=m.predictNoRT)` overlap keeps working.
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+
+from . import _lib, initializers, param
+
+_VARIANT_ID = {"v3": 0, "v3_slim": 1}
+COMPUTE_MODES = {"fp32": 0, "fp16x3": 1, "fp16": 2}
+
+
+def _default_device():
+    for k in ("CVB_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(k):
+            return int(os.environ[k])
+    return 0
+
+
+def _f32c(a, shape_tail):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    n = a.shape[0] if a.ndim > 0 else 0
+    if a.size != n * int(np.prod(shape_tail)):
+        raise ValueError("expected shape (N,%s), got %s" % (",".join(map(str, shape_tail)), a.shape))
+    return a, n
+
+
+class SummaryWriter(object):
+    """Stand-in for tf.summary.FileWriter (clairvoyante_v3.py:253-255): one JSON line per
+    add_summary(summary, step) in <logsPath>/summaries.jsonl."""
+
+    def __init__(self, logsPath):
+        os.makedirs(logsPath, exist_ok=True)
+        self._fh = open(os.path.join(logsPath, "summaries.jsonl"), "a")
+
+    def add_summary(self, summary, step):
+        rec = dict(summary or {})
+        rec["step"] = int(step)
+        self._fh.write(json.dumps(rec) + "\n")
+        self._fh.flush()
+
+    def close(self):
+        self._fh.close()
+
+
+class ClairvoyanteBase(object):
+    VARIANT = "v3"
+
+    def _common_init(self, initialLearningRate, learningRateDecay, dropoutRateFC4, dropoutRateFC5,
+                     l2RegularizationLambda, l2RegularizationLambdaDecay, device):
+        self.learningRateVal = initialLearningRate
+        self.learningRateDecay = learningRateDecay
+        self.dropoutRateFC4Val = dropoutRateFC4
+        self.dropoutRateFC5Val = dropoutRateFC5
+        self.l2RegularizationLambdaVal = l2RegularizationLambda
+        self.l2RegularizationLambdaDecay = l2RegularizationLambdaDecay
+        self.trainLossRTVal = None; self.trainSummaryRTVal = None; self.getLossLossRTVal = None
+        self.predictBaseRTVal = None; self.predictZygosityRTVal = None
+        self.predictVarTypeRTVal = None; self.predictIndelLengthRTVal = None
+        if dropoutRateFC5 != 0.0:
+            raise NotImplementedError("dropoutRateFC5 != 0 is not supported (reference default param.py:22 is 0.0)")
+        self._lib = _lib.load()
+        self.device = _default_device() if device is None else int(device)
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.cvb_create(_VARIANT_ID[self.VARIANT], self.device, ctypes.byref(h)))
+        self._h = h
+        self._dropout_calls = 0
+        self._seed = int.from_bytes(os.urandom(8), "little")   # reference dropout is unseeded (selu.py:55)
+
+    # ---- lifecycle -------------------------------------------------------------------
+    def init(self, seed=None):
+        """init_op (clairvoyante_v3.py:177-178): reference initialisers, zero Adam slots, step 0."""
+        if seed is None:
+            seed = int.from_bytes(os.urandom(4), "little")
+        self.setWeights(initializers.init_weights(self.VARIANT, seed))
+        for name, shape in initializers.variable_shapes(self.VARIANT):
+            z = np.zeros(shape, np.float32)
+            self._set(name, 1, z)
+            self._set(name, 2, z)
+        _lib.check(self._lib.cvb_set_step(self._h, 0))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.cvb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parameters ------------------------------------------------------------------
+    def _set(self, name, slot, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float32)
+        _lib.check(self._lib.cvb_set_variable(self._h, name.encode(), slot, a.ctypes.data, a.size))
+
+    def _get(self, name, slot, shape):
+        a = np.empty(shape, np.float32)
+        _lib.check(self._lib.cvb_get_variable(self._h, name.encode(), slot, a.ctypes.data, a.size))
+        return a
+
+    def setWeights(self, weights):
+        for name, shape in initializers.variable_shapes(self.VARIANT):
+            w = np.asarray(weights[name], np.float32)
+            if w.shape != tuple(shape):
+                raise ValueError("variable %s: expected shape %s, got %s" % (name, shape, w.shape))
+            self._set(name, 0, w)
+
+    def getWeights(self):
+        return {name: self._get(name, 0, shape) for name, shape in initializers.variable_shapes(self.VARIANT)}
+
+    def getGradients(self):
+        out = {}
+        for name, shape in initializers.variable_shapes(self.VARIANT):
+            a = np.empty(shape, np.float32)
+            _lib.check(self._lib.cvb_get_gradient(self._h, name.encode(), a.ctypes.data, a.size))
+            out[name] = a
+        return out
+
+    def setComputeMode(self, mode):
+        _lib.check(self._lib.cvb_set_compute_mode(self._h, COMPUTE_MODES[mode]))
+
+    @staticmethod
+    def _ckpt_path(fn):
+        return fn + ".cvb.npz"
+
+    def saveParameters(self, fn):
+        """tf.train.Saver().save (clairvoyante_v3.py:243-246).  Native container: one .npz
+        holding every variable under its TF name plus the Adam slots `<name>/Adam`,
+        `<name>/Adam_1` and `step` (TF stores beta1_power/beta2_power = beta**step)."""
+        d = {}
+        for name, shape in initializers.variable_shapes(self.VARIANT):
+            d[name] = self._get(name, 0, shape)
+            d[name + "/Adam"] = self._get(name, 1, shape)
+            d[name + "/Adam_1"] = self._get(name, 2, shape)
+        t = ctypes.c_int64()
+        _lib.check(self._lib.cvb_get_step(self._h, ctypes.byref(t)))
+        d["step"] = np.int64(t.value)
+        os.makedirs(os.path.dirname(os.path.abspath(fn)), exist_ok=True)
+        np.savez(self._ckpt_path(fn), **d)
+
+    def restoreParameters(self, fn):
+        """tf.train.Saver().restore (clairvoyante_v3.py:248-251)."""
+        path = None
+        for cand in (self._ckpt_path(fn), fn, fn + ".npz"):
+            if os.path.isfile(cand):
+                path = cand
+                break
+        if path is None:
+            raise IOError("checkpoint not found: %s(.cvb.npz)" % fn)
+        with np.load(path) as d:
+            for name, shape in initializers.variable_shapes(self.VARIANT):
+                self._set(name, 0, d[name].reshape(shape))
+                if name + "/Adam" in d:
+                    self._set(name, 1, d[name + "/Adam"].reshape(shape))
+                    self._set(name, 2, d[name + "/Adam_1"].reshape(shape))
+            _lib.check(self._lib.cvb_set_step(self._h, int(d["step"]) if "step" in d else 0))
+
+    def summaryFileWriter(self, logsPath):
+        return SummaryWriter(logsPath)
+
+    # ---- hyper-parameters (clairvoyante_v3.py:229-241) -------------------------------------
+    def setLearningRate(self, learningRate=None):
+        if learningRate == None:
+            self.learningRateVal = self.learningRateVal * self.learningRateDecay
+        else:
+            self.learningRateVal = learningRate
+        return self.learningRateVal
+
+    def setL2RegularizationLambda(self, l2RegularizationLambda=None):
+        if l2RegularizationLambda == None:
+            self.l2RegularizationLambdaVal = self.l2RegularizationLambdaVal * self.l2RegularizationLambdaDecay
+        else:
+            self.l2RegularizationLambdaVal = l2RegularizationLambda
+        return self.l2RegularizationLambdaVal
+
+    # ---- inference (clairvoyante_v3.py:257-280) --------------------------------------------
+    def _predict16(self, XArray, want_logits=False):
+        x, n = _f32c(XArray, self.inputShape)
+        out = np.empty((n, 16), np.float32)
+        lg = np.empty((n, 16), np.float32) if want_logits else None
+        _lib.check(self._lib.cvb_predict_host(self._h, x.ctypes.data, n, out.ctypes.data,
+                                              lg.ctypes.data if want_logits else None))
+        return out, lg
+
+    def predict(self, XArray):
+        o, _ = self._predict16(XArray)
+        return o[:, 0:4].copy(), o[:, 4:6].copy(), o[:, 6:10].copy(), o[:, 10:16].copy()
+
+    def predictNoRT(self, XArray):
+        self.predictBaseRTVal = None; self.predictZygosityRTVal = None
+        self.predictVarTypeRTVal = None; self.predictIndelLengthRTVal = None
+        self.predictBaseRTVal, self.predictZygosityRTVal, self.predictVarTypeRTVal, self.predictIndelLengthRTVal \
+            = self.predict(XArray)
+
+    def predictLogits(self, XArray):
+        """(out16, logits16): extension used by the parity tests (base head pre-sigmoid)."""
+        return self._predict16(XArray, want_logits=True)
+
+    def predictDevice(self, x_ptr, n, out16_ptr, logits16_ptr=None, stream=None):
+        """Device-resident batch (pointers from e.g. torch.Tensor.data_ptr()); asynchronous."""
+        _lib.check(self._lib.cvb_predict_device(self._h, x_ptr, n, out16_ptr, logits16_ptr, stream))
+
+    def debugRead(self, which, n_sites):
+        """Intermediate of the last device pass: 'p2' | 'p3' | 'h4' (test aid)."""
+        per = {"v3": dict(p2=28 * 128, p3=4608, h4=336), "v3_slim": dict(p2=37 * 64, p3=4224, h4=36)}[self.VARIANT][which]
+        a = np.empty((n_sites, per), np.float32)
+        _lib.check(self._lib.cvb_debug_read(self._h, dict(p2=0, p3=1, h4=2)[which], a.ctypes.data, a.size))
+        return a
+
+    def kernelLaunches(self):
+        return int(self._lib.cvb_kernel_launches(self._h))
+
+    # ---- loss / training (clairvoyante_v3.py:183-227) --------------------------------------
+    def getLoss(self, batchX, batchY):
+        x, n = _f32c(batchX, self.inputShape)
+        y, ny = _f32c(batchY, (16,))
+        if n != ny:
+            raise ValueError("X/Y batch mismatch %d/%d" % (n, ny))
+        loss = ctypes.c_float()
+        _lib.check(self._lib.cvb_loss_host(self._h, x.ctypes.data, y.ctypes.data, n, ctypes.byref(loss)))
+        return np.float32(loss.value)
+
+    def getLossNoRT(self, batchX, batchY):
+        self.getLossLossRTVal = None
+        self.getLossLossRTVal = self.getLoss(batchX, batchY)
+
+    def _train_step(self, batchX, batchY, apply_update=1, seed=None):
+        x, n = _f32c(batchX, self.inputShape)
+        y, ny = _f32c(batchY, (16,))
+        if n != ny:
+            raise ValueError("X/Y batch mismatch %d/%d" % (n, ny))
+        if seed is None:
+            self._dropout_calls += 1
+            seed = (self._seed + self._dropout_calls * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        l5 = (ctypes.c_float * 8)()
+        _lib.check(self._lib.cvb_train_step_host(self._h, x.ctypes.data, y.ctypes.data, n,
+                                                 self.learningRateVal, self.l2RegularizationLambdaVal,
+                                                 self.dropoutRateFC4Val, seed, apply_update, l5))
+        summary = dict(learning_rate=float(self.learningRateVal), l2Lambda=float(self.l2RegularizationLambdaVal),
+                       loss=float(l5[0]), loss1=float(l5[1]), loss2=float(l5[2]), loss3=float(l5[3]),
+                       loss4=float(l5[4]), lossL2=float(l5[5]))
+        return np.float32(l5[0]), summary
+
+    def train(self, batchX, batchY):
+        return self._train_step(batchX, batchY)
+
+    def trainNoRT(self, batchX, batchY):
+        self.trainLossRTVal = None; self.trainSummaryRTVal = None
+        self.trainLossRTVal, self.trainSummaryRTVal = self._train_step(batchX, batchY)
+
+
+class ClairvoyanteV3(ClairvoyanteBase):
+    VARIANT = "v3"
+
+    def __init__(self, inputShape=(2 * param.flankingBaseNum + 1, 4, param.matrixNum),
+                 outputShape1=(4,), outputShape2=(2,), outputShape3=(4,), outputShape4=(6,),
+                 kernelSize1=(1, 4), kernelSize2=(2, 4), kernelSize3=(3, 4),
+                 pollSize1=(5, 1), pollSize2=(4, 1), pollSize3=(3, 1),
+                 numFeature1=16, numFeature2=32, numFeature3=48,
+                 hiddenLayerUnits4=336, hiddenLayerUnits5=168,
+                 initialLearningRate=param.initialLearningRate, learningRateDecay=param.learningRateDecay,
+                 dropoutRateFC4=param.dropoutRateFC4, dropoutRateFC5=param.dropoutRateFC5,
+                 l2RegularizationLambda=param.l2RegularizationLambda,
+                 l2RegularizationLambdaDecay=param.l2RegularizationLambdaDecay, device=None):
+        geom = (tuple(inputShape), tuple(outputShape1), tuple(outputShape2), tuple(outputShape3), tuple(outputShape4),
+                tuple(kernelSize1), tuple(kernelSize2), tuple(kernelSize3), tuple(pollSize1), tuple(pollSize2),
+                tuple(pollSize3), numFeature1, numFeature2, numFeature3, hiddenLayerUnits4, hiddenLayerUnits5)
+        if geom != ((33, 4, 4), (4,), (2,), (4,), (6,), (1, 4), (2, 4), (3, 4), (5, 1), (4, 1), (3, 1), 16, 32, 48, 336, 168):
+            raise NotImplementedError("libcvb200 kernels are compiled for the reference v3 geometry "
+                                      "(clairvoyante_v3.py:7-12); got %r" % (geom,))
+        self.inputShape = inputShape
+        self.outputShape1 = outputShape1; self.outputShape2 = outputShape2
+        self.outputShape3 = outputShape3; self.outputShape4 = outputShape4
+        self.kernelSize1 = kernelSize1; self.kernelSize2 = kernelSize2; self.kernelSize3 = kernelSize3
+        self.pollSize1 = pollSize1; self.pollSize2 = pollSize2; self.pollSize3 = pollSize3
+        self.numFeature1 = numFeature1; self.numFeature2 = numFeature2; self.numFeature3 = numFeature3
+        self.hiddenLayerUnits4 = hiddenLayerUnits4; self.hiddenLayerUnits5 = hiddenLayerUnits5
+        self._common_init(initialLearningRate, learningRateDecay, dropoutRateFC4, dropoutRateFC5,
+                          l2RegularizationLambda, l2RegularizationLambdaDecay, device)
+
+
+class ClairvoyanteV3Slim(ClairvoyanteBase):
+    VARIANT = "v3_slim"
+
+    def __init__(self, inputShape=(2 * param.flankingBaseNum + 1, 4, param.matrixNum),
+                 outputShape1=(4,), outputShape2=(2,), outputShape3=(4,), outputShape4=(6,),
+                 kernelSize1=(1, 4), kernelSize2=(3, 4), kernelSize3=(5, 4),
+                 numFeature1=8, numFeature2=16, numFeature3=32,
+                 hiddenLayerUnits4=36, hiddenLayerUnits5=18,
+                 initialLearningRate=param.initialLearningRate, learningRateDecay=param.learningRateDecay,
+                 dropoutRateFC4=param.dropoutRateFC4, dropoutRateFC5=param.dropoutRateFC5,
+                 l2RegularizationLambda=param.l2RegularizationLambda,
+                 l2RegularizationLambdaDecay=param.l2RegularizationLambdaDecay, device=None):
+        geom = (tuple(inputShape), tuple(outputShape1), tuple(outputShape2), tuple(outputShape3), tuple(outputShape4),
+                tuple(kernelSize1), tuple(kernelSize2), tuple(kernelSize3), numFeature1, numFeature2, numFeature3,
+                hiddenLayerUnits4, hiddenLayerUnits5)
+        if geom != ((33, 4, 4), (4,), (2,), (4,), (6,), (1, 4), (3, 4), (5, 4), 8, 16, 32, 36, 18):
+            raise NotImplementedError("libcvb200 kernels are compiled for the reference v3_slim geometry "
+                                      "(clairvoyante_v3_slim.py:7-11); got %r" % (geom,))
+        self.inputShape = inputShape
+        self.outputShape1 = outputShape1; self.outputShape2 = outputShape2
+        self.outputShape3 = outputShape3; self.outputShape4 = outputShape4
+        self.kernelSize1 = kernelSize1; self.kernelSize2 = kernelSize2; self.kernelSize3 = kernelSize3
+        self.numFeature1 = numFeature1; self.numFeature2 = numFeature2; self.numFeature3 = numFeature3
+        self.hiddenLayerUnits4 = hiddenLayerUnits4; self.hiddenLayerUnits5 = hiddenLayerUnits5
+        self._common_init(initialLearningRate, learningRateDecay, dropoutRateFC4, dropoutRateFC5,
+                          l2RegularizationLambda, l2RegularizationLambdaDecay, device)

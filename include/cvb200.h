@@ -1,0 +1,115 @@
+/* cvb200.h -- C ABI of libcvb200.so: the B200-native Clairvoyante v3 / v3_slim
+ * network (forward, loss, train step) for (33,4,4) pileup tensors.
+ *
+ * The reference has no FFI: its seam is the duck-typed Python object
+ * `Clairvoyante` (clairvoyante/clairvoyante_v3.py:5-283,
+ * clairvoyante_v3_slim.py:5-260) whose methods call TensorFlow's
+ * `session.run`.  Every entry point below replaces one of those
+ * `session.run` call sites; clairvoyante_b200/clairvoyante_v3.py binds them
+ * with ctypes.  Plain pointers and sizes only -- no
+ * torch / CUDA types in any signature (streams are passed as void*).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message
+ *     is available from cvb_last_error() (thread-local).
+ *   - x is float32 NHWC (n,33,4,4): element (i,h,w,c) at i*528+h*16+w*4+c
+ *     (dataPrepScripts/CreateTensor.py:20-21,37-40; utils_v2.py:45), already
+ *     channel-subtracted (utils_v2.py:46).
+ *   - out16 is float32 (n,16): [base 4 | zygosity 2 | varType 4 | indelLength 6]
+ *     = sigmoid / softmax outputs in the label order of callVar.py:54-57.
+ *   - logits16 (optional, may be NULL) is the same layout before the final
+ *     sigmoid / softmax: base pre-sigmoid, the others SELU(FC)+1e-10
+ *     (clairvoyante_v3.py:124-137).
+ *   - n == 0 is legal and a no-op (utils_v2.py:56-59 can yield empty batches).
+ *   - a handle is bound to one CUDA device; calls may come from any host
+ *     thread but only one call per handle may be in flight
+ *     (callVar.py:197-205 contract).
+ */
+#ifndef CVB200_H
+#define CVB200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cvb_model cvb_model;
+
+enum { CVB_V3 = 0, CVB_V3_SLIM = 1 };
+/* arithmetic mode of the forward pass */
+enum {
+  CVB_COMPUTE_FP32 = 0,    /* fp32 SIMT everywhere (bit-faithful op order per layer) */
+  CVB_COMPUTE_FP16X3 = 1,  /* conv3/FC4 on tcgen05 with split-fp16 (hi+lo) operands, fp32 accumulate */
+  CVB_COMPUTE_FP16 = 2     /* conv3/FC4 on tcgen05 with plain fp16 operands, fp32 accumulate */
+};
+
+const char* cvb_last_error(void);
+int cvb_version(void);
+
+/* replaces Clairvoyante.__init__/_buildGraph (clairvoyante_v3.py:7-175): allocates
+ * parameters, Adam slots and work buffers on CUDA device `device`.              */
+int cvb_create(int variant, int device, cvb_model** out);
+/* replaces close()/__del__ (clairvoyante_v3.py:180,282) */
+int cvb_destroy(cvb_model* m);
+
+/* the 18 trainable variables by TF name (visualization.ipynb:100-121) */
+int cvb_num_variables(const cvb_model* m);
+int cvb_variable_info(const cvb_model* m, int idx, char* name, int name_cap,
+                      int64_t* numel, int* ndim, int64_t dims[4]);
+int64_t cvb_num_parameters(const cvb_model* m);
+/* replaces restoreParameters / init (clairvoyante_v3.py:177,248): upload one variable.
+ * slot 0 = value, 1 = Adam m, 2 = Adam v                                            */
+int cvb_set_variable(cvb_model* m, const char* name, int slot, const float* host, int64_t n);
+/* replaces saveParameters (clairvoyante_v3.py:243): download one variable */
+int cvb_get_variable(cvb_model* m, const char* name, int slot, float* host, int64_t n);
+/* Adam step counter t (TF keeps beta1_power/beta2_power; t is their exponent) */
+int cvb_set_step(cvb_model* m, int64_t t);
+int cvb_get_step(const cvb_model* m, int64_t* t);
+int cvb_set_compute_mode(cvb_model* m, int mode);
+
+/* replaces predict/predictNoRT (clairvoyante_v3.py:257-280) with HOST buffers:
+ * stages x through pinned memory, copies host->device, runs the kernels, copies
+ * (n,16) results back.  x may be pageable or pinned.  Blocks until results are
+ * in out16.                                                                      */
+int cvb_predict_host(cvb_model* m, const float* x, int64_t n, float* out16, float* logits16);
+/* same computation on DEVICE buffers (x, out16, logits16 are device pointers on the
+ * handle's device); enqueued on `stream` (a cudaStream_t, NULL = the handle's own
+ * stream) and NOT synchronised.                                                  */
+int cvb_predict_device(cvb_model* m, const float* x, int64_t n, float* out16, float* logits16,
+                       void* stream);
+
+/* replaces getLoss/getLossNoRT (clairvoyante_v3.py:207-227): forward with phase=False,
+ * lambda=0; returns the SUM-over-batch loss (clairvoyante_v3.py:140-152).
+ * x (n,33,4,4) and y (n,16) float32 host buffers.                                */
+int cvb_loss_host(cvb_model* m, const float* x, const float* y, int64_t n, float* loss);
+
+/* replaces train/trainNoRT (clairvoyante_v3.py:183-205): forward (SELU dropout on FC4
+ * with `drop4`, selu.py:34-69), loss + l2*sum(0.5*||kernel||^2), backward, TF-1.x Adam
+ * (clairvoyante_v3.py:174).  loss5 receives [loss, loss1..4-sum parts are folded: total,
+ * base, zygosity, varType, indelLength] BEFORE the update, like session.run's fetch.
+ * If apply_update == 0 the gradients are left in the gradient buffer (for a
+ * data-parallel all-reduce by the caller) and cvb_apply_adam finishes the step.    */
+int cvb_train_step_host(cvb_model* m, const float* x, const float* y, int64_t n,
+                        float lr, float l2, float drop4, uint64_t dropout_seed,
+                        int apply_update, float* loss5);
+/* device pointer + element count of the flat fp32 gradient buffer (all 18 variables in
+ * cvb_variable_info order, followed by 5 loss terms) for an external all-reduce     */
+int cvb_grad_buffer(cvb_model* m, void** dev_ptr, int64_t* numel);
+/* download gradients of one variable (testing) */
+int cvb_get_gradient(cvb_model* m, const char* name, float* host, int64_t n);
+int cvb_apply_adam(cvb_model* m, float lr, float l2);
+
+/* pinned host memory helpers for the batch feed (utils_v2.GetTensor replacement) */
+int cvb_alloc_pinned(int64_t bytes, void** out);
+int cvb_free_pinned(void* p);
+
+/* test aid: copy the first n floats of an intermediate of the LAST device pass to host.
+ * which: 0 = p2 (pooled conv2, padded rows), 1 = p3 (pooled conv3 = FC4 input), 2 = h4 (FC4 output) */
+int cvb_debug_read(cvb_model* m, int which, float* host, int64_t n);
+
+/* counters for bench.py: number of this library's kernels launched so far on the handle */
+int64_t cvb_kernel_launches(const cvb_model* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
