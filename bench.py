@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- candidate sites/sec (inference), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload = BASELINE.json configs[1]: 4M synthetic (33,4,4) candidate sites, clairvoyante_v3
+forward, fp32, per GPU (the site list shards with no collective: every rank runs the same
+4M-site pass on its own GPU => weak scaling).  One "step" = one pass of the hot path over
+those sites.
+  value : whole-job sites/s with the inputs resident in HBM (CUDA events, max over ranks)
+  e2e   : same metric through the public `Clairvoyante` object with pinned HOST buffers,
+          H2D of every input byte and D2H of every result inside the timed region
+  roofline : dominant kernel, algorithmic FLOPs / live CUDA-event duration (the path is
+          compute-bound: 3,708 FLOP per HBM byte); HBM view alongside
+  cpu_baseline : the oracle's torch-CPU fp32 restatement of the TF graph on the host cores
+--impl reference times that CPU restatement alone (the reference itself needs TensorFlow
+1.12 + Python 2 and cannot run here or on the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FLOPS_PER_SITE = {  # SURVEY.md 8d / BASELINE.md section 2 (2*MAC)
+    "v3": dict(front=67584 + 950272, conv3=3833856, fc4=3096576, tail=112896 + 6720, total=8067904),
+    "v3_slim": dict(front=33792 + 405504, conv3=2703360, fc4=304128, tail=1296 + 720, total=3448800),
+}
+HBM_BYTES_PER_SITE = 2176          # 2112 in + 64 out, fp32 I/O
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.45: 148 SMs x 128 FMA lanes x 2 x clocks.max.sm
+METRIC = "candidate sites/sec (inference)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_reference_rate(variant, W, budget_s, batch=1000):
+    """sites/s of the torch-CPU fp32 restatement (oracle) with all host threads, batch =
+    param.predictBatchSize (param.py:12); ~budget_s seconds of CPU work."""
+    import torch
+    from oracle import cv_oracle_torch as OT
+    from clairvoyante_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pred = OT.CpuPredictor(W, variant)
+    x = synth.make_sites(batch, seed=99)
+    for _ in range(3):
+        pred.predict(x)
+    n = 0
+    t0 = time.perf_counter()
+    while True:
+        pred.predict(x)
+        n += batch
+        if time.perf_counter() - t0 >= budget_s and n >= 8 * batch:
+            break
+    dt = time.perf_counter() - t0
+    return n / dt, cores, n, pred.threads
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (here: its restatement,
+    see module docstring) on the host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from clairvoyante_b200 import initializers
+    W = initializers.init_weights(args.variant, seed=0)
+    import torch
+    from oracle import cv_oracle_torch as OT
+    from clairvoyante_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pred = OT.CpuPredictor(W, args.variant)
+    sample = 16 * 1000                                     # sites per step: 16 batches of predictBatchSize
+    xs = [synth.make_sites(1000, seed=100 + i) for i in range(16)]
+    def step():
+        for x in xs:
+            pred.predict(x)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    line = dict(metric=METRIC, value=v, unit="sites/s", impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=dt / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic",
+                config=dict(workload="configs[1]: 4M synthetic (33,4,4) sites, %s forward fp32" % args.variant,
+                            sample="bounded: %d sites per step in batches of 1000 (param.predictBatchSize)" % sample),
+                cpu_baseline=dict(value=v, unit="sites/s", cores=cores, kind="port",
+                                  sample="%d sites/step x %d steps, torch-CPU fp32 restatement of the TF graph, %d threads"
+                                         % (sample, args.steps, pred.threads)),
+                e2e=dict(value=v, unit="sites/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                note="reference needs TensorFlow 1.12/Python 2 (absent): oracle/cv_oracle_torch.py stands in (kind=port)")
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", default="v3", choices=["v3", "v3_slim"])
+    ap.add_argument("--sites", type=int, default=4 * 1024 * 1024, help="sites per GPU per step")
+    ap.add_argument("--e2e-sites", type=int, default=None, help="sites per GPU per e2e step (default: --sites)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run --nproc-per-node %d" % (args.gpus, world, args.gpus))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from clairvoyante_b200 import initializers, synth
+    if args.variant == "v3":
+        from clairvoyante_b200 import clairvoyante_v3 as cv
+    else:
+        from clairvoyante_b200 import clairvoyante_v3_slim as cv
+    W = initializers.init_weights(args.variant, seed=0)
+    m = cv.Clairvoyante(device=local)
+    m.setWeights(W)
+
+    # ---- synthetic inputs: 65,536 unique seeded sites (rank-distinct), tiled to --sites in HBM
+    n = args.sites
+    pool_n = min(65536, n)
+    pool = synth.make_sites(pool_n, seed=1000 + rank)
+    reps = (n + pool_n - 1) // pool_n
+    xd = torch.from_numpy(pool).cuda().repeat(reps, 1, 1, 1)[:n].contiguous()      # 8.45 GB for 4M sites >> 126 MB L2
+    od = torch.empty((n, 16), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        m.predictDevice(xd.data_ptr(), n, od.data_ptr(), None, stream)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    l0 = m.kernelLaunches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = m.kernelLaunches() - l0
+    clk = clocks.stop()
+    value = world * n * args.steps / (ms / 1e3)
+
+    # ---- per-kernel durations, live, CUDA events on the launching stream (separate short pass so
+    #      the event records do not sit inside the headline timing)
+    m.profileBegin()
+    for _ in range(2):
+        step()
+    prof = m.profileRead()
+    fl = FLOPS_PER_SITE[args.variant]
+    kern = {}
+    for k, (tms, cnt) in prof.items():
+        kern[k] = dict(ms_per_launch=tms / max(cnt, 1), launches=cnt, share=tms / max(sum(v[0] for v in prof.values()), 1e-9),
+                       tflops=fl[k] * (2 * n) / (tms / 1e3) / 1e12)
+    dom = max(kern, key=lambda k: kern[k]["share"])
+    pk = peaks()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.variant, {}).get(dom)
+    sites_per_launch = min(n, 16384)
+    roofline = dict(kernel=dom, bound="fp32_fma", achieved=kern[dom]["tflops"], peak=FP32_NOMINAL_TFLOPS, unit="TFLOP/s",
+                    frac=kern[dom]["tflops"] / FP32_NOMINAL_TFLOPS,
+                    peak_source="nominal fp32 FMA (148 SM x 128 lanes x 2 x 1.965 GHz); MEASURED_PEAKS.json has no fp32-SIMT figure",
+                    algorithmic_flops_per_launch=fl[dom] * sites_per_launch, ms_per_launch=kern[dom]["ms_per_launch"],
+                    traffic=traffic, kernels=kern,
+                    whole_pass=dict(tflops=value / world * fl["total"] / 1e12, frac_fp32_nominal=value / world * fl["total"] / 1e12 / FP32_NOMINAL_TFLOPS),
+                    hbm=dict(achieved_gbs=value / world * HBM_BYTES_PER_SITE / 1e9, peak_gbs=pk["hbm_gbs"],
+                             frac=value / world * HBM_BYTES_PER_SITE / 1e9 / pk["hbm_gbs"], peak_source=pk["source"],
+                             note="not the binding bound: 3,708 FLOP per algorithmic HBM byte"))
+
+    # ---- e2e: public API, pinned host input, H2D + D2H inside the timed region
+    ne = args.e2e_sites or n
+    del xd, od
+    torch.cuda.empty_cache()
+    xh = torch.empty((ne, 33, 4, 4), dtype=torch.float32).pin_memory()
+    xh_np = xh.numpy()
+    for i in range(0, ne, pool_n):
+        k = min(pool_n, ne - i)
+        xh_np[i:i + k] = pool[:k]
+    checksum = 0.0
+    for _ in range(max(1, min(args.warmup, 2))):
+        m.predict(xh_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        base, z, t, l = m.predict(xh_np)
+        checksum += float(t[0, 0])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    dt = max_over_ranks(dt)
+    e2e_value = world * ne * args.steps / dt
+    e2e = dict(value=e2e_value, unit="sites/s", h2d_bytes_per_step=ne * 528 * 4, d2h_bytes_per_step=ne * 16 * 4,
+               sites_per_step=ne, ms_per_step=dt / args.steps * 1e3, api="Clairvoyante.predict(X) on pinned NumPy X")
+
+    cpu = None
+    if rank == 0 and world == 1:
+        v, cores, nsamp, thr = cpu_reference_rate(args.variant, W, args.cpu_seconds)
+        cpu = dict(value=v, unit="sites/s", cores=cores, kind="port",
+                   sample="%d sites in batches of 1000, torch-CPU fp32 restatement of the TF graph (oracle/cv_oracle_torch.py), %d threads"
+                          % (nsamp, thr))
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit="sites/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    data="synthetic",
+                    config=dict(workload="configs[1]: 4M synthetic (33,4,4) candidate sites, clairvoyante_%s forward, fp32" % args.variant,
+                                sites_per_gpu_per_step=n, unique_sites=pool_n, parallelism="site-list sharding, no collective",
+                                l2="inputs (%.2f GB/GPU) exceed the 126 MB L2; no flush needed" % (n * 2112 / 1e9),
+                                weights="reference initialisers, seed 0", compute_mode="fp32 SIMT"),
+                    clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu, checksum=checksum)
+        print(json.dumps(line))
+    m.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -71,6 +71,8 @@ SIGNATURES = {
     "cvb_alloc_pinned": (ctypes.c_int, [c_i64, ctypes.POINTER(c_vp)]),
     "cvb_free_pinned": (ctypes.c_int, [c_vp]),
     "cvb_debug_read": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_i64]),
+    "cvb_profile_begin": (ctypes.c_int, [c_vp]),
+    "cvb_profile_read": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_i64)]),
     "cvb_kernel_launches": (c_i64, [c_vp]),
 }
 

@@ -63,6 +63,9 @@ struct cvb_model {
   cudaEvent_t e_h2d[2], e_comp[2], e_d2h[2];
   bool events = false;
   int64_t launches = 0;
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;  // 5 per chunk: before front, after front, conv3, fc4, tail
+  size_t prof_used = 0;
   TrainWork* train = nullptr;
   const float* var(const char* n) const {
     for (auto& v : vars)
@@ -157,6 +160,7 @@ extern "C" int cvb_destroy(cvb_model* m) {
   cudaSetDevice(m->device);
   cudaDeviceSynchronize();
   train_work_free(m->train);
+  for (auto e : m->prof_events) cudaEventDestroy(e);
   cudaFree(m->d_params); cudaFree(m->d_m); cudaFree(m->d_v); cudaFree(m->d_grad);
   cudaFree(m->d_p2); cudaFree(m->d_p3); cudaFree(m->d_h4);
   for (int i = 0; i < 2; ++i) {
@@ -243,9 +247,21 @@ static HeadPtrs head_ptrs(const cvb_model* m) {
 }
 
 // one chunk (n <= CHUNK) of the forward pass on `st`
+static int prof_mark(cvb_model* m, cudaStream_t st) {
+  if (!m->profiling) return 0;
+  if (m->prof_used == m->prof_events.size()) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    m->prof_events.push_back(e);
+  }
+  CK(cudaEventRecord(m->prof_events[m->prof_used++], st));
+  return 0;
+}
+
 static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, float* logits16, cudaStream_t st) {
   if (n <= 0) return 0;
   const int sms = m->num_sms;
+  if (prof_mark(m, st)) return 1;
   if (m->variant == CVB_V3) {
     {
       using F = FrontV3<4>;
@@ -256,6 +272,7 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
                                           m->var("conv2/bias"), m->d_p2);
       CK(cudaGetLastError());
+      if (prof_mark(m, st)) return 1;
     }
     {
       using C = ConvCfg<32, 48, 3, 26, 3, 8, 8>;
@@ -266,6 +283,7 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       int grid = (int)std::min<int64_t>(tiles, sms);
       k<<<grid, 256, L::SMEM_BYTES, st>>>(m->d_p2, n, m->var("conv3/kernel"), m->var("conv3/bias"), m->d_p3);
       CK(cudaGetLastError());
+      if (prof_mark(m, st)) return 1;
     }
     {
       using F = FcCfg<336, 21, 16, 12, 8>;
@@ -274,11 +292,13 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       int grid = (int)((n + F::M - 1) / F::M);
       k<<<grid, 256, F::SMEM_BYTES, st>>>(m->d_p3, n, 4608, m->var("fc4/kernel"), m->var("fc4/bias"), m->d_h4);
       CK(cudaGetLastError());
+      if (prof_mark(m, st)) return 1;
     }
     {
       int grid = (int)((n + 15) / 16);
       k_tail<336, 168, 16><<<grid, 256, 0, st>>>(m->d_h4, n, head_ptrs(m), out16, logits16);
       CK(cudaGetLastError());
+      if (prof_mark(m, st)) return 1;
     }
     m->launches += 4;
   } else {
@@ -291,6 +311,7 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
                                           m->var("conv2/bias"), m->d_p2);
       CK(cudaGetLastError());
+      if (prof_mark(m, st)) return 1;
     }
     {
       using C = ConvCfg<16, 32, 5, 33, 3, 8, 8>;
@@ -301,6 +322,7 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       int grid = (int)std::min<int64_t>(tiles, sms);
       k<<<grid, 256, L::SMEM_BYTES, st>>>(m->d_p2, n, m->var("conv3/kernel"), m->var("conv3/bias"), m->d_p3);
       CK(cudaGetLastError());
+      if (prof_mark(m, st)) return 1;
     }
     {
       using F = FcCfg<36, 9, 4, 28, 8>;
@@ -309,11 +331,13 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       int grid = (int)((n + F::M - 1) / F::M);
       k<<<grid, 256, F::SMEM_BYTES, st>>>(m->d_p3, n, 4224, m->var("fc4/kernel"), m->var("fc4/bias"), m->d_h4);
       CK(cudaGetLastError());
+      if (prof_mark(m, st)) return 1;
     }
     {
       int grid = (int)((n + 15) / 16);
       k_tail<36, 18, 16><<<grid, 256, 0, st>>>(m->d_h4, n, head_ptrs(m), out16, logits16);
       CK(cudaGetLastError());
+      if (prof_mark(m, st)) return 1;
     }
     m->launches += 4;
   }
@@ -326,7 +350,7 @@ extern "C" int cvb_predict_device(cvb_model* m, const float* x, int64_t n, float
   if (n == 0) return 0;
   if (!x || !out16) return fail("cvb_predict_device: NULL buffer");
   CK(cudaSetDevice(m->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : m->s_comp;
+  cudaStream_t st = (cudaStream_t)stream;
   for (int64_t s = 0; s < n; s += CHUNK) {
     int64_t c = std::min<int64_t>(CHUNK, n - s);
     if (forward_chunk(m, x + s * 528, c, out16 + s * 16, logits16 ? logits16 + s * 16 : nullptr, st)) return 1;
@@ -406,6 +430,30 @@ extern "C" int cvb_debug_read(cvb_model* m, int which, float* host, int64_t n) {
   CK(cudaSetDevice(m->device));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(host, src, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int cvb_profile_begin(cvb_model* m) {
+  if (!m) return fail("cvb_profile_begin: NULL model");
+  CK(cudaSetDevice(m->device));
+  CK(cudaDeviceSynchronize());
+  m->profiling = true;
+  m->prof_used = 0;
+  return 0;
+}
+extern "C" int cvb_profile_read(cvb_model* m, double ms[4], int64_t launches[4]) {
+  if (!m || !ms || !launches) return fail("cvb_profile_read: NULL argument");
+  CK(cudaSetDevice(m->device));
+  CK(cudaDeviceSynchronize());
+  for (int k = 0; k < 4; ++k) { ms[k] = 0; launches[k] = 0; }
+  for (size_t i = 0; i + 5 <= m->prof_used; i += 5)
+    for (int k = 0; k < 4; ++k) {
+      float t = 0;
+      CK(cudaEventElapsedTime(&t, m->prof_events[i + k], m->prof_events[i + k + 1]));
+      ms[k] += t;
+      launches[k] += 1;
+    }
+  m->profiling = false;
   return 0;
 }
 

@@ -219,6 +219,16 @@ class ClairvoyanteBase(object):
         _lib.check(self._lib.cvb_debug_read(self._h, dict(p2=0, p3=1, h4=2)[which], a.ctypes.data, a.size))
         return a
 
+    def profileBegin(self):
+        _lib.check(self._lib.cvb_profile_begin(self._h))
+
+    def profileRead(self):
+        """{kernel: (total_ms, launches)} since profileBegin(); synchronises the device."""
+        ms = (ctypes.c_double * 4)()
+        cnt = (ctypes.c_int64 * 4)()
+        _lib.check(self._lib.cvb_profile_read(self._h, ms, cnt))
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(("front", "conv3", "fc4", "tail"))}
+
     def kernelLaunches(self):
         return int(self._lib.cvb_kernel_launches(self._h))
 

@@ -72,8 +72,8 @@ int cvb_set_compute_mode(cvb_model* m, int mode);
  * in out16.                                                                      */
 int cvb_predict_host(cvb_model* m, const float* x, int64_t n, float* out16, float* logits16);
 /* same computation on DEVICE buffers (x, out16, logits16 are device pointers on the
- * handle's device); enqueued on `stream` (a cudaStream_t, NULL = the handle's own
- * stream) and NOT synchronised.                                                  */
+ * handle's device); enqueued on `stream` (a cudaStream_t; NULL = the CUDA legacy default
+ * stream, exactly as in the runtime API) and NOT synchronised.                                                  */
 int cvb_predict_device(cvb_model* m, const float* x, int64_t n, float* out16, float* logits16,
                        void* stream);
 
@@ -105,6 +105,13 @@ int cvb_free_pinned(void* p);
 /* test aid: copy the first n floats of an intermediate of the LAST device pass to host.
  * which: 0 = p2 (pooled conv2, padded rows), 1 = p3 (pooled conv3 = FC4 input), 2 = h4 (FC4 output) */
 int cvb_debug_read(cvb_model* m, int which, float* host, int64_t n);
+
+/* per-kernel device timing for bench.py's roofline: while enabled, every kernel launch of
+ * the forward pass is bracketed by CUDA events on the launching stream.  cvb_profile_read
+ * synchronises the device and returns, per kernel kind (0 front, 1 conv3, 2 fc4, 3 tail),
+ * the summed duration in ms and the number of launches since cvb_profile_begin.            */
+int cvb_profile_begin(cvb_model* m);
+int cvb_profile_read(cvb_model* m, double ms[4], int64_t launches[4]);
 
 /* counters for bench.py: number of this library's kernels launched so far on the handle */
 int64_t cvb_kernel_launches(const cvb_model* m);

@@ -151,7 +151,7 @@ def forward(weights, x, variant="v3", dtype=np.float64, return_all=False,
         layers["conv%d" % i] = a
         a = maxpool_h(a, pool)
         layers["pool%d" % i] = a
-    flat = a.reshape(a.shape[0], -1)               # (h, w, c) order, c fastest; :99-102
+    flat = a.reshape(a.shape[0], int(np.prod(a.shape[1:])))               # (h, w, c) order, c fastest; :99-102
     fc4 = selu(flat @ W["fc4/kernel"] + W["fc4/bias"])
     d4 = dropout_selu(fc4, drop4_rate, drop4_mask)
     fc5 = selu(d4 @ W["fc5/kernel"] + W["fc5/bias"])
