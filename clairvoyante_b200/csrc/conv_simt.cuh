@@ -14,7 +14,8 @@
 // (pair = i*MT + t) so that adjacent lanes touch adjacent rows; with the row stride
 // RS = 4*CIN+4 floats (== 4 mod 32 for CIN>=8, 20 for CIN=4) the 16-byte A loads of a
 // warp fall in distinct banks.  B (weights, HWIO exactly as TF stores them) is read as
-// float4 over output channels and broadcast across the lanes that share a channel group.
+// float4 over output channels; thread nt owns the float4 channel groups nt, nt+NT, ... so a
+// warp's B load covers consecutive 16-byte chunks (no bank conflict even for COUT=48).
 #pragma once
 #include "common.cuh"
 
@@ -75,7 +76,7 @@ __device__ __forceinline__ void conv_compute(const float* __restrict__ in_s, con
   for (int kh = 0; kh < C::KH; ++kh) {
     for (int kw = kw_lo; kw <= kw_hi; ++kw) {
       const float* a_ptr = in_s + kh * C::RS + kw * C::CIN;
-      const float* b_ptr = w_s + ((kh * 4 + kw) * C::CIN) * C::COUT + th.nt * C::TN;
+      const float* b_ptr = w_s + ((kh * 4 + kw) * C::CIN) * C::COUT + th.nt * 4;
 #pragma unroll(C::CIN / 4 >= 2 ? 2 : 1)
       for (int c4 = 0; c4 < C::CIN / 4; ++c4) {
         float4 a[C::TM];
@@ -86,7 +87,7 @@ __device__ __forceinline__ void conv_compute(const float* __restrict__ in_s, con
           float4 b[C::TN / 4];
 #pragma unroll
           for (int j = 0; j < C::TN / 4; ++j)
-            b[j] = *reinterpret_cast<const float4*>(b_ptr + (c4 * 4 + cc) * C::COUT + j * 4);
+            b[j] = *reinterpret_cast<const float4*>(b_ptr + (c4 * 4 + cc) * C::COUT + j * (4 * C::NT));
 #pragma unroll
           for (int i = 0; i < C::TM; ++i) {
             const float av = cc == 0 ? a[i].x : cc == 1 ? a[i].y : cc == 2 ? a[i].z : a[i].w;
@@ -113,13 +114,13 @@ __device__ __forceinline__ void conv_store_selu_smem(const float (&acc)[C::TM][C
   if (!th.active) return;
   float bv[C::TN];
 #pragma unroll
-  for (int j = 0; j < C::TN; ++j) bv[j] = bias_s[th.nt * C::TN + j];
+  for (int j = 0; j < C::TN; ++j) bv[j] = bias_s[(th.nt + C::NT * (j / 4)) * 4 + (j & 3)];
 #pragma unroll
   for (int i = 0; i < C::TM; ++i) {
     int p = th.pair(i);
     if (p < 0) continue;
     int site = p / C::HOUT, h = p - site * C::HOUT;
-    float* d = dst + (site * DROWS + h + DR0) * DRS + th.w * C::COUT + th.nt * C::TN;
+    float* d = dst + (site * DROWS + h + DR0) * DRS + th.w * C::COUT + th.nt * 4;
 #pragma unroll
     for (int j = 0; j < C::TN / 4; ++j) {
       float4 v;
@@ -127,7 +128,7 @@ __device__ __forceinline__ void conv_store_selu_smem(const float (&acc)[C::TM][C
       v.y = selu_f(acc[i][j * 4 + 1] + bv[j * 4 + 1]);
       v.z = selu_f(acc[i][j * 4 + 2] + bv[j * 4 + 2]);
       v.w = selu_f(acc[i][j * 4 + 3] + bv[j * 4 + 3]);
-      *reinterpret_cast<float4*>(d + j * 4) = v;
+      *reinterpret_cast<float4*>(d + j * (4 * C::NT)) = v;
     }
   }
 }
@@ -140,14 +141,14 @@ __device__ __forceinline__ void conv_store_selu_global(const float (&acc)[C::TM]
   if (!th.active) return;
   float bv[C::TN];
 #pragma unroll
-  for (int j = 0; j < C::TN; ++j) bv[j] = bias_s[th.nt * C::TN + j];
+  for (int j = 0; j < C::TN; ++j) bv[j] = bias_s[(th.nt + C::NT * (j / 4)) * 4 + (j & 3)];
 #pragma unroll
   for (int i = 0; i < C::TM; ++i) {
     int p = th.pair(i);
     if (p < 0) continue;
     int site = p / C::HOUT, h = p - site * C::HOUT;
     if (site >= nsites) continue;
-    float* d = dst + ((int64_t)site * DROWS + h + DR0) * DRS + th.w * C::COUT + th.nt * C::TN;
+    float* d = dst + ((int64_t)site * DROWS + h + DR0) * DRS + th.w * C::COUT + th.nt * 4;
 #pragma unroll
     for (int j = 0; j < C::TN / 4; ++j) {
       float4 v;
@@ -155,7 +156,7 @@ __device__ __forceinline__ void conv_store_selu_global(const float (&acc)[C::TM]
       v.y = selu_f(acc[i][j * 4 + 1] + bv[j * 4 + 1]);
       v.z = selu_f(acc[i][j * 4 + 2] + bv[j * 4 + 2]);
       v.w = selu_f(acc[i][j * 4 + 3] + bv[j * 4 + 3]);
-      *reinterpret_cast<float4*>(d + j * 4) = v;
+      *reinterpret_cast<float4*>(d + j * (4 * C::NT)) = v;
     }
   }
 }

@@ -46,10 +46,12 @@ struct VarInfo {
   int64_t numel, offset;
 };
 
-static const int CHUNK = 16384;  // sites per device pass (bounds the intermediates)
+// sites per device pass: bounds the intermediates and makes k_fc4's grid exactly one wave
+// (M-tile 96 sites x #SMs for v3; 224 x #SMs for slim)
 
 struct cvb_model {
   int variant = 0, device = 0, compute_mode = CVB_COMPUTE_FP32, num_sms = 148;
+  int64_t CHUNK = 96 * 148;
   std::vector<VarInfo> vars;
   int64_t nparams = 0, step = 0;
   float *d_params = nullptr, *d_m = nullptr, *d_v = nullptr, *d_grad = nullptr;
@@ -134,6 +136,8 @@ extern "C" int cvb_create(int variant, int device, cvb_model** out) {
   m->device = device;
   m->num_sms = prop.multiProcessorCount;
   build_vars(m);
+  m->CHUNK = (int64_t)m->num_sms * (variant == CVB_V3 ? 96 : 224);
+  const int64_t CHUNK = m->CHUNK;
   const size_t pb = (size_t)m->nparams * 4;
   CK(cudaMalloc(&m->d_params, pb)); CK(cudaMemset(m->d_params, 0, pb));
   CK(cudaMalloc(&m->d_m, pb));      CK(cudaMemset(m->d_m, 0, pb));
@@ -351,6 +355,7 @@ extern "C" int cvb_predict_device(cvb_model* m, const float* x, int64_t n, float
   if (!x || !out16) return fail("cvb_predict_device: NULL buffer");
   CK(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
+  const int64_t CHUNK = m->CHUNK;
   for (int64_t s = 0; s < n; s += CHUNK) {
     int64_t c = std::min<int64_t>(CHUNK, n - s);
     if (forward_chunk(m, x + s * 528, c, out16 + s * 16, logits16 ? logits16 + s * 16 : nullptr, st)) return 1;
@@ -360,6 +365,7 @@ extern "C" int cvb_predict_device(cvb_model* m, const float* x, int64_t n, float
 
 static int ensure_host_slots(cvb_model* m) {
   if (m->d_x[0]) return 0;
+  const int64_t CHUNK = m->CHUNK;
   for (int i = 0; i < 2; ++i) {
     CK(cudaMalloc(&m->d_x[i], (size_t)CHUNK * 528 * 4));
     CK(cudaMalloc(&m->d_out[i], (size_t)CHUNK * 16 * 4));
@@ -385,6 +391,7 @@ extern "C" int cvb_predict_host(cvb_model* m, const float* x, int64_t n, float* 
   CK(cudaSetDevice(m->device));
   if (ensure_host_slots(m)) return 1;
   const bool pinned_in = is_pinned(x);
+  const int64_t CHUNK = m->CHUNK;
   const int64_t nchunks = (n + CHUNK - 1) / CHUNK;
   // software pipeline over chunks: H2D(c+1) || kernels(c) || D2H(c-1)
   for (int64_t c = 0; c <= nchunks; ++c) {
@@ -426,7 +433,7 @@ extern "C" int cvb_debug_read(cvb_model* m, int which, float* host, int64_t n) {
   const float* src = which == 0 ? m->d_p2 : which == 1 ? m->d_p3 : which == 2 ? m->d_h4 : nullptr;
   const int64_t per = which == 0 ? m->p2_site : which == 1 ? m->p3_site : m->h4_site;
   if (!src) return fail("cvb_debug_read: bad selector %d", which);
-  if (n < 0 || n > (int64_t)CHUNK * per) return fail("cvb_debug_read: n out of range");
+  if (n < 0 || n > m->CHUNK * per) return fail("cvb_debug_read: n out of range");
   CK(cudaSetDevice(m->device));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(host, src, (size_t)n * 4, cudaMemcpyDeviceToHost));
