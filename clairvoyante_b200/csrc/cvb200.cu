@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "fwd_simt.cuh"
+#include "fc4_tc.cuh"
 #include "train_simt.cuh"
 
 using namespace cvb;
@@ -65,6 +66,13 @@ struct cvb_model {
   cudaEvent_t e_h2d[2], e_comp[2], e_d2h[2];
   bool events = false;
   int64_t launches = 0;
+  // tensor-core path (CVB_COMPUTE_FP16X3): pre-split FC4 weights + TMA descriptors
+  __half *d_w4t_hi = nullptr, *d_w4t_lo = nullptr;
+  unsigned int* d_absmax = nullptr;
+  float* d_inv_scale = nullptr;
+  bool tc_ready = false, tc_weights_dirty = true;
+  CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
+  int64_t alloc_sites = 0;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;  // 5 per chunk: before front, after front, conv3, fc4, tail
   size_t prof_used = 0;
@@ -137,7 +145,8 @@ extern "C" int cvb_create(int variant, int device, cvb_model** out) {
   m->num_sms = prop.multiProcessorCount;
   build_vars(m);
   m->CHUNK = (int64_t)m->num_sms * (variant == CVB_V3 ? 96 : 224);
-  const int64_t CHUNK = m->CHUNK;
+  m->alloc_sites = (int64_t)m->num_sms * 224;  // every mode's chunk fits (fp32: 96/SM, tensor: 128/SM, slim: 224/SM)
+  const int64_t CHUNK = m->alloc_sites;
   const size_t pb = (size_t)m->nparams * 4;
   CK(cudaMalloc(&m->d_params, pb)); CK(cudaMemset(m->d_params, 0, pb));
   CK(cudaMalloc(&m->d_m, pb));      CK(cudaMemset(m->d_m, 0, pb));
@@ -167,6 +176,7 @@ extern "C" int cvb_destroy(cvb_model* m) {
   for (auto e : m->prof_events) cudaEventDestroy(e);
   cudaFree(m->d_params); cudaFree(m->d_m); cudaFree(m->d_v); cudaFree(m->d_grad);
   cudaFree(m->d_p2); cudaFree(m->d_p3); cudaFree(m->d_h4);
+  cudaFree(m->d_w4t_hi); cudaFree(m->d_w4t_lo); cudaFree(m->d_absmax); cudaFree(m->d_inv_scale);
   for (int i = 0; i < 2; ++i) {
     cudaFree(m->d_x[i]); cudaFree(m->d_out[i]); cudaFree(m->d_lg[i]);
     cudaFreeHost(m->h_x[i]); cudaFreeHost(m->h_out[i]); cudaFreeHost(m->h_lg[i]);
@@ -208,6 +218,7 @@ extern "C" int cvb_set_variable(cvb_model* m, const char* name, int slot, const 
   if (!base) return fail("cvb_set_variable: bad slot %d", slot);
   CK(cudaSetDevice(m->device));
   CK(cudaMemcpy(base + v->offset, host, (size_t)n * 4, cudaMemcpyHostToDevice));
+  if (slot == 0) m->tc_weights_dirty = true;
   return 0;
 }
 extern "C" int cvb_get_variable(cvb_model* m, const char* name, int slot, float* host, int64_t n) {
@@ -222,12 +233,88 @@ extern "C" int cvb_get_variable(cvb_model* m, const char* name, int slot, float*
   CK(cudaMemcpy(host, base + v->offset, (size_t)n * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
+// ------------------------------------------------------------------------------------
+// tensor-core path setup: TMA descriptors (driver entry point fetched through the runtime,
+// so the library has no link-time dependency on libcuda) and pre-split FC4 weights
+// ------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+// fp16 row-major [rows][cols] tensor, box = box_cols x box_rows, given swizzle
+static int make_map_f16(CUtensorMap* map, void* base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows,
+                        CUtensorMapSwizzle sw) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+static int tc_setup(cvb_model* m) {
+  if (m->tc_ready) return 0;
+  using F = tc::Fc4Tc;
+  const int K = 4608;
+  CK(cudaMalloc(&m->d_w4t_hi, (size_t)F::N * K * 2));
+  CK(cudaMalloc(&m->d_w4t_lo, (size_t)F::N * K * 2));
+  CK(cudaMalloc(&m->d_absmax, 16));
+  CK(cudaMalloc(&m->d_inv_scale, 16));
+  __half* a_hi = reinterpret_cast<__half*>(m->d_p3);
+  __half* a_lo = a_hi + m->alloc_sites * K;
+  if (make_map_f16(&m->map_a_hi, a_hi, (uint64_t)m->alloc_sites, K, F::BK, F::BM, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  if (make_map_f16(&m->map_a_lo, a_lo, (uint64_t)m->alloc_sites, K, F::BK, F::BM, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  if (make_map_f16(&m->map_b_hi, m->d_w4t_hi, F::N, K, F::BK, F::B_BOX_ROWS, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  if (make_map_f16(&m->map_b_lo, m->d_w4t_lo, F::N, K, F::BK, F::B_BOX_ROWS, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  CK(cudaFuncSetAttribute(tc::k_fc4_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
+  m->tc_ready = true;
+  m->tc_weights_dirty = true;
+  return 0;
+}
+
+// (re)build the split fp16 copy of fc4/kernel on `st` if the fp32 master changed
+static int tc_refresh_weights(cvb_model* m, cudaStream_t st) {
+  if (!m->tc_weights_dirty) return 0;
+  using F = tc::Fc4Tc;
+  const int K = 4608;
+  CK(cudaMemsetAsync(m->d_absmax, 0, 4, st));
+  tc::k_absmax<<<256, 256, 0, st>>>(m->var("fc4/kernel"), (int64_t)K * F::N, m->d_absmax);
+  CK(cudaGetLastError());
+  dim3 grid((K + 31) / 32, (F::N + 31) / 32), block(32, 8);
+  tc::k_prep_fc_weights<<<grid, block, 0, st>>>(m->var("fc4/kernel"), K, F::N, m->d_absmax, m->d_w4t_hi, m->d_w4t_lo,
+                                                 m->d_inv_scale);
+  CK(cudaGetLastError());
+  m->launches += 2;
+  m->tc_weights_dirty = false;
+  return 0;
+}
+
 extern "C" int cvb_set_step(cvb_model* m, int64_t t) { if (!m) return fail("NULL model"); m->step = t; return 0; }
 extern "C" int cvb_get_step(const cvb_model* m, int64_t* t) { if (!m || !t) return fail("NULL argument"); *t = m->step; return 0; }
 extern "C" int cvb_set_compute_mode(cvb_model* m, int mode) {
   if (!m) return fail("NULL model");
-  if (mode != CVB_COMPUTE_FP32) return fail("cvb_set_compute_mode: mode %d is not built into this library yet", mode);
+  if (mode != CVB_COMPUTE_FP32 && mode != CVB_COMPUTE_FP16X3)
+    return fail("cvb_set_compute_mode: mode %d is not built into this library yet", mode);
+  if (mode == CVB_COMPUTE_FP16X3 && m->variant != CVB_V3)
+    return fail("cvb_set_compute_mode: the tensor-core path is built for v3 only so far");
+  CK(cudaSetDevice(m->device));
+  if (mode == CVB_COMPUTE_FP16X3 && tc_setup(m)) return 1;
   m->compute_mode = mode;
+  m->CHUNK = (int64_t)m->num_sms * (m->variant == CVB_V3 ? (mode == CVB_COMPUTE_FP32 ? 96 : 128) : 224);
   return 0;
 }
 extern "C" int64_t cvb_kernel_launches(const cvb_model* m) { return m ? m->launches : 0; }
@@ -265,6 +352,8 @@ static int prof_mark(cvb_model* m, cudaStream_t st) {
 static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, float* logits16, cudaStream_t st) {
   if (n <= 0) return 0;
   const int sms = m->num_sms;
+  const bool tensor = m->compute_mode == CVB_COMPUTE_FP16X3;
+  if (tensor && tc_refresh_weights(m, st)) return 1;
   if (prof_mark(m, st)) return 1;
   if (m->variant == CVB_V3) {
     {
@@ -281,15 +370,29 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
     {
       using C = ConvCfg<32, 48, 3, 26, 3, 8, 8>;
       using L = ConvLayerSmem<C, 3>;
-      auto k = k_conv_layer<C, 3, 256>;
-      CK(set_smem(k, L::SMEM_BYTES));
       int64_t tiles = (n + C::S - 1) / C::S;
       int grid = (int)std::min<int64_t>(tiles, sms);
-      k<<<grid, 256, L::SMEM_BYTES, st>>>(m->d_p2, n, m->var("conv3/kernel"), m->var("conv3/bias"), m->d_p3);
+      if (tensor) {
+        auto k = k_conv_layer<C, 3, 256, true>;
+        CK(set_smem(k, L::SMEM_BYTES));
+        k<<<grid, 256, L::SMEM_BYTES, st>>>(m->d_p2, n, m->var("conv3/kernel"), m->var("conv3/bias"), m->d_p3,
+                                            reinterpret_cast<__half*>(m->d_p3) + m->alloc_sites * 4608);
+      } else {
+        auto k = k_conv_layer<C, 3, 256, false>;
+        CK(set_smem(k, L::SMEM_BYTES));
+        k<<<grid, 256, L::SMEM_BYTES, st>>>(m->d_p2, n, m->var("conv3/kernel"), m->var("conv3/bias"), m->d_p3, nullptr);
+      }
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
     }
-    {
+    if (tensor) {
+      using F = tc::Fc4Tc;
+      int grid = (int)((n + F::BM - 1) / F::BM);
+      tc::k_fc4_tc<<<grid, F::THREADS, F::SMEM_BYTES, st>>>(m->map_a_hi, m->map_a_lo, m->map_b_hi, m->map_b_lo, n, 4608,
+                                                            m->var("fc4/bias"), m->d_inv_scale, m->d_h4);
+      CK(cudaGetLastError());
+      if (prof_mark(m, st)) return 1;
+    } else {
       using F = FcCfg<336, 21, 16, 12, 8>;
       auto k = k_fc4<F>;
       CK(set_smem(k, F::SMEM_BYTES));
@@ -320,11 +423,11 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
     {
       using C = ConvCfg<16, 32, 5, 33, 3, 8, 8>;
       using L = ConvLayerSmem<C, 1>;
-      auto k = k_conv_layer<C, 1, 256>;
+      auto k = k_conv_layer<C, 1, 256, false>;
       CK(set_smem(k, L::SMEM_BYTES));
       int64_t tiles = (n + C::S - 1) / C::S;
       int grid = (int)std::min<int64_t>(tiles, sms);
-      k<<<grid, 256, L::SMEM_BYTES, st>>>(m->d_p2, n, m->var("conv3/kernel"), m->var("conv3/bias"), m->d_p3);
+      k<<<grid, 256, L::SMEM_BYTES, st>>>(m->d_p2, n, m->var("conv3/kernel"), m->var("conv3/bias"), m->d_p3, nullptr);
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
     }

@@ -1,0 +1,196 @@
+// fc4_tc.cuh -- FC4 (clairvoyante_v3.py:104-108: h4 = SELU(p3 @ W4 + b4), 4608 -> 336) on the
+// 5th-gen tensor cores with split-fp16 operands:
+//     x = x_hi + x_lo (two fp16),   p3 @ W4 ~= A_hi B_hi + A_hi B_lo + A_lo B_hi   (fp32 accumulate in TMEM)
+// which keeps ~22 mantissa bits per operand (dropped term A_lo B_lo ~ 2^-22 relative), so the
+// fp32 configuration's 1e-3 logit tolerance holds while the work runs on tcgen05.
+//
+// One CTA = 128 sites x all 336 outputs.  Warp roles (192 threads):
+//   warp 0    : TMA producer (one elected lane) -- per K-block of 32: A_hi, A_lo (128 x 64 B) and
+//               B_hi, B_lo (336 x 64 B, two 168-row boxes each) into a 3-stage smem ring, 64-byte swizzle
+//   warp 1    : TMEM allocator + MMA issuer (one elected lane): per stage 2 K-steps x 3 terms x 2 N-halves
+//               (N = 176 + 160; UMMA N <= 256) of tcgen05.mma.cta_group::1.kind::f16, M = 128
+//   warps 2-5 : epilogue -- tcgen05.ld the 128 x 336 fp32 accumulator (one site per thread), undo the weight
+//               pre-scale, + bias, SELU, store h4 (fp32, row-major)
+// W4 is pre-transposed / pre-split once per weight update into [336][4608] fp16 hi/lo, scaled by a power of two
+// so that the lo parts stay in fp16's normal range (k_prep_fc4_weights).
+#pragma once
+#include "tc_common.cuh"
+
+namespace cvb {
+namespace tc {
+
+struct Fc4Tc {
+  static constexpr int BM = 128, N = 336, N1 = 176, N2 = 160, BK = 32, STAGES = 3;
+  static constexpr int ROW_BYTES = BK * 2;                // 64 B = one SWIZZLE_64B atom row
+  static constexpr int A_BYTES = BM * ROW_BYTES;          // 8192
+  static constexpr int B_BYTES = N * ROW_BYTES;           // 21504
+  static constexpr int B_BOX_ROWS = 168;                  // TMA box dims are <= 256: two boxes per B tile
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 59392
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int THREADS = 192;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr uint32_t SBO = 8 * ROW_BYTES;          // 512 B between 8-row groups
+  static constexpr uint32_t LAYOUT = 4;                   // SWIZZLE_64B
+};
+
+// |w|max over a tensor as float bits (values are non-negative so uint order == float order)
+__global__ void k_absmax(const float* __restrict__ w, int64_t n, unsigned int* __restrict__ out_bits) {
+  float m = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(w[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));
+}
+
+// W [K][N] fp32 (TF dense kernel) -> Wt_hi, Wt_lo [N][K] fp16 of W * 2^s, s chosen so |W|max * 2^s < 2^14.
+// inv_scale[0] receives 2^-s for the epilogue.
+__global__ void k_prep_fc_weights(const float* __restrict__ w, int K, int N, const unsigned int* __restrict__ absmax_bits,
+                                  __half* __restrict__ wt_hi, __half* __restrict__ wt_lo, float* __restrict__ inv_scale) {
+  __shared__ float tile[32][33];
+  const float am = fmaxf(__uint_as_float(*absmax_bits), 1e-30f);
+  int e;
+  frexpf(am, &e);  // am < 2^e
+  int s = 14 - e;
+  s = s < -20 ? -20 : (s > 30 ? 30 : s);
+  const float scale = ldexpf(1.f, s);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) inv_scale[0] = ldexpf(1.f, -s);
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int k = k0 + r, n = n0 + threadIdx.x;
+    tile[r][threadIdx.x] = (k < K && n < N) ? w[(int64_t)k * N + n] * scale : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int n = n0 + r, k = k0 + threadIdx.x;
+    if (n < N && k < K) {
+      __half hi, lo;
+      split_f16(tile[threadIdx.x][r], hi, lo);
+      wt_hi[(int64_t)n * K + k] = hi;
+      wt_lo[(int64_t)n * K + k] = lo;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(Fc4Tc::THREADS, 1)
+k_fc4_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+         const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, int64_t n, int K,
+         const float* __restrict__ bias, const float* __restrict__ inv_scale, float* __restrict__ out) {
+  using F = Fc4Tc;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte aligned operand ring (swizzle atoms need 512 B; 1024 keeps room for SWIZZLE_128B later)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F::STAGES * F::STAGE_BYTES);
+  uint64_t* full = bars;                 // [STAGES]  TMA -> MMA
+  uint64_t* empty = bars + F::STAGES;    // [STAGES]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * F::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * F::STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t site0 = (int64_t)blockIdx.x * F::BM;
+  const int nkb = K / F::BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
+    tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
+    for (int s = 0; s < F::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, F::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % F::STAGES;
+        const uint32_t ph = (kb / F::STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);  // first pass over the ring falls through
+        uint8_t* st = smem + s * F::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[s], F::STAGE_BYTES);
+        const int k0 = kb * F::BK;
+        tma_load_2d(st, &map_a_hi, &full[s], k0, (int)site0);
+        tma_load_2d(st + F::A_BYTES, &map_a_lo, &full[s], k0, (int)site0);
+        uint8_t* bh = st + 2 * F::A_BYTES;
+        uint8_t* bl = bh + F::B_BYTES;
+        tma_load_2d(bh, &map_b_hi, &full[s], k0, 0);
+        tma_load_2d(bh + F::B_BOX_ROWS * F::ROW_BYTES, &map_b_hi, &full[s], k0, F::B_BOX_ROWS);
+        tma_load_2d(bl, &map_b_lo, &full[s], k0, 0);
+        tma_load_2d(bl + F::B_BOX_ROWS * F::ROW_BYTES, &map_b_lo, &full[s], k0, F::B_BOX_ROWS);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc1 = umma_idesc_f16(F::BM, F::N1);
+      constexpr uint32_t idesc2 = umma_idesc_f16(F::BM, F::N2);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % F::STAGES;
+        const uint32_t ph = (kb / F::STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * F::STAGE_BYTES);
+        const uint32_t a_hi = st, a_lo = st + F::A_BYTES, b_hi = st + 2 * F::A_BYTES, b_lo = b_hi + F::B_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < F::BK / 16; ++ks) {
+          const uint32_t ko = ks * 32;  // 16 fp16 = 32 bytes along the swizzled row
+          const uint32_t first = (kb | ks) != 0;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t boff = half ? F::N1 * F::ROW_BYTES : 0;
+            const uint32_t tcol = tmem_base + (half ? F::N1 : 0);
+            const uint32_t idesc = half ? idesc2 : idesc1;
+            const uint64_t dah = umma_desc(a_hi + ko, 16, F::SBO, F::LAYOUT);
+            const uint64_t dal = umma_desc(a_lo + ko, 16, F::SBO, F::LAYOUT);
+            const uint64_t dbh = umma_desc(b_hi + boff + ko, 16, F::SBO, F::LAYOUT);
+            const uint64_t dbl = umma_desc(b_lo + boff + ko, 16, F::SBO, F::LAYOUT);
+            umma_f16(tcol, dah, dbh, idesc, first);
+            umma_f16(tcol, dah, dbl, idesc, 1u);
+            umma_f16(tcol, dal, dbh, idesc, 1u);
+          }
+        }
+        umma_commit(&empty[s]);  // smem slot reusable once these MMAs have read it
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    const int64_t site = site0 + row;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const float isc = inv_scale[0];
+    float* dst = out + site * F::N;
+#pragma unroll 1
+    for (int c = 0; c < F::N; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c, r);
+      tmem_ld_wait();
+      if (site < n) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(bias + c + j);
+          float4 v;
+          v.x = selu_f(fmaf(__uint_as_float(r[j + 0]), isc, bv.x));
+          v.y = selu_f(fmaf(__uint_as_float(r[j + 1]), isc, bv.y));
+          v.z = selu_f(fmaf(__uint_as_float(r[j + 2]), isc, bv.z));
+          v.w = selu_f(fmaf(__uint_as_float(r[j + 3]), isc, bv.w));
+          *reinterpret_cast<float4*>(dst + c + j) = v;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, F::TMEM_COLS);
+  }
+}
+
+}  // namespace tc
+}  // namespace cvb

@@ -10,6 +10,7 @@
 // p2 carries one zero row above and below the 26 pooled rows (conv3's SAME padding).
 #pragma once
 #include "conv_simt.cuh"
+#include "tc_common.cuh"
 
 namespace cvb {
 
@@ -226,10 +227,13 @@ __device__ __forceinline__ void conv_tile_load_async(float* __restrict__ buf, co
   }
 }
 
-template <class C, int POOL, int NTHREADS>
+// SPLIT = false: out is fp32 [n][HP][4*COUT].
+// SPLIT = true : out is reinterpreted as two fp16 tensors of the same shape, hi at out and lo at
+//                out_lo, with hi + lo ~= value (operands of the split-fp16 tensor-core FC4, fc4_tc.cuh).
+template <class C, int POOL, int NTHREADS, bool SPLIT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_conv_layer(const float* __restrict__ in, int64_t n, const float* __restrict__ wg, const float* __restrict__ bg,
-             float* __restrict__ out) {
+             float* __restrict__ out, void* __restrict__ out_lo) {
   using L = ConvLayerSmem<C, POOL>;
   static_assert(C::THREADS <= NTHREADS, "tile does not fit the CTA");
   extern __shared__ __align__(16) float smem[];
@@ -266,7 +270,16 @@ k_conv_layer(const float* __restrict__ in, int64_t n, const float* __restrict__ 
       float4 v = *reinterpret_cast<const float4*>(src);
 #pragma unroll
       for (int j = 1; j < POOL; ++j) v = max4(v, *reinterpret_cast<const float4*>(src + j * L::ORS));
-      *reinterpret_cast<float4*>(out + ((site0 + s) * L::HP + h) * (4 * C::COUT) + q * 4) = v;
+      const int64_t o = ((site0 + s) * L::HP + h) * (4 * C::COUT) + q * 4;
+      if constexpr (SPLIT) {
+        __half hi[4], lo[4];
+        tc::split_f16(v.x, hi[0], lo[0]); tc::split_f16(v.y, hi[1], lo[1]);
+        tc::split_f16(v.z, hi[2], lo[2]); tc::split_f16(v.w, hi[3], lo[3]);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + o) = *reinterpret_cast<const uint2*>(hi);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out_lo) + o) = *reinterpret_cast<const uint2*>(lo);
+      } else {
+        *reinterpret_cast<float4*>(out + o) = v;
+      }
     }
     __syncthreads();  // pooled reads done before the next-next tile load lands in `cur`
   }
