@@ -278,8 +278,8 @@ static int tc_setup(cvb_model* m) {
   __half* a_lo = a_hi + m->alloc_sites * K;
   if (make_map_f16(&m->map_a_hi, a_hi, (uint64_t)m->alloc_sites, K, F::BK, F::BM, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   if (make_map_f16(&m->map_a_lo, a_lo, (uint64_t)m->alloc_sites, K, F::BK, F::BM, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-  if (make_map_f16(&m->map_b_hi, m->d_w4t_hi, F::N, K, F::BK, F::B_BOX_ROWS, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-  if (make_map_f16(&m->map_b_lo, m->d_w4t_lo, F::N, K, F::BK, F::B_BOX_ROWS, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  if (make_map_f16(&m->map_b_hi, m->d_w4t_hi, F::N, K, F::BK, F::NH, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  if (make_map_f16(&m->map_b_lo, m->d_w4t_lo, F::N, K, F::BK, F::NH, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   CK(cudaFuncSetAttribute(tc::k_fc4_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
   m->tc_ready = true;
   m->tc_weights_dirty = true;
@@ -314,7 +314,7 @@ extern "C" int cvb_set_compute_mode(cvb_model* m, int mode) {
   CK(cudaSetDevice(m->device));
   if (mode == CVB_COMPUTE_FP16X3 && tc_setup(m)) return 1;
   m->compute_mode = mode;
-  m->CHUNK = (int64_t)m->num_sms * (m->variant == CVB_V3 ? (mode == CVB_COMPUTE_FP32 ? 96 : 128) : 224);
+  m->CHUNK = (int64_t)m->num_sms * (m->variant == CVB_V3 ? (mode == CVB_COMPUTE_FP32 ? 96 : 64) : 224);
   return 0;
 }
 extern "C" int64_t cvb_kernel_launches(const cvb_model* m) { return m ? m->launches : 0; }
@@ -387,7 +387,7 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
     }
     if (tensor) {
       using F = tc::Fc4Tc;
-      int grid = (int)((n + F::BM - 1) / F::BM);
+      dim3 grid((unsigned)((n + F::BM - 1) / F::BM), 2);
       tc::k_fc4_tc<<<grid, F::THREADS, F::SMEM_BYTES, st>>>(m->map_a_hi, m->map_a_lo, m->map_b_hi, m->map_b_lo, n, 4608,
                                                             m->var("fc4/bias"), m->d_inv_scale, m->d_h4);
       CK(cudaGetLastError());
@@ -468,7 +468,7 @@ extern "C" int cvb_predict_device(cvb_model* m, const float* x, int64_t n, float
 
 static int ensure_host_slots(cvb_model* m) {
   if (m->d_x[0]) return 0;
-  const int64_t CHUNK = m->CHUNK;
+  const int64_t CHUNK = m->alloc_sites;  // large enough for every compute mode's chunk
   for (int i = 0; i < 2; ++i) {
     CK(cudaMalloc(&m->d_x[i], (size_t)CHUNK * 528 * 4));
     CK(cudaMalloc(&m->d_out[i], (size_t)CHUNK * 16 * 4));
@@ -536,7 +536,7 @@ extern "C" int cvb_debug_read(cvb_model* m, int which, float* host, int64_t n) {
   const float* src = which == 0 ? m->d_p2 : which == 1 ? m->d_p3 : which == 2 ? m->d_h4 : nullptr;
   const int64_t per = which == 0 ? m->p2_site : which == 1 ? m->p3_site : m->h4_site;
   if (!src) return fail("cvb_debug_read: bad selector %d", which);
-  if (n < 0 || n > m->CHUNK * per) return fail("cvb_debug_read: n out of range");
+  if (n < 0 || n > m->alloc_sites * per) return fail("cvb_debug_read: n out of range");
   CK(cudaSetDevice(m->device));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(host, src, (size_t)n * 4, cudaMemcpyDeviceToHost));
