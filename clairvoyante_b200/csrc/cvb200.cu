@@ -13,6 +13,8 @@
 
 #include "fwd_simt.cuh"
 #include "fc4_tc.cuh"
+#include "conv3_tc.cuh"
+#include <stdlib.h>
 #include "train_simt.cuh"
 
 using namespace cvb;
@@ -72,6 +74,10 @@ struct cvb_model {
   float* d_inv_scale = nullptr;
   bool tc_ready = false, tc_weights_dirty = true;
   CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
+  // conv3 on tensor cores: B = rearranged conv3 weights [3*192][128], A = p2 hi/lo [sites*28][128]
+  __half *d_w3b_hi = nullptr, *d_w3b_lo = nullptr;
+  CUtensorMap map_c3a_hi, map_c3a_lo, map_c3b_hi, map_c3b_lo;
+  bool tc_conv3 = true;
   int64_t alloc_sites = 0;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;  // 5 per chunk: before front, after front, conv3, fc4, tail
@@ -176,6 +182,7 @@ extern "C" int cvb_destroy(cvb_model* m) {
   for (auto e : m->prof_events) cudaEventDestroy(e);
   cudaFree(m->d_params); cudaFree(m->d_m); cudaFree(m->d_v); cudaFree(m->d_grad);
   cudaFree(m->d_p2); cudaFree(m->d_p3); cudaFree(m->d_h4);
+  cudaFree(m->d_w3b_hi); cudaFree(m->d_w3b_lo);
   cudaFree(m->d_w4t_hi); cudaFree(m->d_w4t_lo); cudaFree(m->d_absmax); cudaFree(m->d_inv_scale);
   for (int i = 0; i < 2; ++i) {
     cudaFree(m->d_x[i]); cudaFree(m->d_out[i]); cudaFree(m->d_lg[i]);
@@ -281,6 +288,21 @@ static int tc_setup(cvb_model* m) {
   if (make_map_f16(&m->map_b_hi, m->d_w4t_hi, F::N, K, F::BK, F::NH, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   if (make_map_f16(&m->map_b_lo, m->d_w4t_lo, F::N, K, F::BK, F::NH, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   CK(cudaFuncSetAttribute(tc::k_fc4_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
+  {
+    using C = tc::Conv3Tc;
+    CK(cudaMalloc(&m->d_w3b_hi, (size_t)C::B_ROWS_TOTAL * C::KROW * 2));
+    CK(cudaMalloc(&m->d_w3b_lo, (size_t)C::B_ROWS_TOTAL * C::KROW * 2));
+    __half* p2_hi = reinterpret_cast<__half*>(m->d_p2);
+    __half* p2_lo = p2_hi + m->alloc_sites * (C::ROWS_PER_SITE * C::KROW);
+    const uint64_t rows = (uint64_t)m->alloc_sites * C::ROWS_PER_SITE;
+    if (make_map_f16(&m->map_c3a_hi, p2_hi, rows, C::KROW, C::BK, C::QROWS, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (make_map_f16(&m->map_c3a_lo, p2_lo, rows, C::KROW, C::BK, C::QROWS, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (make_map_f16(&m->map_c3b_hi, m->d_w3b_hi, C::B_ROWS_TOTAL, C::KROW, C::BK, 48, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (make_map_f16(&m->map_c3b_lo, m->d_w3b_lo, C::B_ROWS_TOTAL, C::KROW, C::BK, 48, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    CK(cudaFuncSetAttribute(tc::k_conv3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    const char* e = getenv("CVB_TC_CONV3");
+    m->tc_conv3 = !(e && e[0] == '0');
+  }
   m->tc_ready = true;
   m->tc_weights_dirty = true;
   return 0;
@@ -298,7 +320,14 @@ static int tc_refresh_weights(cvb_model* m, cudaStream_t st) {
   tc::k_prep_fc_weights<<<grid, block, 0, st>>>(m->var("fc4/kernel"), K, F::N, m->d_absmax, m->d_w4t_hi, m->d_w4t_lo,
                                                  m->d_inv_scale);
   CK(cudaGetLastError());
-  m->launches += 2;
+  // conv3: separate |w|max and scale (d_absmax[1], d_inv_scale[1])
+  CK(cudaMemsetAsync(m->d_absmax + 1, 0, 4, st));
+  tc::k_absmax<<<64, 256, 0, st>>>(m->var("conv3/kernel"), 3 * 4 * 32 * 48, m->d_absmax + 1);
+  CK(cudaGetLastError());
+  tc::k_prep_conv3_weights<<<(3 * 192 * 128 + 255) / 256, 256, 0, st>>>(m->var("conv3/kernel"), m->d_absmax + 1, m->d_w3b_hi,
+                                                                         m->d_w3b_lo, m->d_inv_scale + 1);
+  CK(cudaGetLastError());
+  m->launches += 4;
   m->tc_weights_dirty = false;
   return 0;
 }
@@ -313,6 +342,11 @@ extern "C" int cvb_set_compute_mode(cvb_model* m, int mode) {
     return fail("cvb_set_compute_mode: the tensor-core path is built for v3 only so far");
   CK(cudaSetDevice(m->device));
   if (mode == CVB_COMPUTE_FP16X3 && tc_setup(m)) return 1;
+  if (mode != m->compute_mode) {
+    // p2's zero padding rows sit at different byte offsets in the fp32 and the fp16 hi/lo layouts
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemset(m->d_p2, 0, (size_t)m->alloc_sites * m->p2_site * 4));
+  }
   m->compute_mode = mode;
   m->CHUNK = (int64_t)m->num_sms * (m->variant == CVB_V3 ? (mode == CVB_COMPUTE_FP32 ? 96 : 64) : 224);
   return 0;
@@ -358,12 +392,20 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
   if (m->variant == CVB_V3) {
     {
       using F = FrontV3<4>;
-      auto k = k_v3_front<4>;
-      CK(set_smem(k, F::SMEM_BYTES));
       int64_t tiles = (n + 3) / 4;
       int grid = (int)std::min<int64_t>(tiles, 2 * sms);
-      k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
-                                          m->var("conv2/bias"), m->d_p2);
+      if (tensor && m->tc_conv3) {
+        auto k = k_v3_front<4, true>;
+        CK(set_smem(k, F::SMEM_BYTES));
+        k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
+                                            m->var("conv2/bias"), m->d_p2,
+                                            reinterpret_cast<__half*>(m->d_p2) + m->alloc_sites * (28 * 128));
+      } else {
+        auto k = k_v3_front<4, false>;
+        CK(set_smem(k, F::SMEM_BYTES));
+        k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
+                                            m->var("conv2/bias"), m->d_p2, nullptr);
+      }
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
     }
@@ -372,7 +414,15 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       using L = ConvLayerSmem<C, 3>;
       int64_t tiles = (n + C::S - 1) / C::S;
       int grid = (int)std::min<int64_t>(tiles, sms);
-      if (tensor) {
+      if (tensor && m->tc_conv3) {
+        using T = tc::Conv3Tc;
+        const int64_t t3 = (n * T::ROWS_PER_SITE + T::TILE_STEP - 1) / T::TILE_STEP;
+        int g3 = (int)std::min<int64_t>(t3, sms);
+        __half* p3_hi = reinterpret_cast<__half*>(m->d_p3);
+        tc::k_conv3_tc<<<g3, T::THREADS, T::SMEM_BYTES, st>>>(m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo, n,
+                                                              m->var("conv3/bias"), m->d_inv_scale + 1, p3_hi,
+                                                              p3_hi + m->alloc_sites * 4608);
+      } else if (tensor) {
         auto k = k_conv_layer<C, 3, 256, true>;
         CK(set_smem(k, L::SMEM_BYTES));
         k<<<grid, 256, L::SMEM_BYTES, st>>>(m->d_p2, n, m->var("conv3/kernel"), m->var("conv3/bias"), m->d_p3,
@@ -533,6 +583,19 @@ extern "C" int cvb_predict_host(cvb_model* m, const float* x, int64_t n, float* 
 
 extern "C" int cvb_debug_read(cvb_model* m, int which, float* host, int64_t n) {
   if (!m || !host) return fail("cvb_debug_read: NULL argument");
+  if (which == 3 || which == 4) {  // fp16 hi/lo pair of p2 (3) / p3 (4) in tensor mode, recombined to fp32
+    const int64_t per3 = which == 3 ? m->p2_site : m->p3_site;
+    const __half* hi = reinterpret_cast<const __half*>(which == 3 ? m->d_p2 : m->d_p3);
+    const __half* lo = hi + m->alloc_sites * per3;
+    if (n < 0 || n > m->alloc_sites * per3) return fail("cvb_debug_read: n out of range");
+    std::vector<__half> h((size_t)n), l((size_t)n);
+    CK(cudaSetDevice(m->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h.data(), hi, (size_t)n * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(l.data(), lo, (size_t)n * 2, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; ++i) host[i] = __half2float(h[i]) + __half2float(l[i]);
+    return 0;
+  }
   const float* src = which == 0 ? m->d_p2 : which == 1 ? m->d_p3 : which == 2 ? m->d_h4 : nullptr;
   const int64_t per = which == 0 ? m->p2_site : which == 1 ? m->p3_site : m->h4_site;
   if (!src) return fail("cvb_debug_read: bad selector %d", which);

@@ -41,10 +41,13 @@ struct FrontV3 {
   static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
 };
 
-template <int S>
+// SPLIT = true: p2 is written as two fp16 tensors (hi at p2, lo at p2_lo), same [n][28][128] shape,
+// hi + lo ~= value: the A operand of the tensor-core conv3 (conv3_tc.cuh).
+template <int S, bool SPLIT>
 __global__ void __launch_bounds__(256, 2)
 k_v3_front(const float* __restrict__ x, int64_t n, const float* __restrict__ w1g, const float* __restrict__ b1g,
-           const float* __restrict__ w2g, const float* __restrict__ b2g, float* __restrict__ p2) {
+           const float* __restrict__ w2g, const float* __restrict__ b2g, float* __restrict__ p2,
+           void* __restrict__ p2_lo) {
   using F = FrontV3<S>;
   using C1 = typename F::C1;
   using C2 = typename F::C2;
@@ -117,7 +120,16 @@ k_v3_front(const float* __restrict__ x, int64_t n, const float* __restrict__ w1g
       float4 v = *reinterpret_cast<const float4*>(src);
 #pragma unroll
       for (int j = 1; j < 4; ++j) v = max4(v, *reinterpret_cast<const float4*>(src + j * F::C2S_RS));
-      *reinterpret_cast<float4*>(p2 + ((site0 + s) * 28 + 1 + h) * 128 + q * 4) = v;
+      const int64_t o = ((site0 + s) * 28 + 1 + h) * 128 + q * 4;
+      if constexpr (SPLIT) {
+        __half hi[4], lo[4];
+        tc::split_f16(v.x, hi[0], lo[0]); tc::split_f16(v.y, hi[1], lo[1]);
+        tc::split_f16(v.z, hi[2], lo[2]); tc::split_f16(v.w, hi[3], lo[3]);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p2) + o) = *reinterpret_cast<const uint2*>(hi);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p2_lo) + o) = *reinterpret_cast<const uint2*>(lo);
+      } else {
+        *reinterpret_cast<float4*>(p2 + o) = v;
+      }
     }
   }
 }

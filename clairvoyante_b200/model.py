@@ -214,9 +214,10 @@ class ClairvoyanteBase(object):
 
     def debugRead(self, which, n_sites):
         """Intermediate of the last device pass: 'p2' | 'p3' | 'h4' (test aid)."""
-        per = {"v3": dict(p2=28 * 128, p3=4608, h4=336), "v3_slim": dict(p2=37 * 64, p3=4224, h4=36)}[self.VARIANT][which]
+        per = {"v3": dict(p2=28 * 128, p3=4608, h4=336), "v3_slim": dict(p2=37 * 64, p3=4224, h4=36)}[self.VARIANT][which.split("_")[0]]
         a = np.empty((n_sites, per), np.float32)
-        _lib.check(self._lib.cvb_debug_read(self._h, dict(p2=0, p3=1, h4=2)[which], a.ctypes.data, a.size))
+        sel = dict(p2=0, p3=1, h4=2, p2_split=3, p3_split=4)[which]
+        _lib.check(self._lib.cvb_debug_read(self._h, sel, a.ctypes.data, a.size))
         return a
 
     def profileBegin(self):

@@ -21,6 +21,15 @@ m.setComputeMode("fp16x3")
 try:
     otc, ltc = m.predictLogits(x)
     h4_tc = m.debugRead("h4", n)
+    L = ref["layers"]
+    if os.environ.get("CVB_TC_CONV3", "1") != "0":
+        p2s = m.debugRead("p2_split", n).reshape(n, 28, 4, 32)
+        print("   p2 split err %.3g pad rows zero %s" % (np.abs(p2s[:, 1:27] - L["pool2"]).max(), bool((p2s[:, 0] == 0).all() and (p2s[:, 27] == 0).all())))
+    p3s = m.debugRead("p3_split", n).reshape(n, 24, 4, 48)
+    e3 = np.abs(p3s - L["pool3"])
+    print("   p3 split err %.3g (mean %.3g); by h: %s" % (e3.max(), e3.mean(), np.round(e3.max((0, 2, 3)), 4)))
+    print("      by w: %s ; by site%%8: %s" % (np.round(e3.max((0, 1, 3)), 4), np.round([e3[i::8].max() for i in range(8)], 4)))
+    np.savez_compressed("gpurun_out/tc_probe_p3.npz", p3s=p3s, ref=L["pool3"])
     e = np.abs(h4_tc - ref["layers"]["fc4"])
     print("fp16x3 : h4 err %.3g (mean %.3g) logit err %.3g ; vs fp32-simt h4 %.3g" % (e.max(), e.mean(), np.abs(ltc - ref["logits"]).max(), np.abs(h4_tc - h4_32).max()))
     print("   err by column block of 16:", np.round(e.max(0).reshape(21, 16).max(1), 4))
