@@ -191,6 +191,9 @@ def main():
     ap.add_argument("--sites", type=int, default=4 * 1024 * 1024, help="sites per GPU per step")
     ap.add_argument("--e2e-sites", type=int, default=None, help="sites per GPU per e2e step (default: --sites)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--compute", default="auto", choices=["auto", "fp32", "fp16x3"],
+                    help="arithmetic path: fp16x3 = conv3/FC4 on tcgen05 with split-fp16 operands + fp32 accumulate "
+                         "(fp32-equivalent, logits within 1e-3 of fp64); fp32 = all-SIMT fp32")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -225,7 +228,10 @@ def main():
         from clairvoyante_b200 import clairvoyante_v3_slim as cv
     W = initializers.init_weights(args.variant, seed=0)
     m = cv.Clairvoyante(device=local)
+    if args.compute != "auto":
+        m.setComputeMode(args.compute)
     m.setWeights(W)
+    tensor = m.computeMode == "fp16x3"
 
     # ---- synthetic inputs: 65,536 unique seeded sites (rank-distinct), tiled to --sites in HBM
     n = args.sites
@@ -273,9 +279,18 @@ def main():
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(args.variant, {}).get(dom)
     sites_per_launch = 2 * n / max(kern[dom]["launches"], 1)
-    roofline = dict(kernel=dom, bound="fp32_fma", achieved=kern[dom]["tflops"], peak=FP32_NOMINAL_TFLOPS, unit="TFLOP/s",
-                    frac=kern[dom]["tflops"] / FP32_NOMINAL_TFLOPS,
-                    peak_source="nominal fp32 FMA (148 SM x 128 lanes x 2 x 1.965 GHz); MEASURED_PEAKS.json has no fp32-SIMT figure",
+    on_tensor = tensor and dom in ("conv3", "fc4")
+    if on_tensor:
+        # the kernel issues 3 fp16 MMAs per algorithmic fp32 MAC (split operands); achieved counts ALGORITHMIC flops
+        r_bound, r_peak = "tensor", pk["bf16_tflops"]
+        r_src = "%s bf16 dense GEMM; this kernel issues 3x the algorithmic flops as fp16 tcgen05.mma (split-fp16)" % pk["source"]
+    else:
+        r_bound, r_peak = "fp32_fma", FP32_NOMINAL_TFLOPS
+        r_src = "nominal fp32 FMA (148 SM x 128 lanes x 2 x 1.965 GHz); MEASURED_PEAKS.json has no fp32-SIMT figure"
+    for k in kern:
+        kern[k]["pipe"] = "tcgen05 (3x split-fp16)" if (tensor and k in ("conv3", "fc4")) else "fp32 SIMT"
+    roofline = dict(kernel=dom, bound=r_bound, achieved=kern[dom]["tflops"], peak=r_peak, unit="TFLOP/s",
+                    frac=kern[dom]["tflops"] / r_peak, peak_source=r_src,
                     algorithmic_flops_per_launch=fl[dom] * sites_per_launch, ms_per_launch=kern[dom]["ms_per_launch"],
                     traffic=traffic, kernels=kern,
                     whole_pass=dict(tflops=value / world * fl["total"] / 1e12, frac_fp32_nominal=value / world * fl["total"] / 1e12 / FP32_NOMINAL_TFLOPS),
@@ -315,12 +330,15 @@ def main():
                           % (nsamp, thr))
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit="sites/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f32 (3x split-fp16 on tcgen05, f32 accumulate)" if tensor else "f32",
                     data="synthetic",
                     config=dict(workload="configs[1]: 4M synthetic (33,4,4) candidate sites, clairvoyante_%s forward, fp32" % args.variant,
                                 sites_per_gpu_per_step=n, unique_sites=pool_n, parallelism="site-list sharding, no collective",
                                 l2="inputs (%.2f GB/GPU) exceed the 126 MB L2; no flush needed" % (n * 2112 / 1e9),
-                                weights="reference initialisers, seed 0", compute_mode="fp32 SIMT"),
+                                weights="reference initialisers, seed 0",
+                                compute_mode=("fp32-equivalent: conv3+FC4 on tcgen05 with 3x split-fp16 operands and fp32 "
+                                              "accumulate, rest fp32 SIMT" if tensor else "fp32 SIMT")),
                     clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu, checksum=checksum)
         print(json.dumps(line))
     m.close()

@@ -74,6 +74,13 @@ class ClairvoyanteBase(object):
         h = ctypes.c_void_p()
         _lib.check(self._lib.cvb_create(_VARIANT_ID[self.VARIANT], self.device, ctypes.byref(h)))
         self._h = h
+        # arithmetic mode: v3 defaults to the tensor-core path (split-fp16 operands, fp32 accumulate,
+        # logits within 1e-3 of fp64); CVB_COMPUTE=fp32 selects the all-SIMT fp32 kernels.
+        mode = os.environ.get("CVB_COMPUTE", "auto")
+        if mode == "auto":
+            mode = "fp16x3" if self.VARIANT == "v3" else "fp32"
+        self.computeMode = None
+        self.setComputeMode(mode)
         self._dropout_calls = 0
         self._seed = int.from_bytes(os.urandom(8), "little")   # reference dropout is unseeded (selu.py:55)
 
@@ -130,6 +137,7 @@ class ClairvoyanteBase(object):
 
     def setComputeMode(self, mode):
         _lib.check(self._lib.cvb_set_compute_mode(self._h, COMPUTE_MODES[mode]))
+        self.computeMode = mode
 
     @staticmethod
     def _ckpt_path(fn):

@@ -18,20 +18,26 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 TOL = 1e-3
 
 
-def _model(variant, W, **kw):
+# (variant, compute mode): every parity test runs on each arithmetic path the library ships
+CASES = [("v3", "fp16x3"), ("v3", "fp32"), ("v3_slim", "fp32")]
+
+
+def _model(variant, W, mode=None, **kw):
     if variant == "v3":
         from clairvoyante_b200 import clairvoyante_v3 as cv
     else:
         from clairvoyante_b200 import clairvoyante_v3_slim as cv
     m = cv.Clairvoyante(**kw)
+    if mode is not None:
+        m.setComputeMode(mode)
     m.setWeights(W)
     return m
 
 
-def _check(variant, W, x, m=None, tol=TOL):
+def _check(variant, W, x, m=None, tol=TOL, mode=None):
     own = m is None
     if own:
-        m = _model(variant, W)
+        m = _model(variant, W, mode)
     out16, lg = m.predictLogits(x)
     ref = O.forward(W, x, variant)
     r16 = O.out16(ref)
@@ -55,35 +61,42 @@ def _check(variant, W, x, m=None, tol=TOL):
         m.close()
 
 
-@pytest.mark.parametrize("variant", ["v3", "v3_slim"])
-def test_golden_fixture(variant):
+def test_default_mode_is_tensor_path_for_v3():
+    m = _model("v3", I.init_weights("v3", 0))
+    assert m.computeMode == "fp16x3"
+    m.close()
+
+
+@pytest.mark.parametrize("variant,mode", CASES)
+def test_golden_fixture(variant, mode):
     d = np.load(os.path.join(GOLD, "forward_%s.npz" % variant))
     W = I.init_weights(variant, int(d["weight_seed"]))
     x = synth.make_sites(int(d["n"]), int(d["data_seed"]))
-    m = _model(variant, W)
+    m = _model(variant, W, mode)
     out16, lg = m.predictLogits(x)
     assert np.abs(lg - d["logits"]).max() <= TOL
     assert np.abs(out16 - d["out16"]).max() <= 2e-4
     m.close()
 
 
-@pytest.mark.parametrize("variant", ["v3", "v3_slim"])
-@pytest.mark.parametrize("n", [0, 1, 2, 3, 5, 95, 96, 97, 999, 1000, 1001])
-def test_edge_batch_sizes(variant, n):
-    # N=0 is legal (utils_v2.py:56-59); 999/1000/1001 straddle predictBatchSize (param.py:12)
+@pytest.mark.parametrize("variant,mode", CASES)
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 5, 95, 96, 97, 127, 128, 129, 999, 1000, 1001])
+def test_edge_batch_sizes(variant, mode, n):
+    # N=0 is legal (utils_v2.py:56-59); 999/1000/1001 straddle predictBatchSize (param.py:12);
+    # 95..129 straddle the kernels' site tiles (96 fp32 FC4, 128 tensor FC4)
     W = I.init_weights(variant, 1)
-    _check(variant, W, synth.make_sites(n, 3))
+    _check(variant, W, synth.make_sites(n, 3), mode=mode)
 
 
-@pytest.mark.parametrize("variant", ["v3", "v3_slim"])
-def test_multi_chunk_and_pinned_paths(variant):
+@pytest.mark.parametrize("variant,mode", CASES)
+def test_multi_chunk_and_pinned_paths(variant, mode):
     """> 1 internal chunk (14208 sites on a 148-SM part), pageable and pinned host input, device-resident input:
     all three routes must give identical bits, and shards must equal the whole."""
     import torch
     W = I.init_weights(variant, 2)
     n = 14208 * 2 + 777
     x = synth.make_sites(n, 4)
-    m = _model(variant, W)
+    m = _model(variant, W, mode)
     o_page, l_page = m.predictLogits(x)
     xp = torch.from_numpy(x).pin_memory()
     o_pin, l_pin = m.predictLogits(xp.numpy())
@@ -96,7 +109,7 @@ def test_multi_chunk_and_pinned_paths(variant):
     torch.cuda.synchronize()
     assert np.array_equal(od.cpu().numpy(), o_page) and np.array_equal(ld.cpu().numpy(), l_page)
     # oracle on a sample (fp64 NumPy on 33k sites would take a while)
-    idx = np.r_[0:64, 14208 - 32:14208 + 32, n - 64:n]
+    idx = np.r_[0:64, 9472 - 32:9472 + 32, 14208 - 32:14208 + 32, n - 64:n]
     ref = O.forward(W, x[idx], variant)
     assert np.abs(l_page[idx] - ref["logits"]).max() <= TOL
     # sharding: contiguous site ranges concatenated in order == single pass
@@ -105,7 +118,8 @@ def test_multi_chunk_and_pinned_paths(variant):
     m.close()
 
 
-def test_extreme_inputs_v3():
+@pytest.mark.parametrize("mode", ["fp16x3", "fp32"])
+def test_extreme_inputs_v3(mode):
     """all-zero tensors, maximum depth (dcov cap 250, CreateTensor.py:296) and negative-heavy tensors"""
     W = I.init_weights("v3", 5)
     x = np.zeros((40, 33, 4, 4), np.float32)
@@ -113,7 +127,7 @@ def test_extreme_inputs_v3():
     x[20:30, :, :, 1:4] = -250.0
     x[30:40] = synth.make_sites(10, 9) * 3.0
     ref = O.forward(W, x, "v3")
-    m = _model("v3", W)
+    m = _model("v3", W, mode)
     out16, lg = m.predictLogits(x)
     scale = max(1.0, np.abs(ref["logits"]).max() / 100.0)    # tolerance is quoted at |logit| ~ 1e2
     assert np.abs(lg - ref["logits"]).max() <= TOL * scale
@@ -121,20 +135,51 @@ def test_extreme_inputs_v3():
     m.close()
 
 
-def test_stage_intermediates_v3():
+@pytest.mark.parametrize("mode", ["fp16x3", "fp32"])
+def test_stage_intermediates_v3(mode):
     """conv stack and FC4 outputs individually against the oracle's layers"""
     W = I.init_weights("v3", 6)
-    x = synth.make_sites(50, 8)
-    m = _model("v3", W)
+    x = synth.make_sites(300, 8)          # > 2 tensor-core M-tiles of 128 rows / 120 conv3 rows
+    m = _model("v3", W, mode)
     m.predictLogits(x)
     L = O.forward(W, x, "v3", return_all=True)["layers"]
-    p2 = m.debugRead("p2", 50).reshape(50, 28, 4, 32)
+    sfx = "_split" if mode == "fp16x3" else ""
+    p2 = m.debugRead("p2" + sfx, 300).reshape(300, 28, 4, 32)
     assert (p2[:, 0] == 0).all() and (p2[:, 27] == 0).all()
     assert np.abs(p2[:, 1:27] - L["pool2"]).max() <= 2e-4
-    p3 = m.debugRead("p3", 50).reshape(50, 24, 4, 48)
+    p3 = m.debugRead("p3" + sfx, 300).reshape(300, 24, 4, 48)
     assert np.abs(p3 - L["pool3"]).max() <= 3e-4
-    h4 = m.debugRead("h4", 50)
+    h4 = m.debugRead("h4", 300)
     assert np.abs(h4 - L["fc4"]).max() <= 5e-4
+    m.close()
+
+
+def test_mode_switch_back_and_forth():
+    """the fp32 and fp16 hi/lo layouts alias the same buffers: switching must not leak stale padding rows"""
+    W = I.init_weights("v3", 8)
+    x = synth.make_sites(500, 9)
+    ref = O.forward(W, x, "v3")["logits"]
+    m = _model("v3", W, "fp32")
+    for mode in ("fp16x3", "fp32", "fp16x3"):
+        m.setComputeMode(mode)
+        assert np.abs(m.predictLogits(x)[1] - ref).max() <= TOL
+    m.close()
+
+
+def test_tensor_path_tracks_weight_updates():
+    """the split fp16 weight copies are rebuilt whenever the fp32 master changes"""
+    Wa, Wb = I.init_weights("v3", 1), I.init_weights("v3", 2)
+    x = synth.make_sites(200, 5)
+    m = _model("v3", Wa, "fp16x3")
+    la = m.predictLogits(x)[1]
+    m.setWeights(Wb)
+    lb = m.predictLogits(x)[1]
+    assert np.abs(la - O.forward(Wa, x, "v3")["logits"]).max() <= TOL
+    assert np.abs(lb - O.forward(Wb, x, "v3")["logits"]).max() <= TOL
+    big = {k: (v * 40.0 if k in ("fc4/kernel", "conv3/kernel") else v) for k, v in Wa.items()}   # different power-of-two pre-scale
+    m.setWeights(big)
+    ref = O.forward(big, x, "v3")["logits"]
+    assert np.abs(m.predictLogits(x)[1] - ref).max() <= TOL * max(1.0, np.abs(ref).max() / 100.0)
     m.close()
 
 
