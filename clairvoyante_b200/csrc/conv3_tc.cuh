@@ -14,11 +14,11 @@
 // quadrant's epilogue warp and each tile owns 120 output rows.  Rows whose in-site index is >= 26
 // (>= 24 after pooling) mix two sites and are simply not stored (26/28 useful).
 //
-// Persistent CTAs (one per SM), warp roles (320 threads):
+// Persistent CTAs (one per SM), warp roles (576 threads):
 //   warp 0    : TMA producer   -- 12 stages per tile (kh x w'): 4 quadrant boxes of A_hi/A_lo (32 rows x 64 B)
 //                                  and N/48 boxes of B_hi/B_lo (48 rows x 64 B), 64-byte swizzle, 4-stage ring
 //   warp 1    : MMA issuer     -- per stage 2 K-steps x 3 split terms, D in one of two TMEM buffers (192 columns)
-//   warps 2-9 : epilogue       -- tcgen05.ld (row per thread, 96 columns per warp), descale, + bias, SELU,
+//   warps 2-17: epilogue       -- tcgen05.ld (row per thread, 48 columns per warp), descale, + bias, SELU,
 //                                  shuffle max-pool, fp16 hi/lo split, store p3 [site][24*192] for FC4
 // K per output is 384 -> 72 accumulate steps: the round-toward-zero accumulation bias (fc4_tc.cuh) stays < 1e-6
 // relative, so no K-chunking is needed here.
@@ -37,7 +37,8 @@ struct Conv3Tc {
   static constexpr int B_BYTES = NOUT * ROW_BYTES;             // 12288 per hi|lo (max N)
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 40960
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr int THREADS = 320;
+  static constexpr int EPI_WARPS = 16;                          // 4 per TMEM lane quadrant, 48 columns each
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int TMEM_COLS = 512;
   static constexpr uint32_t SBO = 8 * ROW_BYTES, LAYOUT = 4;   // SWIZZLE_64B
   static constexpr int B_ROWS_TOTAL = 3 * NOUT;                // B tensor rows: [kh][w][co]
@@ -85,6 +86,8 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
+  __shared__ float bias_s[F::COUT];
+  if (threadIdx.x < F::COUT) bias_s[threadIdx.x] = bias[threadIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t total_rows = n * F::ROWS_PER_SITE;
   const int64_t ntiles = (total_rows + F::TILE_STEP - 1) / F::TILE_STEP;
@@ -93,7 +96,7 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
     tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
     tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
     for (int s = 0; s < F::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], F::EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, F::TMEM_COLS);
@@ -171,9 +174,9 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue (warps 2..17) =====================
     const int q = warp & 3;             // TMEM lane quadrant
-    const int chalf = (warp - 2) >> 2;  // column half: 0 -> [0,96), 1 -> [96,192)
+    const int wblk = (warp - 2) >> 2;   // output column block w (48 channels) owned by this warp
     const float isc = inv_scale[0];
     uint32_t tcount = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
@@ -182,33 +185,31 @@ k_conv3_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__
       const int64_t site = r / F::ROWS_PER_SITE;
       const int hs = (int)(r - site * F::ROWS_PER_SITE);
       const bool store = lane < F::QSTEP && hs < F::HPOOL && site < n;
-      __half* dhi = out_hi + site * (F::HPOOL * F::NOUT) + hs * F::NOUT;
-      __half* dlo = out_lo + site * (F::HPOOL * F::NOUT) + hs * F::NOUT;
+      __half* dhi = out_hi + site * (F::HPOOL * F::NOUT) + hs * F::NOUT + wblk * F::COUT;
+      __half* dlo = out_lo + site * (F::HPOOL * F::NOUT) + hs * F::NOUT + wblk * F::COUT;
       mbar_wait(&acc_full[buf], (tcount >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + chalf * 96;
-#pragma unroll 1
-      for (int cc = 0; cc < 96; cc += 16) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + wblk * F::COUT;
+#pragma unroll
+      for (int cc = 0; cc < F::COUT; cc += 16) {
         uint32_t rr[16];
         tmem_ld16(taddr + cc, rr);
         tmem_ld_wait();
-        const int col = chalf * 96 + cc;  // 16 columns never straddle a 48-channel block
-        const float* bp = bias + (col % 48);
         __align__(16) __half hi[16];
         __align__(16) __half lo[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float v = selu_f(fmaf(__uint_as_float(rr[j]), isc, bp[j]));
+          float v = selu_f(fmaf(__uint_as_float(rr[j]), isc, bias_s[cc + j]));
           const float v1 = __shfl_down_sync(0xffffffffu, v, 1);
           const float v2 = __shfl_down_sync(0xffffffffu, v, 2);
           v = fmaxf(v, fmaxf(v1, v2));  // pool3 (3,1) over rows r, r+1, r+2
           split_f16(v, hi[j], lo[j]);
         }
         if (store) {
-          *reinterpret_cast<uint4*>(dhi + col) = *reinterpret_cast<const uint4*>(hi);
-          *reinterpret_cast<uint4*>(dhi + col + 8) = *reinterpret_cast<const uint4*>(hi + 8);
-          *reinterpret_cast<uint4*>(dlo + col) = *reinterpret_cast<const uint4*>(lo);
-          *reinterpret_cast<uint4*>(dlo + col + 8) = *reinterpret_cast<const uint4*>(lo + 8);
+          *reinterpret_cast<uint4*>(dhi + cc) = *reinterpret_cast<const uint4*>(hi);
+          *reinterpret_cast<uint4*>(dhi + cc + 8) = *reinterpret_cast<const uint4*>(hi + 8);
+          *reinterpret_cast<uint4*>(dlo + cc) = *reinterpret_cast<const uint4*>(lo);
+          *reinterpret_cast<uint4*>(dlo + cc + 8) = *reinterpret_cast<const uint4*>(lo + 8);
         }
       }
       tc_fence_before();

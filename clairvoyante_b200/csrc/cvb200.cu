@@ -15,6 +15,7 @@
 #include "fc4_tc.cuh"
 #include "conv3_tc.cuh"
 #include <stdlib.h>
+#include <sys/mman.h>
 #include "train_simt.cuh"
 
 using namespace cvb;
@@ -59,7 +60,7 @@ struct cvb_model {
   int64_t nparams = 0, step = 0;
   float *d_params = nullptr, *d_m = nullptr, *d_v = nullptr, *d_grad = nullptr;
   // forward work buffers
-  float *d_p2 = nullptr, *d_p3 = nullptr, *d_h4 = nullptr;
+  float *d_p2 = nullptr, *d_p3 = nullptr, *d_h4 = nullptr, *d_h5 = nullptr;
   int64_t p2_site = 0, p3_site = 0, h4_site = 0;
   // host path: 2 slots
   float *d_x[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr}, *d_lg[2] = {nullptr, nullptr};
@@ -161,6 +162,7 @@ extern "C" int cvb_create(int variant, int device, cvb_model** out) {
   CK(cudaMalloc(&m->d_p2, (size_t)CHUNK * m->p2_site * 4)); CK(cudaMemset(m->d_p2, 0, (size_t)CHUNK * m->p2_site * 4));
   CK(cudaMalloc(&m->d_p3, (size_t)CHUNK * m->p3_site * 4));
   CK(cudaMalloc(&m->d_h4, (size_t)CHUNK * m->h4_site * 4));
+  CK(cudaMalloc(&m->d_h5, (size_t)CHUNK * 168 * 4));
   CK(cudaStreamCreateWithFlags(&m->s_comp, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&m->s_h2d, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking));
@@ -181,7 +183,7 @@ extern "C" int cvb_destroy(cvb_model* m) {
   train_work_free(m->train);
   for (auto e : m->prof_events) cudaEventDestroy(e);
   cudaFree(m->d_params); cudaFree(m->d_m); cudaFree(m->d_v); cudaFree(m->d_grad);
-  cudaFree(m->d_p2); cudaFree(m->d_p3); cudaFree(m->d_h4);
+  cudaFree(m->d_p2); cudaFree(m->d_p3); cudaFree(m->d_h4); cudaFree(m->d_h5);
   cudaFree(m->d_w3b_hi); cudaFree(m->d_w3b_lo);
   cudaFree(m->d_w4t_hi); cudaFree(m->d_w4t_lo); cudaFree(m->d_absmax); cudaFree(m->d_inv_scale);
   for (int i = 0; i < 2; ++i) {
@@ -348,7 +350,7 @@ extern "C" int cvb_set_compute_mode(cvb_model* m, int mode) {
     CK(cudaMemset(m->d_p2, 0, (size_t)m->alloc_sites * m->p2_site * 4));
   }
   m->compute_mode = mode;
-  m->CHUNK = (int64_t)m->num_sms * (m->variant == CVB_V3 ? (mode == CVB_COMPUTE_FP32 ? 96 : 64) : 224);
+  m->CHUNK = (int64_t)m->num_sms * (m->variant == CVB_V3 ? (mode == CVB_COMPUTE_FP32 ? 96 : 128) : 224);
   return 0;
 }
 extern "C" int64_t cvb_kernel_launches(const cvb_model* m) { return m ? m->launches : 0; }
@@ -452,12 +454,17 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       if (prof_mark(m, st)) return 1;
     }
     {
-      int grid = (int)((n + 15) / 16);
-      k_tail<336, 168, 16><<<grid, 256, 0, st>>>(m->d_h4, n, head_ptrs(m), out16, logits16);
+      using F5 = FcCfg<168, 21, 8, 12, 8>;  // FC5: h5 = SELU(h4 @ W5 + b5), same SGEMM as the fp32 FC4
+      auto k = k_fc4<F5>;
+      CK(set_smem(k, F5::SMEM_BYTES));
+      int grid = (int)((n + F5::M - 1) / F5::M);
+      k<<<grid, 256, F5::SMEM_BYTES, st>>>(m->d_h4, n, 336, m->var("fc5/kernel"), m->var("fc5/bias"), m->d_h5);
+      CK(cudaGetLastError());
+      k_heads<336, 168><<<(int)((n + 15) / 16), 256, 0, st>>>(m->d_h4, m->d_h5, n, head_ptrs(m), out16, logits16);
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
     }
-    m->launches += 4;
+    m->launches += 5;
   } else {
     {
       using F = FrontSlim<6>;
@@ -536,13 +543,26 @@ static bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-extern "C" int cvb_predict_host(cvb_model* m, const float* x, int64_t n, float* out16, float* logits16) {
+// Large fresh output arrays cost one page fault per 4 KB on first touch; ask for 2 MB pages.
+static void advise_hugepages(void* p, size_t bytes) {
+  const uintptr_t a = ((uintptr_t)p + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1);
+  const uintptr_t e = ((uintptr_t)p + bytes) & ~(uintptr_t)((2u << 20) - 1);
+  if (e > a) madvise((void*)a, e - a, MADV_HUGEPAGE);
+}
+
+extern "C" int cvb_predict_host(cvb_model* m, const float* x, int64_t n, float* base, float* zygosity, float* var_type,
+                                float* indel_length, float* logits16) {
   if (!m) return fail("cvb_predict_host: NULL model");
   if (n < 0) return fail("cvb_predict_host: negative n");
   if (n == 0) return 0;
-  if (!x || !out16) return fail("cvb_predict_host: NULL buffer");
+  if (!x || !base || !zygosity || !var_type || !indel_length) return fail("cvb_predict_host: NULL buffer");
   CK(cudaSetDevice(m->device));
   if (ensure_host_slots(m)) return 1;
+  if (n >= (1 << 18)) {
+    advise_hugepages(base, (size_t)n * 16); advise_hugepages(zygosity, (size_t)n * 8);
+    advise_hugepages(var_type, (size_t)n * 16); advise_hugepages(indel_length, (size_t)n * 24);
+    if (logits16) advise_hugepages(logits16, (size_t)n * 64);
+  }
   const bool pinned_in = is_pinned(x);
   const int64_t CHUNK = m->CHUNK;
   const int64_t nchunks = (n + CHUNK - 1) / CHUNK;
@@ -574,7 +594,12 @@ extern "C" int cvb_predict_host(cvb_model* m, const float* x, int64_t n, float* 
       const int sl = (int)(p & 1);
       const int64_t s0 = p * CHUNK, cn = std::min<int64_t>(CHUNK, n - s0);
       CK(cudaEventSynchronize(m->e_d2h[sl]));
-      memcpy(out16 + s0 * 16, m->h_out[sl], (size_t)cn * 64);
+      // de-interleave [base4 | zyg2 | type4 | len6] into the four arrays the reference's predict() returns
+      const float* o = m->h_out[sl];
+      float* pb = base + s0 * 4; float* pz = zygosity + s0 * 2; float* pt = var_type + s0 * 4; float* pl = indel_length + s0 * 6;
+      for (int64_t i = 0; i < cn; ++i, o += 16, pb += 4, pz += 2, pt += 4, pl += 6) {
+        memcpy(pb, o, 16); memcpy(pz, o + 4, 8); memcpy(pt, o + 6, 16); memcpy(pl, o + 10, 24);
+      }
       if (logits16) memcpy(logits16 + s0 * 16, m->h_lg[sl], (size_t)cn * 64);
     }
   }

@@ -416,6 +416,88 @@ struct HeadPtrs {
   const float *w5, *b5, *wb, *bb, *wz, *bz, *wt, *bt, *wl, *bl;
 };
 
+// ------------------------------------------------------------------------------------
+// k_heads (clairvoyante_v3.py:124-137): the four output heads + sigmoid / softmax.
+//   base  = sigmoid(h4 . Wb + bb)              (input is the FC4 branch, :125)
+//   zyg/type/len = softmax(SELU(h5 . W + b) + 1e-10)
+// FC5 itself runs through k_fc4<FcCfg<N5,...>> (same SGEMM, A = h4, K = N4).
+// One thread per (site, output): 16 threads per site, 16 sites per CTA.
+// ------------------------------------------------------------------------------------
+template <int N4, int N5>
+__global__ void __launch_bounds__(256)
+k_heads(const float* __restrict__ h4, const float* __restrict__ h5, int64_t n, HeadPtrs hp, float* __restrict__ out16,
+        float* __restrict__ logits16) {
+  __shared__ float lg[16 * 16];
+  const int tid = threadIdx.x;
+  const int s = tid >> 4, o = tid & 15;
+  const int64_t site = (int64_t)blockIdx.x * 16 + s;
+  float acc = 0.f;
+  if (site < n) {
+    if (o < 4) {
+      const float4* a = reinterpret_cast<const float4*>(h4 + site * N4);
+#pragma unroll 4
+      for (int k = 0; k < N4 / 4; ++k) {
+        const float4 v = a[k];
+        acc = fmaf(v.x, hp.wb[(4 * k + 0) * 4 + o], acc);
+        acc = fmaf(v.y, hp.wb[(4 * k + 1) * 4 + o], acc);
+        acc = fmaf(v.z, hp.wb[(4 * k + 2) * 4 + o], acc);
+        acc = fmaf(v.w, hp.wb[(4 * k + 3) * 4 + o], acc);
+      }
+      acc += hp.bb[o];
+    } else {
+      const float* w;
+      int ld, col;
+      float b;
+      if (o < 6) { w = hp.wz; ld = 2; col = o - 4; b = hp.bz[col]; }
+      else if (o < 10) { w = hp.wt; ld = 4; col = o - 6; b = hp.bt[col]; }
+      else { w = hp.wl; ld = 6; col = o - 10; b = hp.bl[col]; }
+      const float* a = h5 + site * N5;
+      if constexpr (N5 % 4 == 0) {
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+#pragma unroll 4
+        for (int k = 0; k < N5 / 4; ++k) {
+          const float4 v = a4[k];
+          acc = fmaf(v.x, w[(4 * k + 0) * ld + col], acc);
+          acc = fmaf(v.y, w[(4 * k + 1) * ld + col], acc);
+          acc = fmaf(v.z, w[(4 * k + 2) * ld + col], acc);
+          acc = fmaf(v.w, w[(4 * k + 3) * ld + col], acc);
+        }
+      } else {
+        for (int k = 0; k < N5; ++k) acc = fmaf(a[k], w[k * ld + col], acc);
+      }
+      acc = selu_f(acc + b) + 1e-10f;  // clairvoyante_v3.py:127-128
+    }
+  }
+  lg[tid] = acc;
+  __syncthreads();
+  if (tid < 16) {
+    const int64_t st = (int64_t)blockIdx.x * 16 + tid;
+    if (st < n) {
+      const float* l = lg + tid * 16;
+      float ov[16];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ov[k] = 1.f / (1.f + __expf(-l[k]));
+      auto sm = [&](int a, int b) {
+        float m = l[a];
+        for (int k = a + 1; k < b; ++k) m = fmaxf(m, l[k]);
+        float sum = 0.f;
+        for (int k = a; k < b; ++k) { ov[k] = __expf(l[k] - m); sum += ov[k]; }
+        const float inv = 1.f / sum;
+        for (int k = a; k < b; ++k) ov[k] *= inv;
+      };
+      sm(4, 6); sm(6, 10); sm(10, 16);
+      float4* d = reinterpret_cast<float4*>(out16 + st * 16);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d[k] = make_float4(ov[4 * k], ov[4 * k + 1], ov[4 * k + 2], ov[4 * k + 3]);
+      if (logits16) {
+        float4* dl = reinterpret_cast<float4*>(logits16 + st * 16);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dl[k] = make_float4(l[4 * k], l[4 * k + 1], l[4 * k + 2], l[4 * k + 3]);
+      }
+    }
+  }
+}
+
 template <int N4, int N5, int TS>
 __global__ void __launch_bounds__(256, 2)
 k_tail(const float* __restrict__ h4, int64_t n, HeadPtrs hp, float* __restrict__ out16, float* __restrict__ logits16) {

@@ -194,17 +194,17 @@ class ClairvoyanteBase(object):
         return self.l2RegularizationLambdaVal
 
     # ---- inference (clairvoyante_v3.py:257-280) --------------------------------------------
-    def _predict16(self, XArray, want_logits=False):
+    def _predict(self, XArray, want_logits=False):
         x, n = _f32c(XArray, self.inputShape)
-        out = np.empty((n, 16), np.float32)
+        base = np.empty((n, 4), np.float32); z = np.empty((n, 2), np.float32)
+        t = np.empty((n, 4), np.float32); l = np.empty((n, 6), np.float32)
         lg = np.empty((n, 16), np.float32) if want_logits else None
-        _lib.check(self._lib.cvb_predict_host(self._h, x.ctypes.data, n, out.ctypes.data,
-                                              lg.ctypes.data if want_logits else None))
-        return out, lg
+        _lib.check(self._lib.cvb_predict_host(self._h, x.ctypes.data, n, base.ctypes.data, z.ctypes.data, t.ctypes.data,
+                                              l.ctypes.data, lg.ctypes.data if want_logits else None))
+        return base, z, t, l, lg
 
     def predict(self, XArray):
-        o, _ = self._predict16(XArray)
-        return o[:, 0:4].copy(), o[:, 4:6].copy(), o[:, 6:10].copy(), o[:, 10:16].copy()
+        return self._predict(XArray)[:4]
 
     def predictNoRT(self, XArray):
         self.predictBaseRTVal = None; self.predictZygosityRTVal = None
@@ -214,7 +214,8 @@ class ClairvoyanteBase(object):
 
     def predictLogits(self, XArray):
         """(out16, logits16): extension used by the parity tests (base head pre-sigmoid)."""
-        return self._predict16(XArray, want_logits=True)
+        base, z, t, l, lg = self._predict(XArray, want_logits=True)
+        return np.concatenate([base, z, t, l], axis=1), lg
 
     def predictDevice(self, x_ptr, n, out16_ptr, logits16_ptr=None, stream=None):
         """Device-resident batch (pointers from e.g. torch.Tensor.data_ptr()); asynchronous."""

@@ -68,9 +68,10 @@ int cvb_set_compute_mode(cvb_model* m, int mode);
 
 /* replaces predict/predictNoRT (clairvoyante_v3.py:257-280) with HOST buffers:
  * stages x through pinned memory, copies host->device, runs the kernels, copies
- * (n,16) results back.  x may be pageable or pinned.  Blocks until results are
+ * the results back into the four per-head arrays the reference's predict() returns.  x may be pageable or pinned.  Blocks until results are
  * in out16.                                                                      */
-int cvb_predict_host(cvb_model* m, const float* x, int64_t n, float* out16, float* logits16);
+int cvb_predict_host(cvb_model* m, const float* x, int64_t n, float* base /*n,4*/, float* zygosity /*n,2*/,
+                     float* var_type /*n,4*/, float* indel_length /*n,6*/, float* logits16 /*n,16 or NULL*/);
 /* same computation on DEVICE buffers (x, out16, logits16 are device pointers on the
  * handle's device); enqueued on `stream` (a cudaStream_t; NULL = the CUDA legacy default
  * stream, exactly as in the runtime API) and NOT synchronised.                                                  */
