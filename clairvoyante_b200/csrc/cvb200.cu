@@ -13,7 +13,7 @@
 
 #include "fwd_simt.cuh"
 #include "fc4_tc.cuh"
-#include "conv3_tc.cuh"
+#include "conv_tc.cuh"
 #include <stdlib.h>
 #include <sys/mman.h>
 #include "train_simt.cuh"
@@ -79,6 +79,10 @@ struct cvb_model {
   __half *d_w3b_hi = nullptr, *d_w3b_lo = nullptr;
   CUtensorMap map_c3a_hi, map_c3a_lo, map_c3b_hi, map_c3b_lo;
   bool tc_conv3 = true;
+  // conv2 on tensor cores: A = p1 hi/lo [sites*30][64] (written by k_v3_c1), B = rearranged conv2 weights [2*128][64]
+  __half *d_p1 = nullptr, *d_w2b_hi = nullptr, *d_w2b_lo = nullptr;
+  CUtensorMap map_c2a_hi, map_c2a_lo, map_c2b_hi, map_c2b_lo;
+  bool tc_conv2 = true;
   int64_t alloc_sites = 0;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;  // 5 per chunk: before front, after front, conv3, fc4, tail
@@ -184,7 +188,7 @@ extern "C" int cvb_destroy(cvb_model* m) {
   for (auto e : m->prof_events) cudaEventDestroy(e);
   cudaFree(m->d_params); cudaFree(m->d_m); cudaFree(m->d_v); cudaFree(m->d_grad);
   cudaFree(m->d_p2); cudaFree(m->d_p3); cudaFree(m->d_h4); cudaFree(m->d_h5);
-  cudaFree(m->d_w3b_hi); cudaFree(m->d_w3b_lo);
+  cudaFree(m->d_w3b_hi); cudaFree(m->d_w3b_lo); cudaFree(m->d_p1); cudaFree(m->d_w2b_hi); cudaFree(m->d_w2b_lo);
   cudaFree(m->d_w4t_hi); cudaFree(m->d_w4t_lo); cudaFree(m->d_absmax); cudaFree(m->d_inv_scale);
   for (int i = 0; i < 2; ++i) {
     cudaFree(m->d_x[i]); cudaFree(m->d_out[i]); cudaFree(m->d_lg[i]);
@@ -295,15 +299,31 @@ static int tc_setup(cvb_model* m) {
     CK(cudaMalloc(&m->d_w3b_hi, (size_t)C::B_ROWS_TOTAL * C::KROW * 2));
     CK(cudaMalloc(&m->d_w3b_lo, (size_t)C::B_ROWS_TOTAL * C::KROW * 2));
     __half* p2_hi = reinterpret_cast<__half*>(m->d_p2);
-    __half* p2_lo = p2_hi + m->alloc_sites * (C::ROWS_PER_SITE * C::KROW);
-    const uint64_t rows = (uint64_t)m->alloc_sites * C::ROWS_PER_SITE;
+    __half* p2_lo = p2_hi + m->alloc_sites * (C::RPS * C::KROW);
+    const uint64_t rows = (uint64_t)m->alloc_sites * C::RPS;
     if (make_map_f16(&m->map_c3a_hi, p2_hi, rows, C::KROW, C::BK, C::QROWS, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     if (make_map_f16(&m->map_c3a_lo, p2_lo, rows, C::KROW, C::BK, C::QROWS, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-    if (make_map_f16(&m->map_c3b_hi, m->d_w3b_hi, C::B_ROWS_TOTAL, C::KROW, C::BK, 48, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-    if (make_map_f16(&m->map_c3b_lo, m->d_w3b_lo, C::B_ROWS_TOTAL, C::KROW, C::BK, 48, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-    CK(cudaFuncSetAttribute(tc::k_conv3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    if (make_map_f16(&m->map_c3b_hi, m->d_w3b_hi, C::B_ROWS_TOTAL, C::KROW, C::BK, C::COUT, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (make_map_f16(&m->map_c3b_lo, m->d_w3b_lo, C::B_ROWS_TOTAL, C::KROW, C::BK, C::COUT, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    CK(cudaFuncSetAttribute(tc::k_conv_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     const char* e = getenv("CVB_TC_CONV3");
     m->tc_conv3 = !(e && e[0] == '0');
+  }
+  {
+    using C = tc::Conv2Tc;
+    const size_t p1_halves = (size_t)m->alloc_sites * C::RPS * C::KROW;
+    CK(cudaMalloc(&m->d_p1, p1_halves * 2 * 2));
+    CK(cudaMemset(m->d_p1, 0, p1_halves * 2 * 2));  // row 29 of every site stays zero (conv2's bottom SAME pad)
+    CK(cudaMalloc(&m->d_w2b_hi, (size_t)C::B_ROWS_TOTAL * C::KROW * 2));
+    CK(cudaMalloc(&m->d_w2b_lo, (size_t)C::B_ROWS_TOTAL * C::KROW * 2));
+    const uint64_t rows = (uint64_t)m->alloc_sites * C::RPS;
+    if (make_map_f16(&m->map_c2a_hi, m->d_p1, rows, C::KROW, C::BK, C::QROWS, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+    if (make_map_f16(&m->map_c2a_lo, m->d_p1 + p1_halves, rows, C::KROW, C::BK, C::QROWS, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+    if (make_map_f16(&m->map_c2b_hi, m->d_w2b_hi, C::B_ROWS_TOTAL, C::KROW, C::BK, C::COUT, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+    if (make_map_f16(&m->map_c2b_lo, m->d_w2b_lo, C::B_ROWS_TOTAL, C::KROW, C::BK, C::COUT, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+    CK(cudaFuncSetAttribute(tc::k_conv_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    const char* e = getenv("CVB_TC_CONV2");
+    m->tc_conv2 = m->tc_conv3 && !(e && e[0] == '0');
   }
   m->tc_ready = true;
   m->tc_weights_dirty = true;
@@ -326,10 +346,16 @@ static int tc_refresh_weights(cvb_model* m, cudaStream_t st) {
   CK(cudaMemsetAsync(m->d_absmax + 1, 0, 4, st));
   tc::k_absmax<<<64, 256, 0, st>>>(m->var("conv3/kernel"), 3 * 4 * 32 * 48, m->d_absmax + 1);
   CK(cudaGetLastError());
-  tc::k_prep_conv3_weights<<<(3 * 192 * 128 + 255) / 256, 256, 0, st>>>(m->var("conv3/kernel"), m->d_absmax + 1, m->d_w3b_hi,
-                                                                         m->d_w3b_lo, m->d_inv_scale + 1);
+  tc::k_prep_conv_weights<tc::Conv3Tc><<<(3 * 192 * 128 + 255) / 256, 256, 0, st>>>(
+      m->var("conv3/kernel"), m->d_absmax + 1, m->d_w3b_hi, m->d_w3b_lo, m->d_inv_scale + 1);
   CK(cudaGetLastError());
-  m->launches += 4;
+  CK(cudaMemsetAsync(m->d_absmax + 2, 0, 4, st));
+  tc::k_absmax<<<16, 256, 0, st>>>(m->var("conv2/kernel"), 2 * 4 * 16 * 32, m->d_absmax + 2);
+  CK(cudaGetLastError());
+  tc::k_prep_conv_weights<tc::Conv2Tc><<<(2 * 128 * 64 + 255) / 256, 256, 0, st>>>(
+      m->var("conv2/kernel"), m->d_absmax + 2, m->d_w2b_hi, m->d_w2b_lo, m->d_inv_scale + 2);
+  CK(cudaGetLastError());
+  m->launches += 6;
   m->tc_weights_dirty = false;
   return 0;
 }
@@ -396,7 +422,23 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       using F = FrontV3<4>;
       int64_t tiles = (n + 3) / 4;
       int grid = (int)std::min<int64_t>(tiles, 2 * sms);
-      if (tensor && m->tc_conv3) {
+      if (tensor && m->tc_conv2) {
+        using C1K = C1Only<7>;
+        auto k1 = k_v3_c1<7>;
+        CK(set_smem(k1, C1K::SMEM_BYTES));
+        const size_t p1_halves = (size_t)m->alloc_sites * 30 * 64;
+        int g1 = (int)std::min<int64_t>((n + 6) / 7, 2 * sms);
+        k1<<<g1, 256, C1K::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->d_p1, m->d_p1 + p1_halves);
+        CK(cudaGetLastError());
+        using T = tc::Conv2Tc;
+        const int64_t t2 = (n * T::RPS + T::TILE_STEP - 1) / T::TILE_STEP;
+        int g2 = (int)std::min<int64_t>(t2, sms);
+        __half* p2_hi = reinterpret_cast<__half*>(m->d_p2);
+        tc::k_conv_tc<T><<<g2, T::THREADS, T::SMEM_BYTES, st>>>(m->map_c2a_hi, m->map_c2a_lo, m->map_c2b_hi, m->map_c2b_lo, n,
+                                                                 m->var("conv2/bias"), m->d_inv_scale + 2, p2_hi,
+                                                                 p2_hi + m->alloc_sites * (28 * 128));
+        m->launches += 1;
+      } else if (tensor && m->tc_conv3) {
         auto k = k_v3_front<4, true>;
         CK(set_smem(k, F::SMEM_BYTES));
         k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
@@ -418,10 +460,10 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       int grid = (int)std::min<int64_t>(tiles, sms);
       if (tensor && m->tc_conv3) {
         using T = tc::Conv3Tc;
-        const int64_t t3 = (n * T::ROWS_PER_SITE + T::TILE_STEP - 1) / T::TILE_STEP;
+        const int64_t t3 = (n * T::RPS + T::TILE_STEP - 1) / T::TILE_STEP;
         int g3 = (int)std::min<int64_t>(t3, sms);
         __half* p3_hi = reinterpret_cast<__half*>(m->d_p3);
-        tc::k_conv3_tc<<<g3, T::THREADS, T::SMEM_BYTES, st>>>(m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo, n,
+        tc::k_conv_tc<T><<<g3, T::THREADS, T::SMEM_BYTES, st>>>(m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo, n,
                                                               m->var("conv3/bias"), m->d_inv_scale + 1, p3_hi,
                                                               p3_hi + m->alloc_sites * 4608);
       } else if (tensor) {

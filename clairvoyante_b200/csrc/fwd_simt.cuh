@@ -135,6 +135,75 @@ k_v3_front(const float* __restrict__ x, int64_t n, const float* __restrict__ w1g
 }
 
 // ------------------------------------------------------------------------------------
+// k_v3_c1 (tensor path): x -> conv1+SELU -> pool1 -> p1 as fp16 hi/lo [n][30][64] (row 29 is the
+// zero SAME-padding row of conv2 and is never written), the A operand of the tcgen05 conv2.
+// ------------------------------------------------------------------------------------
+template <int S>
+struct C1Only {
+  using C1 = ConvCfg<4, 16, 1, 33, S, 8, 8>;
+  static_assert(C1::THREADS <= 256, "tile does not fit the CTA");
+  static constexpr int C1S_RS = 68;
+  static constexpr int W1 = 0;
+  static constexpr int B1 = W1 + C1::W_FLOATS;
+  static constexpr int XS = B1 + 16;
+  static constexpr int C1S = XS + C1::IN_FLOATS;
+  static constexpr int SMEM_FLOATS = C1S + S * 33 * C1S_RS;
+  static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
+};
+
+template <int S>
+__global__ void __launch_bounds__(256, 2)
+k_v3_c1(const float* __restrict__ x, int64_t n, const float* __restrict__ w1g, const float* __restrict__ b1g,
+        __half* __restrict__ p1_hi, __half* __restrict__ p1_lo) {
+  using F = C1Only<S>;
+  using C1 = typename F::C1;
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  float* w1s = smem + F::W1;
+  float* b1s = smem + F::B1;
+  float* xs = smem + F::XS;
+  float* c1s = smem + F::C1S;
+  for (int i = tid; i < C1::W_FLOATS; i += 256) w1s[i] = w1g[i];
+  if (tid < 16) b1s[tid] = b1g[tid];
+  const ConvThread<C1> th1(tid);
+  const int64_t ntiles = (n + S - 1) / S;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t site0 = tile * S;
+    __syncthreads();
+    for (int i = tid; i < S * 33 * 4; i += 256) {
+      int s = i / 132, r = i - s * 132;
+      int h = r >> 2, q = r & 3;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (site0 + s < n) v = ldg_stream(reinterpret_cast<const float4*>(x + (site0 + s) * 528) + r);
+      *reinterpret_cast<float4*>(xs + (s * C1::ROWS + h) * C1::RS + q * 4) = v;
+    }
+    __syncthreads();
+    {
+      float acc[C1::TM][C1::TN];
+      conv_compute<C1>(xs, w1s, th1, acc);
+      conv_store_selu_smem<C1, 33, F::C1S_RS, 0>(acc, b1s, th1, c1s);
+    }
+    __syncthreads();
+    // pool1 (5,1) -> global p1[site][h<29][64] as hi/lo halves
+    for (int i = tid; i < S * 29 * 16; i += 256) {
+      int s = i / (29 * 16), r = i - s * (29 * 16);
+      int h = r >> 4, q = r & 15;
+      if (site0 + s >= n) continue;
+      const float* src = c1s + (s * 33 + h) * F::C1S_RS + q * 4;
+      float4 v = *reinterpret_cast<const float4*>(src);
+#pragma unroll
+      for (int j = 1; j < 5; ++j) v = max4(v, *reinterpret_cast<const float4*>(src + j * F::C1S_RS));
+      const int64_t o = ((site0 + s) * 30 + h) * 64 + q * 4;
+      __half hi[4], lo[4];
+      tc::split_f16(v.x, hi[0], lo[0]); tc::split_f16(v.y, hi[1], lo[1]);
+      tc::split_f16(v.z, hi[2], lo[2]); tc::split_f16(v.w, hi[3], lo[3]);
+      *reinterpret_cast<uint2*>(p1_hi + o) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(p1_lo + o) = *reinterpret_cast<const uint2*>(lo);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // k_slim_front (clairvoyante_v3_slim.py:54-70): x -> conv1(1x4,8)+SELU -> conv2(3x4,16)+SELU
 //   -> p2 [n][37][64] (two zero rows above and below the 33 rows: conv3 is 5x4 SAME)
 // ------------------------------------------------------------------------------------
