@@ -13,11 +13,15 @@ namespace cvb {
 
 // reference clairvoyante/selu.py:23-24
 __device__ __forceinline__ float selu_f(float x) {
-  const float alpha = 1.6732632423543772848170429916717f;
+  // scale * where(x >= 0, x, alpha * (exp(x) - 1))   (selu.py:25), arranged as 2 FMUL + EX2 + FFMA + select:
+  //   x >= 0 : scale * x          x < 0 : (scale*alpha) * 2^(x*log2 e) - scale*alpha
+  // (for large positive x the unused branch is +inf, never NaN)
   const float scale = 1.0507009873554804934193349852946f;
-  // scale * where(x >= 0, x, alpha * (exp(x) - 1))   (selu.py:25)
-  float neg = alpha * (__expf(fminf(x, 0.f)) - 1.0f);
-  return scale * (x >= 0.f ? x : neg);
+  const float sa = 1.0507009873554804934193349852946f * 1.6732632423543772848170429916717f;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  const float neg = fmaf(sa, e, -sa);
+  return x >= 0.f ? scale * x : neg;
 }
 // d selu / dx expressed through the OUTPUT y = selu(x):  x>=0 -> scale ; x<0 -> y + scale*alpha
 __device__ __forceinline__ float selu_grad_from_out(float y) {

@@ -208,21 +208,26 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
         uint32_t rr[16];
         tmem_ld16(taddr + cc, rr);
         tmem_ld_wait();
-        __align__(16) __half hi[16];
-        __align__(16) __half lo[16];
+        __align__(16) __half2 hi[8];
+        __align__(16) __half2 lo[8];
+        float pv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float v = selu_f(fmaf(__uint_as_float(rr[j]), isc, bias_s[cc + j]));
+          // SELU is monotonic and the bias is per column, so pooling the raw accumulators first is exact:
+          // max_r selu(a_r * isc + b) == selu(max_r(a_r) * isc + b)   (isc > 0)
+          const float v = __uint_as_float(rr[j]);
           float mx = v;
 #pragma unroll
           for (int d = 1; d < F::POOL; ++d) mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, v, d));  // rows r .. r+POOL-1
-          split_f16(mx, hi[j], lo[j]);
+          pv[j] = selu_f(fmaf(mx, isc, bias_s[cc + j]));
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split_f16x2(pv[2 * j], pv[2 * j + 1], hi[j], lo[j]);
         if (store) {
           *reinterpret_cast<uint4*>(dhi + cc) = *reinterpret_cast<const uint4*>(hi);
-          *reinterpret_cast<uint4*>(dhi + cc + 8) = *reinterpret_cast<const uint4*>(hi + 8);
+          *reinterpret_cast<uint4*>(dhi + cc + 8) = *reinterpret_cast<const uint4*>(hi + 4);
           *reinterpret_cast<uint4*>(dlo + cc) = *reinterpret_cast<const uint4*>(lo);
-          *reinterpret_cast<uint4*>(dlo + cc + 8) = *reinterpret_cast<const uint4*>(lo + 8);
+          *reinterpret_cast<uint4*>(dlo + cc + 8) = *reinterpret_cast<const uint4*>(lo + 4);
         }
       }
       tc_fence_before();

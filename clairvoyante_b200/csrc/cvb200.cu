@@ -481,7 +481,7 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
     }
     if (tensor) {
       using F = tc::Fc4Tc;
-      dim3 grid((unsigned)((n + F::BM - 1) / F::BM), 2);
+      dim3 grid(2, (unsigned)((n + F::BM - 1) / F::BM));
       tc::k_fc4_tc<<<grid, F::THREADS, F::SMEM_BYTES, st>>>(m->map_a_hi, m->map_a_lo, m->map_b_hi, m->map_b_lo, n, 4608,
                                                             m->var("fc4/bias"), m->d_inv_scale, m->d_h4);
       CK(cudaGetLastError());

@@ -92,8 +92,10 @@ k_fc4_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ C
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t site0 = (int64_t)blockIdx.x * F::BM;
-  const int half = blockIdx.y;
+  // half is the fast grid index: the two CTAs that read the same A tile are launched back to back, so the
+  // second read of A is served by L2 instead of HBM
+  const int64_t site0 = (int64_t)blockIdx.y * F::BM;
+  const int half = blockIdx.x;
   const int nkb = K / F::BK;
   constexpr int KB_PER_CHUNK = F::KCH / F::BK;
   const int nchunks = nkb / KB_PER_CHUNK;
