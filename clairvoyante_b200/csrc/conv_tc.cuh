@@ -86,9 +86,16 @@ __global__ void k_prep_conv_weights(const float* __restrict__ w, const unsigned 
 template <class F>
 __global__ void __launch_bounds__(F::THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, int64_t n,
+          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+          const __grid_constant__ CUtensorMap map_a4, const __grid_constant__ CUtensorMap map_b2,
+          const __grid_constant__ CUtensorMap map_b3, const __grid_constant__ CUtensorMap map_b4, int merged, int64_t n,
           const float* __restrict__ bias, const float* __restrict__ inv_scale, __half* __restrict__ out_hi,
           __half* __restrict__ out_lo) {
+  // merged != 0: 2 TMA operations per stage instead of 8 + 2*nb --
+  //   map_a4  : 4-D view (k, row-in-quadrant, quadrant, plane) of the activation: quadrant stride QSTEP rows
+  //             (overlapping windows), plane stride = hi -> lo; one box {BK, 32, 4, 2} = A_hi (128 rows) then A_lo
+  //   map_b{2,3,4}: 3-D view (k, row, plane) of the weights with box {BK, nb*COUT, 2} = B_hi rows then B_lo rows
+  // The issuing thread, not the bytes, is what bounds the small-box variant (profiles/r01_tensor_path.md).
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F::STAGES * F::STAGE_BYTES);
@@ -107,6 +114,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
     tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
+    tma_prefetch_desc(&map_a4); tma_prefetch_desc(&map_b2); tma_prefetch_desc(&map_b3); tma_prefetch_desc(&map_b4);
     for (int s = 0; s < F::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], F::EPI_WARPS); }
     fence_barrier_init();
@@ -136,6 +144,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = smem + s * F::STAGE_BYTES;
           mbar_arrive_expect_tx(&full[s], 2 * F::A_BYTES + 2 * nb * F::COUT * F::ROW_BYTES);
+          if (merged) {
+            tma_load_4d(st, &map_a4, &full[s], wp * F::CIN, kh, (int)(tile * 4), 0);
+            const CUtensorMap* mb = nb == 2 ? &map_b2 : (nb == 3 ? &map_b3 : &map_b4);
+            tma_load_3d(st + 2 * F::A_BYTES, mb, &full[s], wp * F::CIN, kh * F::NOUT + wl * F::COUT, 0);
+            continue;
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int r = (int)(base + q * F::QSTEP + kh);
@@ -168,7 +182,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t st = smem_u32(smem + s * F::STAGE_BYTES);
-          const uint32_t a_hi = st, a_lo = st + F::A_BYTES, b_hi = st + 2 * F::A_BYTES, b_lo = b_hi + F::B_BYTES;
+          const uint32_t a_hi = st, a_lo = st + F::A_BYTES, b_hi = st + 2 * F::A_BYTES;
+          const uint32_t b_lo = b_hi + (merged ? nb * F::COUT * F::ROW_BYTES : F::B_BYTES);  // planes are packed when merged
 #pragma unroll
           for (int ks = 0; ks < F::BK / 16; ++ks) {
             const uint32_t ko = ks * 32;

@@ -83,6 +83,11 @@ struct cvb_model {
   __half *d_p1 = nullptr, *d_w2b_hi = nullptr, *d_w2b_lo = nullptr;
   CUtensorMap map_c2a_hi, map_c2a_lo, map_c2b_hi, map_c2b_lo;
   bool tc_conv2 = true;
+  // rows per fp16 plane of p1 / p2 (sites*RPS + slack, a multiple of the consumer's quadrant step so that the
+  // merged 4-D TMA view's plane stride is a multiple of its quadrant stride); lo plane = hi plane + rows*KROW
+  int64_t p1_rows = 0, p2_rows = 0;
+  CUtensorMap map_c2a4, map_c2b2, map_c2b3, map_c2b4, map_c3a4, map_c3b2, map_c3b3, map_c3b4;
+  int tc_merged = 1;
   int64_t alloc_sites = 0;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;  // 5 per chunk: before front, after front, conv3, fc4, tail
@@ -163,7 +168,10 @@ extern "C" int cvb_create(int variant, int device, cvb_model** out) {
   CK(cudaMalloc(&m->d_m, pb));      CK(cudaMemset(m->d_m, 0, pb));
   CK(cudaMalloc(&m->d_v, pb));      CK(cudaMemset(m->d_v, 0, pb));
   CK(cudaMalloc(&m->d_grad, pb + 64)); CK(cudaMemset(m->d_grad, 0, pb + 64));
-  CK(cudaMalloc(&m->d_p2, (size_t)CHUNK * m->p2_site * 4)); CK(cudaMemset(m->d_p2, 0, (size_t)CHUNK * m->p2_site * 4));
+  m->p2_rows = ((CHUNK * 28 + 160 + 29) / 30) * 30;
+  m->p1_rows = ((CHUNK * 30 + 160 + 28) / 29) * 29;
+  const size_t p2_bytes = std::max((size_t)CHUNK * m->p2_site * 4, (size_t)m->p2_rows * 128 * 2 * 2) + 4096;
+  CK(cudaMalloc(&m->d_p2, p2_bytes)); CK(cudaMemset(m->d_p2, 0, p2_bytes));
   CK(cudaMalloc(&m->d_p3, (size_t)CHUNK * m->p3_site * 4));
   CK(cudaMalloc(&m->d_h4, (size_t)CHUNK * m->h4_site * 4));
   CK(cudaMalloc(&m->d_h5, (size_t)CHUNK * 168 * 4));
@@ -188,7 +196,7 @@ extern "C" int cvb_destroy(cvb_model* m) {
   for (auto e : m->prof_events) cudaEventDestroy(e);
   cudaFree(m->d_params); cudaFree(m->d_m); cudaFree(m->d_v); cudaFree(m->d_grad);
   cudaFree(m->d_p2); cudaFree(m->d_p3); cudaFree(m->d_h4); cudaFree(m->d_h5);
-  cudaFree(m->d_w3b_hi); cudaFree(m->d_w3b_lo); cudaFree(m->d_p1); cudaFree(m->d_w2b_hi); cudaFree(m->d_w2b_lo);
+  cudaFree(m->d_w3b_hi); cudaFree(m->d_p1); cudaFree(m->d_w2b_hi);
   cudaFree(m->d_w4t_hi); cudaFree(m->d_w4t_lo); cudaFree(m->d_absmax); cudaFree(m->d_inv_scale);
   for (int i = 0; i < 2; ++i) {
     cudaFree(m->d_x[i]); cudaFree(m->d_out[i]); cudaFree(m->d_lg[i]);
@@ -279,6 +287,41 @@ static int make_map_f16(CUtensorMap* map, void* base, uint64_t rows, uint64_t co
   return 0;
 }
 
+// general fp16 tensor map: dims/box innermost first, strides (bytes) for dims 1..rank-1
+static int make_map_nd(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, CUtensorMapSwizzle sw) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base, d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(rank %d) failed with CUresult %d", rank, (int)r);
+  return 0;
+}
+
+// merged views for k_conv_tc (conv_tc.cuh): activation planes at `act`, `rows` rows per plane; weights planes at `wts`
+template <class C>
+static int make_conv_merged_maps(void* act, int64_t rows, void* wts, CUtensorMapSwizzle sw, CUtensorMap* a4, CUtensorMap* b2,
+                                 CUtensorMap* b3, CUtensorMap* b4) {
+  const uint64_t rext = C::QROWS + C::KH - 1;
+  const uint64_t Q = (uint64_t)(rows - rext) / C::QSTEP + 1;
+  const uint64_t ad[4] = {(uint64_t)C::KROW, rext, Q, 2};
+  const uint64_t as[3] = {(uint64_t)C::KROW * 2, (uint64_t)C::QSTEP * C::KROW * 2, (uint64_t)rows * C::KROW * 2};
+  const uint32_t ab[4] = {(uint32_t)C::BK, 32, 4, 2};
+  if (make_map_nd(a4, act, 4, ad, as, ab, sw)) return 1;
+  const uint64_t bd[3] = {(uint64_t)C::KROW, (uint64_t)C::B_ROWS_TOTAL, 2};
+  const uint64_t bs[2] = {(uint64_t)C::KROW * 2, (uint64_t)C::B_ROWS_TOTAL * C::KROW * 2};
+  CUtensorMap* bm[3] = {b2, b3, b4};
+  for (int nb = 2; nb <= 4; ++nb) {
+    const uint32_t bb[3] = {(uint32_t)C::BK, (uint32_t)(nb * C::COUT), 2};
+    if (make_map_nd(bm[nb - 2], wts, 3, bd, bs, bb, sw)) return 1;
+  }
+  return 0;
+}
+
 static int tc_setup(cvb_model* m) {
   if (m->tc_ready) return 0;
   using F = tc::Fc4Tc;
@@ -296,10 +339,10 @@ static int tc_setup(cvb_model* m) {
   CK(cudaFuncSetAttribute(tc::k_fc4_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
   {
     using C = tc::Conv3Tc;
-    CK(cudaMalloc(&m->d_w3b_hi, (size_t)C::B_ROWS_TOTAL * C::KROW * 2));
-    CK(cudaMalloc(&m->d_w3b_lo, (size_t)C::B_ROWS_TOTAL * C::KROW * 2));
+    CK(cudaMalloc(&m->d_w3b_hi, (size_t)C::B_ROWS_TOTAL * C::KROW * 2 * 2));  // hi plane then lo plane
+    m->d_w3b_lo = m->d_w3b_hi + (size_t)C::B_ROWS_TOTAL * C::KROW;
     __half* p2_hi = reinterpret_cast<__half*>(m->d_p2);
-    __half* p2_lo = p2_hi + m->alloc_sites * (C::RPS * C::KROW);
+    __half* p2_lo = p2_hi + m->p2_rows * C::KROW;
     const uint64_t rows = (uint64_t)m->alloc_sites * C::RPS;
     if (make_map_f16(&m->map_c3a_hi, p2_hi, rows, C::KROW, C::BK, C::QROWS, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     if (make_map_f16(&m->map_c3a_lo, p2_lo, rows, C::KROW, C::BK, C::QROWS, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
@@ -308,14 +351,21 @@ static int tc_setup(cvb_model* m) {
     CK(cudaFuncSetAttribute(tc::k_conv_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     const char* e = getenv("CVB_TC_CONV3");
     m->tc_conv3 = !(e && e[0] == '0');
+    const char* em = getenv("CVB_TC_MERGED");
+    m->tc_merged = !(em && em[0] == '0');
+    if (m->tc_merged && make_conv_merged_maps<C>(p2_hi, m->p2_rows, m->d_w3b_hi, CU_TENSOR_MAP_SWIZZLE_64B, &m->map_c3a4,
+                                                 &m->map_c3b2, &m->map_c3b3, &m->map_c3b4)) {
+      m->tc_merged = 0;  // overlapping-window view rejected by this driver: fall back to per-quadrant boxes
+      m->map_c3a4 = m->map_c3a_hi; m->map_c3b2 = m->map_c3b3 = m->map_c3b4 = m->map_c3b_hi;
+    }
   }
   {
     using C = tc::Conv2Tc;
-    const size_t p1_halves = (size_t)m->alloc_sites * C::RPS * C::KROW;
+    const size_t p1_halves = (size_t)m->p1_rows * C::KROW;
     CK(cudaMalloc(&m->d_p1, p1_halves * 2 * 2));
     CK(cudaMemset(m->d_p1, 0, p1_halves * 2 * 2));  // row 29 of every site stays zero (conv2's bottom SAME pad)
-    CK(cudaMalloc(&m->d_w2b_hi, (size_t)C::B_ROWS_TOTAL * C::KROW * 2));
-    CK(cudaMalloc(&m->d_w2b_lo, (size_t)C::B_ROWS_TOTAL * C::KROW * 2));
+    CK(cudaMalloc(&m->d_w2b_hi, (size_t)C::B_ROWS_TOTAL * C::KROW * 2 * 2));  // hi plane then lo plane
+    m->d_w2b_lo = m->d_w2b_hi + (size_t)C::B_ROWS_TOTAL * C::KROW;
     const uint64_t rows = (uint64_t)m->alloc_sites * C::RPS;
     if (make_map_f16(&m->map_c2a_hi, m->d_p1, rows, C::KROW, C::BK, C::QROWS, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
     if (make_map_f16(&m->map_c2a_lo, m->d_p1 + p1_halves, rows, C::KROW, C::BK, C::QROWS, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
@@ -324,6 +374,13 @@ static int tc_setup(cvb_model* m) {
     CK(cudaFuncSetAttribute(tc::k_conv_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     const char* e = getenv("CVB_TC_CONV2");
     m->tc_conv2 = m->tc_conv3 && !(e && e[0] == '0');
+    if (m->tc_merged && make_conv_merged_maps<C>(m->d_p1, m->p1_rows, m->d_w2b_hi, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c2a4,
+                                                 &m->map_c2b2, &m->map_c2b3, &m->map_c2b4))
+      m->tc_merged = 0;
+    if (!m->tc_merged) {
+      m->map_c2a4 = m->map_c2a_hi; m->map_c2b2 = m->map_c2b3 = m->map_c2b4 = m->map_c2b_hi;
+      m->map_c3a4 = m->map_c3a_hi; m->map_c3b2 = m->map_c3b3 = m->map_c3b4 = m->map_c3b_hi;
+    }
   }
   m->tc_ready = true;
   m->tc_weights_dirty = true;
@@ -373,7 +430,7 @@ extern "C" int cvb_set_compute_mode(cvb_model* m, int mode) {
   if (mode != m->compute_mode) {
     // p2's zero padding rows sit at different byte offsets in the fp32 and the fp16 hi/lo layouts
     CK(cudaDeviceSynchronize());
-    CK(cudaMemset(m->d_p2, 0, (size_t)m->alloc_sites * m->p2_site * 4));
+    CK(cudaMemset(m->d_p2, 0, std::max((size_t)m->alloc_sites * m->p2_site * 4, (size_t)m->p2_rows * 128 * 2 * 2)));
   }
   m->compute_mode = mode;
   m->CHUNK = (int64_t)m->num_sms * (m->variant == CVB_V3 ? (mode == CVB_COMPUTE_FP32 ? 96 : 128) : 224);
@@ -426,7 +483,7 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
         using C1K = C1Only<7>;
         auto k1 = k_v3_c1<7>;
         CK(set_smem(k1, C1K::SMEM_BYTES));
-        const size_t p1_halves = (size_t)m->alloc_sites * 30 * 64;
+        const size_t p1_halves = (size_t)m->p1_rows * 64;
         int g1 = (int)std::min<int64_t>((n + 6) / 7, 2 * sms);
         k1<<<g1, 256, C1K::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->d_p1, m->d_p1 + p1_halves);
         CK(cudaGetLastError());
@@ -434,16 +491,17 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
         const int64_t t2 = (n * T::RPS + T::TILE_STEP - 1) / T::TILE_STEP;
         int g2 = (int)std::min<int64_t>(t2, sms);
         __half* p2_hi = reinterpret_cast<__half*>(m->d_p2);
-        tc::k_conv_tc<T><<<g2, T::THREADS, T::SMEM_BYTES, st>>>(m->map_c2a_hi, m->map_c2a_lo, m->map_c2b_hi, m->map_c2b_lo, n,
-                                                                 m->var("conv2/bias"), m->d_inv_scale + 2, p2_hi,
-                                                                 p2_hi + m->alloc_sites * (28 * 128));
+        tc::k_conv_tc<T><<<g2, T::THREADS, T::SMEM_BYTES, st>>>(m->map_c2a_hi, m->map_c2a_lo, m->map_c2b_hi, m->map_c2b_lo,
+                                                                 m->map_c2a4, m->map_c2b2, m->map_c2b3, m->map_c2b4, m->tc_merged,
+                                                                 n, m->var("conv2/bias"), m->d_inv_scale + 2, p2_hi,
+                                                                 p2_hi + m->p2_rows * 128);
         m->launches += 1;
       } else if (tensor && m->tc_conv3) {
         auto k = k_v3_front<4, true>;
         CK(set_smem(k, F::SMEM_BYTES));
         k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
                                             m->var("conv2/bias"), m->d_p2,
-                                            reinterpret_cast<__half*>(m->d_p2) + m->alloc_sites * (28 * 128));
+                                            reinterpret_cast<__half*>(m->d_p2) + m->p2_rows * 128);
       } else {
         auto k = k_v3_front<4, false>;
         CK(set_smem(k, F::SMEM_BYTES));
@@ -463,7 +521,8 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
         const int64_t t3 = (n * T::RPS + T::TILE_STEP - 1) / T::TILE_STEP;
         int g3 = (int)std::min<int64_t>(t3, sms);
         __half* p3_hi = reinterpret_cast<__half*>(m->d_p3);
-        tc::k_conv_tc<T><<<g3, T::THREADS, T::SMEM_BYTES, st>>>(m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo, n,
+        tc::k_conv_tc<T><<<g3, T::THREADS, T::SMEM_BYTES, st>>>(m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo,
+                                                                 m->map_c3a4, m->map_c3b2, m->map_c3b3, m->map_c3b4, m->tc_merged, n,
                                                               m->var("conv3/bias"), m->d_inv_scale + 1, p3_hi,
                                                               p3_hi + m->alloc_sites * 4608);
       } else if (tensor) {
@@ -653,7 +712,7 @@ extern "C" int cvb_debug_read(cvb_model* m, int which, float* host, int64_t n) {
   if (which == 3 || which == 4) {  // fp16 hi/lo pair of p2 (3) / p3 (4) in tensor mode, recombined to fp32
     const int64_t per3 = which == 3 ? m->p2_site : m->p3_site;
     const __half* hi = reinterpret_cast<const __half*>(which == 3 ? m->d_p2 : m->d_p3);
-    const __half* lo = hi + m->alloc_sites * per3;
+    const __half* lo = hi + (which == 3 ? m->p2_rows * 128 : m->alloc_sites * per3);
     if (n < 0 || n > m->alloc_sites * per3) return fail("cvb_debug_read: n out of range");
     std::vector<__half> h((size_t)n), l((size_t)n);
     CK(cudaSetDevice(m->device));
