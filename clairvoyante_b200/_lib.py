@@ -67,7 +67,7 @@ SIGNATURES = {
                                            ctypes.c_float, ctypes.c_uint64, ctypes.c_int, c_vp]),
     "cvb_grad_buffer": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64)]),
     "cvb_get_gradient": (ctypes.c_int, [c_vp, ctypes.c_char_p, c_vp, c_i64]),
-    "cvb_apply_adam": (ctypes.c_int, [c_vp, ctypes.c_float, ctypes.c_float]),
+    "cvb_apply_adam": (ctypes.c_int, [c_vp, ctypes.c_float, ctypes.c_float, c_vp]),
     "cvb_alloc_pinned": (ctypes.c_int, [c_i64, ctypes.POINTER(c_vp)]),
     "cvb_free_pinned": (ctypes.c_int, [c_vp]),
     "cvb_debug_read": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_i64]),

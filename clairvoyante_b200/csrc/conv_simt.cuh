@@ -21,9 +21,11 @@
 
 namespace cvb {
 
-template <int CIN_, int COUT_, int KH_, int HOUT_, int S_, int TM_, int TN_>
+// PL = zero columns to the left of w = 0 (1 for the forward SAME conv; 2 for its data-gradient, which is the
+// correlation of the output gradient with the flipped kernel and therefore pads (2 left, 1 right)).
+template <int CIN_, int COUT_, int KH_, int HOUT_, int S_, int TM_, int TN_, int PL_ = 1>
 struct ConvCfg {
-  static constexpr int CIN = CIN_, COUT = COUT_, KH = KH_, HOUT = HOUT_, S = S_, TM = TM_, TN = TN_;
+  static constexpr int CIN = CIN_, COUT = COUT_, KH = KH_, HOUT = HOUT_, S = S_, TM = TM_, TN = TN_, PL = PL_;
   static constexpr int ROWS = HOUT + KH - 1;  // stored input rows per site (zero pad rows included)
   static constexpr int RS = 4 * CIN + 4;      // input row stride in floats
   static constexpr int P = S * HOUT;          // (site,row) pairs per output column
@@ -69,10 +71,11 @@ __device__ __forceinline__ void conv_compute(const float* __restrict__ in_s, con
     int p = th.pair(i);
     p = p < 0 ? 0 : p;
     int site = p / C::HOUT, h = p - site * C::HOUT;
-    base[i] = (site * C::ROWS + h) * C::RS + (th.w - 1) * C::CIN;
+    base[i] = (site * C::ROWS + h) * C::RS + (th.w - C::PL) * C::CIN;
   }
-  const int kw_lo = th.w == 0 ? 1 : 0;
-  const int kw_hi = th.w <= 1 ? 3 : 4 - th.w;  // inclusive
+  // taps kw with 0 <= w + kw - PL <= 3
+  const int kw_lo = C::PL - th.w > 0 ? C::PL - th.w : 0;
+  const int kw_hi = 3 + C::PL - th.w < 3 ? 3 + C::PL - th.w : 3;  // inclusive
   for (int kh = 0; kh < C::KH; ++kh) {
     for (int kw = kw_lo; kw <= kw_hi; ++kw) {
       const float* a_ptr = in_s + kh * C::RS + kw * C::CIN;
@@ -108,13 +111,14 @@ __device__ __forceinline__ void conv_compute(const float* __restrict__ in_s, con
 // bias + SELU, then write the thread's tile into an smem activation buffer laid out
 // [site][row][w][COUT] with row stride DRS floats and DROWS rows per site; output row h
 // goes to stored row h + DR0.
-template <class C, int DROWS, int DRS, int DR0>
+// ACT = true: bias + SELU (forward layers);  ACT = false: raw accumulators (data-gradient convolutions)
+template <class C, int DROWS, int DRS, int DR0, bool ACT = true>
 __device__ __forceinline__ void conv_store_selu_smem(const float (&acc)[C::TM][C::TN], const float* __restrict__ bias_s,
                                                      const ConvThread<C>& th, float* __restrict__ dst) {
   if (!th.active) return;
   float bv[C::TN];
 #pragma unroll
-  for (int j = 0; j < C::TN; ++j) bv[j] = bias_s[(th.nt + C::NT * (j / 4)) * 4 + (j & 3)];
+  for (int j = 0; j < C::TN; ++j) bv[j] = ACT ? bias_s[(th.nt + C::NT * (j / 4)) * 4 + (j & 3)] : 0.f;
 #pragma unroll
   for (int i = 0; i < C::TM; ++i) {
     int p = th.pair(i);
@@ -124,10 +128,14 @@ __device__ __forceinline__ void conv_store_selu_smem(const float (&acc)[C::TM][C
 #pragma unroll
     for (int j = 0; j < C::TN / 4; ++j) {
       float4 v;
-      v.x = selu_f(acc[i][j * 4 + 0] + bv[j * 4 + 0]);
-      v.y = selu_f(acc[i][j * 4 + 1] + bv[j * 4 + 1]);
-      v.z = selu_f(acc[i][j * 4 + 2] + bv[j * 4 + 2]);
-      v.w = selu_f(acc[i][j * 4 + 3] + bv[j * 4 + 3]);
+      if (ACT) {
+        v.x = selu_f(acc[i][j * 4 + 0] + bv[j * 4 + 0]);
+        v.y = selu_f(acc[i][j * 4 + 1] + bv[j * 4 + 1]);
+        v.z = selu_f(acc[i][j * 4 + 2] + bv[j * 4 + 2]);
+        v.w = selu_f(acc[i][j * 4 + 3] + bv[j * 4 + 3]);
+      } else {
+        v = make_float4(acc[i][j * 4 + 0], acc[i][j * 4 + 1], acc[i][j * 4 + 2], acc[i][j * 4 + 3]);
+      }
       *reinterpret_cast<float4*>(d + j * (4 * C::NT)) = v;
     }
   }

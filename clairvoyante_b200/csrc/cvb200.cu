@@ -14,6 +14,7 @@
 #include "fwd_simt.cuh"
 #include "fc4_tc.cuh"
 #include "conv_tc.cuh"
+#include <math.h>
 #include <stdlib.h>
 #include <sys/mman.h>
 #include "train_simt.cuh"
@@ -167,7 +168,7 @@ extern "C" int cvb_create(int variant, int device, cvb_model** out) {
   CK(cudaMalloc(&m->d_params, pb)); CK(cudaMemset(m->d_params, 0, pb));
   CK(cudaMalloc(&m->d_m, pb));      CK(cudaMemset(m->d_m, 0, pb));
   CK(cudaMalloc(&m->d_v, pb));      CK(cudaMemset(m->d_v, 0, pb));
-  CK(cudaMalloc(&m->d_grad, pb + 64)); CK(cudaMemset(m->d_grad, 0, pb + 64));
+  CK(cudaMalloc(&m->d_grad, pb + 256)); CK(cudaMemset(m->d_grad, 0, pb + 256));
   m->p2_rows = ((CHUNK * 28 + 160 + 29) / 30) * 30;
   m->p1_rows = ((CHUNK * 30 + 160 + 28) / 29) * 29;
   const size_t p2_bytes = std::max((size_t)CHUNK * m->p2_site * 4, (size_t)m->p2_rows * 128 * 2 * 2) + 4096;
@@ -550,7 +551,7 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       auto k = k_fc4<F>;
       CK(set_smem(k, F::SMEM_BYTES));
       int grid = (int)((n + F::M - 1) / F::M);
-      k<<<grid, 256, F::SMEM_BYTES, st>>>(m->d_p3, n, 4608, m->var("fc4/kernel"), m->var("fc4/bias"), m->d_h4);
+      k<<<grid, 256, F::SMEM_BYTES, st>>>(m->d_p3, n, 4608, m->var("fc4/kernel"), m->var("fc4/bias"), m->d_h4, 336, 336);
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
     }
@@ -559,7 +560,7 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       auto k = k_fc4<F5>;
       CK(set_smem(k, F5::SMEM_BYTES));
       int grid = (int)((n + F5::M - 1) / F5::M);
-      k<<<grid, 256, F5::SMEM_BYTES, st>>>(m->d_h4, n, 336, m->var("fc5/kernel"), m->var("fc5/bias"), m->d_h5);
+      k<<<grid, 256, F5::SMEM_BYTES, st>>>(m->d_h4, n, 336, m->var("fc5/kernel"), m->var("fc5/bias"), m->d_h5, 168, 168);
       CK(cudaGetLastError());
       k_heads<336, 168><<<(int)((n + 15) / 16), 256, 0, st>>>(m->d_h4, m->d_h5, n, head_ptrs(m), out16, logits16);
       CK(cudaGetLastError());
@@ -594,7 +595,7 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       auto k = k_fc4<F>;
       CK(set_smem(k, F::SMEM_BYTES));
       int grid = (int)((n + F::M - 1) / F::M);
-      k<<<grid, 256, F::SMEM_BYTES, st>>>(m->d_p3, n, 4224, m->var("fc4/kernel"), m->var("fc4/bias"), m->d_h4);
+      k<<<grid, 256, F::SMEM_BYTES, st>>>(m->d_p3, n, 4224, m->var("fc4/kernel"), m->var("fc4/bias"), m->d_h4, 36, 36);
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
     }
@@ -767,21 +768,304 @@ extern "C" int cvb_free_pinned(void* p) {
 }
 
 // ------------------------------------------------------------------------------------
-// loss / training (train_simt.cuh)
+// loss / training (train_simt.cuh).  v3 only in this round; fp32 SIMT kernels.
 // ------------------------------------------------------------------------------------
+static const int64_t TRAIN_CHUNK = 5120;  // sites per micro-chunk (activations + gradients ~180 KB/site)
+
+static int ensure_train_work(cvb_model* m) {
+  if (m->train) return 0;
+  if (m->variant != CVB_V3) return fail("loss/training kernels are built for clairvoyante_v3 only in this round");
+  TrainWork* w = new TrainWork();
+  w->cap = TRAIN_CHUNK;
+  const int64_t c = w->cap;
+  struct Item { float** p; int64_t n; };
+  Item items[] = {
+      {&w->x, c * 528}, {&w->y, c * 16}, {&w->c1, c * 33 * 64}, {&w->p1p, c * 30 * 64}, {&w->c2, c * 29 * 128},
+      {&w->p2p, c * 28 * 128}, {&w->c3, c * 26 * 192}, {&w->p3, c * 24 * 192}, {&w->h4, c * 336}, {&w->d4, c * 336},
+      {&w->h5, c * 168}, {&w->logits, c * 16}, {&w->out16, c * 16}, {&w->dlog, c * 16}, {&w->g5, c * 176},
+      {&w->g4, c * 336}, {&w->g4b, c * 336}, {&w->gp3, c * 24 * 192}, {&w->g3p, c * 28 * 192}, {&w->gp2, c * 26 * 128},
+      {&w->g2p, c * 30 * 128}, {&w->gp1, c * 29 * 64}, {&w->g1, c * 33 * 64}, {&w->w3t, 3 * 4 * 48 * 32},
+      {&w->w2t, 2 * 4 * 32 * 16}, {&w->w4t, 336 * 4608}, {&w->w5t, 176 * 336}, {&w->tmpb, 336 * 16}, {&w->tmph, 168 * 16},
+      {&w->loss, 16}};
+  int64_t total = 0;
+  for (auto& it : items) total += (it.n + 63) / 64 * 64;
+  CK(cudaMalloc(&w->all, (size_t)total * 4));
+  CK(cudaMemset(w->all, 0, (size_t)total * 4));  // padding rows / columns of the padded layouts stay zero forever
+  int64_t off = 0;
+  for (auto& it : items) { *it.p = w->all + off; off += (it.n + 63) / 64 * 64; }
+  m->train = w;
+  return 0;
+}
+
+static inline int gsz(int64_t total, int block = 256) { return (int)std::min<int64_t>((total + block - 1) / block, 148 * 16); }
+
+// training-mode forward of one micro-chunk already resident in tw->x: keeps every SELU output
+static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, int64_t index0, cudaStream_t st) {
+  TrainWork* w = m->train;
+  const int sms = m->num_sms;
+  {
+    using C = ConvCfg<4, 16, 1, 33, 6, 8, 8>;
+    using L = ConvLayerSmem<C, 1>;
+    auto k = k_conv_layer<C, 1, 256, false, true>;
+    CK(set_smem(k, L::SMEM_BYTES));
+    k<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, 2 * sms), 256, L::SMEM_BYTES, st>>>(w->x, nc, m->var("conv1/kernel"),
+                                                                                          m->var("conv1/bias"), w->c1, nullptr);
+    CK(cudaGetLastError());
+    k_pool_fwd<5><<<gsz(nc * 29 * 16), 256, 0, st>>>(w->c1, nc, 33, 64, w->p1p, 30, 0);
+  }
+  {
+    using C = ConvCfg<16, 32, 2, 29, 4, 8, 8>;
+    using L = ConvLayerSmem<C, 1>;
+    auto k = k_conv_layer<C, 1, 256, false, true>;
+    CK(set_smem(k, L::SMEM_BYTES));
+    k<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->p1p, nc, m->var("conv2/kernel"),
+                                                                                      m->var("conv2/bias"), w->c2, nullptr);
+    CK(cudaGetLastError());
+    k_pool_fwd<4><<<gsz(nc * 26 * 32), 256, 0, st>>>(w->c2, nc, 29, 128, w->p2p, 28, 1);
+  }
+  {
+    using C = ConvCfg<32, 48, 3, 26, 3, 8, 8>;
+    using L = ConvLayerSmem<C, 1>;
+    auto k = k_conv_layer<C, 1, 256, false, true>;
+    CK(set_smem(k, L::SMEM_BYTES));
+    k<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->p2p, nc, m->var("conv3/kernel"),
+                                                                                      m->var("conv3/bias"), w->c3, nullptr);
+    CK(cudaGetLastError());
+    k_pool_fwd<3><<<gsz(nc * 24 * 48), 256, 0, st>>>(w->c3, nc, 26, 192, w->p3, 24, 0);
+  }
+  {
+    using F = FcCfg<336, 21, 16, 12, 8>;
+    auto k = k_fc4<F, true>;
+    CK(set_smem(k, F::SMEM_BYTES));
+    k<<<(int)((nc + F::M - 1) / F::M), 256, F::SMEM_BYTES, st>>>(w->p3, nc, 4608, m->var("fc4/kernel"), m->var("fc4/bias"), w->h4,
+                                                                 336, 336);
+    CK(cudaGetLastError());
+  }
+  const float* d4 = w->h4;
+  if (drop4 > 0.f) {
+    k_dropout_fwd<<<gsz(nc * 336), 256, 0, st>>>(w->h4, w->d4, nc * 336, index0, seed, drop_const(drop4));
+    d4 = w->d4;
+  }
+  {
+    using F5 = FcCfg<168, 21, 8, 12, 8>;
+    auto k = k_fc4<F5, true>;
+    CK(set_smem(k, F5::SMEM_BYTES));
+    k<<<(int)((nc + F5::M - 1) / F5::M), 256, F5::SMEM_BYTES, st>>>(d4, nc, 336, m->var("fc5/kernel"), m->var("fc5/bias"), w->h5, 168,
+                                                                    168);
+    CK(cudaGetLastError());
+    k_heads<336, 168><<<(int)((nc + 15) / 16), 256, 0, st>>>(d4, w->h5, nc, head_ptrs(m), w->out16, w->logits);
+    CK(cudaGetLastError());
+  }
+  m->launches += 9 + (drop4 > 0.f ? 1 : 0);
+  return 0;
+}
+
+static float* gvar(cvb_model* m, const char* name) { return m->d_grad + m->info(name)->offset; }
+
+static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, int64_t index0, cudaStream_t st) {
+  TrainWork* w = m->train;
+  const int sms = m->num_sms;
+  const float* d4 = drop4 > 0.f ? w->d4 : w->h4;
+  // heads: weight / bias gradients
+  CK(cudaMemsetAsync(w->tmpb, 0, 336 * 16 * 4, st));
+  CK(cudaMemsetAsync(w->tmph, 0, 168 * 16 * 4, st));
+  k_gemm_tn<<<dim3((336 + 63) / 64, 1), 256, 0, st>>>(d4, 336, w->dlog, 16, w->tmpb, 16, 336, 16, nc);
+  k_gemm_tn<<<dim3((168 + 63) / 64, 1), 256, 0, st>>>(w->h5, 168, w->dlog, 16, w->tmph, 16, 168, 16, nc);
+  HeadG hg{gvar(m, "YBaseChangeSigmoid/kernel"), gvar(m, "YZygosityFC/kernel"), gvar(m, "YVarTypeFC/kernel"),
+           gvar(m, "YIndelLengthFC/kernel")};
+  k_scatter_heads<<<(336 * 4 + 255) / 256, 256, 0, st>>>(w->tmpb, w->tmph, 336, 168, hg);
+  k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->dlog + 0, nc, 16, 4, gvar(m, "YBaseChangeSigmoid/bias"));
+  k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->dlog + 4, nc, 16, 2, gvar(m, "YZygosityFC/bias"));
+  k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->dlog + 6, nc, 16, 4, gvar(m, "YVarTypeFC/bias"));
+  k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->dlog + 10, nc, 16, 6, gvar(m, "YIndelLengthFC/bias"));
+  // heads -> g4 (base branch), g5 (x selu')
+  HeadW hw{m->var("YBaseChangeSigmoid/kernel"), m->var("YZygosityFC/kernel"), m->var("YVarTypeFC/kernel"),
+           m->var("YIndelLengthFC/kernel")};
+  k_heads_bwd<<<gsz(nc * (336 + 168)), 256, 0, st>>>(w->dlog, w->h5, nc, 336, 168, hw, w->g4, w->g5, 176);
+  // FC5
+  k_gemm_tn<<<dim3((336 + 63) / 64, (168 + 63) / 64), 256, 0, st>>>(d4, 336, w->g5, 176, gvar(m, "fc5/kernel"), 168, 336, 168, nc);
+  k_colsum<<<dim3((168 + 31) / 32, 32), 256, 0, st>>>(w->g5, nc, 176, 168, gvar(m, "fc5/bias"));
+  {
+    using F = FcCfg<336, 21, 16, 12, 8>;
+    auto k = k_fc4<F, false>;
+    CK(set_smem(k, F::SMEM_BYTES));
+    k<<<(int)((nc + F::M - 1) / F::M), 256, F::SMEM_BYTES, st>>>(w->g5, nc, 176, w->w5t, nullptr, w->g4b, 336, 336);
+    CK(cudaGetLastError());
+  }
+  k_fc4_bwd_elem<<<gsz(nc * 336), 256, 0, st>>>(w->g4, w->g4b, w->h4, nc * 336, index0, seed, drop_const(drop4), drop4 > 0.f ? 1 : 0);
+  // FC4
+  k_gemm_tn<<<dim3(4608 / 64, (336 + 63) / 64), 256, 0, st>>>(w->p3, 4608, w->g4, 336, gvar(m, "fc4/kernel"), 336, 4608, 336, nc);
+  k_colsum<<<dim3((336 + 31) / 32, 32), 256, 0, st>>>(w->g4, nc, 336, 336, gvar(m, "fc4/bias"));
+  {
+    using F = FcCfg<192, 24, 8, 10, 8>;
+    auto k = k_fc4<F, false>;
+    CK(set_smem(k, F::SMEM_BYTES));
+    k<<<dim3((unsigned)((nc + F::M - 1) / F::M), 4608 / 192), 256, F::SMEM_BYTES, st>>>(w->g4, nc, 336, w->w4t, nullptr, w->gp3, 4608,
+                                                                                       4608);
+    CK(cudaGetLastError());
+  }
+  // conv3
+  k_pool_bwd_selu<3><<<gsz(nc * 26 * 192), 256, 0, st>>>(w->gp3, w->c3, nc, 26, 192, w->g3p, 28, 1);
+  {
+    using W = WgradCfg<32, 48, 3, 26, 4, 12, 4>;
+    auto k = k_conv_wgrad<32, 48, 3, 26, 4, 12, 4>;
+    CK(set_smem(k, W::SMEM_BYTES));
+    k<<<(int)std::min<int64_t>((nc + 3) / 4, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->p2p, w->g3p, 28, 1, nc, gvar(m, "conv3/kernel"));
+    CK(cudaGetLastError());
+    k_colsum<<<dim3(2, 128), 256, 0, st>>>(w->g3p, nc * 28 * 4, 48, 48, gvar(m, "conv3/bias"));
+    using C = ConvCfg<48, 32, 3, 26, 3, 8, 8, 2>;
+    using L = ConvLayerSmem<C, 1>;
+    auto kd = k_conv_layer<C, 1, 256, false, false>;
+    CK(set_smem(kd, L::SMEM_BYTES));
+    kd<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->g3p, nc, w->w3t, nullptr, w->gp2, nullptr);
+    CK(cudaGetLastError());
+  }
+  // conv2
+  k_pool_bwd_selu<4><<<gsz(nc * 29 * 128), 256, 0, st>>>(w->gp2, w->c2, nc, 29, 128, w->g2p, 30, 1);
+  {
+    using W = WgradCfg<16, 32, 2, 29, 4, 4, 4>;
+    auto k = k_conv_wgrad<16, 32, 2, 29, 4, 4, 4>;
+    CK(set_smem(k, W::SMEM_BYTES));
+    k<<<(int)std::min<int64_t>((nc + 3) / 4, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->p1p, w->g2p, 30, 1, nc, gvar(m, "conv2/kernel"));
+    CK(cudaGetLastError());
+    k_colsum<<<dim3(1, 128), 256, 0, st>>>(w->g2p, nc * 30 * 4, 32, 32, gvar(m, "conv2/bias"));
+    using C = ConvCfg<32, 16, 2, 29, 4, 8, 8, 2>;
+    using L = ConvLayerSmem<C, 1>;
+    auto kd = k_conv_layer<C, 1, 256, false, false>;
+    CK(set_smem(kd, L::SMEM_BYTES));
+    kd<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->g2p, nc, w->w2t, nullptr, w->gp1, nullptr);
+    CK(cudaGetLastError());
+  }
+  // conv1 (no data gradient needed)
+  k_pool_bwd_selu<5><<<gsz(nc * 33 * 64), 256, 0, st>>>(w->gp1, w->c1, nc, 33, 64, w->g1, 33, 0);
+  {
+    using W = WgradCfg<4, 16, 1, 33, 1, 4, 8>;
+    auto k = k_conv_wgrad<4, 16, 1, 33, 1, 4, 8>;
+    CK(set_smem(k, W::SMEM_BYTES));
+    k<<<(int)std::min<int64_t>((nc + 7) / 8, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->x, w->g1, 33, 0, nc, gvar(m, "conv1/kernel"));
+    CK(cudaGetLastError());
+    k_colsum<<<dim3(1, 128), 256, 0, st>>>(w->g1, nc * 33 * 4, 16, 16, gvar(m, "conv1/bias"));
+  }
+  CK(cudaGetLastError());
+  m->launches += 27;
+  return 0;
+}
+
+static int train_prepare_weights(cvb_model* m, cudaStream_t st) {
+  TrainWork* w = m->train;
+  k_flip_conv_weights<<<(3 * 4 * 32 * 48 + 255) / 256, 256, 0, st>>>(m->var("conv3/kernel"), 3, 32, 48, w->w3t);
+  k_flip_conv_weights<<<(2 * 4 * 16 * 32 + 255) / 256, 256, 0, st>>>(m->var("conv2/kernel"), 2, 16, 32, w->w2t);
+  k_transpose<<<dim3((336 + 31) / 32, 4608 / 32), dim3(32, 8), 0, st>>>(m->var("fc4/kernel"), 4608, 336, w->w4t);
+  k_transpose<<<dim3((168 + 31) / 32, (336 + 31) / 32), dim3(32, 8), 0, st>>>(m->var("fc5/kernel"), 336, 168, w->w5t);
+  CK(cudaGetLastError());
+  m->launches += 4;
+  return 0;
+}
+
+// forward + loss (+ backward) over a host batch in micro-chunks; loss terms accumulate in train->loss[0..3]
+static int train_pass(cvb_model* m, const float* x, const float* y, int64_t n, float drop4, uint64_t seed, bool backward) {
+  if (ensure_train_work(m)) return 1;
+  TrainWork* w = m->train;
+  cudaStream_t st = m->s_comp;
+  CK(cudaMemsetAsync(w->loss, 0, 16 * 4, st));
+  if (backward) {
+    CK(cudaMemsetAsync(m->d_grad, 0, (size_t)(m->nparams + 16) * 4, st));
+    if (train_prepare_weights(m, st)) return 1;
+  }
+  for (int64_t s0 = 0; s0 < n; s0 += w->cap) {
+    const int64_t nc = std::min<int64_t>(w->cap, n - s0);
+    CK(cudaMemcpyAsync(w->x, x + s0 * 528, (size_t)nc * 528 * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(w->y, y + s0 * 16, (size_t)nc * 16 * 4, cudaMemcpyHostToDevice, st));
+    if (train_forward(m, nc, drop4, seed, s0 * 336, st)) return 1;
+    k_loss_grad<<<gsz(nc, 128), 128, 0, st>>>(w->logits, w->out16, w->y, nc, backward ? w->dlog : nullptr, w->loss);
+    CK(cudaGetLastError());
+    m->launches += 1;
+    if (backward && train_backward(m, nc, drop4, seed, s0 * 336, st)) return 1;
+  }
+  return 0;
+}
+
 extern "C" int cvb_loss_host(cvb_model* m, const float* x, const float* y, int64_t n, float* loss) {
   if (!m || !loss) return fail("cvb_loss_host: NULL argument");
-  return fail("cvb_loss_host: not built yet");
+  if (n < 0) return fail("cvb_loss_host: negative n");
+  *loss = 0.f;
+  if (n == 0) return 0;
+  if (!x || !y) return fail("cvb_loss_host: NULL buffer");
+  CK(cudaSetDevice(m->device));
+  if (train_pass(m, x, y, n, 0.f, 0, false)) return 1;
+  float l[4];
+  CK(cudaMemcpyAsync(l, m->train->loss, 16, cudaMemcpyDeviceToHost, m->s_comp));
+  CK(cudaStreamSynchronize(m->s_comp));
+  *loss = l[0] + l[1] + l[2] + l[3];  // getLoss feeds lambda = 0 (clairvoyante_v3.py:207-216)
+  return 0;
 }
-extern "C" int cvb_train_step_host(cvb_model* m, const float* x, const float* y, int64_t n, float lr, float l2,
-                                   float drop4, uint64_t dropout_seed, int apply_update, float* loss5) {
+
+static const char* kKernels[] = {"conv1/kernel", "conv2/kernel", "conv3/kernel", "fc4/kernel", "fc5/kernel",
+                                 "YBaseChangeSigmoid/kernel", "YZygosityFC/kernel", "YVarTypeFC/kernel", "YIndelLengthFC/kernel"};
+
+// loss6 = [total, loss1, loss2, loss3, loss4, lossL2] from the (possibly all-reduced) sums at d_grad[nparams..+4)
+static int finish_losses(cvb_model* m, float l2, float* loss6) {
+  cudaStream_t st = m->s_comp;
+  TrainWork* w = m->train;
+  CK(cudaMemsetAsync(w->loss + 8, 0, 4, st));
+  for (const char* k : kKernels) {
+    const VarInfo* v = m->info(k);
+    k_sumsq<<<gsz(v->numel), 256, 0, st>>>(m->d_params + v->offset, v->numel, w->loss + 8);
+  }
+  CK(cudaGetLastError());
+  float l[5];
+  CK(cudaMemcpyAsync(l, m->d_grad + m->nparams, 16, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(l + 4, w->loss + 8, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (loss6) {
+    loss6[5] = l2 * 0.5f * l[4];
+    for (int i = 0; i < 4; ++i) loss6[1 + i] = l[i];
+    loss6[0] = l[0] + l[1] + l[2] + l[3] + loss6[5];
+  }
+  m->launches += 9;
+  return 0;
+}
+
+extern "C" int cvb_apply_adam(cvb_model* m, float lr, float l2, float* loss6) {
+  if (!m) return fail("cvb_apply_adam: NULL model");
+  if (!m->train) return fail("cvb_apply_adam: no gradients (call cvb_train_step_host first)");
+  CK(cudaSetDevice(m->device));
+  if (finish_losses(m, l2, loss6)) return 1;  // session.run fetches the loss of the pre-update weights
+  cudaStream_t st = m->s_comp;
+  m->step += 1;
+  const double b1 = 0.9, b2 = 0.999;
+  const float lr_t = (float)(lr * sqrt(1.0 - pow(b2, (double)m->step)) / (1.0 - pow(b1, (double)m->step)));
+  for (auto& v : m->vars) {
+    const bool is_kernel = v.name.find("bias") == std::string::npos;  // clairvoyante_v3.py:150
+    k_adam<<<gsz(v.numel), 256, 0, st>>>(m->d_params + v.offset, m->d_m + v.offset, m->d_v + v.offset, m->d_grad + v.offset, v.numel,
+                                         lr_t, (float)b1, (float)b2, 1e-8f, is_kernel ? l2 : 0.f);
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  m->launches += (int64_t)m->vars.size();
+  m->tc_weights_dirty = true;
+  return 0;
+}
+
+extern "C" int cvb_train_step_host(cvb_model* m, const float* x, const float* y, int64_t n, float lr, float l2, float drop4,
+                                   uint64_t dropout_seed, int apply_update, float* loss6) {
   if (!m) return fail("cvb_train_step_host: NULL model");
-  return fail("cvb_train_step_host: not built yet");
+  if (n <= 0) return fail("cvb_train_step_host: empty batch");
+  if (!x || !y) return fail("cvb_train_step_host: NULL buffer");
+  if (drop4 < 0.f || drop4 >= 1.f) return fail("cvb_train_step_host: dropout rate %g outside [0,1)", drop4);
+  CK(cudaSetDevice(m->device));
+  if (train_pass(m, x, y, n, drop4, dropout_seed, true)) return 1;
+  // loss sums ride at the tail of the gradient buffer so that one all-reduce covers both
+  CK(cudaMemcpyAsync(m->d_grad + m->nparams, m->train->loss, 16, cudaMemcpyDeviceToDevice, m->s_comp));
+  if (apply_update) return cvb_apply_adam(m, lr, l2, loss6);
+  CK(cudaStreamSynchronize(m->s_comp));
+  return 0;
 }
+
 extern "C" int cvb_grad_buffer(cvb_model* m, void** dev_ptr, int64_t* numel) {
   if (!m || !dev_ptr || !numel) return fail("cvb_grad_buffer: NULL argument");
   *dev_ptr = m->d_grad;
-  *numel = m->nparams + 8;
+  *numel = m->nparams + 4;  // gradients (16-byte aligned slots per variable) followed by the four loss sums
   return 0;
 }
 extern "C" int cvb_get_gradient(cvb_model* m, const char* name, float* host, int64_t n) {
@@ -793,8 +1077,4 @@ extern "C" int cvb_get_gradient(cvb_model* m, const char* name, float* host, int
   CK(cudaStreamSynchronize(m->s_comp));
   CK(cudaMemcpy(host, m->d_grad + v->offset, (size_t)n * 4, cudaMemcpyDeviceToHost));
   return 0;
-}
-extern "C" int cvb_apply_adam(cvb_model* m, float lr, float l2) {
-  if (!m) return fail("cvb_apply_adam: NULL model");
-  return fail("cvb_apply_adam: not built yet");
 }

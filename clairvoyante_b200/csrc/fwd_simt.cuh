@@ -311,7 +311,8 @@ __device__ __forceinline__ void conv_tile_load_async(float* __restrict__ buf, co
 // SPLIT = false: out is fp32 [n][HP][4*COUT].
 // SPLIT = true : out is reinterpreted as two fp16 tensors of the same shape, hi at out and lo at
 //                out_lo, with hi + lo ~= value (operands of the split-fp16 tensor-core FC4, fc4_tc.cuh).
-template <class C, int POOL, int NTHREADS, bool SPLIT>
+// ACT = false: no bias / activation (data-gradient convolutions of the training path)
+template <class C, int POOL, int NTHREADS, bool SPLIT, bool ACT = true>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_conv_layer(const float* __restrict__ in, int64_t n, const float* __restrict__ wg, const float* __restrict__ bg,
              float* __restrict__ out, void* __restrict__ out_lo) {
@@ -324,7 +325,7 @@ k_conv_layer(const float* __restrict__ in, int64_t n, const float* __restrict__ 
   float* bufs[2] = {smem + L::BUF0, smem + L::BUF0 + L::BUF};
   const int64_t ntiles = (n + C::S - 1) / C::S;
   for (int i = tid; i < C::W_FLOATS / 4; i += NTHREADS) cp_async16(ws + i * 4, wg + i * 4);
-  if (tid < C::COUT) bs[tid] = bg[tid];
+  if (tid < C::COUT) bs[tid] = ACT ? bg[tid] : 0.f;
   int64_t tile = blockIdx.x;
   if (tile < ntiles) conv_tile_load_async<C>(bufs[0], in, tile * C::S, n, tid, NTHREADS);
   cp_async_commit();
@@ -339,7 +340,7 @@ k_conv_layer(const float* __restrict__ in, int64_t n, const float* __restrict__ 
     float acc[C::TM][C::TN];
     conv_compute<C>(cur, ws, th, acc);
     __syncthreads();  // every thread is done reading the input tile
-    conv_store_selu_smem<C, C::HOUT, L::ORS, 0>(acc, bs, th, cur);
+    conv_store_selu_smem<C, C::HOUT, L::ORS, 0, ACT>(acc, bs, th, cur);
     __syncthreads();
     const int64_t site0 = tile * C::S;
     constexpr int OF4 = C::COUT;  // float4 per output row
@@ -386,10 +387,11 @@ struct FcCfg {
   static_assert(CT * CPT == N && CPT % 4 == 0 && CT * RT <= THREADS, "fc tile shape");
 };
 
+// ldw = row stride of W (>= F::N; W points at the first column of this CTA's N-tile)
 template <class F>
 __device__ __forceinline__ void fc_chunk_load(float* __restrict__ st, const float* __restrict__ A,
                                               const float* __restrict__ W, int64_t site0, int64_t n, int K, int k0,
-                                              int tid) {
+                                              int tid, int ldw) {
   float* as = st;
   float* bs = st + F::A_FLOATS;
   for (int i = tid; i < F::M * (F::KC / 4); i += F::THREADS) {
@@ -397,13 +399,21 @@ __device__ __forceinline__ void fc_chunk_load(float* __restrict__ st, const floa
     bool ok = site0 + s < n;
     cp_async16_zfill(as + s * F::LDA + q * 4, A + (ok ? site0 + s : 0) * (int64_t)K + k0 + q * 4, ok);
   }
-  for (int i = tid; i < F::KC * F::N / 4; i += F::THREADS) cp_async16(bs + i * 4, W + (int64_t)k0 * F::N + i * 4);
+  for (int i = tid; i < F::KC * F::N / 4; i += F::THREADS) {
+    const int r = i / (F::N / 4), q = i - r * (F::N / 4);
+    cp_async16(bs + i * 4, W + (int64_t)(k0 + r) * ldw + q * 4);
+  }
 }
 
-template <class F>
+// EPI = true: out = SELU(A @ W + bias);  EPI = false: out = A @ W (gradient GEMMs).  blockIdx.y selects an
+// N-tile of width F::N inside matrices whose row strides are ldw (W) and ldo (out).
+template <class F, bool EPI = true>
 __global__ void __launch_bounds__(256, 1)
 k_fc4(const float* __restrict__ A, int64_t n, int K, const float* __restrict__ W, const float* __restrict__ bias,
-      float* __restrict__ out) {
+      float* __restrict__ out, int ldw, int ldo) {
+  W += (int64_t)blockIdx.y * F::N;
+  out += (int64_t)blockIdx.y * F::N;
+  if (EPI) bias += (int64_t)blockIdx.y * F::N;
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
   const int ct = tid % F::CT, rt = tid / F::CT;
@@ -417,7 +427,7 @@ k_fc4(const float* __restrict__ A, int64_t n, int K, const float* __restrict__ W
     for (int j = 0; j < F::CPT; ++j) acc[i][j] = 0.f;
 #pragma unroll
   for (int s = 0; s < F::STAGES - 1; ++s) {
-    if (s < nchunks) fc_chunk_load<F>(smem + s * F::STAGE_FLOATS, A, W, site0, n, K, s * F::KC, tid);
+    if (s < nchunks) fc_chunk_load<F>(smem + s * F::STAGE_FLOATS, A, W, site0, n, K, s * F::KC, tid, ldw);
     cp_async_commit();
   }
   for (int c = 0; c < nchunks; ++c) {
@@ -425,7 +435,7 @@ k_fc4(const float* __restrict__ A, int64_t n, int K, const float* __restrict__ W
     __syncthreads();  // chunk c landed; everyone finished chunk c-1 (its stage is refilled below)
     {
       int cn = c + F::STAGES - 1;
-      if (cn < nchunks) fc_chunk_load<F>(smem + (cn % F::STAGES) * F::STAGE_FLOATS, A, W, site0, n, K, cn * F::KC, tid);
+      if (cn < nchunks) fc_chunk_load<F>(smem + (cn % F::STAGES) * F::STAGE_FLOATS, A, W, site0, n, K, cn * F::KC, tid, ldw);
       cp_async_commit();
     }
     if (active) {
@@ -462,17 +472,21 @@ k_fc4(const float* __restrict__ A, int64_t n, int K, const float* __restrict__ W
 #pragma unroll
   for (int j = 0; j < F::CPT / 4; ++j) {
     const int col = (ct + F::CT * j) * 4;
-    const float4 bv = *reinterpret_cast<const float4*>(bias + col);
+    const float4 bv = EPI ? *reinterpret_cast<const float4*>(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < F::TMS; ++i) {
       const int64_t site = site0 + rt + F::RT * i;
       if (site >= n) continue;
       float4 v;
-      v.x = selu_f(acc[i][j * 4 + 0] + bv.x);
-      v.y = selu_f(acc[i][j * 4 + 1] + bv.y);
-      v.z = selu_f(acc[i][j * 4 + 2] + bv.z);
-      v.w = selu_f(acc[i][j * 4 + 3] + bv.w);
-      *reinterpret_cast<float4*>(out + site * F::N + col) = v;
+      if (EPI) {
+        v.x = selu_f(acc[i][j * 4 + 0] + bv.x);
+        v.y = selu_f(acc[i][j * 4 + 1] + bv.y);
+        v.z = selu_f(acc[i][j * 4 + 2] + bv.z);
+        v.w = selu_f(acc[i][j * 4 + 3] + bv.w);
+      } else {
+        v = make_float4(acc[i][j * 4 + 0], acc[i][j * 4 + 1], acc[i][j * 4 + 2], acc[i][j * 4 + 3]);
+      }
+      *reinterpret_cast<float4*>(out + site * ldo + col) = v;
     }
   }
 }

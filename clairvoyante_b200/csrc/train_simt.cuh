@@ -1,7 +1,388 @@
-// train_simt.cuh -- loss / backward / Adam kernels (filled in after the forward path).
+// train_simt.cuh -- loss, backward and optimiser kernels (fp32 SIMT) for
+//   loss          clairvoyante_v3.py:140-152  (SUM over the batch; L2 on non-bias variables)
+//   training_op   clairvoyante_v3.py:174      (tf.train.AdamOptimizer(lr).minimize(loss), TF-1.x update rule)
+//   dropout_selu  selu.py:34-69               (alpha-dropout on the FC4 output, rate 0.5 by default)
+// The forward pass of a training step reuses the inference kernels in their "keep everything" form
+// (k_conv_layer<.., POOL=1> + k_pool_fwd) so that every SELU output is available to the backward pass.
+// Data-gradient convolutions reuse k_conv_layer with flipped/transposed weights (k_flip_conv_weights),
+// ACT=false and pad-left 2; weight gradients are k_conv_wgrad (convs) and k_gemm_tn (dense layers).
 #pragma once
-#include "common.cuh"
+#include "conv_simt.cuh"
+
 namespace cvb {
-struct TrainWork {};
-static inline void train_work_free(TrainWork* w) { delete w; }
+
+struct TrainWork {
+  int64_t cap = 0;  // sites per micro-chunk
+  float *x = nullptr, *y = nullptr;
+  float *c1 = nullptr, *p1p = nullptr, *c2 = nullptr, *p2p = nullptr, *c3 = nullptr, *p3 = nullptr;
+  float *h4 = nullptr, *d4 = nullptr, *h5 = nullptr, *logits = nullptr, *out16 = nullptr;
+  float *dlog = nullptr, *g5 = nullptr, *g4 = nullptr, *g4b = nullptr, *gp3 = nullptr, *g3p = nullptr, *gp2 = nullptr;
+  float *g2p = nullptr, *gp1 = nullptr, *g1 = nullptr;
+  float *w3t = nullptr, *w2t = nullptr, *w4t = nullptr, *w5t = nullptr, *tmpb = nullptr, *tmph = nullptr;
+  float* loss = nullptr;  // [8]: loss1..4 (sums), sum of squares of kernels, spare
+  float* all = nullptr;   // single allocation backing everything above
+};
+static inline void train_work_free(TrainWork* w) {
+  if (!w) return;
+  cudaFree(w->all);
+  delete w;
+}
+
+// ---- counter-based uniform in [0,1): splitmix64 finaliser of (seed, index); reproduced on the host for tests
+__host__ __device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+// SELU-dropout constants for keep probability `keep` (selu.py:59-62; fixedPointMean 0, fixedPointVar 1)
+struct DropConst { float keep, a, b, alpha; };
+static inline DropConst drop_const(float rate) {
+  DropConst d;
+  d.alpha = -1.7580993408473766f;
+  d.keep = 1.0f - rate;
+  d.a = sqrtf(1.0f / (d.keep * ((1.0f - d.keep) * d.alpha * d.alpha + 1.0f)));
+  d.b = -d.a * ((1.0f - d.keep) * d.alpha);
+  return d;
+}
+
+// ---- (P,1) VALID max-pool over rows: in [n][H][C] -> out [n][OROWS][C] at rows OR0..OR0+H-P  (C multiple of 4)
+template <int P>
+__global__ void k_pool_fwd(const float* __restrict__ in, int64_t n, int H, int C, float* __restrict__ out, int OROWS, int OR0) {
+  const int HP = H - P + 1, C4 = C / 4;
+  const int64_t total = n * HP * C4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % C4);
+    const int64_t t = i / C4;
+    const int h = (int)(t % HP);
+    const int64_t s = t / HP;
+    const float4* src = reinterpret_cast<const float4*>(in + (s * H + h) * C) + q;
+    float4 v = src[0];
+#pragma unroll
+    for (int j = 1; j < P; ++j) v = max4(v, src[j * C4]);
+    reinterpret_cast<float4*>(out + (s * OROWS + OR0 + h) * C)[q] = v;
+  }
+}
+
+// ---- max-pool backward fused with the SELU derivative of the conv output c (post-SELU values):
+//   dpre[s][h][k] = selu'(c[h]) * sum_{windows j containing h whose FIRST maximum is at h} dp[s][j][k]
+// written to out [n][OROWS][C] at row OR0 + h (the padded layout the data-gradient conv reads).
+template <int P>
+__global__ void k_pool_bwd_selu(const float* __restrict__ dp, const float* __restrict__ c, int64_t n, int H, int C,
+                                float* __restrict__ out, int OROWS, int OR0) {
+  const int HP = H - P + 1;
+  const int64_t total = n * H * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % C);
+    const int64_t t = i / C;
+    const int h = (int)(t % H);
+    const int64_t s = t / H;
+    const float* cs = c + s * H * C + k;
+    const float ch = cs[h * C];
+    float g = 0.f;
+#pragma unroll
+    for (int d = 0; d < P; ++d) {
+      const int j = h - d;  // window start
+      if (j < 0 || j >= HP) continue;
+      bool is_first_max = true;
+#pragma unroll
+      for (int e = 0; e < P; ++e) {
+        const float v = cs[(j + e) * C];
+        if (e < d ? (v >= ch) : (v > ch)) is_first_max = false;  // earlier element equal or larger, later strictly larger
+      }
+      if (is_first_max) g += dp[(s * HP + j) * C + k];
+    }
+    out[(s * OROWS + OR0 + h) * C + k] = g * selu_grad_from_out(ch);
+  }
+}
+
+// ---- SELU dropout forward on FC4's output (selu.py:54-62): d4 = a*(h4*mask + alpha*(1-mask)) + b
+__global__ void k_dropout_fwd(const float* __restrict__ h4, float* __restrict__ d4, int64_t total, int64_t index0,
+                              uint64_t seed, DropConst dc) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float u = hash_uniform(seed, (uint64_t)(index0 + i));
+    const float mask = floorf(dc.keep + u);  // 1 with probability keep
+    d4[i] = dc.a * (h4[i] * mask + dc.alpha * (1.0f - mask)) + dc.b;
+  }
+}
+
+// ---- loss terms + gradient w.r.t. the 16 head pre-activations
+// logits16: [base pre-sigmoid 4 | SELU(FC)+1e-10 for zyg 2, type 4, len 6]; out16: sigmoid / softmax outputs.
+// dlog[0:4]  = 2 (sigma - y) sigma (1 - sigma)                      (loss1 = sum (sigma - y)^2)
+// dlog[4:16] = (softmax(z) * sum(y) - y) * selu'(FC) per head         (loss2..4 = sum -y log_softmax(z))
+__global__ void k_loss_grad(const float* __restrict__ logits16, const float* __restrict__ out16, const float* __restrict__ y,
+                            int64_t n, float* __restrict__ dlog, float* __restrict__ loss4) {
+  float l[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
+    const float* lg = logits16 + s * 16;
+    const float* o = out16 + s * 16;
+    const float* yy = y + s * 16;
+    float* d = dlog ? dlog + s * 16 : nullptr;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float e = o[k] - yy[k];
+      l[0] += e * e;
+      if (d) d[k] = 2.f * e * o[k] * (1.f - o[k]);
+    }
+    const int a[3] = {4, 6, 10}, b[3] = {6, 10, 16};
+#pragma unroll
+    for (int hd = 0; hd < 3; ++hd) {
+      float m = lg[a[hd]];
+      for (int k = a[hd] + 1; k < b[hd]; ++k) m = fmaxf(m, lg[k]);
+      float se = 0.f, sy = 0.f;
+      for (int k = a[hd]; k < b[hd]; ++k) { se += expf(lg[k] - m); sy += yy[k]; }
+      const float lse = m + logf(se);
+      for (int k = a[hd]; k < b[hd]; ++k) {
+        l[1 + hd] += -yy[k] * (lg[k] - lse);
+        if (d) d[k] = (o[k] * sy - yy[k]) * selu_grad_from_out(lg[k] - 1e-10f);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float v = l[k];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(loss4 + k, v);
+  }
+}
+
+// ---- back through the heads: g5 = (dlog[4:16] . W_{z,t,l}^T) * selu'(h5);  g4 = dlog[0:4] . Wb^T
+struct HeadW { const float *wb, *wz, *wt, *wl; };
+__global__ void k_heads_bwd(const float* __restrict__ dlog, const float* __restrict__ h5, int64_t n, int N4, int N5, HeadW w,
+                            float* __restrict__ g4, float* __restrict__ g5, int ld5) {
+  const int64_t total = n * (N4 + N5);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i / (N4 + N5);
+    const int k = (int)(i - s * (N4 + N5));
+    const float* d = dlog + s * 16;
+    if (k < N4) {
+      const float* wr = w.wb + k * 4;
+      g4[s * N4 + k] = d[0] * wr[0] + d[1] * wr[1] + d[2] * wr[2] + d[3] * wr[3];
+    } else {
+      const int kk = k - N4;
+      float a = d[4] * w.wz[kk * 2] + d[5] * w.wz[kk * 2 + 1];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) a += d[6 + o] * w.wt[kk * 4 + o];
+#pragma unroll
+      for (int o = 0; o < 6; ++o) a += d[10 + o] * w.wl[kk * 6 + o];
+      g5[s * ld5 + kk] = a * selu_grad_from_out(h5[s * N5 + kk]);
+    }
+  }
+}
+
+// ---- dpre4 = (g4 + g4b) * d(dropout)/d(h4) * selu'(h4)   (d4 = a*h4*mask + ...: derivative a*mask)
+__global__ void k_fc4_bwd_elem(float* __restrict__ g4, const float* __restrict__ g4b, const float* __restrict__ h4,
+                               int64_t total, int64_t index0, uint64_t seed, DropConst dc, int use_dropout) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float f = 1.f;
+    if (use_dropout) f = dc.a * floorf(dc.keep + hash_uniform(seed, (uint64_t)(index0 + i)));
+    g4[i] = (g4[i] + g4b[i]) * f * selu_grad_from_out(h4[i]);
+  }
+}
+
+// ---- C[M][N] += sum_k A[k][m] * B[k][n]   (A: [K][lda], B: [K][ldb], C: [M][ldc]); one CTA per 64x64 tile of C
+__global__ void __launch_bounds__(256)
+k_gemm_tn(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc, int M,
+          int N, int64_t K) {
+  __shared__ __align__(16) float As[16][64 + 4];
+  __shared__ __align__(16) float Bs[16][64 + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  float acc[4][4] = {};
+  for (int64_t k0 = 0; k0 < K; k0 += 16) {
+    for (int i = tid; i < 16 * 16; i += 256) {
+      const int r = i >> 4, q = (i & 15) * 4;
+      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+      if (k0 + r < K) {
+        const float* pa = A + (k0 + r) * lda + m0 + q;
+        const float* pb = B + (k0 + r) * ldb + n0 + q;
+        if (m0 + q + 3 < M) va = *reinterpret_cast<const float4*>(pa);
+        else { float t[4] = {0, 0, 0, 0}; for (int e = 0; e < 4; ++e) if (m0 + q + e < M) t[e] = pa[e]; va = make_float4(t[0], t[1], t[2], t[3]); }
+        if (n0 + q + 3 < N) vb = *reinterpret_cast<const float4*>(pb);
+        else { float t[4] = {0, 0, 0, 0}; for (int e = 0; e < 4; ++e) if (n0 + q + e < N) t[e] = pb[e]; vb = make_float4(t[0], t[1], t[2], t[3]); }
+      }
+      *reinterpret_cast<float4*>(&As[r][q]) = va;
+      *reinterpret_cast<float4*>(&Bs[r][q]) = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, nn = n0 + tx * 4 + j;
+      if (m < M && nn < N) C[(int64_t)m * ldc + nn] += acc[i][j];
+    }
+}
+
+// ---- out[c] += sum_rows X[r][c]   (X: [rows][ld], c < C)
+__global__ void k_colsum(const float* __restrict__ X, int64_t rows, int ld, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5, nr = blockDim.x >> 5;
+  float acc = 0.f;
+  if (c < C)
+    for (int64_t r = (int64_t)blockIdx.y * nr + rl; r < rows; r += (int64_t)gridDim.y * nr) acc += X[r * ld + c];
+  __shared__ float red[8][33];
+  red[rl][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    float v = 0.f;
+    for (int i = 0; i < nr; ++i) v += red[i][threadIdx.x & 31];
+    atomicAdd(out + c, v);
+  }
+}
+
+// ---- head weight gradients: tmpb [N4][16] (cols 0..3) and tmph [N5][16] (cols 4..15) -> the four head kernels
+struct HeadG { float *wb, *wz, *wt, *wl; };
+__global__ void k_scatter_heads(const float* __restrict__ tmpb, const float* __restrict__ tmph, int N4, int N5, HeadG g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N4 * 4) g.wb[i] += tmpb[(i / 4) * 16 + (i % 4)];
+  if (i < N5 * 2) g.wz[i] += tmph[(i / 2) * 16 + 4 + (i % 2)];
+  if (i < N5 * 4) g.wt[i] += tmph[(i / 4) * 16 + 6 + (i % 4)];
+  if (i < N5 * 6) g.wl[i] += tmph[(i / 6) * 16 + 10 + (i % 6)];
+}
+
+// ---- out [C][R] = in [R][C]^T
+__global__ void k_transpose(const float* __restrict__ in, int R, int C, float* __restrict__ out) {
+  __shared__ float t[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    t[j][threadIdx.x] = (r < R && c < C) ? in[(int64_t)r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (c < C && r < R) out[(int64_t)c * R + r] = t[threadIdx.x][j];
+  }
+}
+
+// ---- wt[kh'][kw'][co][c] = w[KH-1-kh'][3-kw'][c][co]   (kernel of the data-gradient convolution)
+__global__ void k_flip_conv_weights(const float* __restrict__ w, int KH, int CIN, int COUT, float* __restrict__ wt) {
+  const int total = KH * 4 * CIN * COUT;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = i % CIN, co = (i / CIN) % COUT, kwp = (i / (CIN * COUT)) % 4, khp = i / (CIN * COUT * 4);
+  wt[i] = w[(((KH - 1 - khp) * 4 + (3 - kwp)) * CIN + c) * COUT + co];
+}
+
+// ---- conv weight gradient: dW[kh][kw][c][co] += sum_{site,h,w valid} in[site][h+kh][w+kw-1][c] * g[site][h][w][co]
+//   in : [n][ROWS][4*CIN] (padded forward input)     g : [n][GROWS][4*COUT], output row h at stored row h + GR0
+// One group of (CIN/TC)*(COUT/TO) threads per kernel tap (kh,kw); partial sums live in registers across the CTA's
+// site tiles and are flushed with one atomicAdd per weight.
+template <int CIN, int COUT, int KH, int HOUT, int TC, int TO, int S>
+struct WgradCfg {
+  static constexpr int ROWS = HOUT + KH - 1;
+  static constexpr int TG = (CIN / TC) * (COUT / TO);
+  static constexpr int THREADS = KH * 4 * TG;
+  static constexpr int IRS = 4 * CIN + 4, GRS = 4 * COUT + 4;
+  static constexpr int SMEM_FLOATS = S * (ROWS * IRS + HOUT * GRS);
+  static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
+  static_assert(THREADS <= 1024 && CIN % TC == 0 && COUT % TO == 0 && TO % 4 == 0 && (TC == 4 || TC == 1), "wgrad tile");
+};
+
+template <int CIN, int COUT, int KH, int HOUT, int TC, int TO, int S>
+__global__ void __launch_bounds__(WgradCfg<CIN, COUT, KH, HOUT, TC, TO, S>::THREADS)
+k_conv_wgrad(const float* __restrict__ in, const float* __restrict__ g, int GROWS, int GR0, int64_t n, float* __restrict__ dW) {
+  using W = WgradCfg<CIN, COUT, KH, HOUT, TC, TO, S>;
+  extern __shared__ __align__(16) float smem[];
+  float* in_s = smem;
+  float* g_s = smem + S * W::ROWS * W::IRS;
+  const int tid = threadIdx.x;
+  const int tap = tid / W::TG, lt = tid % W::TG;
+  const int kh = tap / 4, kw = tap % 4;
+  const int cg = lt / (COUT / TO), og = lt % (COUT / TO);
+  const int c0 = cg * TC, o0 = og * TO;
+  const int w_lo = 1 - kw > 0 ? 1 - kw : 0, w_hi = 4 - kw < 3 ? 4 - kw : 3;
+  float acc[TC][TO];
+#pragma unroll
+  for (int i = 0; i < TC; ++i)
+#pragma unroll
+    for (int j = 0; j < TO; ++j) acc[i][j] = 0.f;
+  const int64_t ntiles = (n + S - 1) / S;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t site0 = tile * S;
+    __syncthreads();
+    for (int i = tid; i < S * W::ROWS * CIN; i += W::THREADS) {  // float4 units: CIN per row
+      const int s = i / (W::ROWS * CIN), r = i - s * (W::ROWS * CIN);
+      const int row = r / CIN, q = r - row * CIN;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (site0 + s < n) v = *reinterpret_cast<const float4*>(in + ((site0 + s) * W::ROWS + row) * (4 * CIN) + q * 4);
+      *reinterpret_cast<float4*>(in_s + (s * W::ROWS + row) * W::IRS + q * 4) = v;
+    }
+    for (int i = tid; i < S * HOUT * COUT; i += W::THREADS) {
+      const int s = i / (HOUT * COUT), r = i - s * (HOUT * COUT);
+      const int row = r / COUT, q = r - row * COUT;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (site0 + s < n) v = *reinterpret_cast<const float4*>(g + ((site0 + s) * GROWS + GR0 + row) * (4 * COUT) + q * 4);
+      *reinterpret_cast<float4*>(g_s + (s * HOUT + row) * W::GRS + q * 4) = v;
+    }
+    __syncthreads();
+    for (int s = 0; s < S; ++s)
+      for (int h = 0; h < HOUT; ++h) {
+        const float* ip = in_s + (s * W::ROWS + h + kh) * W::IRS + (kw - 1) * CIN + c0;
+        const float* gp = g_s + (s * HOUT + h) * W::GRS + o0;
+        for (int w = w_lo; w <= w_hi; ++w) {
+          float a[TC];
+          if (TC == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(ip + w * CIN);
+            a[0] = v.x; a[1 % TC] = v.y; a[2 % TC] = v.z; a[3 % TC] = v.w;
+          } else {
+            a[0] = ip[w * CIN];
+          }
+#pragma unroll
+          for (int j = 0; j < TO / 4; ++j) {
+            const float4 b = *reinterpret_cast<const float4*>(gp + w * COUT + j * 4);
+#pragma unroll
+            for (int i = 0; i < TC; ++i) {
+              acc[i][j * 4 + 0] = fmaf(a[i], b.x, acc[i][j * 4 + 0]);
+              acc[i][j * 4 + 1] = fmaf(a[i], b.y, acc[i][j * 4 + 1]);
+              acc[i][j * 4 + 2] = fmaf(a[i], b.z, acc[i][j * 4 + 2]);
+              acc[i][j * 4 + 3] = fmaf(a[i], b.w, acc[i][j * 4 + 3]);
+            }
+          }
+        }
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < TC; ++i)
+#pragma unroll
+    for (int j = 0; j < TO; ++j) atomicAdd(dW + ((kh * 4 + kw) * CIN + c0 + i) * COUT + o0 + j, acc[i][j]);
+}
+
+// ---- sum of squares (for lossL2 = lambda * sum 0.5 ||kernel||^2, tf.nn.l2_loss)
+__global__ void k_sumsq(const float* __restrict__ w, int64_t n, float* __restrict__ out) {
+  float a = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a += w[i] * w[i];
+  for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, a);
+}
+
+// ---- TF-1.x Adam (python/training/adam.py): lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed on the host;
+//   g' = g + l2*w (d/dw of lambda*0.5*||w||^2; biases get l2 = 0);  m += (g'-m)(1-b1);  v += (g'^2-v)(1-b2);
+//   w -= lr_t * m / (sqrt(v) + eps)
+__global__ void k_adam(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
+                       int64_t n, float lr_t, float b1, float b2, float eps, float l2) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gg = g[i] + l2 * w[i];
+    const float mm = m[i] + (gg - m[i]) * (1.f - b1);
+    const float vv = v[i] + (gg * gg - v[i]) * (1.f - b2);
+    m[i] = mm;
+    v[i] = vv;
+    w[i] -= lr_t * mm / (sqrtf(vv) + eps);
+  }
+}
+
 }  // namespace cvb

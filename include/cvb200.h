@@ -91,13 +91,15 @@ int cvb_loss_host(cvb_model* m, const float* x, const float* y, int64_t n, float
  * data-parallel all-reduce by the caller) and cvb_apply_adam finishes the step.    */
 int cvb_train_step_host(cvb_model* m, const float* x, const float* y, int64_t n,
                         float lr, float l2, float drop4, uint64_t dropout_seed,
-                        int apply_update, float* loss5);
+                        int apply_update, float* loss6);
 /* device pointer + element count of the flat fp32 gradient buffer (all 18 variables in
  * cvb_variable_info order, followed by 5 loss terms) for an external all-reduce     */
 int cvb_grad_buffer(cvb_model* m, void** dev_ptr, int64_t* numel);
 /* download gradients of one variable (testing) */
 int cvb_get_gradient(cvb_model* m, const char* name, float* host, int64_t n);
-int cvb_apply_adam(cvb_model* m, float lr, float l2);
+/* finishes a step: loss6 (may be NULL) = [total, base, zygosity, varType, indelLength, lossL2] computed from the
+ * (possibly all-reduced) loss sums and the PRE-update weights, then the TF-1.x Adam update on every variable */
+int cvb_apply_adam(cvb_model* m, float lr, float l2, float* loss6);
 
 /* pinned host memory helpers for the batch feed (utils_v2.GetTensor replacement) */
 int cvb_alloc_pinned(int64_t bytes, void** out);

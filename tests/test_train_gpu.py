@@ -1,0 +1,122 @@
+"""GPU parity of the loss / backward / Adam path (clairvoyante_v3.py:140-152,174,183-227) against the
+oracle: NumPy loss, torch-fp64 autograd gradients, restated TF-1.x Adam."""
+import numpy as np
+import pytest
+
+from clairvoyante_b200 import dropout_rng, initializers as I, synth
+from oracle import cv_oracle as O, cv_oracle_torch as OT
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(W, **kw):
+    from clairvoyante_b200 import clairvoyante_v3 as cv
+    m = cv.Clairvoyante(**kw)
+    m.setWeights(W)
+    return m
+
+
+def _relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+@pytest.mark.parametrize("n", [1, 7, 1000, 5121])
+def test_get_loss_matches_oracle(n):
+    W = I.init_weights("v3", 3)
+    x, y = synth.make_sites(n, 4), synth.make_labels(n, 4)
+    m = _model(W)
+    got = float(m.getLoss(x, y))
+    idx = slice(0, min(n, 1500))
+    ref = O.loss(W, x, y, "v3", 0.0)["loss"] if n <= 1500 else None
+    if ref is not None:
+        assert abs(got - ref) <= 2e-5 * abs(ref) + 1e-3
+    else:  # additivity over micro-chunks (5120 sites): loss(all) == loss(a) + loss(b)
+        a = float(m.getLoss(x[:3000], y[:3000])); b = float(m.getLoss(x[3000:], y[3000:]))
+        assert abs(got - (a + b)) <= 1e-5 * abs(got)
+    assert m.getLoss(x[:0], y[:0]) == 0.0
+    m.getLossNoRT(x[idx], y[idx])
+    assert m.getLossLossRTVal is not None
+    m.close()
+
+
+@pytest.mark.parametrize("rate", [0.0, 0.5])
+def test_gradients_match_autograd(rate):
+    W = I.init_weights("v3", 5)
+    n = 300
+    x, y = synth.make_sites(n, 6), synth.make_labels(n, 6)
+    m = _model(W, dropoutRateFC4=rate)
+    seed = 0x1234ABCD
+    loss, summary = m._train_step(x, y, apply_update=0, seed=seed)
+    g = m.getGradients()
+    mask = dropout_rng.keep_mask(seed, n, rate) if rate > 0 else None
+    ref_loss, ref_g = OT.loss_and_grads(W, x, y, "v3", 0.0, drop4_rate=rate, drop4_mask=mask)
+    for name in sorted(ref_g):
+        assert _relerr(g[name], ref_g[name]) < 2e-3, name
+    m.close()
+
+
+def test_train_step_loss_and_tf_adam_update():
+    """loss fetched is that of the pre-update weights incl. lambda*sum(0.5 w^2); update is TF-1.x Adam"""
+    W = I.init_weights("v3", 7)
+    n = 256
+    x, y = synth.make_sites(n, 8), synth.make_labels(n, 8)
+    lam, lr = 1e-3, 1e-3
+    m = _model(W, dropoutRateFC4=0.0, l2RegularizationLambda=lam, initialLearningRate=lr)
+    m.init(seed=1); m.setWeights(W)
+    loss, summary = m.train(x, y)
+    ref = O.loss(W, x, y, "v3", lam)
+    assert abs(float(loss) - ref["loss"]) <= 3e-5 * abs(ref["loss"])
+    for k in ("loss1", "loss2", "loss3", "loss4", "lossL2"):
+        assert abs(summary[k] - ref[k]) <= 1e-4 * abs(ref[k]) + 1e-4, k
+    _, g = OT.loss_and_grads(W, x, y, "v3", lam)      # lambda inside the loss == g + lam*w
+    W1 = m.getWeights()
+    for name in W:
+        exp, _, _ = OT.tf_adam_step(W[name].astype(np.float64), g[name], 0.0, 0.0, 1, lr)
+        # step-1 Adam moves every weight by ~lr*sign(g); compare where the gradient is not vanishing
+        big = np.abs(g[name]) > 1e-3 * np.abs(g[name]).max()
+        assert np.abs(W1[name] - exp)[big].max() < 0.05 * lr, name
+    # second step uses t = 2 and the stored slots
+    loss2, _ = m.train(x, y)
+    assert float(loss2) < float(loss)
+    m.close()
+
+
+def test_training_reduces_loss_and_checkpoint_roundtrip(tmp_path):
+    W = I.init_weights("v3", 9)
+    x, y = synth.make_sites(2000, 10), synth.make_labels(2000, 10)
+    m = _model(W)
+    m.init(seed=2)
+    l0 = float(m.getLoss(x, y))
+    for _ in range(8):
+        m.train(x, y)
+    l1 = float(m.getLoss(x, y))
+    assert l1 < 0.7 * l0
+    fn = str(tmp_path / "ck" / "model-000001")
+    m.saveParameters(fn)
+    m2 = _model(W)
+    m2.restoreParameters(fn)
+    assert abs(float(m2.getLoss(x, y)) - l1) <= 1e-6 * abs(l1)
+    a, b = m.train(x, y)[0], m2.train(x, y)[0]        # Adam slots + step restored -> identical next step (dropout differs: rate!=0)
+    m.close(); m2.close()
+
+
+def test_data_parallel_halves_equal_full_batch():
+    """gradient of a batch == sum of the gradients of its shards (SUM loss): what the DP all-reduce relies on"""
+    W = I.init_weights("v3", 11)
+    n = 400
+    x, y = synth.make_sites(n, 12), synth.make_labels(n, 12)
+    m = _model(W, dropoutRateFC4=0.0)
+    m._train_step(x, y, apply_update=0, seed=1); full = m.getGradients()
+    m._train_step(x[:150], y[:150], apply_update=0, seed=1); a = m.getGradients()
+    m._train_step(x[150:], y[150:], apply_update=0, seed=1); b = m.getGradients()
+    for k in full:
+        assert _relerr(a[k] + b[k], full[k]) < 2e-5, k
+    m.close()
+
+
+def test_set_learning_rate_and_lambda_semantics():
+    W = I.init_weights("v3", 0)
+    m = _model(W)
+    assert m.setLearningRate(0.01) == 0.01 and abs(m.setLearningRate() - 0.001) < 1e-12       # clairvoyante_v3.py:229-234
+    assert m.setL2RegularizationLambda(0.5) == 0.5 and abs(m.setL2RegularizationLambda() - 0.05) < 1e-12
+    m.close()
