@@ -273,6 +273,15 @@ class ClairvoyanteBase(object):
                        loss4=float(l5[4]), lossL2=float(l5[5]))
         return np.float32(l5[0]), summary
 
+    def applyAdam(self):
+        """finish a step whose gradients were left in the gradient buffer (apply_update=0): loss + TF-1.x Adam"""
+        l6 = (ctypes.c_float * 8)()
+        _lib.check(self._lib.cvb_apply_adam(self._h, self.learningRateVal, self.l2RegularizationLambdaVal, l6))
+        summary = dict(learning_rate=float(self.learningRateVal), l2Lambda=float(self.l2RegularizationLambdaVal),
+                       loss=float(l6[0]), loss1=float(l6[1]), loss2=float(l6[2]), loss3=float(l6[3]),
+                       loss4=float(l6[4]), lossL2=float(l6[5]))
+        return np.float32(l6[0]), summary
+
     def train(self, batchX, batchY):
         return self._train_step(batchX, batchY)
 

@@ -1,0 +1,58 @@
+"""CPU, world_size 2 over gloo: the multi-GPU host logic (site-list sharding, gather order) with a stub model."""
+import os
+import socket
+
+import numpy as np
+import torch.multiprocessing as mp
+
+from clairvoyante_b200 import parallel
+
+
+def test_shard_ranges_cover_and_order():
+    for n in (0, 1, 7, 8, 1000, 1001):
+        for w in (1, 2, 3, 8):
+            r = [parallel.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+class _Stub(object):
+    def predict(self, X):
+        s = X.reshape(len(X), 528).sum(1, keepdims=True).astype(np.float32)
+        return s * np.ones((1, 4), np.float32), s * np.ones((1, 2), np.float32), s + np.zeros((1, 4), np.float32), s + np.zeros((1, 6), np.float32)
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((37, 33, 4, 4)).astype(np.float32)
+
+    def gather(local):
+        out = [None] * world
+        dist.all_gather_object(out, local)
+        return out
+
+    full = parallel.predict_sharded(_Stub(), X, rank, world, gather)
+    single = _Stub().predict(X)
+    ok = all(np.array_equal(a, b) for a, b in zip(full, single))
+    lo, hi = parallel.shard_range(len(X), rank, world)
+    local = parallel.predict_sharded(_Stub(), X, rank, world)
+    ok = ok and len(local[0]) == hi - lo
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_sharded_predict_equals_single_process_gloo():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
