@@ -80,6 +80,6 @@ def test_dp_trainer_single_rank_equals_plain_step():
     lb, _ = parallel.DataParallelTrainer(b).train(x, y, seed=5)
     assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(la))
     wa, wb = a.getWeights(), b.getWeights()
-    for k in wa:
-        assert np.array_equal(wa[k], wb[k]), k
+    for k in wa:       # weight-gradient kernels accumulate with atomics: summation order differs run to run
+        assert np.allclose(wa[k], wb[k], rtol=1e-5, atol=1e-7), k
     a.close(); b.close()
