@@ -14,6 +14,7 @@
 #include "fwd_simt.cuh"
 #include "fc4_tc.cuh"
 #include "conv_tc.cuh"
+#include "tail_tc.cuh"
 #include <math.h>
 #include <stdlib.h>
 #include <sys/mman.h>
@@ -89,6 +90,10 @@ struct cvb_model {
   int64_t p1_rows = 0, p2_rows = 0;
   CUtensorMap map_c2a4, map_c2b2, map_c2b3, map_c2b4, map_c3a4, map_c3b2, map_c3b3, map_c3b4;
   int tc_merged = 1;
+  // fused tail (FC5 + heads) on tensor cores: A = h4 hi/lo [sites][336], B = [W5 | Wb]^T [176][336]
+  __half *d_h4s = nullptr, *d_wtail = nullptr;
+  CUtensorMap map_ta_hi, map_ta_lo, map_tb_hi, map_tb_lo;
+  bool tc_tail = true;
   int64_t alloc_sites = 0;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;  // 5 per chunk: before front, after front, conv3, fc4, tail
@@ -197,7 +202,7 @@ extern "C" int cvb_destroy(cvb_model* m) {
   for (auto e : m->prof_events) cudaEventDestroy(e);
   cudaFree(m->d_params); cudaFree(m->d_m); cudaFree(m->d_v); cudaFree(m->d_grad);
   cudaFree(m->d_p2); cudaFree(m->d_p3); cudaFree(m->d_h4); cudaFree(m->d_h5);
-  cudaFree(m->d_w3b_hi); cudaFree(m->d_p1); cudaFree(m->d_w2b_hi);
+  cudaFree(m->d_w3b_hi); cudaFree(m->d_p1); cudaFree(m->d_w2b_hi); cudaFree(m->d_h4s); cudaFree(m->d_wtail);
   cudaFree(m->d_w4t_hi); cudaFree(m->d_w4t_lo); cudaFree(m->d_absmax); cudaFree(m->d_inv_scale);
   for (int i = 0; i < 2; ++i) {
     cudaFree(m->d_x[i]); cudaFree(m->d_out[i]); cudaFree(m->d_lg[i]);
@@ -383,6 +388,19 @@ static int tc_setup(cvb_model* m) {
       m->map_c3a4 = m->map_c3a_hi; m->map_c3b2 = m->map_c3b3 = m->map_c3b4 = m->map_c3b_hi;
     }
   }
+  {
+    using T = tc::TailTc;
+    const size_t plane = (size_t)m->alloc_sites * T::N4;
+    CK(cudaMalloc(&m->d_h4s, plane * 2 * 2));
+    CK(cudaMalloc(&m->d_wtail, (size_t)T::NB * T::N4 * 2 * 2));
+    if (make_map_f16(&m->map_ta_hi, m->d_h4s, (uint64_t)m->alloc_sites, T::N4, T::BK, T::BM, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (make_map_f16(&m->map_ta_lo, m->d_h4s + plane, (uint64_t)m->alloc_sites, T::N4, T::BK, T::BM, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (make_map_f16(&m->map_tb_hi, m->d_wtail, T::NB, T::N4, T::BK, T::NB, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (make_map_f16(&m->map_tb_lo, m->d_wtail + (size_t)T::NB * T::N4, T::NB, T::N4, T::BK, T::NB, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    CK(cudaFuncSetAttribute(tc::k_tail_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+    const char* e = getenv("CVB_TC_TAIL");
+    m->tc_tail = !(e && e[0] == '0');
+  }
   m->tc_ready = true;
   m->tc_weights_dirty = true;
   return 0;
@@ -413,7 +431,17 @@ static int tc_refresh_weights(cvb_model* m, cudaStream_t st) {
   tc::k_prep_conv_weights<tc::Conv2Tc><<<(2 * 128 * 64 + 255) / 256, 256, 0, st>>>(
       m->var("conv2/kernel"), m->d_absmax + 2, m->d_w2b_hi, m->d_w2b_lo, m->d_inv_scale + 2);
   CK(cudaGetLastError());
-  m->launches += 6;
+  {
+    using T = tc::TailTc;
+    CK(cudaMemsetAsync(m->d_absmax + 3, 0, 4, st));
+    tc::k_absmax<<<64, 256, 0, st>>>(m->var("fc5/kernel"), (int64_t)T::N4 * T::N5, m->d_absmax + 3);
+    tc::k_absmax<<<4, 256, 0, st>>>(m->var("YBaseChangeSigmoid/kernel"), (int64_t)T::N4 * 4, m->d_absmax + 3);
+    tc::k_prep_tail_weights<<<(T::NB * T::N4 + 255) / 256, 256, 0, st>>>(m->var("fc5/kernel"), m->var("YBaseChangeSigmoid/kernel"),
+                                                                         m->d_absmax + 3, m->d_wtail,
+                                                                         m->d_wtail + (size_t)T::NB * T::N4, m->d_inv_scale + 3);
+    CK(cudaGetLastError());
+  }
+  m->launches += 9;
   m->tc_weights_dirty = false;
   return 0;
 }
@@ -543,7 +571,9 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       using F = tc::Fc4Tc;
       dim3 grid(2, (unsigned)((n + F::BM - 1) / F::BM));
       tc::k_fc4_tc<<<grid, F::THREADS, F::SMEM_BYTES, st>>>(m->map_a_hi, m->map_a_lo, m->map_b_hi, m->map_b_lo, n, 4608,
-                                                            m->var("fc4/bias"), m->d_inv_scale, m->d_h4);
+                                                            m->var("fc4/bias"), m->d_inv_scale, m->d_h4,
+                                                            m->tc_tail ? m->d_h4s : nullptr,
+                                                            m->tc_tail ? m->d_h4s + (size_t)m->alloc_sites * 336 : nullptr);
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
     } else {
@@ -555,7 +585,18 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
     }
-    {
+    if (tensor && m->tc_tail) {
+      using T = tc::TailTc;
+      tc::TailHeads th{m->var("fc5/bias"), m->var("YBaseChangeSigmoid/bias"), m->var("YZygosityFC/kernel"), m->var("YZygosityFC/bias"),
+                       m->var("YVarTypeFC/kernel"), m->var("YVarTypeFC/bias"), m->var("YIndelLengthFC/kernel"),
+                       m->var("YIndelLengthFC/bias")};
+      tc::k_tail_tc<<<(int)((n + T::BM - 1) / T::BM), T::THREADS, T::SMEM_BYTES, st>>>(m->map_ta_hi, m->map_ta_lo, m->map_tb_hi,
+                                                                                        m->map_tb_lo, n, th, m->d_inv_scale + 3, out16,
+                                                                                        logits16);
+      CK(cudaGetLastError());
+      if (prof_mark(m, st)) return 1;
+      m->launches -= 1;  // one fused kernel instead of FC5 + heads (the common "+= 5" below counts two)
+    } else {
       using F5 = FcCfg<168, 21, 8, 12, 8>;  // FC5: h5 = SELU(h4 @ W5 + b5), same SGEMM as the fp32 FC4
       auto k = k_fc4<F5>;
       CK(set_smem(k, F5::SMEM_BYTES));

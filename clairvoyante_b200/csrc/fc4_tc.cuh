@@ -80,7 +80,9 @@ __global__ void k_prep_fc_weights(const float* __restrict__ w, int K, int N, con
 __global__ void __launch_bounds__(Fc4Tc::THREADS, 1)
 k_fc4_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, int64_t n, int K,
-         const float* __restrict__ bias, const float* __restrict__ inv_scale, float* __restrict__ out) {
+         const float* __restrict__ bias, const float* __restrict__ inv_scale, float* __restrict__ out,
+         __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  // out_hi / out_lo (optional): h4 again as split fp16 [n][336], the A operand of the fused tail (tail_tc.cuh)
   using F = Fc4Tc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -201,6 +203,13 @@ k_fc4_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ C
           v.z = selu_f(fmaf(sum[cc + 2], isc, bv.z));
           v.w = selu_f(fmaf(sum[cc + 3], isc, bv.w));
           *reinterpret_cast<float4*>(dst + cc) = v;
+          if (out_hi) {
+            __half2 hi[2], lo[2];
+            split_f16x2(v.x, v.y, hi[0], lo[0]);
+            split_f16x2(v.z, v.w, hi[1], lo[1]);
+            *reinterpret_cast<uint2*>(out_hi + site * F::N + col0 + cc) = *reinterpret_cast<const uint2*>(hi);
+            *reinterpret_cast<uint2*>(out_lo + site * F::N + col0 + cc) = *reinterpret_cast<const uint2*>(lo);
+          }
         }
       }
     }
