@@ -147,9 +147,11 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   lo = __float2half_rn(x - __half2float(hi));
 }
 
-// two values at once, no clamp (activations are bounded far below 65504; an overflow would already be
-// an overflow of the network): 2 F2FP + 2 unpack + 2 FADD per pair
+// two values at once.  Values are saturated to fp16's finite range: an activation beyond +-65504 (never seen with
+// trained or initialiser weights, |activation| ~ 1e2) loses accuracy instead of turning into inf/NaN.
 __device__ __forceinline__ void split_f16x2(float a, float b, __half2& hi, __half2& lo) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
   hi = __floats2half2_rn(a, b);
   const float2 hf = __half22float2(hi);
   lo = __floats2half2_rn(a - hf.x, b - hf.y);
