@@ -31,8 +31,8 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 FLOPS_PER_SITE = {  # SURVEY.md 8d / BASELINE.md section 2 (2*MAC)
-    "v3": dict(front=67584 + 950272, conv3=3833856, fc4=3096576, tail=112896 + 6720, total=8067904),
-    "v3_slim": dict(front=33792 + 405504, conv3=2703360, fc4=304128, tail=1296 + 720, total=3448800),
+    "v3": dict(conv1=67584, conv2=950272, conv3=3833856, fc4=3096576, tail=112896 + 6720, total=8067904),
+    "v3_slim": dict(conv1=33792, conv2=405504, conv3=2703360, fc4=304128, tail=1296 + 720, total=3448800),
 }
 HBM_BYTES_PER_SITE = 2176          # 2112 in + 64 out, fp32 I/O
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.45: 148 SMs x 128 FMA lanes x 2 x clocks.max.sm
@@ -269,7 +269,11 @@ def main():
     for _ in range(2):
         step()
     prof = m.profileRead()
-    fl = FLOPS_PER_SITE[args.variant]
+    fl = dict(FLOPS_PER_SITE[args.variant])
+    conv2_separate = prof["conv2"][0] > 0.01 * prof["front"][0]      # tcgen05 conv2 runs as its own kernel
+    fl["front"] = fl["conv1"] if conv2_separate else fl["conv1"] + fl["conv2"]
+    if not conv2_separate:
+        prof.pop("conv2")
     kern = {}
     for k, (tms, cnt) in prof.items():
         kern[k] = dict(ms_per_launch=tms / max(cnt, 1), launches=cnt, share=tms / max(sum(v[0] for v in prof.values()), 1e-9),
@@ -281,7 +285,7 @@ def main():
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(args.variant, {}).get(dom)
     sites_per_launch = 2 * n / max(kern[dom]["launches"], 1)
-    on_tensor = tensor and dom in ("conv3", "fc4")
+    on_tensor = tensor and dom in ("conv2", "conv3", "fc4", "tail")
     if on_tensor:
         # the kernel issues 3 fp16 MMAs per algorithmic fp32 MAC (split operands); achieved counts ALGORITHMIC flops
         r_bound, r_peak = "tensor", pk["bf16_tflops"]
@@ -290,7 +294,7 @@ def main():
         r_bound, r_peak = "fp32_fma", FP32_NOMINAL_TFLOPS
         r_src = "nominal fp32 FMA (148 SM x 128 lanes x 2 x 1.965 GHz); MEASURED_PEAKS.json has no fp32-SIMT figure"
     for k in kern:
-        kern[k]["pipe"] = "tcgen05 (3x split-fp16)" if (tensor and k in ("conv3", "fc4")) else "fp32 SIMT"
+        kern[k]["pipe"] = "tcgen05 (3x split-fp16)" if (tensor and k in ("conv2", "conv3", "fc4", "tail")) else "fp32 SIMT"
     roofline = dict(kernel=dom, bound=r_bound, achieved=kern[dom]["tflops"], peak=r_peak, unit="TFLOP/s",
                     frac=kern[dom]["tflops"] / r_peak, peak_source=r_src,
                     algorithmic_flops_per_launch=fl[dom] * sites_per_launch, ms_per_launch=kern[dom]["ms_per_launch"],

@@ -96,7 +96,7 @@ struct cvb_model {
   bool tc_tail = true;
   int64_t alloc_sites = 0;
   bool profiling = false;
-  std::vector<cudaEvent_t> prof_events;  // 5 per chunk: before front, after front, conv3, fc4, tail
+  std::vector<cudaEvent_t> prof_events;  // 6 per chunk: start, after SIMT front, conv2(tc), conv3, fc4, tail
   size_t prof_used = 0;
   TrainWork* train = nullptr;
   const float* var(const char* n) const {
@@ -516,6 +516,7 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
         int g1 = (int)std::min<int64_t>((n + 6) / 7, 2 * sms);
         k1<<<g1, 256, C1K::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->d_p1, m->d_p1 + p1_halves);
         CK(cudaGetLastError());
+        if (prof_mark(m, st)) return 1;  // kind 0 = SIMT front (conv1+pool1 here), kind 1 = tcgen05 conv2
         using T = tc::Conv2Tc;
         const int64_t t2 = (n * T::RPS + T::TILE_STEP - 1) / T::TILE_STEP;
         int g2 = (int)std::min<int64_t>(t2, sms);
@@ -531,11 +532,15 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
         k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
                                             m->var("conv2/bias"), m->d_p2,
                                             reinterpret_cast<__half*>(m->d_p2) + m->p2_rows * 128);
+        CK(cudaGetLastError());
+        if (prof_mark(m, st)) return 1;  // fused SIMT front = kind 0; kind 1 (tcgen05 conv2) stays empty
       } else {
         auto k = k_v3_front<4, false>;
         CK(set_smem(k, F::SMEM_BYTES));
         k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
                                             m->var("conv2/bias"), m->d_p2, nullptr);
+        CK(cudaGetLastError());
+        if (prof_mark(m, st)) return 1;
       }
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
@@ -619,6 +624,7 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
                                           m->var("conv2/bias"), m->d_p2);
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
+      if (prof_mark(m, st)) return 1;  // (no separate conv2 kernel)
     }
     {
       using C = ConvCfg<16, 32, 5, 33, 3, 8, 8>;
@@ -782,13 +788,13 @@ extern "C" int cvb_profile_begin(cvb_model* m) {
   m->prof_used = 0;
   return 0;
 }
-extern "C" int cvb_profile_read(cvb_model* m, double ms[4], int64_t launches[4]) {
+extern "C" int cvb_profile_read(cvb_model* m, double ms[5], int64_t launches[5]) {
   if (!m || !ms || !launches) return fail("cvb_profile_read: NULL argument");
   CK(cudaSetDevice(m->device));
   CK(cudaDeviceSynchronize());
-  for (int k = 0; k < 4; ++k) { ms[k] = 0; launches[k] = 0; }
-  for (size_t i = 0; i + 5 <= m->prof_used; i += 5)
-    for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < 5; ++k) { ms[k] = 0; launches[k] = 0; }
+  for (size_t i = 0; i + 6 <= m->prof_used; i += 6)
+    for (int k = 0; k < 5; ++k) {
       float t = 0;
       CK(cudaEventElapsedTime(&t, m->prof_events[i + k], m->prof_events[i + k + 1]));
       ms[k] += t;

@@ -234,10 +234,10 @@ class ClairvoyanteBase(object):
 
     def profileRead(self):
         """{kernel: (total_ms, launches)} since profileBegin(); synchronises the device."""
-        ms = (ctypes.c_double * 4)()
-        cnt = (ctypes.c_int64 * 4)()
+        ms = (ctypes.c_double * 5)()
+        cnt = (ctypes.c_int64 * 5)()
         _lib.check(self._lib.cvb_profile_read(self._h, ms, cnt))
-        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(("front", "conv3", "fc4", "tail"))}
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(("front", "conv2", "conv3", "fc4", "tail"))}
 
     def kernelLaunches(self):
         return int(self._lib.cvb_kernel_launches(self._h))

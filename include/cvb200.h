@@ -111,10 +111,11 @@ int cvb_debug_read(cvb_model* m, int which, float* host, int64_t n);
 
 /* per-kernel device timing for bench.py's roofline: while enabled, every kernel launch of
  * the forward pass is bracketed by CUDA events on the launching stream.  cvb_profile_read
- * synchronises the device and returns, per kernel kind (0 front, 1 conv3, 2 fc4, 3 tail),
- * the summed duration in ms and the number of launches since cvb_profile_begin.            */
+ * synchronises the device and returns, per kernel kind,
+ * the summed duration in ms and the number of launches since cvb_profile_begin.
+ * kinds: 0 SIMT front (conv1[+conv2]), 1 tcgen05 conv2, 2 conv3, 3 fc4, 4 tail (FC5 + heads)        */
 int cvb_profile_begin(cvb_model* m);
-int cvb_profile_read(cvb_model* m, double ms[4], int64_t launches[4]);
+int cvb_profile_read(cvb_model* m, double ms[5], int64_t launches[5]);
 
 /* counters for bench.py: number of this library's kernels launched so far on the handle */
 int64_t cvb_kernel_launches(const cvb_model* m);
