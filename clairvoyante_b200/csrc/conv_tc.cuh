@@ -83,19 +83,25 @@ __global__ void k_prep_conv_weights(const float* __restrict__ w, const unsigned 
   b_lo[i] = lo;
 }
 
-template <class F>
+// CL2 = true: launched as clusters of 2 CTAs.  Both CTAs walk the same (kh, w') stage sequence on their own tiles;
+// each loads HALF of every stage's weight rows and TMA-multicasts it to the pair, so the weights leave L2 once per
+// pair instead of once per CTA (the kernel is bound by L2 -> SMEM traffic, profiles/r01_tensor_path.md).  A stage
+// slot is refilled only after BOTH CTAs' MMAs have released it (empty barrier count 2, multicast commit).
+template <class F, bool CL2>
 __global__ void __launch_bounds__(F::THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
           const __grid_constant__ CUtensorMap map_a4, const __grid_constant__ CUtensorMap map_b2,
-          const __grid_constant__ CUtensorMap map_b3, const __grid_constant__ CUtensorMap map_b4, int merged, int64_t n,
+          const __grid_constant__ CUtensorMap map_b3, const __grid_constant__ CUtensorMap map_b4,
+          const __grid_constant__ CUtensorMap map_h2, const __grid_constant__ CUtensorMap map_h3,
+          const __grid_constant__ CUtensorMap map_h4, int merged, int64_t n,
           const float* __restrict__ bias, const float* __restrict__ inv_scale, __half* __restrict__ out_hi,
           __half* __restrict__ out_lo) {
   // merged != 0: 2 TMA operations per stage instead of 8 + 2*nb --
   //   map_a4  : 4-D view (k, row-in-quadrant, quadrant, plane) of the activation: quadrant stride QSTEP rows
   //             (overlapping windows), plane stride = hi -> lo; one box {BK, 32, 4, 2} = A_hi (128 rows) then A_lo
   //   map_b{2,3,4}: 3-D view (k, row, plane) of the weights with box {BK, nb*COUT, 2} = B_hi rows then B_lo rows
-  // The issuing thread, not the bytes, is what bounds the small-box variant (profiles/r01_tensor_path.md).
+  //   map_h{2,3,4}: same view with box {BK, nb*COUT/2, 1}: one plane of one half of the rows (cluster multicast)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F::STAGES * F::STAGE_BYTES);
@@ -115,15 +121,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
     tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
     tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
     tma_prefetch_desc(&map_a4); tma_prefetch_desc(&map_b2); tma_prefetch_desc(&map_b3); tma_prefetch_desc(&map_b4);
-    for (int s = 0; s < F::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < F::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL2 ? 2 : 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], F::EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, F::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();  // the partner's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = CL2 ? cluster_ctarank() : 0;
+  // with clusters every CTA runs the same number of tiles (tiles past the end load zeros and store nothing)
+  const int64_t tile_end = CL2 ? ((ntiles + gridDim.x - 1) / gridDim.x) * gridDim.x : ntiles;
 
   // step order inside a tile: (kh=0, w'=2) first -- it covers all NOUT columns, so its first MMA can
   // initialise the whole accumulator -- then (kh=0, w'=0,1,3), then kh = 1.. with w' = 0..3.
@@ -134,7 +144,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
     // ===================== TMA producer =====================
     if (elect_one()) {
       uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int64_t tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
         const int64_t base = tile * F::TILE_STEP;
         for (int stp = 0; stp < F::STEPS; ++stp, ++it) {
           const int kh = step_kh(stp), wp = step_wp(stp);
@@ -146,8 +156,18 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
           mbar_arrive_expect_tx(&full[s], 2 * F::A_BYTES + 2 * nb * F::COUT * F::ROW_BYTES);
           if (merged) {
             tma_load_4d(st, &map_a4, &full[s], wp * F::CIN, kh, (int)(tile * 4), 0);
-            const CUtensorMap* mb = nb == 2 ? &map_b2 : (nb == 3 ? &map_b3 : &map_b4);
-            tma_load_3d(st + 2 * F::A_BYTES, mb, &full[s], wp * F::CIN, kh * F::NOUT + wl * F::COUT, 0);
+            if (CL2) {
+              const CUtensorMap* mh = nb == 2 ? &map_h2 : (nb == 3 ? &map_h3 : &map_h4);
+              const int half_rows = nb * F::COUT / 2;
+              const int brow = kh * F::NOUT + wl * F::COUT + (int)crank * half_rows;
+#pragma unroll
+              for (int pl = 0; pl < 2; ++pl)
+                tma_load_3d_mc(st + 2 * F::A_BYTES + pl * (nb * F::COUT * F::ROW_BYTES) + crank * (half_rows * F::ROW_BYTES), mh,
+                               &full[s], wp * F::CIN, brow, pl, (uint16_t)3);
+            } else {
+              const CUtensorMap* mb = nb == 2 ? &map_b2 : (nb == 3 ? &map_b3 : &map_b4);
+              tma_load_3d(st + 2 * F::A_BYTES, mb, &full[s], wp * F::CIN, kh * F::NOUT + wl * F::COUT, 0);
+            }
             continue;
           }
 #pragma unroll
@@ -168,7 +188,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
     // ===================== MMA issuer =====================
     if (elect_one()) {
       uint32_t it = 0, tcount = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      for (int64_t tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++tcount) {
         const int buf = tcount & 1;
         mbar_wait(&acc_empty[buf], ((tcount >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -195,7 +215,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
             umma_f16(tcol, dah, dbl, idesc, 1u);
             umma_f16(tcol, dah, dbh, idesc, 1u);
           }
-          umma_commit(&empty[s]);
+          if (CL2) umma_commit_mc(&empty[s], (uint16_t)3);
+          else umma_commit(&empty[s]);
         }
         umma_commit(&acc_full[buf]);
       }
@@ -206,7 +227,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
     const int wblk = (warp - 2) >> 2;   // output column block w (COUT channels) owned by this warp
     const float isc = inv_scale[0];
     uint32_t tcount = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+    for (int64_t tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++tcount) {
       const int buf = tcount & 1;
       const int64_t r = tile * F::TILE_STEP + q * F::QSTEP + lane;  // flattened stored row of this thread
       const int64_t site = r / F::RPS;
@@ -252,6 +273,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();  // no CTA may exit while its partner can still multicast into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, F::TMEM_COLS);

@@ -90,6 +90,8 @@ struct cvb_model {
   int64_t p1_rows = 0, p2_rows = 0;
   CUtensorMap map_c2a4, map_c2b2, map_c2b3, map_c2b4, map_c3a4, map_c3b2, map_c3b3, map_c3b4;
   int tc_merged = 1;
+  int tc_cluster = 1;  // 2-CTA clusters with weight multicast in the conv tensor kernels (needs tc_merged)
+  CUtensorMap map_c2h2, map_c2h3, map_c2h4, map_c3h2, map_c3h3, map_c3h4;
   // fused tail (FC5 + heads) on tensor cores: A = h4 hi/lo [sites][336], B = [W5 | Wb]^T [176][336]
   __half *d_h4s = nullptr, *d_wtail = nullptr;
   CUtensorMap map_ta_hi, map_ta_lo, map_tb_hi, map_tb_lo;
@@ -311,7 +313,7 @@ static int make_map_nd(CUtensorMap* map, void* base, int rank, const uint64_t* d
 // merged views for k_conv_tc (conv_tc.cuh): activation planes at `act`, `rows` rows per plane; weights planes at `wts`
 template <class C>
 static int make_conv_merged_maps(void* act, int64_t rows, void* wts, CUtensorMapSwizzle sw, CUtensorMap* a4, CUtensorMap* b2,
-                                 CUtensorMap* b3, CUtensorMap* b4) {
+                                 CUtensorMap* b3, CUtensorMap* b4, CUtensorMap* h2, CUtensorMap* h3, CUtensorMap* h4) {
   const uint64_t rext = C::QROWS + C::KH - 1;
   const uint64_t Q = (uint64_t)(rows - rext) / C::QSTEP + 1;
   const uint64_t ad[4] = {(uint64_t)C::KROW, rext, Q, 2};
@@ -321,9 +323,12 @@ static int make_conv_merged_maps(void* act, int64_t rows, void* wts, CUtensorMap
   const uint64_t bd[3] = {(uint64_t)C::KROW, (uint64_t)C::B_ROWS_TOTAL, 2};
   const uint64_t bs[2] = {(uint64_t)C::KROW * 2, (uint64_t)C::B_ROWS_TOTAL * C::KROW * 2};
   CUtensorMap* bm[3] = {b2, b3, b4};
+  CUtensorMap* hm[3] = {h2, h3, h4};
   for (int nb = 2; nb <= 4; ++nb) {
     const uint32_t bb[3] = {(uint32_t)C::BK, (uint32_t)(nb * C::COUT), 2};
     if (make_map_nd(bm[nb - 2], wts, 3, bd, bs, bb, sw)) return 1;
+    const uint32_t hb[3] = {(uint32_t)C::BK, (uint32_t)(nb * C::COUT / 2), 1};  // one plane, half the rows (cluster multicast)
+    if (make_map_nd(hm[nb - 2], wts, 3, bd, bs, hb, sw)) return 1;
   }
   return 0;
 }
@@ -354,13 +359,17 @@ static int tc_setup(cvb_model* m) {
     if (make_map_f16(&m->map_c3a_lo, p2_lo, rows, C::KROW, C::BK, C::QROWS, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     if (make_map_f16(&m->map_c3b_hi, m->d_w3b_hi, C::B_ROWS_TOTAL, C::KROW, C::BK, C::COUT, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     if (make_map_f16(&m->map_c3b_lo, m->d_w3b_lo, C::B_ROWS_TOTAL, C::KROW, C::BK, C::COUT, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-    CK(cudaFuncSetAttribute(tc::k_conv_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::k_conv_tc<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::k_conv_tc<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     const char* e = getenv("CVB_TC_CONV3");
     m->tc_conv3 = !(e && e[0] == '0');
     const char* em = getenv("CVB_TC_MERGED");
     m->tc_merged = !(em && em[0] == '0');
+    const char* ec = getenv("CVB_TC_CLUSTER");
+    m->tc_cluster = !(ec && ec[0] == '0');
     if (m->tc_merged && make_conv_merged_maps<C>(p2_hi, m->p2_rows, m->d_w3b_hi, CU_TENSOR_MAP_SWIZZLE_64B, &m->map_c3a4,
-                                                 &m->map_c3b2, &m->map_c3b3, &m->map_c3b4)) {
+                                                 &m->map_c3b2, &m->map_c3b3, &m->map_c3b4, &m->map_c3h2, &m->map_c3h3,
+                                                 &m->map_c3h4)) {
       m->tc_merged = 0;  // overlapping-window view rejected by this driver: fall back to per-quadrant boxes
       m->map_c3a4 = m->map_c3a_hi; m->map_c3b2 = m->map_c3b3 = m->map_c3b4 = m->map_c3b_hi;
     }
@@ -377,13 +386,17 @@ static int tc_setup(cvb_model* m) {
     if (make_map_f16(&m->map_c2a_lo, m->d_p1 + p1_halves, rows, C::KROW, C::BK, C::QROWS, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
     if (make_map_f16(&m->map_c2b_hi, m->d_w2b_hi, C::B_ROWS_TOTAL, C::KROW, C::BK, C::COUT, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
     if (make_map_f16(&m->map_c2b_lo, m->d_w2b_lo, C::B_ROWS_TOTAL, C::KROW, C::BK, C::COUT, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
-    CK(cudaFuncSetAttribute(tc::k_conv_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::k_conv_tc<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::k_conv_tc<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     const char* e = getenv("CVB_TC_CONV2");
     m->tc_conv2 = m->tc_conv3 && !(e && e[0] == '0');
     if (m->tc_merged && make_conv_merged_maps<C>(m->d_p1, m->p1_rows, m->d_w2b_hi, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c2a4,
-                                                 &m->map_c2b2, &m->map_c2b3, &m->map_c2b4))
+                                                 &m->map_c2b2, &m->map_c2b3, &m->map_c2b4, &m->map_c2h2, &m->map_c2h3,
+                                                 &m->map_c2h4))
       m->tc_merged = 0;
     if (!m->tc_merged) {
+      m->tc_cluster = 0;
+      m->map_c2h2 = m->map_c2h3 = m->map_c2h4 = m->map_c3h2 = m->map_c3h3 = m->map_c3h4 = m->map_c2b_hi;
       m->map_c2a4 = m->map_c2a_hi; m->map_c2b2 = m->map_c2b3 = m->map_c2b4 = m->map_c2b_hi;
       m->map_c3a4 = m->map_c3a_hi; m->map_c3b2 = m->map_c3b3 = m->map_c3b4 = m->map_c3b_hi;
     }
@@ -486,6 +499,36 @@ static HeadPtrs head_ptrs(const cvb_model* m) {
 }
 
 // one chunk (n <= CHUNK) of the forward pass on `st`
+// launches k_conv_tc<T> either plainly or as 2-CTA clusters (weight multicast)
+template <class T>
+static int launch_conv_tc(cvb_model* m, int64_t n, cudaStream_t st, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                          const CUtensorMap& b_hi, const CUtensorMap& b_lo, const CUtensorMap& a4, const CUtensorMap& b2,
+                          const CUtensorMap& b3, const CUtensorMap& b4, const CUtensorMap& h2, const CUtensorMap& h3,
+                          const CUtensorMap& h4, const float* bias, const float* inv_scale, __half* out_hi, __half* out_lo) {
+  const int64_t tiles = (n * T::RPS + T::TILE_STEP - 1) / T::TILE_STEP;
+  int grid = (int)std::min<int64_t>(tiles, m->num_sms);
+  if (m->tc_cluster && m->tc_merged && grid >= 2) {
+    grid &= ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(T::THREADS);
+    cfg.dynamicSmemBytes = T::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, tc::k_conv_tc<T, true>, a_hi, a_lo, b_hi, b_lo, a4, b2, b3, b4, h2, h3, h4, 1, n, bias, inv_scale,
+                          out_hi, out_lo));
+  } else {
+    tc::k_conv_tc<T, false><<<grid, T::THREADS, T::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, a4, b2, b3, b4, h2, h3, h4, m->tc_merged, n,
+                                                                      bias, inv_scale, out_hi, out_lo);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
 static int prof_mark(cvb_model* m, cudaStream_t st) {
   if (!m->profiling) return 0;
   if (m->prof_used == m->prof_events.size()) {
@@ -518,13 +561,11 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
         CK(cudaGetLastError());
         if (prof_mark(m, st)) return 1;  // kind 0 = SIMT front (conv1+pool1 here), kind 1 = tcgen05 conv2
         using T = tc::Conv2Tc;
-        const int64_t t2 = (n * T::RPS + T::TILE_STEP - 1) / T::TILE_STEP;
-        int g2 = (int)std::min<int64_t>(t2, sms);
         __half* p2_hi = reinterpret_cast<__half*>(m->d_p2);
-        tc::k_conv_tc<T><<<g2, T::THREADS, T::SMEM_BYTES, st>>>(m->map_c2a_hi, m->map_c2a_lo, m->map_c2b_hi, m->map_c2b_lo,
-                                                                 m->map_c2a4, m->map_c2b2, m->map_c2b3, m->map_c2b4, m->tc_merged,
-                                                                 n, m->var("conv2/bias"), m->d_inv_scale + 2, p2_hi,
-                                                                 p2_hi + m->p2_rows * 128);
+        if (launch_conv_tc<T>(m, n, st, m->map_c2a_hi, m->map_c2a_lo, m->map_c2b_hi, m->map_c2b_lo, m->map_c2a4, m->map_c2b2,
+                              m->map_c2b3, m->map_c2b4, m->map_c2h2, m->map_c2h3, m->map_c2h4, m->var("conv2/bias"),
+                              m->d_inv_scale + 2, p2_hi, p2_hi + m->p2_rows * 128))
+          return 1;
         m->launches += 1;
       } else if (tensor && m->tc_conv3) {
         auto k = k_v3_front<4, true>;
@@ -552,13 +593,11 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       int grid = (int)std::min<int64_t>(tiles, sms);
       if (tensor && m->tc_conv3) {
         using T = tc::Conv3Tc;
-        const int64_t t3 = (n * T::RPS + T::TILE_STEP - 1) / T::TILE_STEP;
-        int g3 = (int)std::min<int64_t>(t3, sms);
         __half* p3_hi = reinterpret_cast<__half*>(m->d_p3);
-        tc::k_conv_tc<T><<<g3, T::THREADS, T::SMEM_BYTES, st>>>(m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo,
-                                                                 m->map_c3a4, m->map_c3b2, m->map_c3b3, m->map_c3b4, m->tc_merged, n,
-                                                              m->var("conv3/bias"), m->d_inv_scale + 1, p3_hi,
-                                                              p3_hi + m->alloc_sites * 4608);
+        if (launch_conv_tc<T>(m, n, st, m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo, m->map_c3a4, m->map_c3b2,
+                              m->map_c3b3, m->map_c3b4, m->map_c3h2, m->map_c3h3, m->map_c3h4, m->var("conv3/bias"),
+                              m->d_inv_scale + 1, p3_hi, p3_hi + m->alloc_sites * 4608))
+          return 1;
       } else if (tensor) {
         auto k = k_conv_layer<C, 3, 256, true>;
         CK(set_smem(k, L::SMEM_BYTES));
