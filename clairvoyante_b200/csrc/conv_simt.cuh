@@ -169,4 +169,29 @@ __device__ __forceinline__ void conv_store_selu_global(const float (&acc)[C::TM]
   }
 }
 
+// Same as conv_store_selu_global but as two fp16 planes (hi at dst_hi, lo at dst_lo), hi + lo ~= value: the A operand
+// of a tensor-core consumer (conv_tc.cuh).  tc::split_f16x2 lives in tc_common.cuh; include that before use.
+template <class C, int DROWS, int DRS, int DR0, class SplitFn>
+__device__ __forceinline__ void conv_store_selu_global_split(const float (&acc)[C::TM][C::TN], const float* __restrict__ bias_s,
+                                                             const ConvThread<C>& th, void* __restrict__ dst_hi,
+                                                             void* __restrict__ dst_lo, int nsites, SplitFn split) {
+  if (!th.active) return;
+  float bv[C::TN];
+#pragma unroll
+  for (int j = 0; j < C::TN; ++j) bv[j] = bias_s[(th.nt + C::NT * (j / 4)) * 4 + (j & 3)];
+#pragma unroll
+  for (int i = 0; i < C::TM; ++i) {
+    int p = th.pair(i);
+    if (p < 0) continue;
+    int site = p / C::HOUT, h = p - site * C::HOUT;
+    if (site >= nsites) continue;
+    const int64_t o = ((int64_t)site * DROWS + h + DR0) * DRS + th.w * C::COUT + th.nt * 4;
+#pragma unroll
+    for (int j = 0; j < C::TN / 4; ++j)
+      split(selu_f(acc[i][j * 4 + 0] + bv[j * 4 + 0]), selu_f(acc[i][j * 4 + 1] + bv[j * 4 + 1]),
+            selu_f(acc[i][j * 4 + 2] + bv[j * 4 + 2]), selu_f(acc[i][j * 4 + 3] + bv[j * 4 + 3]), dst_hi, dst_lo,
+            o + j * (4 * C::NT));
+  }
+}
+
 }  // namespace cvb

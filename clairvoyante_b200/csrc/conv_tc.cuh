@@ -31,9 +31,11 @@ namespace tc {
 
 // RPS  rows per site of the input layout      HOUT  conv output rows per site (stored row r -> h = r % RPS)
 // ORPS rows per site of the output layout     OR0   output row of pooled row 0 (1 if the consumer needs a zero row on top)
-template <int RPS_, int KH_, int CIN_, int COUT_, int HOUT_, int POOL_, int ORPS_, int OR0_, int STAGES_>
+// OUTF32 = true: the epilogue stores fp32 [site][ORPS][4*COUT] (consumer is a SIMT kernel) instead of fp16 hi/lo planes
+template <int RPS_, int KH_, int CIN_, int COUT_, int HOUT_, int POOL_, int ORPS_, int OR0_, int STAGES_, bool OUTF32_ = false>
 struct ConvTcCfg {
   static constexpr int RPS = RPS_, KH = KH_, CIN = CIN_, COUT = COUT_, HOUT = HOUT_, POOL = POOL_, ORPS = ORPS_, OR0 = OR0_;
+  static constexpr bool OUT_F32 = OUTF32_;
   static constexpr int HPOOL = HOUT - POOL + 1, NOUT = 4 * COUT, KROW = 4 * CIN;
   static constexpr int QROWS = 32, QSTEP = 33 - POOL, TILE_STEP = 4 * QSTEP;
   static constexpr int BK = CIN, STAGES = STAGES_, STEPS = KH * 4;
@@ -56,6 +58,9 @@ struct ConvTcCfg {
 
 using Conv2Tc = ConvTcCfg<30, 2, 16, 32, 29, 4, 28, 1, 6>;  // p1 [site][30][64]  -> p2 [site][28][128] (rows 1..26)
 using Conv3Tc = ConvTcCfg<28, 3, 32, 48, 26, 3, 24, 0, 4>;  // p2 [site][28][128] -> p3 [site][24][192]
+// v3_slim conv3 (clairvoyante_v3_slim.py:72-79): 5x4, 16 -> 32, no pooling; p2 [site][37][64] (2 zero rows above and
+// below) -> p3 fp32 [site][33][128] = the 4224-wide input of the slim FC4 (SIMT)
+using SlimConv3Tc = ConvTcCfg<37, 5, 16, 32, 33, 1, 33, 0, 6, true>;
 
 // W [KH][4][CIN][COUT] fp32 (HWIO) -> B [kh][w][co][(w',c)] fp16 hi/lo, K-major rows of 4*CIN, scaled by 2^s with
 // |W|max * 2^s < 2^14; entries whose kw = w'-w+1 falls outside [0,3] are zero (never read by the kernel).
@@ -259,7 +264,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) split_f16x2(pv[2 * j], pv[2 * j + 1], hi[j], lo[j]);
-        if (store) {
+        if (F::OUT_F32) {
+          if (store) {
+            float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_hi) + o + cc);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = make_float4(pv[4 * j], pv[4 * j + 1], pv[4 * j + 2], pv[4 * j + 3]);
+          }
+        } else if (store) {
           *reinterpret_cast<uint4*>(dhi + cc) = *reinterpret_cast<const uint4*>(hi);
           *reinterpret_cast<uint4*>(dhi + cc + 8) = *reinterpret_cast<const uint4*>(hi + 4);
           *reinterpret_cast<uint4*>(dlo + cc) = *reinterpret_cast<const uint4*>(lo);

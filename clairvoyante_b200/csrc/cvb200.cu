@@ -88,6 +88,7 @@ struct cvb_model {
   // rows per fp16 plane of p1 / p2 (sites*RPS + slack, a multiple of the consumer's quadrant step so that the
   // merged 4-D TMA view's plane stride is a multiple of its quadrant stride); lo plane = hi plane + rows*KROW
   int64_t p1_rows = 0, p2_rows = 0;
+  size_t p2_bytes = 0;
   CUtensorMap map_c2a4, map_c2b2, map_c2b3, map_c2b4, map_c3a4, map_c3b2, map_c3b3, map_c3b4;
   int tc_merged = 1;
   int tc_cluster = 1;  // 2-CTA clusters with weight multicast in the conv tensor kernels (needs tc_merged)
@@ -176,9 +177,11 @@ extern "C" int cvb_create(int variant, int device, cvb_model** out) {
   CK(cudaMalloc(&m->d_m, pb));      CK(cudaMemset(m->d_m, 0, pb));
   CK(cudaMalloc(&m->d_v, pb));      CK(cudaMemset(m->d_v, 0, pb));
   CK(cudaMalloc(&m->d_grad, pb + 256)); CK(cudaMemset(m->d_grad, 0, pb + 256));
-  m->p2_rows = ((CHUNK * 28 + 160 + 29) / 30) * 30;
+  if (variant == CVB_V3) m->p2_rows = ((CHUNK * 28 + 160 + 29) / 30) * 30;   // multiple of conv3's quadrant step
+  else m->p2_rows = ((CHUNK * 37 + 160 + 31) / 32) * 32;                      // slim: 37 rows/site, quadrant step 32
   m->p1_rows = ((CHUNK * 30 + 160 + 28) / 29) * 29;
-  const size_t p2_bytes = std::max((size_t)CHUNK * m->p2_site * 4, (size_t)m->p2_rows * 128 * 2 * 2) + 4096;
+  m->p2_bytes = std::max((size_t)CHUNK * m->p2_site * 4, (size_t)m->p2_rows * (variant == CVB_V3 ? 128 : 64) * 2 * 2) + 4096;
+  const size_t p2_bytes = m->p2_bytes;
   CK(cudaMalloc(&m->d_p2, p2_bytes)); CK(cudaMemset(m->d_p2, 0, p2_bytes));
   CK(cudaMalloc(&m->d_p3, (size_t)CHUNK * m->p3_site * 4));
   CK(cudaMalloc(&m->d_h4, (size_t)CHUNK * m->h4_site * 4));
@@ -419,9 +422,44 @@ static int tc_setup(cvb_model* m) {
   return 0;
 }
 
+// v3_slim: only conv3 (78 % of its FLOPs) runs on tcgen05; conv1+conv2 stay in the SIMT front kernel (which then writes
+// p2 as fp16 hi/lo planes), FC4/FC5/heads stay SIMT and read conv3's fp32 output.
+static int tc_setup_slim(cvb_model* m) {
+  if (m->tc_ready) return 0;
+  using C = tc::SlimConv3Tc;
+  CK(cudaMalloc(&m->d_absmax, 16));
+  CK(cudaMalloc(&m->d_inv_scale, 16));
+  CK(cudaMalloc(&m->d_w3b_hi, (size_t)C::B_ROWS_TOTAL * C::KROW * 2 * 2));
+  m->d_w3b_lo = m->d_w3b_hi + (size_t)C::B_ROWS_TOTAL * C::KROW;
+  if (make_conv_merged_maps<C>(m->d_p2, m->p2_rows, m->d_w3b_hi, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c3a4, &m->map_c3b2, &m->map_c3b3,
+                               &m->map_c3b4, &m->map_c3h2, &m->map_c3h3, &m->map_c3h4))
+    return 1;
+  m->map_c3a_hi = m->map_c3a_lo = m->map_c3a4;  // the per-quadrant 2-D maps are not used in merged mode
+  m->map_c3b_hi = m->map_c3b_lo = m->map_c3b2;
+  m->tc_merged = 1;
+  const char* ec = getenv("CVB_TC_CLUSTER");
+  m->tc_cluster = !(ec && ec[0] == '0');
+  CK(cudaFuncSetAttribute(tc::k_conv_tc<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tc::k_conv_tc<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  m->tc_ready = true;
+  m->tc_weights_dirty = true;
+  return 0;
+}
+
 // (re)build the split fp16 copy of fc4/kernel on `st` if the fp32 master changed
 static int tc_refresh_weights(cvb_model* m, cudaStream_t st) {
   if (!m->tc_weights_dirty) return 0;
+  if (m->variant == CVB_V3_SLIM) {
+    using C = tc::SlimConv3Tc;
+    CK(cudaMemsetAsync(m->d_absmax + 1, 0, 4, st));
+    tc::k_absmax<<<32, 256, 0, st>>>(m->var("conv3/kernel"), 5 * 4 * 16 * 32, m->d_absmax + 1);
+    tc::k_prep_conv_weights<C><<<(C::B_ROWS_TOTAL * C::KROW + 255) / 256, 256, 0, st>>>(m->var("conv3/kernel"), m->d_absmax + 1,
+                                                                                        m->d_w3b_hi, m->d_w3b_lo, m->d_inv_scale + 1);
+    CK(cudaGetLastError());
+    m->launches += 2;
+    m->tc_weights_dirty = false;
+    return 0;
+  }
   using F = tc::Fc4Tc;
   const int K = 4608;
   CK(cudaMemsetAsync(m->d_absmax, 0, 4, st));
@@ -465,14 +503,12 @@ extern "C" int cvb_set_compute_mode(cvb_model* m, int mode) {
   if (!m) return fail("NULL model");
   if (mode != CVB_COMPUTE_FP32 && mode != CVB_COMPUTE_FP16X3)
     return fail("cvb_set_compute_mode: mode %d is not built into this library yet", mode);
-  if (mode == CVB_COMPUTE_FP16X3 && m->variant != CVB_V3)
-    return fail("cvb_set_compute_mode: the tensor-core path is built for v3 only so far");
   CK(cudaSetDevice(m->device));
-  if (mode == CVB_COMPUTE_FP16X3 && tc_setup(m)) return 1;
+  if (mode == CVB_COMPUTE_FP16X3 && (m->variant == CVB_V3 ? tc_setup(m) : tc_setup_slim(m))) return 1;
   if (mode != m->compute_mode) {
     // p2's zero padding rows sit at different byte offsets in the fp32 and the fp16 hi/lo layouts
     CK(cudaDeviceSynchronize());
-    CK(cudaMemset(m->d_p2, 0, std::max((size_t)m->alloc_sites * m->p2_site * 4, (size_t)m->p2_rows * 128 * 2 * 2)));
+    CK(cudaMemset(m->d_p2, 0, m->p2_bytes));
   }
   m->compute_mode = mode;
   m->CHUNK = (int64_t)m->num_sms * (m->variant == CVB_V3 ? (mode == CVB_COMPUTE_FP32 ? 96 : 128) : 224);
@@ -655,17 +691,31 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
   } else {
     {
       using F = FrontSlim<6>;
-      auto k = k_slim_front<6>;
-      CK(set_smem(k, F::SMEM_BYTES));
       int64_t tiles = (n + 5) / 6;
       int grid = (int)std::min<int64_t>(tiles, 4 * sms);
-      k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
-                                          m->var("conv2/bias"), m->d_p2);
+      if (tensor) {
+        auto k = k_slim_front<6, true>;
+        CK(set_smem(k, F::SMEM_BYTES));
+        k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
+                                            m->var("conv2/bias"), m->d_p2, reinterpret_cast<__half*>(m->d_p2) + m->p2_rows * 64);
+      } else {
+        auto k = k_slim_front<6, false>;
+        CK(set_smem(k, F::SMEM_BYTES));
+        k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
+                                            m->var("conv2/bias"), m->d_p2, nullptr);
+      }
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
       if (prof_mark(m, st)) return 1;  // (no separate conv2 kernel)
     }
-    {
+    if (tensor) {
+      using T = tc::SlimConv3Tc;
+      if (launch_conv_tc<T>(m, n, st, m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo, m->map_c3a4, m->map_c3b2, m->map_c3b3,
+                            m->map_c3b4, m->map_c3h2, m->map_c3h3, m->map_c3h4, m->var("conv3/bias"), m->d_inv_scale + 1,
+                            reinterpret_cast<__half*>(m->d_p3), nullptr))
+        return 1;
+      if (prof_mark(m, st)) return 1;
+    } else {
       using C = ConvCfg<16, 32, 5, 33, 3, 8, 8>;
       using L = ConvLayerSmem<C, 1>;
       auto k = k_conv_layer<C, 1, 256, false>;
@@ -799,7 +849,7 @@ extern "C" int cvb_debug_read(cvb_model* m, int which, float* host, int64_t n) {
   if (which == 3 || which == 4) {  // fp16 hi/lo pair of p2 (3) / p3 (4) in tensor mode, recombined to fp32
     const int64_t per3 = which == 3 ? m->p2_site : m->p3_site;
     const __half* hi = reinterpret_cast<const __half*>(which == 3 ? m->d_p2 : m->d_p3);
-    const __half* lo = hi + (which == 3 ? m->p2_rows * 128 : m->alloc_sites * per3);
+    const __half* lo = hi + (which == 3 ? m->p2_rows * (m->variant == CVB_V3 ? 128 : 64) : m->alloc_sites * per3);
     if (n < 0 || n > m->alloc_sites * per3) return fail("cvb_debug_read: n out of range");
     std::vector<__half> h((size_t)n), l((size_t)n);
     CK(cudaSetDevice(m->device));

@@ -223,10 +223,11 @@ struct FrontSlim {
   static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
 };
 
-template <int S>
+// SPLIT = true: p2 as two fp16 planes (hi at p2, lo at p2_lo) for the tcgen05 slim conv3
+template <int S, bool SPLIT>
 __global__ void __launch_bounds__(256, 2)
 k_slim_front(const float* __restrict__ x, int64_t n, const float* __restrict__ w1g, const float* __restrict__ b1g,
-             const float* __restrict__ w2g, const float* __restrict__ b2g, float* __restrict__ p2) {
+             const float* __restrict__ w2g, const float* __restrict__ b2g, float* __restrict__ p2, void* __restrict__ p2_lo) {
   using F = FrontSlim<S>;
   using C1 = typename F::C1;
   using C2 = typename F::C2;
@@ -271,7 +272,19 @@ k_slim_front(const float* __restrict__ x, int64_t n, const float* __restrict__ w
       float acc[C2::TM][C2::TN];
       conv_compute<C2>(c1s, w2s, th2, acc);
       int nsites = (int)((n - site0) < S ? (n - site0) : S);
-      conv_store_selu_global<C2, 37, 64, 2>(acc, b2s, th2, p2 + site0 * (37 * 64), nsites);
+      if constexpr (SPLIT) {
+        auto split4 = [](float a, float b, float c, float d, void* hi, void* lo, int64_t o) {
+          __half2 h[2], l[2];
+          tc::split_f16x2(a, b, h[0], l[0]);
+          tc::split_f16x2(c, d, h[1], l[1]);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(hi) + o) = *reinterpret_cast<const uint2*>(h);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(lo) + o) = *reinterpret_cast<const uint2*>(l);
+        };
+        conv_store_selu_global_split<C2, 37, 64, 2>(acc, b2s, th2, reinterpret_cast<__half*>(p2) + site0 * (37 * 64),
+                                                    reinterpret_cast<__half*>(p2_lo) + site0 * (37 * 64), nsites, split4);
+      } else {
+        conv_store_selu_global<C2, 37, 64, 2>(acc, b2s, th2, p2 + site0 * (37 * 64), nsites);
+      }
     }
   }
 }

@@ -74,11 +74,11 @@ class ClairvoyanteBase(object):
         h = ctypes.c_void_p()
         _lib.check(self._lib.cvb_create(_VARIANT_ID[self.VARIANT], self.device, ctypes.byref(h)))
         self._h = h
-        # arithmetic mode: v3 defaults to the tensor-core path (split-fp16 operands, fp32 accumulate,
+        # arithmetic mode: defaults to the tensor-core path (split-fp16 operands, fp32 accumulate,
         # logits within 1e-3 of fp64); CVB_COMPUTE=fp32 selects the all-SIMT fp32 kernels.
         mode = os.environ.get("CVB_COMPUTE", "auto")
         if mode == "auto":
-            mode = "fp16x3" if self.VARIANT == "v3" else "fp32"
+            mode = "fp16x3"        # v3: conv2/conv3/FC4/tail on tcgen05; v3_slim: conv3 on tcgen05
         self.computeMode = None
         self.setComputeMode(mode)
         self._dropout_calls = 0

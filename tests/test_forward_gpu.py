@@ -19,7 +19,7 @@ TOL = 1e-3
 
 
 # (variant, compute mode): every parity test runs on each arithmetic path the library ships
-CASES = [("v3", "fp16x3"), ("v3", "fp32"), ("v3_slim", "fp32")]
+CASES = [("v3", "fp16x3"), ("v3", "fp32"), ("v3_slim", "fp16x3"), ("v3_slim", "fp32")]
 
 
 def _model(variant, W, mode=None, **kw):
@@ -61,8 +61,9 @@ def _check(variant, W, x, m=None, tol=TOL, mode=None):
         m.close()
 
 
-def test_default_mode_is_tensor_path_for_v3():
-    m = _model("v3", I.init_weights("v3", 0))
+@pytest.mark.parametrize("variant", ["v3", "v3_slim"])
+def test_default_mode_is_tensor_path(variant):
+    m = _model(variant, I.init_weights(variant, 0))
     assert m.computeMode == "fp16x3"
     m.close()
 
