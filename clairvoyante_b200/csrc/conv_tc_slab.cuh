@@ -1,0 +1,240 @@
+// conv_tc_slab.cuh -- second-generation tcgen05 conv kernel: same math and epilogue contract as conv_tc.cuh
+// (row-shifted implicit GEMM, split-fp16 operands, bias + SELU + (POOL,1) max-pool, hi/lo or fp32 output), but the
+// activation operand is loaded ONCE per (tile, input column w') as a slab of 128 + KH - 1 rows and re-used for every kh
+// through row-shifted UMMA descriptors: tools/umma_shift_probe.cu shows that a K-major SWIZZLE_64B/32B descriptor whose
+// start address is advanced by whole rows reads rows (i + shift) with base_offset = 0 (the swizzle is a function of the
+// absolute shared-memory address).  conv_tc.cuh re-loads A for every kh: 196 KB of A per conv3 tile instead of 70 KB,
+// and the kernels are bound by operand ingest (profiles/r01_tensor_path.md).
+//
+// Tile = 128 CONSECUTIVE flattened rows (TMEM lane = row); a tile owns TILE_STEP = 129 - POOL pooled rows.  The pooling
+// window of the last POOL-1 lanes of a TMEM quadrant reaches into the next quadrant, which another warp holds: every
+// epilogue warp publishes the raw accumulators of its first POOL-1 lanes in a small smem exchange buffer, the four warps
+// of a column block meet at a named barrier, and the top lanes read their neighbours' rows from there.
+//
+// Warp roles (64 + 32*16 threads), persistent CTAs:
+//   warp 0    : TMA producer -- per tile: for w' in (2,0,1,3): one A slab {BK, 136 rows, 2 planes}; for kh: one weight box
+//   warp 1    : MMA issuer   -- per (w', kh): CIN/16 K-steps x 3 split terms with A start = slab + kh rows
+//   warps 2-17: epilogue     -- whole accumulator row (COUT columns) to registers, TMEM released early, exchange, pool,
+//                               SELU, split, store
+#pragma once
+#include "conv_tc.cuh"
+
+namespace cvb {
+namespace tc {
+
+template <class F, int SA_, int SB_>
+struct ConvSlabCfg {
+  static constexpr int SA = SA_, SB = SB_;
+  static constexpr int SLAB_ROWS = ((128 + F::KH - 1 + 7) / 8) * 8;
+  static constexpr int TILE_STEP = 129 - F::POOL;
+  static constexpr int A_PLANE = SLAB_ROWS * F::ROW_BYTES;
+  static constexpr int A_SLOT = 2 * A_PLANE;
+  static constexpr int B_SLOT = 2 * F::NOUT * F::ROW_BYTES;
+  static constexpr int XCH_FLOATS = F::POOL > 1 ? 2 * 4 * 4 * (F::POOL - 1) * F::COUT : 4;
+  static constexpr int RING_BYTES = SA * A_SLOT + SB * B_SLOT;
+  static constexpr int SMEM_BYTES = RING_BYTES + 1024 + 512 + XCH_FLOATS * 4;
+  static_assert(A_SLOT % 1024 == 0 || F::ROW_BYTES == 32, "slab slots keep the swizzle atoms aligned");
+  static_assert(SMEM_BYTES <= 227 * 1024, "does not fit in shared memory");
+};
+
+using Conv2Slab = ConvSlabCfg<Conv2Tc, 4, 8>;
+using Conv3Slab = ConvSlabCfg<Conv3Tc, 3, 6>;
+using SlimConv3Slab = ConvSlabCfg<SlimConv3Tc, 4, 8>;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <class F, class S>
+__global__ void __launch_bounds__(F::THREADS, 1)
+k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane), box {BK, SLAB_ROWS, 2}
+            const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ CUtensorMap map_b3,
+            const __grid_constant__ CUtensorMap map_b4,  // 3-D (k, row, plane), box {BK, nb*COUT, 2}
+            int64_t n, const float* __restrict__ bias, const float* __restrict__ inv_scale, __half* __restrict__ out_hi,
+            __half* __restrict__ out_lo) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + S::SA * S::A_SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::RING_BYTES);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + S::SA;
+  uint64_t* fullB = emptyA + S::SA;
+  uint64_t* emptyB = fullB + S::SB;
+  uint64_t* acc_full = emptyB + S::SB;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* xch = reinterpret_cast<float*>(smem + S::RING_BYTES + 512);
+  static_assert((2 * S::SA + 2 * S::SB + 4) * 8 + 8 <= 512, "barrier block");
+
+  __shared__ float bias_s[F::COUT];
+  if (threadIdx.x < F::COUT) bias_s[threadIdx.x] = bias[threadIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t total_rows = n * F::RPS;
+  const int64_t ntiles = (total_rows + S::TILE_STEP - 1) / S::TILE_STEP;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b2); tma_prefetch_desc(&map_b3); tma_prefetch_desc(&map_b4);
+    for (int s = 0; s < S::SA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < S::SB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], F::EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, F::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // w' order inside a tile: 2 first (its MMAs cover all NOUT columns and initialise the accumulator), then 0, 1, 3
+  auto wp_of = [](int i) { return i == 0 ? 2 : (i < 3 ? i - 1 : 3); };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      uint32_t ia = 0, ib = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int r0 = (int)(tile * S::TILE_STEP);
+        for (int i = 0; i < 4; ++i, ++ia) {
+          const int wp = wp_of(i);
+          const int wl = F::wlo(wp), nb = F::whi(wp) - wl + 1;
+          const int sa = ia % S::SA;
+          mbar_wait(&emptyA[sa], ((ia / S::SA) & 1) ^ 1);
+          mbar_arrive_expect_tx(&fullA[sa], S::A_SLOT);
+          tma_load_3d(a_ring + sa * S::A_SLOT, &map_a, &fullA[sa], wp * F::CIN, r0, 0);
+          const CUtensorMap* mb = nb == 2 ? &map_b2 : (nb == 3 ? &map_b3 : &map_b4);
+          for (int kh = 0; kh < F::KH; ++kh, ++ib) {
+            const int sb = ib % S::SB;
+            mbar_wait(&emptyB[sb], ((ib / S::SB) & 1) ^ 1);
+            mbar_arrive_expect_tx(&fullB[sb], 2 * nb * F::COUT * F::ROW_BYTES);
+            tma_load_3d(b_ring + sb * S::B_SLOT, mb, &fullB[sb], wp * F::CIN, kh * F::NOUT + wl * F::COUT, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      uint32_t ia = 0, ib = 0, tcount = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        const int buf = tcount & 1;
+        mbar_wait(&acc_empty[buf], ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int i = 0; i < 4; ++i, ++ia) {
+          const int wp = wp_of(i);
+          const int wl = F::wlo(wp), nb = F::whi(wp) - wl + 1;
+          const uint32_t idesc = umma_idesc_f16(128, nb * F::COUT);
+          const uint32_t tcol = tmem_base + buf * 256 + wl * F::COUT;
+          const int sa = ia % S::SA;
+          mbar_wait(&fullA[sa], (ia / S::SA) & 1);
+          const uint32_t a_hi0 = smem_u32(a_ring + sa * S::A_SLOT), a_lo0 = a_hi0 + S::A_PLANE;
+          for (int kh = 0; kh < F::KH; ++kh, ++ib) {
+            const int sb = ib % S::SB;
+            mbar_wait(&fullB[sb], (ib / S::SB) & 1);
+            tc_fence_after();
+            const uint32_t b_hi = smem_u32(b_ring + sb * S::B_SLOT), b_lo = b_hi + nb * F::COUT * F::ROW_BYTES;
+            const uint32_t a_hi = a_hi0 + kh * F::ROW_BYTES, a_lo = a_lo0 + kh * F::ROW_BYTES;  // rows shifted by kh
+#pragma unroll
+            for (int ks = 0; ks < F::BK / 16; ++ks) {
+              const uint32_t ko = ks * 32;
+              const uint64_t dah = umma_desc(a_hi + ko, 16, F::SBO, F::LAYOUT);
+              const uint64_t dal = umma_desc(a_lo + ko, 16, F::SBO, F::LAYOUT);
+              const uint64_t dbh = umma_desc(b_hi + ko, 16, F::SBO, F::LAYOUT);
+              const uint64_t dbl = umma_desc(b_lo + ko, 16, F::SBO, F::LAYOUT);
+              umma_f16(tcol, dal, dbh, idesc, (uint32_t)((i | kh | ks) != 0));
+              umma_f16(tcol, dah, dbl, idesc, 1u);
+              umma_f16(tcol, dah, dbh, idesc, 1u);
+            }
+            umma_commit(&emptyB[sb]);
+          }
+          umma_commit(&emptyA[sa]);
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..17) =====================
+    const int q = warp & 3;             // TMEM lane quadrant
+    const int wblk = (warp - 2) >> 2;   // output column block w (COUT channels) owned by this warp
+    const float isc = inv_scale[0];
+    uint32_t tcount = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const int buf = tcount & 1;
+      const int tr = q * 32 + lane;                                  // row inside the tile
+      const int64_t r = tile * S::TILE_STEP + tr;                    // flattened stored row of this thread
+      const int64_t site = r / F::RPS;
+      const int hs = (int)(r - site * F::RPS);
+      const bool store = tr < S::TILE_STEP && hs < F::HPOOL && site < n;
+      const int64_t o = (site * F::ORPS + hs + F::OR0) * F::NOUT + wblk * F::COUT;
+      mbar_wait(&acc_full[buf], (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + wblk * F::COUT;
+      float raw[F::COUT];
+#pragma unroll
+      for (int cc = 0; cc < F::COUT; cc += 16) {
+        uint32_t rr[16];
+        tmem_ld16(taddr + cc, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) raw[cc + j] = __uint_as_float(rr[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);  // the accumulator is in registers: let the next tile's MMAs start
+      if (F::POOL > 1) {
+        float* xb = xch + ((size_t)(buf * 4 + wblk) * 4) * (F::POOL - 1) * F::COUT;  // [q][POOL-1][COUT]
+        if (lane < F::POOL - 1) {
+          float* d = xb + (q * (F::POOL - 1) + lane) * F::COUT;
+#pragma unroll
+          for (int j = 0; j < F::COUT; j += 4) *reinterpret_cast<float4*>(d + j) = make_float4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
+        }
+        named_bar_sync(1 + wblk, 128);  // the four quadrant warps of this column block
+        const float* nx = xb + ((q + 1) & 3) * (F::POOL - 1) * F::COUT;  // rows 0..POOL-2 of the next quadrant (unused for q = 3)
+#pragma unroll
+        for (int j = 0; j < F::COUT; ++j) {
+          const float v = raw[j];
+          float mx = v;
+#pragma unroll
+          for (int d = 1; d < F::POOL; ++d) {
+            float t = __shfl_down_sync(0xffffffffu, v, d);
+            if (lane + d >= 32) t = nx[(lane + d - 32) * F::COUT + j];
+            mx = fmaxf(mx, t);
+          }
+          raw[j] = mx;  // max over rows r .. r+POOL-1 (pooling raw accumulators before SELU is exact, see conv_tc.cuh)
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < F::COUT; cc += 16) {
+        float pv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pv[j] = selu_f(fmaf(raw[cc + j], isc, bias_s[cc + j]));
+        if (F::OUT_F32) {
+          if (store) {
+            float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_hi) + o + cc);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = make_float4(pv[4 * j], pv[4 * j + 1], pv[4 * j + 2], pv[4 * j + 3]);
+          }
+        } else {
+          __align__(16) __half2 hi[8];
+          __align__(16) __half2 lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) split_f16x2(pv[2 * j], pv[2 * j + 1], hi[j], lo[j]);
+          if (store) {
+            *reinterpret_cast<uint4*>(out_hi + o + cc) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(out_hi + o + cc + 8) = *reinterpret_cast<const uint4*>(hi + 4);
+            *reinterpret_cast<uint4*>(out_lo + o + cc) = *reinterpret_cast<const uint4*>(lo);
+            *reinterpret_cast<uint4*>(out_lo + o + cc + 8) = *reinterpret_cast<const uint4*>(lo + 4);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, F::TMEM_COLS);
+  }
+}
+
+}  // namespace tc
+}  // namespace cvb

@@ -14,6 +14,7 @@
 #include "fwd_simt.cuh"
 #include "fc4_tc.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc_slab.cuh"
 #include "tail_tc.cuh"
 #include <math.h>
 #include <stdlib.h>
@@ -92,6 +93,8 @@ struct cvb_model {
   CUtensorMap map_c2a4, map_c2b2, map_c2b3, map_c2b4, map_c3a4, map_c3b2, map_c3b3, map_c3b4;
   int tc_merged = 1;
   int tc_cluster = 1;  // 2-CTA clusters with weight multicast in the conv tensor kernels (needs tc_merged)
+  int tc_slab = 1;     // slab-mode conv kernels (conv_tc_slab.cuh): A loaded once per (tile, w'), re-used across kh
+  CUtensorMap map_c2slab, map_c3slab;
   CUtensorMap map_c2h2, map_c2h3, map_c2h4, map_c3h2, map_c3h3, map_c3h4;
   // fused tail (FC5 + heads) on tensor cores: A = h4 hi/lo [sites][336], B = [W5 | Wb]^T [176][336]
   __half *d_h4s = nullptr, *d_wtail = nullptr;
@@ -336,6 +339,15 @@ static int make_conv_merged_maps(void* act, int64_t rows, void* wts, CUtensorMap
   return 0;
 }
 
+// slab view for k_conv_slab: plain 3-D (k, row, plane) tensor, box {BK, SLAB_ROWS, 2}
+template <class C, class S>
+static int make_slab_map(void* act, int64_t rows, CUtensorMapSwizzle sw, CUtensorMap* out) {
+  const uint64_t d[3] = {(uint64_t)C::KROW, (uint64_t)rows, 2};
+  const uint64_t st[2] = {(uint64_t)C::KROW * 2, (uint64_t)rows * C::KROW * 2};
+  const uint32_t b[3] = {(uint32_t)C::BK, (uint32_t)S::SLAB_ROWS, 2};
+  return make_map_nd(out, act, 3, d, st, b, sw);
+}
+
 static int tc_setup(cvb_model* m) {
   if (m->tc_ready) return 0;
   using F = tc::Fc4Tc;
@@ -370,6 +382,10 @@ static int tc_setup(cvb_model* m) {
     m->tc_merged = !(em && em[0] == '0');
     const char* ec = getenv("CVB_TC_CLUSTER");
     m->tc_cluster = !(ec && ec[0] == '0');
+    const char* es = getenv("CVB_TC_SLAB");
+    m->tc_slab = !(es && es[0] == '0');
+    if (make_slab_map<C, tc::Conv3Slab>(p2_hi, m->p2_rows, CU_TENSOR_MAP_SWIZZLE_64B, &m->map_c3slab)) return 1;
+    CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::Conv3Slab>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Conv3Slab::SMEM_BYTES));
     if (m->tc_merged && make_conv_merged_maps<C>(p2_hi, m->p2_rows, m->d_w3b_hi, CU_TENSOR_MAP_SWIZZLE_64B, &m->map_c3a4,
                                                  &m->map_c3b2, &m->map_c3b3, &m->map_c3b4, &m->map_c3h2, &m->map_c3h3,
                                                  &m->map_c3h4)) {
@@ -393,12 +409,15 @@ static int tc_setup(cvb_model* m) {
     CK(cudaFuncSetAttribute(tc::k_conv_tc<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     const char* e = getenv("CVB_TC_CONV2");
     m->tc_conv2 = m->tc_conv3 && !(e && e[0] == '0');
+    if (make_slab_map<C, tc::Conv2Slab>(m->d_p1, m->p1_rows, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c2slab)) return 1;
+    CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::Conv2Slab>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Conv2Slab::SMEM_BYTES));
     if (m->tc_merged && make_conv_merged_maps<C>(m->d_p1, m->p1_rows, m->d_w2b_hi, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c2a4,
                                                  &m->map_c2b2, &m->map_c2b3, &m->map_c2b4, &m->map_c2h2, &m->map_c2h3,
                                                  &m->map_c2h4))
       m->tc_merged = 0;
     if (!m->tc_merged) {
       m->tc_cluster = 0;
+      m->tc_slab = 0;  // the slab kernels use the merged weight boxes
       m->map_c2h2 = m->map_c2h3 = m->map_c2h4 = m->map_c3h2 = m->map_c3h3 = m->map_c3h4 = m->map_c2b_hi;
       m->map_c2a4 = m->map_c2a_hi; m->map_c2b2 = m->map_c2b3 = m->map_c2b4 = m->map_c2b_hi;
       m->map_c3a4 = m->map_c3a_hi; m->map_c3b2 = m->map_c3b3 = m->map_c3b4 = m->map_c3b_hi;
@@ -439,6 +458,11 @@ static int tc_setup_slim(cvb_model* m) {
   m->tc_merged = 1;
   const char* ec = getenv("CVB_TC_CLUSTER");
   m->tc_cluster = !(ec && ec[0] == '0');
+  const char* es = getenv("CVB_TC_SLAB");
+  m->tc_slab = !(es && es[0] == '0');
+  if (make_slab_map<C, tc::SlimConv3Slab>(m->d_p2, m->p2_rows, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c3slab)) return 1;
+  CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::SlimConv3Slab>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          tc::SlimConv3Slab::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tc::k_conv_tc<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tc::k_conv_tc<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   m->tc_ready = true;
@@ -536,11 +560,19 @@ static HeadPtrs head_ptrs(const cvb_model* m) {
 
 // one chunk (n <= CHUNK) of the forward pass on `st`
 // launches k_conv_tc<T> either plainly or as 2-CTA clusters (weight multicast)
-template <class T>
-static int launch_conv_tc(cvb_model* m, int64_t n, cudaStream_t st, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+template <class T, class S>
+static int launch_conv_tc(cvb_model* m, int64_t n, cudaStream_t st, const CUtensorMap* slab, const CUtensorMap& a_hi,
+                          const CUtensorMap& a_lo,
                           const CUtensorMap& b_hi, const CUtensorMap& b_lo, const CUtensorMap& a4, const CUtensorMap& b2,
                           const CUtensorMap& b3, const CUtensorMap& b4, const CUtensorMap& h2, const CUtensorMap& h3,
                           const CUtensorMap& h4, const float* bias, const float* inv_scale, __half* out_hi, __half* out_lo) {
+  if (m->tc_slab && slab) {
+    const int64_t st_tiles = (n * T::RPS + S::TILE_STEP - 1) / S::TILE_STEP;
+    const int g = (int)std::min<int64_t>(st_tiles, m->num_sms);
+    tc::k_conv_slab<T, S><<<g, T::THREADS, S::SMEM_BYTES, st>>>(*slab, b2, b3, b4, n, bias, inv_scale, out_hi, out_lo);
+    CK(cudaGetLastError());
+    return 0;
+  }
   const int64_t tiles = (n * T::RPS + T::TILE_STEP - 1) / T::TILE_STEP;
   int grid = (int)std::min<int64_t>(tiles, m->num_sms);
   if (m->tc_cluster && m->tc_merged && grid >= 2) {
@@ -598,7 +630,7 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
         if (prof_mark(m, st)) return 1;  // kind 0 = SIMT front (conv1+pool1 here), kind 1 = tcgen05 conv2
         using T = tc::Conv2Tc;
         __half* p2_hi = reinterpret_cast<__half*>(m->d_p2);
-        if (launch_conv_tc<T>(m, n, st, m->map_c2a_hi, m->map_c2a_lo, m->map_c2b_hi, m->map_c2b_lo, m->map_c2a4, m->map_c2b2,
+        if (launch_conv_tc<T, tc::Conv2Slab>(m, n, st, &m->map_c2slab, m->map_c2a_hi, m->map_c2a_lo, m->map_c2b_hi, m->map_c2b_lo, m->map_c2a4, m->map_c2b2,
                               m->map_c2b3, m->map_c2b4, m->map_c2h2, m->map_c2h3, m->map_c2h4, m->var("conv2/bias"),
                               m->d_inv_scale + 2, p2_hi, p2_hi + m->p2_rows * 128))
           return 1;
@@ -630,9 +662,10 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       if (tensor && m->tc_conv3) {
         using T = tc::Conv3Tc;
         __half* p3_hi = reinterpret_cast<__half*>(m->d_p3);
-        if (launch_conv_tc<T>(m, n, st, m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo, m->map_c3a4, m->map_c3b2,
-                              m->map_c3b3, m->map_c3b4, m->map_c3h2, m->map_c3h3, m->map_c3h4, m->var("conv3/bias"),
-                              m->d_inv_scale + 1, p3_hi, p3_hi + m->alloc_sites * 4608))
+        if (launch_conv_tc<T, tc::Conv3Slab>(m, n, st, &m->map_c3slab, m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo,
+                                             m->map_c3a4, m->map_c3b2, m->map_c3b3, m->map_c3b4, m->map_c3h2, m->map_c3h3,
+                                             m->map_c3h4, m->var("conv3/bias"), m->d_inv_scale + 1, p3_hi,
+                                             p3_hi + m->alloc_sites * 4608))
           return 1;
       } else if (tensor) {
         auto k = k_conv_layer<C, 3, 256, true>;
@@ -710,7 +743,8 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
     }
     if (tensor) {
       using T = tc::SlimConv3Tc;
-      if (launch_conv_tc<T>(m, n, st, m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo, m->map_c3a4, m->map_c3b2, m->map_c3b3,
+      if (launch_conv_tc<T, tc::SlimConv3Slab>(m, n, st, &m->map_c3slab, m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo,
+                                               m->map_c3a4, m->map_c3b2, m->map_c3b3,
                             m->map_c3b4, m->map_c3h2, m->map_c3h3, m->map_c3h4, m->var("conv3/bias"), m->d_inv_scale + 1,
                             reinterpret_cast<__half*>(m->d_p3), nullptr))
         return 1;
