@@ -51,7 +51,9 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
             const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ CUtensorMap map_b3,
             const __grid_constant__ CUtensorMap map_b4,  // 3-D (k, row, plane), box {BK, nb*COUT, 2}
             int64_t n, const float* __restrict__ bias, const float* __restrict__ inv_scale, __half* __restrict__ out_hi,
-            __half* __restrict__ out_lo) {
+            __half* __restrict__ out_lo, int ablate) {
+  // ablate (timing experiments only, results are wrong): 1 = epilogue skips pooling/SELU/stores, 2 = no MMAs issued,
+  // 4 = weight boxes are not loaded, 8 = activation slabs are not loaded
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;
@@ -99,14 +101,20 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
           const int wl = F::wlo(wp), nb = F::whi(wp) - wl + 1;
           const int sa = ia % S::SA;
           mbar_wait(&emptyA[sa], ((ia / S::SA) & 1) ^ 1);
-          mbar_arrive_expect_tx(&fullA[sa], S::A_SLOT);
-          tma_load_3d(a_ring + sa * S::A_SLOT, &map_a, &fullA[sa], wp * F::CIN, r0, 0);
+          if (ablate & 8) mbar_arrive(&fullA[sa]);
+          else {
+            mbar_arrive_expect_tx(&fullA[sa], S::A_SLOT);
+            tma_load_3d(a_ring + sa * S::A_SLOT, &map_a, &fullA[sa], wp * F::CIN, r0, 0);
+          }
           const CUtensorMap* mb = nb == 2 ? &map_b2 : (nb == 3 ? &map_b3 : &map_b4);
           for (int kh = 0; kh < F::KH; ++kh, ++ib) {
             const int sb = ib % S::SB;
             mbar_wait(&emptyB[sb], ((ib / S::SB) & 1) ^ 1);
-            mbar_arrive_expect_tx(&fullB[sb], 2 * nb * F::COUT * F::ROW_BYTES);
-            tma_load_3d(b_ring + sb * S::B_SLOT, mb, &fullB[sb], wp * F::CIN, kh * F::NOUT + wl * F::COUT, 0);
+            if (ablate & 4) mbar_arrive(&fullB[sb]);
+            else {
+              mbar_arrive_expect_tx(&fullB[sb], 2 * nb * F::COUT * F::ROW_BYTES);
+              tma_load_3d(b_ring + sb * S::B_SLOT, mb, &fullB[sb], wp * F::CIN, kh * F::NOUT + wl * F::COUT, 0);
+            }
           }
         }
       }
@@ -135,6 +143,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
             const uint32_t a_hi = a_hi0 + kh * F::ROW_BYTES, a_lo = a_lo0 + kh * F::ROW_BYTES;  // rows shifted by kh
 #pragma unroll
             for (int ks = 0; ks < F::BK / 16; ++ks) {
+              if (ablate & 2) break;
               const uint32_t ko = ks * 32;
               const uint64_t dah = umma_desc(a_hi + ko, 16, F::SBO, F::LAYOUT);
               const uint64_t dal = umma_desc(a_lo + ko, 16, F::SBO, F::LAYOUT);
@@ -180,6 +189,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);  // the accumulator is in registers: let the next tile's MMAs start
+      if (ablate & 1) continue;
       if (F::POOL > 1) {
         float* xb = xch + ((size_t)(buf * 4 + wblk) * 4) * (F::POOL - 1) * F::COUT;  // [q][POOL-1][COUT]
         if (lane < F::POOL - 1) {

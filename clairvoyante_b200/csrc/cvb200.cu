@@ -569,7 +569,8 @@ static int launch_conv_tc(cvb_model* m, int64_t n, cudaStream_t st, const CUtens
   if (m->tc_slab && slab) {
     const int64_t st_tiles = (n * T::RPS + S::TILE_STEP - 1) / S::TILE_STEP;
     const int g = (int)std::min<int64_t>(st_tiles, m->num_sms);
-    tc::k_conv_slab<T, S><<<g, T::THREADS, S::SMEM_BYTES, st>>>(*slab, b2, b3, b4, n, bias, inv_scale, out_hi, out_lo);
+    static const int ablate = getenv("CVB_ABLATE") ? atoi(getenv("CVB_ABLATE")) : 0;  // timing experiments only
+    tc::k_conv_slab<T, S><<<g, T::THREADS, S::SMEM_BYTES, st>>>(*slab, b2, b3, b4, n, bias, inv_scale, out_hi, out_lo, ablate);
     CK(cudaGetLastError());
     return 0;
   }
