@@ -54,6 +54,13 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
                : "l"(p));
   return r;
 }
+// 256-bit global store (STG.E.256 on sm_100a): one full 32-byte sector per thread per instruction; p 32-byte aligned
+__device__ __forceinline__ void st_global_256(void* p, const void* src8x32) {
+  const uint32_t* v = reinterpret_cast<const uint32_t*>(src8x32);
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+               "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ float4 max4(float4 a, float4 b) {
   return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }

@@ -218,21 +218,19 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
 #pragma unroll
         for (int j = 0; j < 16; ++j) pv[j] = selu_f(fmaf(raw[cc + j], isc, bias_s[cc + j]));
         if (F::OUT_F32) {
-          if (store) {
-            float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_hi) + o + cc);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) d[j] = make_float4(pv[4 * j], pv[4 * j + 1], pv[4 * j + 2], pv[4 * j + 3]);
+          if (store) {  // 64 B per thread: two full-sector 256-bit stores
+            float* d = reinterpret_cast<float*>(out_hi) + o + cc;
+            st_global_256(d, pv);
+            st_global_256(d + 8, pv + 8);
           }
         } else {
           __align__(16) __half2 hi[8];
           __align__(16) __half2 lo[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) split_f16x2(pv[2 * j], pv[2 * j + 1], hi[j], lo[j]);
-          if (store) {
-            *reinterpret_cast<uint4*>(out_hi + o + cc) = *reinterpret_cast<const uint4*>(hi);
-            *reinterpret_cast<uint4*>(out_hi + o + cc + 8) = *reinterpret_cast<const uint4*>(hi + 4);
-            *reinterpret_cast<uint4*>(out_lo + o + cc) = *reinterpret_cast<const uint4*>(lo);
-            *reinterpret_cast<uint4*>(out_lo + o + cc + 8) = *reinterpret_cast<const uint4*>(lo + 4);
+          if (store) {  // 16 halves = one 32-byte sector per plane: one 256-bit store each
+            st_global_256(out_hi + o + cc, hi);
+            st_global_256(out_lo + o + cc, lo);
           }
         }
       }
