@@ -53,7 +53,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
             int64_t n, const float* __restrict__ bias, const float* __restrict__ inv_scale, __half* __restrict__ out_hi,
             __half* __restrict__ out_lo, int ablate) {
   // ablate (timing experiments only, results are wrong): 1 = epilogue skips pooling/SELU/stores, 2 = no MMAs issued,
-  // 4 = weight boxes are not loaded, 8 = activation slabs are not loaded
+  // 4 = weight boxes are not loaded, 8 = activation slabs are not loaded, 16 = no global stores, 32 = no pooling
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;
@@ -172,7 +172,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
       const int64_t r = tile * S::TILE_STEP + tr;                    // flattened stored row of this thread
       const int64_t site = r / F::RPS;
       const int hs = (int)(r - site * F::RPS);
-      const bool store = tr < S::TILE_STEP && hs < F::HPOOL && site < n;
+      const bool store = tr < S::TILE_STEP && hs < F::HPOOL && site < n && !(ablate & 16);
       const int64_t o = (site * F::ORPS + hs + F::OR0) * F::NOUT + wblk * F::COUT;
       mbar_wait(&acc_full[buf], (tcount >> 1) & 1);
       tc_fence_after();
@@ -190,7 +190,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);  // the accumulator is in registers: let the next tile's MMAs start
       if (ablate & 1) continue;
-      if (F::POOL > 1) {
+      if (F::POOL > 1 && !(ablate & 32)) {
         float* xb = xch + ((size_t)(buf * 4 + wblk) * 4) * (F::POOL - 1) * F::COUT;  // [q][POOL-1][COUT]
         if (lane < F::POOL - 1) {
           float* d = xb + (q * (F::POOL - 1) + lane) * F::COUT;
