@@ -199,6 +199,20 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
         }
         named_bar_sync(1 + wblk, 128);  // the four quadrant warps of this column block
         const float* nx = xb + ((q + 1) & 3) * (F::POOL - 1) * F::COUT;  // rows 0..POOL-2 of the next quadrant (unused for q = 3)
+        if (F::POOL == 4) {
+          // tree: m2[r] = max(v[r], v[r+1]); m4[r] = max(m2[r], m2[r+2]) -- two shuffles per channel instead of three
+          // (the shuffle pipe, one warp instruction per clock per SM, is a measurable part of this epilogue)
+#pragma unroll
+          for (int j = 0; j < F::COUT; ++j) {
+            const float v = raw[j];
+            float t1 = __shfl_down_sync(0xffffffffu, v, 1);
+            if (lane == 31) t1 = nx[j];
+            const float m2 = fmaxf(v, t1);
+            float t2 = __shfl_down_sync(0xffffffffu, m2, 2);
+            if (lane >= 30) t2 = fmaxf(nx[(lane - 30) * F::COUT + j], nx[(lane - 29) * F::COUT + j]);
+            raw[j] = fmaxf(m2, t2);
+          }
+        } else
 #pragma unroll
         for (int j = 0; j < F::COUT; ++j) {
           const float v = raw[j];

@@ -66,10 +66,13 @@ struct cvb_model {
   float *d_p2 = nullptr, *d_p3 = nullptr, *d_h4 = nullptr, *d_h5 = nullptr;
   int64_t p2_site = 0, p3_site = 0, h4_site = 0;
   // host path: 2 slots
-  float *d_x[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr}, *d_lg[2] = {nullptr, nullptr};
-  float *h_x[2] = {nullptr, nullptr}, *h_out[2] = {nullptr, nullptr}, *h_lg[2] = {nullptr, nullptr};
+  // host-call pipeline slots.  Two are not enough: with H2D(c) ~ kernels(c) ~ 0.7 ms the copy engine only gets its next
+  // transfer after the host has seen D2H(c-1), so every host wake-up and de-interleave shows up as a PCIe bubble.
+  static constexpr int NSLOT = 4;
+  float *d_x[NSLOT] = {}, *d_out[NSLOT] = {}, *d_lg[NSLOT] = {};
+  float *h_x[NSLOT] = {}, *h_out[NSLOT] = {}, *h_lg[NSLOT] = {};
   cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
-  cudaEvent_t e_h2d[2], e_comp[2], e_d2h[2];
+  cudaEvent_t e_h2d[NSLOT], e_comp[NSLOT], e_d2h[NSLOT];
   bool events = false;
   int64_t launches = 0;
   // tensor-core path (CVB_COMPUTE_FP16X3): pre-split FC4 weights + TMA descriptors
@@ -78,6 +81,8 @@ struct cvb_model {
   float* d_inv_scale = nullptr;
   bool tc_ready = false, tc_weights_dirty = true;
   CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
+  CUtensorMap map_bh_hi, map_bh_lo;  // FC4 weights with NH/2-row boxes (cluster multicast)
+  int tc_fc4_cluster = 1;
   // conv3 on tensor cores: B = rearranged conv3 weights [3*192][128], A = p2 hi/lo [sites*28][128]
   __half *d_w3b_hi = nullptr, *d_w3b_lo = nullptr;
   CUtensorMap map_c3a_hi, map_c3a_lo, map_c3b_hi, map_c3b_lo;
@@ -192,7 +197,7 @@ extern "C" int cvb_create(int variant, int device, cvb_model** out) {
   CK(cudaStreamCreateWithFlags(&m->s_comp, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&m->s_h2d, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < cvb_model::NSLOT; ++i) {
     CK(cudaEventCreateWithFlags(&m->e_h2d[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&m->e_comp[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&m->e_d2h[i], cudaEventDisableTiming));
@@ -212,7 +217,7 @@ extern "C" int cvb_destroy(cvb_model* m) {
   cudaFree(m->d_p2); cudaFree(m->d_p3); cudaFree(m->d_h4); cudaFree(m->d_h5);
   cudaFree(m->d_w3b_hi); cudaFree(m->d_p1); cudaFree(m->d_w2b_hi); cudaFree(m->d_h4s); cudaFree(m->d_wtail);
   cudaFree(m->d_w4t_hi); cudaFree(m->d_w4t_lo); cudaFree(m->d_absmax); cudaFree(m->d_inv_scale);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < cvb_model::NSLOT; ++i) {
     cudaFree(m->d_x[i]); cudaFree(m->d_out[i]); cudaFree(m->d_lg[i]);
     cudaFreeHost(m->h_x[i]); cudaFreeHost(m->h_out[i]); cudaFreeHost(m->h_lg[i]);
     if (m->events) { cudaEventDestroy(m->e_h2d[i]); cudaEventDestroy(m->e_comp[i]); cudaEventDestroy(m->e_d2h[i]); }
@@ -362,7 +367,14 @@ static int tc_setup(cvb_model* m) {
   if (make_map_f16(&m->map_a_lo, a_lo, (uint64_t)m->alloc_sites, K, F::BK, F::BM, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   if (make_map_f16(&m->map_b_hi, m->d_w4t_hi, F::N, K, F::BK, F::NH, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   if (make_map_f16(&m->map_b_lo, m->d_w4t_lo, F::N, K, F::BK, F::NH, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-  CK(cudaFuncSetAttribute(tc::k_fc4_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
+  if (make_map_f16(&m->map_bh_hi, m->d_w4t_hi, F::N, K, F::BK, F::NH / 2, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  if (make_map_f16(&m->map_bh_lo, m->d_w4t_lo, F::N, K, F::BK, F::NH / 2, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  CK(cudaFuncSetAttribute(tc::k_fc4_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tc::k_fc4_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
+  {
+    const char* e = getenv("CVB_TC_FC4_CLUSTER");
+    m->tc_fc4_cluster = !(e && e[0] == '0');
+  }
   {
     using C = tc::Conv3Tc;
     CK(cudaMalloc(&m->d_w3b_hi, (size_t)C::B_ROWS_TOTAL * C::KROW * 2 * 2));  // hi plane then lo plane
@@ -683,11 +695,27 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
     }
     if (tensor) {
       using F = tc::Fc4Tc;
-      dim3 grid(2, (unsigned)((n + F::BM - 1) / F::BM));
-      tc::k_fc4_tc<<<grid, F::THREADS, F::SMEM_BYTES, st>>>(m->map_a_hi, m->map_a_lo, m->map_b_hi, m->map_b_lo, n, 4608,
-                                                            m->var("fc4/bias"), m->d_inv_scale, m->d_h4,
-                                                            m->tc_tail ? m->d_h4s : nullptr,
-                                                            m->tc_tail ? m->d_h4s + (size_t)m->alloc_sites * 336 : nullptr);
+      const unsigned tiles4 = (unsigned)((n + F::BM - 1) / F::BM);
+      __half* h4hi = m->tc_tail ? m->d_h4s : nullptr;
+      __half* h4lo = m->tc_tail ? m->d_h4s + (size_t)m->alloc_sites * 336 : nullptr;
+      if (m->tc_fc4_cluster && tiles4 >= 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2, (tiles4 + 1) & ~1u);  // pairs of site tiles; a padding tile loads zeros and stores nothing
+        cfg.blockDim = dim3(F::THREADS);
+        cfg.dynamicSmemBytes = F::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, tc::k_fc4_tc<true>, m->map_a_hi, m->map_a_lo, m->map_bh_hi, m->map_bh_lo, n, 4608,
+                              m->var("fc4/bias"), (const float*)m->d_inv_scale, m->d_h4, h4hi, h4lo));
+      } else {
+        tc::k_fc4_tc<false><<<dim3(2, tiles4), F::THREADS, F::SMEM_BYTES, st>>>(m->map_a_hi, m->map_a_lo, m->map_b_hi, m->map_b_lo, n,
+                                                                                4608, m->var("fc4/bias"), m->d_inv_scale, m->d_h4,
+                                                                                h4hi, h4lo);
+      }
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
     } else {
@@ -799,7 +827,7 @@ extern "C" int cvb_predict_device(cvb_model* m, const float* x, int64_t n, float
 static int ensure_host_slots(cvb_model* m) {
   if (m->d_x[0]) return 0;
   const int64_t CHUNK = m->alloc_sites;  // large enough for every compute mode's chunk
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < cvb_model::NSLOT; ++i) {
     CK(cudaMalloc(&m->d_x[i], (size_t)CHUNK * 528 * 4));
     CK(cudaMalloc(&m->d_out[i], (size_t)CHUNK * 16 * 4));
     CK(cudaMalloc(&m->d_lg[i], (size_t)CHUNK * 16 * 4));
@@ -839,22 +867,24 @@ extern "C" int cvb_predict_host(cvb_model* m, const float* x, int64_t n, float* 
   const bool pinned_in = is_pinned(x);
   const int64_t CHUNK = m->CHUNK;
   const int64_t nchunks = (n + CHUNK - 1) / CHUNK;
-  // software pipeline over chunks: H2D(c+1) || kernels(c) || D2H(c-1)
-  for (int64_t c = 0; c <= nchunks; ++c) {
+  // software pipeline over chunks: the host enqueues H2D(c), kernels(c), D2H(c) and only then collects chunk c-LAG, so
+  // the copy engines always have LAG chunks of work queued ahead of the host
+  constexpr int NS = cvb_model::NSLOT, LAG = NS - 1;
+  for (int64_t c = 0; c < nchunks + LAG; ++c) {
     if (c < nchunks) {
-      const int sl = (int)(c & 1);
+      const int sl = (int)(c % NS);
       const int64_t s0 = c * CHUNK, cn = std::min<int64_t>(CHUNK, n - s0);
       const float* src = x + s0 * 528;
       if (!pinned_in) {
-        if (c >= 2) CK(cudaEventSynchronize(m->e_h2d[sl]));  // staging buffer free again
+        if (c >= NS) CK(cudaEventSynchronize(m->e_h2d[sl]));  // staging buffer free again
         memcpy(m->h_x[sl], src, (size_t)cn * 528 * 4);
         src = m->h_x[sl];
       }
-      if (c >= 2) CK(cudaStreamWaitEvent(m->s_h2d, m->e_comp[sl], 0));  // d_x[sl] consumed
+      if (c >= NS) CK(cudaStreamWaitEvent(m->s_h2d, m->e_comp[sl], 0));  // d_x[sl] consumed
       CK(cudaMemcpyAsync(m->d_x[sl], src, (size_t)cn * 528 * 4, cudaMemcpyHostToDevice, m->s_h2d));
       CK(cudaEventRecord(m->e_h2d[sl], m->s_h2d));
       CK(cudaStreamWaitEvent(m->s_comp, m->e_h2d[sl], 0));
-      if (c >= 2) CK(cudaStreamWaitEvent(m->s_comp, m->e_d2h[sl], 0));  // d_out[sl] drained
+      if (c >= NS) CK(cudaStreamWaitEvent(m->s_comp, m->e_d2h[sl], 0));  // d_out[sl] drained
       if (forward_chunk(m, m->d_x[sl], cn, m->d_out[sl], logits16 ? m->d_lg[sl] : nullptr, m->s_comp)) return 1;
       CK(cudaEventRecord(m->e_comp[sl], m->s_comp));
       CK(cudaStreamWaitEvent(m->s_d2h, m->e_comp[sl], 0));
@@ -862,9 +892,9 @@ extern "C" int cvb_predict_host(cvb_model* m, const float* x, int64_t n, float* 
       if (logits16) CK(cudaMemcpyAsync(m->h_lg[sl], m->d_lg[sl], (size_t)cn * 64, cudaMemcpyDeviceToHost, m->s_d2h));
       CK(cudaEventRecord(m->e_d2h[sl], m->s_d2h));
     }
-    if (c >= 1) {
-      const int64_t p = c - 1;
-      const int sl = (int)(p & 1);
+    if (c >= LAG) {
+      const int64_t p = c - LAG;
+      const int sl = (int)(p % NS);
       const int64_t s0 = p * CHUNK, cn = std::min<int64_t>(CHUNK, n - s0);
       CK(cudaEventSynchronize(m->e_d2h[sl]));
       // de-interleave [base4 | zyg2 | type4 | len6] into the four arrays the reference's predict() returns

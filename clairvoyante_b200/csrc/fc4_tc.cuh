@@ -77,6 +77,10 @@ __global__ void k_prep_fc_weights(const float* __restrict__ w, int K, int N, con
 // ~1e2.  So K is cut into chunks of KCH: each chunk is accumulated FROM ZERO into one of two TMEM
 // buffers (ping-pong), and the epilogue warps add the finished chunk's partial sums into fp32
 // registers (round-to-nearest) while the tensor pipe works on the next chunk.
+// CL2 = true: clusters of 2 CTAs along the site-tile axis (same N-half): the pair shares the weight operand, each CTA
+// loads half of its rows per stage and TMA-multicasts them to both (this kernel is bound by operand ingest: 1.66 GB of
+// TMA traffic per 18,944-site launch, 58 % of it weights).  map_b_* then carry boxes of NH/2 rows.
+template <bool CL2>
 __global__ void __launch_bounds__(Fc4Tc::THREADS, 1)
 k_fc4_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, int64_t n, int K,
@@ -105,15 +109,17 @@ k_fc4_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
     tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
-    for (int s = 0; s < F::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < F::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL2 ? 2 : 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, F::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = CL2 ? cluster_ctarank() : 0;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -127,8 +133,16 @@ k_fc4_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ C
         const int k0 = kb * F::BK;
         tma_load_2d(st, &map_a_hi, &full[s], k0, (int)site0);
         tma_load_2d(st + F::A_BYTES, &map_a_lo, &full[s], k0, (int)site0);
-        tma_load_2d(st + 2 * F::A_BYTES, &map_b_hi, &full[s], k0, half * F::NH);  // rows >= 336 zero-fill
-        tma_load_2d(st + 2 * F::A_BYTES + F::B_BYTES, &map_b_lo, &full[s], k0, half * F::NH);
+        if (CL2) {
+          constexpr int HR = F::NH / 2;  // 88 rows = 11 swizzle atoms
+          tma_load_2d_mc(st + 2 * F::A_BYTES + crank * (HR * F::ROW_BYTES), &map_b_hi, &full[s], k0, half * F::NH + (int)crank * HR,
+                         (uint16_t)3);
+          tma_load_2d_mc(st + 2 * F::A_BYTES + F::B_BYTES + crank * (HR * F::ROW_BYTES), &map_b_lo, &full[s], k0,
+                         half * F::NH + (int)crank * HR, (uint16_t)3);
+        } else {
+          tma_load_2d(st + 2 * F::A_BYTES, &map_b_hi, &full[s], k0, half * F::NH);  // rows >= 336 zero-fill
+          tma_load_2d(st + 2 * F::A_BYTES + F::B_BYTES, &map_b_lo, &full[s], k0, half * F::NH);
+        }
       }
     }
   } else if (warp == 1) {
@@ -159,7 +173,8 @@ k_fc4_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ C
             umma_f16(tcol, dah, dbl, idesc, 1u);
             umma_f16(tcol, dah, dbh, idesc, 1u);
           }
-          umma_commit(&empty[s]);  // smem slot reusable once these MMAs have read it
+          if (CL2) umma_commit_mc(&empty[s], (uint16_t)3);  // the slot is refilled only when BOTH CTAs have read it
+          else umma_commit(&empty[s]);
         }
         umma_commit(&acc_full[buf]);
       }
@@ -216,6 +231,7 @@ k_fc4_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, F::TMEM_COLS);
