@@ -351,8 +351,9 @@ def main():
                                 sites_per_gpu_per_step=n, unique_sites=pool_n, parallelism="site-list sharding, no collective",
                                 l2="inputs (%.2f GB/GPU) exceed the 126 MB L2; no flush needed" % (n * 2112 / 1e9),
                                 weights="reference initialisers, seed 0",
-                                compute_mode=("fp32-equivalent: conv3+FC4 on tcgen05 with 3x split-fp16 operands and fp32 "
-                                              "accumulate, rest fp32 SIMT" if tensor else "fp32 SIMT")),
+                                compute_mode=(("fp32-equivalent: %s on tcgen05 with 3x split-fp16 operands and fp32 accumulate, "
+                                               "rest fp32 SIMT" % ("conv2+conv3+FC4+FC5/heads" if args.variant == "v3" else "conv3"))
+                                              if tensor else "fp32 SIMT")),
                     clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu, checksum=checksum)
         print(json.dumps(line))
     m.close()

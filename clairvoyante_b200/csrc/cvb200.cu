@@ -41,6 +41,8 @@ static int fail(const char* fmt, ...) {
   } while (0)
 
 extern "C" const char* cvb_last_error(void) { return g_err; }
+// for the host-only translation units of the library (text_feed.cpp)
+void cvb_internal_set_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
 extern "C" int cvb_version(void) { return 100; }
 
 // ------------------------------------------------------------------------------------
@@ -969,17 +971,36 @@ extern "C" int cvb_free_pinned(void* p) {
 }
 
 // ------------------------------------------------------------------------------------
-// loss / training (train_simt.cuh).  v3 only in this round; fp32 SIMT kernels.
+// loss / training (train_simt.cuh), fp32 SIMT kernels, both variants.
 // ------------------------------------------------------------------------------------
 static const int64_t TRAIN_CHUNK = 5120;  // sites per micro-chunk (activations + gradients ~180 KB/site)
 
 static int ensure_train_work(cvb_model* m) {
   if (m->train) return 0;
-  if (m->variant != CVB_V3) return fail("loss/training kernels are built for clairvoyante_v3 only in this round");
   TrainWork* w = new TrainWork();
   w->cap = TRAIN_CHUNK;
   const int64_t c = w->cap;
   struct Item { float** p; int64_t n; };
+  // v3_slim (clairvoyante_v3_slim.py:54-118): no pools, so the "pooled + padded" buffers are just the conv outputs moved
+  // into the next conv's zero-padded row layout (35 rows for KH=3, 37 for KH=5) and p3 is c3 itself
+  Item slim_items[] = {
+      {&w->x, c * 528}, {&w->y, c * 16}, {&w->c1, c * 33 * 32}, {&w->p1p, c * 35 * 32}, {&w->c2, c * 33 * 64},
+      {&w->p2p, c * 37 * 64}, {&w->c3, c * 33 * 128}, {&w->h4, c * 36}, {&w->d4, c * 36},
+      {&w->h5, c * 24}, {&w->logits, c * 16}, {&w->out16, c * 16}, {&w->dlog, c * 16}, {&w->g5, c * 24},
+      {&w->g4, c * 36}, {&w->g4b, c * 36}, {&w->gp3, c * 33 * 128}, {&w->g3p, c * 37 * 128}, {&w->gp2, c * 33 * 64},
+      {&w->g2p, c * 35 * 64}, {&w->gp1, c * 33 * 32}, {&w->g1, c * 33 * 32}, {&w->w3t, 5 * 4 * 32 * 16},
+      {&w->w2t, 3 * 4 * 16 * 8}, {&w->tmpb, 36 * 16}, {&w->tmph, 24 * 16}, {&w->loss, 16}};
+  if (m->variant != CVB_V3) {
+    int64_t total = 0;
+    for (auto& it : slim_items) total += (it.n + 63) / 64 * 64;
+    CK(cudaMalloc(&w->all, (size_t)total * 4));
+    CK(cudaMemset(w->all, 0, (size_t)total * 4));
+    int64_t off = 0;
+    for (auto& it : slim_items) { *it.p = w->all + off; off += (it.n + 63) / 64 * 64; }
+    w->p3 = w->c3;
+    m->train = w;
+    return 0;
+  }
   Item items[] = {
       {&w->x, c * 528}, {&w->y, c * 16}, {&w->c1, c * 33 * 64}, {&w->p1p, c * 30 * 64}, {&w->c2, c * 29 * 128},
       {&w->p2p, c * 28 * 128}, {&w->c3, c * 26 * 192}, {&w->p3, c * 24 * 192}, {&w->h4, c * 336}, {&w->d4, c * 336},
@@ -1001,7 +1022,119 @@ static int ensure_train_work(cvb_model* m) {
 static inline int gsz(int64_t total, int block = 256) { return (int)std::min<int64_t>((total + block - 1) / block, 148 * 16); }
 
 // training-mode forward of one micro-chunk already resident in tw->x: keeps every SELU output
+template <class C>
+static int launch_conv_keep(cvb_model* m, const float* in, int64_t nc, const float* wg, const float* bg, float* out, bool act,
+                            cudaStream_t st) {
+  using L = ConvLayerSmem<C, 1>;
+  const int grid = (int)std::min<int64_t>((nc + C::S - 1) / C::S, 2 * m->num_sms);
+  if (act) {
+    auto k = k_conv_layer<C, 1, 256, false, true>;
+    CK(set_smem(k, L::SMEM_BYTES));
+    k<<<grid, 256, L::SMEM_BYTES, st>>>(in, nc, wg, bg, out, nullptr);
+  } else {
+    auto k = k_conv_layer<C, 1, 256, false, false>;
+    CK(set_smem(k, L::SMEM_BYTES));
+    k<<<grid, 256, L::SMEM_BYTES, st>>>(in, nc, wg, bg, out, nullptr);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int train_forward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t seed, int64_t index0, cudaStream_t st) {
+  TrainWork* w = m->train;
+  if (launch_conv_keep<ConvCfg<4, 8, 1, 33, 12, 8, 8>>(m, w->x, nc, m->var("conv1/kernel"), m->var("conv1/bias"), w->c1, true, st)) return 1;
+  k_pool_fwd<1><<<gsz(nc * 33 * 8), 256, 0, st>>>(w->c1, nc, 33, 32, w->p1p, 35, 1);
+  if (launch_conv_keep<ConvCfg<8, 16, 3, 33, 6, 8, 8>>(m, w->p1p, nc, m->var("conv2/kernel"), m->var("conv2/bias"), w->c2, true, st)) return 1;
+  k_pool_fwd<1><<<gsz(nc * 33 * 16), 256, 0, st>>>(w->c2, nc, 33, 64, w->p2p, 37, 2);
+  if (launch_conv_keep<ConvCfg<16, 32, 5, 33, 3, 8, 8>>(m, w->p2p, nc, m->var("conv3/kernel"), m->var("conv3/bias"), w->c3, true, st)) return 1;
+  {
+    using F = FcCfg<36, 9, 4, 28, 8>;
+    auto k = k_fc4<F, true>;
+    CK(set_smem(k, F::SMEM_BYTES));
+    k<<<(int)((nc + F::M - 1) / F::M), 256, F::SMEM_BYTES, st>>>(w->c3, nc, 4224, m->var("fc4/kernel"), m->var("fc4/bias"), w->h4, 36, 36);
+    CK(cudaGetLastError());
+  }
+  const float* d4 = w->h4;
+  if (drop4 > 0.f) {
+    k_dropout_fwd<<<gsz(nc * 36), 256, 0, st>>>(w->h4, w->d4, nc * 36, index0, seed, drop_const(drop4));
+    d4 = w->d4;
+  }
+  k_dense_small<true><<<gsz(nc * 18), 256, 0, st>>>(d4, 36, 36, m->var("fc5/kernel"), 18, m->var("fc5/bias"), w->h5, 18, nc);
+  k_heads<36, 18><<<(int)((nc + 15) / 16), 256, 0, st>>>(d4, w->h5, nc, head_ptrs(m), w->out16, w->logits);
+  CK(cudaGetLastError());
+  m->launches += 8 + (drop4 > 0.f ? 1 : 0);
+  return 0;
+}
+
+static float* gvar(cvb_model* m, const char* name) { return m->d_grad + m->info(name)->offset; }
+
+static int train_backward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t seed, int64_t index0, cudaStream_t st) {
+  TrainWork* w = m->train;
+  const int sms = m->num_sms;
+  const float* d4 = drop4 > 0.f ? w->d4 : w->h4;
+  // heads
+  CK(cudaMemsetAsync(w->tmpb, 0, 36 * 16 * 4, st));
+  CK(cudaMemsetAsync(w->tmph, 0, 24 * 16 * 4, st));
+  k_gemm_tn<<<dim3(1, 1), 256, 0, st>>>(d4, 36, w->dlog, 16, w->tmpb, 16, 36, 16, nc);
+  k_gemm_tn<<<dim3(1, 1), 256, 0, st>>>(w->h5, 18, w->dlog, 16, w->tmph, 16, 18, 16, nc);
+  HeadG hg{gvar(m, "YBaseChangeSigmoid/kernel"), gvar(m, "YZygosityFC/kernel"), gvar(m, "YVarTypeFC/kernel"),
+           gvar(m, "YIndelLengthFC/kernel")};
+  k_scatter_heads<<<1, 256, 0, st>>>(w->tmpb, w->tmph, 36, 18, hg);
+  k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->dlog + 0, nc, 16, 4, gvar(m, "YBaseChangeSigmoid/bias"));
+  k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->dlog + 4, nc, 16, 2, gvar(m, "YZygosityFC/bias"));
+  k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->dlog + 6, nc, 16, 4, gvar(m, "YVarTypeFC/bias"));
+  k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->dlog + 10, nc, 16, 6, gvar(m, "YIndelLengthFC/bias"));
+  HeadW hw{m->var("YBaseChangeSigmoid/kernel"), m->var("YZygosityFC/kernel"), m->var("YVarTypeFC/kernel"),
+           m->var("YIndelLengthFC/kernel")};
+  k_heads_bwd<<<gsz(nc * (36 + 18)), 256, 0, st>>>(w->dlog, w->h5, nc, 36, 18, hw, w->g4, w->g5, 24);
+  // FC5
+  k_gemm_tn<<<dim3(1, 1), 256, 0, st>>>(d4, 36, w->g5, 24, gvar(m, "fc5/kernel"), 18, 36, 18, nc);
+  k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->g5, nc, 24, 18, gvar(m, "fc5/bias"));
+  k_dense_bwd_small<<<gsz(nc * 36), 256, 0, st>>>(w->g5, 24, 18, m->var("fc5/kernel"), 36, w->g4b, 36, nc);
+  k_fc4_bwd_elem<<<gsz(nc * 36), 256, 0, st>>>(w->g4, w->g4b, w->h4, nc * 36, index0, seed, drop_const(drop4), drop4 > 0.f ? 1 : 0);
+  // FC4
+  k_gemm_tn<<<dim3(4224 / 64, 1), 256, 0, st>>>(w->c3, 4224, w->g4, 36, gvar(m, "fc4/kernel"), 36, 4224, 36, nc);
+  k_colsum<<<dim3(2, 32), 256, 0, st>>>(w->g4, nc, 36, 36, gvar(m, "fc4/bias"));
+  k_dense_bwd_small<<<gsz(nc * 4224), 256, 0, st>>>(w->g4, 36, 36, m->var("fc4/kernel"), 4224, w->gp3, 4224, nc);
+  // conv3 (5x4, 16 -> 32)
+  k_pool_bwd_selu<1><<<gsz(nc * 33 * 128), 256, 0, st>>>(w->gp3, w->c3, nc, 33, 128, w->g3p, 37, 2);
+  {
+    using W = WgradCfg<16, 32, 5, 33, 4, 8, 4>;
+    auto k = k_conv_wgrad<16, 32, 5, 33, 4, 8, 4>;
+    CK(set_smem(k, W::SMEM_BYTES));
+    k<<<(int)std::min<int64_t>((nc + 3) / 4, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->p2p, w->g3p, 37, 2, nc, gvar(m, "conv3/kernel"));
+    CK(cudaGetLastError());
+    k_colsum<<<dim3(1, 128), 256, 0, st>>>(w->g3p, nc * 37 * 4, 32, 32, gvar(m, "conv3/bias"));
+    if (launch_conv_keep<ConvCfg<32, 16, 5, 33, 3, 8, 8, 2>>(m, w->g3p, nc, w->w3t, nullptr, w->gp2, false, st)) return 1;
+  }
+  // conv2 (3x4, 8 -> 16)
+  k_pool_bwd_selu<1><<<gsz(nc * 33 * 64), 256, 0, st>>>(w->gp2, w->c2, nc, 33, 64, w->g2p, 35, 1);
+  {
+    using W = WgradCfg<8, 16, 3, 33, 4, 4, 4>;
+    auto k = k_conv_wgrad<8, 16, 3, 33, 4, 4, 4>;
+    CK(set_smem(k, W::SMEM_BYTES));
+    k<<<(int)std::min<int64_t>((nc + 3) / 4, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->p1p, w->g2p, 35, 1, nc, gvar(m, "conv2/kernel"));
+    CK(cudaGetLastError());
+    k_colsum<<<dim3(1, 128), 256, 0, st>>>(w->g2p, nc * 35 * 4, 16, 16, gvar(m, "conv2/bias"));
+    if (launch_conv_keep<ConvCfg<16, 8, 3, 33, 6, 8, 8, 2>>(m, w->g2p, nc, w->w2t, nullptr, w->gp1, false, st)) return 1;
+  }
+  // conv1 (1x4, 4 -> 8)
+  k_pool_bwd_selu<1><<<gsz(nc * 33 * 32), 256, 0, st>>>(w->gp1, w->c1, nc, 33, 32, w->g1, 33, 0);
+  {
+    using W = WgradCfg<4, 8, 1, 33, 1, 4, 8>;
+    auto k = k_conv_wgrad<4, 8, 1, 33, 1, 4, 8>;
+    CK(set_smem(k, W::SMEM_BYTES));
+    k<<<(int)std::min<int64_t>((nc + 7) / 8, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->x, w->g1, 33, 0, nc, gvar(m, "conv1/kernel"));
+    CK(cudaGetLastError());
+    k_colsum<<<dim3(1, 128), 256, 0, st>>>(w->g1, nc * 33 * 4, 8, 8, gvar(m, "conv1/bias"));
+  }
+  CK(cudaGetLastError());
+  m->launches += 27;
+  return 0;
+}
+
 static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, int64_t index0, cudaStream_t st) {
+  if (m->variant != CVB_V3) return train_forward_slim(m, nc, drop4, seed, index0, st);
   TrainWork* w = m->train;
   const int sms = m->num_sms;
   {
@@ -1061,9 +1194,8 @@ static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, i
   return 0;
 }
 
-static float* gvar(cvb_model* m, const char* name) { return m->d_grad + m->info(name)->offset; }
-
 static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, int64_t index0, cudaStream_t st) {
+  if (m->variant != CVB_V3) return train_backward_slim(m, nc, drop4, seed, index0, st);
   TrainWork* w = m->train;
   const int sms = m->num_sms;
   const float* d4 = drop4 > 0.f ? w->d4 : w->h4;
@@ -1154,6 +1286,13 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
 
 static int train_prepare_weights(cvb_model* m, cudaStream_t st) {
   TrainWork* w = m->train;
+  if (m->variant != CVB_V3) {
+    k_flip_conv_weights<<<(5 * 4 * 16 * 32 + 255) / 256, 256, 0, st>>>(m->var("conv3/kernel"), 5, 16, 32, w->w3t);
+    k_flip_conv_weights<<<(3 * 4 * 8 * 16 + 255) / 256, 256, 0, st>>>(m->var("conv2/kernel"), 3, 8, 16, w->w2t);
+    CK(cudaGetLastError());
+    m->launches += 2;
+    return 0;
+  }
   k_flip_conv_weights<<<(3 * 4 * 32 * 48 + 255) / 256, 256, 0, st>>>(m->var("conv3/kernel"), 3, 32, 48, w->w3t);
   k_flip_conv_weights<<<(2 * 4 * 16 * 32 + 255) / 256, 256, 0, st>>>(m->var("conv2/kernel"), 2, 16, 32, w->w2t);
   k_transpose<<<dim3((336 + 31) / 32, 4608 / 32), dim3(32, 8), 0, st>>>(m->var("fc4/kernel"), 4608, 336, w->w4t);
@@ -1177,11 +1316,12 @@ static int train_pass(cvb_model* m, const float* x, const float* y, int64_t n, f
     const int64_t nc = std::min<int64_t>(w->cap, n - s0);
     CK(cudaMemcpyAsync(w->x, x + s0 * 528, (size_t)nc * 528 * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(w->y, y + s0 * 16, (size_t)nc * 16 * 4, cudaMemcpyHostToDevice, st));
-    if (train_forward(m, nc, drop4, seed, s0 * 336, st)) return 1;
+    const int64_t n4 = m->variant == CVB_V3 ? 336 : 36;  // dropout counter = flat index into the whole batch's FC4 output
+    if (train_forward(m, nc, drop4, seed, s0 * n4, st)) return 1;
     k_loss_grad<<<gsz(nc, 128), 128, 0, st>>>(w->logits, w->out16, w->y, nc, backward ? w->dlog : nullptr, w->loss);
     CK(cudaGetLastError());
     m->launches += 1;
-    if (backward && train_backward(m, nc, drop4, seed, s0 * 336, st)) return 1;
+    if (backward && train_backward(m, nc, drop4, seed, s0 * n4, st)) return 1;
   }
   return 0;
 }

@@ -1,0 +1,170 @@
+// text_feed.cpp -- native parser for the candidate-tensor text stream (host code, no CUDA).
+//
+// Replaces the per-row `row.split()` + `np.array(528 strings)` + channel subtract of the reference feed
+// (clairvoyante/utils_v2.py:29-47; row format `chrom pos refseq v0 .. v527`, values printed "%0.1f",
+// dataPrepScripts/CreateTensor.py:56).  SURVEY.md 8(f) rank 1: once the network runs at 10^7 sites/s the CPython
+// tokeniser (10^3..10^4 rows/s) is the wall of callVar.py.
+//
+// One call parses up to max_lines complete lines of a byte buffer:
+//   pass 1 (caller thread)  finds the line boundaries,
+//   pass 2 (worker threads) tokenises each line, converts the 528 values, subtracts channel 0 from channels 1..3
+//                           (utils_v2.py:46) and writes the row at its line index,
+//   pass 3 (caller thread)  compacts the kept rows to the front of x (drops are rare).
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <thread>
+#include <vector>
+
+#include "../../include/cvb200.h"
+
+void cvb_internal_set_error(const char* msg);  // cvb200.cu
+
+namespace {
+
+int fail(const char* msg) { cvb_internal_set_error(msg); return 1; }
+
+struct SpaceTable {
+  uint8_t t[256];
+  constexpr SpaceTable() : t() {
+    for (int i = 0; i < 256; ++i) t[i] = 0;
+    t[(int)' '] = t[(int)'\t'] = t[(int)'\r'] = t[(int)'\n'] = t[(int)'\v'] = t[(int)'\f'] = 1;
+    t[0x1c] = t[0x1d] = t[0x1e] = t[0x1f] = 1;  // str.split() also breaks on the ASCII separators
+  }
+};
+constexpr SpaceTable kSpace;
+inline bool is_space(char c) { return kSpace.t[(uint8_t)c] != 0; }
+
+// any token NumPy's string -> float32 conversion accepts (exponents, inf, nan ...): via double like NumPy
+bool parse_value_slow(const char* p, const char* e, float* out) {
+  char tmp[64];
+  const size_t n = (size_t)(e - p);
+  if (n == 0 || n >= sizeof(tmp)) return false;
+  memcpy(tmp, p, n);
+  tmp[n] = 0;
+  char* endp = nullptr;
+  const double v = strtod(tmp, &endp);
+  if (endp != tmp + n) return false;
+  *out = (float)v;
+  return true;
+}
+
+// One field starting at p (not a blank): returns the end of the token; *ok = false if it is not a number.
+// Fast path "[+-]digits[.digits]" with at most 15 significant digits: the integer numerator and the power of ten are
+// exact doubles, so the single division rounds like strtod; "%0.1f" rows of counts (".0") skip the division altogether.
+inline const char* parse_field(const char* p, const char* e, float* out, bool* ok) {
+  const char* q = p;
+  bool neg = false;
+  if (*q == '-' || *q == '+') { neg = *q == '-'; ++q; }
+  uint64_t ip = 0, fp = 0;
+  int nd = 0, nf = 0;
+  while (q < e && (unsigned)(*q - '0') < 10u && nd < 15) { ip = ip * 10 + (uint64_t)(*q - '0'); ++q; ++nd; }
+  if (q < e && *q == '.') {
+    ++q;
+    while (q < e && (unsigned)(*q - '0') < 10u && nd + nf < 15) { fp = fp * 10 + (uint64_t)(*q - '0'); ++q; ++nf; }
+  }
+  if ((q == e || is_space(*q)) && nd + nf > 0) {
+    static const double p10[16] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+    const double v = fp == 0 ? (double)ip : ((double)ip * p10[nf] + (double)fp) / p10[nf];
+    *out = (float)(neg ? -v : v);
+    return q;
+  }
+  while (q < e && !is_space(*q)) ++q;
+  if (!parse_value_slow(p, q, out)) *ok = false;
+  return q;
+}
+
+struct LineMeta {  // mirrors the int64[10] record documented in cvb200.h
+  int64_t status, line_off, line_len, chrom_off, chrom_len, pos_off, pos_len, seq_off, seq_len, reserved;
+};
+
+void parse_line(const char* buf, LineMeta* m, float* row) {
+  const char* p = buf + m->line_off;
+  const char* e = p + m->line_len;
+  const char* tokb[3];
+  const char* toke[3];
+  int nt = 0;
+  bool numbers_ok = true;
+  while (p < e) {
+    while (p < e && is_space(*p)) ++p;
+    if (p >= e) break;
+    if (nt < 3) {
+      tokb[nt] = p;
+      while (p < e && !is_space(*p)) ++p;
+      toke[nt] = p;
+    } else if (nt < 531) {
+      p = parse_field(p, e, row + (nt - 3), &numbers_ok);
+    } else {
+      while (p < e && !is_space(*p)) ++p;  // too many fields
+    }
+    ++nt;
+  }
+  const bool bad_number = !numbers_ok;
+  if (nt == 0) { m->status = CVB_LINE_BLANK; return; }
+  if (nt != 531) { m->status = CVB_LINE_MALFORMED; return; }
+  m->chrom_off = tokb[0] - buf; m->chrom_len = toke[0] - tokb[0];
+  m->pos_off = tokb[1] - buf;   m->pos_len = toke[1] - tokb[1];
+  m->seq_off = tokb[2] - buf;   m->seq_len = toke[2] - tokb[2];
+  if (m->seq_len <= 16) { m->status = CVB_LINE_MALFORMED; return; }
+  const char c = (char)(tokb[2][16] & ~0x20);  // ASCII upper-case of the centre reference base (utils_v2.py:38-39)
+  if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) { m->status = CVB_LINE_SKIPPED; return; }
+  if (bad_number) { m->status = CVB_LINE_MALFORMED; return; }
+  for (int i = 0; i < 528; i += 4) {  // utils_v2.py:46: channels 1..3 relative to the reference channel
+    const float r = row[i];
+    row[i + 1] -= r; row[i + 2] -= r; row[i + 3] -= r;
+  }
+  m->status = CVB_LINE_KEPT;
+}
+
+}  // namespace
+
+extern "C" int cvb_parse_tensor_text(const char* buf, int64_t len, int final_chunk, int64_t max_lines, int threads, float* x,
+                                     int64_t* meta, int64_t* lines, int64_t* kept, int64_t* consumed) {
+  if (!lines || !kept || !consumed) return fail("cvb_parse_tensor_text: NULL result pointer");
+  *lines = 0; *kept = 0; *consumed = 0;
+  if (len < 0 || max_lines < 0) return fail("cvb_parse_tensor_text: negative size");
+  if (len == 0 || max_lines == 0) return 0;
+  if (!buf || !x || !meta) return fail("cvb_parse_tensor_text: NULL buffer");
+  LineMeta* M = reinterpret_cast<LineMeta*>(meta);
+  int64_t n = 0, off = 0;
+  while (n < max_lines && off < len) {
+    const char* nl = static_cast<const char*>(memchr(buf + off, '\n', (size_t)(len - off)));
+    int64_t end;
+    if (nl) end = nl - buf;
+    else if (final_chunk) end = len;  // last line of the stream without a newline
+    else break;                       // incomplete line: the caller re-submits it with more data
+    memset(&M[n], 0, sizeof(LineMeta));
+    M[n].line_off = off;
+    M[n].line_len = end - off;
+    ++n;
+    off = nl ? end + 1 : end;
+  }
+  *lines = n;
+  *consumed = off;
+  if (n == 0) return 0;
+  int T = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(T, 64), n / 64));  // >= 64 lines (~170 KB) per thread
+  auto work = [&](int64_t a, int64_t b) {
+    for (int64_t i = a; i < b; ++i) parse_line(buf, &M[i], x + i * 528);
+  };
+  if (T == 1) {
+    work(0, n);
+  } else {
+    std::vector<std::thread> pool;
+    pool.reserve((size_t)T - 1);
+    const int64_t per = (n + T - 1) / T;
+    for (int t = 1; t < T; ++t) pool.emplace_back(work, std::min(n, t * per), std::min(n, (t + 1) * per));
+    work(0, std::min(n, per));
+    for (auto& th : pool) th.join();
+  }
+  int64_t k = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (M[i].status != CVB_LINE_KEPT) continue;
+    if (k != i) memcpy(x + k * 528, x + i * 528, 528 * sizeof(float));
+    ++k;
+  }
+  *kept = k;
+  return 0;
+}

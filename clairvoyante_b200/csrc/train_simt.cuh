@@ -197,9 +197,9 @@ k_gemm_tn(const float* __restrict__ A, int lda, const float* __restrict__ B, int
       if (k0 + r < K) {
         const float* pa = A + (k0 + r) * lda + m0 + q;
         const float* pb = B + (k0 + r) * ldb + n0 + q;
-        if (m0 + q + 3 < M) va = *reinterpret_cast<const float4*>(pa);
+        if (m0 + q + 3 < M && !(lda & 3)) va = *reinterpret_cast<const float4*>(pa);  // (v3_slim's h5 has lda = 18)
         else { float t[4] = {0, 0, 0, 0}; for (int e = 0; e < 4; ++e) if (m0 + q + e < M) t[e] = pa[e]; va = make_float4(t[0], t[1], t[2], t[3]); }
-        if (n0 + q + 3 < N) vb = *reinterpret_cast<const float4*>(pb);
+        if (n0 + q + 3 < N && !(ldb & 3)) vb = *reinterpret_cast<const float4*>(pb);
         else { float t[4] = {0, 0, 0, 0}; for (int e = 0; e < 4; ++e) if (n0 + q + e < N) t[e] = pb[e]; vb = make_float4(t[0], t[1], t[2], t[3]); }
       }
       *reinterpret_cast<float4*>(&As[r][q]) = va;
@@ -252,6 +252,37 @@ __global__ void k_scatter_heads(const float* __restrict__ tmpb, const float* __r
   if (i < N5 * 2) g.wz[i] += tmph[(i / 2) * 16 + 4 + (i % 2)];
   if (i < N5 * 4) g.wt[i] += tmph[(i / 4) * 16 + 6 + (i % 4)];
   if (i < N5 * 6) g.wl[i] += tmph[(i / 6) * 16 + 10 + (i % 6)];
+}
+
+// ---- tiny dense layers of v3_slim (36 / 18 units: K is not a multiple of k_fc4's 16-wide chunks and the work is <1 % of
+//      a step): one thread per output element.   out[s][o] = act(sum_k A[s][k] * W[k][o] + b[o])
+template <bool ACT>
+__global__ void k_dense_small(const float* __restrict__ A, int lda, int K, const float* __restrict__ W, int N,
+                              const float* __restrict__ bias, float* __restrict__ out, int ldo, int64_t n) {
+  const int64_t total = n * N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i / N;
+    const int o = (int)(i - s * N);
+    const float* a = A + s * lda;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf(a[k], W[k * N + o], acc);
+    if (bias) acc += bias[o];
+    out[s * ldo + o] = ACT ? selu_f(acc) : acc;
+  }
+}
+// ---- gradient w.r.t. the input of a dense layer, W in its forward [K][J] layout:  out[s][k] = sum_j G[s][j] * W[k][j]
+__global__ void k_dense_bwd_small(const float* __restrict__ G, int ldg, int J, const float* __restrict__ W, int K,
+                                  float* __restrict__ out, int ldo, int64_t n) {
+  const int64_t total = n * K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i / K;
+    const int k = (int)(i - s * K);
+    const float* g = G + s * ldg;
+    const float* w = W + (int64_t)k * J;
+    float acc = 0.f;
+    for (int j = 0; j < J; ++j) acc = fmaf(g[j], w[j], acc);
+    out[s * ldo + k] = acc;
+  }
 }
 
 // ---- out [C][R] = in [R][C]^T

@@ -16,6 +16,7 @@ Differences that are deliberate and documented:
     row's fields (utils_v2.py:34-41), silently duplicating a record.
 """
 import bisect
+import ctypes
 import gc
 import io
 import random
@@ -26,7 +27,7 @@ import zlib
 
 import numpy as np
 
-from . import param
+from . import _lib, param
 
 base2num = dict(zip("ACGT", (0, 1, 2, 3)))
 _ACGT = frozenset("ACGT")
@@ -67,44 +68,92 @@ def _subtract_reference_channel(x):
     return x
 
 
-def GetTensor(tensor_fn, num):
+def _open_bytes(fn):
+    """binary twin of _open_text for the native parser"""
+    if fn == "PIPE":
+        return None, sys.stdin.buffer
+    proc = subprocess.Popen(shlex.split("gzip -fdc %s" % fn), stdout=subprocess.PIPE, bufsize=1 << 20)
+    try:                                   # 1 MB pipe instead of 64 KB: fewer wake-ups per 32 MB read (Linux only)
+        import fcntl
+        fcntl.fcntl(proc.stdout.fileno(), getattr(fcntl, "F_SETPIPE_SZ", 1031), 1 << 20)
+    except (ImportError, OSError):
+        pass
+    return proc, proc.stdout
+
+
+_READ_BYTES = 32 << 20        # ~12k rows of ~2.7 KB per read
+
+
+def _native_rows(tensor_fn, num, threads=0):
+    """Drives cvb_parse_tensor_text (csrc/text_feed.cpp) over the stream.  Yields (rows, recs) with rows a fresh
+    float32 (k, 528) array (k <= num, channel 0 already subtracted, utils_v2.py:46) and recs the k
+    (chrom, pos, SEQ) string triples of those rows.  Every yield but the last has k == num."""
+    lib = _lib.load()
+    proc, fb = _open_bytes(tensor_fn)
+    width = _site_floats()
+    if width != 528:
+        raise NotImplementedError("the native parser is compiled for (33,4,4) tensors")
+    n_lines, n_kept, n_used = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+    buf, off, eof = b"", 0, False
+    rows = np.empty((num, width), dtype=np.float32)
+    meta = np.empty((max(num, 1), 10), dtype=np.int64)
+    recs, c = [], 0
+    while True:
+        base = ctypes.cast(ctypes.c_char_p(buf), ctypes.c_void_p).value or 0
+        _lib.check(lib.cvb_parse_tensor_text(base + off, len(buf) - off, 1 if eof else 0, num - c, threads,
+                                             rows[c:].ctypes.data, meta.ctypes.data,
+                                             ctypes.byref(n_lines), ctypes.byref(n_kept), ctypes.byref(n_used)))
+        nl = n_lines.value
+        if nl:
+            st = meta[:nl, 0]
+            for i in np.nonzero(st == 2)[0]:            # CVB_LINE_MALFORMED (reference message, utils_v2.py:35)
+                a, l = int(meta[i, 1]) + off, int(meta[i, 2])
+                print("UnpackATensorRecord Failure", buf[a:a + l].decode("ascii", "replace"), file=sys.stderr)
+            for i in np.nonzero(st == 0)[0]:            # CVB_LINE_KEPT
+                m = meta[i]
+                recs.append((buf[off + m[3]:off + m[3] + m[4]].decode("ascii", "replace"),
+                             buf[off + m[5]:off + m[5] + m[6]].decode("ascii", "replace"),
+                             buf[off + m[7]:off + m[7] + m[8]].decode("ascii", "replace").upper()))
+            c += n_kept.value
+            off += n_used.value
+        if c == num and num > 0:
+            yield rows, recs
+            rows = np.empty((num, width), dtype=np.float32)   # fresh storage: the consumer still holds the batch
+            recs, c = [], 0
+            continue
+        if nl == 0 or off >= len(buf):
+            if eof:
+                break
+            chunk = fb.read(_READ_BYTES)
+            if chunk:
+                buf, off = buf[off:] + chunk, 0
+            else:
+                eof = True                               # one more pass: a last line without '\n'
+    if proc is not None:
+        fb.close()
+        proc.wait()
+    yield rows[:c], recs
+
+
+def GetTensor(tensor_fn, num, threads=0):
     """Generator over batches of `num` candidate sites parsed from `chrom pos refseq33 v0..v527` rows
     (format: dataPrepScripts/CreateTensor.py:56).  Yields (0, num, X, pos) for full batches and finally
-    (1, c, X[:c], pos) with 0 <= c < num (possibly empty), X float32 (c,33,4,4), pos = 'chrom:pos:seq'."""
-    proc, fo = _open_text(tensor_fn)
-    width = _site_floats()
-    h, centre = 2 * param.flankingBaseNum + 1, param.flankingBaseNum
+    (1, c, X[:c], pos) with 0 <= c < num (possibly empty), X float32 (c,33,4,4), pos = 'chrom:pos:seq'.
+    Tokenising, number conversion and the channel subtract run in the C library (all host threads by default)."""
+    h = 2 * param.flankingBaseNum + 1
     total = 0
-    rows = np.empty((num, width), dtype=np.float32)
-    pos, c = [], 0
-    for row in fo:
-        f = row.split()
-        if len(f) != width + 3:
-            if f:
-                print("UnpackATensorRecord Failure", row, file=sys.stderr)
-            continue
-        seq = f[2].upper()
-        if seq[centre] not in _ACGT:          # TODO in the reference too: IUPAC codes (utils_v2.py:39)
-            continue
-        try:
-            rows[c] = np.array(f[3:], dtype=np.float32)
-        except ValueError:
-            print("UnpackATensorRecord Failure", row, file=sys.stderr)
-            continue
-        pos.append(f[0] + ":" + f[1] + ":" + seq)
-        c += 1
-        if c == num:
-            x = _subtract_reference_channel(rows.reshape(num, h, 4, param.matrixNum))
-            total += c
-            print("Processed %d tensors" % total, file=sys.stderr)
-            yield 0, c, x, pos
-            rows = np.empty((num, width), dtype=np.float32)   # fresh storage: the consumer still holds x
-            pos, c = [], 0
-    _close_text(proc, fo)
-    x = _subtract_reference_channel(rows[:c].reshape(c, h, 4, param.matrixNum))
-    total += c
+    it = _native_rows(tensor_fn, num, threads)
+    prev = next(it)
+    for cur in it:
+        rows, recs = prev
+        total += len(recs)
+        print("Processed %d tensors" % total, file=sys.stderr)
+        yield 0, len(recs), rows.reshape(-1, h, 4, param.matrixNum), [":".join(r) for r in recs]
+        prev = cur
+    rows, recs = prev
+    total += len(recs)
     print("Processed %d tensors" % total, file=sys.stderr)
-    yield 1, c, x, pos
+    yield 1, len(recs), rows.reshape(-1, h, 4, param.matrixNum), [":".join(r) for r in recs]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -202,29 +251,21 @@ def GetTrainingArray(tensor_fn, var_fn, bed_fn, shuffle=True):
 
     X = {}
     h, centre = 2 * param.flankingBaseNum + 1, param.flankingBaseNum
-    width = _site_floats()
-    proc, fh = _open_text(tensor_fn)
     total = 0
-    for row in fh:
-        f = row.split()
-        if len(f) != width + 3:
-            continue
-        chrom, coord, seq = f[0], f[1], f[2].upper()
-        if regions is not None and (chrom not in regions or not regions.hit(chrom, int(coord))):
-            continue
-        if seq[centre] not in _ACGT:
-            continue
-        key = chrom + ":" + coord
-        X[key] = _subtract_reference_channel(np.array(f[3:], dtype=np.float32).reshape(h, 4, param.matrixNum))
-        if key not in Y:                      # non-variant default label (utils_v2.py:141-148)
-            v = [0.0] * 16
-            v[base2num[seq[centre]]] = 1.0
-            v[5] = v[6] = v[10] = 1.0
-            Y[key] = v
-        total += 1
-        if total % 100000 == 0:
-            print("Processed %d tensors" % total, file=sys.stderr)
-    _close_text(proc, fh)
+    for rows, recs in _native_rows(tensor_fn, 4096):
+        for r, (chrom, coord, seq) in zip(rows.reshape(-1, h, 4, param.matrixNum), recs):
+            if regions is not None and (chrom not in regions or not regions.hit(chrom, int(coord))):
+                continue
+            key = chrom + ":" + coord
+            X[key] = r
+            if key not in Y:                      # non-variant default label (utils_v2.py:141-148)
+                v = [0.0] * 16
+                v[base2num[seq[centre]]] = 1.0
+                v[5] = v[6] = v[10] = 1.0
+                Y[key] = v
+            total += 1
+            if total % 100000 == 0:
+                print("Processed %d tensors" % total, file=sys.stderr)
 
     keys = sorted(X.keys())
     if shuffle:

@@ -101,6 +101,23 @@ int cvb_get_gradient(cvb_model* m, const char* name, float* host, int64_t n);
  * (possibly all-reduced) loss sums and the PRE-update weights, then the TF-1.x Adam update on every variable */
 int cvb_apply_adam(cvb_model* m, float lr, float l2, float* loss6);
 
+/* ---- batch feed: native parser of the candidate-tensor text stream -------------------------------------------------
+ * Replaces the per-row split()/np.array()/channel-subtract of utils_v2.GetTensor (clairvoyante/utils_v2.py:29-47) for
+ * rows `chrom pos refseq v0 .. v527` (dataPrepScripts/CreateTensor.py:56).  Host code; needs no GPU.
+ *
+ * Parses at most max_lines COMPLETE lines from buf[0,len).  A trailing line without '\n' is parsed only if
+ * final_chunk != 0, otherwise it is left for the next call (*consumed tells where to resume).
+ * Per line i (0 <= i < *lines) meta[i*10 ..] = {status, line_off, line_len, chrom_off, chrom_len, pos_off, pos_len,
+ * seq_off, seq_len, 0} (byte offsets into buf).  status: KEPT = 531 fields, all 528 values numeric, centre base
+ * refseq[16] in ACGT (utils_v2.py:39); SKIPPED = well-formed but centre base not ACGT; MALFORMED = wrong field count
+ * or a non-numeric value (the reference prints "UnpackATensorRecord Failure"); BLANK = whitespace only.
+ * The KEPT rows are written compacted to x[0 .. *kept) as 528 floats each, already with channels 1..3 made relative
+ * to channel 0 (utils_v2.py:46).  x must hold max_lines*528 floats, meta max_lines*10 int64.
+ * threads <= 0: use the hardware concurrency (capped at 64 and at one thread per 64 lines).                         */
+enum { CVB_LINE_KEPT = 0, CVB_LINE_SKIPPED = 1, CVB_LINE_MALFORMED = 2, CVB_LINE_BLANK = 3 };
+int cvb_parse_tensor_text(const char* buf, int64_t len, int final_chunk, int64_t max_lines, int threads, float* x,
+                          int64_t* meta, int64_t* lines, int64_t* kept, int64_t* consumed);
+
 /* pinned host memory helpers for the batch feed (utils_v2.GetTensor replacement) */
 int cvb_alloc_pinned(int64_t bytes, void** out);
 int cvb_free_pinned(void* p);

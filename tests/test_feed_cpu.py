@@ -47,6 +47,88 @@ def test_get_tensor_empty_final_batch(tmp_path):
     assert got[-1][2].shape == (0, 33, 4, 4) and got[-1][3] == []
 
 
+def _nasty_stream(n, seed):
+    """rows with everything the tokeniser must survive: tabs / runs of blanks / CRLF, lower-case and N centre bases,
+    blank lines, short and over-long rows, exponent / signed / integer / non-numeric tokens, no final newline"""
+    rng = np.random.RandomState(seed)
+    x = synth.make_sites(n, seed)
+    rows = _rows(x, chrom="chrX", start=5)
+    out = []
+    for i, r in enumerate(rows):
+        f = r.split(" ")
+        k = rng.randint(0, 12)
+        if k == 0:
+            f[2] = f[2].lower()
+        elif k == 1:
+            f[2] = f[2][:16] + "N" + f[2][17:]
+        elif k == 2:
+            f = f[:-3]                                  # too few fields
+        elif k == 3:
+            f = f + ["1.0"]                             # too many fields
+        elif k == 4:
+            f[3 + rng.randint(528)] = "abc"             # not a number
+        elif k == 5:
+            j = 3 + rng.randint(528)
+            f[j] = "%.3e" % float(f[j])                 # exponent form (strtod path)
+        elif k == 6:
+            j = 3 + rng.randint(528)
+            f[j] = "+" + f[j].lstrip("-")
+            f[j + 1 if j < 530 else j] = "7"            # bare integer
+        sep = ["\t", "  ", " "][rng.randint(3)]
+        line = sep.join(f)
+        if k == 7:
+            line = "  " + line + " \r"                  # leading blanks, CRLF
+        out.append(line)
+        if k == 8:
+            out.append("")                              # blank line
+        if k == 9:
+            out.append("   \t ")
+    return "\n".join(out)                               # NO trailing newline
+
+
+@pytest.mark.parametrize("seed,num,threads", [(1, 1000, 0), (2, 37, 1), (3, 64, 3), (4, 5000, 0)])
+def test_native_parser_matches_python_restatement(tmp_path, seed, num, threads, monkeypatch):
+    """csrc/text_feed.cpp (through utils_v2.GetTensor) vs the row-by-row restatement of utils_v2.py:23-59 on the same bytes;
+    small read size so that lines straddle read boundaries"""
+    from oracle import feed_oracle as FO
+    text = _nasty_stream(700 if seed != 4 else 3000, seed)
+    fn = str(tmp_path / "t.txt")
+    open(fn, "w").write(text)
+    monkeypatch.setattr(U, "_READ_BYTES", 50021)
+    got = list(U.GetTensor(fn, num, threads))
+    ref = list(FO.GetTensor(fn, num))
+    assert [(g[0], g[1]) for g in got] == [(r[0], r[1]) for r in ref]
+    for g, r in zip(got, ref):
+        assert g[2].dtype == np.float32 and g[2].shape == r[2].shape
+        assert np.array_equal(g[2], r[2])
+        assert g[3] == r[3]
+    assert sum(g[1] for g in got) > 300
+
+
+def test_native_parser_c_abi_edges():
+    """direct C-ABI calls: empty input, partial last line with and without final_chunk, max_lines cap"""
+    import ctypes
+    from clairvoyante_b200 import _lib
+    lib = _lib.load()
+    row = ("c 7 " + "ACGT" * 8 + "A " + " ".join(["2.0", "3.0", "2.0", "1.0"] * 132)).encode()
+    x = np.full((4, 528), -1, np.float32); meta = np.zeros((4, 10), np.int64)
+    nl, nk, nu = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+
+    def call(buf, final, cap):
+        _lib.check(lib.cvb_parse_tensor_text(buf, len(buf), final, cap, 1, x.ctypes.data, meta.ctypes.data,
+                                             ctypes.byref(nl), ctypes.byref(nk), ctypes.byref(nu)))
+        return nl.value, nk.value, nu.value
+    assert call(b"", 1, 4) == (0, 0, 0)
+    assert call(row, 0, 4) == (0, 0, 0)                          # incomplete line is left for the next call
+    assert call(row, 1, 4) == (1, 1, len(row))
+    assert np.array_equal(x[0, :4], [2.0, 1.0, 0.0, -1.0])       # channels 1..3 relative to channel 0
+    assert bytes(row[meta[0, 3]:meta[0, 3] + meta[0, 4]]) == b"c" and meta[0, 8] == 33
+    three = row + b"\n" + row + b"\n" + row + b"\n"
+    assert call(three, 0, 2) == (2, 2, 2 * (len(row) + 1))       # stops at max_lines, reports where to resume
+    assert lib.cvb_parse_tensor_text(None, 5, 0, 1, 1, None, None, ctypes.byref(nl), ctypes.byref(nk), ctypes.byref(nu)) != 0
+    assert b"NULL" in lib.cvb_last_error()
+
+
 def test_decompress_array_slicing():
     rng = np.random.default_rng(0)
     total = 1234

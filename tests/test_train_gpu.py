@@ -9,8 +9,15 @@ from oracle import cv_oracle as O, cv_oracle_torch as OT
 pytestmark = pytest.mark.gpu
 
 
-def _model(W, **kw):
-    from clairvoyante_b200 import clairvoyante_v3 as cv
+VARIANTS = ["v3", "v3_slim"]
+N4 = {"v3": 336, "v3_slim": 36}
+
+
+def _model(W, variant="v3", **kw):
+    if variant == "v3":
+        from clairvoyante_b200 import clairvoyante_v3 as cv
+    else:
+        from clairvoyante_b200 import clairvoyante_v3_slim as cv
     m = cv.Clairvoyante(**kw)
     m.setWeights(W)
     return m
@@ -20,14 +27,15 @@ def _relerr(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("n", [1, 7, 1000, 5121])
-def test_get_loss_matches_oracle(n):
-    W = I.init_weights("v3", 3)
+def test_get_loss_matches_oracle(variant, n):
+    W = I.init_weights(variant, 3)
     x, y = synth.make_sites(n, 4), synth.make_labels(n, 4)
-    m = _model(W)
+    m = _model(W, variant)
     got = float(m.getLoss(x, y))
     idx = slice(0, min(n, 1500))
-    ref = O.loss(W, x, y, "v3", 0.0)["loss"] if n <= 1500 else None
+    ref = O.loss(W, x, y, variant, 0.0)["loss"] if n <= 1500 else None
     if ref is not None:
         assert abs(got - ref) <= 2e-5 * abs(ref) + 1e-3
     else:  # additivity over micro-chunks (5120 sites): loss(all) == loss(a) + loss(b)
@@ -39,36 +47,38 @@ def test_get_loss_matches_oracle(n):
     m.close()
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("rate", [0.0, 0.5])
-def test_gradients_match_autograd(rate):
-    W = I.init_weights("v3", 5)
+def test_gradients_match_autograd(variant, rate):
+    W = I.init_weights(variant, 5)
     n = 300
     x, y = synth.make_sites(n, 6), synth.make_labels(n, 6)
-    m = _model(W, dropoutRateFC4=rate)
+    m = _model(W, variant, dropoutRateFC4=rate)
     seed = 0x1234ABCD
     loss, summary = m._train_step(x, y, apply_update=0, seed=seed)
     g = m.getGradients()
-    mask = dropout_rng.keep_mask(seed, n, rate) if rate > 0 else None
-    ref_loss, ref_g = OT.loss_and_grads(W, x, y, "v3", 0.0, drop4_rate=rate, drop4_mask=mask)
+    mask = dropout_rng.keep_mask(seed, n, rate, width=N4[variant]) if rate > 0 else None
+    ref_loss, ref_g = OT.loss_and_grads(W, x, y, variant, 0.0, drop4_rate=rate, drop4_mask=mask)
     for name in sorted(ref_g):
         assert _relerr(g[name], ref_g[name]) < 2e-3, name
     m.close()
 
 
-def test_train_step_loss_and_tf_adam_update():
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_train_step_loss_and_tf_adam_update(variant):
     """loss fetched is that of the pre-update weights incl. lambda*sum(0.5 w^2); update is TF-1.x Adam"""
-    W = I.init_weights("v3", 7)
+    W = I.init_weights(variant, 7)
     n = 256
     x, y = synth.make_sites(n, 8), synth.make_labels(n, 8)
     lam, lr = 1e-3, 1e-3
-    m = _model(W, dropoutRateFC4=0.0, l2RegularizationLambda=lam, initialLearningRate=lr)
+    m = _model(W, variant, dropoutRateFC4=0.0, l2RegularizationLambda=lam, initialLearningRate=lr)
     m.init(seed=1); m.setWeights(W)
     loss, summary = m.train(x, y)
-    ref = O.loss(W, x, y, "v3", lam)
+    ref = O.loss(W, x, y, variant, lam)
     assert abs(float(loss) - ref["loss"]) <= 3e-5 * abs(ref["loss"])
     for k in ("loss1", "loss2", "loss3", "loss4", "lossL2"):
         assert abs(summary[k] - ref[k]) <= 1e-4 * abs(ref[k]) + 1e-4, k
-    _, g = OT.loss_and_grads(W, x, y, "v3", lam)      # lambda inside the loss == g + lam*w
+    _, g = OT.loss_and_grads(W, x, y, variant, lam)      # lambda inside the loss == g + lam*w
     W1 = m.getWeights()
     for name in W:
         exp, _, _ = OT.tf_adam_step(W[name].astype(np.float64), g[name], 0.0, 0.0, 1, lr)
@@ -77,7 +87,7 @@ def test_train_step_loss_and_tf_adam_update():
         assert np.abs(W1[name] - exp)[big].max() < 0.05 * lr, name
     # second step: t = 2 with the stored slots (oracle gradients taken at the GPU's own W1)
     m1 = {k: 0.1 * g[k] for k in g}; v1 = {k: 0.001 * g[k] ** 2 for k in g}
-    _, g2 = OT.loss_and_grads(W1, x, y, "v3", lam)
+    _, g2 = OT.loss_and_grads(W1, x, y, variant, lam)
     m.train(x, y)
     W2 = m.getWeights()
     for name in W:
@@ -87,10 +97,11 @@ def test_train_step_loss_and_tf_adam_update():
     m.close()
 
 
-def test_training_reduces_loss_and_checkpoint_roundtrip(tmp_path):
-    W = I.init_weights("v3", 9)
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_training_reduces_loss_and_checkpoint_roundtrip(variant, tmp_path):
+    W = I.init_weights(variant, 9)
     x, y = synth.make_sites(2000, 10), synth.make_labels(2000, 10)
-    m = _model(W, initialLearningRate=1e-4)      # Adam moves every weight by ~lr per step: 1e-3 overshoots random weights
+    m = _model(W, variant, initialLearningRate=1e-4)      # Adam moves every weight by ~lr per step: 1e-3 overshoots random weights
     m.init(seed=2)
     l0 = float(m.getLoss(x, y))
     for _ in range(10):
@@ -99,19 +110,20 @@ def test_training_reduces_loss_and_checkpoint_roundtrip(tmp_path):
     assert l1 < l0
     fn = str(tmp_path / "ck" / "model-000001")
     m.saveParameters(fn)
-    m2 = _model(W)
+    m2 = _model(W, variant)
     m2.restoreParameters(fn)
     assert abs(float(m2.getLoss(x, y)) - l1) <= 1e-6 * abs(l1)
     a, b = m.train(x, y)[0], m2.train(x, y)[0]        # Adam slots + step restored -> identical next step (dropout differs: rate!=0)
     m.close(); m2.close()
 
 
-def test_data_parallel_halves_equal_full_batch():
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_data_parallel_halves_equal_full_batch(variant):
     """gradient of a batch == sum of the gradients of its shards (SUM loss): what the DP all-reduce relies on"""
-    W = I.init_weights("v3", 11)
+    W = I.init_weights(variant, 11)
     n = 400
     x, y = synth.make_sites(n, 12), synth.make_labels(n, 12)
-    m = _model(W, dropoutRateFC4=0.0)
+    m = _model(W, variant, dropoutRateFC4=0.0)
     m._train_step(x, y, apply_update=0, seed=1); full = m.getGradients()
     m._train_step(x[:150], y[:150], apply_update=0, seed=1); a = m.getGradients()
     m._train_step(x[150:], y[150:], apply_update=0, seed=1); b = m.getGradients()

@@ -1,7 +1,7 @@
 """First-light check on a GPU box: per-stage error of the CUDA forward against the oracle,
 plus a quick device-resident throughput number.  Not a test, not the bench."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from clairvoyante_b200 import initializers as I, synth

@@ -1,7 +1,7 @@
 """GPU probe for the tensor-core path: fp32 SIMT vs split-fp16 tcgen05 FC4 vs oracle, plus
 structured-weight cases that localise descriptor / swizzle mistakes.  Dumps to gpurun_out/."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from clairvoyante_b200 import initializers as I, synth, clairvoyante_v3 as cv
