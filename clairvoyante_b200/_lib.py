@@ -29,7 +29,8 @@ def build(force=False, verbose=False):
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB_PATH, os.path.join(CSRC, "cvb200.cu"), os.path.join(CSRC, "text_feed.cpp")]
+        ["-o", LIB_PATH, os.path.join(CSRC, "cvb200.cu")] + \
+        sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cpp"))
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr))
@@ -70,6 +71,7 @@ SIGNATURES = {
     "cvb_apply_adam": (ctypes.c_int, [c_vp, ctypes.c_float, ctypes.c_float, c_vp]),
     "cvb_parse_tensor_text": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, c_i64, ctypes.c_int, c_vp, c_vp,
                                              ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
+    "cvb_crc32c": (ctypes.c_uint32, [ctypes.c_uint32, c_vp, c_i64]),
     "cvb_alloc_pinned": (ctypes.c_int, [c_i64, ctypes.POINTER(c_vp)]),
     "cvb_free_pinned": (ctypes.c_int, [c_vp]),
     "cvb_debug_read": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_i64]),

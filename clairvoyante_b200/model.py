@@ -14,7 +14,7 @@ import os
 
 import numpy as np
 
-from . import _lib, initializers, param
+from . import _lib, tf_bundle, initializers, param
 
 _VARIANT_ID = {"v3": 0, "v3_slim": 1}
 COMPUTE_MODES = {"fp32": 0, "fp16x3": 1, "fp16": 2}
@@ -144,9 +144,12 @@ class ClairvoyanteBase(object):
         return fn + ".cvb.npz"
 
     def saveParameters(self, fn):
-        """tf.train.Saver().save (clairvoyante_v3.py:243-246).  Native container: one .npz
-        holding every variable under its TF name plus the Adam slots `<name>/Adam`,
-        `<name>/Adam_1` and `step` (TF stores beta1_power/beta2_power = beta**step)."""
+        """tf.train.Saver().save (clairvoyante_v3.py:243-246).  Writes two equivalent containers:
+          * `fn.index` + `fn.data-00000-of-00001`: a TensorFlow V2 checkpoint bundle (tf_bundle.py) with the names
+            tf.train.Saver() stores for this graph -- the 18 variables, their Adam slots `<name>/Adam`, `<name>/Adam_1`
+            and `beta1_power` / `beta2_power` (= beta**(step+1), TF-1.x AdamOptimizer) -- so the reference's
+            `restoreParameters` can load a model trained here;
+          * `fn.cvb.npz`: the same arrays plus the integer `step`."""
         d = {}
         for name, shape in initializers.variable_shapes(self.VARIANT):
             d[name] = self._get(name, 0, shape)
@@ -154,26 +157,49 @@ class ClairvoyanteBase(object):
             d[name + "/Adam_1"] = self._get(name, 2, shape)
         t = ctypes.c_int64()
         _lib.check(self._lib.cvb_get_step(self._h, ctypes.byref(t)))
-        d["step"] = np.int64(t.value)
         os.makedirs(os.path.dirname(os.path.abspath(fn)), exist_ok=True)
+        tf_bundle.write_bundle(fn, dict(d, beta1_power=np.float32(0.9 ** (t.value + 1)),
+                                        beta2_power=np.float32(0.999 ** (t.value + 1))))
+        d["step"] = np.int64(t.value)
         np.savez(self._ckpt_path(fn), **d)
 
+    def getStep(self):
+        """number of Adam updates applied so far (what TF keeps as beta1_power / beta2_power)"""
+        t = ctypes.c_int64()
+        _lib.check(self._lib.cvb_get_step(self._h, ctypes.byref(t)))
+        return int(t.value)
+
     def restoreParameters(self, fn):
-        """tf.train.Saver().restore (clairvoyante_v3.py:248-251)."""
-        path = None
-        for cand in (self._ckpt_path(fn), fn, fn + ".npz"):
-            if os.path.isfile(cand):
-                path = cand
-                break
-        if path is None:
-            raise IOError("checkpoint not found: %s(.cvb.npz)" % fn)
-        with np.load(path) as d:
-            for name, shape in initializers.variable_shapes(self.VARIANT):
-                self._set(name, 0, d[name].reshape(shape))
-                if name + "/Adam" in d:
-                    self._set(name, 1, d[name + "/Adam"].reshape(shape))
-                    self._set(name, 2, d[name + "/Adam_1"].reshape(shape))
-            _lib.check(self._lib.cvb_set_step(self._h, int(d["step"]) if "step" in d else 0))
+        """tf.train.Saver().restore (clairvoyante_v3.py:248-251): a TensorFlow V2 bundle prefix (the reference's
+        published `trainedModels`, or one written by saveParameters) or a `.cvb.npz`."""
+        if tf_bundle.is_bundle(fn):
+            d = tf_bundle.read_bundle(fn)
+            step = 0
+            if "beta2_power" in d:                        # beta2**(step+1); beta1_power underflows float32 after ~800 steps
+                b2 = float(np.asarray(d["beta2_power"]).reshape(-1)[0])
+                step = max(0, int(round(np.log(b2) / np.log(0.999))) - 1) if b2 > 0 else 1 << 20
+        else:
+            path = None
+            for cand in (self._ckpt_path(fn), fn, fn + ".npz"):
+                if os.path.isfile(cand):
+                    path = cand
+                    break
+            if path is None:
+                raise IOError("checkpoint not found: %s(.index | .cvb.npz)" % fn)
+            with np.load(path) as z:
+                d = {k: z[k] for k in z.files}
+            step = int(d["step"]) if "step" in d else 0
+        for name, shape in initializers.variable_shapes(self.VARIANT):
+            if name not in d:
+                raise KeyError("checkpoint %s has no variable %s" % (fn, name))
+            if int(np.prod(d[name].shape)) != int(np.prod(shape)):
+                raise ValueError("checkpoint %s: %s has shape %r, this model needs %r (wrong variant?)"
+                                 % (fn, name, d[name].shape, tuple(shape)))
+            self._set(name, 0, np.asarray(d[name], np.float32).reshape(shape))
+            if name + "/Adam" in d and name + "/Adam_1" in d:
+                self._set(name, 1, np.asarray(d[name + "/Adam"], np.float32).reshape(shape))
+                self._set(name, 2, np.asarray(d[name + "/Adam_1"], np.float32).reshape(shape))
+        _lib.check(self._lib.cvb_set_step(self._h, step))
 
     def summaryFileWriter(self, logsPath):
         return SummaryWriter(logsPath)

@@ -118,6 +118,10 @@ enum { CVB_LINE_KEPT = 0, CVB_LINE_SKIPPED = 1, CVB_LINE_MALFORMED = 2, CVB_LINE
 int cvb_parse_tensor_text(const char* buf, int64_t len, int final_chunk, int64_t max_lines, int threads, float* x,
                           int64_t* meta, int64_t* lines, int64_t* kept, int64_t* consumed);
 
+/* CRC-32C (Castagnoli) of data[0,n) continuing from `crc` (0 to start): the checksum TensorFlow's checkpoint bundles
+ * carry per tensor and per index block (tf.train.Saver, clairvoyante_v3.py:243-251).  Host code. */
+uint32_t cvb_crc32c(uint32_t crc, const void* data, int64_t n);
+
 /* pinned host memory helpers for the batch feed (utils_v2.GetTensor replacement) */
 int cvb_alloc_pinned(int64_t bytes, void** out);
 int cvb_free_pinned(void* p);

@@ -118,6 +118,44 @@ def test_training_reduces_loss_and_checkpoint_roundtrip(variant, tmp_path):
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
+def test_checkpoint_is_a_tensorflow_bundle(variant, tmp_path):
+    """saveParameters writes the tf.train.Saver layout (clairvoyante_v3.py:243-251): restoring from the bundle alone
+    brings back weights, Adam slots and the step; the .cvb.npz alone does the same"""
+    import os
+    from clairvoyante_b200 import tf_bundle
+    W = I.init_weights(variant, 4)
+    x, y = synth.make_sites(500, 3), synth.make_labels(500, 3)
+    m = _model(W, variant, initialLearningRate=1e-4, dropoutRateFC4=0.0)
+    m.init(seed=5); m.setWeights(W)
+    for _ in range(3):
+        m.train(x, y)
+    fn = str(tmp_path / "out" / "m-000003")
+    m.saveParameters(fn)
+    ent = tf_bundle.read_bundle(fn)
+    assert len(ent) == 18 * 3 + 2 and abs(float(ent["beta1_power"]) - 0.9 ** 4) < 1e-7
+    W3 = m.getWeights()
+    assert all(np.array_equal(ent[k], W3[k]) for k in W3)
+    la = m.train(x, y)[0]
+    for drop in (".cvb.npz", ".index"):                       # bundle only, then npz only
+        os.rename(fn + drop, fn + drop + ".bak")
+        m2 = _model(W, variant, initialLearningRate=1e-4, dropoutRateFC4=0.0)
+        m2.restoreParameters(fn)
+        assert m2.getStep() == 3
+        W2 = m2.getWeights()
+        assert all(np.array_equal(W2[k], W3[k]) for k in W3)
+        lb = m2.train(x, y)[0]
+        assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(la))
+        assert _relerr(m2.getWeights()["fc4/kernel"], m.getWeights()["fc4/kernel"]) < 1e-6   # same Adam slots -> same update
+        m2.close()
+        os.rename(fn + drop + ".bak", fn + drop)
+    other = "v3_slim" if variant == "v3" else "v3"
+    m3 = _model(I.init_weights(other, 0), other)
+    with pytest.raises(ValueError):
+        m3.restoreParameters(fn)                              # wrong variant: shapes differ
+    m3.close(); m.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_data_parallel_halves_equal_full_batch(variant):
     """gradient of a batch == sum of the gradients of its shards (SUM loss): what the DP all-reduce relies on"""
     W = I.init_weights(variant, 11)
