@@ -71,6 +71,9 @@ SIGNATURES = {
     "cvb_apply_adam": (ctypes.c_int, [c_vp, ctypes.c_float, ctypes.c_float, c_vp]),
     "cvb_parse_tensor_text": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, c_i64, ctypes.c_int, c_vp, c_vp,
                                              ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
+    "cvb_blosc_info": (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
+                                      ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "cvb_blosc_decompress": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, ctypes.POINTER(c_i64)]),
     "cvb_crc32c": (ctypes.c_uint32, [ctypes.c_uint32, c_vp, c_i64]),
     "cvb_alloc_pinned": (ctypes.c_int, [c_i64, ctypes.POINTER(c_vp)]),
     "cvb_free_pinned": (ctypes.c_int, [c_vp]),

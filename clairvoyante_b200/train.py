@@ -12,7 +12,6 @@ the same command line (train.py:225-259) and the same schedule:
 import argparse
 import logging
 import os
-import pickle
 import sys
 import time
 from threading import Thread
@@ -71,11 +70,7 @@ def _confusion(pred, truth, k):
 def TrainAll(args, m, utils):
     logging.info("Loading the training dataset ...")
     if args.bin_fn is not None:
-        with open(args.bin_fn, "rb") as fh:
-            total = pickle.load(fh)
-            XBlocks = pickle.load(fh)
-            YBlocks = pickle.load(fh)
-            posBlocks = pickle.load(fh)       # noqa: F841  (kept for format parity)
+        total, XBlocks, YBlocks, posBlocks = utils.load_bin(args.bin_fn)       # noqa: F841  (positions kept for format parity)
     else:
         total, XBlocks, YBlocks, posBlocks = utils.GetTrainingArray(args.tensor_fn, args.var_fn, args.bed_fn)
     logging.info("The size of training dataset: {}".format(total))

@@ -8,10 +8,11 @@ yield / return contracts:
   DecompressArray(blocks, start, num, maximum)    utils_v2.py:189-207 -> (array, num, endFlag)
 
 Differences that are deliberate and documented:
-  * python-blosc and intervaltree (requirements.txt:3-4) are not available; blocks are packed with
-    zlib + np.save (`pack_array` / `unpack_array`) and BED membership uses sorted arrays + bisect with the
-    same half-open [begin, end-1) semantics the reference builds (utils_v2.py:71-74).  A .bin written by the
-    reference (blosc frames) is rejected with a clear error; reading it is a "next" row.
+  * python-blosc and intervaltree (requirements.txt:3-4) are not available; blocks are WRITTEN with
+    zlib + np.save (`pack_array`) and BED membership uses sorted arrays + bisect with the same half-open
+    [begin, end-1) semantics the reference builds (utils_v2.py:71-74).  Blocks are READ from either container:
+    `unpack_array` also decodes the python-blosc LZ4HC frames of a .bin written by the reference
+    (csrc/blosc_frame.cpp).
   * a malformed row is reported and SKIPPED; the reference prints the failure and then re-uses the previous
     row's fields (utils_v2.py:34-41), silently duplicating a record.
 """
@@ -19,6 +20,7 @@ import bisect
 import ctypes
 import gc
 import io
+import pickle
 import random
 import shlex
 import subprocess
@@ -165,11 +167,60 @@ def pack_array(a):
     return _MAGIC + zlib.compress(buf.getvalue(), 1)
 
 
+class _RestrictedUnpickler(pickle.Unpickler):
+    """The reference unpickles its .bin blindly (train.py:41-44, blosc.unpack_array); only the globals a pickled
+    ndarray / list / int needs are resolved here."""
+    _ALLOWED = {("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+                ("numpy", "ndarray"), ("numpy", "dtype"), ("_codecs", "encode")}
+
+    def find_class(self, module, name):
+        if (module, name) not in self._ALLOWED:
+            raise pickle.UnpicklingError("refusing to load %s.%s from a tensor file" % (module, name))
+        if name == "_reconstruct":
+            return np._core.multiarray._reconstruct if hasattr(np, "_core") else np.core.multiarray._reconstruct
+        if module == "_codecs":
+            import codecs
+            return codecs.encode
+        return getattr(np, name)
+
+
+def _unpickle(data, encoding):
+    return _RestrictedUnpickler(io.BytesIO(data), encoding=encoding).load()
+
+
+def _blosc_unpack(b):
+    """blosc.unpack_array (utils_v2.py:198): Blosc-1 frame -> pickled ndarray (Python-2 pickles load with latin1)"""
+    lib = _lib.load()
+    nbytes = ctypes.c_int64()
+    _lib.check(lib.cvb_blosc_info(b, len(b), ctypes.byref(nbytes), None, None, None))
+    out = ctypes.create_string_buffer(max(1, nbytes.value))
+    got = ctypes.c_int64()
+    _lib.check(lib.cvb_blosc_decompress(b, len(b), out, nbytes.value, ctypes.byref(got)))
+    return _unpickle(out.raw[:got.value], "latin1")
+
+
 def unpack_array(b):
-    if not isinstance(b, (bytes, bytearray)) or bytes(b[:5]) != _MAGIC:
-        raise ValueError("not a clairvoyante_b200 block (a reference .bin holds python-blosc frames; "
-                         "re-create it with this repo's tensor2Bin.py)")
-    return np.load(io.BytesIO(zlib.decompress(bytes(b[5:]))), allow_pickle=False)
+    """one block of a .bin: this repo's container (pack_array) or a python-blosc frame written by the reference"""
+    if isinstance(b, str):                          # a Python-2 `str` that went through a latin1 unpickle
+        b = b.encode("latin1")
+    if not isinstance(b, (bytes, bytearray)):
+        raise ValueError("tensor block is not a byte string")
+    b = bytes(b)
+    if b[:5] == _MAGIC:
+        return np.load(io.BytesIO(zlib.decompress(b[5:])), allow_pickle=False)
+    if len(b) >= 16 and b[0] in (1, 2) and int.from_bytes(b[12:16], "little") == len(b):
+        return _blosc_unpack(b)
+    raise ValueError("not a tensor block: neither this repo's container nor a Blosc-1 frame")
+
+
+def load_bin(fn):
+    """train.py:40-44: four consecutive pickles (total, X blocks, Y blocks, position blocks); accepts files written by
+    this repo's tensor2Bin.py and by the reference's (Python 2, python-blosc frames)"""
+    with open(fn, "rb") as fh:
+        data = fh.read()
+    bio = io.BytesIO(data)
+    out = [_RestrictedUnpickler(bio, encoding="bytes").load() for _ in range(4)]
+    return int(out[0]), list(out[1]), list(out[2]), list(out[3])
 
 
 class _Regions(object):

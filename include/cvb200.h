@@ -122,6 +122,13 @@ int cvb_parse_tensor_text(const char* buf, int64_t len, int final_chunk, int64_t
  * carry per tensor and per index block (tf.train.Saver, clairvoyante_v3.py:243-251).  Host code. */
 uint32_t cvb_crc32c(uint32_t crc, const void* data, int64_t n);
 
+/* Blosc-1 frames with LZ4 / LZ4HC blocks: what `blosc.pack_array(a, cname='lz4hc')` produced for the reference's
+ * training set (clairvoyante/utils_v2.py:174-176) and `blosc.unpack_array` reads (:198,202).  Host code.
+ * cvb_blosc_info: uncompressed / compressed size, typesize and flag byte of a frame (any pointer may be NULL).
+ * cvb_blosc_decompress: frame -> dst[0, *out_n) (the pickled ndarray); byte-shuffle undone; other codecs are refused. */
+int cvb_blosc_info(const void* frame, int64_t n, int64_t* nbytes, int64_t* cbytes, int* typesize, int* flags);
+int cvb_blosc_decompress(const void* frame, int64_t n, void* dst, int64_t cap, int64_t* out_n);
+
 /* pinned host memory helpers for the batch feed (utils_v2.GetTensor replacement) */
 int cvb_alloc_pinned(int64_t bytes, void** out);
 int cvb_free_pinned(void* p);

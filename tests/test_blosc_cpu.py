@@ -1,0 +1,137 @@
+"""CPU: Blosc-1 / LZ4 frame decoder (csrc/blosc_frame.cpp) and the reference-format .bin loader
+(train.py:40-44, utils_v2.py:174-176,198).  Frames and Python-2 pickles are produced by the test-side encoder
+tests/blosc_writer.py (python-blosc is absent: parity unpinned against frames written by the real library)."""
+import ctypes
+import os
+import pickle
+import struct
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import blosc_writer as BW   # noqa: E402
+
+from clairvoyante_b200 import _lib, param, synth, utils_v2 as U   # noqa: E402
+
+
+def _decompress(frame):
+    lib = _lib.load()
+    n, c, ts, fl = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int(), ctypes.c_int()
+    _lib.check(lib.cvb_blosc_info(frame, len(frame), ctypes.byref(n), ctypes.byref(c), ctypes.byref(ts), ctypes.byref(fl)))
+    assert c.value == len(frame)
+    out = ctypes.create_string_buffer(max(1, n.value))
+    got = ctypes.c_int64()
+    _lib.check(lib.cvb_blosc_decompress(frame, len(frame), out, n.value, ctypes.byref(got)))
+    return out.raw[:got.value]
+
+
+def test_lz4_hand_vectors():
+    """LZ4 block format by hand: literals + match, overlapping match (run), length extension bytes"""
+    def frame(stream, nbytes):        # one block, one stream, no shuffle, typesize 1
+        return struct.pack("<BBBBIII", 2, 1, 1 << 5, 1, nbytes, nbytes, 16 + 4 + 4 + len(stream)) + struct.pack("<i", 20) + \
+            struct.pack("<i", len(stream)) + stream
+    s = bytes([0x44]) + b"abcd" + bytes([4, 0]) + bytes([0x50]) + b"vwxyz"           # "abcd" + copy 8 from -4 + "vwxyz"
+    assert _decompress(frame(s, 17)) == b"abcdabcdabcdvwxyz"
+    s = bytes([0x1F]) + b"a" + bytes([1, 0]) + bytes([255, 10]) + bytes([0x50]) + b"12345"   # run: 4+15+255+10 = 284 x 'a'
+    assert _decompress(frame(s, 1 + 284 + 5)) == b"a" * 285 + b"12345"
+    lit = bytes(range(256)) * 2
+    s = bytes([0xF0, 255, 512 - 15 - 255]) + lit                                     # 512 literals, no match
+    assert _decompress(frame(s, 512)) == lit
+    for bad in (bytes([0x44]) + b"abcd" + bytes([9, 0]) + bytes([0x50]) + b"vwxyz",  # offset before the start
+                bytes([0x44]) + b"abcd" + bytes([0, 0]) + bytes([0x50]) + b"vwxyz",  # offset 0
+                bytes([0x44]) + b"ab"):                                              # truncated literals
+        lib = _lib.load()
+        f = frame(bad, 17)
+        out = ctypes.create_string_buffer(32)
+        assert lib.cvb_blosc_decompress(f, len(f), out, 32, None) != 0
+        assert b"corrupt" in lib.cvb_last_error()
+
+
+@pytest.mark.parametrize("typesize,blocksize,kw", [
+    (4, 32768, {}),                                  # split into 4 streams per block, trailing partial block unsplit
+    (4, 1 << 20, {}),                                # single partial block
+    (8, 16384, {}),                                  # labels are float64 (utils_v2.py:175)
+    (4, 32768, dict(dont_split=True)),               # flag 0x10
+    (4, 32768, dict(do_shuffle=False)),
+    (40, 8192, {}),                                  # position strings: typesize > 16 -> never split, still shuffled
+    (4, 300, {}),                                    # blocksize / typesize < 128 -> not split
+    (4, 32768, dict(memcpyed=True)),
+])
+def test_frame_layouts_roundtrip(typesize, blocksize, kw):
+    rng = np.random.RandomState(typesize + blocksize)
+    data = (rng.poisson(2.0, 70001) * (rng.rand(70001) < 0.4)).astype(np.uint8).tobytes() + rng.bytes(3000)
+    f = BW.blosc_compress(data, typesize, blocksize, **kw)
+    assert _decompress(f) == data
+
+
+def test_incompressible_stream_is_stored_raw():
+    data = np.random.RandomState(1).bytes(4 * 128 * 64)
+    f = BW.blosc_compress(data, 4, 4 * 128 * 16)
+    assert _decompress(f) == data and len(f) <= len(data) + 16 + 4 * 4 + 4 * 16 + 64
+
+
+def test_rejects_other_codecs_and_truncation():
+    lib = _lib.load()
+    data = b"x" * 4096
+    f = bytearray(BW.blosc_compress(data, 1, 4096))
+    out = ctypes.create_string_buffer(4096)
+    g = bytes(f[:2]) + bytes([(f[2] & 0x1f) | (0 << 5)]) + bytes(f[3:])               # blosclz codec id
+    assert lib.cvb_blosc_decompress(g, len(g), out, 4096, None) != 0 and b"LZ4" in lib.cvb_last_error()
+    assert lib.cvb_blosc_decompress(bytes(f), len(f) - 3, out, 4096, None) != 0       # cbytes > buffer
+    assert lib.cvb_blosc_decompress(bytes(f), len(f), out, 100, None) != 0            # destination too small
+    assert lib.cvb_blosc_decompress(b"short", 5, out, 4096, None) != 0
+
+
+def test_unpack_array_python2_pickles():
+    x = synth.make_sites(500, 3)
+    y = synth.make_labels(500, 3).astype(np.float64)
+    pos = np.array(["chr%d:%d" % (i % 22 + 1, 10000 + i) for i in range(500)], dtype="S")
+    for a, ts in ((x, 4), (y, 8), (pos, pos.dtype.itemsize)):
+        frame = BW.blosc_compress(BW.py2_pickle_ndarray(a), ts, 65536)
+        b = U.unpack_array(frame)
+        assert b.dtype == a.dtype and b.shape == a.shape and np.array_equal(a, b)
+    # this repo's own container still loads, garbage is refused
+    assert np.array_equal(U.unpack_array(U.pack_array(x)), x)
+    with pytest.raises(ValueError):
+        U.unpack_array(b"\x02\x01" + b"\x00" * 30)
+
+
+def test_load_reference_style_bin_and_decompress(tmp_path):
+    """a .bin laid out like the reference's tensor2Bin.py output (Python-2 pickles of lists of blosc frames) feeds
+    DecompressArray exactly like this repo's own .bin"""
+    n, bs = 1234, param.bloscBlockSize
+    x = synth.make_sites(n, 5)
+    y = synth.make_labels(n, 5).astype(np.float64)
+    pos = np.array(["chr1:%d" % (5000 + i) for i in range(n)], dtype="S")
+    xb, yb, pb = [], [], []
+    for i in range(0, n, bs):
+        xb.append(BW.blosc_compress(BW.py2_pickle_ndarray(x[i:i + bs]), 4, 131072))
+        yb.append(BW.blosc_compress(BW.py2_pickle_ndarray(y[i:i + bs]), 8, 131072))
+        pb.append(BW.blosc_compress(BW.py2_pickle_ndarray(pos[i:i + bs]), pos.dtype.itemsize, 131072))
+    fn = str(tmp_path / "ref.bin")
+    with open(fn, "wb") as fh:
+        fh.write(BW.py2_pickle_int(n) + BW.py2_pickle_list_of_str(xb) + BW.py2_pickle_list_of_str(yb) + BW.py2_pickle_list_of_str(pb))
+    total, X, Y, P = U.load_bin(fn)
+    assert total == n and len(X) == len(xb) == 3
+    got, num, end = U.DecompressArray(X, 400, 700, total)
+    assert (num, end) == (700, 0) and np.array_equal(got, x[400:1100])
+    got, num, end = U.DecompressArray(Y, 1000, 500, total)
+    assert (num, end) == (234, 1) and np.array_equal(got, y[1000:])
+    # own writer -> same loader
+    fn2 = str(tmp_path / "own.bin")
+    with open(fn2, "wb") as fh:
+        for obj in (n, [U.pack_array(x[i:i + bs]) for i in range(0, n, bs)], [U.pack_array(y[i:i + bs]) for i in range(0, n, bs)],
+                    [U.pack_array(pos[i:i + bs]) for i in range(0, n, bs)]):
+            pickle.dump(obj, fh)
+    t2, X2, _, _ = U.load_bin(fn2)
+    assert t2 == n and np.array_equal(U.DecompressArray(X2, 0, n, n)[0], x)
+
+
+def test_bin_loader_refuses_arbitrary_globals(tmp_path):
+    fn = str(tmp_path / "evil.bin")
+    with open(fn, "wb") as fh:
+        fh.write(b"\x80\x02cos\nsystem\nU\x04trueq\x00\x85R.")
+    with pytest.raises(pickle.UnpicklingError):
+        U.load_bin(fn)
