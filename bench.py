@@ -332,8 +332,8 @@ def main():
     dt = max_over_ranks(dt)
     ne = ncalls * call_n
     e2e_value = world * ne * args.steps / dt
-    e2e = dict(value=e2e_value, unit="sites/s", h2d_bytes_per_step=ne * 528 * 4, d2h_bytes_per_step=ne * 16 * 4,
-               sites_per_step=ne, calls_per_step=ncalls, ms_per_step=dt / args.steps * 1e3,
+    e2e = dict(value=e2e_value, unit="sites/s", h2d_bytes_per_step=world * ne * 528 * 4, d2h_bytes_per_step=world * ne * 16 * 4,
+               sites_per_step=world * ne, sites_per_gpu_per_step=ne, calls_per_step=ncalls, ms_per_step=dt / args.steps * 1e3,
                api="Clairvoyante.predict(X) on pinned NumPy X, %d sites per call" % call_n)
 
     cpu = None
