@@ -336,6 +336,25 @@ def main():
                sites_per_step=world * ne, sites_per_gpu_per_step=ne, calls_per_step=ncalls, ms_per_step=dt / args.steps * 1e3,
                api="Clairvoyante.predict(X) on pinned NumPy X, %d sites per call" % call_n)
 
+    # the same step with the caller holding the count tensors as fp16 (BASELINE configs[2] "fp16 I/O"): half the H2D bytes,
+    # bit-identical outputs (tests/test_forward_gpu.py); reported beside e2e, not instead of it
+    xh16 = torch.empty((call_n, 33, 4, 4), dtype=torch.float16).pin_memory()
+    xh16_np = xh16.numpy()
+    xh16_np[...] = xh_np
+    del xh, xh_np
+    for _ in range(2):
+        m.predict(xh16_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _c in range(ncalls):
+            base, z, t, l = m.predict(xh16_np)
+    torch.cuda.synchronize()
+    dt16 = max_over_ranks(time.perf_counter() - t0)
+    e2e["fp16_input"] = dict(value=world * ne * args.steps / dt16, unit="sites/s", h2d_bytes_per_step=world * ne * 528 * 2,
+                             ms_per_step=dt16 / args.steps * 1e3, api="Clairvoyante.predict(X.astype(float16)), pinned")
+    del xh16, xh16_np
+
     cpu = None
     if rank == 0 and world == 1:
         v, cores, nsamp, thr = cpu_reference_rate(args.variant, W, args.cpu_seconds)

@@ -62,6 +62,7 @@ SIGNATURES = {
     "cvb_get_step": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64)]),
     "cvb_set_compute_mode": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "cvb_predict_host": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cvb_predict_host_f16": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cvb_predict_device": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "cvb_loss_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "cvb_train_step_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_float, ctypes.c_float,

@@ -72,6 +72,7 @@ struct cvb_model {
   // transfer after the host has seen D2H(c-1), so every host wake-up and de-interleave shows up as a PCIe bubble.
   static constexpr int NSLOT = 4;
   float *d_x[NSLOT] = {}, *d_out[NSLOT] = {}, *d_lg[NSLOT] = {};
+  __half* d_x16[NSLOT] = {};  // fp16 input slots (cvb_predict_host_f16)
   float *h_x[NSLOT] = {}, *h_out[NSLOT] = {}, *h_lg[NSLOT] = {};
   cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t e_h2d[NSLOT], e_comp[NSLOT], e_d2h[NSLOT];
@@ -220,7 +221,7 @@ extern "C" int cvb_destroy(cvb_model* m) {
   cudaFree(m->d_w3b_hi); cudaFree(m->d_p1); cudaFree(m->d_w2b_hi); cudaFree(m->d_h4s); cudaFree(m->d_wtail);
   cudaFree(m->d_w4t_hi); cudaFree(m->d_w4t_lo); cudaFree(m->d_absmax); cudaFree(m->d_inv_scale);
   for (int i = 0; i < cvb_model::NSLOT; ++i) {
-    cudaFree(m->d_x[i]); cudaFree(m->d_out[i]); cudaFree(m->d_lg[i]);
+    cudaFree(m->d_x[i]); cudaFree(m->d_x16[i]); cudaFree(m->d_out[i]); cudaFree(m->d_lg[i]);
     cudaFreeHost(m->h_x[i]); cudaFreeHost(m->h_out[i]); cudaFreeHost(m->h_lg[i]);
     if (m->events) { cudaEventDestroy(m->e_h2d[i]); cudaEventDestroy(m->e_comp[i]); cudaEventDestroy(m->e_d2h[i]); }
   }
@@ -612,6 +613,12 @@ static int launch_conv_tc(cvb_model* m, int64_t n, cudaStream_t st, const CUtens
   return 0;
 }
 
+// fp16 candidate tensors (counts are integers, |x| <= 250: exact in fp16) widened to the fp32 layout the front kernels read
+__global__ void k_half_to_float(const __half2* __restrict__ in, float2* __restrict__ out, int64_t n2) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __half22float2(in[i]);
+}
+
 static int prof_mark(cvb_model* m, cudaStream_t st) {
   if (!m->profiling) return 0;
   if (m->prof_used == m->prof_events.size()) {
@@ -831,6 +838,7 @@ static int ensure_host_slots(cvb_model* m) {
   const int64_t CHUNK = m->alloc_sites;  // large enough for every compute mode's chunk
   for (int i = 0; i < cvb_model::NSLOT; ++i) {
     CK(cudaMalloc(&m->d_x[i], (size_t)CHUNK * 528 * 4));
+    CK(cudaMalloc(&m->d_x16[i], (size_t)CHUNK * 528 * 2));
     CK(cudaMalloc(&m->d_out[i], (size_t)CHUNK * 16 * 4));
     CK(cudaMalloc(&m->d_lg[i], (size_t)CHUNK * 16 * 4));
     CK(cudaMallocHost(&m->h_x[i], (size_t)CHUNK * 528 * 4));
@@ -853,8 +861,22 @@ static void advise_hugepages(void* p, size_t bytes) {
   if (e > a) madvise((void*)a, e - a, MADV_HUGEPAGE);
 }
 
+static int predict_host_impl(cvb_model* m, const void* xv, bool half_in, int64_t n, float* base, float* zygosity, float* var_type,
+                             float* indel_length, float* logits16);
+
 extern "C" int cvb_predict_host(cvb_model* m, const float* x, int64_t n, float* base, float* zygosity, float* var_type,
                                 float* indel_length, float* logits16) {
+  return predict_host_impl(m, x, false, n, base, zygosity, var_type, indel_length, logits16);
+}
+extern "C" int cvb_predict_host_f16(cvb_model* m, const uint16_t* x, int64_t n, float* base, float* zygosity, float* var_type,
+                                    float* indel_length, float* logits16) {
+  return predict_host_impl(m, x, true, n, base, zygosity, var_type, indel_length, logits16);
+}
+
+static int predict_host_impl(cvb_model* m, const void* xv, bool half_in, int64_t n, float* base, float* zygosity, float* var_type,
+                             float* indel_length, float* logits16) {
+  const char* x = static_cast<const char*>(xv);
+  const size_t esz = half_in ? 2 : 4;
   if (!m) return fail("cvb_predict_host: NULL model");
   if (n < 0) return fail("cvb_predict_host: negative n");
   if (n == 0) return 0;
@@ -876,17 +898,24 @@ extern "C" int cvb_predict_host(cvb_model* m, const float* x, int64_t n, float* 
     if (c < nchunks) {
       const int sl = (int)(c % NS);
       const int64_t s0 = c * CHUNK, cn = std::min<int64_t>(CHUNK, n - s0);
-      const float* src = x + s0 * 528;
+      const char* src = x + (size_t)s0 * 528 * esz;
       if (!pinned_in) {
         if (c >= NS) CK(cudaEventSynchronize(m->e_h2d[sl]));  // staging buffer free again
-        memcpy(m->h_x[sl], src, (size_t)cn * 528 * 4);
-        src = m->h_x[sl];
+        memcpy(m->h_x[sl], src, (size_t)cn * 528 * esz);
+        src = reinterpret_cast<const char*>(m->h_x[sl]);
       }
-      if (c >= NS) CK(cudaStreamWaitEvent(m->s_h2d, m->e_comp[sl], 0));  // d_x[sl] consumed
-      CK(cudaMemcpyAsync(m->d_x[sl], src, (size_t)cn * 528 * 4, cudaMemcpyHostToDevice, m->s_h2d));
+      if (c >= NS) CK(cudaStreamWaitEvent(m->s_h2d, m->e_comp[sl], 0));  // d_x[sl] / d_x16[sl] consumed
+      CK(cudaMemcpyAsync(half_in ? (void*)m->d_x16[sl] : (void*)m->d_x[sl], src, (size_t)cn * 528 * esz, cudaMemcpyHostToDevice,
+                         m->s_h2d));
       CK(cudaEventRecord(m->e_h2d[sl], m->s_h2d));
       CK(cudaStreamWaitEvent(m->s_comp, m->e_h2d[sl], 0));
       if (c >= NS) CK(cudaStreamWaitEvent(m->s_comp, m->e_d2h[sl], 0));  // d_out[sl] drained
+      if (half_in) {
+        k_half_to_float<<<m->num_sms * 8, 256, 0, m->s_comp>>>(reinterpret_cast<const __half2*>(m->d_x16[sl]),
+                                                              reinterpret_cast<float2*>(m->d_x[sl]), cn * 264);
+        CK(cudaGetLastError());
+        m->launches += 1;
+      }
       if (forward_chunk(m, m->d_x[sl], cn, m->d_out[sl], logits16 ? m->d_lg[sl] : nullptr, m->s_comp)) return 1;
       CK(cudaEventRecord(m->e_comp[sl], m->s_comp));
       CK(cudaStreamWaitEvent(m->s_d2h, m->e_comp[sl], 0));

@@ -221,12 +221,20 @@ class ClairvoyanteBase(object):
 
     # ---- inference (clairvoyante_v3.py:257-280) --------------------------------------------
     def _predict(self, XArray, want_logits=False):
-        x, n = _f32c(XArray, self.inputShape)
+        half = isinstance(XArray, np.ndarray) and XArray.dtype == np.float16     # fp16 feed: half the PCIe bytes (cvb200.h)
+        if half:
+            x = np.ascontiguousarray(XArray)
+            n = x.shape[0] if x.ndim > 0 else 0
+            if x.size != n * int(np.prod(self.inputShape)):
+                raise ValueError("expected shape (N,33,4,4), got %s" % (x.shape,))
+        else:
+            x, n = _f32c(XArray, self.inputShape)
         base = np.empty((n, 4), np.float32); z = np.empty((n, 2), np.float32)
         t = np.empty((n, 4), np.float32); l = np.empty((n, 6), np.float32)
         lg = np.empty((n, 16), np.float32) if want_logits else None
-        _lib.check(self._lib.cvb_predict_host(self._h, x.ctypes.data, n, base.ctypes.data, z.ctypes.data, t.ctypes.data,
-                                              l.ctypes.data, lg.ctypes.data if want_logits else None))
+        fn = self._lib.cvb_predict_host_f16 if half else self._lib.cvb_predict_host
+        _lib.check(fn(self._h, x.ctypes.data, n, base.ctypes.data, z.ctypes.data, t.ctypes.data,
+                      l.ctypes.data, lg.ctypes.data if want_logits else None))
         return base, z, t, l, lg
 
     def predict(self, XArray):

@@ -72,6 +72,12 @@ int cvb_set_compute_mode(cvb_model* m, int mode);
  * in out16.                                                                      */
 int cvb_predict_host(cvb_model* m, const float* x, int64_t n, float* base /*n,4*/, float* zygosity /*n,2*/,
                      float* var_type /*n,4*/, float* indel_length /*n,6*/, float* logits16 /*n,16 or NULL*/);
+/* same call for candidate tensors the caller already holds as IEEE fp16 (`np.float16`, (n,33,4,4) C-contiguous): halves the
+ * host->device bytes, which is what bounds cvb_predict_host on a PCIe-attached B200.  Exact whenever the values are
+ * integers with |x| <= 2048 -- CreateTensor's counts are capped at 250 (dataPrepScripts/CreateTensor.py:296) -- because the
+ * first device step widens them to the fp32 layout of cvb_predict_host; results are then bit-identical to it. */
+int cvb_predict_host_f16(cvb_model* m, const uint16_t* x, int64_t n, float* base, float* zygosity, float* var_type,
+                         float* indel_length, float* logits16);
 /* same computation on DEVICE buffers (x, out16, logits16 are device pointers on the
  * handle's device); enqueued on `stream` (a cudaStream_t; NULL = the CUDA legacy default
  * stream, exactly as in the runtime API) and NOT synchronised.                                                  */

@@ -119,6 +119,34 @@ def test_multi_chunk_and_pinned_paths(variant, mode):
     m.close()
 
 
+@pytest.mark.parametrize("variant,mode", CASES)
+def test_fp16_input_is_bit_identical_for_count_tensors(variant, mode):
+    """cvb_predict_host_f16 (BASELINE config 3, "fp16 I/O"): CreateTensor counts are integers <= 250, exact in fp16, so the
+    half-width feed must reproduce the fp32 feed bit for bit -- pageable and pinned, across chunk boundaries, N = 0"""
+    import torch
+    W = I.init_weights(variant, 4)
+    n = 14208 * 2 + 333
+    x = synth.make_sites(n, 6)
+    x[5] *= 6.0                                     # depth-250 scale values
+    xh = x.astype(np.float16)
+    assert np.array_equal(xh.astype(np.float32), x)
+    m = _model(variant, W, mode)
+    o32, l32 = m.predictLogits(x)
+    o16, l16 = m.predictLogits(xh)
+    assert np.array_equal(o32, o16) and np.array_equal(l32, l16)
+    xp = torch.from_numpy(xh).pin_memory()
+    o16p, l16p = m.predictLogits(xp.numpy())
+    assert np.array_equal(o32, o16p) and np.array_equal(l32, l16p)
+    base, z, t, l = m.predict(xh[:0])
+    assert base.shape == (0, 4) and l.shape == (0, 6)
+    # non-integer input: defined as the fp32 path applied to the widened halves
+    y = (x[:500] * 0.37).astype(np.float16)
+    assert np.array_equal(m.predictLogits(y)[1], m.predictLogits(y.astype(np.float32))[1])
+    with pytest.raises(ValueError):
+        m.predict(np.zeros((3, 33, 4, 3), np.float16))
+    m.close()
+
+
 @pytest.mark.parametrize("mode", ["fp16x3", "fp32"])
 def test_extreme_inputs_v3(mode):
     """all-zero tensors, maximum depth (dcov cap 250, CreateTensor.py:296) and negative-heavy tensors"""
