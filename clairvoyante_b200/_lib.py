@@ -67,6 +67,7 @@ SIGNATURES = {
     "cvb_loss_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "cvb_train_step_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_float, ctypes.c_float,
                                            ctypes.c_float, ctypes.c_uint64, ctypes.c_int, c_vp]),
+    "cvb_set_train_mode": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "cvb_grad_buffer": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64)]),
     "cvb_get_gradient": (ctypes.c_int, [c_vp, ctypes.c_char_p, c_vp, c_i64]),
     "cvb_apply_adam": (ctypes.c_int, [c_vp, ctypes.c_float, ctypes.c_float, c_vp]),

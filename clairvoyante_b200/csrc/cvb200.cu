@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <sys/mman.h>
 #include "train_simt.cuh"
+#include "gemm_tc.cuh"
 
 using namespace cvb;
 
@@ -113,6 +114,7 @@ struct cvb_model {
   std::vector<cudaEvent_t> prof_events;  // 6 per chunk: start, after SIMT front, conv2(tc), conv3, fc4, tail
   size_t prof_used = 0;
   TrainWork* train = nullptr;
+  int train_mode = CVB_TRAIN_BF16X3;  // arithmetic of the FC4 contractions in a training step (v3)
   const float* var(const char* n) const {
     for (auto& v : vars)
       if (v.name == n) return d_params + v.offset;
@@ -551,6 +553,13 @@ extern "C" int cvb_set_compute_mode(cvb_model* m, int mode) {
   }
   m->compute_mode = mode;
   m->CHUNK = (int64_t)m->num_sms * (m->variant == CVB_V3 ? (mode == CVB_COMPUTE_FP32 ? 96 : 128) : 224);
+  return 0;
+}
+extern "C" int cvb_set_train_mode(cvb_model* m, int mode) {
+  if (!m) return fail("NULL model");
+  if (mode != CVB_TRAIN_FP32 && mode != CVB_TRAIN_BF16X3 && mode != CVB_TRAIN_BF16)
+    return fail("cvb_set_train_mode: unknown mode %d", mode);
+  m->train_mode = mode;
   return 0;
 }
 extern "C" int64_t cvb_kernel_launches(const cvb_model* m) { return m ? m->launches : 0; }
@@ -1044,11 +1053,62 @@ static int ensure_train_work(cvb_model* m) {
   CK(cudaMemset(w->all, 0, (size_t)total * 4));  // padding rows / columns of the padded layouts stay zero forever
   int64_t off = 0;
   for (auto& it : items) { *it.p = w->all + off; off += (it.n + 63) / 64 * 64; }
+  {
+    // split-bf16 operand copies for the tensor-core FC4 contractions: each buffer = hi plane followed by lo plane
+    w->ldt = c;
+    struct Item16 { uint16_t** p; int64_t n; };
+    Item16 it16[] = {{&w->p3s, 2 * c * 4608}, {&w->p3t, 2 * 4608 * c}, {&w->g4s, 2 * c * 336},
+                     {&w->g4t, 2 * 336 * c},  {&w->w4s, 2 * 4608 * 336}, {&w->w4ts, 2 * 336 * 4608}};
+    int64_t t16 = 0;
+    for (auto& it : it16) t16 += (it.n + 127) / 128 * 128;
+    CK(cudaMalloc(&w->all16, (size_t)t16 * 2));
+    CK(cudaMemset(w->all16, 0, (size_t)t16 * 2));
+    int64_t o16 = 0;
+    for (auto& it : it16) { *it.p = w->all16 + o16; o16 += (it.n + 127) / 128 * 128; }
+  }
   m->train = w;
   return 0;
 }
 
 static inline int gsz(int64_t total, int block = 256) { return (int)std::min<int64_t>((total + block - 1) / block, 148 * 16); }
+
+
+// ---- tensor-core FC4 contractions of the training path (gemm_tc.cuh) ------------------------------------------------
+// C[M][N] (op)= A[M][K] . B[N][K]^T ; a / b point at the hi plane, the lo plane follows `a_plane` / `b_plane` elements later;
+// lda / ldb = row pitch in elements (multiple of 8: TMA strides are 16-byte granular)
+template <int BN, bool CHUNKED, int EPI>
+static int launch_gemm_tc(cvb_model* m, const uint16_t* a, int64_t a_plane, int64_t lda, const uint16_t* b, int64_t b_plane,
+                          int64_t ldb, int M, int N, int K, float* C, int64_t ldc, const float* bias, cudaStream_t st) {
+  using G = tc::GemmTc<BN>;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  const uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, db[2] = {(uint64_t)K, (uint64_t)N};
+  const uint64_t sa[1] = {(uint64_t)lda * 2}, sb[1] = {(uint64_t)ldb * 2};
+  const uint32_t ba[2] = {(uint32_t)G::BK, (uint32_t)G::BM}, bb[2] = {(uint32_t)G::BK, (uint32_t)BN};
+  if (make_map_nd(&ma_hi, (void*)a, 2, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  if (make_map_nd(&ma_lo, (void*)(a + a_plane), 2, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  if (make_map_nd(&mb_hi, (void*)b, 2, db, sb, bb, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  if (make_map_nd(&mb_lo, (void*)(b + b_plane), 2, db, sb, bb, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  auto k = tc::k_gemm_tc<BN, CHUNKED, EPI>;
+  CK(set_smem(k, G::SMEM_BYTES));
+  const dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + G::BM - 1) / G::BM));
+  k<<<grid, G::THREADS, G::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K, m->train_mode == CVB_TRAIN_BF16 ? 1 : 3, C, ldc,
+                                            bias);
+  CK(cudaGetLastError());
+  return 0;
+}
+static inline __nv_bfloat16* bf(uint16_t* p) { return reinterpret_cast<__nv_bfloat16*>(p); }
+static int split_rows_bf16(const float* src, int64_t rows, int cols, uint16_t* dst, int64_t plane, cudaStream_t st) {
+  tc::k_split_bf16<<<gsz(rows * (cols / 4)), 256, 0, st>>>(src, rows, cols, cols, bf(dst), bf(dst + plane), cols);
+  CK(cudaGetLastError());
+  return 0;
+}
+static int split_transpose_bf16(const float* src, int64_t R, int C, uint16_t* dst, int64_t plane, int64_t ld_dst, cudaStream_t st) {
+  if (R <= 0) return 0;
+  tc::k_split_transpose_bf16<<<dim3((unsigned)((C + 31) / 32), (unsigned)((R + 63) / 64)), dim3(32, 8), 0, st>>>(
+      src, R, C, C, bf(dst), bf(dst + plane), ld_dst);
+  CK(cudaGetLastError());
+  return 0;
+}
 
 // training-mode forward of one micro-chunk already resident in tw->x: keeps every SELU output
 template <class C>
@@ -1196,7 +1256,14 @@ static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, i
     CK(cudaGetLastError());
     k_pool_fwd<3><<<gsz(nc * 24 * 48), 256, 0, st>>>(w->c3, nc, 26, 192, w->p3, 24, 0);
   }
-  {
+  if (m->train_mode != CVB_TRAIN_FP32) {
+    // FC4 on tcgen05: p3 -> split bf16 (K-major), B = W4^T prepared once per step (train_prepare_weights)
+    if (split_rows_bf16(w->p3, nc, 4608, w->p3s, w->cap * 4608, st)) return 1;
+    if (launch_gemm_tc<176, true, tc::GEMM_EPI_BIAS_SELU>(m, w->p3s, w->cap * 4608, 4608, w->w4ts, 336 * 4608, 4608, (int)nc, 336,
+                                                          4608, w->h4, 336, m->var("fc4/bias"), st))
+      return 1;
+    m->launches += 1;
+  } else {
     using F = FcCfg<336, 21, 16, 12, 8>;
     auto k = k_fc4<F, true>;
     CK(set_smem(k, F::SMEM_BYTES));
@@ -1256,9 +1323,22 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
   }
   k_fc4_bwd_elem<<<gsz(nc * 336), 256, 0, st>>>(w->g4, w->g4b, w->h4, nc * 336, index0, seed, drop_const(drop4), drop4 > 0.f ? 1 : 0);
   // FC4
-  k_gemm_tn<<<dim3(4608 / 64, (336 + 63) / 64), 256, 0, st>>>(w->p3, 4608, w->g4, 336, gvar(m, "fc4/kernel"), 336, 4608, 336, nc);
   k_colsum<<<dim3((336 + 31) / 32, 32), 256, 0, st>>>(w->g4, nc, 336, 336, gvar(m, "fc4/bias"));
-  {
+  if (m->train_mode != CVB_TRAIN_FP32) {
+    // weight gradient  dW4 [4608][336] += p3^T . dpre4   (K = sites: both operands transposed into K-major planes)
+    if (split_transpose_bf16(w->p3, nc, 4608, w->p3t, 4608 * w->ldt, w->ldt, st)) return 1;
+    if (split_transpose_bf16(w->g4, nc, 336, w->g4t, 336 * w->ldt, w->ldt, st)) return 1;
+    if (launch_gemm_tc<176, true, tc::GEMM_EPI_ACCUM>(m, w->p3t, 4608 * w->ldt, w->ldt, w->g4t, 336 * w->ldt, w->ldt, 4608, 336,
+                                                      (int)nc, gvar(m, "fc4/kernel"), 336, nullptr, st))
+      return 1;
+    // data gradient  gp3 [sites][4608] = dpre4 . W4^T      (B = W4 as stored: [4608][336] is K-major for K = 336)
+    if (split_rows_bf16(w->g4, nc, 336, w->g4s, w->cap * 336, st)) return 1;
+    if (launch_gemm_tc<192, false, tc::GEMM_EPI_STORE>(m, w->g4s, w->cap * 336, 336, w->w4s, 4608 * 336, 336, (int)nc, 4608, 336,
+                                                       w->gp3, 4608, nullptr, st))
+      return 1;
+    m->launches += 3;
+  } else {
+    k_gemm_tn<<<dim3(4608 / 64, (336 + 63) / 64), 256, 0, st>>>(w->p3, 4608, w->g4, 336, gvar(m, "fc4/kernel"), 336, 4608, 336, nc);
     using F = FcCfg<192, 24, 8, 10, 8>;
     auto k = k_fc4<F, false>;
     CK(set_smem(k, F::SMEM_BYTES));
@@ -1313,21 +1393,30 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
   return 0;
 }
 
-static int train_prepare_weights(cvb_model* m, cudaStream_t st) {
+static int train_prepare_weights(cvb_model* m, cudaStream_t st, bool backward) {
   TrainWork* w = m->train;
   if (m->variant != CVB_V3) {
+    if (!backward) return 0;
     k_flip_conv_weights<<<(5 * 4 * 16 * 32 + 255) / 256, 256, 0, st>>>(m->var("conv3/kernel"), 5, 16, 32, w->w3t);
     k_flip_conv_weights<<<(3 * 4 * 8 * 16 + 255) / 256, 256, 0, st>>>(m->var("conv2/kernel"), 3, 8, 16, w->w2t);
     CK(cudaGetLastError());
     m->launches += 2;
     return 0;
   }
+  if (m->train_mode != CVB_TRAIN_FP32) {  // the forward pass (getLoss included) reads W4^T, the data gradient W4
+    if (split_transpose_bf16(m->var("fc4/kernel"), 4608, 336, w->w4ts, 336 * 4608, 4608, st)) return 1;
+    if (backward && split_rows_bf16(m->var("fc4/kernel"), 4608, 336, w->w4s, 4608 * 336, st)) return 1;
+    m->launches += backward ? 2 : 1;
+  } else if (backward) {
+    k_transpose<<<dim3((336 + 31) / 32, 4608 / 32), dim3(32, 8), 0, st>>>(m->var("fc4/kernel"), 4608, 336, w->w4t);
+    m->launches += 1;
+  }
+  if (!backward) return 0;
   k_flip_conv_weights<<<(3 * 4 * 32 * 48 + 255) / 256, 256, 0, st>>>(m->var("conv3/kernel"), 3, 32, 48, w->w3t);
   k_flip_conv_weights<<<(2 * 4 * 16 * 32 + 255) / 256, 256, 0, st>>>(m->var("conv2/kernel"), 2, 16, 32, w->w2t);
-  k_transpose<<<dim3((336 + 31) / 32, 4608 / 32), dim3(32, 8), 0, st>>>(m->var("fc4/kernel"), 4608, 336, w->w4t);
   k_transpose<<<dim3((168 + 31) / 32, (336 + 31) / 32), dim3(32, 8), 0, st>>>(m->var("fc5/kernel"), 336, 168, w->w5t);
   CK(cudaGetLastError());
-  m->launches += 4;
+  m->launches += 3;
   return 0;
 }
 
@@ -1337,10 +1426,8 @@ static int train_pass(cvb_model* m, const float* x, const float* y, int64_t n, f
   TrainWork* w = m->train;
   cudaStream_t st = m->s_comp;
   CK(cudaMemsetAsync(w->loss, 0, 16 * 4, st));
-  if (backward) {
-    CK(cudaMemsetAsync(m->d_grad, 0, (size_t)(m->nparams + 16) * 4, st));
-    if (train_prepare_weights(m, st)) return 1;
-  }
+  if (backward) CK(cudaMemsetAsync(m->d_grad, 0, (size_t)(m->nparams + 16) * 4, st));
+  if (train_prepare_weights(m, st, backward)) return 1;
   for (int64_t s0 = 0; s0 < n; s0 += w->cap) {
     const int64_t nc = std::min<int64_t>(w->cap, n - s0);
     CK(cudaMemcpyAsync(w->x, x + s0 * 528, (size_t)nc * 528 * 4, cudaMemcpyHostToDevice, st));

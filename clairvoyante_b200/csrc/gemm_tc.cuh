@@ -1,0 +1,262 @@
+// gemm_tc.cuh -- the three dense contractions of a training step's FC4 layer on tcgen05
+// (clairvoyante_v3.py:104-108 forward; its two gradients come from training_op, :174):
+//     forward   h4  = SELU(p3 @ W4 + b4)        M = sites, N = 336,  K = 4608
+//     dgrad     gp3 = dpre4 @ W4^T              M = sites, N = 4608, K = 336
+//     wgrad     dW4 += p3^T @ dpre4             M = 4608,  N = 336,  K = sites
+// as ONE kernel:  C[M][N] (op)= A[M][K] . B[N][K]^T  with both operands K-major bf16 in HBM, split as
+// x = hi + lo (two bf16, ~16 mantissa bits, fp32's exponent range so gradients need no scaling):
+//     A B^T ~= A_lo B_hi + A_hi B_lo + A_hi B_hi      (terms = 3; terms = 1 keeps only the last = plain bf16)
+// fp32 accumulation in TMEM.  Layout of a CTA as in fc4_tc.cuh: 192 threads = TMA producer warp, MMA issuer
+// warp, 4 epilogue warps (one output row per thread); 4-stage ring of {A_hi, A_lo 128 x 64 B, B_hi, B_lo BN x 64 B},
+// 64-byte swizzle.  CHUNKED: K is accumulated from zero in chunks of 256 into ping-pong TMEM buffers and the
+// chunk partials are added in fp32 registers (tcgen05 accumulation truncates; see fc4_tc.cuh).
+// Rows / columns / K beyond the tensor edges are zero-filled by TMA and masked in the epilogue.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "tc_common.cuh"
+
+namespace cvb {
+namespace tc {
+
+enum { GEMM_EPI_STORE = 0, GEMM_EPI_BIAS_SELU = 1, GEMM_EPI_ACCUM = 2 };
+
+template <int BN_>
+struct GemmTc {
+  static constexpr int BM = 128, BN = BN_, BK = 32, STAGES = 4, KCH_BLOCKS = 8;
+  static constexpr int ROW_BYTES = BK * 2;
+  static constexpr int A_BYTES = BM * ROW_BYTES;
+  static constexpr int B_BYTES = BN * ROW_BYTES;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int THREADS = 192;
+  static constexpr int TMEM_COLS = 512;  // two accumulator buffers at columns 0 and 256
+  static constexpr uint32_t SBO = 8 * ROW_BYTES;
+  static constexpr uint32_t LAYOUT = 4;  // SWIZZLE_64B
+  static_assert(BN % 16 == 0 && BN <= 256 && BN >= 16, "UMMA N for M = 128");
+  static_assert(B_BYTES % 512 == 0, "operand tiles start on a swizzle atom");
+};
+
+// kind::f16 instruction descriptor with bf16 A/B (a_format = b_format = 1), fp32 accumulate
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) { return umma_idesc_f16(M, N) | (1u << 7) | (1u << 10); }
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// src fp32 [rows][cols] (row pitch ld_src) -> hi, lo bf16 [rows][ld_dst].   cols % 4 == 0
+__global__ void k_split_bf16(const float* __restrict__ src, int64_t rows, int cols, int64_t ld_src, __nv_bfloat16* __restrict__ hi,
+                             __nv_bfloat16* __restrict__ lo, int64_t ld_dst) {
+  const int c4 = cols >> 2;
+  const int64_t total = rows * c4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c4;
+    const int q = (int)(i - r * c4);
+    const float4 v = *reinterpret_cast<const float4*>(src + r * ld_src + q * 4);
+    __nv_bfloat16 h[4], l[4];
+    split_bf16(v.x, h[0], l[0]);
+    split_bf16(v.y, h[1], l[1]);
+    split_bf16(v.z, h[2], l[2]);
+    split_bf16(v.w, h[3], l[3]);
+    *reinterpret_cast<uint2*>(hi + r * ld_dst + q * 4) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + r * ld_dst + q * 4) = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
+// src fp32 [R][C] (row pitch ld_src) -> hi, lo bf16 [C][ld_dst] = the transpose (ld_dst even, >= R rounded up to 2).
+// grid (ceil(C/32), ceil(R/64)), block (32, 8): 64 x 32 tile through shared memory, paired bf16 stores.
+__global__ void k_split_transpose_bf16(const float* __restrict__ src, int64_t R, int C, int64_t ld_src,
+                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t ld_dst) {
+  __shared__ float tile[64][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.y * 64;
+  const int c0 = blockIdx.x * 32;
+#pragma unroll
+  for (int rr = 0; rr < 64; rr += 8) {
+    const int64_t r = r0 + rr + ty;
+    const int c = c0 + tx;
+    tile[rr + ty][tx] = (r < R && c < C) ? src[r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int cc = ty; cc < 32; cc += 8) {
+    const int c = c0 + cc;
+    const int64_t r = r0 + 2 * tx;
+    if (c < C && r < R) {
+      __nv_bfloat16 h[2], l[2];
+      split_bf16(tile[2 * tx][cc], h[0], l[0]);
+      split_bf16(tile[2 * tx + 1][cc], h[1], l[1]);  // zero when r + 1 >= R
+      *reinterpret_cast<uint32_t*>(hi + (int64_t)c * ld_dst + r) = *reinterpret_cast<const uint32_t*>(h);
+      *reinterpret_cast<uint32_t*>(lo + (int64_t)c * ld_dst + r) = *reinterpret_cast<const uint32_t*>(l);
+    }
+  }
+}
+
+// grid (ceil(N/BN), ceil(M/128)).  terms = 3 (split bf16) or 1 (plain bf16: the lo planes are neither loaded nor multiplied).
+template <int BN, bool CHUNKED, int EPI>
+__global__ void __launch_bounds__(GemmTc<BN>::THREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, int M, int N, int K,
+          int terms, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias) {
+  using G = GemmTc<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::STAGES * G::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + G::STAGES;
+  uint64_t* acc_full = bars + 2 * G::STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * G::BM, n0 = blockIdx.x * BN;
+  const int nkb = (K + G::BK - 1) / G::BK;
+  const int nchunks = CHUNKED ? (nkb + G::KCH_BLOCKS - 1) / G::KCH_BLOCKS : 1;
+  const bool split = terms == 3;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_b_hi);
+    if (split) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
+    for (int s = 0; s < G::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, G::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t bytes = split ? G::STAGE_BYTES : G::A_BYTES + G::B_BYTES;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % G::STAGES;
+        const uint32_t ph = (kb / G::STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = smem + s * G::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[s], bytes);
+        const int k0 = kb * G::BK;
+        tma_load_2d(st, &map_a_hi, &full[s], k0, m0);
+        tma_load_2d(st + 2 * G::A_BYTES, &map_b_hi, &full[s], k0, n0);
+        if (split) {
+          tma_load_2d(st + G::A_BYTES, &map_a_lo, &full[s], k0, m0);
+          tma_load_2d(st + 2 * G::A_BYTES + G::B_BYTES, &map_b_lo, &full[s], k0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(G::BM, BN);
+      int kb = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        mbar_wait(&acc_empty[buf], ((c >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tcol = tmem_base + buf * 256;
+        const int kb_end = CHUNKED ? min(nkb, (c + 1) * G::KCH_BLOCKS) : nkb;
+        for (int j = 0; kb < kb_end; ++j, ++kb) {
+          const int s = kb % G::STAGES;
+          const uint32_t ph = (kb / G::STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * G::STAGE_BYTES);
+          const uint32_t a_hi = st, a_lo = st + G::A_BYTES, b_hi = st + 2 * G::A_BYTES, b_lo = b_hi + G::B_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < G::BK / 16; ++ks) {
+            const uint32_t ko = ks * 32;
+            const uint64_t dah = umma_desc(a_hi + ko, 16, G::SBO, G::LAYOUT);
+            const uint64_t dbh = umma_desc(b_hi + ko, 16, G::SBO, G::LAYOUT);
+            const uint32_t first = (uint32_t)((j | ks) != 0);
+            if (split) {
+              const uint64_t dal = umma_desc(a_lo + ko, 16, G::SBO, G::LAYOUT);
+              const uint64_t dbl = umma_desc(b_lo + ko, 16, G::SBO, G::LAYOUT);
+              umma_f16(tcol, dal, dbh, idesc, first);  // small terms first
+              umma_f16(tcol, dah, dbl, idesc, 1u);
+              umma_f16(tcol, dah, dbh, idesc, 1u);
+            } else {
+              umma_f16(tcol, dah, dbh, idesc, first);
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5): one output row per thread =====================
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    float* crow = C + (int64_t)row * ldc + n0;
+    auto emit = [&](int cc, const float (&v)[16]) {  // 16 consecutive columns starting at n0 + cc
+      if (row >= M) return;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const int col = n0 + cc + j;
+        if (col >= N) break;  // N % 4 == 0
+        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (EPI == GEMM_EPI_BIAS_SELU) {
+          const float4 b = *reinterpret_cast<const float4*>(bias + col);
+          o.x = selu_f(o.x + b.x); o.y = selu_f(o.y + b.y); o.z = selu_f(o.z + b.z); o.w = selu_f(o.w + b.w);
+        } else if (EPI == GEMM_EPI_ACCUM) {
+          const float4 p = *reinterpret_cast<const float4*>(crow + cc + j);
+          o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+        }
+        *reinterpret_cast<float4*>(crow + cc + j) = o;
+      }
+    };
+    if (CHUNKED) {
+      float sum[BN];
+#pragma unroll
+      for (int i = 0; i < BN; ++i) sum[i] = 0.f;
+      for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        mbar_wait(&acc_full[buf], (c >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
+#pragma unroll
+        for (int cc = 0; cc < BN; cc += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + cc, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sum[cc + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
+#pragma unroll
+      for (int cc = 0; cc < BN; cc += 16) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = sum[cc + j];
+        emit(cc, v);
+      }
+    } else {
+      mbar_wait(&acc_full[0], 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 2
+      for (int cc = 0; cc < BN; cc += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + cc, r);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        emit(cc, v);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, G::TMEM_COLS);
+  }
+}
+
+}  // namespace tc
+}  // namespace cvb

@@ -21,10 +21,16 @@ struct TrainWork {
   float *w3t = nullptr, *w2t = nullptr, *w4t = nullptr, *w5t = nullptr, *tmpb = nullptr, *tmph = nullptr;
   float* loss = nullptr;  // [8]: loss1..4 (sums), sum of squares of kernels, spare
   float* all = nullptr;   // single allocation backing everything above
+  // tensor-core FC4 (gemm_tc.cuh): split-bf16 operands, planes [hi | lo].  p3s/g4s row-major copies, p3t/g4t transposes
+  // (row pitch ldt = cap), w4s = W4 [4608][336], w4ts = W4^T [336][4608]
+  uint16_t *p3s = nullptr, *p3t = nullptr, *g4s = nullptr, *g4t = nullptr, *w4s = nullptr, *w4ts = nullptr;
+  int64_t ldt = 0;
+  uint16_t* all16 = nullptr;
 };
 static inline void train_work_free(TrainWork* w) {
   if (!w) return;
   cudaFree(w->all);
+  cudaFree(w->all16);
   delete w;
 }
 

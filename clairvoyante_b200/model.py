@@ -18,6 +18,7 @@ from . import _lib, tf_bundle, initializers, param
 
 _VARIANT_ID = {"v3": 0, "v3_slim": 1}
 COMPUTE_MODES = {"fp32": 0, "fp16x3": 1, "fp16": 2}
+TRAIN_MODES = {"fp32": 0, "bf16x3": 1, "bf16": 2}
 
 
 def _default_device():
@@ -81,6 +82,10 @@ class ClairvoyanteBase(object):
             mode = "fp16x3"        # v3: conv2/conv3/FC4/tail on tcgen05; v3_slim: conv3 on tcgen05
         self.computeMode = None
         self.setComputeMode(mode)
+        # arithmetic of the training step's large contractions (cvb200.h CVB_TRAIN_*): split-bf16 on tcgen05 by default,
+        # CVB_TRAIN=fp32 selects the all-SIMT kernels, CVB_TRAIN=bf16 plain bf16 operands
+        self.trainMode = None
+        self.setTrainMode(os.environ.get("CVB_TRAIN", "bf16x3"))
         self._dropout_calls = 0
         self._seed = int.from_bytes(os.urandom(8), "little")   # reference dropout is unseeded (selu.py:55)
 
@@ -138,6 +143,10 @@ class ClairvoyanteBase(object):
     def setComputeMode(self, mode):
         _lib.check(self._lib.cvb_set_compute_mode(self._h, COMPUTE_MODES[mode]))
         self.computeMode = mode
+
+    def setTrainMode(self, mode):
+        _lib.check(self._lib.cvb_set_train_mode(self._h, TRAIN_MODES[mode]))
+        self.trainMode = mode
 
     @staticmethod
     def _ckpt_path(fn):

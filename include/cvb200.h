@@ -98,6 +98,13 @@ int cvb_loss_host(cvb_model* m, const float* x, const float* y, int64_t n, float
 int cvb_train_step_host(cvb_model* m, const float* x, const float* y, int64_t n,
                         float lr, float l2, float drop4, uint64_t dropout_seed,
                         int apply_update, float* loss6);
+/* arithmetic of the large contractions of cvb_train_step_host / cvb_loss_host (train.py's model.train / getLoss path,
+ * clairvoyante_v3.py:174,183-227).  FP32: fp32 SIMT kernels throughout.  BF16X3 (default): FC4 forward, data gradient and
+ * weight gradient on tcgen05 with split-bf16 operands (x = hi + lo, three products, fp32 accumulate: ~2^-16 relative per
+ * operand, fp32's exponent range).  BF16: the same kernels with the hi planes only -- BASELINE config "bf16 compute,
+ * fp32 master weights".  Master weights, Adam slots, gradients and every other layer stay fp32 in all modes.          */
+enum { CVB_TRAIN_FP32 = 0, CVB_TRAIN_BF16X3 = 1, CVB_TRAIN_BF16 = 2 };
+int cvb_set_train_mode(cvb_model* m, int mode);
 /* device pointer + element count of the flat fp32 gradient buffer (all 18 variables in
  * cvb_variable_info order, followed by 5 loss terms) for an external all-reduce     */
 int cvb_grad_buffer(cvb_model* m, void** dev_ptr, int64_t* numel);
