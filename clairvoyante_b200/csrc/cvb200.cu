@@ -1046,7 +1046,7 @@ static int ensure_train_work(cvb_model* m) {
       {&w->g4, c * 336}, {&w->g4b, c * 336}, {&w->gp3, c * 24 * 192}, {&w->g3p, c * 28 * 192}, {&w->gp2, c * 26 * 128},
       {&w->g2p, c * 30 * 128}, {&w->gp1, c * 29 * 64}, {&w->g1, c * 33 * 64}, {&w->w3t, 3 * 4 * 48 * 32},
       {&w->w2t, 2 * 4 * 32 * 16}, {&w->w4t, 336 * 4608}, {&w->w5t, 176 * 336}, {&w->tmpb, 336 * 16}, {&w->tmph, 168 * 16},
-      {&w->loss, 16}};
+      {&w->tmp5, 336 * 184}, {&w->loss, 16}};
   int64_t total = 0;
   for (auto& it : items) total += (it.n + 63) / 64 * 64;
   CK(cudaMalloc(&w->all, (size_t)total * 4));
@@ -1058,7 +1058,8 @@ static int ensure_train_work(cvb_model* m) {
     w->ldt = c;
     struct Item16 { uint16_t** p; int64_t n; };
     Item16 it16[] = {{&w->p3s, 2 * c * 4608}, {&w->p3t, 2 * 4608 * c}, {&w->g4s, 2 * c * 336},
-                     {&w->g4t, 2 * 336 * c},  {&w->w4s, 2 * 4608 * 336}, {&w->w4ts, 2 * 336 * 4608}};
+                     {&w->g4t, 2 * 336 * c},  {&w->w4s, 2 * 4608 * 336}, {&w->w4ts, 2 * 336 * 4608},
+                     {&w->d4t, 2 * 336 * c},  {&w->h5t, 2 * 168 * c},    {&w->gct, 2 * 184 * c}};
     int64_t t16 = 0;
     for (auto& it : it16) t16 += (it.n + 127) / 128 * 128;
     CK(cudaMalloc(&w->all16, (size_t)t16 * 2));
@@ -1102,10 +1103,11 @@ static int split_rows_bf16(const float* src, int64_t rows, int cols, uint16_t* d
   CK(cudaGetLastError());
   return 0;
 }
-static int split_transpose_bf16(const float* src, int64_t R, int C, uint16_t* dst, int64_t plane, int64_t ld_dst, cudaStream_t st) {
+static int split_transpose_bf16(const float* src, int64_t R, int C, int64_t ld_src, uint16_t* dst, int64_t plane, int64_t ld_dst,
+                                cudaStream_t st) {
   if (R <= 0) return 0;
   tc::k_split_transpose_bf16<<<dim3((unsigned)((C + 31) / 32), (unsigned)((R + 63) / 64)), dim3(32, 8), 0, st>>>(
-      src, R, C, C, bf(dst), bf(dst + plane), ld_dst);
+      src, R, C, ld_src, bf(dst), bf(dst + plane), ld_dst);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1186,39 +1188,30 @@ static int train_backward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t s
   k_colsum<<<dim3(2, 32), 256, 0, st>>>(w->g4, nc, 36, 36, gvar(m, "fc4/bias"));
   k_dense_bwd_small<<<gsz(nc * 4224), 256, 0, st>>>(w->g4, 36, 36, m->var("fc4/kernel"), 4224, w->gp3, 4224, nc);
   // conv3 (5x4, 16 -> 32)
-  k_pool_bwd_selu<1><<<gsz(nc * 33 * 128), 256, 0, st>>>(w->gp3, w->c3, nc, 33, 128, w->g3p, 37, 2);
+  k_pool_bwd_selu<1, 128, 256><<<gsz(nc * 33 * 128), 256, 0, st>>>(w->gp3, w->c3, nc, 33, w->g3p, 37, 2, gvar(m, "conv3/bias"));
   {
     using W = WgradCfg<16, 32, 5, 33, 4, 8, 4>;
     auto k = k_conv_wgrad<16, 32, 5, 33, 4, 8, 4>;
     CK(set_smem(k, W::SMEM_BYTES));
     k<<<(int)std::min<int64_t>((nc + 3) / 4, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->p2p, w->g3p, 37, 2, nc, gvar(m, "conv3/kernel"));
     CK(cudaGetLastError());
-    k_colsum<<<dim3(1, 128), 256, 0, st>>>(w->g3p, nc * 37 * 4, 32, 32, gvar(m, "conv3/bias"));
     if (launch_conv_keep<ConvCfg<32, 16, 5, 33, 3, 8, 8, 2>>(m, w->g3p, nc, w->w3t, nullptr, w->gp2, false, st)) return 1;
   }
   // conv2 (3x4, 8 -> 16)
-  k_pool_bwd_selu<1><<<gsz(nc * 33 * 64), 256, 0, st>>>(w->gp2, w->c2, nc, 33, 64, w->g2p, 35, 1);
+  k_pool_bwd_selu<1, 64, 256><<<gsz(nc * 33 * 64), 256, 0, st>>>(w->gp2, w->c2, nc, 33, w->g2p, 35, 1, gvar(m, "conv2/bias"));
   {
     using W = WgradCfg<8, 16, 3, 33, 4, 4, 4>;
     auto k = k_conv_wgrad<8, 16, 3, 33, 4, 4, 4>;
     CK(set_smem(k, W::SMEM_BYTES));
     k<<<(int)std::min<int64_t>((nc + 3) / 4, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->p1p, w->g2p, 35, 1, nc, gvar(m, "conv2/kernel"));
     CK(cudaGetLastError());
-    k_colsum<<<dim3(1, 128), 256, 0, st>>>(w->g2p, nc * 35 * 4, 16, 16, gvar(m, "conv2/bias"));
     if (launch_conv_keep<ConvCfg<16, 8, 3, 33, 6, 8, 8, 2>>(m, w->g2p, nc, w->w2t, nullptr, w->gp1, false, st)) return 1;
   }
   // conv1 (1x4, 4 -> 8)
-  k_pool_bwd_selu<1><<<gsz(nc * 33 * 32), 256, 0, st>>>(w->gp1, w->c1, nc, 33, 32, w->g1, 33, 0);
-  {
-    using W = WgradCfg<4, 8, 1, 33, 1, 4, 8>;
-    auto k = k_conv_wgrad<4, 8, 1, 33, 1, 4, 8>;
-    CK(set_smem(k, W::SMEM_BYTES));
-    k<<<(int)std::min<int64_t>((nc + 7) / 8, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->x, w->g1, 33, 0, nc, gvar(m, "conv1/kernel"));
-    CK(cudaGetLastError());
-    k_colsum<<<dim3(1, 128), 256, 0, st>>>(w->g1, nc * 33 * 4, 8, 8, gvar(m, "conv1/bias"));
-  }
+  k_pool_bwd_selu<1, 32, 256><<<gsz(nc * 33 * 32), 256, 0, st>>>(w->gp1, w->c1, nc, 33, w->g1, 33, 0, gvar(m, "conv1/bias"));
+  k_conv1_wgrad<8, 4><<<(int)std::min<int64_t>((nc + 3) / 4, 4 * sms), 128, 0, st>>>(w->x, w->g1, nc, gvar(m, "conv1/kernel"));
   CK(cudaGetLastError());
-  m->launches += 27;
+  m->launches += 24;
   return 0;
 }
 
@@ -1295,24 +1288,43 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
   TrainWork* w = m->train;
   const int sms = m->num_sms;
   const float* d4 = drop4 > 0.f ? w->d4 : w->h4;
-  // heads: weight / bias gradients
-  CK(cudaMemsetAsync(w->tmpb, 0, 336 * 16 * 4, st));
-  CK(cudaMemsetAsync(w->tmph, 0, 168 * 16 * 4, st));
-  k_gemm_tn<<<dim3((336 + 63) / 64, 1), 256, 0, st>>>(d4, 336, w->dlog, 16, w->tmpb, 16, 336, 16, nc);
-  k_gemm_tn<<<dim3((168 + 63) / 64, 1), 256, 0, st>>>(w->h5, 168, w->dlog, 16, w->tmph, 16, 168, 16, nc);
+  // heads: bias gradients; heads -> g4 (base branch), g5 (x selu')
+  const bool tcm = m->train_mode != CVB_TRAIN_FP32;
   HeadG hg{gvar(m, "YBaseChangeSigmoid/kernel"), gvar(m, "YZygosityFC/kernel"), gvar(m, "YVarTypeFC/kernel"),
            gvar(m, "YIndelLengthFC/kernel")};
-  k_scatter_heads<<<(336 * 4 + 255) / 256, 256, 0, st>>>(w->tmpb, w->tmph, 336, 168, hg);
   k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->dlog + 0, nc, 16, 4, gvar(m, "YBaseChangeSigmoid/bias"));
   k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->dlog + 4, nc, 16, 2, gvar(m, "YZygosityFC/bias"));
   k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->dlog + 6, nc, 16, 4, gvar(m, "YVarTypeFC/bias"));
   k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->dlog + 10, nc, 16, 6, gvar(m, "YIndelLengthFC/bias"));
-  // heads -> g4 (base branch), g5 (x selu')
   HeadW hw{m->var("YBaseChangeSigmoid/kernel"), m->var("YZygosityFC/kernel"), m->var("YVarTypeFC/kernel"),
            m->var("YIndelLengthFC/kernel")};
   k_heads_bwd<<<gsz(nc * (336 + 168)), 256, 0, st>>>(w->dlog, w->h5, nc, 336, 168, hw, w->g4, w->g5, 176);
+  if (tcm) {
+    // weight gradients of FC5 and the four heads as two tcgen05 contractions over K = sites:
+    //   tmp5 [336][184] = d4^T . [g5 | dlog]   (cols 0..167 -> fc5/kernel, 168..171 -> base head: its input is dropout4)
+    //   tmph [168][16]  = h5^T . dlog          (cols 4..15 -> zygosity / varType / indelLength heads)
+    const int64_t ldt = w->ldt;
+    if (split_transpose_bf16(d4, nc, 336, 336, w->d4t, 336 * ldt, ldt, st)) return 1;
+    if (split_transpose_bf16(w->h5, nc, 168, 168, w->h5t, 168 * ldt, ldt, st)) return 1;
+    if (split_transpose_bf16(w->g5, nc, 168, 176, w->gct, 184 * ldt, ldt, st)) return 1;
+    if (split_transpose_bf16(w->dlog, nc, 16, 16, w->gct + 168 * ldt, 184 * ldt, ldt, st)) return 1;
+    if (launch_gemm_tc<192, true, tc::GEMM_EPI_STORE>(m, w->d4t, 336 * ldt, ldt, w->gct, 184 * ldt, ldt, 336, 184, (int)nc, w->tmp5,
+                                                      184, nullptr, st))
+      return 1;
+    if (launch_gemm_tc<16, true, tc::GEMM_EPI_STORE>(m, w->h5t, 168 * ldt, ldt, w->gct + 168 * ldt, 184 * ldt, ldt, 168, 16,
+                                                     (int)nc, w->tmph, 16, nullptr, st))
+      return 1;
+    k_scatter_fc5_heads<<<(336 * 168 + 255) / 256, 256, 0, st>>>(w->tmp5, w->tmph, gvar(m, "fc5/kernel"), hg);
+    CK(cudaGetLastError());
+  } else {
+    CK(cudaMemsetAsync(w->tmpb, 0, 336 * 16 * 4, st));
+    CK(cudaMemsetAsync(w->tmph, 0, 168 * 16 * 4, st));
+    k_gemm_tn<<<dim3((336 + 63) / 64, 1), 256, 0, st>>>(d4, 336, w->dlog, 16, w->tmpb, 16, 336, 16, nc);
+    k_gemm_tn<<<dim3((168 + 63) / 64, 1), 256, 0, st>>>(w->h5, 168, w->dlog, 16, w->tmph, 16, 168, 16, nc);
+    k_scatter_heads<<<(336 * 4 + 255) / 256, 256, 0, st>>>(w->tmpb, w->tmph, 336, 168, hg);
+    k_gemm_tn<<<dim3((336 + 63) / 64, (168 + 63) / 64), 256, 0, st>>>(d4, 336, w->g5, 176, gvar(m, "fc5/kernel"), 168, 336, 168, nc);
+  }
   // FC5
-  k_gemm_tn<<<dim3((336 + 63) / 64, (168 + 63) / 64), 256, 0, st>>>(d4, 336, w->g5, 176, gvar(m, "fc5/kernel"), 168, 336, 168, nc);
   k_colsum<<<dim3((168 + 31) / 32, 32), 256, 0, st>>>(w->g5, nc, 176, 168, gvar(m, "fc5/bias"));
   {
     using F = FcCfg<336, 21, 16, 12, 8>;
@@ -1326,8 +1338,8 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
   k_colsum<<<dim3((336 + 31) / 32, 32), 256, 0, st>>>(w->g4, nc, 336, 336, gvar(m, "fc4/bias"));
   if (m->train_mode != CVB_TRAIN_FP32) {
     // weight gradient  dW4 [4608][336] += p3^T . dpre4   (K = sites: both operands transposed into K-major planes)
-    if (split_transpose_bf16(w->p3, nc, 4608, w->p3t, 4608 * w->ldt, w->ldt, st)) return 1;
-    if (split_transpose_bf16(w->g4, nc, 336, w->g4t, 336 * w->ldt, w->ldt, st)) return 1;
+    if (split_transpose_bf16(w->p3, nc, 4608, 4608, w->p3t, 4608 * w->ldt, w->ldt, st)) return 1;
+    if (split_transpose_bf16(w->g4, nc, 336, 336, w->g4t, 336 * w->ldt, w->ldt, st)) return 1;
     if (launch_gemm_tc<176, true, tc::GEMM_EPI_ACCUM>(m, w->p3t, 4608 * w->ldt, w->ldt, w->g4t, 336 * w->ldt, w->ldt, 4608, 336,
                                                       (int)nc, gvar(m, "fc4/kernel"), 336, nullptr, st))
       return 1;
@@ -1347,14 +1359,13 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
     CK(cudaGetLastError());
   }
   // conv3
-  k_pool_bwd_selu<3><<<gsz(nc * 26 * 192), 256, 0, st>>>(w->gp3, w->c3, nc, 26, 192, w->g3p, 28, 1);
+  k_pool_bwd_selu<3, 192, 192><<<gsz(nc * 26 * 192, 192), 192, 0, st>>>(w->gp3, w->c3, nc, 26, w->g3p, 28, 1, gvar(m, "conv3/bias"));
   {
     using W = WgradCfg<32, 48, 3, 26, 4, 12, 4>;
     auto k = k_conv_wgrad<32, 48, 3, 26, 4, 12, 4>;
     CK(set_smem(k, W::SMEM_BYTES));
     k<<<(int)std::min<int64_t>((nc + 3) / 4, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->p2p, w->g3p, 28, 1, nc, gvar(m, "conv3/kernel"));
     CK(cudaGetLastError());
-    k_colsum<<<dim3(2, 128), 256, 0, st>>>(w->g3p, nc * 28 * 4, 48, 48, gvar(m, "conv3/bias"));
     using C = ConvCfg<48, 32, 3, 26, 3, 8, 8, 2>;
     using L = ConvLayerSmem<C, 1>;
     auto kd = k_conv_layer<C, 1, 256, false, false>;
@@ -1363,14 +1374,13 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
     CK(cudaGetLastError());
   }
   // conv2
-  k_pool_bwd_selu<4><<<gsz(nc * 29 * 128), 256, 0, st>>>(w->gp2, w->c2, nc, 29, 128, w->g2p, 30, 1);
+  k_pool_bwd_selu<4, 128, 256><<<gsz(nc * 29 * 128), 256, 0, st>>>(w->gp2, w->c2, nc, 29, w->g2p, 30, 1, gvar(m, "conv2/bias"));
   {
     using W = WgradCfg<16, 32, 2, 29, 4, 4, 4>;
     auto k = k_conv_wgrad<16, 32, 2, 29, 4, 4, 4>;
     CK(set_smem(k, W::SMEM_BYTES));
     k<<<(int)std::min<int64_t>((nc + 3) / 4, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->p1p, w->g2p, 30, 1, nc, gvar(m, "conv2/kernel"));
     CK(cudaGetLastError());
-    k_colsum<<<dim3(1, 128), 256, 0, st>>>(w->g2p, nc * 30 * 4, 32, 32, gvar(m, "conv2/bias"));
     using C = ConvCfg<32, 16, 2, 29, 4, 8, 8, 2>;
     using L = ConvLayerSmem<C, 1>;
     auto kd = k_conv_layer<C, 1, 256, false, false>;
@@ -1379,17 +1389,10 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
     CK(cudaGetLastError());
   }
   // conv1 (no data gradient needed)
-  k_pool_bwd_selu<5><<<gsz(nc * 33 * 64), 256, 0, st>>>(w->gp1, w->c1, nc, 33, 64, w->g1, 33, 0);
-  {
-    using W = WgradCfg<4, 16, 1, 33, 1, 4, 8>;
-    auto k = k_conv_wgrad<4, 16, 1, 33, 1, 4, 8>;
-    CK(set_smem(k, W::SMEM_BYTES));
-    k<<<(int)std::min<int64_t>((nc + 7) / 8, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->x, w->g1, 33, 0, nc, gvar(m, "conv1/kernel"));
-    CK(cudaGetLastError());
-    k_colsum<<<dim3(1, 128), 256, 0, st>>>(w->g1, nc * 33 * 4, 16, 16, gvar(m, "conv1/bias"));
-  }
+  k_pool_bwd_selu<5, 64, 256><<<gsz(nc * 33 * 64), 256, 0, st>>>(w->gp1, w->c1, nc, 33, w->g1, 33, 0, gvar(m, "conv1/bias"));
+  k_conv1_wgrad<16, 4><<<(int)std::min<int64_t>((nc + 3) / 4, 4 * sms), 256, 0, st>>>(w->x, w->g1, nc, gvar(m, "conv1/kernel"));
   CK(cudaGetLastError());
-  m->launches += 27;
+  m->launches += 24;
   return 0;
 }
 
@@ -1404,7 +1407,7 @@ static int train_prepare_weights(cvb_model* m, cudaStream_t st, bool backward) {
     return 0;
   }
   if (m->train_mode != CVB_TRAIN_FP32) {  // the forward pass (getLoss included) reads W4^T, the data gradient W4
-    if (split_transpose_bf16(m->var("fc4/kernel"), 4608, 336, w->w4ts, 336 * 4608, 4608, st)) return 1;
+    if (split_transpose_bf16(m->var("fc4/kernel"), 4608, 336, 336, w->w4ts, 336 * 4608, 4608, st)) return 1;
     if (backward && split_rows_bf16(m->var("fc4/kernel"), 4608, 336, w->w4s, 4608 * 336, st)) return 1;
     m->launches += backward ? 2 : 1;
   } else if (backward) {

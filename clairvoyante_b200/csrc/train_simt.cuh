@@ -24,6 +24,9 @@ struct TrainWork {
   // tensor-core FC4 (gemm_tc.cuh): split-bf16 operands, planes [hi | lo].  p3s/g4s row-major copies, p3t/g4t transposes
   // (row pitch ldt = cap), w4s = W4 [4608][336], w4ts = W4^T [336][4608]
   uint16_t *p3s = nullptr, *p3t = nullptr, *g4s = nullptr, *g4t = nullptr, *w4s = nullptr, *w4ts = nullptr;
+  // transposed operands of the FC5 / head weight gradients: d4^T [336][ldt], h5^T [168][ldt], [g5 | dlog]^T [184][ldt]
+  uint16_t *d4t = nullptr, *h5t = nullptr, *gct = nullptr;
+  float* tmp5 = nullptr;  // [336][184] = d4^T . [g5 | dlog]
   int64_t ldt = 0;
   uint16_t* all16 = nullptr;
 };
@@ -73,19 +76,30 @@ __global__ void k_pool_fwd(const float* __restrict__ in, int64_t n, int H, int C
 
 // ---- max-pool backward fused with the SELU derivative of the conv output c (post-SELU values):
 //   dpre[s][h][k] = selu'(c[h]) * sum_{windows j containing h whose FIRST maximum is at h} dp[s][j][k]
-// written to out [n][OROWS][C] at row OR0 + h (the padded layout the data-gradient conv reads).
-template <int P>
-__global__ void k_pool_bwd_selu(const float* __restrict__ dp, const float* __restrict__ c, int64_t n, int H, int C,
-                                float* __restrict__ out, int OROWS, int OR0) {
+// written to out [n][OROWS][C] at row OR0 + h (the padded layout the data-gradient conv reads), and the conv's bias
+// gradient  bias_grad[k % COUT] += sum over (s, h, w) of dpre  (C = 4 * COUT; one atomicAdd per channel per CTA).
+// Thread = one channel k of one row; a CTA walks rows (s, h) with stride, THREADS / C rows at a time.
+template <int P, int C, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_pool_bwd_selu(const float* __restrict__ dp, const float* __restrict__ c, int64_t n, int H, float* __restrict__ out, int OROWS,
+                int OR0, float* __restrict__ bias_grad) {
+  static_assert(THREADS % C == 0 && C % 4 == 0, "whole rows per pass");
+  constexpr int RPI = THREADS / C, COUT = C / 4;
   const int HP = H - P + 1;
-  const int64_t total = n * H * C;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i % C);
-    const int64_t t = i / C;
-    const int h = (int)(t % H);
-    const int64_t s = t / H;
+  const int k = threadIdx.x % C, rsub = threadIdx.x / C;
+  float bsum = 0.f;
+  const int64_t rows = n * H;
+  for (int64_t row = (int64_t)blockIdx.x * RPI + rsub; row < rows; row += (int64_t)gridDim.x * RPI) {
+    const int64_t s = row / H;
+    const int h = (int)(row - s * H);
     const float* cs = c + s * H * C + k;
-    const float ch = cs[h * C];
+    float win[2 * P - 1];  // c at rows h-P+1 .. h+P-1 (out-of-range rows never take part in a valid window)
+#pragma unroll
+    for (int e = 0; e < 2 * P - 1; ++e) {
+      const int r = h - (P - 1) + e;
+      win[e] = (r >= 0 && r < H) ? cs[r * C] : 0.f;
+    }
+    const float ch = win[P - 1];
     float g = 0.f;
 #pragma unroll
     for (int d = 0; d < P; ++d) {
@@ -94,13 +108,56 @@ __global__ void k_pool_bwd_selu(const float* __restrict__ dp, const float* __res
       bool is_first_max = true;
 #pragma unroll
       for (int e = 0; e < P; ++e) {
-        const float v = cs[(j + e) * C];
+        const float v = win[P - 1 - d + e];
         if (e < d ? (v >= ch) : (v > ch)) is_first_max = false;  // earlier element equal or larger, later strictly larger
       }
       if (is_first_max) g += dp[(s * HP + j) * C + k];
     }
-    out[(s * OROWS + OR0 + h) * C + k] = g * selu_grad_from_out(ch);
+    g *= selu_grad_from_out(ch);
+    out[(s * OROWS + OR0 + h) * C + k] = g;
+    bsum += g;
   }
+  __shared__ float red[THREADS];
+  red[threadIdx.x] = bsum;
+  __syncthreads();
+  if (threadIdx.x < COUT) {
+    float v = 0.f;
+    for (int i = threadIdx.x; i < THREADS; i += COUT) v += red[i];
+    atomicAdd(bias_grad + threadIdx.x, v);
+  }
+}
+
+// ---- conv1 weight gradient (1x4 kernel, CIN = 4): dW[kw][c][co] += sum_{site,h,w} x[site][h][w+kw-1][c] * g[site][h][w][co]
+// One thread per weight (4 * 4 * COUT = THREADS); S sites per tile staged in shared memory.
+template <int COUT, int S>
+__global__ void __launch_bounds__(16 * COUT)
+k_conv1_wgrad(const float* __restrict__ x, const float* __restrict__ g, int64_t n, float* __restrict__ dW) {
+  constexpr int THREADS = 16 * COUT, XS = 33 * 16, GS = 33 * 4 * COUT;
+  __shared__ __align__(16) float xs[S * XS];
+  __shared__ __align__(16) float gs[S * GS];
+  const int tid = threadIdx.x;
+  const int co = tid % COUT, cc = (tid / COUT) & 3, kw = tid / (4 * COUT);
+  const int w_lo = 1 - kw > 0 ? 1 - kw : 0, w_hi = 4 - kw < 3 ? 4 - kw : 3;
+  float acc = 0.f;
+  const int64_t ntiles = (n + S - 1) / S;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t s0 = tile * S;
+    const int ns = (int)((n - s0) < S ? (n - s0) : S);
+    __syncthreads();
+    for (int i = tid; i < ns * XS / 4; i += THREADS)
+      reinterpret_cast<float4*>(xs)[i] = reinterpret_cast<const float4*>(x + s0 * XS)[i];
+    for (int i = tid; i < ns * GS / 4; i += THREADS)
+      reinterpret_cast<float4*>(gs)[i] = reinterpret_cast<const float4*>(g + s0 * GS)[i];
+    __syncthreads();
+    for (int r = 0; r < ns * 33; ++r) {  // (site, h) rows are contiguous in both tiles
+      const float* xr = xs + r * 16 + (kw - 1) * 4 + cc;
+      const float* gr = gs + r * 4 * COUT + co;
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        if (w >= w_lo && w <= w_hi) acc = fmaf(xr[w * 4], gr[w * COUT], acc);
+    }
+  }
+  atomicAdd(dW + tid, acc);  // tid == (kw * 4 + c) * COUT + co
 }
 
 // ---- SELU dropout forward on FC4's output (selu.py:54-62): d4 = a*(h4*mask + alpha*(1-mask)) + b
@@ -255,6 +312,18 @@ struct HeadG { float *wb, *wz, *wt, *wl; };
 __global__ void k_scatter_heads(const float* __restrict__ tmpb, const float* __restrict__ tmph, int N4, int N5, HeadG g) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N4 * 4) g.wb[i] += tmpb[(i / 4) * 16 + (i % 4)];
+  if (i < N5 * 2) g.wz[i] += tmph[(i / 2) * 16 + 4 + (i % 2)];
+  if (i < N5 * 4) g.wt[i] += tmph[(i / 4) * 16 + 6 + (i % 4)];
+  if (i < N5 * 6) g.wl[i] += tmph[(i / 6) * 16 + 10 + (i % 6)];
+}
+
+// ---- tensor-path variant: tmp5 [N4][N5 + 16] = d4^T . [g5 | dlog], tmph [N5][16] = h5^T . dlog  (v3: N4 = 336, N5 = 168)
+__global__ void k_scatter_fc5_heads(const float* __restrict__ tmp5, const float* __restrict__ tmph, float* __restrict__ g_fc5,
+                                    HeadG g) {
+  constexpr int N4 = 336, N5 = 168, LD = N5 + 16;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N4 * N5) g_fc5[i] += tmp5[(i / N5) * LD + (i % N5)];
+  if (i < N4 * 4) g.wb[i] += tmp5[(i / 4) * LD + N5 + (i % 4)];
   if (i < N5 * 2) g.wz[i] += tmph[(i / 2) * 16 + 4 + (i % 2)];
   if (i < N5 * 4) g.wt[i] += tmph[(i / 4) * 16 + 6 + (i % 4)];
   if (i < N5 * 6) g.wl[i] += tmph[(i / 6) * 16 + 10 + (i % 6)];
