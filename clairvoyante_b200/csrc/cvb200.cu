@@ -1046,7 +1046,7 @@ static int ensure_train_work(cvb_model* m) {
       {&w->g4, c * 336}, {&w->g4b, c * 336}, {&w->gp3, c * 24 * 192}, {&w->g3p, c * 28 * 192}, {&w->gp2, c * 26 * 128},
       {&w->g2p, c * 30 * 128}, {&w->gp1, c * 29 * 64}, {&w->g1, c * 33 * 64}, {&w->w3t, 3 * 4 * 48 * 32},
       {&w->w2t, 2 * 4 * 32 * 16}, {&w->w4t, 336 * 4608}, {&w->w5t, 176 * 336}, {&w->tmpb, 336 * 16}, {&w->tmph, 168 * 16},
-      {&w->tmp5, 336 * 184}, {&w->loss, 16}};
+      {&w->tmp5, 336 * 184}, {&w->tmpw, 3 * 128 * 192}, {&w->loss, 16}};
   int64_t total = 0;
   for (auto& it : items) total += (it.n + 63) / 64 * 64;
   CK(cudaMalloc(&w->all, (size_t)total * 4));
@@ -1059,7 +1059,9 @@ static int ensure_train_work(cvb_model* m) {
     struct Item16 { uint16_t** p; int64_t n; };
     Item16 it16[] = {{&w->p3s, 2 * c * 4608}, {&w->p3t, 2 * 4608 * c}, {&w->g4s, 2 * c * 336},
                      {&w->g4t, 2 * 336 * c},  {&w->w4s, 2 * 4608 * 336}, {&w->w4ts, 2 * 336 * 4608},
-                     {&w->d4t, 2 * 336 * c},  {&w->h5t, 2 * 168 * c},    {&w->gct, 2 * 184 * c}};
+                     {&w->d4t, 2 * 336 * c},  {&w->h5t, 2 * 168 * c},    {&w->gct, 2 * 184 * c},
+                     {&w->cta, 3 * 2 * 128 * c * 30}, {&w->ctb, 2 * 192 * c * 30}};
+    w->ldr = c * 30;
     int64_t t16 = 0;
     for (auto& it : it16) t16 += (it.n + 127) / 128 * 128;
     CK(cudaMalloc(&w->all16, (size_t)t16 * 2));
@@ -1077,12 +1079,18 @@ static inline int gsz(int64_t total, int block = 256) { return (int)std::min<int
 // ---- tensor-core FC4 contractions of the training path (gemm_tc.cuh) ------------------------------------------------
 // C[M][N] (op)= A[M][K] . B[N][K]^T ; a / b point at the hi plane, the lo plane follows `a_plane` / `b_plane` elements later;
 // lda / ldb = row pitch in elements (multiple of 8: TMA strides are 16-byte granular)
+struct GemmExtra {  // batched / split-K launches, see tc::GemmArgs
+  int batches = 1, a_batch_rows = 0;
+  int64_t c_batch_stride = 0;
+  int kslices = 1;
+};
 template <int BN, bool CHUNKED, int EPI>
 static int launch_gemm_tc(cvb_model* m, const uint16_t* a, int64_t a_plane, int64_t lda, const uint16_t* b, int64_t b_plane,
-                          int64_t ldb, int M, int N, int K, float* C, int64_t ldc, const float* bias, cudaStream_t st) {
+                          int64_t ldb, int M, int N, int K, float* C, int64_t ldc, const float* bias, cudaStream_t st,
+                          const GemmExtra& ex = GemmExtra()) {
   using G = tc::GemmTc<BN>;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  const uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, db[2] = {(uint64_t)K, (uint64_t)N};
+  const uint64_t da[2] = {(uint64_t)K, (uint64_t)(M + (ex.batches - 1) * ex.a_batch_rows)}, db[2] = {(uint64_t)K, (uint64_t)N};
   const uint64_t sa[1] = {(uint64_t)lda * 2}, sb[1] = {(uint64_t)ldb * 2};
   const uint32_t ba[2] = {(uint32_t)G::BK, (uint32_t)G::BM}, bb[2] = {(uint32_t)G::BK, (uint32_t)BN};
   if (make_map_nd(&ma_hi, (void*)a, 2, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
@@ -1091,9 +1099,17 @@ static int launch_gemm_tc(cvb_model* m, const uint16_t* a, int64_t a_plane, int6
   if (make_map_nd(&mb_lo, (void*)(b + b_plane), 2, db, sb, bb, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   auto k = tc::k_gemm_tc<BN, CHUNKED, EPI>;
   CK(set_smem(k, G::SMEM_BYTES));
-  const dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + G::BM - 1) / G::BM));
-  k<<<grid, G::THREADS, G::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, M, N, K, m->train_mode == CVB_TRAIN_BF16 ? 1 : 3, C, ldc,
-                                            bias);
+  tc::GemmArgs g;
+  g.M = M; g.N = N; g.K = K;
+  g.terms = m->train_mode == CVB_TRAIN_BF16 ? 1 : 3;
+  g.C = C; g.ldc = ldc; g.bias = bias;
+  g.m_tiles = (M + G::BM - 1) / G::BM;
+  g.a_batch_rows = ex.a_batch_rows; g.c_batch_stride = ex.c_batch_stride;
+  const int nkb = (K + G::BK - 1) / G::BK;
+  g.kb_per_slice = (nkb + ex.kslices - 1) / ex.kslices;
+  const int kslices = (nkb + g.kb_per_slice - 1) / g.kb_per_slice;  // no empty slice
+  const dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)(g.m_tiles * ex.batches), (unsigned)kslices);
+  k<<<grid, G::THREADS, G::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, g);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1104,11 +1120,39 @@ static int split_rows_bf16(const float* src, int64_t rows, int cols, uint16_t* d
   return 0;
 }
 static int split_transpose_bf16(const float* src, int64_t R, int C, int64_t ld_src, uint16_t* dst, int64_t plane, int64_t ld_dst,
-                                cudaStream_t st) {
+                                cudaStream_t st, int row_shift = 0) {
   if (R <= 0) return 0;
   tc::k_split_transpose_bf16<<<dim3((unsigned)((C + 31) / 32), (unsigned)((R + 63) / 64)), dim3(32, 8), 0, st>>>(
-      src, R, C, ld_src, bf(dst), bf(dst + plane), ld_dst);
+      src, R, C, ld_src, bf(dst), bf(dst + plane), ld_dst, row_shift);
   CK(cudaGetLastError());
+  return 0;
+}
+
+// Conv weight gradient on tcgen05 (training_op, clairvoyante_v3.py:174, for conv2 / conv3):
+//   dW[kh][kw][c][co] = sum_R in[R - 1 + kh][(w', c)] * g[R][(w, co)],   w' = w + kw - 1,
+// over the flattened (site, row) index R of the padded layouts (g stored one row down, its pad rows are zero, so terms that
+// cross a site boundary vanish).  Both operands are transposed into K-major bf16 planes (K = R), `in` once per kh with its
+// rows shifted by kh - 1 (TMA cannot apply a K offset that is not a multiple of 16 bytes); one batched GEMM gives
+// tmpW[kh] = in_kh^T . g  = every (w', c) x (w, co) product (13 of the 16 (w', w) pairs are real taps), K split
+// over the SMs with atomic accumulation; k_scatter_conv_wgrad adds the taps into dW.
+template <int CIN, int COUT, int KH>
+static int launch_conv_wgrad_tc(cvb_model* m, const float* in, const float* g, int64_t R, float* dW, cudaStream_t st) {
+  TrainWork* w = m->train;
+  const int64_t ld = w->ldr;
+  constexpr int MA = 4 * CIN;  // rows of one (shifted) copy of in^T; the KH copies are stacked: [kh][(w', c)][R]
+  for (int kh = 0; kh < KH; ++kh)
+    if (split_transpose_bf16(in, R, MA, MA, w->cta + (int64_t)kh * MA * ld, (int64_t)KH * MA * ld, ld, st, kh - 1)) return 1;
+  if (split_transpose_bf16(g, R, 4 * COUT, 4 * COUT, w->ctb, 192 * ld, ld, st)) return 1;
+  CK(cudaMemsetAsync(w->tmpw, 0, (size_t)KH * MA * 192 * 4, st));
+  GemmExtra ex;
+  ex.batches = KH; ex.a_batch_rows = MA; ex.c_batch_stride = (int64_t)MA * 192;
+  ex.kslices = std::max(1, m->num_sms / KH);
+  if (launch_gemm_tc<192, true, tc::GEMM_EPI_ATOMIC>(m, w->cta, (int64_t)KH * MA * ld, ld, w->ctb, 192 * ld, ld, MA, 4 * COUT, (int)R,
+                                                     w->tmpw, 192, nullptr, st, ex))
+    return 1;
+  k_scatter_conv_wgrad<CIN, COUT, KH><<<(KH * 4 * CIN * COUT + 255) / 256, 256, 0, st>>>(w->tmpw, dW);
+  CK(cudaGetLastError());
+  m->launches += 3 + KH;
   return 0;
 }
 
@@ -1361,11 +1405,15 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
   // conv3
   k_pool_bwd_selu<3, 192, 192><<<gsz(nc * 26 * 192, 192), 192, 0, st>>>(w->gp3, w->c3, nc, 26, w->g3p, 28, 1, gvar(m, "conv3/bias"));
   {
-    using W = WgradCfg<32, 48, 3, 26, 4, 12, 4>;
-    auto k = k_conv_wgrad<32, 48, 3, 26, 4, 12, 4>;
-    CK(set_smem(k, W::SMEM_BYTES));
-    k<<<(int)std::min<int64_t>((nc + 3) / 4, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->p2p, w->g3p, 28, 1, nc, gvar(m, "conv3/kernel"));
-    CK(cudaGetLastError());
+    if (tcm) {
+      if (launch_conv_wgrad_tc<32, 48, 3>(m, w->p2p, w->g3p, nc * 28, gvar(m, "conv3/kernel"), st)) return 1;
+    } else {
+      using W = WgradCfg<32, 48, 3, 26, 4, 12, 4>;
+      auto k = k_conv_wgrad<32, 48, 3, 26, 4, 12, 4>;
+      CK(set_smem(k, W::SMEM_BYTES));
+      k<<<(int)std::min<int64_t>((nc + 3) / 4, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->p2p, w->g3p, 28, 1, nc, gvar(m, "conv3/kernel"));
+      CK(cudaGetLastError());
+    }
     using C = ConvCfg<48, 32, 3, 26, 3, 8, 8, 2>;
     using L = ConvLayerSmem<C, 1>;
     auto kd = k_conv_layer<C, 1, 256, false, false>;
@@ -1376,11 +1424,15 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
   // conv2
   k_pool_bwd_selu<4, 128, 256><<<gsz(nc * 29 * 128), 256, 0, st>>>(w->gp2, w->c2, nc, 29, w->g2p, 30, 1, gvar(m, "conv2/bias"));
   {
-    using W = WgradCfg<16, 32, 2, 29, 4, 4, 4>;
-    auto k = k_conv_wgrad<16, 32, 2, 29, 4, 4, 4>;
-    CK(set_smem(k, W::SMEM_BYTES));
-    k<<<(int)std::min<int64_t>((nc + 3) / 4, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->p1p, w->g2p, 30, 1, nc, gvar(m, "conv2/kernel"));
-    CK(cudaGetLastError());
+    if (tcm) {
+      if (launch_conv_wgrad_tc<16, 32, 2>(m, w->p1p, w->g2p, nc * 30, gvar(m, "conv2/kernel"), st)) return 1;
+    } else {
+      using W = WgradCfg<16, 32, 2, 29, 4, 4, 4>;
+      auto k = k_conv_wgrad<16, 32, 2, 29, 4, 4, 4>;
+      CK(set_smem(k, W::SMEM_BYTES));
+      k<<<(int)std::min<int64_t>((nc + 3) / 4, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->p1p, w->g2p, 30, 1, nc, gvar(m, "conv2/kernel"));
+      CK(cudaGetLastError());
+    }
     using C = ConvCfg<32, 16, 2, 29, 4, 8, 8, 2>;
     using L = ConvLayerSmem<C, 1>;
     auto kd = k_conv_layer<C, 1, 256, false, false>;

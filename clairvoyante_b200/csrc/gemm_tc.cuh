@@ -19,7 +19,23 @@
 namespace cvb {
 namespace tc {
 
-enum { GEMM_EPI_STORE = 0, GEMM_EPI_BIAS_SELU = 1, GEMM_EPI_ACCUM = 2 };
+enum { GEMM_EPI_STORE = 0, GEMM_EPI_BIAS_SELU = 1, GEMM_EPI_ACCUM = 2, GEMM_EPI_ATOMIC = 3 };
+
+// C, bias as above.  Batched / split-K launches (the conv weight gradients, see launch_conv_wgrad_tc in cvb200.cu):
+//   grid.y = batches * m_tiles: batch b = blockIdx.y / m_tiles reads A rows b * a_batch_rows + [0, M) and writes
+//            C + b * c_batch_stride; every batch shares B.  (A K-shift per batch would be the natural formulation of the
+//            row-shifted conv taps, but cp.async.bulk.tensor faults -- "illegal instruction" -- when the innermost
+//            coordinate is not a multiple of 16 bytes, measured on B200; the shifted copies are made by the transpose.)
+//   grid.z = K slices of kb_per_slice 32-wide K blocks each (use GEMM_EPI_ATOMIC when > 1)
+struct GemmArgs {
+  int M, N, K, terms;
+  float* C;
+  int64_t ldc;
+  const float* bias;
+  int m_tiles, a_batch_rows;
+  int64_t c_batch_stride;
+  int kb_per_slice;
+};
 
 template <int BN_>
 struct GemmTc {
@@ -64,19 +80,21 @@ __global__ void k_split_bf16(const float* __restrict__ src, int64_t rows, int co
   }
 }
 
-// src fp32 [R][C] (row pitch ld_src) -> hi, lo bf16 [C][ld_dst] = the transpose (ld_dst even, >= R rounded up to 2).
+// src fp32 [R][C] (row pitch ld_src) -> hi, lo bf16 [C][ld_dst]: dst[c][r] = src[r + row_shift][c] (zero outside [0, R)),
+// i.e. the transpose, optionally of the row-shifted matrix (ld_dst even, >= R rounded up to 2).
 // grid (ceil(C/32), ceil(R/64)), block (32, 8): 64 x 32 tile through shared memory, paired bf16 stores.
 __global__ void k_split_transpose_bf16(const float* __restrict__ src, int64_t R, int C, int64_t ld_src,
-                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t ld_dst) {
+                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t ld_dst,
+                                       int row_shift) {
   __shared__ float tile[64][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int64_t r0 = (int64_t)blockIdx.y * 64;
   const int c0 = blockIdx.x * 32;
 #pragma unroll
   for (int rr = 0; rr < 64; rr += 8) {
-    const int64_t r = r0 + rr + ty;
+    const int64_t r = r0 + rr + ty + row_shift;
     const int c = c0 + tx;
-    tile[rr + ty][tx] = (r < R && c < C) ? src[r * ld_src + c] : 0.f;
+    tile[rr + ty][tx] = (r >= 0 && r < R && c < C) ? src[r * ld_src + c] : 0.f;
   }
   __syncthreads();
 #pragma unroll
@@ -97,8 +115,7 @@ __global__ void k_split_transpose_bf16(const float* __restrict__ src, int64_t R,
 template <int BN, bool CHUNKED, int EPI>
 __global__ void __launch_bounds__(GemmTc<BN>::THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, int M, int N, int K,
-          int terms, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias) {
+          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const GemmArgs g) {
   using G = GemmTc<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -110,10 +127,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * G::BM, n0 = blockIdx.x * BN;
-  const int nkb = (K + G::BK - 1) / G::BK;
+  const int M = g.M, N = g.N;
+  const int batch = blockIdx.y / g.m_tiles;
+  const int m0 = (blockIdx.y - batch * g.m_tiles) * G::BM, n0 = blockIdx.x * BN;
+  const int am0 = m0 + batch * g.a_batch_rows;  // row of this tile in the A tensor
+  float* const C = g.C + batch * g.c_batch_stride;
+  const int64_t ldc = g.ldc;
+  const float* const bias = g.bias;
+  const int kb_begin = blockIdx.z * g.kb_per_slice;
+  const int kb_stop = min((g.K + G::BK - 1) / G::BK, kb_begin + g.kb_per_slice);
+  const int nkb = kb_stop - kb_begin;  // K blocks of this CTA's slice
+  if (nkb <= 0) return;                // (uniform per CTA; the host never launches empty slices)
   const int nchunks = CHUNKED ? (nkb + G::KCH_BLOCKS - 1) / G::KCH_BLOCKS : 1;
-  const bool split = terms == 3;
+  const bool split = g.terms == 3;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_b_hi);
@@ -137,11 +163,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* st = smem + s * G::STAGE_BYTES;
         mbar_arrive_expect_tx(&full[s], bytes);
-        const int k0 = kb * G::BK;
-        tma_load_2d(st, &map_a_hi, &full[s], k0, m0);
+        const int k0 = (kb_begin + kb) * G::BK;
+        tma_load_2d(st, &map_a_hi, &full[s], k0, am0);
         tma_load_2d(st + 2 * G::A_BYTES, &map_b_hi, &full[s], k0, n0);
         if (split) {
-          tma_load_2d(st + G::A_BYTES, &map_a_lo, &full[s], k0, m0);
+          tma_load_2d(st + G::A_BYTES, &map_a_lo, &full[s], k0, am0);
           tma_load_2d(st + 2 * G::A_BYTES + G::B_BYTES, &map_b_lo, &full[s], k0, n0);
         }
       }
@@ -203,7 +229,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
           const float4 p = *reinterpret_cast<const float4*>(crow + cc + j);
           o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
         }
-        *reinterpret_cast<float4*>(crow + cc + j) = o;
+        if (EPI == GEMM_EPI_ATOMIC) {
+          atomicAdd(crow + cc + j, o.x); atomicAdd(crow + cc + j + 1, o.y);
+          atomicAdd(crow + cc + j + 2, o.z); atomicAdd(crow + cc + j + 3, o.w);
+        } else {
+          *reinterpret_cast<float4*>(crow + cc + j) = o;
+        }
       }
     };
     if (CHUNKED) {

@@ -27,6 +27,10 @@ struct TrainWork {
   // transposed operands of the FC5 / head weight gradients: d4^T [336][ldt], h5^T [168][ldt], [g5 | dlog]^T [184][ldt]
   uint16_t *d4t = nullptr, *h5t = nullptr, *gct = nullptr;
   float* tmp5 = nullptr;  // [336][184] = d4^T . [g5 | dlog]
+  // conv weight gradients on tcgen05: transposed (in, g) of one conv layer, row pitch ldr = cap * 30; tmpw [KH][4 CIN][192]
+  uint16_t *cta = nullptr, *ctb = nullptr;
+  int64_t ldr = 0;
+  float* tmpw = nullptr;
   int64_t ldt = 0;
   uint16_t* all16 = nullptr;
 };
@@ -466,6 +470,22 @@ k_conv_wgrad(const float* __restrict__ in, const float* __restrict__ g, int GROW
   for (int i = 0; i < TC; ++i)
 #pragma unroll
     for (int j = 0; j < TO; ++j) atomicAdd(dW + ((kh * 4 + kw) * CIN + c0 + i) * COUT + o0 + j, acc[i][j]);
+}
+
+// ---- taps of the tensor-core conv weight gradient: tmpw[kh][w' * CIN + c][w * COUT + co] (row pitch 192) holds every
+//      (w', w) product; dW[kh][kw][c][co] += sum over w of the entries with w' = w + kw - 1 in [0, 3]
+template <int CIN, int COUT, int KH>
+__global__ void k_scatter_conv_wgrad(const float* __restrict__ tmpw, float* __restrict__ dW) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= KH * 4 * CIN * COUT) return;
+  const int co = i % COUT, c = (i / COUT) % CIN, kw = (i / (COUT * CIN)) % 4, kh = i / (COUT * CIN * 4);
+  float a = 0.f;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const int wp = w + kw - 1;
+    if (wp >= 0 && wp < 4) a += tmpw[((int64_t)kh * 4 * CIN + wp * CIN + c) * 192 + w * COUT + co];
+  }
+  dW[i] += a;
 }
 
 // ---- sum of squares (for lossL2 = lambda * sum 0.5 ||kernel||^2, tf.nn.l2_loss)
