@@ -32,10 +32,16 @@ namespace tc {
 // RPS  rows per site of the input layout      HOUT  conv output rows per site (stored row r -> h = r % RPS)
 // ORPS rows per site of the output layout     OR0   output row of pooled row 0 (1 if the consumer needs a zero row on top)
 // OUTF32 = true: the epilogue stores fp32 [site][ORPS][4*COUT] (consumer is a SIMT kernel) instead of fp16 hi/lo planes
-template <int RPS_, int KH_, int CIN_, int COUT_, int HOUT_, int POOL_, int ORPS_, int OR0_, int STAGES_, bool OUTF32_ = false>
+// PADL  left SAME padding in W: 1 for the forward convs, 2 for the data-gradient convs (flipped kernel), so that input
+//       column w' feeds output columns w in [w' - (3 - PADL), w' + PADL] through tap kw = w' - w + PADL
+// ACT   = false: the epilogue stores acc * inv_scale (no bias, no SELU) -- data gradients
+// BF16  = true: operands are split bf16 (fp32's exponent range, for gradients) instead of split fp16
+template <int RPS_, int KH_, int CIN_, int COUT_, int HOUT_, int POOL_, int ORPS_, int OR0_, int STAGES_, bool OUTF32_ = false,
+          int PADL_ = 1, bool ACT_ = true, bool BF16_ = false>
 struct ConvTcCfg {
   static constexpr int RPS = RPS_, KH = KH_, CIN = CIN_, COUT = COUT_, HOUT = HOUT_, POOL = POOL_, ORPS = ORPS_, OR0 = OR0_;
-  static constexpr bool OUT_F32 = OUTF32_;
+  static constexpr bool OUT_F32 = OUTF32_, ACT = ACT_, BF16 = BF16_;
+  static constexpr int PADL = PADL_;
   static constexpr int HPOOL = HOUT - POOL + 1, NOUT = 4 * COUT, KROW = 4 * CIN;
   static constexpr int QROWS = 32, QSTEP = 33 - POOL, TILE_STEP = 4 * QSTEP;
   static constexpr int BK = CIN, STAGES = STAGES_, STEPS = KH * 4;
@@ -48,12 +54,16 @@ struct ConvTcCfg {
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int TMEM_COLS = 512;
   static constexpr uint32_t SBO = 8 * ROW_BYTES;
-  static constexpr uint32_t LAYOUT = ROW_BYTES == 64 ? 4 : 6;   // SWIZZLE_64B / SWIZZLE_32B
+  static constexpr uint32_t LAYOUT = ROW_BYTES == 128 ? 2 : (ROW_BYTES == 64 ? 4 : 6);  // SWIZZLE_128B / 64B / 32B
   static constexpr int B_ROWS_TOTAL = KH * NOUT;                // B tensor rows: [kh][w][co]
-  static_assert(CIN == 16 || CIN == 32, "K-slice must be one or two UMMA K-steps");
+  static_assert(CIN == 16 || CIN == 32 || CIN == 64, "K-slice = one swizzle-atom row of 1, 2 or 4 UMMA K-steps");
+  static_assert(PADL == 1 || PADL == 2, "taps kw = w' - w + PADL");
   static_assert(COUT % 16 == 0 && NOUT <= 256, "UMMA N constraints");
-  __host__ __device__ static constexpr int wlo(int wp) { return wp - 2 < 0 ? 0 : wp - 2; }
-  __host__ __device__ static constexpr int whi(int wp) { return wp + 1 > 3 ? 3 : wp + 1; }
+  __host__ __device__ static constexpr int wlo(int wp) { return wp - (3 - PADL) < 0 ? 0 : wp - (3 - PADL); }
+  __host__ __device__ static constexpr int whi(int wp) { return wp + PADL > 3 ? 3 : wp + PADL; }
+  // order in which a tile walks the input columns: the one that feeds all four output columns first (its MMAs
+  // initialise the whole accumulator), then the rest in ascending order
+  __host__ __device__ static constexpr int wp_of(int i) { return i == 0 ? 3 - PADL : (i <= 3 - PADL ? i - 1 : i); }
 };
 
 using Conv2Tc = ConvTcCfg<30, 2, 16, 32, 29, 4, 28, 1, 6>;  // p1 [site][30][64]  -> p2 [site][28][128] (rows 1..26)
@@ -86,6 +96,24 @@ __global__ void k_prep_conv_weights(const float* __restrict__ w, const unsigned 
   split_f16(v, hi, lo);
   b_hi[i] = hi;
   b_lo[i] = lo;
+}
+
+// Training path: W [KH][4][CREAL][COUT] fp32 (HWIO; for a data-gradient conv the flipped kernel of k_flip_conv_weights)
+// -> B [kh][w][co][(w', c)], c < CIN with zero padding for c >= CREAL, tap kw = w' - w + PADL, as split bf16 (unscaled).
+template <class F, int CREAL>
+__global__ void k_prep_conv_weights_bf16(const float* __restrict__ w, __nv_bfloat16* __restrict__ b_hi,
+                                         __nv_bfloat16* __restrict__ b_lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over B_ROWS_TOTAL * KROW
+  if (i >= F::B_ROWS_TOTAL * F::KROW) return;
+  const int k = i % F::KROW, row = i / F::KROW;
+  const int kh = row / F::NOUT, n = row % F::NOUT;
+  const int wo = n / F::COUT, co = n % F::COUT, wp = k / F::CIN, c = k % F::CIN;
+  const int kw = wp - wo + F::PADL;
+  float v = 0.f;
+  if (kw >= 0 && kw <= 3 && c < CREAL) v = w[((kh * 4 + kw) * CREAL + c) * F::COUT + co];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  b_hi[i] = hi;
+  b_lo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
 // CL2 = true: launched as clusters of 2 CTAs.  Both CTAs walk the same (kh, w') stage sequence on their own tiles;

@@ -70,7 +70,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
   static_assert((2 * S::SA + 2 * S::SB + 4) * 8 + 8 <= 512, "barrier block");
 
   __shared__ float bias_s[F::COUT];
-  if (threadIdx.x < F::COUT) bias_s[threadIdx.x] = bias[threadIdx.x];
+  if (threadIdx.x < F::COUT) bias_s[threadIdx.x] = F::ACT ? bias[threadIdx.x] : 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t total_rows = n * F::RPS;
   const int64_t ntiles = (total_rows + S::TILE_STEP - 1) / S::TILE_STEP;
@@ -87,8 +87,8 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // w' order inside a tile: 2 first (its MMAs cover all NOUT columns and initialise the accumulator), then 0, 1, 3
-  auto wp_of = [](int i) { return i == 0 ? 2 : (i < 3 ? i - 1 : 3); };
+  // w' order inside a tile: the column whose MMAs cover all NOUT output columns first (initialises the accumulator)
+  auto wp_of = [](int i) { return F::wp_of(i); };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -130,7 +130,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
         for (int i = 0; i < 4; ++i, ++ia) {
           const int wp = wp_of(i);
           const int wl = F::wlo(wp), nb = F::whi(wp) - wl + 1;
-          const uint32_t idesc = umma_idesc_f16(128, nb * F::COUT);
+          const uint32_t idesc = F::BF16 ? umma_idesc_bf16(128, nb * F::COUT) : umma_idesc_f16(128, nb * F::COUT);
           const uint32_t tcol = tmem_base + buf * 256 + wl * F::COUT;
           const int sa = ia % S::SA;
           mbar_wait(&fullA[sa], (ia / S::SA) & 1);
@@ -230,7 +230,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
       for (int cc = 0; cc < F::COUT; cc += 16) {
         float pv[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pv[j] = selu_f(fmaf(raw[cc + j], isc, bias_s[cc + j]));
+        for (int j = 0; j < 16; ++j) pv[j] = F::ACT ? selu_f(fmaf(raw[cc + j], isc, bias_s[cc + j])) : raw[cc + j] * isc;
         if (F::OUT_F32) {
           if (store) {  // 64 B per thread: two full-sector 256-bit stores
             float* d = reinterpret_cast<float*>(out_hi) + o + cc;

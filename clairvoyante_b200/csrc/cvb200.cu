@@ -1046,7 +1046,7 @@ static int ensure_train_work(cvb_model* m) {
       {&w->g4, c * 336}, {&w->g4b, c * 336}, {&w->gp3, c * 24 * 192}, {&w->g3p, c * 28 * 192}, {&w->gp2, c * 26 * 128},
       {&w->g2p, c * 30 * 128}, {&w->gp1, c * 29 * 64}, {&w->g1, c * 33 * 64}, {&w->w3t, 3 * 4 * 48 * 32},
       {&w->w2t, 2 * 4 * 32 * 16}, {&w->w4t, 336 * 4608}, {&w->w5t, 176 * 336}, {&w->tmpb, 336 * 16}, {&w->tmph, 168 * 16},
-      {&w->tmp5, 336 * 184}, {&w->tmpw, 3 * 128 * 192}, {&w->loss, 16}};
+      {&w->tmp5, 336 * 184}, {&w->tmpw, 3 * 128 * 192}, {&w->fsc, 16}, {&w->loss, 16}};
   int64_t total = 0;
   for (auto& it : items) total += (it.n + 63) / 64 * 64;
   CK(cudaMalloc(&w->all, (size_t)total * 4));
@@ -1060,8 +1060,14 @@ static int ensure_train_work(cvb_model* m) {
     Item16 it16[] = {{&w->p3s, 2 * c * 4608}, {&w->p3t, 2 * 4608 * c}, {&w->g4s, 2 * c * 336},
                      {&w->g4t, 2 * 336 * c},  {&w->w4s, 2 * 4608 * 336}, {&w->w4ts, 2 * 336 * 4608},
                      {&w->d4t, 2 * 336 * c},  {&w->h5t, 2 * 168 * c},    {&w->gct, 2 * 184 * c},
-                     {&w->cta, 3 * 2 * 128 * c * 30}, {&w->ctb, 2 * 192 * c * 30}};
+                     {&w->cta, 3 * 2 * 128 * c * 30}, {&w->ctb, 2 * 192 * c * 30},
+                     {&w->p1h, 2 * c * 30 * 64}, {&w->p2h, 2 * c * 28 * 128}, {&w->g3h, 2 * c * 28 * 256}, {&w->g2h, 2 * c * 30 * 128},
+                     {&w->wf2, 2 * 2 * 128 * 64}, {&w->wf3, 2 * 3 * 192 * 128}, {&w->wd2, 2 * 2 * 64 * 128},
+                     {&w->wd3, 2 * 3 * 128 * 256}};
     w->ldr = c * 30;
+    CK(cudaMalloc(&w->amax, 16));
+    const float one = 1.f;
+    CK(cudaMemcpy(w->fsc + 2, &one, 4, cudaMemcpyHostToDevice));
     int64_t t16 = 0;
     for (auto& it : it16) t16 += (it.n + 127) / 128 * 128;
     CK(cudaMalloc(&w->all16, (size_t)t16 * 2));
@@ -1114,6 +1120,7 @@ static int launch_gemm_tc(cvb_model* m, const uint16_t* a, int64_t a_plane, int6
   return 0;
 }
 static inline __nv_bfloat16* bf(uint16_t* p) { return reinterpret_cast<__nv_bfloat16*>(p); }
+static inline __half* hp(uint16_t* p) { return reinterpret_cast<__half*>(p); }
 static int split_rows_bf16(const float* src, int64_t rows, int cols, uint16_t* dst, int64_t plane, cudaStream_t st) {
   tc::k_split_bf16<<<gsz(rows * (cols / 4)), 256, 0, st>>>(src, rows, cols, cols, bf(dst), bf(dst + plane), cols);
   CK(cudaGetLastError());
@@ -1156,6 +1163,46 @@ static int launch_conv_wgrad_tc(cvb_model* m, const float* in, const float* g, i
   return 0;
 }
 
+// ---- tcgen05 convs of the training path (conv_tc_slab.cuh): POOL = 1, fp32 output, every SELU output kept ------------
+// forward (split fp16, scaled weights, bias + SELU) and data gradient (split bf16, flipped kernel, PADL = 2, no activation)
+namespace trc {
+using Conv2F = tc::ConvTcCfg<30, 2, 16, 32, 29, 1, 29, 0, 6, true>;                      // p1h [.][30][64]  -> c2 [.][29][128]
+using Conv3F = tc::ConvTcCfg<28, 3, 32, 48, 26, 1, 26, 0, 4, true>;                      // p2h [.][28][128] -> c3 [.][26][192]
+using Conv3D = tc::ConvTcCfg<28, 3, 64, 32, 26, 1, 26, 0, 4, true, 2, false, true>;      // g3h [.][28][256] -> gp2 [.][26][128]
+using Conv2D = tc::ConvTcCfg<30, 2, 32, 16, 29, 1, 29, 0, 4, true, 2, false, true>;      // g2h [.][30][128] -> gp1 [.][29][64]
+using Conv2FS = tc::ConvSlabCfg<Conv2F, 4, 8>;
+using Conv3FS = tc::ConvSlabCfg<Conv3F, 3, 6>;
+using Conv3DS = tc::ConvSlabCfg<Conv3D, 3, 3>;
+using Conv2DS = tc::ConvSlabCfg<Conv2D, 3, 6>;
+}  // namespace trc
+
+// act: hi plane [rows = nc * RPS][KROW], lo plane act_plane elements later; wts: B [KH * NOUT][KROW] hi then lo plane
+template <class F, class S>
+static int launch_train_conv(cvb_model* m, const uint16_t* act, int64_t act_plane, const uint16_t* wts, int64_t nc, const float* bias,
+                             const float* inv_scale, float* out, cudaStream_t st) {
+  const CUtensorMapSwizzle sw = F::ROW_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                    : (F::ROW_BYTES == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap ma, mb[3];
+  const uint64_t ad[3] = {(uint64_t)F::KROW, (uint64_t)(nc * F::RPS), 2};
+  const uint64_t as[2] = {(uint64_t)F::KROW * 2, (uint64_t)act_plane * 2};
+  const uint32_t ab[3] = {(uint32_t)F::BK, (uint32_t)S::SLAB_ROWS, 2};
+  if (make_map_nd(&ma, (void*)act, 3, ad, as, ab, sw)) return 1;
+  const uint64_t bd[3] = {(uint64_t)F::KROW, (uint64_t)F::B_ROWS_TOTAL, 2};
+  const uint64_t bs[2] = {(uint64_t)F::KROW * 2, (uint64_t)F::B_ROWS_TOTAL * F::KROW * 2};
+  for (int nb = 2; nb <= 4; ++nb) {
+    const uint32_t bb[3] = {(uint32_t)F::BK, (uint32_t)(nb * F::COUT), 2};
+    if (make_map_nd(&mb[nb - 2], (void*)wts, 3, bd, bs, bb, sw)) return 1;
+  }
+  auto k = tc::k_conv_slab<F, S>;
+  CK(set_smem(k, S::SMEM_BYTES));
+  const int64_t tiles = (nc * F::RPS + S::TILE_STEP - 1) / S::TILE_STEP;
+  const int grid = (int)std::min<int64_t>(tiles, m->num_sms);
+  k<<<grid, F::THREADS, S::SMEM_BYTES, st>>>(ma, mb[0], mb[1], mb[2], nc, bias, inv_scale, reinterpret_cast<__half*>(out), nullptr, 0);
+  CK(cudaGetLastError());
+  m->launches += 1;
+  return 0;
+}
+
 // training-mode forward of one micro-chunk already resident in tw->x: keeps every SELU output
 template <class C>
 static int launch_conv_keep(cvb_model* m, const float* in, int64_t nc, const float* wg, const float* bg, float* out, bool act,
@@ -1178,9 +1225,9 @@ static int launch_conv_keep(cvb_model* m, const float* in, int64_t nc, const flo
 static int train_forward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t seed, int64_t index0, cudaStream_t st) {
   TrainWork* w = m->train;
   if (launch_conv_keep<ConvCfg<4, 8, 1, 33, 12, 8, 8>>(m, w->x, nc, m->var("conv1/kernel"), m->var("conv1/bias"), w->c1, true, st)) return 1;
-  k_pool_fwd<1><<<gsz(nc * 33 * 8), 256, 0, st>>>(w->c1, nc, 33, 32, w->p1p, 35, 1);
+  k_pool_fwd<1><<<gsz(nc * 33 * 8), 256, 0, st>>>(w->c1, nc, 33, 32, w->p1p, 35, 1, nullptr, nullptr);
   if (launch_conv_keep<ConvCfg<8, 16, 3, 33, 6, 8, 8>>(m, w->p1p, nc, m->var("conv2/kernel"), m->var("conv2/bias"), w->c2, true, st)) return 1;
-  k_pool_fwd<1><<<gsz(nc * 33 * 16), 256, 0, st>>>(w->c2, nc, 33, 64, w->p2p, 37, 2);
+  k_pool_fwd<1><<<gsz(nc * 33 * 16), 256, 0, st>>>(w->c2, nc, 33, 64, w->p2p, 37, 2, nullptr, nullptr);
   if (launch_conv_keep<ConvCfg<16, 32, 5, 33, 3, 8, 8>>(m, w->p2p, nc, m->var("conv3/kernel"), m->var("conv3/bias"), w->c3, true, st)) return 1;
   {
     using F = FcCfg<36, 9, 4, 28, 8>;
@@ -1263,6 +1310,7 @@ static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, i
   if (m->variant != CVB_V3) return train_forward_slim(m, nc, drop4, seed, index0, st);
   TrainWork* w = m->train;
   const int sms = m->num_sms;
+  const bool tcm = m->train_mode != CVB_TRAIN_FP32;
   {
     using C = ConvCfg<4, 16, 1, 33, 6, 8, 8>;
     using L = ConvLayerSmem<C, 1>;
@@ -1271,27 +1319,38 @@ static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, i
     k<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, 2 * sms), 256, L::SMEM_BYTES, st>>>(w->x, nc, m->var("conv1/kernel"),
                                                                                           m->var("conv1/bias"), w->c1, nullptr);
     CK(cudaGetLastError());
-    k_pool_fwd<5><<<gsz(nc * 29 * 16), 256, 0, st>>>(w->c1, nc, 33, 64, w->p1p, 30, 0);
+    k_pool_fwd<5><<<gsz(nc * 29 * 16), 256, 0, st>>>(w->c1, nc, 33, 64, w->p1p, 30, 0, tcm ? hp(w->p1h) : nullptr,
+                                                     tcm ? hp(w->p1h) + w->cap * 30 * 64 : nullptr);
   }
-  {
-    using C = ConvCfg<16, 32, 2, 29, 4, 8, 8>;
-    using L = ConvLayerSmem<C, 1>;
-    auto k = k_conv_layer<C, 1, 256, false, true>;
-    CK(set_smem(k, L::SMEM_BYTES));
-    k<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->p1p, nc, m->var("conv2/kernel"),
-                                                                                      m->var("conv2/bias"), w->c2, nullptr);
+  if (tcm) {
+    if (launch_train_conv<trc::Conv2F, trc::Conv2FS>(m, w->p1h, w->cap * 30 * 64, w->wf2, nc, m->var("conv2/bias"), w->fsc + 0, w->c2, st))
+      return 1;
+    k_pool_fwd<4><<<gsz(nc * 26 * 32), 256, 0, st>>>(w->c2, nc, 29, 128, w->p2p, 28, 1, hp(w->p2h), hp(w->p2h) + w->cap * 28 * 128);
+    if (launch_train_conv<trc::Conv3F, trc::Conv3FS>(m, w->p2h, w->cap * 28 * 128, w->wf3, nc, m->var("conv3/bias"), w->fsc + 1, w->c3, st))
+      return 1;
+    k_pool_fwd<3><<<gsz(nc * 24 * 48), 256, 0, st>>>(w->c3, nc, 26, 192, w->p3, 24, 0, nullptr, nullptr);
     CK(cudaGetLastError());
-    k_pool_fwd<4><<<gsz(nc * 26 * 32), 256, 0, st>>>(w->c2, nc, 29, 128, w->p2p, 28, 1);
-  }
-  {
-    using C = ConvCfg<32, 48, 3, 26, 3, 8, 8>;
-    using L = ConvLayerSmem<C, 1>;
-    auto k = k_conv_layer<C, 1, 256, false, true>;
-    CK(set_smem(k, L::SMEM_BYTES));
-    k<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->p2p, nc, m->var("conv3/kernel"),
-                                                                                      m->var("conv3/bias"), w->c3, nullptr);
-    CK(cudaGetLastError());
-    k_pool_fwd<3><<<gsz(nc * 24 * 48), 256, 0, st>>>(w->c3, nc, 26, 192, w->p3, 24, 0);
+  } else {
+    {
+      using C = ConvCfg<16, 32, 2, 29, 4, 8, 8>;
+      using L = ConvLayerSmem<C, 1>;
+      auto k = k_conv_layer<C, 1, 256, false, true>;
+      CK(set_smem(k, L::SMEM_BYTES));
+      k<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->p1p, nc, m->var("conv2/kernel"),
+                                                                                        m->var("conv2/bias"), w->c2, nullptr);
+      CK(cudaGetLastError());
+      k_pool_fwd<4><<<gsz(nc * 26 * 32), 256, 0, st>>>(w->c2, nc, 29, 128, w->p2p, 28, 1, nullptr, nullptr);
+    }
+    {
+      using C = ConvCfg<32, 48, 3, 26, 3, 8, 8>;
+      using L = ConvLayerSmem<C, 1>;
+      auto k = k_conv_layer<C, 1, 256, false, true>;
+      CK(set_smem(k, L::SMEM_BYTES));
+      k<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->p2p, nc, m->var("conv3/kernel"),
+                                                                                        m->var("conv3/bias"), w->c3, nullptr);
+      CK(cudaGetLastError());
+      k_pool_fwd<3><<<gsz(nc * 24 * 48), 256, 0, st>>>(w->c3, nc, 26, 192, w->p3, 24, 0, nullptr, nullptr);
+    }
   }
   if (m->train_mode != CVB_TRAIN_FP32) {
     // FC4 on tcgen05: p3 -> split bf16 (K-major), B = W4^T prepared once per step (train_prepare_weights)
@@ -1403,7 +1462,9 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
     CK(cudaGetLastError());
   }
   // conv3
-  k_pool_bwd_selu<3, 192, 192><<<gsz(nc * 26 * 192, 192), 192, 0, st>>>(w->gp3, w->c3, nc, 26, w->g3p, 28, 1, gvar(m, "conv3/bias"));
+  k_pool_bwd_selu<3, 192, 192, 64><<<gsz(nc * 26 * 192, 192), 192, 0, st>>>(w->gp3, w->c3, nc, 26, w->g3p, 28, 1, gvar(m, "conv3/bias"),
+                                                                            tcm ? bf(w->g3h) : nullptr,
+                                                                            tcm ? bf(w->g3h) + w->cap * 28 * 256 : nullptr);
   {
     if (tcm) {
       if (launch_conv_wgrad_tc<32, 48, 3>(m, w->p2p, w->g3p, nc * 28, gvar(m, "conv3/kernel"), st)) return 1;
@@ -1414,15 +1475,21 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
       k<<<(int)std::min<int64_t>((nc + 3) / 4, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->p2p, w->g3p, 28, 1, nc, gvar(m, "conv3/kernel"));
       CK(cudaGetLastError());
     }
-    using C = ConvCfg<48, 32, 3, 26, 3, 8, 8, 2>;
-    using L = ConvLayerSmem<C, 1>;
-    auto kd = k_conv_layer<C, 1, 256, false, false>;
-    CK(set_smem(kd, L::SMEM_BYTES));
-    kd<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->g3p, nc, w->w3t, nullptr, w->gp2, nullptr);
-    CK(cudaGetLastError());
+    if (tcm) {
+      if (launch_train_conv<trc::Conv3D, trc::Conv3DS>(m, w->g3h, w->cap * 28 * 256, w->wd3, nc, nullptr, w->fsc + 2, w->gp2, st)) return 1;
+    } else {
+      using C = ConvCfg<48, 32, 3, 26, 3, 8, 8, 2>;
+      using L = ConvLayerSmem<C, 1>;
+      auto kd = k_conv_layer<C, 1, 256, false, false>;
+      CK(set_smem(kd, L::SMEM_BYTES));
+      kd<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->g3p, nc, w->w3t, nullptr, w->gp2, nullptr);
+      CK(cudaGetLastError());
+    }
   }
   // conv2
-  k_pool_bwd_selu<4, 128, 256><<<gsz(nc * 29 * 128), 256, 0, st>>>(w->gp2, w->c2, nc, 29, w->g2p, 30, 1, gvar(m, "conv2/bias"));
+  k_pool_bwd_selu<4, 128, 256, 32><<<gsz(nc * 29 * 128), 256, 0, st>>>(w->gp2, w->c2, nc, 29, w->g2p, 30, 1, gvar(m, "conv2/bias"),
+                                                                       tcm ? bf(w->g2h) : nullptr,
+                                                                       tcm ? bf(w->g2h) + w->cap * 30 * 128 : nullptr);
   {
     if (tcm) {
       if (launch_conv_wgrad_tc<16, 32, 2>(m, w->p1p, w->g2p, nc * 30, gvar(m, "conv2/kernel"), st)) return 1;
@@ -1433,12 +1500,16 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
       k<<<(int)std::min<int64_t>((nc + 3) / 4, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->p1p, w->g2p, 30, 1, nc, gvar(m, "conv2/kernel"));
       CK(cudaGetLastError());
     }
-    using C = ConvCfg<32, 16, 2, 29, 4, 8, 8, 2>;
-    using L = ConvLayerSmem<C, 1>;
-    auto kd = k_conv_layer<C, 1, 256, false, false>;
-    CK(set_smem(kd, L::SMEM_BYTES));
-    kd<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->g2p, nc, w->w2t, nullptr, w->gp1, nullptr);
-    CK(cudaGetLastError());
+    if (tcm) {
+      if (launch_train_conv<trc::Conv2D, trc::Conv2DS>(m, w->g2h, w->cap * 30 * 128, w->wd2, nc, nullptr, w->fsc + 2, w->gp1, st)) return 1;
+    } else {
+      using C = ConvCfg<32, 16, 2, 29, 4, 8, 8, 2>;
+      using L = ConvLayerSmem<C, 1>;
+      auto kd = k_conv_layer<C, 1, 256, false, false>;
+      CK(set_smem(kd, L::SMEM_BYTES));
+      kd<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->g2p, nc, w->w2t, nullptr, w->gp1, nullptr);
+      CK(cudaGetLastError());
+    }
   }
   // conv1 (no data gradient needed)
   k_pool_bwd_selu<5, 64, 256><<<gsz(nc * 33 * 64), 256, 0, st>>>(w->gp1, w->c1, nc, 33, w->g1, 33, 0, gvar(m, "conv1/bias"));
@@ -1461,7 +1532,18 @@ static int train_prepare_weights(cvb_model* m, cudaStream_t st, bool backward) {
   if (m->train_mode != CVB_TRAIN_FP32) {  // the forward pass (getLoss included) reads W4^T, the data gradient W4
     if (split_transpose_bf16(m->var("fc4/kernel"), 4608, 336, 336, w->w4ts, 336 * 4608, 4608, st)) return 1;
     if (backward && split_rows_bf16(m->var("fc4/kernel"), 4608, 336, w->w4s, 4608 * 336, st)) return 1;
-    m->launches += backward ? 2 : 1;
+    // forward conv2 / conv3 operands: rearranged, power-of-two scaled split-fp16 weights (as on the inference path)
+    using F2 = trc::Conv2F;
+    using F3 = trc::Conv3F;
+    CK(cudaMemsetAsync(w->amax, 0, 8, st));
+    tc::k_absmax<<<16, 256, 0, st>>>(m->var("conv2/kernel"), 2 * 4 * 16 * 32, w->amax + 0);
+    tc::k_absmax<<<64, 256, 0, st>>>(m->var("conv3/kernel"), 3 * 4 * 32 * 48, w->amax + 1);
+    tc::k_prep_conv_weights<F2><<<(F2::B_ROWS_TOTAL * F2::KROW + 255) / 256, 256, 0, st>>>(
+        m->var("conv2/kernel"), w->amax + 0, hp(w->wf2), hp(w->wf2) + F2::B_ROWS_TOTAL * F2::KROW, w->fsc + 0);
+    tc::k_prep_conv_weights<F3><<<(F3::B_ROWS_TOTAL * F3::KROW + 255) / 256, 256, 0, st>>>(
+        m->var("conv3/kernel"), w->amax + 1, hp(w->wf3), hp(w->wf3) + F3::B_ROWS_TOTAL * F3::KROW, w->fsc + 1);
+    CK(cudaGetLastError());
+    m->launches += backward ? 6 : 5;
   } else if (backward) {
     k_transpose<<<dim3((336 + 31) / 32, 4608 / 32), dim3(32, 8), 0, st>>>(m->var("fc4/kernel"), 4608, 336, w->w4t);
     m->launches += 1;
@@ -1470,6 +1552,15 @@ static int train_prepare_weights(cvb_model* m, cudaStream_t st, bool backward) {
   k_flip_conv_weights<<<(3 * 4 * 32 * 48 + 255) / 256, 256, 0, st>>>(m->var("conv3/kernel"), 3, 32, 48, w->w3t);
   k_flip_conv_weights<<<(2 * 4 * 16 * 32 + 255) / 256, 256, 0, st>>>(m->var("conv2/kernel"), 2, 16, 32, w->w2t);
   k_transpose<<<dim3((168 + 31) / 32, (336 + 31) / 32), dim3(32, 8), 0, st>>>(m->var("fc5/kernel"), 336, 168, w->w5t);
+  if (m->train_mode != CVB_TRAIN_FP32) {  // flipped kernels of the data-gradient convs as split-bf16 tcgen05 operands
+    using D2 = trc::Conv2D;
+    using D3 = trc::Conv3D;
+    tc::k_prep_conv_weights_bf16<D3, 48><<<(D3::B_ROWS_TOTAL * D3::KROW + 255) / 256, 256, 0, st>>>(
+        w->w3t, bf(w->wd3), bf(w->wd3) + D3::B_ROWS_TOTAL * D3::KROW);
+    tc::k_prep_conv_weights_bf16<D2, 32><<<(D2::B_ROWS_TOTAL * D2::KROW + 255) / 256, 256, 0, st>>>(
+        w->w2t, bf(w->wd2), bf(w->wd2) + D2::B_ROWS_TOTAL * D2::KROW);
+    m->launches += 2;
+  }
   CK(cudaGetLastError());
   m->launches += 3;
   return 0;

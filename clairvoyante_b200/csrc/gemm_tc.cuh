@@ -53,9 +53,6 @@ struct GemmTc {
   static_assert(B_BYTES % 512 == 0, "operand tiles start on a swizzle atom");
 };
 
-// kind::f16 instruction descriptor with bf16 A/B (a_format = b_format = 1), fp32 accumulate
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) { return umma_idesc_f16(M, N) | (1u << 7) | (1u << 10); }
-
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));

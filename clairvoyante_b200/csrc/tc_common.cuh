@@ -5,6 +5,7 @@
 // code is used).
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -131,6 +132,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with bf16 A/B (a_format = b_format = 1)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) { return umma_idesc_f16(M, N) | (1u << 7) | (1u << 10); }
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues for the CTA
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

@@ -8,6 +8,7 @@
 // ACT=false and pad-left 2; weight gradients are k_conv_wgrad (convs) and k_gemm_tn (dense layers).
 #pragma once
 #include "conv_simt.cuh"
+#include "tc_common.cuh"
 
 namespace cvb {
 
@@ -31,6 +32,13 @@ struct TrainWork {
   uint16_t *cta = nullptr, *ctb = nullptr;
   int64_t ldr = 0;
   float* tmpw = nullptr;
+  // tcgen05 forward / data-gradient convs (conv_tc_slab.cuh): activations as split planes [hi | lo] in the consumer's padded
+  // row layout -- p1h [cap*30][64], p2h [cap*28][128] fp16; g3h [cap*28][4*64] (48 -> 64 channels), g2h [cap*30][128] bf16 --
+  // and rearranged weights: wf2 / wf3 forward (fp16, scaled: inv scales in fsc[0..1]), wd2 / wd3 flipped kernels (bf16)
+  uint16_t *p1h = nullptr, *p2h = nullptr, *g3h = nullptr, *g2h = nullptr, *wf2 = nullptr, *wf3 = nullptr, *wd2 = nullptr,
+           *wd3 = nullptr;
+  float* fsc = nullptr;          // [0] conv2, [1] conv3 forward inverse weight scales, [2] = 1.0f
+  unsigned int* amax = nullptr;  // [2] |w|max scratch
   int64_t ldt = 0;
   uint16_t* all16 = nullptr;
 };
@@ -60,9 +68,12 @@ static inline DropConst drop_const(float rate) {
   return d;
 }
 
-// ---- (P,1) VALID max-pool over rows: in [n][H][C] -> out [n][OROWS][C] at rows OR0..OR0+H-P  (C multiple of 4)
+// ---- (P,1) VALID max-pool over rows: in [n][H][C] -> out [n][OROWS][C] at rows OR0..OR0+H-P  (C multiple of 4);
+//      hi / lo (optional): the same values again as split-fp16 planes in the same layout = the activation operand of the
+//      next layer's tcgen05 conv kernel (conv_tc_slab.cuh)
 template <int P>
-__global__ void k_pool_fwd(const float* __restrict__ in, int64_t n, int H, int C, float* __restrict__ out, int OROWS, int OR0) {
+__global__ void k_pool_fwd(const float* __restrict__ in, int64_t n, int H, int C, float* __restrict__ out, int OROWS, int OR0,
+                           __half* __restrict__ hi, __half* __restrict__ lo) {
   const int HP = H - P + 1, C4 = C / 4;
   const int64_t total = n * HP * C4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -74,7 +85,15 @@ __global__ void k_pool_fwd(const float* __restrict__ in, int64_t n, int H, int C
     float4 v = src[0];
 #pragma unroll
     for (int j = 1; j < P; ++j) v = max4(v, src[j * C4]);
-    reinterpret_cast<float4*>(out + (s * OROWS + OR0 + h) * C)[q] = v;
+    const int64_t o = (s * OROWS + OR0 + h) * C + q * 4;
+    *reinterpret_cast<float4*>(out + o) = v;
+    if (hi) {
+      __half2 h2[2], l2[2];
+      tc::split_f16x2(v.x, v.y, h2[0], l2[0]);
+      tc::split_f16x2(v.z, v.w, h2[1], l2[1]);
+      *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h2);
+      *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l2);
+    }
   }
 }
 
@@ -83,10 +102,13 @@ __global__ void k_pool_fwd(const float* __restrict__ in, int64_t n, int H, int C
 // written to out [n][OROWS][C] at row OR0 + h (the padded layout the data-gradient conv reads), and the conv's bias
 // gradient  bias_grad[k % COUT] += sum over (s, h, w) of dpre  (C = 4 * COUT; one atomicAdd per channel per CTA).
 // Thread = one channel k of one row; a CTA walks rows (s, h) with stride, THREADS / C rows at a time.
-template <int P, int C, int THREADS>
+// hi / lo (optional): dpre again as split-bf16 planes [n][OROWS][4][CP] (channels padded from C / 4 to CP with zeros that
+// are never written) = the activation operand of the tcgen05 data-gradient conv.
+template <int P, int C, int THREADS, int CP = C / 4>
 __global__ void __launch_bounds__(THREADS)
 k_pool_bwd_selu(const float* __restrict__ dp, const float* __restrict__ c, int64_t n, int H, float* __restrict__ out, int OROWS,
-                int OR0, float* __restrict__ bias_grad) {
+                int OR0, float* __restrict__ bias_grad, __nv_bfloat16* __restrict__ hi = nullptr,
+                __nv_bfloat16* __restrict__ lo = nullptr) {
   static_assert(THREADS % C == 0 && C % 4 == 0, "whole rows per pass");
   constexpr int RPI = THREADS / C, COUT = C / 4;
   const int HP = H - P + 1;
@@ -119,6 +141,12 @@ k_pool_bwd_selu(const float* __restrict__ dp, const float* __restrict__ c, int64
     }
     g *= selu_grad_from_out(ch);
     out[(s * OROWS + OR0 + h) * C + k] = g;
+    if (hi) {
+      const int64_t o = ((s * OROWS + OR0 + h) * 4 + k / COUT) * CP + k % COUT;
+      const __nv_bfloat16 gh = __float2bfloat16_rn(g);
+      hi[o] = gh;
+      lo[o] = __float2bfloat16_rn(g - __bfloat162float(gh));
+    }
     bsum += g;
   }
   __shared__ float red[THREADS];
