@@ -1017,12 +1017,16 @@ static int ensure_train_work(cvb_model* m) {
   if (m->train) return 0;
   TrainWork* w = new TrainWork();
   w->cap = TRAIN_CHUNK;
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreateWithFlags(&w->ev_up[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&w->ev_done[i], cudaEventDisableTiming));
+  }
   const int64_t c = w->cap;
   struct Item { float** p; int64_t n; };
   // v3_slim (clairvoyante_v3_slim.py:54-118): no pools, so the "pooled + padded" buffers are just the conv outputs moved
   // into the next conv's zero-padded row layout (35 rows for KH=3, 37 for KH=5) and p3 is c3 itself
   Item slim_items[] = {
-      {&w->x, c * 528}, {&w->y, c * 16}, {&w->c1, c * 33 * 32}, {&w->p1p, c * 35 * 32}, {&w->c2, c * 33 * 64},
+      {&w->xs[0], c * 528}, {&w->ys[0], c * 16}, {&w->xs[1], c * 528}, {&w->ys[1], c * 16}, {&w->c1, c * 33 * 32}, {&w->p1p, c * 35 * 32}, {&w->c2, c * 33 * 64},
       {&w->p2p, c * 37 * 64}, {&w->c3, c * 33 * 128}, {&w->h4, c * 36}, {&w->d4, c * 36},
       {&w->h5, c * 24}, {&w->logits, c * 16}, {&w->out16, c * 16}, {&w->dlog, c * 16}, {&w->g5, c * 24},
       {&w->g4, c * 36}, {&w->g4b, c * 36}, {&w->gp3, c * 33 * 128}, {&w->g3p, c * 37 * 128}, {&w->gp2, c * 33 * 64},
@@ -1040,7 +1044,7 @@ static int ensure_train_work(cvb_model* m) {
     return 0;
   }
   Item items[] = {
-      {&w->x, c * 528}, {&w->y, c * 16}, {&w->c1, c * 33 * 64}, {&w->p1p, c * 30 * 64}, {&w->c2, c * 29 * 128},
+      {&w->xs[0], c * 528}, {&w->ys[0], c * 16}, {&w->xs[1], c * 528}, {&w->ys[1], c * 16}, {&w->c1, c * 33 * 64}, {&w->p1p, c * 30 * 64}, {&w->c2, c * 29 * 128},
       {&w->p2p, c * 28 * 128}, {&w->c3, c * 26 * 192}, {&w->p3, c * 24 * 192}, {&w->h4, c * 336}, {&w->d4, c * 336},
       {&w->h5, c * 168}, {&w->logits, c * 16}, {&w->out16, c * 16}, {&w->dlog, c * 16}, {&w->g5, c * 176},
       {&w->g4, c * 336}, {&w->g4b, c * 336}, {&w->gp3, c * 24 * 192}, {&w->g3p, c * 28 * 192}, {&w->gp2, c * 26 * 128},
@@ -1279,7 +1283,7 @@ static int train_backward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t s
   k_colsum<<<dim3(2, 32), 256, 0, st>>>(w->g4, nc, 36, 36, gvar(m, "fc4/bias"));
   k_dense_bwd_small<<<gsz(nc * 4224), 256, 0, st>>>(w->g4, 36, 36, m->var("fc4/kernel"), 4224, w->gp3, 4224, nc);
   // conv3 (5x4, 16 -> 32)
-  k_pool_bwd_selu<1, 128, 256><<<gsz(nc * 33 * 128), 256, 0, st>>>(w->gp3, w->c3, nc, 33, w->g3p, 37, 2, gvar(m, "conv3/bias"));
+  k_pool_bwd_selu<1, 128, 256><<<gsz(nc * 33 * 32), 256, 0, st>>>(w->gp3, w->c3, nc, 33, w->g3p, 37, 2, gvar(m, "conv3/bias"));
   {
     using W = WgradCfg<16, 32, 5, 33, 4, 8, 4>;
     auto k = k_conv_wgrad<16, 32, 5, 33, 4, 8, 4>;
@@ -1289,7 +1293,7 @@ static int train_backward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t s
     if (launch_conv_keep<ConvCfg<32, 16, 5, 33, 3, 8, 8, 2>>(m, w->g3p, nc, w->w3t, nullptr, w->gp2, false, st)) return 1;
   }
   // conv2 (3x4, 8 -> 16)
-  k_pool_bwd_selu<1, 64, 256><<<gsz(nc * 33 * 64), 256, 0, st>>>(w->gp2, w->c2, nc, 33, w->g2p, 35, 1, gvar(m, "conv2/bias"));
+  k_pool_bwd_selu<1, 64, 256><<<gsz(nc * 33 * 16), 256, 0, st>>>(w->gp2, w->c2, nc, 33, w->g2p, 35, 1, gvar(m, "conv2/bias"));
   {
     using W = WgradCfg<8, 16, 3, 33, 4, 4, 4>;
     auto k = k_conv_wgrad<8, 16, 3, 33, 4, 4, 4>;
@@ -1299,7 +1303,7 @@ static int train_backward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t s
     if (launch_conv_keep<ConvCfg<16, 8, 3, 33, 6, 8, 8, 2>>(m, w->g2p, nc, w->w2t, nullptr, w->gp1, false, st)) return 1;
   }
   // conv1 (1x4, 4 -> 8)
-  k_pool_bwd_selu<1, 32, 256><<<gsz(nc * 33 * 32), 256, 0, st>>>(w->gp1, w->c1, nc, 33, w->g1, 33, 0, gvar(m, "conv1/bias"));
+  k_pool_bwd_selu<1, 32, 256><<<gsz(nc * 33 * 8), 256, 0, st>>>(w->gp1, w->c1, nc, 33, w->g1, 33, 0, gvar(m, "conv1/bias"));
   k_conv1_wgrad<8, 4><<<(int)std::min<int64_t>((nc + 3) / 4, 4 * sms), 128, 0, st>>>(w->x, w->g1, nc, gvar(m, "conv1/kernel"));
   CK(cudaGetLastError());
   m->launches += 24;
@@ -1462,7 +1466,7 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
     CK(cudaGetLastError());
   }
   // conv3
-  k_pool_bwd_selu<3, 192, 192, 64><<<gsz(nc * 26 * 192, 192), 192, 0, st>>>(w->gp3, w->c3, nc, 26, w->g3p, 28, 1, gvar(m, "conv3/bias"),
+  k_pool_bwd_selu<3, 192, 192, 64><<<gsz(nc * 26 * 48, 192), 192, 0, st>>>(w->gp3, w->c3, nc, 26, w->g3p, 28, 1, gvar(m, "conv3/bias"),
                                                                             tcm ? bf(w->g3h) : nullptr,
                                                                             tcm ? bf(w->g3h) + w->cap * 28 * 256 : nullptr);
   {
@@ -1487,7 +1491,7 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
     }
   }
   // conv2
-  k_pool_bwd_selu<4, 128, 256, 32><<<gsz(nc * 29 * 128), 256, 0, st>>>(w->gp2, w->c2, nc, 29, w->g2p, 30, 1, gvar(m, "conv2/bias"),
+  k_pool_bwd_selu<4, 128, 256, 32><<<gsz(nc * 29 * 32), 256, 0, st>>>(w->gp2, w->c2, nc, 29, w->g2p, 30, 1, gvar(m, "conv2/bias"),
                                                                        tcm ? bf(w->g2h) : nullptr,
                                                                        tcm ? bf(w->g2h) + w->cap * 30 * 128 : nullptr);
   {
@@ -1512,7 +1516,7 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
     }
   }
   // conv1 (no data gradient needed)
-  k_pool_bwd_selu<5, 64, 256><<<gsz(nc * 33 * 64), 256, 0, st>>>(w->gp1, w->c1, nc, 33, w->g1, 33, 0, gvar(m, "conv1/bias"));
+  k_pool_bwd_selu<5, 64, 256><<<gsz(nc * 33 * 16), 256, 0, st>>>(w->gp1, w->c1, nc, 33, w->g1, 33, 0, gvar(m, "conv1/bias"));
   k_conv1_wgrad<16, 4><<<(int)std::min<int64_t>((nc + 3) / 4, 4 * sms), 256, 0, st>>>(w->x, w->g1, nc, gvar(m, "conv1/kernel"));
   CK(cudaGetLastError());
   m->launches += 24;
@@ -1574,16 +1578,26 @@ static int train_pass(cvb_model* m, const float* x, const float* y, int64_t n, f
   CK(cudaMemsetAsync(w->loss, 0, 16 * 4, st));
   if (backward) CK(cudaMemsetAsync(m->d_grad, 0, (size_t)(m->nparams + 16) * 4, st));
   if (train_prepare_weights(m, st, backward)) return 1;
-  for (int64_t s0 = 0; s0 < n; s0 += w->cap) {
+  // micro-chunks alternate between two upload slots: chunk c+1 is copied on the H2D stream (a pageable source blocks the
+  // host inside cudaMemcpyAsync) while chunk c's kernels, already enqueued, run on the compute stream
+  int64_t ci = 0;
+  for (int64_t s0 = 0; s0 < n; s0 += w->cap, ++ci) {
     const int64_t nc = std::min<int64_t>(w->cap, n - s0);
-    CK(cudaMemcpyAsync(w->x, x + s0 * 528, (size_t)nc * 528 * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(w->y, y + s0 * 16, (size_t)nc * 16 * 4, cudaMemcpyHostToDevice, st));
+    const int slot = (int)(ci & 1);
+    if (ci >= 2) CK(cudaStreamWaitEvent(m->s_h2d, w->ev_done[slot], 0));
+    CK(cudaMemcpyAsync(w->xs[slot], x + s0 * 528, (size_t)nc * 528 * 4, cudaMemcpyHostToDevice, m->s_h2d));
+    CK(cudaMemcpyAsync(w->ys[slot], y + s0 * 16, (size_t)nc * 16 * 4, cudaMemcpyHostToDevice, m->s_h2d));
+    CK(cudaEventRecord(w->ev_up[slot], m->s_h2d));
+    CK(cudaStreamWaitEvent(st, w->ev_up[slot], 0));
+    w->x = w->xs[slot];
+    w->y = w->ys[slot];
     const int64_t n4 = m->variant == CVB_V3 ? 336 : 36;  // dropout counter = flat index into the whole batch's FC4 output
     if (train_forward(m, nc, drop4, seed, s0 * n4, st)) return 1;
     k_loss_grad<<<gsz(nc, 128), 128, 0, st>>>(w->logits, w->out16, w->y, nc, backward ? w->dlog : nullptr, w->loss);
     CK(cudaGetLastError());
     m->launches += 1;
     if (backward && train_backward(m, nc, drop4, seed, s0 * n4, st)) return 1;
+    CK(cudaEventRecord(w->ev_done[slot], st));
   }
   return 0;
 }

@@ -12,9 +12,13 @@
 
 namespace cvb {
 
+__device__ __forceinline__ float f4c(const float4& v, int q) { return q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w)); }
+
 struct TrainWork {
   int64_t cap = 0;  // sites per micro-chunk
-  float *x = nullptr, *y = nullptr;
+  float *x = nullptr, *y = nullptr;  // the micro-chunk being computed: one of the two upload slots below
+  float *xs[2] = {nullptr, nullptr}, *ys[2] = {nullptr, nullptr};
+  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};  // slot uploaded / slot's compute finished
   float *c1 = nullptr, *p1p = nullptr, *c2 = nullptr, *p2p = nullptr, *c3 = nullptr, *p3 = nullptr;
   float *h4 = nullptr, *d4 = nullptr, *h5 = nullptr, *logits = nullptr, *out16 = nullptr;
   float *dlog = nullptr, *g5 = nullptr, *g4 = nullptr, *g4b = nullptr, *gp3 = nullptr, *g3p = nullptr, *gp2 = nullptr;
@@ -46,6 +50,10 @@ static inline void train_work_free(TrainWork* w) {
   if (!w) return;
   cudaFree(w->all);
   cudaFree(w->all16);
+  for (int i = 0; i < 2; ++i) {
+    if (w->ev_up[i]) cudaEventDestroy(w->ev_up[i]);
+    if (w->ev_done[i]) cudaEventDestroy(w->ev_done[i]);
+  }
   delete w;
 }
 
@@ -101,60 +109,72 @@ __global__ void k_pool_fwd(const float* __restrict__ in, int64_t n, int H, int C
 //   dpre[s][h][k] = selu'(c[h]) * sum_{windows j containing h whose FIRST maximum is at h} dp[s][j][k]
 // written to out [n][OROWS][C] at row OR0 + h (the padded layout the data-gradient conv reads), and the conv's bias
 // gradient  bias_grad[k % COUT] += sum over (s, h, w) of dpre  (C = 4 * COUT; one atomicAdd per channel per CTA).
-// Thread = one channel k of one row; a CTA walks rows (s, h) with stride, THREADS / C rows at a time.
 // hi / lo (optional): dpre again as split-bf16 planes [n][OROWS][4][CP] (channels padded from C / 4 to CP with zeros that
 // are never written) = the activation operand of the tcgen05 data-gradient conv.
+// Thread = four consecutive channels of one row (128-bit loads / stores); a CTA walks rows with stride, THREADS / (C/4) at a time.
 template <int P, int C, int THREADS, int CP = C / 4>
 __global__ void __launch_bounds__(THREADS)
 k_pool_bwd_selu(const float* __restrict__ dp, const float* __restrict__ c, int64_t n, int H, float* __restrict__ out, int OROWS,
                 int OR0, float* __restrict__ bias_grad, __nv_bfloat16* __restrict__ hi = nullptr,
                 __nv_bfloat16* __restrict__ lo = nullptr) {
-  static_assert(THREADS % C == 0 && C % 4 == 0, "whole rows per pass");
-  constexpr int RPI = THREADS / C, COUT = C / 4;
+  constexpr int C4 = C / 4, RPI = THREADS / C4, COUT = C / 4;
+  static_assert(THREADS % C4 == 0 && COUT % 4 == 0 && CP % 4 == 0, "whole rows per pass, float4 groups inside one column block");
   const int HP = H - P + 1;
-  const int k = threadIdx.x % C, rsub = threadIdx.x / C;
-  float bsum = 0.f;
+  const int k4 = threadIdx.x % C4, rsub = threadIdx.x / C4, k = k4 * 4;
+  float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
   const int64_t rows = n * H;
   for (int64_t row = (int64_t)blockIdx.x * RPI + rsub; row < rows; row += (int64_t)gridDim.x * RPI) {
     const int64_t s = row / H;
     const int h = (int)(row - s * H);
-    const float* cs = c + s * H * C + k;
-    float win[2 * P - 1];  // c at rows h-P+1 .. h+P-1 (out-of-range rows never take part in a valid window)
+    const float4* cs = reinterpret_cast<const float4*>(c + s * H * C) + k4;
+    float4 win[2 * P - 1];  // c at rows h-P+1 .. h+P-1 (out-of-range rows never take part in a valid window)
 #pragma unroll
     for (int e = 0; e < 2 * P - 1; ++e) {
       const int r = h - (P - 1) + e;
-      win[e] = (r >= 0 && r < H) ? cs[r * C] : 0.f;
+      win[e] = (r >= 0 && r < H) ? cs[r * C4] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float ch = win[P - 1];
-    float g = 0.f;
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int d = 0; d < P; ++d) {
       const int j = h - d;  // window start
       if (j < 0 || j >= HP) continue;
-      bool is_first_max = true;
+      const float4 dv = *(reinterpret_cast<const float4*>(dp + (s * HP + j) * C) + k4);
+      const float dvv[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
-      for (int e = 0; e < P; ++e) {
-        const float v = win[P - 1 - d + e];
-        if (e < d ? (v >= ch) : (v > ch)) is_first_max = false;  // earlier element equal or larger, later strictly larger
+      for (int q = 0; q < 4; ++q) {
+        const float ch = f4c(win[P - 1], q);
+        bool is_first_max = true;
+#pragma unroll
+        for (int e = 0; e < P; ++e) {
+          const float v = f4c(win[P - 1 - d + e], q);
+          if (e < d ? (v >= ch) : (v > ch)) is_first_max = false;  // earlier element equal or larger, later strictly larger
+        }
+        if (is_first_max) g[q] += dvv[q];
       }
-      if (is_first_max) g += dp[(s * HP + j) * C + k];
     }
-    g *= selu_grad_from_out(ch);
-    out[(s * OROWS + OR0 + h) * C + k] = g;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g[q] *= selu_grad_from_out(f4c(win[P - 1], q));
+    const int64_t orow = s * OROWS + OR0 + h;
+    *reinterpret_cast<float4*>(out + orow * C + k) = make_float4(g[0], g[1], g[2], g[3]);
     if (hi) {
-      const int64_t o = ((s * OROWS + OR0 + h) * 4 + k / COUT) * CP + k % COUT;
-      const __nv_bfloat16 gh = __float2bfloat16_rn(g);
-      hi[o] = gh;
-      lo[o] = __float2bfloat16_rn(g - __bfloat162float(gh));
+      const int64_t o = (orow * 4 + k / COUT) * CP + k % COUT;
+      __nv_bfloat16 gh[4], gl[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        gh[q] = __float2bfloat16_rn(g[q]);
+        gl[q] = __float2bfloat16_rn(g[q] - __bfloat162float(gh[q]));
+      }
+      *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(gh);
+      *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(gl);
     }
-    bsum += g;
+    bsum.x += g[0]; bsum.y += g[1]; bsum.z += g[2]; bsum.w += g[3];
   }
-  __shared__ float red[THREADS];
+  __shared__ float4 red[THREADS];
   red[threadIdx.x] = bsum;
   __syncthreads();
-  if (threadIdx.x < COUT) {
+  if (threadIdx.x < COUT) {  // channel j: component j % 4 of every thread whose float4 group is j / 4 (mod COUT / 4)
     float v = 0.f;
-    for (int i = threadIdx.x; i < THREADS; i += COUT) v += red[i];
+    for (int i = threadIdx.x / 4; i < THREADS; i += COUT / 4) v += f4c(red[i], threadIdx.x & 3);
     atomicAdd(bias_grad + threadIdx.x, v);
   }
 }
