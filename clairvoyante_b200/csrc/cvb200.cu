@@ -655,8 +655,14 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
         auto k1 = k_v3_c1<7>;
         CK(set_smem(k1, C1K::SMEM_BYTES));
         const size_t p1_halves = (size_t)m->p1_rows * 64;
-        int g1 = (int)std::min<int64_t>((n + 6) / 7, 2 * sms);
-        k1<<<g1, 256, C1K::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->d_p1, m->d_p1 + p1_halves);
+        static const bool c1_reg = !(getenv("CVB_C1_REG") && getenv("CVB_C1_REG")[0] == '0');
+        if (c1_reg) {
+          k_v3_c1_reg<<<(unsigned)((n * 16 + 127) / 128), 128, 0, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->d_p1,
+                                                                       m->d_p1 + p1_halves);
+        } else {
+          int g1 = (int)std::min<int64_t>((n + 6) / 7, 2 * sms);
+          k1<<<g1, 256, C1K::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->d_p1, m->d_p1 + p1_halves);
+        }
         CK(cudaGetLastError());
         if (prof_mark(m, st)) return 1;  // kind 0 = SIMT front (conv1+pool1 here), kind 1 = tcgen05 conv2
         using T = tc::Conv2Tc;

@@ -204,6 +204,93 @@ k_v3_c1(const float* __restrict__ x, int64_t n, const float* __restrict__ w1g, c
 }
 
 // ------------------------------------------------------------------------------------
+// k_v3_c1_reg: the same layer (clairvoyante_v3.py:54-66: conv1 1x4, 4 -> 16, SELU, pool1 (5,1)) with everything in
+// registers -- no shared memory, no barriers.  16 threads per site: thread (w, cq) owns output column w, channels
+// 4cq..4cq+3, keeps its 4 x 4 x 4 weights in registers (zero where the SAME padding cuts the tap), walks the site's 33 rows,
+// and pools with a 5-deep register ring (max of raw sums, then bias + SELU: SELU is monotonic).  The 16 x values of a row
+// are read as 4 x 128-bit read-only loads (the 16 threads of a site hit the same 64 bytes: L1 broadcast); products run as
+// packed FFMA2 (fma.rn.f32x2) over channel pairs.  Stores: 8 B per thread per plane, 128 B contiguous per site row.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__global__ void __launch_bounds__(128)
+k_v3_c1_reg(const float* __restrict__ x, int64_t n, const float* __restrict__ w1g, const float* __restrict__ b1g,
+            __half* __restrict__ p1_hi, __half* __restrict__ p1_lo) {
+  const int64_t gt = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  const int64_t site = gt >> 4;
+  const int w = (int)(gt & 15) >> 2, cq = (int)(gt & 3);
+  if ((gt >> 5) * 2 >= n) return;  // whole warp past the end
+  unsigned long long wr[4][2][4];  // [w'][channel pair][co]: {W[kw][2cp][co], W[kw][2cp+1][co]}, kw = w' - w + 1
+#pragma unroll
+  for (int wp = 0; wp < 4; ++wp) {
+    const int kw = wp - w + 1;
+    const bool valid = kw >= 0 && kw <= 3;
+#pragma unroll
+    for (int cp = 0; cp < 2; ++cp)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kwc = valid ? kw : 0;  // always a legal address: the compiler may hoist the load above the select
+        const float a = __ldg(w1g + (kwc * 4 + 2 * cp) * 16 + 4 * cq + j);
+        const float b = __ldg(w1g + (kwc * 4 + 2 * cp + 1) * 16 + 4 * cq + j);
+        wr[wp][cp][j] = valid ? pack_f32x2(a, b) : 0ull;
+      }
+  }
+  const float4 bias = __ldg(reinterpret_cast<const float4*>(b1g) + cq);
+  // stage the warp's two sites (4224 contiguous bytes) with 16-byte cp.async: every byte is in flight at once -- row-by-row
+  // loads from 16 threads per site leave too few bytes in flight to cover DRAM latency (measured: 245 GB/s)
+  __shared__ __align__(16) float xs_all[4][2 * 528];
+  float* xs = xs_all[threadIdx.x >> 5];
+  {
+    const int lane = threadIdx.x & 31;
+    const int64_t wsite0 = (gt >> 5) * 2;  // first site of this warp
+    const float* src = x + wsite0 * 528;
+    const int nchunk = (wsite0 + 1 < n) ? 264 : 132;
+    for (int c = lane; c < nchunk; c += 32) cp_async16(xs + c * 4, src + c * 4);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+  }
+  if (site >= n) return;  // odd tail: the second half-warp has no site
+  const ulonglong2* xp = reinterpret_cast<const ulonglong2*>(xs + ((gt >> 4) & 1) * 528);
+  float ring[5][4];
+  __half* ohi = p1_hi + site * (30 * 64) + w * 16 + cq * 4;
+  __half* olo = p1_lo + site * (30 * 64) + w * 16 + cq * 4;
+#pragma unroll
+  for (int h = 0; h < 33; ++h) {
+    ulonglong2 xa[4];
+#pragma unroll
+    for (int wp = 0; wp < 4; ++wp) xa[wp] = xp[h * 4 + wp];
+    unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+    for (int wp = 0; wp < 4; ++wp)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ffma2(acc[j], xa[wp].x, wr[wp][0][j]);
+        ffma2(acc[j], xa[wp].y, wr[wp][1][j]);
+      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      ring[h % 5][j] = __uint_as_float((unsigned)acc[j]) + __uint_as_float((unsigned)(acc[j] >> 32));
+    if (h >= 4) {
+      float m[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        m[j] = fmaxf(fmaxf(fmaxf(ring[0][j], ring[1][j]), fmaxf(ring[2][j], ring[3][j])), ring[4][j]);
+      const float y0 = selu_f(m[0] + bias.x), y1 = selu_f(m[1] + bias.y), y2 = selu_f(m[2] + bias.z), y3 = selu_f(m[3] + bias.w);
+      __half2 hi[2], lo[2];
+      tc::split_f16x2(y0, y1, hi[0], lo[0]);
+      tc::split_f16x2(y2, y3, hi[1], lo[1]);
+      *reinterpret_cast<uint2*>(ohi + (h - 4) * 64) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(olo + (h - 4) * 64) = *reinterpret_cast<const uint2*>(lo);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // k_slim_front (clairvoyante_v3_slim.py:54-70): x -> conv1(1x4,8)+SELU -> conv2(3x4,16)+SELU
 //   -> p2 [n][37][64] (two zero rows above and below the 33 rows: conv3 is 5x4 SAME)
 // ------------------------------------------------------------------------------------

@@ -46,6 +46,7 @@ class DataParallelTrainer(object):
 
     def __init__(self, model, dist=None):
         import torch
+        self._torch = torch
         self.m = model
         self.dist = dist
         self.rank = dist.get_rank() if dist is not None else 0
@@ -61,4 +62,8 @@ class DataParallelTrainer(object):
         self.m._train_step(X[lo:hi], Y[lo:hi], apply_update=0, seed=(seed + 0x51ED270B * self.rank) & 0xFFFFFFFFFFFFFFFF)
         if self.dist is not None and self.world > 1:
             self.dist.all_reduce(self.grad, op=self.dist.ReduceOp.SUM)
+            if self.grad.is_cuda:
+                # NCCL enqueues the reduction on torch's stream and returns; the optimizer kernels run on the library's
+                # own (non-blocking) stream, so the reduced gradients must be complete before applyAdam reads them
+                self._torch.cuda.current_stream(self.grad.device).synchronize()
         return self.m.applyAdam()

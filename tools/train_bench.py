@@ -33,8 +33,8 @@ def main():
         for _ in range(steps):
             m.getLoss(x, y)
         dl = (time.time() - t) / steps
-        out[variant] = dict(batch=n, train_ms_per_step=round(dt * 1e3, 3), train_tensors_per_s=round(n / dt),
-                            getloss_tensors_per_s=round(n / dl), last_loss=float(loss))
+        out[variant] = dict(batch=n, train_mode=m.trainMode, train_ms_per_step=round(dt * 1e3, 3),
+                            train_tensors_per_s=round(n / dt), getloss_tensors_per_s=round(n / dl), last_loss=float(loss))
         m.close()
     print(json.dumps(out))
 
