@@ -55,7 +55,9 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
   // ablate (timing experiments only, results are wrong): 1 = epilogue skips pooling/SELU/stores, 2 = no MMAs issued,
   // 4 = weight boxes are not loaded, 8 = activation slabs are not loaded, 16 = no global stores, 32 = no pooling
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned by OFFSET from the extern array, so that the compiler still knows these are shared-memory addresses (a pointer
+  // rebuilt from an integer is generic: the exchange-buffer traffic below was compiled to LD.E / ST.E)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + S::SA * S::A_SLOT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::RING_BYTES);
@@ -178,13 +180,16 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + wblk * F::COUT;
       float raw[F::COUT];
+      {
+        // all COUT columns are requested before the single wait: TMEM load latency is paid once per tile, not COUT/16 times
+        uint32_t rr[F::COUT / 16][16];
 #pragma unroll
-      for (int cc = 0; cc < F::COUT; cc += 16) {
-        uint32_t rr[16];
-        tmem_ld16(taddr + cc, rr);
+        for (int cc = 0; cc < F::COUT / 16; ++cc) tmem_ld16(taddr + cc * 16, rr[cc]);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) raw[cc + j] = __uint_as_float(rr[j]);
+        for (int cc = 0; cc < F::COUT / 16; ++cc)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) raw[cc * 16 + j] = __uint_as_float(rr[cc][j]);
       }
       tc_fence_before();
       __syncwarp();
@@ -198,32 +203,56 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
           for (int j = 0; j < F::COUT; j += 4) *reinterpret_cast<float4*>(d + j) = make_float4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
         }
         named_bar_sync(1 + wblk, 128);  // the four quadrant warps of this column block
-        const float* nx = xb + ((q + 1) & 3) * (F::POOL - 1) * F::COUT;  // rows 0..POOL-2 of the next quadrant (unused for q = 3)
+        // rows 0..POOL-2 of the next quadrant (unused for q = 3); read as 128-bit vectors, one group of 4 channels at a time,
+        // by the last POOL-1 lanes only (a scalar predicated load per channel cost 3 x COUT warp instructions per tile)
+        const float4* nx = reinterpret_cast<const float4*>(xb + ((q + 1) & 3) * (F::POOL - 1) * F::COUT);
+        constexpr int C4 = F::COUT / 4;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (F::POOL == 4) {
           // tree: m2[r] = max(v[r], v[r+1]); m4[r] = max(m2[r], m2[r+2]) -- two shuffles per channel instead of three
           // (the shuffle pipe, one warp instruction per clock per SM, is a measurable part of this epilogue)
 #pragma unroll
-          for (int j = 0; j < F::COUT; ++j) {
-            const float v = raw[j];
-            float t1 = __shfl_down_sync(0xffffffffu, v, 1);
-            if (lane == 31) t1 = nx[j];
-            const float m2 = fmaxf(v, t1);
-            float t2 = __shfl_down_sync(0xffffffffu, m2, 2);
-            if (lane >= 30) t2 = fmaxf(nx[(lane - 30) * F::COUT + j], nx[(lane - 29) * F::COUT + j]);
-            raw[j] = fmaxf(m2, t2);
-          }
-        } else
+          for (int g = 0; g < C4; ++g) {
+            const float4 n0 = lane == 31 ? nx[g] : z4;                                   // v[32] for lane 31
+            const float4 na = lane >= 30 ? nx[(lane - 30) * C4 + g] : z4;                // m2[lane + 2] = max(v[lane+2], v[lane+3])
+            const float4 nb2 = lane >= 30 ? nx[(lane - 29) * C4 + g] : z4;
+            const float n0v[4] = {n0.x, n0.y, n0.z, n0.w};
+            const float m2n[4] = {fmaxf(na.x, nb2.x), fmaxf(na.y, nb2.y), fmaxf(na.z, nb2.z), fmaxf(na.w, nb2.w)};
 #pragma unroll
-        for (int j = 0; j < F::COUT; ++j) {
-          const float v = raw[j];
-          float mx = v;
-#pragma unroll
-          for (int d = 1; d < F::POOL; ++d) {
-            float t = __shfl_down_sync(0xffffffffu, v, d);
-            if (lane + d >= 32) t = nx[(lane + d - 32) * F::COUT + j];
-            mx = fmaxf(mx, t);
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * g + e;
+              const float v = raw[j];
+              float t1 = __shfl_down_sync(0xffffffffu, v, 1);
+              if (lane == 31) t1 = n0v[e];
+              const float m2 = fmaxf(v, t1);
+              float t2 = __shfl_down_sync(0xffffffffu, m2, 2);
+              if (lane >= 30) t2 = m2n[e];
+              raw[j] = fmaxf(m2, t2);
+            }
           }
-          raw[j] = mx;  // max over rows r .. r+POOL-1 (pooling raw accumulators before SELU is exact, see conv_tc.cuh)
+        } else {
+#pragma unroll
+          for (int g = 0; g < C4; ++g) {
+            float nv[F::POOL > 1 ? F::POOL - 1 : 1][4];  // nv[d-1] = v[lane + d] for the lanes whose window leaves the quadrant
+#pragma unroll
+            for (int d = 1; d < F::POOL; ++d) {
+              const float4 t = lane + d >= 32 ? nx[(lane + d - 32) * C4 + g] : z4;
+              nv[d - 1][0] = t.x; nv[d - 1][1] = t.y; nv[d - 1][2] = t.z; nv[d - 1][3] = t.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * g + e;
+              const float v = raw[j];
+              float mx = v;
+#pragma unroll
+              for (int d = 1; d < F::POOL; ++d) {
+                float t = __shfl_down_sync(0xffffffffu, v, d);
+                if (lane + d >= 32) t = nv[d - 1][e];
+                mx = fmaxf(mx, t);
+              }
+              raw[j] = mx;  // max over rows r .. r+POOL-1 (pooling raw accumulators before SELU is exact, see conv_tc.cuh)
+            }
+          }
         }
       }
 #pragma unroll
