@@ -594,7 +594,7 @@ static int launch_conv_tc(cvb_model* m, int64_t n, cudaStream_t st, const CUtens
     const int64_t st_tiles = (n * T::RPS + S::TILE_STEP - 1) / S::TILE_STEP;
     const int g = (int)std::min<int64_t>(st_tiles, m->num_sms);
     static const int ablate = getenv("CVB_ABLATE") ? atoi(getenv("CVB_ABLATE")) : 0;  // timing experiments only
-    tc::k_conv_slab<T, S><<<g, T::THREADS, S::SMEM_BYTES, st>>>(*slab, b2, b3, b4, n, bias, inv_scale, out_hi, out_lo, ablate);
+    tc::k_conv_slab<T, S><<<g, S::THREADS, S::SMEM_BYTES, st>>>(*slab, b2, b3, b4, n, bias, inv_scale, out_hi, out_lo, ablate);
     CK(cudaGetLastError());
     return 0;
   }
@@ -1207,7 +1207,7 @@ static int launch_train_conv(cvb_model* m, const uint16_t* act, int64_t act_plan
   CK(set_smem(k, S::SMEM_BYTES));
   const int64_t tiles = (nc * F::RPS + S::TILE_STEP - 1) / S::TILE_STEP;
   const int grid = (int)std::min<int64_t>(tiles, m->num_sms);
-  k<<<grid, F::THREADS, S::SMEM_BYTES, st>>>(ma, mb[0], mb[1], mb[2], nc, bias, inv_scale, reinterpret_cast<__half*>(out), nullptr, 0);
+  k<<<grid, S::THREADS, S::SMEM_BYTES, st>>>(ma, mb[0], mb[1], mb[2], nc, bias, inv_scale, reinterpret_cast<__half*>(out), nullptr, 0);
   CK(cudaGetLastError());
   m->launches += 1;
   return 0;
