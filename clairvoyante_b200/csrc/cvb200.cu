@@ -86,6 +86,7 @@ struct cvb_model {
   bool tc_ready = false, tc_weights_dirty = true;
   CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
   CUtensorMap map_bh_hi, map_bh_lo;  // FC4 weights with NH/2-row boxes (cluster multicast)
+  CUtensorMap map_ah_hi, map_ah_lo;  // FC4 activations with BM/2-row boxes (4-CTA clusters)
   int tc_fc4_cluster = 1;
   // conv3 on tensor cores: B = rearranged conv3 weights [3*192][128], A = p2 hi/lo [sites*28][128]
   __half *d_w3b_hi = nullptr, *d_w3b_lo = nullptr;
@@ -374,11 +375,14 @@ static int tc_setup(cvb_model* m) {
   if (make_map_f16(&m->map_b_lo, m->d_w4t_lo, F::N, K, F::BK, F::NH, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   if (make_map_f16(&m->map_bh_hi, m->d_w4t_hi, F::N, K, F::BK, F::NH / 2, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   if (make_map_f16(&m->map_bh_lo, m->d_w4t_lo, F::N, K, F::BK, F::NH / 2, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-  CK(cudaFuncSetAttribute(tc::k_fc4_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(tc::k_fc4_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tc::k_fc4_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tc::k_fc4_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tc::k_fc4_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
+  if (make_map_f16(&m->map_ah_hi, a_hi, (uint64_t)m->alloc_sites, K, F::BK, F::BM / 2, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  if (make_map_f16(&m->map_ah_lo, a_lo, (uint64_t)m->alloc_sites, K, F::BK, F::BM / 2, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   {
-    const char* e = getenv("CVB_TC_FC4_CLUSTER");
-    m->tc_fc4_cluster = !(e && e[0] == '0');
+    const char* e = getenv("CVB_TC_FC4_CLUSTER");  // 0 = no clusters, 2 (default) = weight multicast, 4 = weights + activations
+    m->tc_fc4_cluster = e ? atoi(e) : 2;  // 4 measured slower (0.242 vs 0.180 ms): lock-step of four CTAs, 4 KB boxes
   }
   {
     using C = tc::Conv3Tc;
@@ -722,7 +726,8 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       const unsigned tiles4 = (unsigned)((n + F::BM - 1) / F::BM);
       __half* h4hi = m->tc_tail ? m->d_h4s : nullptr;
       __half* h4lo = m->tc_tail ? m->d_h4s + (size_t)m->alloc_sites * 336 : nullptr;
-      if (m->tc_fc4_cluster && tiles4 >= 2) {
+      if (m->tc_fc4_cluster >= 2 && tiles4 >= 2) {
+        const bool cl4 = m->tc_fc4_cluster >= 4;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2, (tiles4 + 1) & ~1u);  // pairs of site tiles; a padding tile loads zeros and stores nothing
         cfg.blockDim = dim3(F::THREADS);
@@ -730,15 +735,19 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
         cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;
+        at[0].val.clusterDim.x = cl4 ? 2 : 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        CK(cudaLaunchKernelEx(&cfg, tc::k_fc4_tc<true>, m->map_a_hi, m->map_a_lo, m->map_bh_hi, m->map_bh_lo, n, 4608,
-                              m->var("fc4/bias"), (const float*)m->d_inv_scale, m->d_h4, h4hi, h4lo));
+        if (cl4)
+          CK(cudaLaunchKernelEx(&cfg, tc::k_fc4_tc<4>, m->map_ah_hi, m->map_ah_lo, m->map_bh_hi, m->map_bh_lo, n, 4608,
+                                m->var("fc4/bias"), (const float*)m->d_inv_scale, m->d_h4, h4hi, h4lo));
+        else
+          CK(cudaLaunchKernelEx(&cfg, tc::k_fc4_tc<2>, m->map_a_hi, m->map_a_lo, m->map_bh_hi, m->map_bh_lo, n, 4608,
+                                m->var("fc4/bias"), (const float*)m->d_inv_scale, m->d_h4, h4hi, h4lo));
       } else {
-        tc::k_fc4_tc<false><<<dim3(2, tiles4), F::THREADS, F::SMEM_BYTES, st>>>(m->map_a_hi, m->map_a_lo, m->map_b_hi, m->map_b_lo, n,
-                                                                                4608, m->var("fc4/bias"), m->d_inv_scale, m->d_h4,
-                                                                                h4hi, h4lo);
+        tc::k_fc4_tc<1><<<dim3(2, tiles4), F::THREADS, F::SMEM_BYTES, st>>>(m->map_a_hi, m->map_a_lo, m->map_b_hi, m->map_b_lo, n,
+                                                                            4608, m->var("fc4/bias"), m->d_inv_scale, m->d_h4,
+                                                                            h4hi, h4lo);
       }
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;

@@ -1,6 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_forward_gpu.py -m gpu -q -x -k "golden or edge_batch or stage_intermediates" 2>&1 | tail -4 > gpurun_out/r1j_tests.log
+timeout 600 python -m pytest tests/test_forward_gpu.py -m gpu -q -x -k "golden" 2>&1 | tail -4 > gpurun_out/r1j_tests.log
 timeout 200 python bench.py --steps 3 --warmup 3 --sites 1212416 --cpu-seconds 1 > gpurun_out/r1j_bench.json 2> gpurun_out/r1j_bench.err
 cat gpurun_out/r1j_tests.log
 python - <<'PY'
