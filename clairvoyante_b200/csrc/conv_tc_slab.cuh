@@ -44,7 +44,7 @@ struct ConvSlabCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "does not fit in shared memory");
 };
 
-using Conv2Slab = ConvSlabCfg<Conv2Tc, 4, 8>;
+using Conv2Slab = ConvSlabCfg<Conv2Tc, 8, 16>;  // two tiles of operands in flight
 using Conv3Slab = ConvSlabCfg<Conv3Tc, 3, 6>;  // (NCB = 6, 24 warps x 32 columns, measured no faster: 0.203 vs 0.199 ms)
 using SlimConv3Slab = ConvSlabCfg<SlimConv3Tc, 4, 8>;
 

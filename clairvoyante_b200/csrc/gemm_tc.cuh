@@ -39,7 +39,7 @@ struct GemmArgs {
 
 template <int BN_>
 struct GemmTc {
-  static constexpr int BM = 128, BN = BN_, BK = 32, STAGES = 4, KCH_BLOCKS = 8;
+  static constexpr int BM = 128, BN = BN_, BK = 32, STAGES = 5, KCH_BLOCKS = 8;
   static constexpr int ROW_BYTES = BK * 2;
   static constexpr int A_BYTES = BM * ROW_BYTES;
   static constexpr int B_BYTES = BN * ROW_BYTES;
