@@ -1347,7 +1347,8 @@ static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, i
     k_pool_fwd<4><<<gsz(nc * 26 * 32), 256, 0, st>>>(w->c2, nc, 29, 128, w->p2p, 28, 1, hp(w->p2h), hp(w->p2h) + w->cap * 28 * 128);
     if (launch_train_conv<trc::Conv3F, trc::Conv3FS>(m, w->p2h, w->cap * 28 * 128, w->wf3, nc, m->var("conv3/bias"), w->fsc + 1, w->c3, st))
       return 1;
-    k_pool_fwd<3><<<gsz(nc * 24 * 48), 256, 0, st>>>(w->c3, nc, 26, 192, w->p3, 24, 0, nullptr, nullptr);
+    // pool3 also writes p3 as the split-bf16 A operand of the FC4 forward GEMM
+    k_pool_fwd<3, true><<<gsz(nc * 24 * 48), 256, 0, st>>>(w->c3, nc, 26, 192, w->p3, 24, 0, hp(w->p3s), hp(w->p3s) + w->cap * 4608);
     CK(cudaGetLastError());
   } else {
     {
@@ -1373,7 +1374,6 @@ static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, i
   }
   if (m->train_mode != CVB_TRAIN_FP32) {
     // FC4 on tcgen05: p3 -> split bf16 (K-major), B = W4^T prepared once per step (train_prepare_weights)
-    if (split_rows_bf16(w->p3, nc, 4608, w->p3s, w->cap * 4608, st)) return 1;
     if (launch_gemm_tc<176, true, tc::GEMM_EPI_BIAS_SELU>(m, w->p3s, w->cap * 4608, 4608, w->w4ts, 336 * 4608, 4608, (int)nc, 336,
                                                           4608, w->h4, 336, m->var("fc4/bias"), st))
       return 1;

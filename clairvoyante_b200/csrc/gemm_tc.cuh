@@ -53,11 +53,6 @@ struct GemmTc {
   static_assert(B_BYTES % 512 == 0, "operand tiles start on a swizzle atom");
 };
 
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-}
-
 // src fp32 [rows][cols] (row pitch ld_src) -> hi, lo bf16 [rows][ld_dst].   cols % 4 == 0
 __global__ void k_split_bf16(const float* __restrict__ src, int64_t rows, int cols, int64_t ld_src, __nv_bfloat16* __restrict__ hi,
                              __nv_bfloat16* __restrict__ lo, int64_t ld_dst) {

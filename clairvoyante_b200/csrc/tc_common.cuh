@@ -185,6 +185,12 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   lo = __float2half_rn(x - __half2float(hi));
 }
 
+// fp32 -> (hi, lo) bf16 pair: ~16 mantissa bits with fp32's exponent range (gradients need no scaling)
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
 // two values at once.  Values are saturated to fp16's finite range: an activation beyond +-65504 (never seen with
 // trained or initialiser weights, |activation| ~ 1e2) loses accuracy instead of turning into inf/NaN.
 __device__ __forceinline__ void split_f16x2(float a, float b, __half2& hi, __half2& lo) {

@@ -79,7 +79,8 @@ static inline DropConst drop_const(float rate) {
 // ---- (P,1) VALID max-pool over rows: in [n][H][C] -> out [n][OROWS][C] at rows OR0..OR0+H-P  (C multiple of 4);
 //      hi / lo (optional): the same values again as split-fp16 planes in the same layout = the activation operand of the
 //      next layer's tcgen05 conv kernel (conv_tc_slab.cuh)
-template <int P>
+//      BF = true: the planes are split bf16 instead (operand of the FC4 GEMMs, gemm_tc.cuh)
+template <int P, bool BF = false>
 __global__ void k_pool_fwd(const float* __restrict__ in, int64_t n, int H, int C, float* __restrict__ out, int OROWS, int OR0,
                            __half* __restrict__ hi, __half* __restrict__ lo) {
   const int HP = H - P + 1, C4 = C / 4;
@@ -95,7 +96,15 @@ __global__ void k_pool_fwd(const float* __restrict__ in, int64_t n, int H, int C
     for (int j = 1; j < P; ++j) v = max4(v, src[j * C4]);
     const int64_t o = (s * OROWS + OR0 + h) * C + q * 4;
     *reinterpret_cast<float4*>(out + o) = v;
-    if (hi) {
+    if (hi && BF) {
+      __nv_bfloat16 hb[4], lb[4];
+      tc::split_bf16(v.x, hb[0], lb[0]);
+      tc::split_bf16(v.y, hb[1], lb[1]);
+      tc::split_bf16(v.z, hb[2], lb[2]);
+      tc::split_bf16(v.w, hb[3], lb[3]);
+      *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(hb);
+      *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(lb);
+    } else if (hi) {
       __half2 h2[2], l2[2];
       tc::split_f16x2(v.x, v.y, h2[0], l2[0]);
       tc::split_f16x2(v.z, v.w, h2[1], l2[1]);
