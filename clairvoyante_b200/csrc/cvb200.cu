@@ -1065,7 +1065,7 @@ static int ensure_train_work(cvb_model* m) {
       {&w->g4, c * 336}, {&w->g4b, c * 336}, {&w->gp3, c * 24 * 192}, {&w->g3p, c * 28 * 192}, {&w->gp2, c * 26 * 128},
       {&w->g2p, c * 30 * 128}, {&w->gp1, c * 29 * 64}, {&w->g1, c * 33 * 64}, {&w->w3t, 3 * 4 * 48 * 32},
       {&w->w2t, 2 * 4 * 32 * 16}, {&w->w4t, 336 * 4608}, {&w->w5t, 176 * 336}, {&w->tmpb, 336 * 16}, {&w->tmph, 168 * 16},
-      {&w->tmp5, 336 * 184}, {&w->tmpw, 3 * 128 * 192}, {&w->fsc, 16}, {&w->loss, 16}};
+      {&w->tmp5, 336 * 184}, {&w->tmpw, 3 * 128 * 256}, {&w->fsc, 16}, {&w->loss, 16}};
   int64_t total = 0;
   for (auto& it : items) total += (it.n + 63) / 64 * 64;
   CK(cudaMalloc(&w->all, (size_t)total * 4));
@@ -1076,14 +1076,12 @@ static int ensure_train_work(cvb_model* m) {
     // split-bf16 operand copies for the tensor-core FC4 contractions: each buffer = hi plane followed by lo plane
     w->ldt = c;
     struct Item16 { uint16_t** p; int64_t n; };
-    Item16 it16[] = {{&w->p3s, 2 * c * 4608}, {&w->p3t, 2 * 4608 * c}, {&w->g4s, 2 * c * 336},
-                     {&w->g4t, 2 * 336 * c},  {&w->w4s, 2 * 4608 * 336}, {&w->w4ts, 2 * 336 * 4608},
+    Item16 it16[] = {{&w->p3s, 2 * c * 4608}, {&w->g4s, 2 * c * 336}, {&w->w4s, 2 * 4608 * 336}, {&w->w4ts, 2 * 336 * 4608},
                      {&w->d4t, 2 * 336 * c},  {&w->h5t, 2 * 168 * c},    {&w->gct, 2 * 184 * c},
-                     {&w->cta, 3 * 2 * 128 * c * 30}, {&w->ctb, 2 * 192 * c * 30},
+                     {&w->p1b, 2 * c * 30 * 64}, {&w->p2b, 2 * c * 28 * 128},
                      {&w->p1h, 2 * c * 30 * 64}, {&w->p2h, 2 * c * 28 * 128}, {&w->g3h, 2 * c * 28 * 256}, {&w->g2h, 2 * c * 30 * 128},
                      {&w->wf2, 2 * 2 * 128 * 64}, {&w->wf3, 2 * 3 * 192 * 128}, {&w->wd2, 2 * 2 * 64 * 128},
                      {&w->wd3, 2 * 3 * 128 * 256}};
-    w->ldr = c * 30;
     CK(cudaMalloc(&w->amax, 16));
     const float one = 1.f;
     CK(cudaMemcpy(w->fsc + 2, &one, 4, cudaMemcpyHostToDevice));
@@ -1105,24 +1103,35 @@ static inline int gsz(int64_t total, int block = 256) { return (int)std::min<int
 // C[M][N] (op)= A[M][K] . B[N][K]^T ; a / b point at the hi plane, the lo plane follows `a_plane` / `b_plane` elements later;
 // lda / ldb = row pitch in elements (multiple of 8: TMA strides are 16-byte granular)
 struct GemmExtra {  // batched / split-K launches, see tc::GemmArgs
-  int batches = 1, a_batch_rows = 0;
+  int batches = 1, a_batch_rows = 0, a_kshift0 = 0, a_kshift_per_batch = 0;
   int64_t c_batch_stride = 0;
   int kslices = 1;
 };
-template <int BN, bool CHUNKED, int EPI>
+// MN = false: a [M][K], b [N][K] (K-major; lda / ldb = row pitch).  MN = true: a [K][M], b [K][N] (transposed operands read in
+// place as MN-major tiles; lda / ldb = pitch of a K row).
+template <int BN, bool CHUNKED, int EPI, bool MN = false>
 static int launch_gemm_tc(cvb_model* m, const uint16_t* a, int64_t a_plane, int64_t lda, const uint16_t* b, int64_t b_plane,
                           int64_t ldb, int M, int N, int K, float* C, int64_t ldc, const float* bias, cudaStream_t st,
                           const GemmExtra& ex = GemmExtra()) {
-  using G = tc::GemmTc<BN>;
+  using G = tc::GemmTc<BN, MN>;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  const uint64_t da[2] = {(uint64_t)K, (uint64_t)(M + (ex.batches - 1) * ex.a_batch_rows)}, db[2] = {(uint64_t)K, (uint64_t)N};
   const uint64_t sa[1] = {(uint64_t)lda * 2}, sb[1] = {(uint64_t)ldb * 2};
-  const uint32_t ba[2] = {(uint32_t)G::BK, (uint32_t)G::BM}, bb[2] = {(uint32_t)G::BK, (uint32_t)BN};
-  if (make_map_nd(&ma_hi, (void*)a, 2, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-  if (make_map_nd(&ma_lo, (void*)(a + a_plane), 2, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-  if (make_map_nd(&mb_hi, (void*)b, 2, db, sb, bb, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-  if (make_map_nd(&mb_lo, (void*)(b + b_plane), 2, db, sb, bb, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-  auto k = tc::k_gemm_tc<BN, CHUNKED, EPI>;
+  if (MN) {
+    const uint64_t da[2] = {(uint64_t)M, (uint64_t)K}, db[2] = {(uint64_t)N, (uint64_t)K};
+    const uint32_t bx[2] = {64, (uint32_t)G::BK};
+    if (make_map_nd(&ma_hi, (void*)a, 2, da, sa, bx, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (make_map_nd(&ma_lo, (void*)(a + a_plane), 2, da, sa, bx, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (make_map_nd(&mb_hi, (void*)b, 2, db, sb, bx, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (make_map_nd(&mb_lo, (void*)(b + b_plane), 2, db, sb, bx, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  } else {
+    const uint64_t da[2] = {(uint64_t)K, (uint64_t)(M + (ex.batches - 1) * ex.a_batch_rows)}, db[2] = {(uint64_t)K, (uint64_t)N};
+    const uint32_t ba[2] = {(uint32_t)G::BK, (uint32_t)G::BM}, bb[2] = {(uint32_t)G::BK, (uint32_t)BN};
+    if (make_map_nd(&ma_hi, (void*)a, 2, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (make_map_nd(&ma_lo, (void*)(a + a_plane), 2, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (make_map_nd(&mb_hi, (void*)b, 2, db, sb, bb, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    if (make_map_nd(&mb_lo, (void*)(b + b_plane), 2, db, sb, bb, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  }
+  auto k = tc::k_gemm_tc<BN, CHUNKED, EPI, MN>;
   CK(set_smem(k, G::SMEM_BYTES));
   tc::GemmArgs g;
   g.M = M; g.N = N; g.K = K;
@@ -1130,6 +1139,7 @@ static int launch_gemm_tc(cvb_model* m, const uint16_t* a, int64_t a_plane, int6
   g.C = C; g.ldc = ldc; g.bias = bias;
   g.m_tiles = (M + G::BM - 1) / G::BM;
   g.a_batch_rows = ex.a_batch_rows; g.c_batch_stride = ex.c_batch_stride;
+  g.a_kshift0 = ex.a_kshift0; g.a_kshift_per_batch = ex.a_kshift_per_batch;
   const int nkb = (K + G::BK - 1) / G::BK;
   g.kb_per_slice = (nkb + ex.kslices - 1) / ex.kslices;
   const int kslices = (nkb + g.kb_per_slice - 1) / g.kb_per_slice;  // no empty slice
@@ -1157,28 +1167,26 @@ static int split_transpose_bf16(const float* src, int64_t R, int C, int64_t ld_s
 // Conv weight gradient on tcgen05 (training_op, clairvoyante_v3.py:174, for conv2 / conv3):
 //   dW[kh][kw][c][co] = sum_R in[R - 1 + kh][(w', c)] * g[R][(w, co)],   w' = w + kw - 1,
 // over the flattened (site, row) index R of the padded layouts (g stored one row down, its pad rows are zero, so terms that
-// cross a site boundary vanish).  Both operands are transposed into K-major bf16 planes (K = R), `in` once per kh with its
-// rows shifted by kh - 1 (TMA cannot apply a K offset that is not a multiple of 16 bytes); one batched GEMM gives
-// tmpW[kh] = in_kh^T . g  = every (w', c) x (w, co) product (13 of the 16 (w', w) pairs are real taps), K split
-// over the SMs with atomic accumulation; k_scatter_conv_wgrad adds the taps into dW.
-template <int CIN, int COUT, int KH>
-static int launch_conv_wgrad_tc(cvb_model* m, const float* in, const float* g, int64_t R, float* dW, cudaStream_t st) {
+// cross a site boundary vanish).  K = R is the slow index of both factors, i.e. they are the TRANSPOSED operands of the GEMM
+// tmpW[kh] = in(shifted by kh - 1 rows)^T . g: one batched (batch = kh), split-K launch of k_gemm_tc in MN-major mode reads
+// the split-bf16 planes written by the forward pool kernel (in) and by pool-backward (g, COUT padded to CP) in place and
+// accumulates every (w', c) x (w, co) product with fp32 atomics; k_scatter_conv_wgrad adds the 13 of 16 (w', w) pairs that
+// are taps into dW.
+template <int CIN, int COUT, int KH, int CP>
+static int launch_conv_wgrad_tc(cvb_model* m, const uint16_t* in, int64_t in_plane, const uint16_t* g, int64_t g_plane, int64_t R,
+                                float* dW, cudaStream_t st) {
   TrainWork* w = m->train;
-  const int64_t ld = w->ldr;
-  constexpr int MA = 4 * CIN;  // rows of one (shifted) copy of in^T; the KH copies are stacked: [kh][(w', c)][R]
-  for (int kh = 0; kh < KH; ++kh)
-    if (split_transpose_bf16(in, R, MA, MA, w->cta + (int64_t)kh * MA * ld, (int64_t)KH * MA * ld, ld, st, kh - 1)) return 1;
-  if (split_transpose_bf16(g, R, 4 * COUT, 4 * COUT, w->ctb, 192 * ld, ld, st)) return 1;
-  CK(cudaMemsetAsync(w->tmpw, 0, (size_t)KH * MA * 192 * 4, st));
+  constexpr int MA = 4 * CIN, NB = 4 * CP;
+  CK(cudaMemsetAsync(w->tmpw, 0, (size_t)KH * MA * NB * 4, st));
   GemmExtra ex;
-  ex.batches = KH; ex.a_batch_rows = MA; ex.c_batch_stride = (int64_t)MA * 192;
+  ex.batches = KH; ex.a_kshift0 = -1; ex.a_kshift_per_batch = 1; ex.c_batch_stride = (int64_t)MA * NB;
   ex.kslices = std::max(1, m->num_sms / KH);
-  if (launch_gemm_tc<192, true, tc::GEMM_EPI_ATOMIC>(m, w->cta, (int64_t)KH * MA * ld, ld, w->ctb, 192 * ld, ld, MA, 4 * COUT, (int)R,
-                                                     w->tmpw, 192, nullptr, st, ex))
+  if (launch_gemm_tc<NB, false, tc::GEMM_EPI_ATOMIC, true>(m, in, in_plane, MA, g, g_plane, NB, MA, NB, (int)R, w->tmpw, NB, nullptr,
+                                                           st, ex))
     return 1;
-  k_scatter_conv_wgrad<CIN, COUT, KH><<<(KH * 4 * CIN * COUT + 255) / 256, 256, 0, st>>>(w->tmpw, dW);
+  k_scatter_conv_wgrad<CIN, COUT, KH, CP><<<(KH * 4 * CIN * COUT + 255) / 256, 256, 0, st>>>(w->tmpw, dW);
   CK(cudaGetLastError());
-  m->launches += 3 + KH;
+  m->launches += 2;
   return 0;
 }
 
@@ -1339,12 +1347,14 @@ static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, i
                                                                                           m->var("conv1/bias"), w->c1, nullptr);
     CK(cudaGetLastError());
     k_pool_fwd<5><<<gsz(nc * 29 * 16), 256, 0, st>>>(w->c1, nc, 33, 64, w->p1p, 30, 0, tcm ? hp(w->p1h) : nullptr,
-                                                     tcm ? hp(w->p1h) + w->cap * 30 * 64 : nullptr);
+                                                     tcm ? hp(w->p1h) + w->cap * 30 * 64 : nullptr, tcm ? bf(w->p1b) : nullptr,
+                                                     tcm ? bf(w->p1b) + w->cap * 30 * 64 : nullptr);
   }
   if (tcm) {
     if (launch_train_conv<trc::Conv2F, trc::Conv2FS>(m, w->p1h, w->cap * 30 * 64, w->wf2, nc, m->var("conv2/bias"), w->fsc + 0, w->c2, st))
       return 1;
-    k_pool_fwd<4><<<gsz(nc * 26 * 32), 256, 0, st>>>(w->c2, nc, 29, 128, w->p2p, 28, 1, hp(w->p2h), hp(w->p2h) + w->cap * 28 * 128);
+    k_pool_fwd<4><<<gsz(nc * 26 * 32), 256, 0, st>>>(w->c2, nc, 29, 128, w->p2p, 28, 1, hp(w->p2h), hp(w->p2h) + w->cap * 28 * 128,
+                                                     bf(w->p2b), bf(w->p2b) + w->cap * 28 * 128);
     if (launch_train_conv<trc::Conv3F, trc::Conv3FS>(m, w->p2h, w->cap * 28 * 128, w->wf3, nc, m->var("conv3/bias"), w->fsc + 1, w->c3, st))
       return 1;
     // pool3 also writes p3 as the split-bf16 A operand of the FC4 forward GEMM
@@ -1459,14 +1469,13 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
   // FC4
   k_colsum<<<dim3((336 + 31) / 32, 32), 256, 0, st>>>(w->g4, nc, 336, 336, gvar(m, "fc4/bias"));
   if (m->train_mode != CVB_TRAIN_FP32) {
-    // weight gradient  dW4 [4608][336] += p3^T . dpre4   (K = sites: both operands transposed into K-major planes)
-    if (split_transpose_bf16(w->p3, nc, 4608, 4608, w->p3t, 4608 * w->ldt, w->ldt, st)) return 1;
-    if (split_transpose_bf16(w->g4, nc, 336, 336, w->g4t, 336 * w->ldt, w->ldt, st)) return 1;
-    if (launch_gemm_tc<176, true, tc::GEMM_EPI_ACCUM>(m, w->p3t, 4608 * w->ldt, w->ldt, w->g4t, 336 * w->ldt, w->ldt, 4608, 336,
-                                                      (int)nc, gvar(m, "fc4/kernel"), 336, nullptr, st))
+    // weight gradient  dW4 [4608][336] += p3^T . dpre4   (K = sites)
+    // p3s [sites][4608] (written by pool3) and g4s [sites][336] are its transposed operands: read in place, MN-major
+    if (split_rows_bf16(w->g4, nc, 336, w->g4s, w->cap * 336, st)) return 1;
+    if (launch_gemm_tc<192, true, tc::GEMM_EPI_ACCUM, true>(m, w->p3s, w->cap * 4608, 4608, w->g4s, w->cap * 336, 336, 4608, 336,
+                                                            (int)nc, gvar(m, "fc4/kernel"), 336, nullptr, st))
       return 1;
     // data gradient  gp3 [sites][4608] = dpre4 . W4^T      (B = W4 as stored: [4608][336] is K-major for K = 336)
-    if (split_rows_bf16(w->g4, nc, 336, w->g4s, w->cap * 336, st)) return 1;
     if (launch_gemm_tc<192, false, tc::GEMM_EPI_STORE>(m, w->g4s, w->cap * 336, 336, w->w4s, 4608 * 336, 336, (int)nc, 4608, 336,
                                                        w->gp3, 4608, nullptr, st))
       return 1;
@@ -1486,7 +1495,8 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
                                                                             tcm ? bf(w->g3h) + w->cap * 28 * 256 : nullptr);
   {
     if (tcm) {
-      if (launch_conv_wgrad_tc<32, 48, 3>(m, w->p2p, w->g3p, nc * 28, gvar(m, "conv3/kernel"), st)) return 1;
+      if (launch_conv_wgrad_tc<32, 48, 3, 64>(m, w->p2b, w->cap * 28 * 128, w->g3h, w->cap * 28 * 256, nc * 28, gvar(m, "conv3/kernel"), st))
+        return 1;
     } else {
       using W = WgradCfg<32, 48, 3, 26, 4, 12, 4>;
       auto k = k_conv_wgrad<32, 48, 3, 26, 4, 12, 4>;
@@ -1511,7 +1521,8 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
                                                                        tcm ? bf(w->g2h) + w->cap * 30 * 128 : nullptr);
   {
     if (tcm) {
-      if (launch_conv_wgrad_tc<16, 32, 2>(m, w->p1p, w->g2p, nc * 30, gvar(m, "conv2/kernel"), st)) return 1;
+      if (launch_conv_wgrad_tc<16, 32, 2, 32>(m, w->p1b, w->cap * 30 * 64, w->g2h, w->cap * 30 * 128, nc * 30, gvar(m, "conv2/kernel"), st))
+        return 1;
     } else {
       using W = WgradCfg<16, 32, 2, 29, 4, 4, 4>;
       auto k = k_conv_wgrad<16, 32, 2, 29, 4, 4, 4>;

@@ -27,6 +27,13 @@ enum { GEMM_EPI_STORE = 0, GEMM_EPI_BIAS_SELU = 1, GEMM_EPI_ACCUM = 2, GEMM_EPI_
 //            row-shifted conv taps, but cp.async.bulk.tensor faults -- "illegal instruction" -- when the innermost
 //            coordinate is not a multiple of 16 bytes, measured on B200; the shifted copies are made by the transpose.)
 //   grid.z = K slices of kb_per_slice 32-wide K blocks each (use GEMM_EPI_ATOMIC when > 1)
+//
+// MN = true: the operands are given TRANSPOSED -- A as [K][M], B as [K][N], i.e. exactly how a weight gradient finds its
+// factors in memory (K = sites or flattened rows) -- and are fed to the MMA as MN-major operands: TMA boxes of {64 elements
+// along M/N, 32 rows along K} under SWIZZLE_128B, descriptor LBO = distance between 64-element blocks, SBO = 1024 (8 k-rows),
+// K-step = 16 rows = 2048 bytes, instruction-descriptor a_major = b_major = 1 (recipe established on the GPU by
+// tools/umma_mnmajor_probe.cu).  No transposing copies, and a per-batch ROW shift of A (the kh taps of a conv weight
+// gradient) is just the outer TMA coordinate: a_kshift0 + batch * a_kshift_per_batch.
 struct GemmArgs {
   int M, N, K, terms;
   float* C;
@@ -35,16 +42,21 @@ struct GemmArgs {
   int m_tiles, a_batch_rows;
   int64_t c_batch_stride;
   int kb_per_slice;
+  int a_kshift0, a_kshift_per_batch;  // MN only
 };
 
-template <int BN_>
+template <int BN_, bool MN_ = false>
 struct GemmTc {
-  static constexpr int BM = 128, BN = BN_, BK = 32, STAGES = 5, KCH_BLOCKS = 8;
+  static constexpr int BM = 128, BN = BN_, BK = 32, KCH_BLOCKS = 8;
+  static constexpr bool MN = MN_;
   static constexpr int ROW_BYTES = BK * 2;
-  static constexpr int A_BYTES = BM * ROW_BYTES;
-  static constexpr int B_BYTES = BN * ROW_BYTES;
+  static constexpr int A_BYTES = BM * ROW_BYTES;   // K-major: 128 rows x 64 B;  MN-major: 2 blocks of [32 k][128 B] -- same size
+  static constexpr int B_BYTES = BN * ROW_BYTES;   // K-major: BN rows x 64 B;   MN-major: BN/64 blocks of [32 k][128 B]
+  static constexpr int MN_BLOCK = BK * 128;        // one 64-element block of an MN-major operand tile
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = 5 * STAGE_BYTES + 1280 <= 227 * 1024 ? 5 : 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static_assert(!MN || BN % 64 == 0, "MN-major operand tiles are whole 64-element swizzle blocks");
   static constexpr int THREADS = 192;
   static constexpr int TMEM_COLS = 512;  // two accumulator buffers at columns 0 and 256
   static constexpr uint32_t SBO = 8 * ROW_BYTES;
@@ -104,11 +116,11 @@ __global__ void k_split_transpose_bf16(const float* __restrict__ src, int64_t R,
 }
 
 // grid (ceil(N/BN), ceil(M/128)).  terms = 3 (split bf16) or 1 (plain bf16: the lo planes are neither loaded nor multiplied).
-template <int BN, bool CHUNKED, int EPI>
-__global__ void __launch_bounds__(GemmTc<BN>::THREADS, 1)
+template <int BN, bool CHUNKED, int EPI, bool MN = false>
+__global__ void __launch_bounds__(GemmTc<BN, MN>::THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const GemmArgs g) {
-  using G = GemmTc<BN>;
+  using G = GemmTc<BN, MN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::STAGES * G::STAGE_BYTES);
@@ -156,17 +168,31 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
         uint8_t* st = smem + s * G::STAGE_BYTES;
         mbar_arrive_expect_tx(&full[s], bytes);
         const int k0 = (kb_begin + kb) * G::BK;
-        tma_load_2d(st, &map_a_hi, &full[s], k0, am0);
-        tma_load_2d(st + 2 * G::A_BYTES, &map_b_hi, &full[s], k0, n0);
-        if (split) {
-          tma_load_2d(st + G::A_BYTES, &map_a_lo, &full[s], k0, am0);
-          tma_load_2d(st + 2 * G::A_BYTES + G::B_BYTES, &map_b_lo, &full[s], k0, n0);
+        if (MN) {
+          const int ka = k0 + g.a_kshift0 + batch * g.a_kshift_per_batch;  // rows outside [0, K) read as zero
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            tma_load_2d(st + b * G::MN_BLOCK, &map_a_hi, &full[s], m0 + b * 64, ka);
+            if (split) tma_load_2d(st + G::A_BYTES + b * G::MN_BLOCK, &map_a_lo, &full[s], m0 + b * 64, ka);
+          }
+#pragma unroll
+          for (int b = 0; b < BN / 64; ++b) {
+            tma_load_2d(st + 2 * G::A_BYTES + b * G::MN_BLOCK, &map_b_hi, &full[s], n0 + b * 64, k0);
+            if (split) tma_load_2d(st + 2 * G::A_BYTES + G::B_BYTES + b * G::MN_BLOCK, &map_b_lo, &full[s], n0 + b * 64, k0);
+          }
+        } else {
+          tma_load_2d(st, &map_a_hi, &full[s], k0, am0);
+          tma_load_2d(st + 2 * G::A_BYTES, &map_b_hi, &full[s], k0, n0);
+          if (split) {
+            tma_load_2d(st + G::A_BYTES, &map_a_lo, &full[s], k0, am0);
+            tma_load_2d(st + 2 * G::A_BYTES + G::B_BYTES, &map_b_lo, &full[s], k0, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(G::BM, BN);
+      constexpr uint32_t idesc = umma_idesc_bf16(G::BM, BN) | (MN ? (1u << 15) | (1u << 16) : 0u);  // a_major, b_major = MN
       int kb = 0;
       for (int c = 0; c < nchunks; ++c) {
         const int buf = c & 1;
@@ -183,13 +209,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
           const uint32_t a_hi = st, a_lo = st + G::A_BYTES, b_hi = st + 2 * G::A_BYTES, b_lo = b_hi + G::B_BYTES;
 #pragma unroll
           for (int ks = 0; ks < G::BK / 16; ++ks) {
-            const uint32_t ko = ks * 32;
-            const uint64_t dah = umma_desc(a_hi + ko, 16, G::SBO, G::LAYOUT);
-            const uint64_t dbh = umma_desc(b_hi + ko, 16, G::SBO, G::LAYOUT);
+            // K-major: 16 elements = 32 bytes along the 64-byte swizzled row; MN-major: 16 k-rows of 128 bytes
+            const uint32_t ko = MN ? ks * 2048 : ks * 32;
+            const uint32_t lbo = MN ? G::MN_BLOCK : 16, sbo = MN ? 1024 : G::SBO, lay = MN ? 2 : G::LAYOUT;
+            const uint64_t dah = umma_desc(a_hi + ko, lbo, sbo, lay);
+            const uint64_t dbh = umma_desc(b_hi + ko, lbo, sbo, lay);
             const uint32_t first = (uint32_t)((j | ks) != 0);
             if (split) {
-              const uint64_t dal = umma_desc(a_lo + ko, 16, G::SBO, G::LAYOUT);
-              const uint64_t dbl = umma_desc(b_lo + ko, 16, G::SBO, G::LAYOUT);
+              const uint64_t dal = umma_desc(a_lo + ko, lbo, sbo, lay);
+              const uint64_t dbl = umma_desc(b_lo + ko, lbo, sbo, lay);
               umma_f16(tcol, dal, dbh, idesc, first);  // small terms first
               umma_f16(tcol, dah, dbl, idesc, 1u);
               umma_f16(tcol, dah, dbh, idesc, 1u);

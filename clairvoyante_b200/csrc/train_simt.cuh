@@ -26,21 +26,19 @@ struct TrainWork {
   float *w3t = nullptr, *w2t = nullptr, *w4t = nullptr, *w5t = nullptr, *tmpb = nullptr, *tmph = nullptr;
   float* loss = nullptr;  // [8]: loss1..4 (sums), sum of squares of kernels, spare
   float* all = nullptr;   // single allocation backing everything above
-  // tensor-core FC4 (gemm_tc.cuh): split-bf16 operands, planes [hi | lo].  p3s/g4s row-major copies, p3t/g4t transposes
-  // (row pitch ldt = cap), w4s = W4 [4608][336], w4ts = W4^T [336][4608]
-  uint16_t *p3s = nullptr, *p3t = nullptr, *g4s = nullptr, *g4t = nullptr, *w4s = nullptr, *w4ts = nullptr;
+  // tensor-core FC4 (gemm_tc.cuh): split-bf16 operands, planes [hi | lo].  p3s [cap][4608] / g4s [cap][336] row-major copies
+  // (K-major for the forward / data gradient, MN-major for the weight gradient), w4s = W4 [4608][336], w4ts = W4^T [336][4608]
+  uint16_t *p3s = nullptr, *g4s = nullptr, *w4s = nullptr, *w4ts = nullptr;
   // transposed operands of the FC5 / head weight gradients: d4^T [336][ldt], h5^T [168][ldt], [g5 | dlog]^T [184][ldt]
   uint16_t *d4t = nullptr, *h5t = nullptr, *gct = nullptr;
   float* tmp5 = nullptr;  // [336][184] = d4^T . [g5 | dlog]
-  // conv weight gradients on tcgen05: transposed (in, g) of one conv layer, row pitch ldr = cap * 30; tmpw [KH][4 CIN][192]
-  uint16_t *cta = nullptr, *ctb = nullptr;
-  int64_t ldr = 0;
-  float* tmpw = nullptr;
+  float* tmpw = nullptr;  // conv weight gradients on tcgen05: every (w', c) x (w, co) product, [KH][4 CIN][4 CP]
   // tcgen05 forward / data-gradient convs (conv_tc_slab.cuh): activations as split planes [hi | lo] in the consumer's padded
   // row layout -- p1h [cap*30][64], p2h [cap*28][128] fp16; g3h [cap*28][4*64] (48 -> 64 channels), g2h [cap*30][128] bf16 --
   // and rearranged weights: wf2 / wf3 forward (fp16, scaled: inv scales in fsc[0..1]), wd2 / wd3 flipped kernels (bf16)
   uint16_t *p1h = nullptr, *p2h = nullptr, *g3h = nullptr, *g2h = nullptr, *wf2 = nullptr, *wf3 = nullptr, *wd2 = nullptr,
            *wd3 = nullptr;
+  uint16_t *p1b = nullptr, *p2b = nullptr;  // p1 / p2 again as split bf16 (same layouts): A operands of the conv weight gradients
   float* fsc = nullptr;          // [0] conv2, [1] conv3 forward inverse weight scales, [2] = 1.0f
   unsigned int* amax = nullptr;  // [2] |w|max scratch
   int64_t ldt = 0;
@@ -80,9 +78,12 @@ static inline DropConst drop_const(float rate) {
 //      hi / lo (optional): the same values again as split-fp16 planes in the same layout = the activation operand of the
 //      next layer's tcgen05 conv kernel (conv_tc_slab.cuh)
 //      BF = true: the planes are split bf16 instead (operand of the FC4 GEMMs, gemm_tc.cuh)
+//      bhi / blo (optional, BF = false): the same values once more as split bf16 planes = the (MN-major) A operand of this
+//      layer's weight-gradient GEMM
 template <int P, bool BF = false>
 __global__ void k_pool_fwd(const float* __restrict__ in, int64_t n, int H, int C, float* __restrict__ out, int OROWS, int OR0,
-                           __half* __restrict__ hi, __half* __restrict__ lo) {
+                           __half* __restrict__ hi, __half* __restrict__ lo, __nv_bfloat16* __restrict__ bhi = nullptr,
+                           __nv_bfloat16* __restrict__ blo = nullptr) {
   const int HP = H - P + 1, C4 = C / 4;
   const int64_t total = n * HP * C4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -110,6 +111,15 @@ __global__ void k_pool_fwd(const float* __restrict__ in, int64_t n, int H, int C
       tc::split_f16x2(v.z, v.w, h2[1], l2[1]);
       *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h2);
       *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l2);
+    }
+    if (!BF && bhi) {
+      __nv_bfloat16 hb[4], lb[4];
+      tc::split_bf16(v.x, hb[0], lb[0]);
+      tc::split_bf16(v.y, hb[1], lb[1]);
+      tc::split_bf16(v.z, hb[2], lb[2]);
+      tc::split_bf16(v.w, hb[3], lb[3]);
+      *reinterpret_cast<uint2*>(bhi + o) = *reinterpret_cast<const uint2*>(hb);
+      *reinterpret_cast<uint2*>(blo + o) = *reinterpret_cast<const uint2*>(lb);
     }
   }
 }
@@ -529,9 +539,10 @@ k_conv_wgrad(const float* __restrict__ in, const float* __restrict__ g, int GROW
     for (int j = 0; j < TO; ++j) atomicAdd(dW + ((kh * 4 + kw) * CIN + c0 + i) * COUT + o0 + j, acc[i][j]);
 }
 
-// ---- taps of the tensor-core conv weight gradient: tmpw[kh][w' * CIN + c][w * COUT + co] (row pitch 192) holds every
-//      (w', w) product; dW[kh][kw][c][co] += sum over w of the entries with w' = w + kw - 1 in [0, 3]
-template <int CIN, int COUT, int KH>
+// ---- taps of the tensor-core conv weight gradient: tmpw[kh][w' * CIN + c][w * CP + co] (row pitch LDW = 4 * CP; CP = COUT
+//      padded to the data-gradient operand's channel pitch) holds every (w', w) product;
+//      dW[kh][kw][c][co] += sum over w of the entries with w' = w + kw - 1 in [0, 3]
+template <int CIN, int COUT, int KH, int CP>
 __global__ void k_scatter_conv_wgrad(const float* __restrict__ tmpw, float* __restrict__ dW) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= KH * 4 * CIN * COUT) return;
@@ -540,7 +551,7 @@ __global__ void k_scatter_conv_wgrad(const float* __restrict__ tmpw, float* __re
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
     const int wp = w + kw - 1;
-    if (wp >= 0 && wp < 4) a += tmpw[((int64_t)kh * 4 * CIN + wp * CIN + c) * 192 + w * COUT + co];
+    if (wp >= 0 && wp < 4) a += tmpw[((int64_t)kh * 4 * CIN + wp * CIN + c) * (4 * CP) + w * CP + co];
   }
   dW[i] += a;
 }
