@@ -1078,7 +1078,8 @@ static int ensure_train_work(cvb_model* m) {
     struct Item16 { uint16_t** p; int64_t n; };
     Item16 it16[] = {{&w->p3s, 2 * c * 4608}, {&w->g4s, 2 * c * 336}, {&w->w4s, 2 * 4608 * 336}, {&w->w4ts, 2 * 336 * 4608},
                      {&w->d4t, 2 * 336 * c},  {&w->h5t, 2 * 168 * c},    {&w->gct, 2 * 184 * c},
-                     {&w->p1b, 2 * c * 30 * 64}, {&w->p2b, 2 * c * 28 * 128},
+                     {&w->p1b, 2 * c * 30 * 64}, {&w->p2b, 2 * c * 28 * 128}, {&w->d4s, 2 * c * 336}, {&w->g5s, 2 * c * 168},
+                     {&w->w5s, 2 * 336 * 168}, {&w->w5ts, 2 * 168 * 336},
                      {&w->p1h, 2 * c * 30 * 64}, {&w->p2h, 2 * c * 28 * 128}, {&w->g3h, 2 * c * 28 * 256}, {&w->g2h, 2 * c * 30 * 128},
                      {&w->wf2, 2 * 2 * 128 * 64}, {&w->wf3, 2 * 3 * 192 * 128}, {&w->wd2, 2 * 2 * 64 * 128},
                      {&w->wd3, 2 * 3 * 128 * 256}};
@@ -1150,8 +1151,8 @@ static int launch_gemm_tc(cvb_model* m, const uint16_t* a, int64_t a_plane, int6
 }
 static inline __nv_bfloat16* bf(uint16_t* p) { return reinterpret_cast<__nv_bfloat16*>(p); }
 static inline __half* hp(uint16_t* p) { return reinterpret_cast<__half*>(p); }
-static int split_rows_bf16(const float* src, int64_t rows, int cols, uint16_t* dst, int64_t plane, cudaStream_t st) {
-  tc::k_split_bf16<<<gsz(rows * (cols / 4)), 256, 0, st>>>(src, rows, cols, cols, bf(dst), bf(dst + plane), cols);
+static int split_rows_bf16(const float* src, int64_t rows, int cols, uint16_t* dst, int64_t plane, cudaStream_t st, int64_t ld_src = 0) {
+  tc::k_split_bf16<<<gsz(rows * (cols / 4)), 256, 0, st>>>(src, rows, cols, ld_src ? ld_src : cols, bf(dst), bf(dst + plane), cols);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1401,16 +1402,23 @@ static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, i
     k_dropout_fwd<<<gsz(nc * 336), 256, 0, st>>>(w->h4, w->d4, nc * 336, index0, seed, drop_const(drop4));
     d4 = w->d4;
   }
-  {
+  if (tcm) {
+    // FC5 on tcgen05: h5 = SELU(d4 . W5 + b5), B = W5^T [168][336] prepared once per step
+    if (split_rows_bf16(d4, nc, 336, w->d4s, w->cap * 336, st)) return 1;
+    if (launch_gemm_tc<176, false, tc::GEMM_EPI_BIAS_SELU>(m, w->d4s, w->cap * 336, 336, w->w5ts, 168 * 336, 336, (int)nc, 168, 336,
+                                                           w->h5, 168, m->var("fc5/bias"), st))
+      return 1;
+    m->launches += 1;
+  } else {
     using F5 = FcCfg<168, 21, 8, 12, 8>;
     auto k = k_fc4<F5, true>;
     CK(set_smem(k, F5::SMEM_BYTES));
     k<<<(int)((nc + F5::M - 1) / F5::M), 256, F5::SMEM_BYTES, st>>>(d4, nc, 336, m->var("fc5/kernel"), m->var("fc5/bias"), w->h5, 168,
                                                                     168);
     CK(cudaGetLastError());
-    k_heads<336, 168><<<(int)((nc + 15) / 16), 256, 0, st>>>(d4, w->h5, nc, head_ptrs(m), w->out16, w->logits);
-    CK(cudaGetLastError());
   }
+  k_heads<336, 168><<<(int)((nc + 15) / 16), 256, 0, st>>>(d4, w->h5, nc, head_ptrs(m), w->out16, w->logits);
+  CK(cudaGetLastError());
   m->launches += 9 + (drop4 > 0.f ? 1 : 0);
   return 0;
 }
@@ -1440,11 +1448,17 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
     if (split_transpose_bf16(w->h5, nc, 168, 168, w->h5t, 168 * ldt, ldt, st)) return 1;
     if (split_transpose_bf16(w->g5, nc, 168, 176, w->gct, 184 * ldt, ldt, st)) return 1;
     if (split_transpose_bf16(w->dlog, nc, 16, 16, w->gct + 168 * ldt, 184 * ldt, ldt, st)) return 1;
-    if (launch_gemm_tc<192, true, tc::GEMM_EPI_STORE>(m, w->d4t, 336 * ldt, ldt, w->gct, 184 * ldt, ldt, 336, 184, (int)nc, w->tmp5,
-                                                      184, nullptr, st))
+    // 3 and 2 output tiles only: K (= sites) is split over the SMs and the slices meet in fp32 atomics
+    CK(cudaMemsetAsync(w->tmp5, 0, 336 * 184 * 4, st));
+    CK(cudaMemsetAsync(w->tmph, 0, 168 * 16 * 4, st));
+    GemmExtra sk;
+    sk.kslices = std::max(1, m->num_sms / 3);
+    if (launch_gemm_tc<192, true, tc::GEMM_EPI_ATOMIC>(m, w->d4t, 336 * ldt, ldt, w->gct, 184 * ldt, ldt, 336, 184, (int)nc, w->tmp5,
+                                                       184, nullptr, st, sk))
       return 1;
-    if (launch_gemm_tc<16, true, tc::GEMM_EPI_STORE>(m, w->h5t, 168 * ldt, ldt, w->gct + 168 * ldt, 184 * ldt, ldt, 168, 16,
-                                                     (int)nc, w->tmph, 16, nullptr, st))
+    sk.kslices = std::max(1, m->num_sms / 4);
+    if (launch_gemm_tc<16, true, tc::GEMM_EPI_ATOMIC>(m, w->h5t, 168 * ldt, ldt, w->gct + 168 * ldt, 184 * ldt, ldt, 168, 16,
+                                                      (int)nc, w->tmph, 16, nullptr, st, sk))
       return 1;
     k_scatter_fc5_heads<<<(336 * 168 + 255) / 256, 256, 0, st>>>(w->tmp5, w->tmph, gvar(m, "fc5/kernel"), hg);
     CK(cudaGetLastError());
@@ -1458,7 +1472,13 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
   }
   // FC5
   k_colsum<<<dim3((168 + 31) / 32, 32), 256, 0, st>>>(w->g5, nc, 176, 168, gvar(m, "fc5/bias"));
-  {
+  if (tcm) {
+    // data gradient of FC5: g4b [sites][336] = g5 . W5^T   (B = W5 as stored: [336][168] is K-major for K = 168)
+    if (split_rows_bf16(w->g5, nc, 168, w->g5s, w->cap * 168, st, 176)) return 1;
+    if (launch_gemm_tc<176, false, tc::GEMM_EPI_STORE>(m, w->g5s, w->cap * 168, 168, w->w5s, 336 * 168, 168, (int)nc, 336, 168, w->g4b,
+                                                       336, nullptr, st))
+      return 1;
+  } else {
     using F = FcCfg<336, 21, 16, 12, 8>;
     auto k = k_fc4<F, false>;
     CK(set_smem(k, F::SMEM_BYTES));
@@ -1472,8 +1492,10 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
     // weight gradient  dW4 [4608][336] += p3^T . dpre4   (K = sites)
     // p3s [sites][4608] (written by pool3) and g4s [sites][336] are its transposed operands: read in place, MN-major
     if (split_rows_bf16(w->g4, nc, 336, w->g4s, w->cap * 336, st)) return 1;
-    if (launch_gemm_tc<192, true, tc::GEMM_EPI_ACCUM, true>(m, w->p3s, w->cap * 4608, 4608, w->g4s, w->cap * 336, 336, 4608, 336,
-                                                            (int)nc, gvar(m, "fc4/kernel"), 336, nullptr, st))
+    GemmExtra k2;
+    k2.kslices = 2;  // 72 output tiles x 2 K slices = 144 CTAs; the gradient buffer was zeroed at the start of the step
+    if (launch_gemm_tc<192, true, tc::GEMM_EPI_ATOMIC, true>(m, w->p3s, w->cap * 4608, 4608, w->g4s, w->cap * 336, 336, 4608, 336,
+                                                             (int)nc, gvar(m, "fc4/kernel"), 336, nullptr, st, k2))
       return 1;
     // data gradient  gp3 [sites][4608] = dpre4 . W4^T      (B = W4 as stored: [4608][336] is K-major for K = 336)
     if (launch_gemm_tc<192, false, tc::GEMM_EPI_STORE>(m, w->g4s, w->cap * 336, 336, w->w4s, 4608 * 336, 336, (int)nc, 4608, 336,
@@ -1562,6 +1584,8 @@ static int train_prepare_weights(cvb_model* m, cudaStream_t st, bool backward) {
   if (m->train_mode != CVB_TRAIN_FP32) {  // the forward pass (getLoss included) reads W4^T, the data gradient W4
     if (split_transpose_bf16(m->var("fc4/kernel"), 4608, 336, 336, w->w4ts, 336 * 4608, 4608, st)) return 1;
     if (backward && split_rows_bf16(m->var("fc4/kernel"), 4608, 336, w->w4s, 4608 * 336, st)) return 1;
+    if (split_transpose_bf16(m->var("fc5/kernel"), 336, 168, 168, w->w5ts, 168 * 336, 336, st)) return 1;
+    if (backward && split_rows_bf16(m->var("fc5/kernel"), 336, 168, w->w5s, 336 * 168, st)) return 1;
     // forward conv2 / conv3 operands: rearranged, power-of-two scaled split-fp16 weights (as on the inference path)
     using F2 = trc::Conv2F;
     using F3 = trc::Conv3F;

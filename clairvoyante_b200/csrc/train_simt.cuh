@@ -38,6 +38,7 @@ struct TrainWork {
   // and rearranged weights: wf2 / wf3 forward (fp16, scaled: inv scales in fsc[0..1]), wd2 / wd3 flipped kernels (bf16)
   uint16_t *p1h = nullptr, *p2h = nullptr, *g3h = nullptr, *g2h = nullptr, *wf2 = nullptr, *wf3 = nullptr, *wd2 = nullptr,
            *wd3 = nullptr;
+  uint16_t *d4s = nullptr, *g5s = nullptr, *w5s = nullptr, *w5ts = nullptr;  // FC5 forward / data-gradient operands (split bf16)
   uint16_t *p1b = nullptr, *p2b = nullptr;  // p1 / p2 again as split bf16 (same layouts): A operands of the conv weight gradients
   float* fsc = nullptr;          // [0] conv2, [1] conv3 forward inverse weight scales, [2] = 1.0f
   unsigned int* amax = nullptr;  // [2] |w|max scratch

