@@ -547,7 +547,7 @@ extern "C" int cvb_get_step(const cvb_model* m, int64_t* t) { if (!m || !t) retu
 extern "C" int cvb_set_compute_mode(cvb_model* m, int mode) {
   if (!m) return fail("NULL model");
   if (mode != CVB_COMPUTE_FP32 && mode != CVB_COMPUTE_FP16X3)
-    return fail("cvb_set_compute_mode: mode %d is not built into this library yet", mode);
+    return fail("cvb_set_compute_mode: unknown mode %d", mode);
   CK(cudaSetDevice(m->device));
   if (mode == CVB_COMPUTE_FP16X3 && (m->variant == CVB_V3 ? tc_setup(m) : tc_setup_slim(m))) return 1;
   if (mode != m->compute_mode) {

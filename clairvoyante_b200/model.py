@@ -17,7 +17,7 @@ import numpy as np
 from . import _lib, tf_bundle, initializers, param
 
 _VARIANT_ID = {"v3": 0, "v3_slim": 1}
-COMPUTE_MODES = {"fp32": 0, "fp16x3": 1, "fp16": 2}
+COMPUTE_MODES = {"fp32": 0, "fp16x3": 1}
 TRAIN_MODES = {"fp32": 0, "bf16x3": 1, "bf16": 2}
 
 

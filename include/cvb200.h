@@ -37,9 +37,9 @@ typedef struct cvb_model cvb_model;
 enum { CVB_V3 = 0, CVB_V3_SLIM = 1 };
 /* arithmetic mode of the forward pass */
 enum {
-  CVB_COMPUTE_FP32 = 0,    /* fp32 SIMT everywhere (bit-faithful op order per layer) */
-  CVB_COMPUTE_FP16X3 = 1,  /* conv3/FC4 on tcgen05 with split-fp16 (hi+lo) operands, fp32 accumulate */
-  CVB_COMPUTE_FP16 = 2     /* conv3/FC4 on tcgen05 with plain fp16 operands, fp32 accumulate */
+  CVB_COMPUTE_FP32 = 0,   /* fp32 SIMT everywhere (bit-faithful op order per layer) */
+  CVB_COMPUTE_FP16X3 = 1  /* conv2/conv3/FC4/FC5+heads on tcgen05 with split-fp16 (hi+lo) operands, fp32 accumulate:
+                             fp32-equivalent (logits within 1e-3 of fp64), the default */
 };
 
 const char* cvb_last_error(void);

@@ -47,3 +47,15 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "/root/reference" not in txt, f
+
+
+def test_mode_enums_match_the_python_tables():
+    """CVB_COMPUTE_* / CVB_TRAIN_* in the header are the values model.py passes through ctypes"""
+    from clairvoyante_b200 import model
+    src = open(os.path.join(ROOT, "include", "cvb200.h")).read()
+    enums = {k: int(v) for k, v in re.findall(r"\b(CVB_[A-Z0-9_]+)\s*=\s*(\d+)", src)}
+    assert {"CVB_COMPUTE_" + k.upper(): v for k, v in model.COMPUTE_MODES.items()} == \
+        {k: v for k, v in enums.items() if k.startswith("CVB_COMPUTE_")}
+    assert {"CVB_TRAIN_" + k.upper(): v for k, v in model.TRAIN_MODES.items()} == \
+        {k: v for k, v in enums.items() if k.startswith("CVB_TRAIN_")}
+    assert enums["CVB_V3"] == model._VARIANT_ID["v3"] and enums["CVB_V3_SLIM"] == model._VARIANT_ID["v3_slim"]
