@@ -1046,7 +1046,8 @@ static int ensure_train_work(cvb_model* m) {
       {&w->h5, c * 24}, {&w->logits, c * 16}, {&w->out16, c * 16}, {&w->dlog, c * 16}, {&w->g5, c * 24},
       {&w->g4, c * 36}, {&w->g4b, c * 36}, {&w->gp3, c * 33 * 128}, {&w->g3p, c * 37 * 128}, {&w->gp2, c * 33 * 64},
       {&w->g2p, c * 35 * 64}, {&w->gp1, c * 33 * 32}, {&w->g1, c * 33 * 32}, {&w->w3t, 5 * 4 * 32 * 16},
-      {&w->w2t, 3 * 4 * 16 * 8}, {&w->tmpb, 36 * 16}, {&w->tmph, 24 * 16}, {&w->loss, 16}};
+      {&w->w2t, 3 * 4 * 16 * 8}, {&w->tmpb, 36 * 16}, {&w->tmph, 24 * 16}, {&w->tmpw, 5 * 64 * 128}, {&w->fsc, 16},
+      {&w->loss, 16}};
   if (m->variant != CVB_V3) {
     int64_t total = 0;
     for (auto& it : slim_items) total += (it.n + 63) / 64 * 64;
@@ -1055,6 +1056,24 @@ static int ensure_train_work(cvb_model* m) {
     int64_t off = 0;
     for (auto& it : slim_items) { *it.p = w->all + off; off += (it.n + 63) / 64 * 64; }
     w->p3 = w->c3;
+    {
+      // tensor-core conv3 + FC4 of the v3_slim step (CVB_TRAIN_SLIM_TC=0 keeps the SIMT kernels): operand planes [hi | lo]
+      const char* e = getenv("CVB_TRAIN_SLIM_TC");
+      w->slim_tc = e ? atoi(e) != 0 : true;
+      struct Item16 { uint16_t** p; int64_t n; };
+      Item16 it16[] = {{&w->p2h, 2 * c * 37 * 64}, {&w->p2b, 2 * c * 37 * 64}, {&w->g3h, 2 * c * 37 * 128}, {&w->p3s, 2 * c * 4224},
+                       {&w->g4s, 2 * c * 40}, {&w->w4s, 2 * 4224 * 40}, {&w->w4ts, 2 * 36 * 4224}, {&w->wf3, 2 * 5 * 128 * 64},
+                       {&w->wd3, 2 * 5 * 64 * 128}};
+      int64_t t16 = 0;
+      for (auto& it : it16) t16 += (it.n + 127) / 128 * 128;
+      CK(cudaMalloc(&w->all16, (size_t)t16 * 2));
+      CK(cudaMemset(w->all16, 0, (size_t)t16 * 2));  // pad rows / pad columns (g4s, w4s: 36 -> 40) stay zero
+      int64_t o16 = 0;
+      for (auto& it : it16) { *it.p = w->all16 + o16; o16 += (it.n + 127) / 128 * 128; }
+      CK(cudaMalloc(&w->amax, 16));
+      const float one = 1.f;
+      CK(cudaMemcpy(w->fsc + 2, &one, 4, cudaMemcpyHostToDevice));
+    }
     m->train = w;
     return 0;
   }
@@ -1151,8 +1170,10 @@ static int launch_gemm_tc(cvb_model* m, const uint16_t* a, int64_t a_plane, int6
 }
 static inline __nv_bfloat16* bf(uint16_t* p) { return reinterpret_cast<__nv_bfloat16*>(p); }
 static inline __half* hp(uint16_t* p) { return reinterpret_cast<__half*>(p); }
-static int split_rows_bf16(const float* src, int64_t rows, int cols, uint16_t* dst, int64_t plane, cudaStream_t st, int64_t ld_src = 0) {
-  tc::k_split_bf16<<<gsz(rows * (cols / 4)), 256, 0, st>>>(src, rows, cols, ld_src ? ld_src : cols, bf(dst), bf(dst + plane), cols);
+static int split_rows_bf16(const float* src, int64_t rows, int cols, uint16_t* dst, int64_t plane, cudaStream_t st, int64_t ld_src = 0,
+                           int64_t ld_dst = 0) {
+  tc::k_split_bf16<<<gsz(rows * (cols / 4)), 256, 0, st>>>(src, rows, cols, ld_src ? ld_src : cols, bf(dst), bf(dst + plane),
+                                                           ld_dst ? ld_dst : cols);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1173,14 +1194,15 @@ static int split_transpose_bf16(const float* src, int64_t R, int C, int64_t ld_s
 // the split-bf16 planes written by the forward pool kernel (in) and by pool-backward (g, COUT padded to CP) in place and
 // accumulates every (w', c) x (w, co) product with fp32 atomics; k_scatter_conv_wgrad adds the 13 of 16 (w', w) pairs that
 // are taps into dW.
-template <int CIN, int COUT, int KH, int CP>
+// SHIFT0 = -(row of the g layout that holds output row 0): -1 for the v3 layers, -2 for v3_slim's 5-row conv3
+template <int CIN, int COUT, int KH, int CP, int SHIFT0 = -1>
 static int launch_conv_wgrad_tc(cvb_model* m, const uint16_t* in, int64_t in_plane, const uint16_t* g, int64_t g_plane, int64_t R,
                                 float* dW, cudaStream_t st) {
   TrainWork* w = m->train;
   constexpr int MA = 4 * CIN, NB = 4 * CP;
   CK(cudaMemsetAsync(w->tmpw, 0, (size_t)KH * MA * NB * 4, st));
   GemmExtra ex;
-  ex.batches = KH; ex.a_kshift0 = -1; ex.a_kshift_per_batch = 1; ex.c_batch_stride = (int64_t)MA * NB;
+  ex.batches = KH; ex.a_kshift0 = SHIFT0; ex.a_kshift_per_batch = 1; ex.c_batch_stride = (int64_t)MA * NB;
   ex.kslices = std::max(1, m->num_sms / KH);
   if (launch_gemm_tc<NB, false, tc::GEMM_EPI_ATOMIC, true>(m, in, in_plane, MA, g, g_plane, NB, MA, NB, (int)R, w->tmpw, NB, nullptr,
                                                            st, ex))
@@ -1198,6 +1220,9 @@ using Conv2F = tc::ConvTcCfg<30, 2, 16, 32, 29, 1, 29, 0, 6, true>;             
 using Conv3F = tc::ConvTcCfg<28, 3, 32, 48, 26, 1, 26, 0, 4, true>;                      // p2h [.][28][128] -> c3 [.][26][192]
 using Conv3D = tc::ConvTcCfg<28, 3, 64, 32, 26, 1, 26, 0, 4, true, 2, false, true>;      // g3h [.][28][256] -> gp2 [.][26][128]
 using Conv2D = tc::ConvTcCfg<30, 2, 32, 16, 29, 1, 29, 0, 4, true, 2, false, true>;      // g2h [.][30][128] -> gp1 [.][29][64]
+// v3_slim conv3 (5x4, 16 -> 32, rows padded 2 + 33 + 2): forward = the inference configuration; data gradient 32 -> 16
+using SlimConv3D = tc::ConvTcCfg<37, 5, 32, 16, 33, 1, 33, 0, 4, true, 2, false, true>;  // g3h [.][37][128] -> gp2 [.][33][64]
+using SlimConv3DS = tc::ConvSlabCfg<SlimConv3D, 3, 6>;
 using Conv2FS = tc::ConvSlabCfg<Conv2F, 4, 8>;
 using Conv3FS = tc::ConvSlabCfg<Conv3F, 3, 6>;
 using Conv3DS = tc::ConvSlabCfg<Conv3D, 3, 3>;
@@ -1255,9 +1280,23 @@ static int train_forward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t se
   if (launch_conv_keep<ConvCfg<4, 8, 1, 33, 12, 8, 8>>(m, w->x, nc, m->var("conv1/kernel"), m->var("conv1/bias"), w->c1, true, st)) return 1;
   k_pool_fwd<1><<<gsz(nc * 33 * 8), 256, 0, st>>>(w->c1, nc, 33, 32, w->p1p, 35, 1, nullptr, nullptr);
   if (launch_conv_keep<ConvCfg<8, 16, 3, 33, 6, 8, 8>>(m, w->p1p, nc, m->var("conv2/kernel"), m->var("conv2/bias"), w->c2, true, st)) return 1;
-  k_pool_fwd<1><<<gsz(nc * 33 * 16), 256, 0, st>>>(w->c2, nc, 33, 64, w->p2p, 37, 2, nullptr, nullptr);
-  if (launch_conv_keep<ConvCfg<16, 32, 5, 33, 3, 8, 8>>(m, w->p2p, nc, m->var("conv3/kernel"), m->var("conv3/bias"), w->c3, true, st)) return 1;
-  {
+  const bool stc = w->slim_tc && m->train_mode != CVB_TRAIN_FP32;
+  k_pool_fwd<1><<<gsz(nc * 33 * 16), 256, 0, st>>>(w->c2, nc, 33, 64, w->p2p, 37, 2, stc ? hp(w->p2h) : nullptr,
+                                                   stc ? hp(w->p2h) + w->cap * 37 * 64 : nullptr, stc ? bf(w->p2b) : nullptr,
+                                                   stc ? bf(w->p2b) + w->cap * 37 * 64 : nullptr);
+  if (stc) {
+    // conv3 on the tcgen05 slab kernel (the inference configuration already keeps every SELU output: no pooling in slim),
+    // FC4 = c3 [sites][4224] . W4 as a split-bf16 GEMM (N = 36 in one 48-column tile)
+    if (launch_train_conv<tc::SlimConv3Tc, tc::SlimConv3Slab>(m, w->p2h, w->cap * 37 * 64, w->wf3, nc, m->var("conv3/bias"), w->fsc + 1,
+                                                              w->c3, st))
+      return 1;
+    if (split_rows_bf16(w->c3, nc, 4224, w->p3s, w->cap * 4224, st)) return 1;
+    if (launch_gemm_tc<48, true, tc::GEMM_EPI_BIAS_SELU>(m, w->p3s, w->cap * 4224, 4224, w->w4ts, 36 * 4224, 4224, (int)nc, 36, 4224,
+                                                         w->h4, 36, m->var("fc4/bias"), st))
+      return 1;
+    m->launches += 2;
+  } else {
+    if (launch_conv_keep<ConvCfg<16, 32, 5, 33, 3, 8, 8>>(m, w->p2p, nc, m->var("conv3/kernel"), m->var("conv3/bias"), w->c3, true, st)) return 1;
     using F = FcCfg<36, 9, 4, 28, 8>;
     auto k = k_fc4<F, true>;
     CK(set_smem(k, F::SMEM_BYTES));
@@ -1303,8 +1342,28 @@ static int train_backward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t s
   k_dense_bwd_small<<<gsz(nc * 36), 256, 0, st>>>(w->g5, 24, 18, m->var("fc5/kernel"), 36, w->g4b, 36, nc);
   k_fc4_bwd_elem<<<gsz(nc * 36), 256, 0, st>>>(w->g4, w->g4b, w->h4, nc * 36, index0, seed, drop_const(drop4), drop4 > 0.f ? 1 : 0);
   // FC4
-  k_gemm_tn<<<dim3(4224 / 64, 1), 256, 0, st>>>(w->c3, 4224, w->g4, 36, gvar(m, "fc4/kernel"), 36, 4224, 36, nc);
+  const bool stc = w->slim_tc && m->train_mode != CVB_TRAIN_FP32;
   k_colsum<<<dim3(2, 32), 256, 0, st>>>(w->g4, nc, 36, 36, gvar(m, "fc4/bias"));
+  if (stc) {
+    // dpre4 [sites][36] as split bf16 with rows padded to 40 (TMA strides are 16-byte granular); weight gradient reads
+    // c3 / dpre4 in place as MN-major operands (K = sites, 33 output tiles x 4 K slices), data gradient is K-major (K = 36)
+    if (split_rows_bf16(w->g4, nc, 36, w->g4s, w->cap * 40, st, 36, 40)) return 1;
+    GemmExtra k4;
+    k4.kslices = 4;
+    if (launch_gemm_tc<64, true, tc::GEMM_EPI_ATOMIC, true>(m, w->p3s, w->cap * 4224, 4224, w->g4s, w->cap * 40, 40, 4224, 36, (int)nc,
+                                                            gvar(m, "fc4/kernel"), 36, nullptr, st, k4))
+      return 1;
+    if (launch_gemm_tc<192, false, tc::GEMM_EPI_STORE>(m, w->g4s, w->cap * 40, 40, w->w4s, 4224 * 40, 40, (int)nc, 4224, 36, w->gp3, 4224,
+                                                       nullptr, st))
+      return 1;
+    k_pool_bwd_selu<1, 128, 256, 32><<<gsz(nc * 33 * 32), 256, 0, st>>>(w->gp3, w->c3, nc, 33, w->g3p, 37, 2, gvar(m, "conv3/bias"),
+                                                                        bf(w->g3h), bf(w->g3h) + w->cap * 37 * 128);
+    if (launch_conv_wgrad_tc<16, 32, 5, 32, -2>(m, w->p2b, w->cap * 37 * 64, w->g3h, w->cap * 37 * 128, nc * 37, gvar(m, "conv3/kernel"), st))
+      return 1;
+    if (launch_train_conv<trc::SlimConv3D, trc::SlimConv3DS>(m, w->g3h, w->cap * 37 * 128, w->wd3, nc, nullptr, w->fsc + 2, w->gp2, st))
+      return 1;
+  } else {
+  k_gemm_tn<<<dim3(4224 / 64, 1), 256, 0, st>>>(w->c3, 4224, w->g4, 36, gvar(m, "fc4/kernel"), 36, 4224, 36, nc);
   k_dense_bwd_small<<<gsz(nc * 4224), 256, 0, st>>>(w->g4, 36, 36, m->var("fc4/kernel"), 4224, w->gp3, 4224, nc);
   // conv3 (5x4, 16 -> 32)
   k_pool_bwd_selu<1, 128, 256><<<gsz(nc * 33 * 32), 256, 0, st>>>(w->gp3, w->c3, nc, 33, w->g3p, 37, 2, gvar(m, "conv3/bias"));
@@ -1315,6 +1374,7 @@ static int train_backward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t s
     k<<<(int)std::min<int64_t>((nc + 3) / 4, sms), W::THREADS, W::SMEM_BYTES, st>>>(w->p2p, w->g3p, 37, 2, nc, gvar(m, "conv3/kernel"));
     CK(cudaGetLastError());
     if (launch_conv_keep<ConvCfg<32, 16, 5, 33, 3, 8, 8, 2>>(m, w->g3p, nc, w->w3t, nullptr, w->gp2, false, st)) return 1;
+  }
   }
   // conv2 (3x4, 8 -> 16)
   k_pool_bwd_selu<1, 64, 256><<<gsz(nc * 33 * 16), 256, 0, st>>>(w->gp2, w->c2, nc, 33, w->g2p, 35, 1, gvar(m, "conv2/bias"));
@@ -1574,9 +1634,26 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
 static int train_prepare_weights(cvb_model* m, cudaStream_t st, bool backward) {
   TrainWork* w = m->train;
   if (m->variant != CVB_V3) {
+    const bool stc = w->slim_tc && m->train_mode != CVB_TRAIN_FP32;
+    if (stc) {  // forward operands (getLoss included): conv3 weights rearranged + scaled fp16, W4^T [36][4224] split bf16
+      using F3 = tc::SlimConv3Tc;
+      CK(cudaMemsetAsync(w->amax, 0, 8, st));
+      tc::k_absmax<<<32, 256, 0, st>>>(m->var("conv3/kernel"), 5 * 4 * 16 * 32, w->amax + 1);
+      tc::k_prep_conv_weights<F3><<<(F3::B_ROWS_TOTAL * F3::KROW + 255) / 256, 256, 0, st>>>(
+          m->var("conv3/kernel"), w->amax + 1, hp(w->wf3), hp(w->wf3) + F3::B_ROWS_TOTAL * F3::KROW, w->fsc + 1);
+      if (split_transpose_bf16(m->var("fc4/kernel"), 4224, 36, 36, w->w4ts, 36 * 4224, 4224, st)) return 1;
+      m->launches += 3;
+    }
     if (!backward) return 0;
     k_flip_conv_weights<<<(5 * 4 * 16 * 32 + 255) / 256, 256, 0, st>>>(m->var("conv3/kernel"), 5, 16, 32, w->w3t);
     k_flip_conv_weights<<<(3 * 4 * 8 * 16 + 255) / 256, 256, 0, st>>>(m->var("conv2/kernel"), 3, 8, 16, w->w2t);
+    if (stc) {
+      using D3 = trc::SlimConv3D;
+      if (split_rows_bf16(m->var("fc4/kernel"), 4224, 36, w->w4s, 4224 * 40, st, 36, 40)) return 1;
+      tc::k_prep_conv_weights_bf16<D3, 32><<<(D3::B_ROWS_TOTAL * D3::KROW + 255) / 256, 256, 0, st>>>(
+          w->w3t, bf(w->wd3), bf(w->wd3) + D3::B_ROWS_TOTAL * D3::KROW);
+      m->launches += 2;
+    }
     CK(cudaGetLastError());
     m->launches += 2;
     return 0;

@@ -16,6 +16,7 @@ __device__ __forceinline__ float f4c(const float4& v, int q) { return q == 0 ? v
 
 struct TrainWork {
   int64_t cap = 0;  // sites per micro-chunk
+  bool slim_tc = false;  // v3_slim: conv3 + FC4 of the training step on tcgen05
   float *x = nullptr, *y = nullptr;  // the micro-chunk being computed: one of the two upload slots below
   float *xs[2] = {nullptr, nullptr}, *ys[2] = {nullptr, nullptr};
   cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};  // slot uploaded / slot's compute finished

@@ -71,13 +71,13 @@ def test_gradients_match_autograd(variant, rate, mode):
     m.close()
 
 
-@pytest.mark.parametrize("n", [1, 37, 129, 5121])
-def test_tensor_and_simt_training_paths_agree(n):
-    """the tcgen05 FC4 contractions (split bf16) against the fp32 SIMT kernels on ragged batch sizes: K = sites of the
+@pytest.mark.parametrize("variant,n", [("v3", 1), ("v3", 37), ("v3", 129), ("v3", 5121), ("v3_slim", 37), ("v3_slim", 5121)])
+def test_tensor_and_simt_training_paths_agree(variant, n):
+    """the tcgen05 contractions (split bf16) against the fp32 SIMT kernels on ragged batch sizes: K = sites of the
     weight gradient not a multiple of the 32-wide K block, M tiles with masked rows, two micro-chunks"""
-    W = I.init_weights("v3", 13)
+    W = I.init_weights(variant, 13)
     x, y = synth.make_sites(n, 14), synth.make_labels(n, 14)
-    m = _model(W, "v3", dropoutRateFC4=0.5)
+    m = _model(W, variant, dropoutRateFC4=0.5)
     out = {}
     for mode in ("fp32", "bf16x3"):
         m.setTrainMode(mode)
