@@ -6,7 +6,7 @@
 //
 // One CTA = 128 sites x one half of the 336 outputs (176 columns).  Warp roles (192 threads):
 //   warp 0    : TMA producer (one elected lane) -- per K-block of 32: A_hi, A_lo (128 x 64 B) and
-//               B_hi, B_lo (176 x 64 B) into a 4-stage smem ring, 64-byte swizzle
+//               B_hi, B_lo (176 x 64 B) into a 5-stage smem ring, 64-byte swizzle
 //   warp 1    : TMEM allocator + MMA issuer (one elected lane): per stage 2 K-steps x 3 terms of
 //               tcgen05.mma.cta_group::1.kind::f16, M = 128, N = 176, into ping-pong TMEM accumulators
 //   warps 2-5 : epilogue -- tcgen05.ld each finished K-chunk's 128 x 176 fp32 partial (one site per thread),

@@ -7,7 +7,7 @@
 // x = hi + lo (two bf16, ~16 mantissa bits, fp32's exponent range so gradients need no scaling):
 //     A B^T ~= A_lo B_hi + A_hi B_lo + A_hi B_hi      (terms = 3; terms = 1 keeps only the last = plain bf16)
 // fp32 accumulation in TMEM.  Layout of a CTA as in fc4_tc.cuh: 192 threads = TMA producer warp, MMA issuer
-// warp, 4 epilogue warps (one output row per thread); 4-stage ring of {A_hi, A_lo 128 x 64 B, B_hi, B_lo BN x 64 B},
+// warp, 4 epilogue warps (one output row per thread); 5-stage ring (4 for BN = 256) of {A_hi, A_lo 128 x 64 B, B_hi, B_lo BN x 64 B},
 // 64-byte swizzle.  CHUNKED: K is accumulated from zero in chunks of 256 into ping-pong TMEM buffers and the
 // chunk partials are added in fp32 registers (tcgen05 accumulation truncates; see fc4_tc.cuh).
 // Rows / columns / K beyond the tensor edges are zero-filled by TMA and masked in the epilogue.
