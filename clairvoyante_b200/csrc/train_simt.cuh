@@ -50,6 +50,7 @@ static inline void train_work_free(TrainWork* w) {
   if (!w) return;
   cudaFree(w->all);
   cudaFree(w->all16);
+  cudaFree(w->amax);
   for (int i = 0; i < 2; ++i) {
     if (w->ev_up[i]) cudaEventDestroy(w->ev_up[i]);
     if (w->ev_done[i]) cudaEventDestroy(w->ev_done[i]);
