@@ -76,6 +76,14 @@ SIGNATURES = {
     "cvb_blosc_info": (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
                                       ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "cvb_blosc_decompress": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, ctypes.POINTER(c_i64)]),
+    "cvb_pileup_create": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "cvb_pileup_destroy": (ctypes.c_int, [c_vp]),
+    "cvb_pileup_feed": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int]),
+    "cvb_pileup_ready": (c_i64, [c_vp]),
+    "cvb_pileup_take": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(c_i64)]),
+    "cvb_pileup_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64)]),
+    "cvb_pileup_format_rows": (c_i64, [ctypes.c_char_p, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64]),
     "cvb_crc32c": (ctypes.c_uint32, [ctypes.c_uint32, c_vp, c_i64]),
     "cvb_alloc_pinned": (ctypes.c_int, [c_i64, ctypes.POINTER(c_vp)]),
     "cvb_free_pinned": (ctypes.c_int, [c_vp]),

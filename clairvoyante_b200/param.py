@@ -8,6 +8,7 @@ parameterOutputPlaceHolder = 6
 flankingBaseNum = 16
 matrixNum = 4
 bloscBlockSize = 500
+expandReferenceRegion = 1000000   # dataPrepScripts/param.py:3 (reference bases fetched around a --ctgStart/--ctgEnd region)
 
 # Model hyperparameters
 trainBatchSize = 10000

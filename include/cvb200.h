@@ -142,6 +142,30 @@ uint32_t cvb_crc32c(uint32_t crc, const void* data, int64_t n);
 int cvb_blosc_info(const void* frame, int64_t n, int64_t* nbytes, int64_t* cbytes, int* typesize, int* flags);
 int cvb_blosc_decompress(const void* frame, int64_t n, void* dst, int64_t cap, int64_t* out_n);
 
+/* ---- alignment pile-up: SAM records -> candidate tensors ---------------------------------------------------------------
+ * Replaces dataPrepScripts/CreateTensor.py (GenerateTensor :23-59, OutputAlnTensor :96-258), the producer of the tensor
+ * text stream in the reference's pipelines (callVarBam.py:61).  Host code; needs no GPU.  One handle = one contig / region.
+ *   ref_seq / ref_len : reference bases of the fetched region (what `samtools faidx` returned, header and newlines removed)
+ *   ref_start         : 1-based position of ref_seq[0] (the reference's args.refStart), 0 = sequence starts at position 1
+ *   cand_pos          : candidate positions (column 2 of the candidate list, 1-based), any order
+ *   min_mq, dcov, min_coverage, consider_left_edge : the command-line options of CreateTensor.py:281-300
+ * cvb_pileup_feed takes SAM text (`samtools view -F 2308` output, position-sorted) in arbitrary chunks; final_chunk != 0
+ * flushes the centres still open.  Finished tensors queue up in ascending position order: cvb_pileup_take copies up to
+ * max_sites of them as float32 (n,33,4,4) RAW counts (CreateTensor's alnCode: channel 0 is not yet subtracted,
+ * utils_v2.py:46 does that) plus their centre positions.  stats = {SAM rows, rows used, malformed rows, open centres}.     */
+typedef struct cvb_pileup cvb_pileup;
+int cvb_pileup_create(const char* ref_seq, int64_t ref_len, int64_t ref_start, const int64_t* cand_pos, int64_t n_cand,
+                      int min_mq, int dcov, int min_coverage, int consider_left_edge, cvb_pileup** out);
+int cvb_pileup_destroy(cvb_pileup* p);
+int cvb_pileup_feed(cvb_pileup* p, const char* sam, int64_t len, int final_chunk);
+int64_t cvb_pileup_ready(const cvb_pileup* p);
+int cvb_pileup_take(cvb_pileup* p, int64_t max_sites, float* x, int64_t* center, int64_t* n_out);
+int cvb_pileup_stats(const cvb_pileup* p, int64_t stats[4]);
+/* the text rows of CreateTensor.py:56 for n tensors ("ctg pos refseq33 v0 .. v527\n", values "%0.1f"); returns the number of
+ * bytes written to out[0, cap) or -1 (cap must allow 8.6 KB + strlen(ctg) per row) */
+int64_t cvb_pileup_format_rows(const char* ctg, const int64_t* center, const float* x, int64_t n, const char* ref_seq,
+                               int64_t ref_len, int64_t ref_start, char* out, int64_t cap);
+
 /* pinned host memory helpers for the batch feed (utils_v2.GetTensor replacement) */
 int cvb_alloc_pinned(int64_t bytes, void** out);
 int cvb_free_pinned(void* p);
