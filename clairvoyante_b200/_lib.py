@@ -84,6 +84,15 @@ SIGNATURES = {
     "cvb_pileup_take": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(c_i64)]),
     "cvb_pileup_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64)]),
     "cvb_pileup_format_rows": (c_i64, [ctypes.c_char_p, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64]),
+    "cvb_candidates_create": (ctypes.c_int, [ctypes.c_char_p, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, ctypes.c_int,
+                                             ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_uint64,
+                                             ctypes.POINTER(c_vp)]),
+    "cvb_candidates_destroy": (ctypes.c_int, [c_vp]),
+    "cvb_candidates_feed": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int]),
+    "cvb_candidates_pending_bytes": (c_i64, [c_vp]),
+    "cvb_candidates_pending": (c_i64, [c_vp]),
+    "cvb_candidates_take": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp, c_i64, ctypes.POINTER(c_i64)]),
+    "cvb_candidates_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64)]),
     "cvb_crc32c": (ctypes.c_uint32, [ctypes.c_uint32, c_vp, c_i64]),
     "cvb_alloc_pinned": (ctypes.c_int, [c_i64, ctypes.POINTER(c_vp)]),
     "cvb_free_pinned": (ctypes.c_int, [c_vp]),

@@ -166,6 +166,33 @@ int cvb_pileup_stats(const cvb_pileup* p, int64_t stats[4]);
 int64_t cvb_pileup_format_rows(const char* ctg, const int64_t* center, const float* x, int64_t n, const char* ref_seq,
                                int64_t ref_len, int64_t ref_start, char* out, int64_t cap);
 
+/* ---- variant-candidate extraction: SAM records -> candidate positions ------------------------------------------------
+ * Replaces dataPrepScripts/ExtractVariantCandidates.py (OutputCandidate :22-42, MakeCandidates :53-253), the first stage
+ * of the reference's calling pipeline (callVarBam.py:56-66).  Host code; needs no GPU.  One handle = one contig / region.
+ *   ctg_name                 : rows whose RNAME differs are skipped (:133-135)
+ *   ref_seq, ref_len, ref_start : as for cvb_pileup_create
+ *   ctg_start, ctg_end       : the region test of :187-188 exactly as the reference evaluates it -- 0-based position p is
+ *                              kept when ctg_start <= p <= ctg_end, where ctg_start is the --ctgStart argument + 1 (:63);
+ *                              pass -1, -1 for no region
+ *   bed_begin/bed_end/n_bed  : half-open [begin, end) intervals of this contig as the reference builds them (:95-98:
+ *                              end = column 3 - 1, +1 if that equals begin); n_bed = -1 for no BED file
+ *   min_mq, min_coverage, threshold : --minMQ, --minCoverage, --threshold
+ *   output_prob, seed        : --gen4Training subsample probability (< 0: keep everything), hash seed
+ * cvb_candidates_feed takes position-sorted SAM text in arbitrary chunks (final_chunk != 0 ends the input);
+ * cvb_candidates_take moves out the finished rows ("ctg pos refBase total k0 n0 .. k6 n6\n") and their 1-based positions.
+ * stats = {SAM rows, reads processed, malformed rows, open positions}.                                                  */
+typedef struct cvb_candidates cvb_candidates;
+int cvb_candidates_create(const char* ctg_name, const char* ref_seq, int64_t ref_len, int64_t ref_start, int64_t ctg_start,
+                          int64_t ctg_end, const int64_t* bed_begin, const int64_t* bed_end, int64_t n_bed, int min_mq,
+                          double min_coverage, double threshold, double output_prob, uint64_t seed, cvb_candidates** out);
+int cvb_candidates_destroy(cvb_candidates* c);
+int cvb_candidates_feed(cvb_candidates* c, const char* sam, int64_t len, int final_chunk);
+int64_t cvb_candidates_pending_bytes(const cvb_candidates* c);
+int64_t cvb_candidates_pending(const cvb_candidates* c);
+int cvb_candidates_take(cvb_candidates* c, char* text, int64_t text_cap, int64_t* text_len, int64_t* pos, int64_t pos_cap,
+                        int64_t* n_pos);
+int cvb_candidates_stats(const cvb_candidates* c, int64_t stats[4]);
+
 /* pinned host memory helpers for the batch feed (utils_v2.GetTensor replacement) */
 int cvb_alloc_pinned(int64_t bytes, void** out);
 int cvb_free_pinned(void* p);

@@ -9,8 +9,8 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from clairvoyante_b200 import CreateTensor as CT   # noqa: E402
-from oracle import createtensor_oracle as O          # noqa: E402
+from clairvoyante_b200 import CreateTensor as CT, ExtractVariantCandidates as EVC   # noqa: E402
+from oracle import createtensor_oracle as O, candidates_oracle as OC                  # noqa: E402
 
 
 def make(ref_len, coverage, read_len=150, seed=0, spacing=50):
@@ -19,17 +19,21 @@ def make(ref_len, coverage, read_len=150, seed=0, spacing=50):
     n_reads = ref_len * coverage // read_len
     starts = np.sort(rng.integers(0, ref_len - read_len - 10, size=n_reads))
     rows = []
+    snps = {int(q): "ACGT"[("ACGT".index(ref[int(q)]) + 1 + int(rng.integers(0, 3))) % 4]      # heterozygous SNP every ~300 bases
+            for q in rng.integers(0, ref_len, size=ref_len // 300)}
+    hap = "".join(snps.get(i, c) for i, c in enumerate(ref))
     for i, st in enumerate(starts.tolist()):
         r = rng.random()
+        src = hap if rng.random() < 0.5 else ref
         if r < 0.85:
-            cigar, seq = "%dM" % read_len, ref[st:st + read_len]
+            cigar, seq = "%dM" % read_len, src[st:st + read_len]
         elif r < 0.93:
             a = int(rng.integers(20, 100)); k = int(rng.integers(1, 5))
-            cigar, seq = "%dM%dI%dM" % (a, k, read_len - a - k), ref[st:st + a] + "ACGT"[:k] + ref[st + a:st + read_len - k]
+            cigar, seq = "%dM%dI%dM" % (a, k, read_len - a - k), src[st:st + a] + "ACGT"[:k] + src[st + a:st + read_len - k]
         else:
             a = int(rng.integers(20, 100)); k = int(rng.integers(1, 5))
-            cigar, seq = "%dM%dD%dM" % (a, k, read_len - a), ref[st:st + a] + ref[st + a + k:st + read_len + k]
-        if rng.random() < 0.3:                              # a mismatch
+            cigar, seq = "%dM%dD%dM" % (a, k, read_len - a), src[st:st + a] + src[st + a + k:st + read_len + k]
+        if rng.random() < 0.3:                              # a sequencing error
             j = int(rng.integers(0, len(seq))); seq = seq[:j] + "ACGT"[(("ACGT".index(seq[j]) + 1) % 4)] + seq[j + 1:]
         rows.append("r%d\t0\tctg\t%d\t60\t%s\t*\t0\t0\t%s\t*" % (i, st + 1, cigar, seq))
     cands = sorted(set(int(c) for c in rng.integers(20, ref_len - 20, size=ref_len // spacing)))
@@ -71,6 +75,24 @@ def main():
     dt = time.perf_counter() - t
     out["python_restatement"] = dict(sites=len(w), sites_per_s=round(len(w) / dt), reads_per_s=round(sub.count("\n") / dt))
     out["speedup_sites_per_s"] = round(out["native"]["sites_per_s"] / max(out["python_restatement"]["sites_per_s"], 1), 1)
+    # stage 1 of the pipeline: candidate extraction on the same reads
+    best = None
+    for _ in range(3):
+        t = time.perf_counter()
+        c = EVC.Candidates("ctg", ref)
+        c.feed(b, final=True)
+        text, pos = c.take()
+        dt = time.perf_counter() - t
+        c.close()
+        best = dt if best is None else min(best, dt)
+    t = time.perf_counter()
+    w = OC.make_candidates(sub, "ctg", ref)
+    dt = time.perf_counter() - t
+    out["candidates_native"] = dict(seconds=round(best, 4), candidates=len(pos), reads_per_s=round(n_reads / best),
+                                    sam_mb_per_s=round(len(b) / best / 1e6, 1), threads=1)
+    out["candidates_python_restatement"] = dict(reads_per_s=round(sub.count("\n") / dt))
+    out["candidates_speedup_reads_per_s"] = round(out["candidates_native"]["reads_per_s"] /
+                                                  max(out["candidates_python_restatement"]["reads_per_s"], 1), 1)
     print(json.dumps(out))
 
 
