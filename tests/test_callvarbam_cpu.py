@@ -71,3 +71,23 @@ def test_candidate_sites_from_vcf(tmp_path, monkeypatch):
     assert n == 40
     body = [l for l in open(tmp_path / "o.vcf") if not l.startswith("#")]
     assert set(int(l.split("\t")[1]) for l in body) <= set(cands[:40])
+
+
+def test_parallel_command_generator(tmp_path):
+    """callVarBamParallel.py:66-89: chunks of refChunkSize over the major contigs of the .fai, BED-less chunks skipped"""
+    from clairvoyante_b200 import callVarBamParallel as P
+    (tmp_path / "ref.fa").write_text(">chr1\nACGT\n")
+    (tmp_path / "ref.fa.fai").write_text("chr1\t2500\t6\t60\t61\nchrUn_x\t900\t9\t60\t61\n21\t1000\t9\t60\t61\n")
+    (tmp_path / "a.bam").write_text("")
+    (tmp_path / "r.bed").write_text("chr1\t1200\t1300\n21\t0\t10\n")
+    a = types.SimpleNamespace(chkpnt_fn="model", ref_fn=str(tmp_path / "ref.fa"), bed_fn=None, refChunkSize=1000, bam_fn=str(tmp_path / "a.bam"),
+                              vcf_fn=None, output_prefix="out/p", includingAllContigs=False, threshold=0.2, minCoverage=4, qual=None,
+                              sampleName="S", considerleftedge=True, samtools="samtools", slim=False)
+    cmds = P.commands(a)
+    regions = [(c.split("--ctgName ")[1].split()[0], int(c.split("--ctgStart ")[1].split()[0]), int(c.split("--ctgEnd ")[1].split()[0])) for c in cmds]
+    assert regions == [("chr1", 0, 1000), ("chr1", 1000, 2000), ("chr1", 2000, 2500), ("21", 0, 1000)]
+    assert all("--call_fn out/p.%s_%d_%d.vcf" % r in c for r, c in zip(regions, cmds))
+    a.bed_fn = str(tmp_path / "r.bed")
+    a.includingAllContigs = True
+    cmds = P.commands(a)
+    assert [c.split("--ctgStart ")[1].split()[0] for c in cmds] == ["1000", "0"] and all("--bed_fn" in c for c in cmds)
