@@ -77,3 +77,69 @@ def test_train_all_schedule(tmp_path, monkeypatch):
     # validation losses 10,9,10,9,10,9 zig-zag -> first switch after epoch 6, next after 6 more, third ends training
     assert epochs == 18 and abs(m.lr - 1e-5) < 1e-12 and abs(m.lam - 1e-5) < 1e-12
     assert m.saved[0].endswith("m-000001") and m.saved[-1].endswith("m-000018")
+
+
+def _dataset(tmp_path, total):
+    X = synth.make_sites(total, 1); Y = synth.make_labels(total, 1).astype(np.float64)
+    xb = [U.pack_array(X[i:i + 50]) for i in range(0, total, 50)]
+    yb = [U.pack_array(Y[i:i + 50]) for i in range(0, total, 50)]
+    fn = str(tmp_path / "d.bin")
+    with open(fn, "wb") as fh:
+        for p in (total, xb, yb, []):
+            pickle.dump(p, fh)
+    return fn, X, Y
+
+
+def test_train_nonstop_runs_to_max_epoch_and_resumes(tmp_path, monkeypatch):
+    """trainNonstop.py:78-124: same epoch loop, no schedule, a checkpoint per epoch until maxEpoch; resume epoch = the
+    checkpoint suffix + 1"""
+    from clairvoyante_b200 import trainNonstop
+    monkeypatch.setattr(param, "trainBatchSize", 100)
+    monkeypatch.setattr(param, "predictBatchSize", 10)
+    monkeypatch.setattr(param, "bloscBlockSize", 50)
+    monkeypatch.setattr(param, "maxEpoch", 5)
+    fn, _, _ = _dataset(tmp_path, 503)
+    m = _Stub()
+    args = types.SimpleNamespace(bin_fn=fn, tensor_fn=None, var_fn=None, bed_fn=None, chkpnt_fn=None, learning_rate=2e-3, lambd=3e-3,
+                                 ochk_prefix=str(tmp_path / "ck" / "m"), olog_dir=None, v2=False, v3=True, slim=False)
+    trainNonstop.TrainAll(args, m, U)
+    assert [s[-8:] for s in m.saved] == ["m-000001", "m-000002", "m-000003", "m-000004"]
+    assert m.trained == [100, 100, 100, 100] * 4 and m.lr == 2e-3 and m.lam == 3e-3      # never decayed
+    m2 = _Stub()
+    args.chkpnt_fn = str(tmp_path / "ck" / "m-000003")
+    trainNonstop.TrainAll(args, m2, U)
+    assert [s[-8:] for s in m2.saved] == ["m-000004"]
+
+
+def test_evaluate_report(tmp_path, monkeypatch):
+    """evaluate.py:55-110 with a model that answers from the labels: perfect on three heads, second-best on base change
+    for every third site"""
+    from clairvoyante_b200 import evaluate
+    monkeypatch.setattr(param, "predictBatchSize", 64)
+    monkeypatch.setattr(param, "bloscBlockSize", 50)
+    total = 333
+    fn, X, Y = _dataset(tmp_path, total)
+
+    class Oracle(object):
+        def __init__(self):
+            self.ptr = 0; self.calls = []
+        def predict(self, Xb):
+            n = len(Xb); y = Y[self.ptr:self.ptr + n].astype(np.float32); idx = np.arange(self.ptr, self.ptr + n)
+            self.ptr += n; self.calls.append(n)
+            truth = np.argmax(y[:, 0:4], axis=1)                  # (all-zero rows count as class 0, like np.argmax in :81)
+            base = np.full((n, 4), 0.1, np.float32)
+            base[np.arange(n), truth] = 0.6
+            worse = idx % 3 == 0                                  # push another class above the true one
+            other = (truth + 1) % 4
+            base[worse, other[worse]] = 0.9
+            return base, y[:, 4:6], y[:, 6:10], y[:, 10:16]
+
+    m = Oracle()
+    args = types.SimpleNamespace(bin_fn=fn, tensor_fn=None, var_fn=None, bed_fn=None)
+    res = evaluate.Test(args, m, U)
+    assert m.calls == [64] * 5 + [13]
+    assert res["all"] == total and res["top2"] == total and res["top1"] == total - len(range(0, total, 3))
+    for key, lo, hi in (("zygosity", 4, 6), ("varType", 6, 10), ("indelLength", 10, 16)):
+        ed = res[key]
+        assert ed.sum() == total and np.trace(ed) == total
+        assert np.array_equal(np.diag(ed), np.bincount(np.argmax(Y[:, lo:hi], axis=1), minlength=hi - lo))
