@@ -26,7 +26,6 @@
 #include <string.h>
 
 #include <algorithm>
-#include <deque>
 #include <map>
 #include <new>
 #include <string>
@@ -82,7 +81,20 @@ struct cvb_candidates {
   uint64_t seed = 0;
   // the reference's `pileup` dict: positions >= `sweep` live in a window indexed by (position - sweep) -- reads arrive in
   // position order, so the open positions are a dense run -- positions created behind the sweep in a small ordered map
-  std::deque<Counts> win;
+  std::vector<Counts> ring;      // power-of-two capacity; slots outside [head, head + count) are all-zero
+  size_t head = 0, count = 0;    // the window covers positions [sweep, sweep + count)
+  inline Counts& slot(size_t i) { return ring[(head + i) & (ring.size() - 1)]; }
+  void reserve_window(size_t n) {  // make positions sweep .. sweep + n - 1 addressable
+    if (n > ring.size()) {
+      size_t cap = ring.empty() ? 1024 : ring.size();
+      while (cap < n) cap <<= 1;
+      std::vector<Counts> bigger(cap);
+      for (size_t i = 0; i < count; ++i) bigger[i] = slot(i);
+      ring.swap(bigger);
+      head = 0;
+    }
+    if (n > count) count = n;
+  }
   std::map<int64_t, Counts> late;
   std::string out_text;
   std::vector<int64_t> out_pos;
@@ -104,17 +116,21 @@ struct cvb_candidates {
   inline Counts& at(int64_t pos) {  // pileup.setdefault(pos, {...})
     if (pos < sweep) { Counts& c = late[pos]; c.touched = 1; return c; }
     const size_t i = (size_t)(pos - sweep);
-    if (i >= win.size()) win.resize(i + 1);
-    win[i].touched = 1;
-    return win[i];
+    if (i >= count) reserve_window(i + 1);
+    Counts& c = slot(i);
+    c.touched = 1;
+    return c;
   }
   // `while sweep < POS` (:178-213): positions in [sweep, POS) are final.  A position BEHIND the sweep can still be created
   // later (an insertion / deletion is booked at refPos-1, which may lie left of the read's own start); the reference never
   // revisits it in this loop -- it stays in the dict until the end-of-input pass, and so it does here (`late`).
   void sweep_before(int64_t pos0) {
-    while (sweep < pos0 && !win.empty()) {
-      if (win.front().touched) finish_position(sweep, win.front());
-      win.pop_front();
+    while (sweep < pos0 && count > 0) {
+      Counts& c = slot(0);
+      if (c.touched) finish_position(sweep, c);
+      c = Counts();
+      head = (head + 1) & (ring.size() - 1);
+      --count;
       ++sweep;
     }
     if (pos0 > sweep) sweep = pos0;
@@ -122,13 +138,16 @@ struct cvb_candidates {
   void finish_all() {  // :215-243: the remaining positions in ascending order
     for (auto& kv : late) finish_position(kv.first, kv.second);
     late.clear();
-    for (size_t i = 0; i < win.size(); ++i)
-      if (win[i].touched) finish_position(sweep + (int64_t)i, win[i]);
-    win.clear();
+    for (size_t i = 0; i < count; ++i) {
+      Counts& c = slot(i);
+      if (c.touched) finish_position(sweep + (int64_t)i, c);
+      c = Counts();
+    }
+    count = 0;
   }
   int64_t open_positions() const {
     int64_t n = (int64_t)late.size();
-    for (const Counts& c : win) n += c.touched;
+    for (const Counts& c : ring) n += c.touched;
     return n;
   }
 };
@@ -218,11 +237,24 @@ void cvb_candidates::read_line(const char* p, const char* e) {
     if (op == 'S') {
       query_pos += adv;
     } else if (op == 'M' || op == '=' || op == 'X') {
-      for (int64_t i = 0; i < adv; ++i) {
-        const char b = (query_pos >= 0 && query_pos < seq_len) ? seq[query_pos] : 'N';
-        ++at(ref_pos).n[read_base_slot(b)];
-        ++ref_pos;
-        ++query_pos;
+      if (ref_pos >= sweep && adv > 0) {  // the whole run lies in the window: one bounds check for the run
+        const size_t i0 = (size_t)(ref_pos - sweep);
+        if (i0 + (size_t)adv > count) reserve_window(i0 + (size_t)adv);
+        for (int64_t i = 0; i < adv; ++i) {
+          const char b = (query_pos + i >= 0 && query_pos + i < seq_len) ? seq[query_pos + i] : 'N';
+          Counts& c = slot(i0 + (size_t)i);
+          c.touched = 1;
+          ++c.n[read_base_slot(b)];
+        }
+        ref_pos += adv;
+        query_pos += adv;
+      } else {
+        for (int64_t i = 0; i < adv; ++i) {
+          const char b = (query_pos >= 0 && query_pos < seq_len) ? seq[query_pos] : 'N';
+          ++at(ref_pos).n[read_base_slot(b)];
+          ++ref_pos;
+          ++query_pos;
+        }
       }
     } else if (op == 'I') {
       ++at(ref_pos - 1).n[kI];
