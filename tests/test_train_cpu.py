@@ -143,3 +143,50 @@ def test_evaluate_report(tmp_path, monkeypatch):
         ed = res[key]
         assert ed.sum() == total and np.trace(ed) == total
         assert np.array_equal(np.diag(ed), np.bincount(np.argmax(Y[:, lo:hi], axis=1), minlength=hi - lo))
+
+
+def test_train_without_validation_skips_the_final_partial_batch(tmp_path, monkeypatch):
+    """trainWithoutValidationNonstop.py:84-105: every batch trains, except that the batch returned together with the
+    end-of-data flag closes the epoch untrained (reference behaviour)"""
+    from clairvoyante_b200 import trainWithoutValidationNonstop as T
+    monkeypatch.setattr(param, "trainBatchSize", 100)
+    monkeypatch.setattr(param, "bloscBlockSize", 50)
+    monkeypatch.setattr(param, "maxEpoch", 3)
+    fn, _, _ = _dataset(tmp_path, 530)
+    m = _Stub()
+    args = types.SimpleNamespace(bin_fn=fn, tensor_fn=None, var_fn=None, bed_fn=None, chkpnt_fn=None, learning_rate=1e-3, lambd=1e-3,
+                                 ochk_prefix=str(tmp_path / "m"), olog_dir=None, v2=False, v3=True, slim=False)
+    T.TrainAll(args, m, U)
+    assert m.trained == [100, 100, 100, 100, 100] * 2 and m.validated == []
+    assert [s[-8:] for s in m.saved] == ["m-000001", "m-000002"]
+
+
+def test_cal_train_dev_diff_books_every_site_once(tmp_path, monkeypatch):
+    """calTrainDevDiff.py:44-76 with a model whose loss is the number of sites in the batch: the two sums cover the set
+    exactly once, split where the reference's pointer test splits them"""
+    from clairvoyante_b200 import calTrainDevDiff as C
+    monkeypatch.setattr(param, "predictBatchSize", 10)
+    monkeypatch.setattr(param, "bloscBlockSize", 50)
+    total = 503
+    fn, _, _ = _dataset(tmp_path, total)
+
+    class Counter(object):
+        def __init__(self):
+            self.restored, self.sizes = [], []
+        def restoreParameters(self, fn):
+            self.restored.append(os.path.basename(fn))
+        def getLossNoRT(self, X, Y):
+            self.sizes.append(len(X)); self.getLossLossRTVal = float(len(X))
+
+    import os
+    m = Counter()
+    args = types.SimpleNamespace(bin_fn=fn, tensor_fn=None, var_fn=None, bed_fn=None, chkpnt_fn=["ck-000001", "ck-000002"])
+    res = C.CalcAll(args, m, U)
+    assert m.restored == ["ck-000001", "ck-000002"] and len(res) == 2
+    trainingTotal = int(total * 0.9); validationStart = trainingTotal + 1
+    per_ckpt = m.sizes[:len(m.sizes) // 2]
+    assert sum(per_ckpt) == total and per_ckpt[:3] == [10, 10, 10]
+    name, tr, va = res[0]
+    assert abs(tr * trainingTotal + va * (total - validationStart) - total) < 1e-6
+    # batches are booked by the pointer after the NEXT fetch: the batch that ends exactly at validationStart counts as validation
+    assert abs(tr * trainingTotal - 450) < 1e-6 and abs(va * (total - validationStart) - 53) < 1e-6
