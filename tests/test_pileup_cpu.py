@@ -158,3 +158,23 @@ def test_command_line_on_sam_and_fasta(tmp_path):
     assert r.returncode == 0, r.stderr
     want = O.create_tensors(sam, ref, cands)
     assert r.stdout.split("\n")[:-1] == [O.tensor_line("ctg", c, ref, None, t) for c, t in want]
+
+
+def test_golden_alignment_fixture():
+    """tests/golden/alignments.npz (make_golden_alignments.py): both oracles and both native stages reproduce the committed
+    candidate rows and tensors"""
+    from clairvoyante_b200 import ExtractVariantCandidates as EVC
+    from oracle import candidates_oracle as OC
+    g = np.load(os.path.join(ROOT, "tests", "golden", "alignments.npz"))
+    sam, ref = str(g["sam"]), str(g["ref"])
+    rows = [str(r) for r in g["candidate_rows"]]
+    assert OC.make_candidates(sam, "ctg", ref, None) == rows
+    c = EVC.Candidates("ctg", ref)
+    c.feed(sam, final=True)
+    text, pos = c.take()
+    c.close()
+    assert text.decode().split("\n")[:-1] == rows and len(rows) > 20
+    want = O.create_tensors(sam, ref, pos.tolist())
+    centers, x, _ = run_native(sam, ref, pos)
+    assert np.array_equal(centers, g["centers"]) and np.array_equal(x, g["tensors"].astype(np.float32))
+    assert [w[0] for w in want] == g["centers"].tolist() and all(np.array_equal(w[1], x[i]) for i, w in enumerate(want))
