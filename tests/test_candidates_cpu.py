@@ -126,3 +126,33 @@ def test_pipeline_candidates_into_pileup_and_command_line(tmp_path):
     # the reference fetches [ctgStart+1-1e6, ctgEnd+1e6] -> here the whole contig from position 1
     want = O.make_candidates(sam, "ctg", ref, 1, ctgStart=301, ctgEnd=2000, bed=[(200, 1499)])
     assert r.stdout.split("\n")[:-1] == want
+
+
+def test_mutated_sam_rows_never_crash_and_still_agree():
+    """junk CIGAR ops, '*' CIGARs, SEQ shorter than the CIGAR claims, megabase deletions, truncated rows, N/H/P ops: both native
+    stages keep agreeing with their restatements (which define those cases: the regular expression skips junk, short SEQ
+    reads as N, short rows are dropped)"""
+    from oracle import createtensor_oracle as OT
+    rng = np.random.default_rng(123)
+    for it in range(40):
+        ref, sam, cands = synth_alignments(rng, ref_len=int(rng.integers(260, 1200)), n_reads=int(rng.integers(1, 60)), read_len=(5, 90))
+        out = []
+        for r in sam.split("\n"):
+            f, u = r.split("\t"), rng.random()
+            if len(f) >= 10:
+                if u < 0.10: f[5] = f[5] + "7Q3M9"
+                elif u < 0.15: f[5] = "*"
+                elif u < 0.20: f[9] = f[9][:max(1, len(f[9]) // 2)]
+                elif u < 0.25: f[5] = "1000000D5M"
+                elif u < 0.30: f = f[:int(rng.integers(1, 10))]
+                elif u < 0.33: f[5] = "5M2N5M3H2P4="
+            out.append("\t".join(f))
+        sam2 = "\n".join(out)
+        want = OT.create_tensors(sam2, ref, cands)
+        p = CT.Pileup(ref, cands)
+        p.feed(sam2, final=True)
+        cc, x = p.take()
+        p.close()
+        assert [int(v) for v in cc] == [w[0] for w in want] and all(np.array_equal(x[i], w[1]) for i, w in enumerate(want)), it
+        rows, _, _ = run_native(sam2, "ctg", ref, None, minCoverage=0)
+        assert rows == O.make_candidates(sam2, "ctg", ref, None, minCoverage=0), it
