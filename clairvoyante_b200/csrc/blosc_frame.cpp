@@ -1,4 +1,4 @@
-// blosc_frame.cpp -- decoder for Blosc-1 frames holding LZ4 / LZ4HC blocks (host code).
+// blosc_frame.cpp -- decoder and encoder for Blosc-1 frames holding LZ4 / LZ4HC blocks (host code).
 //
 // The reference stores its training set as python-blosc frames, `blosc.pack_array(array, cname='lz4hc')`
 // (clairvoyante/utils_v2.py:174-176,182-184) and reads them back with `blosc.unpack_array` (:198,202).
@@ -148,5 +148,125 @@ extern "C" int cvb_blosc_decompress(const void* frame, int64_t n, void* dst, int
     }
     if (shuffled) unshuffle(tmp.data(), out + b * blocksize, bsize, typesize);
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Encoder: what `blosc.pack_array(a, cname='lz4hc')` (utils_v2.py:174-176) hands to the .bin, so that a training set
+// prepared here can be read by the reference's `blosc.unpack_array`.  Any valid LZ4 block stream decodes with LZ4 / LZ4HC
+// decoders alike (HC only searches harder); this one is the plain greedy scheme: hash of 4 bytes -> last position, extend,
+// the last 5 bytes are literals and no match starts within the last 12 bytes of a stream (format end conditions).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+inline void wr32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+
+// returns the encoded size, or -1 when it would not fit in cap
+int64_t lz4_block_encode(const uint8_t* s, int64_t n, uint8_t* d, int64_t cap) {
+  uint8_t* op = d;
+  uint8_t* const oend = d + cap;
+  auto emit = [&](const uint8_t* lit, int64_t nlit, int64_t mlen, int64_t off) -> bool {
+    const int64_t need = 1 + nlit / 255 + 1 + nlit + (mlen ? 2 + (mlen - 4) / 255 + 1 : 0);
+    if (need > oend - op) return false;
+    const int64_t tl = nlit < 15 ? nlit : 15, tm = mlen ? (mlen - 4 < 15 ? mlen - 4 : 15) : 0;
+    *op++ = (uint8_t)((tl << 4) | tm);
+    if (nlit >= 15) {
+      int64_t r = nlit - 15;
+      while (r >= 255) { *op++ = 255; r -= 255; }
+      *op++ = (uint8_t)r;
+    }
+    memcpy(op, lit, (size_t)nlit);
+    op += nlit;
+    if (mlen) {
+      *op++ = (uint8_t)off;
+      *op++ = (uint8_t)(off >> 8);
+      if (mlen - 4 >= 15) {
+        int64_t r = mlen - 4 - 15;
+        while (r >= 255) { *op++ = 255; r -= 255; }
+        *op++ = (uint8_t)r;
+      }
+    }
+    return true;
+  };
+  constexpr int HB = 14;
+  std::vector<int32_t> table((size_t)1 << HB, -1);
+  int64_t i = 0, anchor = 0;
+  while (i + 12 < n) {
+    const uint32_t key = rd32(s + i);
+    const uint32_t h = (key * 2654435761u) >> (32 - HB);
+    const int64_t cand = table[h];
+    table[h] = (int32_t)i;
+    if (cand >= 0 && i - cand <= 65535 && rd32(s + cand) == key) {
+      int64_t m = 4;
+      while (i + m < n - 5 && s[cand + m] == s[i + m]) ++m;
+      if (!emit(s + anchor, i - anchor, m, i - cand)) return -1;
+      i += m;
+      anchor = i;
+    } else {
+      ++i;
+    }
+  }
+  if (!emit(s + anchor, n - anchor, 0, 0)) return -1;
+  return (int64_t)(op - d);
+}
+
+void shuffle_bytes(const uint8_t* src, uint8_t* dst, int64_t n, int typesize) {
+  const int64_t ne = n / typesize;
+  for (int b = 0; b < typesize; ++b) {
+    const uint8_t* s = src + b;
+    uint8_t* o = dst + (int64_t)b * ne;
+    for (int64_t i = 0; i < ne; ++i, s += typesize) o[i] = *s;
+  }
+  const int64_t done = ne * typesize;
+  memcpy(dst + done, src + done, (size_t)(n - done));
+}
+
+}  // namespace
+
+extern "C" int64_t cvb_blosc_compress_bound(int64_t nbytes) { return nbytes + nbytes / 255 + 16 + 4 * (nbytes / 4096 + 2) + 16 * 64 + 64; }
+
+extern "C" int cvb_blosc_compress(const void* src, int64_t nbytes, int typesize, int do_shuffle, void* dst, int64_t cap,
+                                  int64_t* out_n) {
+  const uint8_t* in = static_cast<const uint8_t*>(src);
+  uint8_t* out = static_cast<uint8_t*>(dst);
+  if (!out || !out_n || (!in && nbytes > 0) || nbytes < 0 || nbytes > 0x7fffffff - 16) return fail("cvb_blosc_compress: bad argument");
+  if (typesize < 1 || typesize > 255) typesize = 1;  // (Blosc treats over-long items as bytes)
+  if (cap < 16 + nbytes) return fail("cvb_blosc_compress: destination too small (see cvb_blosc_compress_bound)");
+  const bool shuf = do_shuffle && typesize > 1;
+  int64_t blocksize = 256 * 1024;
+  if (blocksize > nbytes) blocksize = nbytes > 0 ? nbytes : 1;
+  if (blocksize > typesize) blocksize -= blocksize % typesize;  // whole items per block (c-blosc's rule): the split streams divide
+                                                                // evenly, the odd bytes form a trailing partial block
+  const int64_t nblocks = nbytes > 0 ? (nbytes + blocksize - 1) / blocksize : 0;
+  const uint8_t flags = (uint8_t)((1 << 5) | (shuf ? 0x01 : 0));
+  out[0] = 2; out[1] = 1; out[2] = flags; out[3] = (uint8_t)typesize;
+  wr32(out + 4, (uint32_t)nbytes);
+  wr32(out + 8, (uint32_t)blocksize);
+  int64_t off = 16 + 4 * nblocks;
+  bool fits = off <= cap;
+  std::vector<uint8_t> tmp((size_t)(shuf ? blocksize : 0));
+  for (int64_t b = 0; b < nblocks && fits; ++b) {
+    const int64_t bsize = (b == nblocks - 1 && nbytes % blocksize) ? nbytes % blocksize : blocksize;
+    const bool leftover = bsize != blocksize;
+    const uint8_t* blk = in + b * blocksize;
+    if (shuf) { shuffle_bytes(blk, tmp.data(), bsize, typesize); blk = tmp.data(); }
+    const int nsplits = (typesize <= 16 && blocksize / typesize >= 128 && !leftover) ? typesize : 1;
+    const int64_t ne = bsize / nsplits;
+    wr32(out + 16 + 4 * b, (uint32_t)off);
+    for (int s2 = 0; s2 < nsplits && fits; ++s2) {
+      if (off + 4 + ne > cap) { fits = false; break; }
+      int64_t c = lz4_block_encode(blk + s2 * ne, ne, out + off + 4, ne - 1);  // must be strictly smaller than raw
+      if (c < 0) { memcpy(out + off + 4, blk + s2 * ne, (size_t)ne); c = ne; }   // cbytes == size marks a raw stream
+      wr32(out + off, (uint32_t)c);
+      off += 4 + c;
+    }
+  }
+  if (!fits || off >= 16 + nbytes) {  // did not shrink: store ("memcpyed", flag 0x02)
+    out[2] = (uint8_t)(flags | 0x02);
+    if (nbytes) memcpy(out + 16, in, (size_t)nbytes);
+    off = 16 + nbytes;
+  }
+  wr32(out + 12, (uint32_t)off);
+  *out_n = off;
   return 0;
 }

@@ -1,6 +1,7 @@
 """tensor2Bin -- text tensors (+ truth, BED) -> binary training file; counterpart of reference
 clairvoyante/tensor2Bin.py:18-28: four consecutive pickles (total, X blocks, Y blocks, pos blocks).  Blocks use this
-repo's container (utils_v2.pack_array), not blosc frames."""
+repo's container (utils_v2.pack_array) by default; `--blosc` writes what the reference writes -- python-blosc frames around
+Python-2 pickles, protocol-2 outer pickles -- so that the file also loads in the reference's train.py (:40-44)."""
 import argparse
 import logging
 import pickle
@@ -15,11 +16,15 @@ def Run(args):
     from . import utils_v2 as utils
     utils.SetupEnv()
     logging.info("Loading the dataset ...")
-    parts = utils.GetTrainingArray(args.tensor_fn, args.var_fn, args.bed_fn)
+    blosc = bool(getattr(args, "blosc", False))
+    parts = utils.GetTrainingArray(args.tensor_fn, args.var_fn, args.bed_fn, container="blosc" if blosc else "cvbz")
     logging.info("Writing to binary ...")
     with open(args.bin_fn, "wb") as fh:
         for p in parts:
-            pickle.dump(p, fh)
+            if blosc:
+                pickle.dump(p, fh, protocol=2)       # loadable by Python 2 (bytes travel as latin-1 text through _codecs.encode)
+            else:
+                pickle.dump(p, fh)
 
 
 def main():
@@ -28,6 +33,8 @@ def main():
     parser.add_argument('--var_fn', type=str, default="truthvars", help="Truth variants list input")
     parser.add_argument('--bed_fn', type=str, default=None, help="High confident genome regions input in the BED format")
     parser.add_argument('--bin_fn', type=str, default=None, help="Output a binary tensor file")
+    parser.add_argument('--blosc', type=param.str2bool, nargs='?', const=True, default=False,
+                        help="Write the blocks as python-blosc frames like the reference (default: this repo's container)")
     parser.add_argument('--v3', type=param.str2bool, nargs='?', const=True, default=True, help="Use Clairvoyante version 3")
     parser.add_argument('--v2', type=param.str2bool, nargs='?', const=True, default=False, help="Use Clairvoyante version 2")
     args = parser.parse_args()

@@ -167,6 +167,55 @@ def pack_array(a):
     return _MAGIC + zlib.compress(buf.getvalue(), 1)
 
 
+def _py2_pickle_ndarray(a):
+    """protocol-2 pickle of an ndarray exactly as Python 2 + NumPy 1.x wrote it (the raw buffer is a `str`, the globals
+    live in numpy.core.multiarray): what `blosc.pack_array` compresses (utils_v2.py:174-176), so that frames written
+    here load in the reference's interpreter.  A Python-3 / NumPy-2 pickle would not (numpy._core, _codecs.encode)."""
+    import struct
+    a = np.ascontiguousarray(a)
+
+    def sstr(t):
+        t = t.encode("latin1") if isinstance(t, str) else t
+        return (b"U" + bytes([len(t)]) + t) if len(t) < 256 else (b"T" + struct.pack("<i", len(t)) + t)
+
+    def pint(v):
+        if 0 <= v < 256:
+            return b"K" + bytes([v])
+        if 0 <= v < 65536:
+            return b"M" + struct.pack("<H", v)
+        return b"J" + struct.pack("<i", v)
+    dt = a.dtype
+    if dt.kind not in "fiuSb" or dt.byteorder == ">":
+        raise ValueError("only little-endian numeric and fixed-width byte-string arrays are stored in a tensor file")
+    code = dt.str[1:] if dt.kind != "S" else "S%d" % dt.itemsize
+    order = "|" if dt.kind == "S" or dt.itemsize == 1 else "<"
+    p = b"\x80\x02cnumpy.core.multiarray\n_reconstruct\ncnumpy\nndarray\nK\x00\x85" + sstr("b") + b"\x87R"
+    p += b"(K\x01"                                                  # state tuple: version
+    p += b"(" + b"".join(pint(d) for d in a.shape) + b"t"            # shape
+    p += b"cnumpy\ndtype\n" + sstr(code) + b"K\x00K\x01\x87R"       # dtype(code, 0, 1)
+    size_align = (pint(dt.itemsize) + pint(1)) if dt.kind == "S" else b"J\xff\xff\xff\xffJ\xff\xff\xff\xff"
+    p += b"(K\x03" + sstr(order) + b"NNN" + size_align + b"K\x00tb"
+    p += b"\x89"                                                    # is_fortran = False
+    raw = a.tobytes()
+    p += b"T" + struct.pack("<i", len(raw)) + raw                    # BINSTRING
+    p += b"tb."
+    return p
+
+
+def pack_array_blosc(a):
+    """`blosc.pack_array(a, cname='lz4hc')` (utils_v2.py:174-176): Blosc-1 frame (typesize = itemsize, byte shuffle, LZ4
+    streams -- csrc/blosc_frame.cpp) around the Python-2 pickle of the array.  Readable by the reference and by
+    unpack_array here."""
+    lib = _lib.load()
+    a = np.asarray(a)
+    payload = _py2_pickle_ndarray(a)
+    cap = int(lib.cvb_blosc_compress_bound(len(payload)))
+    out = ctypes.create_string_buffer(cap)
+    got = ctypes.c_int64()
+    _lib.check(lib.cvb_blosc_compress(payload, len(payload), min(int(a.dtype.itemsize), 255), 1, out, cap, ctypes.byref(got)))
+    return out.raw[:got.value]
+
+
 class _RestrictedUnpickler(pickle.Unpickler):
     """The reference unpickles its .bin blindly (train.py:41-44, blosc.unpack_array); only the globals a pickled
     ndarray / list / int needs are resolved here."""
@@ -277,7 +326,10 @@ def _truth_label(ref, alt, gt1, gt2):
     return v
 
 
-def GetTrainingArray(tensor_fn, var_fn, bed_fn, shuffle=True):
+def GetTrainingArray(tensor_fn, var_fn, bed_fn, shuffle=True, container="cvbz"):
+    """utils_v2.py:62-186.  container: "cvbz" = this repo's block container (pack_array), "blosc" = python-blosc frames
+    around Python-2 pickles like the reference writes (pack_array_blosc) -- unpack_array / DecompressArray read both."""
+    pack = pack_array_blosc if container == "blosc" else pack_array
     regions = None
     if bed_fn is not None:
         regions = _Regions()
@@ -325,13 +377,13 @@ def GetTrainingArray(tensor_fn, var_fn, bed_fn, shuffle=True):
     step = param.bloscBlockSize
     for i in range(0, len(keys), step):
         chunk = keys[i:i + step]
-        xb.append(pack_array(np.array([X[k] for k in chunk], dtype=np.float32)))
-        yb.append(pack_array(np.array([Y[k] for k in chunk], dtype=np.float64)))   # labels are float64 upstream (:175)
-        pb.append(pack_array(np.array(chunk, dtype="S")))
+        xb.append(pack(np.array([X[k] for k in chunk], dtype=np.float32)))
+        yb.append(pack(np.array([Y[k] for k in chunk], dtype=np.float64)))   # labels are float64 upstream (:175)
+        pb.append(pack(np.array(chunk, dtype="S")))
     if len(keys) % step == 0:                 # the reference always appends a (possibly empty) trailing block (:181-184)
-        xb.append(pack_array(np.zeros((0, h, 4, param.matrixNum), np.float32)))
-        yb.append(pack_array(np.zeros((0, 16), np.float64)))
-        pb.append(pack_array(np.array([], dtype="S1")))
+        xb.append(pack(np.zeros((0, h, 4, param.matrixNum), np.float32)))
+        yb.append(pack(np.zeros((0, 16), np.float64)))
+        pb.append(pack(np.array([], dtype="S1")))
     return len(keys), xb, yb, pb
 
 

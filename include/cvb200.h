@@ -141,6 +141,10 @@ uint32_t cvb_crc32c(uint32_t crc, const void* data, int64_t n);
  * cvb_blosc_decompress: frame -> dst[0, *out_n) (the pickled ndarray); byte-shuffle undone; other codecs are refused. */
 int cvb_blosc_info(const void* frame, int64_t n, int64_t* nbytes, int64_t* cbytes, int* typesize, int* flags);
 int cvb_blosc_decompress(const void* frame, int64_t n, void* dst, int64_t cap, int64_t* out_n);
+/* the inverse, for `blosc.pack_array` (utils_v2.py:174-176,182-184): src[0, nbytes) -> one Blosc-1 frame with LZ4 streams
+ * (byte-shuffled by typesize when do_shuffle != 0; stored uncompressed when that is not smaller).  cap >= cvb_blosc_compress_bound. */
+int64_t cvb_blosc_compress_bound(int64_t nbytes);
+int cvb_blosc_compress(const void* src, int64_t nbytes, int typesize, int do_shuffle, void* dst, int64_t cap, int64_t* out_n);
 
 /* ---- alignment pile-up: SAM records -> candidate tensors ---------------------------------------------------------------
  * Replaces dataPrepScripts/CreateTensor.py (GenerateTensor :23-59, OutputAlnTensor :96-258), the producer of the tensor

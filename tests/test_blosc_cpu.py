@@ -135,3 +135,71 @@ def test_bin_loader_refuses_arbitrary_globals(tmp_path):
         fh.write(b"\x80\x02cos\nsystem\nU\x04trueq\x00\x85R.")
     with pytest.raises(pickle.UnpicklingError):
         U.load_bin(fn)
+
+
+# ---- the encoder (csrc/blosc_frame.cpp cvb_blosc_compress, utils_v2.pack_array_blosc) ---------------------------------
+def _native_compress(data, typesize, shuffle=1):
+    import ctypes
+    from clairvoyante_b200 import _lib
+    lib = _lib.load()
+    cap = int(lib.cvb_blosc_compress_bound(len(data)))
+    out = ctypes.create_string_buffer(cap)
+    got = ctypes.c_int64()
+    _lib.check(lib.cvb_blosc_compress(data, len(data), typesize, shuffle, out, cap, ctypes.byref(got)))
+    return out.raw[:got.value]
+
+
+def _native_decompress(frame):
+    import ctypes
+    from clairvoyante_b200 import _lib
+    lib = _lib.load()
+    n = ctypes.c_int64()
+    _lib.check(lib.cvb_blosc_info(frame, len(frame), ctypes.byref(n), None, None, None))
+    out = ctypes.create_string_buffer(max(1, n.value))
+    got = ctypes.c_int64()
+    _lib.check(lib.cvb_blosc_decompress(frame, len(frame), out, n.value, ctypes.byref(got)))
+    return out.raw[:got.value]
+
+
+def test_native_encoder_round_trips_and_matches_the_frame_rules():
+    rng = np.random.default_rng(0)
+    cases = [b"", b"a", b"abcd" * 3, bytes(1000), rng.integers(0, 4, 5000, dtype=np.uint8).tobytes(),
+             rng.integers(0, 256, 70000, dtype=np.uint8).tobytes(),                          # incompressible -> stored
+             np.arange(200000, dtype=np.float32).tobytes(), (b"ACGT" * 100000) + b"xyz",   # > 1 block, leftover tail
+             np.repeat(rng.standard_normal(3000), 40).astype(np.float64).tobytes(),
+             bytes(range(256)) * 250 + b"tail!", np.eye(16)[np.arange(500) % 16].tobytes() + b"tb."]   # sizes that are not whole items
+    for data in cases:
+        for typesize in (1, 4, 8):
+            for shuffle in (0, 1):
+                frame = _native_compress(data, typesize, shuffle)
+                assert int.from_bytes(frame[12:16], "little") == len(frame) and frame[0] == 2 and frame[3] == typesize
+                assert int.from_bytes(frame[4:8], "little") == len(data)
+                assert len(frame) <= len(data) + 16                                        # never worse than stored
+                assert _native_decompress(frame) == data
+    big = np.zeros((500, 33, 4, 4), np.float32).tobytes()
+    assert len(_native_compress(big, 4)) < len(big) // 50
+
+
+def test_pack_array_blosc_is_what_the_reference_writes(tmp_path):
+    """blocks written with pack_array_blosc are Blosc-1 frames around Python-2 pickles: they read back here, their payload
+    is byte-identical to the test-side Python-2 pickle writer, and a .bin written with --blosc loads through load_bin"""
+    import pickle
+    from clairvoyante_b200 import utils_v2 as U
+    import blosc_writer as BW
+    x = (np.arange(500 * 528) % 37).astype(np.float32).reshape(500, 33, 4, 4)
+    y = np.eye(16, dtype=np.float64)[np.arange(500) % 16]
+    pos = np.array([b"chr1:%d" % i for i in range(500)], dtype="S")
+    for a in (x, y, pos, x[:0], pos[:0]):
+        frame = U.pack_array_blosc(a)
+        assert frame[:5] != b"CVBZ1" and frame[0] == 2
+        assert _native_decompress(frame) == BW.py2_pickle_ndarray(a)
+        b = U.unpack_array(frame)
+        assert b.dtype == a.dtype and b.shape == a.shape and np.array_equal(b, a)
+    fn = str(tmp_path / "d.bin")
+    with open(fn, "wb") as fh:
+        for p in (500, [U.pack_array_blosc(x)], [U.pack_array_blosc(y)], [U.pack_array_blosc(pos)]):
+            pickle.dump(p, fh, protocol=2)
+    total, xb, yb, pb = U.load_bin(fn)
+    assert total == 500 and np.array_equal(U.unpack_array(xb[0]), x) and np.array_equal(U.unpack_array(pb[0]), pos)
+    X, n, end = U.DecompressArray(xb, 0, 500, 500)
+    assert n == 500 and end == 1 and np.array_equal(X, x)

@@ -169,3 +169,26 @@ def test_get_training_array_labels(tmp_path):
     Y2, _, _ = U.DecompressArray(yb2, 0, total2, total2)
     assert total2 == 6 and (Y2[:, 5] == 1).all() and (Y2[:, 6] == 1).all() and (Y2[:, 10] == 1).all()
     assert [int(np.argmax(r[:4])) for r in Y2] == [0, 1, 2, 3, 0, 1]
+
+
+def test_tensor2bin_blosc_container_equals_default(tmp_path):
+    """tensor2Bin --blosc (reference-format frames + protocol-2 pickles) holds exactly what the default container holds"""
+    import types
+    from clairvoyante_b200 import tensor2Bin
+    x = synth.make_sites(7, 5)
+    seqs = ["ACGTACGTACGTACGT" + c + "CGTACGTACGTACGTA" for c in "ACGTACG"]
+    tfn, vfn = str(tmp_path / "t.txt"), str(tmp_path / "v.txt")
+    open(tfn, "w").write("\n".join(_rows(x, seqs)) + "\n")
+    open(vfn, "w").write("chr1 1000 A G 0 1\nchr1 1003 TACGTAC T 1 1\n")
+    got = {}
+    for blosc in (False, True):
+        fn = str(tmp_path / ("d%d.bin" % blosc))
+        tensor2Bin.Run(types.SimpleNamespace(tensor_fn=tfn, var_fn=vfn, bed_fn=None, bin_fn=fn, blosc=blosc))
+        total, xb, yb, pb = U.load_bin(fn)
+        blocks = [U.unpack_array(b) for b in pb]
+        order = np.argsort(np.concatenate(blocks))                       # GetTrainingArray shuffles
+        got[blosc] = (total, U.DecompressArray(xb, 0, total, total)[0][order], U.DecompressArray(yb, 0, total, total)[0][order],
+                      bytes(xb[0][:5]))
+    assert got[False][0] == got[True][0] == 7
+    assert np.array_equal(got[False][1], got[True][1]) and np.array_equal(got[False][2], got[True][2])
+    assert got[False][3] == b"CVBZ1" and got[True][3][0] == 2             # own container vs Blosc-1 frame
