@@ -129,7 +129,7 @@ def test_pipeline_candidates_into_pileup_and_command_line(tmp_path):
 
 
 def test_mutated_sam_rows_never_crash_and_still_agree():
-    """junk CIGAR ops, '*' CIGARs, SEQ shorter than the CIGAR claims, megabase deletions, truncated rows, N/H/P ops: both native
+    """junk CIGAR ops, '*' CIGARs, SEQ shorter than the CIGAR claims, very long deletions, truncated rows, N/H/P ops: both native
     stages keep agreeing with their restatements (which define those cases: the regular expression skips junk, short SEQ
     reads as N, short rows are dropped)"""
     from oracle import createtensor_oracle as OT
@@ -143,7 +143,7 @@ def test_mutated_sam_rows_never_crash_and_still_agree():
                 if u < 0.10: f[5] = f[5] + "7Q3M9"
                 elif u < 0.15: f[5] = "*"
                 elif u < 0.20: f[9] = f[9][:max(1, len(f[9]) // 2)]
-                elif u < 0.25: f[5] = "1000000D5M"
+                elif u < 0.25: f[5] = "30000D5M"
                 elif u < 0.30: f = f[:int(rng.integers(1, 10))]
                 elif u < 0.33: f[5] = "5M2N5M3H2P4="
             out.append("\t".join(f))
