@@ -48,7 +48,8 @@ bool lz4_block_decode(const uint8_t* s, int64_t slen, uint8_t* d, int64_t dlen) 
       } while (b == 255);
     }
     if (lit > iend - ip || lit > oend - op) return false;
-    memcpy(op, ip, (size_t)lit);
+    if (lit <= 16 && iend - ip >= 16 && oend - op >= 16) memcpy(op, ip, 16);  // short literal runs: one fixed-size copy
+    else memcpy(op, ip, (size_t)lit);
     ip += lit;
     op += lit;
     if (ip >= iend) break;
@@ -68,11 +69,25 @@ bool lz4_block_decode(const uint8_t* s, int64_t slen, uint8_t* d, int64_t dlen) 
     ml += 4;
     if (ml > oend - op) return false;
     const uint8_t* m = op - offset;
-    if (offset >= ml) {
+    if (offset >= 16 && oend - op >= ml + 16) {  // the common case: 16-byte strides never read what they have not written yet
+      for (int64_t k = 0; k < ml; k += 16) memcpy(op + k, m + k, 16);
+      op += ml;
+    } else if (offset >= ml) {
       memcpy(op, m, (size_t)ml);
       op += ml;
-    } else {
-      for (int64_t i = 0; i < ml; ++i) *op++ = *m++;  // overlapping match = run
+    } else if (offset == 1) {  // run of one byte (what long stretches of zeros in a shuffled tensor block become)
+      memset(op, *m, (size_t)ml);
+      op += ml;
+    } else {  // overlapping match = periodic run: copy the period, then keep doubling the copied span
+      uint8_t* const start = op;
+      memcpy(op, m, (size_t)offset);
+      int64_t done = offset;
+      while (done < ml) {
+        const int64_t c = done < ml - done ? done : ml - done;
+        memcpy(start + done, start, (size_t)c);
+        done += c;
+      }
+      op += ml;
     }
   }
   return op == oend;
@@ -80,10 +95,28 @@ bool lz4_block_decode(const uint8_t* s, int64_t slen, uint8_t* d, int64_t dlen) 
 
 void unshuffle(const uint8_t* src, uint8_t* dst, int64_t n, int typesize) {
   const int64_t ne = n / typesize;
-  for (int b = 0; b < typesize; ++b) {
-    const uint8_t* s = src + (int64_t)b * ne;
-    uint8_t* o = dst + b;
-    for (int64_t i = 0; i < ne; ++i, o += typesize) *o = s[i];
+  if (typesize == 4) {  // float32 tensors: gather the four byte planes element by element (sequential writes)
+    const uint8_t *s0 = src, *s1 = src + ne, *s2 = src + 2 * ne, *s3 = src + 3 * ne;
+    uint32_t* o = reinterpret_cast<uint32_t*>(dst);
+    if ((reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+      for (int64_t i = 0; i < ne; ++i) o[i] = (uint32_t)s0[i] | ((uint32_t)s1[i] << 8) | ((uint32_t)s2[i] << 16) | ((uint32_t)s3[i] << 24);
+    } else {
+      for (int64_t i = 0; i < ne; ++i) { dst[4 * i] = s0[i]; dst[4 * i + 1] = s1[i]; dst[4 * i + 2] = s2[i]; dst[4 * i + 3] = s3[i]; }
+    }
+  } else if (typesize == 8) {
+    const uint8_t* sp[8];
+    for (int b = 0; b < 8; ++b) sp[b] = src + (int64_t)b * ne;
+    for (int64_t i = 0; i < ne; ++i) {
+      uint64_t v = 0;
+      for (int b = 0; b < 8; ++b) v |= (uint64_t)sp[b][i] << (8 * b);
+      memcpy(dst + 8 * i, &v, 8);
+    }
+  } else {
+    for (int b = 0; b < typesize; ++b) {
+      const uint8_t* s = src + (int64_t)b * ne;
+      uint8_t* o = dst + b;
+      for (int64_t i = 0; i < ne; ++i, o += typesize) *o = s[i];
+    }
   }
   const int64_t done = ne * typesize;
   memcpy(dst + done, src + done, (size_t)(n - done));

@@ -1,7 +1,7 @@
 """tensor2Bin -- text tensors (+ truth, BED) -> binary training file; counterpart of reference
-clairvoyante/tensor2Bin.py:18-28: four consecutive pickles (total, X blocks, Y blocks, pos blocks).  Blocks use this
-repo's container (utils_v2.pack_array) by default; `--blosc` writes what the reference writes -- python-blosc frames around
-Python-2 pickles, protocol-2 outer pickles -- so that the file also loads in the reference's train.py (:40-44)."""
+clairvoyante/tensor2Bin.py:18-28: four consecutive pickles (total, X blocks, Y blocks, pos blocks).  Blocks are Blosc-1 / LZ4 frames around Python-2-style pickles (utils_v2.pack_array; unshuffled: smaller and faster to decode
+for count tensors); `--blosc` additionally applies python-blosc's default byte shuffle and writes protocol-2 outer pickles,
+i.e. what the reference itself writes, so that the file also loads in the reference's train.py (:40-44)."""
 import argparse
 import logging
 import pickle
@@ -34,7 +34,7 @@ def main():
     parser.add_argument('--bed_fn', type=str, default=None, help="High confident genome regions input in the BED format")
     parser.add_argument('--bin_fn', type=str, default=None, help="Output a binary tensor file")
     parser.add_argument('--blosc', type=param.str2bool, nargs='?', const=True, default=False,
-                        help="Write the blocks as python-blosc frames like the reference (default: this repo's container)")
+                        help="Shuffled frames + protocol-2 outer pickles, exactly like the reference (default: unshuffled frames)")
     parser.add_argument('--v3', type=param.str2bool, nargs='?', const=True, default=True, help="Use Clairvoyante version 3")
     parser.add_argument('--v2', type=param.str2bool, nargs='?', const=True, default=False, help="Use Clairvoyante version 2")
     args = parser.parse_args()

@@ -171,6 +171,12 @@ def test_get_training_array_labels(tmp_path):
     assert [int(np.argmax(r[:4])) for r in Y2] == [0, 1, 2, 3, 0, 1]
 
 
+def test_old_zlib_container_still_reads():
+    x = synth.make_sites(9, 2)
+    b = U.pack_array_zlib(x)
+    assert b[:5] == b"CVBZ1" and np.array_equal(U.unpack_array(b), x)
+
+
 def test_tensor2bin_blosc_container_equals_default(tmp_path):
     """tensor2Bin --blosc (reference-format frames + protocol-2 pickles) holds exactly what the default container holds"""
     import types
@@ -191,4 +197,5 @@ def test_tensor2bin_blosc_container_equals_default(tmp_path):
                       bytes(xb[0][:5]))
     assert got[False][0] == got[True][0] == 7
     assert np.array_equal(got[False][1], got[True][1]) and np.array_equal(got[False][2], got[True][2])
-    assert got[False][3] == b"CVBZ1" and got[True][3][0] == 2             # own container vs Blosc-1 frame
+    # both are Blosc-1 frames around Python-2 pickles; only --blosc applies python-blosc's default byte shuffle
+    assert got[False][3][0] == 2 and got[True][3][0] == 2 and (got[False][3][2] & 1) == 0 and (got[True][3][2] & 1) == 1
