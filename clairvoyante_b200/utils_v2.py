@@ -8,11 +8,11 @@ yield / return contracts:
   DecompressArray(blocks, start, num, maximum)    utils_v2.py:189-207 -> (array, num, endFlag)
 
 Differences that are deliberate and documented:
-  * python-blosc and intervaltree (requirements.txt:3-4) are not available; blocks are WRITTEN with
-    zlib + np.save (`pack_array`) and BED membership uses sorted arrays + bisect with the same half-open
-    [begin, end-1) semantics the reference builds (utils_v2.py:71-74).  Blocks are READ from either container:
-    `unpack_array` also decodes the python-blosc LZ4HC frames of a .bin written by the reference
-    (csrc/blosc_frame.cpp).
+  * python-blosc and intervaltree (requirements.txt:3-4) are not available; blocks are Blosc-1 / LZ4 frames
+    written and read by this library's own codec (csrc/blosc_frame.cpp): `pack_array` (unshuffled),
+    `pack_array_blosc` (byte-shuffled, the reference's layout); `unpack_array` also decodes the python-blosc
+    LZ4HC frames of a .bin written by the reference and this repo's first zlib container.  BED membership uses
+    sorted arrays + bisect with the same half-open [begin, end-1) semantics the reference builds (utils_v2.py:71-74).
   * a malformed row is reported and SKIPPED; the reference prints the failure and then re-uses the previous
     row's fields (utils_v2.py:34-41), silently duplicating a record.
 """
