@@ -162,7 +162,7 @@ extern "C" int cvb_blosc_decompress(const void* frame, int64_t n, void* dst, int
   if (16 + 4 * nblocks > cbytes) return fail("cvb_blosc_decompress: block table truncated");
   const bool shuffled = (flags & 0x01) && typesize > 1;
   const bool dont_split = (flags & 0x10) != 0;
-  std::vector<uint8_t> tmp(shuffled ? (size_t)blocksize : 0);
+  std::vector<uint8_t> tmp(shuffled ? (size_t)(blocksize < nbytes ? blocksize : nbytes) : 0);  // (a block never exceeds the payload)
   for (int64_t b = 0; b < nblocks; ++b) {
     const int64_t bsize = (b == nblocks - 1 && nbytes % blocksize) ? nbytes % blocksize : blocksize;
     const bool leftover = bsize != blocksize;

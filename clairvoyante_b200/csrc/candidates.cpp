@@ -306,7 +306,7 @@ extern "C" int cvb_candidates_feed(cvb_candidates* s, const char* sam, int64_t l
   const char* p = sam;
   const char* e = sam + len;
   if (!s->carry.empty()) {
-    const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+    const char* nl = p < e ? (const char*)memchr(p, '\n', (size_t)(e - p)) : nullptr;
     if (!nl && !final_chunk) { s->carry.append(p, (size_t)(e - p)); return 0; }
     const char* stop = nl ? nl : e;
     s->carry.append(p, (size_t)(stop - p));

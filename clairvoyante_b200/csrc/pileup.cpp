@@ -308,7 +308,7 @@ extern "C" int cvb_pileup_feed(cvb_pileup* s, const char* sam, int64_t len, int 
   const char* p = sam;
   const char* e = sam + len;
   if (!s->carry.empty()) {  // finish the line started in the previous chunk
-    const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+    const char* nl = p < e ? (const char*)memchr(p, '\n', (size_t)(e - p)) : nullptr;
     if (!nl && !final_chunk) { s->carry.append(p, (size_t)(e - p)); return 0; }
     const char* stop = nl ? nl : e;
     s->carry.append(p, (size_t)(stop - p));
