@@ -25,9 +25,18 @@ namespace tc {
 // NCB = column blocks the epilogue splits the NOUT accumulator columns into (4 epilogue warps -- one per TMEM lane quadrant --
 // per block, CB = NOUT / NCB columns per thread).  More, narrower blocks = more warps to hide the epilogue's latencies
 // (TMEM loads, shuffles, exchange barrier): 6 x 32 instead of 4 x 48 for conv3.
-template <class F, int SA_, int SB_, int NCB_ = 4>
+//
+// RES = true ("resident weights"): the weight ring is replaced by ONE copy of the layer's taps that stays in shared memory
+// for the life of the CTA.  The box of the input column that feeds all four output columns (w' = 3 - PADL) holds, per kh,
+// the four taps kw = 3, 2, 1, 0 as consecutive COUT-row blocks; the operand of any other (w', kh) is the contiguous
+// sub-range of those blocks starting at block 3 - w' + wlo(w') - PADL (tap kw = w' - w + PADL falls by one as the output
+// column w rises by one), i.e. a descriptor start address advanced by whole COUT-row blocks -- a multiple of the swizzle
+// period for every layer here.  KH boxes are loaded once instead of 4 KH boxes per tile: conv3 ingests 70 KB of
+// activations per tile instead of 70 KB + 221 KB of weights.  SB is ignored.
+template <class F, int SA_, int SB_, int NCB_ = 4, bool RES_ = false>
 struct ConvSlabCfg {
-  static constexpr int SA = SA_, SB = SB_, NCB = NCB_;
+  static constexpr int SA = SA_, SB = RES_ ? 1 : SB_, NCB = NCB_;
+  static constexpr bool RES = RES_;
   static constexpr int CB = F::NOUT / NCB;
   static constexpr int EPI_WARPS = 4 * NCB;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
@@ -38,7 +47,9 @@ struct ConvSlabCfg {
   static constexpr int A_SLOT = 2 * A_PLANE;
   static constexpr int B_SLOT = 2 * F::NOUT * F::ROW_BYTES;
   static constexpr int XCH_FLOATS = F::POOL > 1 ? 2 * NCB * 4 * (F::POOL - 1) * CB : 4;
-  static constexpr int RING_BYTES = SA * A_SLOT + SB * B_SLOT;
+  static constexpr int W_BYTES = RES ? F::KH * B_SLOT : SB * B_SLOT;  // resident taps [kh][plane][4 * COUT rows], or the weight ring
+  static constexpr int RING_BYTES = SA * A_SLOT + W_BYTES;
+  static_assert(!RES || (F::COUT * F::ROW_BYTES) % (8 * F::ROW_BYTES) == 0, "tap blocks start on a swizzle period");
   static constexpr int SMEM_BYTES = RING_BYTES + 1024 + 512 + XCH_FLOATS * 4;
   static_assert(A_SLOT % 1024 == 0 || F::ROW_BYTES == 32, "slab slots keep the swizzle atoms aligned");
   static_assert(SMEM_BYTES <= 227 * 1024, "does not fit in shared memory");
@@ -47,6 +58,10 @@ struct ConvSlabCfg {
 using Conv2Slab = ConvSlabCfg<Conv2Tc, 8, 16>;  // two tiles of operands in flight
 using Conv3Slab = ConvSlabCfg<Conv3Tc, 3, 6>;  // (NCB = 6, 24 warps x 32 columns, measured no faster: 0.203 vs 0.199 ms)
 using SlimConv3Slab = ConvSlabCfg<SlimConv3Tc, 4, 8>;
+// resident-weight variants (CVB_CONV_RESIDENT=1): the shared memory the weight ring held goes to deeper activation rings
+using Conv2SlabRes = ConvSlabCfg<Conv2Tc, 12, 0, 4, true>;
+using Conv3SlabRes = ConvSlabCfg<Conv3Tc, 6, 0, 4, true>;
+using SlimConv3SlabRes = ConvSlabCfg<SlimConv3Tc, 8, 0, 4, true>;
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
@@ -74,9 +89,10 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
   uint64_t* emptyB = fullB + S::SB;
   uint64_t* acc_full = emptyB + S::SB;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* w_full = acc_empty + 2;  // RES: the resident taps have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
   float* xch = reinterpret_cast<float*>(smem + S::RING_BYTES + 512);
-  static_assert((2 * S::SA + 2 * S::SB + 4) * 8 + 8 <= 512, "barrier block");
+  static_assert((2 * S::SA + 2 * S::SB + 5) * 8 + 8 <= 512, "barrier block");
 
   __shared__ float bias_s[F::COUT];
   if (threadIdx.x < F::COUT) bias_s[threadIdx.x] = F::ACT ? bias[threadIdx.x] : 0.f;
@@ -89,6 +105,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
     for (int s = 0; s < S::SA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
     for (int s = 0; s < S::SB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], S::EPI_WARPS); }
+    mbar_init(w_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, F::TMEM_COLS);
@@ -103,6 +120,11 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
     // ===================== TMA producer =====================
     if (elect_one()) {
       uint32_t ia = 0, ib = 0;
+      if (S::RES) {  // all taps once: per kh the {BK, 4 * COUT, 2} box of the input column that reaches every output column
+        mbar_arrive_expect_tx(w_full, F::KH * S::B_SLOT);
+        for (int kh = 0; kh < F::KH; ++kh)
+          tma_load_3d(b_ring + kh * S::B_SLOT, &map_b4, w_full, (3 - F::PADL) * F::CIN, kh * F::NOUT, 0);
+      }
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int r0 = (int)(tile * S::TILE_STEP);
         for (int i = 0; i < 4; ++i, ++ia) {
@@ -115,6 +137,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
             mbar_arrive_expect_tx(&fullA[sa], S::A_SLOT);
             tma_load_3d(a_ring + sa * S::A_SLOT, &map_a, &fullA[sa], wp * F::CIN, r0, 0);
           }
+          if (S::RES) continue;
           const CUtensorMap* mb = nb == 2 ? &map_b2 : (nb == 3 ? &map_b3 : &map_b4);
           for (int kh = 0; kh < F::KH; ++kh, ++ib) {
             const int sb = ib % S::SB;
@@ -132,6 +155,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
     // ===================== MMA issuer =====================
     if (elect_one()) {
       uint32_t ia = 0, ib = 0, tcount = 0;
+      if (S::RES) mbar_wait(w_full, 0);
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
         const int buf = tcount & 1;
         mbar_wait(&acc_empty[buf], ((tcount >> 1) & 1) ^ 1);
@@ -144,11 +168,19 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
           const int sa = ia % S::SA;
           mbar_wait(&fullA[sa], (ia / S::SA) & 1);
           const uint32_t a_hi0 = smem_u32(a_ring + sa * S::A_SLOT), a_lo0 = a_hi0 + S::A_PLANE;
+          if (S::RES) tc_fence_after();
           for (int kh = 0; kh < F::KH; ++kh, ++ib) {
             const int sb = ib % S::SB;
-            mbar_wait(&fullB[sb], (ib / S::SB) & 1);
-            tc_fence_after();
-            const uint32_t b_hi = smem_u32(b_ring + sb * S::B_SLOT), b_lo = b_hi + nb * F::COUT * F::ROW_BYTES;
+            uint32_t b_hi, b_lo;
+            if (S::RES) {  // tap blocks 3 - w' + wl - PADL .. of the resident copy: planes NOUT rows apart
+              b_hi = smem_u32(b_ring + kh * S::B_SLOT) + (3 - wp + wl - F::PADL) * (F::COUT * F::ROW_BYTES);
+              b_lo = b_hi + F::NOUT * F::ROW_BYTES;
+            } else {
+              mbar_wait(&fullB[sb], (ib / S::SB) & 1);
+              tc_fence_after();
+              b_hi = smem_u32(b_ring + sb * S::B_SLOT);
+              b_lo = b_hi + nb * F::COUT * F::ROW_BYTES;
+            }
             const uint32_t a_hi = a_hi0 + kh * F::ROW_BYTES, a_lo = a_lo0 + kh * F::ROW_BYTES;  // rows shifted by kh
 #pragma unroll
             for (int ks = 0; ks < F::BK / 16; ++ks) {
@@ -162,7 +194,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
               umma_f16(tcol, dah, dbl, idesc, 1u);
               umma_f16(tcol, dah, dbh, idesc, 1u);
             }
-            umma_commit(&emptyB[sb]);
+            if (!S::RES) umma_commit(&emptyB[sb]);
           }
           umma_commit(&emptyA[sa]);
         }

@@ -104,6 +104,8 @@ struct cvb_model {
   int tc_merged = 1;
   int tc_cluster = 1;  // 2-CTA clusters with weight multicast in the conv tensor kernels (needs tc_merged)
   int tc_slab = 1;     // slab-mode conv kernels (conv_tc_slab.cuh): A loaded once per (tile, w'), re-used across kh
+  int tc_resident = 0; // CVB_CONV_RESIDENT bit mask: 1 = conv3, 2 = conv2 keep their taps in shared memory (ConvSlabCfg RES;
+                       // opt-in until it has been timed and parity-checked on a B200)
   CUtensorMap map_c2slab, map_c3slab;
   CUtensorMap map_c2h2, map_c2h3, map_c2h4, map_c3h2, map_c3h3, map_c3h4;
   // fused tail (FC5 + heads) on tensor cores: A = h4 hi/lo [sites][336], B = [W5 | Wb]^T [176][336]
@@ -407,6 +409,9 @@ static int tc_setup(cvb_model* m) {
     m->tc_slab = !(es && es[0] == '0');
     if (make_slab_map<C, tc::Conv3Slab>(p2_hi, m->p2_rows, CU_TENSOR_MAP_SWIZZLE_64B, &m->map_c3slab)) return 1;
     CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::Conv3Slab>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Conv3Slab::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::Conv3SlabRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Conv3SlabRes::SMEM_BYTES));
+    const char* er = getenv("CVB_CONV_RESIDENT");
+    m->tc_resident = er ? atoi(er) : 0;
     if (m->tc_merged && make_conv_merged_maps<C>(p2_hi, m->p2_rows, m->d_w3b_hi, CU_TENSOR_MAP_SWIZZLE_64B, &m->map_c3a4,
                                                  &m->map_c3b2, &m->map_c3b3, &m->map_c3b4, &m->map_c3h2, &m->map_c3h3,
                                                  &m->map_c3h4)) {
@@ -432,6 +437,7 @@ static int tc_setup(cvb_model* m) {
     m->tc_conv2 = m->tc_conv3 && !(e && e[0] == '0');
     if (make_slab_map<C, tc::Conv2Slab>(m->d_p1, m->p1_rows, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c2slab)) return 1;
     CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::Conv2Slab>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Conv2Slab::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::Conv2SlabRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Conv2SlabRes::SMEM_BYTES));
     if (m->tc_merged && make_conv_merged_maps<C>(m->d_p1, m->p1_rows, m->d_w2b_hi, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c2a4,
                                                  &m->map_c2b2, &m->map_c2b3, &m->map_c2b4, &m->map_c2h2, &m->map_c2h3,
                                                  &m->map_c2h4))
@@ -484,6 +490,10 @@ static int tc_setup_slim(cvb_model* m) {
   if (make_slab_map<C, tc::SlimConv3Slab>(m->d_p2, m->p2_rows, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c3slab)) return 1;
   CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::SlimConv3Slab>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           tc::SlimConv3Slab::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::SlimConv3SlabRes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          tc::SlimConv3SlabRes::SMEM_BYTES));
+  const char* er = getenv("CVB_CONV_RESIDENT");
+  m->tc_resident = er ? atoi(er) : 0;
   CK(cudaFuncSetAttribute(tc::k_conv_tc<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tc::k_conv_tc<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   m->tc_ready = true;
@@ -588,8 +598,8 @@ static HeadPtrs head_ptrs(const cvb_model* m) {
 
 // one chunk (n <= CHUNK) of the forward pass on `st`
 // launches k_conv_tc<T> either plainly or as 2-CTA clusters (weight multicast)
-template <class T, class S>
-static int launch_conv_tc(cvb_model* m, int64_t n, cudaStream_t st, const CUtensorMap* slab, const CUtensorMap& a_hi,
+template <class T, class S, class SR>
+static int launch_conv_tc(cvb_model* m, int resident, int64_t n, cudaStream_t st, const CUtensorMap* slab, const CUtensorMap& a_hi,
                           const CUtensorMap& a_lo,
                           const CUtensorMap& b_hi, const CUtensorMap& b_lo, const CUtensorMap& a4, const CUtensorMap& b2,
                           const CUtensorMap& b3, const CUtensorMap& b4, const CUtensorMap& h2, const CUtensorMap& h3,
@@ -598,7 +608,10 @@ static int launch_conv_tc(cvb_model* m, int64_t n, cudaStream_t st, const CUtens
     const int64_t st_tiles = (n * T::RPS + S::TILE_STEP - 1) / S::TILE_STEP;
     const int g = (int)std::min<int64_t>(st_tiles, m->num_sms);
     static const int ablate = getenv("CVB_ABLATE") ? atoi(getenv("CVB_ABLATE")) : 0;  // timing experiments only
-    tc::k_conv_slab<T, S><<<g, S::THREADS, S::SMEM_BYTES, st>>>(*slab, b2, b3, b4, n, bias, inv_scale, out_hi, out_lo, ablate);
+    if (resident)
+      tc::k_conv_slab<T, SR><<<g, SR::THREADS, SR::SMEM_BYTES, st>>>(*slab, b2, b3, b4, n, bias, inv_scale, out_hi, out_lo, ablate);
+    else
+      tc::k_conv_slab<T, S><<<g, S::THREADS, S::SMEM_BYTES, st>>>(*slab, b2, b3, b4, n, bias, inv_scale, out_hi, out_lo, ablate);
     CK(cudaGetLastError());
     return 0;
   }
@@ -671,7 +684,7 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
         if (prof_mark(m, st)) return 1;  // kind 0 = SIMT front (conv1+pool1 here), kind 1 = tcgen05 conv2
         using T = tc::Conv2Tc;
         __half* p2_hi = reinterpret_cast<__half*>(m->d_p2);
-        if (launch_conv_tc<T, tc::Conv2Slab>(m, n, st, &m->map_c2slab, m->map_c2a_hi, m->map_c2a_lo, m->map_c2b_hi, m->map_c2b_lo, m->map_c2a4, m->map_c2b2,
+        if (launch_conv_tc<T, tc::Conv2Slab, tc::Conv2SlabRes>(m, m->tc_resident & 2, n, st, &m->map_c2slab, m->map_c2a_hi, m->map_c2a_lo, m->map_c2b_hi, m->map_c2b_lo, m->map_c2a4, m->map_c2b2,
                               m->map_c2b3, m->map_c2b4, m->map_c2h2, m->map_c2h3, m->map_c2h4, m->var("conv2/bias"),
                               m->d_inv_scale + 2, p2_hi, p2_hi + m->p2_rows * 128))
           return 1;
@@ -703,7 +716,7 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       if (tensor && m->tc_conv3) {
         using T = tc::Conv3Tc;
         __half* p3_hi = reinterpret_cast<__half*>(m->d_p3);
-        if (launch_conv_tc<T, tc::Conv3Slab>(m, n, st, &m->map_c3slab, m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo,
+        if (launch_conv_tc<T, tc::Conv3Slab, tc::Conv3SlabRes>(m, m->tc_resident & 1, n, st, &m->map_c3slab, m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo,
                                              m->map_c3a4, m->map_c3b2, m->map_c3b3, m->map_c3b4, m->map_c3h2, m->map_c3h3,
                                              m->map_c3h4, m->var("conv3/bias"), m->d_inv_scale + 1, p3_hi,
                                              p3_hi + m->alloc_sites * 4608))
@@ -805,7 +818,7 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
     }
     if (tensor) {
       using T = tc::SlimConv3Tc;
-      if (launch_conv_tc<T, tc::SlimConv3Slab>(m, n, st, &m->map_c3slab, m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo,
+      if (launch_conv_tc<T, tc::SlimConv3Slab, tc::SlimConv3SlabRes>(m, m->tc_resident & 1, n, st, &m->map_c3slab, m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo,
                                                m->map_c3a4, m->map_c3b2, m->map_c3b3,
                             m->map_c3b4, m->map_c3h2, m->map_c3h3, m->map_c3h4, m->var("conv3/bias"), m->d_inv_scale + 1,
                             reinterpret_cast<__half*>(m->d_p3), nullptr))
@@ -1227,10 +1240,16 @@ using Conv2FS = tc::ConvSlabCfg<Conv2F, 4, 8>;
 using Conv3FS = tc::ConvSlabCfg<Conv3F, 3, 6>;
 using Conv3DS = tc::ConvSlabCfg<Conv3D, 3, 3>;
 using Conv2DS = tc::ConvSlabCfg<Conv2D, 3, 6>;
+// resident-weight variants (CVB_CONV_RESIDENT bit 4, see ConvSlabCfg)
+using SlimConv3DR = tc::ConvSlabCfg<SlimConv3D, 6, 0, 4, true>;
+using Conv2FR = tc::ConvSlabCfg<Conv2F, 8, 0, 4, true>;
+using Conv3FR = tc::ConvSlabCfg<Conv3F, 6, 0, 4, true>;
+using Conv3DR = tc::ConvSlabCfg<Conv3D, 3, 0, 4, true>;
+using Conv2DR = tc::ConvSlabCfg<Conv2D, 6, 0, 4, true>;
 }  // namespace trc
 
 // act: hi plane [rows = nc * RPS][KROW], lo plane act_plane elements later; wts: B [KH * NOUT][KROW] hi then lo plane
-template <class F, class S>
+template <class F, class S, class SR>
 static int launch_train_conv(cvb_model* m, const uint16_t* act, int64_t act_plane, const uint16_t* wts, int64_t nc, const float* bias,
                              const float* inv_scale, float* out, cudaStream_t st) {
   const CUtensorMapSwizzle sw = F::ROW_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -1246,11 +1265,18 @@ static int launch_train_conv(cvb_model* m, const uint16_t* act, int64_t act_plan
     const uint32_t bb[3] = {(uint32_t)F::BK, (uint32_t)(nb * F::COUT), 2};
     if (make_map_nd(&mb[nb - 2], (void*)wts, 3, bd, bs, bb, sw)) return 1;
   }
-  auto k = tc::k_conv_slab<F, S>;
-  CK(set_smem(k, S::SMEM_BYTES));
   const int64_t tiles = (nc * F::RPS + S::TILE_STEP - 1) / S::TILE_STEP;
   const int grid = (int)std::min<int64_t>(tiles, m->num_sms);
-  k<<<grid, S::THREADS, S::SMEM_BYTES, st>>>(ma, mb[0], mb[1], mb[2], nc, bias, inv_scale, reinterpret_cast<__half*>(out), nullptr, 0);
+  static const int resident = getenv("CVB_CONV_RESIDENT") ? atoi(getenv("CVB_CONV_RESIDENT")) & 4 : 0;
+  if (resident) {
+    auto k = tc::k_conv_slab<F, SR>;
+    CK(set_smem(k, SR::SMEM_BYTES));
+    k<<<grid, SR::THREADS, SR::SMEM_BYTES, st>>>(ma, mb[0], mb[1], mb[2], nc, bias, inv_scale, reinterpret_cast<__half*>(out), nullptr, 0);
+  } else {
+    auto k = tc::k_conv_slab<F, S>;
+    CK(set_smem(k, S::SMEM_BYTES));
+    k<<<grid, S::THREADS, S::SMEM_BYTES, st>>>(ma, mb[0], mb[1], mb[2], nc, bias, inv_scale, reinterpret_cast<__half*>(out), nullptr, 0);
+  }
   CK(cudaGetLastError());
   m->launches += 1;
   return 0;
@@ -1287,7 +1313,7 @@ static int train_forward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t se
   if (stc) {
     // conv3 on the tcgen05 slab kernel (the inference configuration already keeps every SELU output: no pooling in slim),
     // FC4 = c3 [sites][4224] . W4 as a split-bf16 GEMM (N = 36 in one 48-column tile)
-    if (launch_train_conv<tc::SlimConv3Tc, tc::SlimConv3Slab>(m, w->p2h, w->cap * 37 * 64, w->wf3, nc, m->var("conv3/bias"), w->fsc + 1,
+    if (launch_train_conv<tc::SlimConv3Tc, tc::SlimConv3Slab, tc::SlimConv3SlabRes>(m, w->p2h, w->cap * 37 * 64, w->wf3, nc, m->var("conv3/bias"), w->fsc + 1,
                                                               w->c3, st))
       return 1;
     if (split_rows_bf16(w->c3, nc, 4224, w->p3s, w->cap * 4224, st)) return 1;
@@ -1360,7 +1386,7 @@ static int train_backward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t s
                                                                         bf(w->g3h), bf(w->g3h) + w->cap * 37 * 128);
     if (launch_conv_wgrad_tc<16, 32, 5, 32, -2>(m, w->p2b, w->cap * 37 * 64, w->g3h, w->cap * 37 * 128, nc * 37, gvar(m, "conv3/kernel"), st))
       return 1;
-    if (launch_train_conv<trc::SlimConv3D, trc::SlimConv3DS>(m, w->g3h, w->cap * 37 * 128, w->wd3, nc, nullptr, w->fsc + 2, w->gp2, st))
+    if (launch_train_conv<trc::SlimConv3D, trc::SlimConv3DS, trc::SlimConv3DR>(m, w->g3h, w->cap * 37 * 128, w->wd3, nc, nullptr, w->fsc + 2, w->gp2, st))
       return 1;
   } else {
   k_gemm_tn<<<dim3(4224 / 64, 1), 256, 0, st>>>(w->c3, 4224, w->g4, 36, gvar(m, "fc4/kernel"), 36, 4224, 36, nc);
@@ -1412,11 +1438,11 @@ static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, i
                                                      tcm ? bf(w->p1b) + w->cap * 30 * 64 : nullptr);
   }
   if (tcm) {
-    if (launch_train_conv<trc::Conv2F, trc::Conv2FS>(m, w->p1h, w->cap * 30 * 64, w->wf2, nc, m->var("conv2/bias"), w->fsc + 0, w->c2, st))
+    if (launch_train_conv<trc::Conv2F, trc::Conv2FS, trc::Conv2FR>(m, w->p1h, w->cap * 30 * 64, w->wf2, nc, m->var("conv2/bias"), w->fsc + 0, w->c2, st))
       return 1;
     k_pool_fwd<4><<<gsz(nc * 26 * 32), 256, 0, st>>>(w->c2, nc, 29, 128, w->p2p, 28, 1, hp(w->p2h), hp(w->p2h) + w->cap * 28 * 128,
                                                      bf(w->p2b), bf(w->p2b) + w->cap * 28 * 128);
-    if (launch_train_conv<trc::Conv3F, trc::Conv3FS>(m, w->p2h, w->cap * 28 * 128, w->wf3, nc, m->var("conv3/bias"), w->fsc + 1, w->c3, st))
+    if (launch_train_conv<trc::Conv3F, trc::Conv3FS, trc::Conv3FR>(m, w->p2h, w->cap * 28 * 128, w->wf3, nc, m->var("conv3/bias"), w->fsc + 1, w->c3, st))
       return 1;
     // pool3 also writes p3 as the split-bf16 A operand of the FC4 forward GEMM
     k_pool_fwd<3, true><<<gsz(nc * 24 * 48), 256, 0, st>>>(w->c3, nc, 26, 192, w->p3, 24, 0, hp(w->p3s), hp(w->p3s) + w->cap * 4608);
@@ -1587,7 +1613,7 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
       CK(cudaGetLastError());
     }
     if (tcm) {
-      if (launch_train_conv<trc::Conv3D, trc::Conv3DS>(m, w->g3h, w->cap * 28 * 256, w->wd3, nc, nullptr, w->fsc + 2, w->gp2, st)) return 1;
+      if (launch_train_conv<trc::Conv3D, trc::Conv3DS, trc::Conv3DR>(m, w->g3h, w->cap * 28 * 256, w->wd3, nc, nullptr, w->fsc + 2, w->gp2, st)) return 1;
     } else {
       using C = ConvCfg<48, 32, 3, 26, 3, 8, 8, 2>;
       using L = ConvLayerSmem<C, 1>;
@@ -1613,7 +1639,7 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
       CK(cudaGetLastError());
     }
     if (tcm) {
-      if (launch_train_conv<trc::Conv2D, trc::Conv2DS>(m, w->g2h, w->cap * 30 * 128, w->wd2, nc, nullptr, w->fsc + 2, w->gp1, st)) return 1;
+      if (launch_train_conv<trc::Conv2D, trc::Conv2DS, trc::Conv2DR>(m, w->g2h, w->cap * 30 * 128, w->wd2, nc, nullptr, w->fsc + 2, w->gp1, st)) return 1;
     } else {
       using C = ConvCfg<32, 16, 2, 29, 4, 8, 8, 2>;
       using L = ConvLayerSmem<C, 1>;

@@ -1,0 +1,46 @@
+"""A/B of the resident-weight conv kernels (ConvSlabCfg RES, conv_tc_slab.cuh) on one B200: for CVB_CONV_RESIDENT in
+0 (ring, default), 1 (conv3), 2 (conv2), 3 (both) and both variants, checks that the logits are BIT-IDENTICAL to the default
+path (the same MMAs in the same order on the same operands) and prints per-kernel ms per chunk.  Run each setting under its
+own timeout on the GPU box (tools/capture_resident.sh): a mis-programmed descriptor hangs the kernel, it does not fail.
+    python tools/ab_resident.py <variant: v3|slim> <setting>        # writes gpurun_out/ab_resident_<variant>_<setting>.npy/json"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+variant, setting = sys.argv[1], sys.argv[2]
+os.environ["CVB_CONV_RESIDENT"] = setting
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from clairvoyante_b200 import initializers as I, synth  # noqa: E402
+if variant == "v3":
+    from clairvoyante_b200 import clairvoyante_v3 as cv
+else:
+    from clairvoyante_b200 import clairvoyante_v3_slim as cv
+
+os.makedirs("gpurun_out", exist_ok=True)
+m = cv.Clairvoyante()
+m.setWeights(I.init_weights(variant, 0))
+chunk = 18944 if variant == "v3" else 33152
+x = synth.make_sites(chunk + 1234, 1)          # one full chunk and a ragged one
+_, logits = m.predictLogits(x)
+np.save("gpurun_out/ab_resident_%s_%s.npy" % (variant, setting), logits)
+ref_fn = "gpurun_out/ab_resident_%s_0.npy" % variant
+same = bool(np.array_equal(np.load(ref_fn), logits)) if setting != "0" and os.path.exists(ref_fn) else None
+
+N = chunk * 8
+xd = torch.from_numpy(x[:chunk]).cuda().repeat(8, 1, 1, 1).contiguous()
+od = torch.empty((N, 16), device="cuda")
+st = torch.cuda.current_stream().cuda_stream
+for _ in range(2):
+    m.predictDevice(xd.data_ptr(), N, od.data_ptr(), None, st)
+torch.cuda.synchronize()
+m.profileBegin()
+for _ in range(4):
+    m.predictDevice(xd.data_ptr(), N, od.data_ptr(), None, st)
+pr = m.profileRead()
+out = {"variant": variant, "CVB_CONV_RESIDENT": setting, "bit_identical_to_default": same,
+       "ms_per_chunk": {k: round(v[0] / max(v[1], 1), 4) for k, v in pr.items()}}
+print(json.dumps(out))
+json.dump(out, open("gpurun_out/ab_resident_%s_%s.json" % (variant, setting), "w"))
+m.close()
