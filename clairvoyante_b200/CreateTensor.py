@@ -15,6 +15,7 @@ yields exactly what utils_v2.GetTensor yields for the rows this module would hav
 import argparse
 import ctypes
 import gzip
+import re
 import shlex
 import shutil
 import subprocess
@@ -230,12 +231,59 @@ def _load_candidates(args):
     return out
 
 
+_CIGAR_OP = re.compile(rb"(\d+)([MIDNSHP=X])")
+
+
+class _SamTextView(object):
+    """What `samtools view -F 2308 <file> ctg[:start-end]` (reference CreateTensor.py:134-136) prints, for a SAM TEXT file:
+    header lines are dropped, records of other contigs, unmapped / secondary / supplementary records (flag & 2308) and
+    records that do not overlap the 1-based inclusive region are skipped.  File-like: read() hands out filtered chunks."""
+
+    def __init__(self, fh, ctgName, start=None, end=None):
+        self.fh, self.ctg, self.start, self.end, self.carry = fh, ctgName.encode(), start, end, b""
+
+    def _keep(self, line):
+        if line[:1] == b"@":
+            return False
+        f = line.split(b"\t", 6)
+        if len(f) < 6:
+            return bool(line.strip())                  # malformed: let the native stage count it
+        try:
+            if int(f[1]) & 2308 or f[2] != self.ctg:
+                return False
+            if self.start is None:
+                return True
+            lo = int(f[3])
+        except ValueError:
+            return True
+        if lo > self.end:
+            return False
+        if lo >= self.start:
+            return True
+        span = sum(int(n) for n, op in _CIGAR_OP.findall(f[5]) if op in b"MDN=X")
+        return lo + max(span, 1) - 1 >= self.start
+
+    def read(self, size=8 << 20):
+        while True:
+            b = self.fh.read(size)
+            if not b:
+                last, self.carry = self.carry, b""
+                return last if last and self._keep(last) else b""
+            lines = (self.carry + b).split(b"\n")
+            self.carry = lines.pop()
+            out = [ln for ln in lines if self._keep(ln)]
+            if out:
+                return b"\n".join(out) + b"\n"
+
+    def close(self):
+        self.fh.close()
+
+
 def _open_alignments(args):
     fn = args.bam_fn
-    if fn.endswith(".sam"):
-        return None, open(fn, "rb")
-    if fn.endswith(".sam.gz"):
-        return None, gzip.open(fn, "rb")
+    if fn.endswith(".sam") or fn.endswith(".sam.gz"):
+        fh = gzip.open(fn, "rb") if fn.endswith(".gz") else open(fn, "rb")
+        return None, _SamTextView(fh, args.ctgName, args.ctgStart, args.ctgEnd if args.ctgStart is not None else None)
     if not shutil.which(args.samtools):
         sys.exit("samtools not found: pass a .sam / .sam.gz text file as --bam_fn or install samtools")
     region = "%s:%d-%d" % (args.ctgName, args.ctgStart, args.ctgEnd) if args.ctgStart is not None else args.ctgName

@@ -1,6 +1,9 @@
 """Per-site restatement of the reference's VCF record logic (clairvoyante/callVar.py:50-153).
 TEST INFRASTRUCTURE ONLY (see oracle/cv_oracle.py header).  One candidate at a time, scalar Python, following the
-reference's decision order; tests compare clairvoyante_b200.callVar.Output (batched NumPy) against it."""
+reference's decision order; tests compare clairvoyante_b200.callVar.Output (batched NumPy) against it.
+Pinned against the reference itself: the VCF records the reference's own callVar.Test / Output wrote for 630 tensors and a
+fixed probability table (tests/golden/reference_run.npz, made by tests/golden/make_golden_reference_run.py) are reproduced
+line for line (tests/test_reference_run_cpu.py)."""
 from math import log
 
 import numpy as np

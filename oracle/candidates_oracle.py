@@ -5,8 +5,11 @@ Follows MakeCandidates (:53-253) and OutputCandidate (:22-42) statement by state
 per-position counters and its `sweep` loop.  The native extractor (clairvoyante_b200/csrc/candidates.cpp) is checked against
 this on the same SAM text.
 
-Parity unpinned: no reference fixture; `samtools` and `intervaltree` are absent here.  What had to be restated rather than
-copied: (a) the counters are a Python-2 dict literal {"A","C","G","T","I","D","N"} whose `.items()` order decides ties in the
+Pinned against the reference itself: tests/golden/reference_run.npz holds the rows the reference's own script printed for
+three scenarios (defaults; region + BED + MAPQ / threshold / coverage options; low threshold) when it was executed in the
+build container with stand-ins for samtools / gzip / intervaltree and a replayed CPython-2.7 dict order
+(tests/golden/make_golden_reference_run.py); this restatement and the native stage reproduce them byte for byte
+(tests/test_reference_run_cpu.py).  What had to be restated rather than copied: (a) the counters are a Python-2 dict literal {"A","C","G","T","I","D","N"} whose `.items()` order decides ties in the
 stable descending sort (:33) -- for CPython 2.7 (64-bit, no hash randomisation) that order is A, C, D, G, I, N, T (an
 8-slot presized table grows to 32 slots on the sixth insertion; a one-character string hashes to slot (ord(c) ^ 1) & 31);
 under PyPy, which the reference also supports, the order would be the insertion order; (b) the BED lookup

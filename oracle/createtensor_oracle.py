@@ -6,8 +6,11 @@ Follows the reference statement by statement with its own data structures -- `be
 sums the tuples only at flush time in `generate_tensor`, like GenerateTensor (:23-59).  The native pile-up
 (clairvoyante_b200/csrc/pileup.cpp) accumulates on the fly and is checked against this on the same SAM text.
 
-Parity unpinned: the reference ships no fixture for this path and needs `samtools` (absent here) to produce its inputs;
-the SAM rows used by the tests are synthetic, in the column layout `samtools view` prints.
+Pinned against the reference itself: tests/golden/reference_run.npz holds the tensor rows the reference's own script printed
+for three scenarios (defaults; region, MAPQ, depth cap and coverage options; considerleftedge off) when it was executed in
+the build container with stand-ins for samtools / gzip (tests/golden/make_golden_reference_run.py); this restatement and the
+native stage reproduce them -- same centres, same order, byte-identical "%0.1f" text (tests/test_reference_run_cpu.py).
+The SAM rows are synthetic, in the column layout `samtools view` prints.
 
 Restated with these stated differences (shared with the product): (1) centres flushed together are emitted in ascending
 position order -- the reference iterates a Python-2 dict (:238, :248); (2) a reference / read index outside the supplied

@@ -3,8 +3,9 @@
 Pure-Python tokeniser following the reference row by row: `row.split()`, `np.array(strings, float32)`, drop rows whose
 centre reference base is not ACGT (:39), `X[...,1:4] -= X[...,0:1]` (:46,57), batches of `num`, final partial batch with
 endFlag 1.  The native parser (clairvoyante_b200/csrc/text_feed.cpp) is checked against this on the same bytes.
-Parity unpinned: the reference ships no fixture for this path; the rows used by the tests are generated in the
-format of dataPrepScripts/CreateTensor.py:56.  One deliberate difference from the reference (shared with the product):
+Pinned against the reference itself: tests/golden/reference_run.npz holds what the reference's own utils_v2.GetTensor
+yielded for 630 rows when it was executed in the build container (generator and its stand-ins:
+tests/golden/make_golden_reference_run.py; check: tests/test_reference_run_cpu.py).  One deliberate difference from the reference (shared with the product):
 a malformed row is reported and skipped instead of silently re-using the previous row's fields (:34-41).
 """
 import io
