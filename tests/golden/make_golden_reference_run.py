@@ -100,8 +100,10 @@ class _IntervalTree(object):
     def addi(self, begin, end):
         self.iv.append((begin, end))
 
-    def search(self, point):
-        return [iv for iv in self.iv if iv[0] <= point < iv[1]]
+    def search(self, begin, end=None):
+        if end is None:
+            return [iv for iv in self.iv if iv[0] <= begin < iv[1]]
+        return [iv for iv in self.iv if iv[0] < end and begin < iv[1]]
 
 
 def _ref_span(pos1, cigar):
@@ -156,11 +158,17 @@ class _Popen(object):
             text = "".join(out)
         elif argv[:2] == ["gzip", "-fdc"]:
             text = open(argv[2]).read()
+        elif argv == ["gzip", "-c"]:         # writer: text written to .stdin lands (uncompressed) in the file given as stdout
+            self._sink, self.stdin = stdout, _Stdout()
+            return
         else:
             raise AssertionError("command not emulated: %r" % (argv,))
         self.stdout = io.StringIO(text)
 
     def wait(self):
+        if getattr(self, "_sink", None) is not None:
+            self._sink.write(self.stdin.getvalue().encode())
+            self._sink = None
         return self.returncode
 
 
@@ -179,6 +187,22 @@ REWRITES = {
     "utils_v2": [
         (r"print >> sys\.stderr, (.*)$", r"print(\1, file=sys.stderr)", 4),
     ],
+    "train": [
+        (r"dtype=np\.int \)", r"dtype=int )", 3),      # (NumPy removed the np.int alias; not a Python 2 matter)
+    ],
+    "evaluate": [
+        (r"dtype=np\.int \)", r"dtype=int )", 3),
+    ],
+    "calTrainDevDiff": [
+        (r"print >> sys\.stderr, (.*)$", r"print(\1, file=sys.stderr)", 2),
+    ],
+    "GetTruth": [],
+    "PairWithNonVariants": [],
+    "callVarBamParallel": [
+        (r"range\(0,23\)\+", r"list(range(0,23))+", 2),
+    ],
+    "trainNonstop": [],
+    "trainWithoutValidationNonstop": [],
     "callVar": [
         (r"print >> call_fh, (.*)$", r"print(\1, file=call_fh)", 14),
         (r"#print >> sys\.stderr, (.*)$", r"#print(\1, file=sys.stderr)", 1),
@@ -398,6 +422,175 @@ def feed_and_callvar(tensor_text, tmp):
     return fx
 
 
+# --------------------------------------------------------------------------------------- training driver (train.py)
+class StubTrainer(object):
+    """stands where the TensorFlow model would in train.py's TrainAll: deterministic losses (the per-row validation loss
+    alternates from epoch to epoch, which is what drives the reference's learning-rate switches), every call logged"""
+
+    def __init__(self):
+        self.calls, self.epoch, self.lr, self.l2 = [], 1, None, None
+
+    @staticmethod
+    def _cs(X, Y=None):
+        return round(float(np.asarray(X, np.float64).sum()) + (float(np.asarray(Y, np.float64).sum()) if Y is not None else 0.0), 3)
+
+    def _val(self, n):
+        return n * (1.0 + (0.25 if self.epoch % 2 else -0.25) + 0.001 * self.epoch)
+
+    def trainNoRT(self, X, Y):
+        self.calls.append(("trainNoRT", len(X), self._cs(X, Y)))
+        self.trainLossRTVal, self.trainSummaryRTVal = float(np.abs(np.asarray(X, np.float64)).sum()) * 1e-3 / self.epoch, None
+
+    def getLossNoRT(self, X, Y):
+        self.calls.append(("getLossNoRT", len(X), self._cs(X, Y)))
+        self.getLossLossRTVal = self._val(len(X))
+
+    def getLoss(self, X, Y):
+        self.calls.append(("getLoss", len(X), self._cs(X, Y)))
+        return self._val(len(X))
+
+    def setLearningRate(self, v=None):
+        self.lr = self.lr * 0.1 if v is None else v
+        self.calls.append(("setLearningRate", v, self.lr))
+        return self.lr
+
+    def setL2RegularizationLambda(self, v=None):
+        self.l2 = self.l2 * 0.1 if v is None else v
+        self.calls.append(("setL2RegularizationLambda", v, self.l2))
+        return self.l2
+
+    def saveParameters(self, path):
+        self.calls.append(("saveParameters", os.path.basename(path)))
+        self.epoch += 1
+
+    def restoreParameters(self, path):
+        self.calls.append(("restoreParameters", os.path.basename(path)))
+        self.epoch = int(path[-6:])
+
+    def predict(self, X):
+        self.calls.append(("predict", len(X), self._cs(X)))
+        f = np.asarray(X, np.float32).reshape(len(X), -1)
+        return f[:, 256:260], f[:, 260:262], f[:, 262:266], f[:, 266:272]
+
+
+DRIVERS = [   # (module, entry point, param overrides, extra args)
+    ("train", "TrainAll", dict(trainBatchSize=200, predictBatchSize=50), {}),
+    ("trainNonstop", "TrainAll", dict(trainBatchSize=200, predictBatchSize=50, maxEpoch=5), {}),
+    ("trainWithoutValidationNonstop", "TrainAll", dict(trainBatchSize=150, predictBatchSize=50, maxEpoch=4), {}),
+    ("evaluate", "Test", dict(predictBatchSize=70), {}),
+    ("calTrainDevDiff", "CalcAll", dict(predictBatchSize=60), dict(chkpnt_fn=["model-000003", "model-000008"])),
+]
+
+
+def run_drivers(fx, tmp):
+    """train.py / trainNonstop.py / trainWithoutValidationNonstop.py / evaluate.py / calTrainDevDiff.py with StubTrainer"""
+    import logging
+    import pickle
+    X = fx["feed/train_nobed_x"].astype(np.float32)
+    Y = fx["feed/train_nobed_y"]
+    pos = fx["feed/train_nobed_pos"]
+    total = int(fx["feed/train_nobed_total"])
+    utils = load_reference("utils_v2", ref_dir=CV_DIR)
+    bs = utils.param.bloscBlockSize
+    blocks = lambda a: [("blosc-stand-in", a[i:i + bs]) for i in range(0, total, bs)]
+    bin_fn = os.path.join(tmp, "train.bin")
+    with open(bin_fn, "wb") as fh:
+        for obj in (total, blocks(X), blocks(Y), blocks(pos)):
+            pickle.dump(obj, fh)
+    out = {}
+    for name, entry, overrides, extra in DRIVERS:
+        mod = load_reference(name, ref_dir=CV_DIR)
+        for k, v in overrides.items():
+            setattr(mod.param, k, v)
+        msgs = []
+
+        class Collect(logging.Handler):
+            def emit(self, record):
+                msgs.append(record.getMessage())
+
+        h = Collect()
+        logging.getLogger().addHandler(h)
+        logging.getLogger().setLevel(logging.INFO)
+        err = io.StringIO()
+        try:
+            m = StubTrainer()
+            kw = dict(bin_fn=bin_fn, tensor_fn=None, var_fn=None, bed_fn=None, chkpnt_fn=None, learning_rate=1e-3, lambd=1e-3,
+                      ochk_prefix=os.path.join(tmp, "model"), olog_dir=None, v2=False, v3=True, slim=False)
+            kw.update(extra)
+            with contextlib.redirect_stderr(err):
+                getattr(mod, entry)(types.SimpleNamespace(**kw), m, utils)
+        finally:
+            logging.getLogger().removeHandler(h)
+        msgs = [x for x in msgs if "time elapsed" not in x] + [l for l in err.getvalue().split("\n") if l]
+        print("%-30s %4d model calls, %3d log lines" % (name + ".py:", len(m.calls), len(msgs)))
+        out[name + "/calls"] = np.array([repr(c) for c in m.calls])
+        out[name + "/log"] = np.array(msgs)
+    return out
+
+
+# ------------------------------------------------------------------- GetTruth, PairWithNonVariants, callVarBamParallel
+def run_small_scripts(fx, tmp):
+    import random
+    out = {}
+    # GetTruth: VCF -> "ctg pos ref alt gt1 gt2" rows
+    vcf = ["##fileformat=VCFv4.1", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS"]
+    gts = ["0/1", "1/1", "0|1", "1|0", "1|2", "./1", "1/2", "2|1"]
+    rng = np.random.RandomState(3)
+    for i in range(120):
+        ref = "ACGT"[i % 4] + ("TG" * (i % 3 == 2))
+        alts = ["ACGT"[(i + 1) % 4] + "A" * (i % 5 == 1), "ACGT"[(i + 2) % 4] + "CC" * (i % 7 == 3)]
+        gt = gts[i % len(gts)]
+        alt = ",".join(alts) if "2" in gt or i % 11 == 0 else alts[0]
+        vcf.append("\t".join(["ctg" if i % 13 else "other", str(100 + 17 * i), ".", ref, alt, "50", "PASS", ".", "GT:GQ", gt + ":%d" % (i % 90)]))
+    vfn = os.path.join(tmp, "truth.vcf")
+    open(vfn, "w").write("\n".join(vcf) + "\n")
+    out["gettruth/vcf"] = np.array("\n".join(vcf) + "\n")
+    gt_mod = load_reference("GetTruth")
+    out["gettruth/all"] = np.array(run_main(gt_mod, ["--vcf_fn", vfn, "--ctgName", "ctg"]))
+    out["gettruth/region"] = np.array(run_main(gt_mod, ["--vcf_fn", vfn, "--ctgName", "ctg", "--ctgStart", "400", "--ctgEnd", "1500"]))
+    print("GetTruth: %d / %d rows" % (str(out["gettruth/all"]).count("\n"), str(out["gettruth/region"]).count("\n")))
+
+    # PairWithNonVariants: tensors at truth variants + tensors at candidates -> training tensor file (seeded sample)
+    lines = [l for l in fx["feed/tensor_text"].tobytes().decode().split("\n") if l]
+    var_lines, can_lines = lines[:90], lines[60:]
+    tv, tc, bed, outfn = (os.path.join(tmp, n) for n in ("tensor_var", "tensor_can", "pair.bed", "tensor_pair"))
+    open(tv, "w").write("".join(l + "\n" for l in var_lines))
+    open(tc, "w").write("".join(l + "\n" for l in can_lines))
+    open(bed, "w").write("ctg\t0\t1200\nctg\t1500\t700000\n")
+    pw = load_reference("PairWithNonVariants")
+    for tag, b, amp in (("nobed", None, 2), ("bed", bed, 1)):
+        random.seed(12345)
+        argv = ["--tensor_can_fn", tc, "--tensor_var_fn", tv, "--output_fn", outfn, "--amp", str(amp)] + (["--bed_fn", b] if b else [])
+        run_main(pw, argv)
+        got = open(outfn).read()
+        out["pair/%s_positions" % tag] = np.array([" ".join(l.split()[:2]) for l in got.split("\n") if l])
+        out["pair/%s_sha256" % tag] = np.array(hashlib.sha256(got.encode()).hexdigest())
+        print("PairWithNonVariants %-5s: %d rows" % (tag, got.count("\n")))
+    out["pair/n_var"], out["pair/n_can_from"] = np.array(90), np.array(60)
+
+    # callVarBamParallel: the per-chunk commands
+    fa = os.path.join(tmp, "genome.fa")
+    for fn in (fa, os.path.join(tmp, "aln.bam"), os.path.join(tmp, "model.meta")):
+        open(fn, "w").write("x\n")
+    open(fa + ".fai", "w").write("chr1\t25000000\t6\t60\t61\nchr2\t10000001\t7\t60\t61\nchrUn_x\t5000\t8\t60\t61\n21\t9999999\t9\t60\t61\n")
+    cbed = os.path.join(tmp, "chunks.bed")
+    open(cbed, "w").write("chr1\t10000000\t10000001\nchr1\t19999999\t20000500\n21\t5\t500\n")
+    cp = load_reference("callVarBamParallel", ref_dir=CV_DIR)
+    cp.__file__ = os.path.join(CV_DIR, "callVarBamParallel.py")
+    real_subprocess = __import__("subprocess")
+    cp.subprocess = types.SimpleNamespace(Popen=_Popen, PIPE=-1, check_output=real_subprocess.check_output)
+    base = ["--chkpnt_fn", os.path.join(tmp, "model"), "--ref_fn", fa, "--bam_fn", os.path.join(tmp, "aln.bam"), "--pypy", "python",
+            "--samtools", "python", "--output_prefix", "out/calls"]
+    for tag, extra in (("default", []), ("bed_qual", ["--bed_fn", cbed, "--qual", "30", "--refChunkSize", "5000000", "--sampleName", "HG"]),
+                       ("allcontigs", ["--includingAllContigs", "--threshold", "0.2", "--minCoverage", "6", "--tensorflowThreads", "8"])):
+        text = run_main(cp, base + extra)
+        text = text.replace(tmp, "TMP").replace(CV_DIR, "REFDIR")
+        out["parallel/" + tag] = np.array(text)
+        out["parallel/%s_args" % tag] = np.array(extra, dtype=str)
+        print("callVarBamParallel %-10s: %d commands" % (tag, text.count("\n")))
+    return out
+
+
 def main():
     order27 = py27_dict_order(["A", "C", "G", "T", "I", "D", "N"])
     print("CPython 2.7 iteration order of the counter literal:", " ".join(order27))
@@ -441,6 +634,8 @@ def main():
             print("%-28s %4d candidate rows (%d differ under the py3 dict order), %4d tensors"
                   % (n, rows27.count("\n"), sum(a != b for a, b in zip(rows27.split("\n"), rows3.split("\n"))), len(lines)))
         fixture.update(feed_and_callvar("".join(all_tensor_text), tmp))
+        fixture.update(run_drivers(fixture, tmp))
+        fixture.update(run_small_scripts(fixture, tmp))
     fixture["scenarios"] = np.array(names)
     np.savez_compressed(os.path.join(HERE, "reference_run.npz"), **fixture)
     print("written", os.path.join(HERE, "reference_run.npz"))

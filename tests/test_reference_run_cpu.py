@@ -220,3 +220,177 @@ def test_vcf_oracle_equals_the_reference_run(tag, show_ref, qual):
     got = [CO.vcf_line(x[j], pos[j], p[j, 0:4], p[j, 4:6], p[j, 6:10], p[j, 10:16], show_ref, qual) for j in range(len(x))]
     want = [l for l in str(G["callvar/vcf_" + tag]).split("\n") if l and not l.startswith("#")]
     assert [g for g in got if g is not None] == want
+
+
+# ---------------------------------------------------------------- train.py's TrainAll with a stub model ------------------
+class _StubTrainer(object):
+    """same stand-in as tests/golden/make_golden_reference_run.py StubTrainer"""
+
+    def __init__(self):
+        self.calls, self.epoch, self.lr, self.l2 = [], 1, None, None
+
+    @staticmethod
+    def _cs(X, Y=None):
+        return round(float(np.asarray(X, np.float64).sum()) + (float(np.asarray(Y, np.float64).sum()) if Y is not None else 0.0), 3)
+
+    def _val(self, n):
+        return n * (1.0 + (0.25 if self.epoch % 2 else -0.25) + 0.001 * self.epoch)
+
+    def trainNoRT(self, X, Y):
+        self.calls.append(("trainNoRT", len(X), self._cs(X, Y)))
+        self.trainLossRTVal, self.trainSummaryRTVal = float(np.abs(np.asarray(X, np.float64)).sum()) * 1e-3 / self.epoch, None
+
+    def getLossNoRT(self, X, Y):
+        self.calls.append(("getLossNoRT", len(X), self._cs(X, Y)))
+        self.getLossLossRTVal = self._val(len(X))
+
+    def getLoss(self, X, Y):
+        self.calls.append(("getLoss", len(X), self._cs(X, Y)))
+        return self._val(len(X))
+
+    def setLearningRate(self, v=None):
+        self.lr = self.lr * 0.1 if v is None else v
+        self.calls.append(("setLearningRate", v, self.lr))
+        return self.lr
+
+    def setL2RegularizationLambda(self, v=None):
+        self.l2 = self.l2 * 0.1 if v is None else v
+        self.calls.append(("setL2RegularizationLambda", v, self.l2))
+        return self.l2
+
+    def saveParameters(self, path):
+        self.calls.append(("saveParameters", os.path.basename(path)))
+        self.epoch += 1
+
+    def restoreParameters(self, path):
+        self.calls.append(("restoreParameters", os.path.basename(path)))
+        self.epoch = int(path[-6:])
+
+    def predict(self, X):
+        self.calls.append(("predict", len(X), self._cs(X)))
+        f = np.asarray(X, np.float32).reshape(len(X), -1)
+        return f[:, 256:260], f[:, 260:262], f[:, 262:266], f[:, 266:272]
+
+
+DRIVERS = [   # as in tests/golden/make_golden_reference_run.py
+    ("train", "TrainAll", dict(trainBatchSize=200, predictBatchSize=50), {}),
+    ("trainNonstop", "TrainAll", dict(trainBatchSize=200, predictBatchSize=50, maxEpoch=5), {}),
+    ("trainWithoutValidationNonstop", "TrainAll", dict(trainBatchSize=150, predictBatchSize=50, maxEpoch=4), {}),
+    ("evaluate", "Test", dict(predictBatchSize=70), {}),
+    ("calTrainDevDiff", "CalcAll", dict(predictBatchSize=60), dict(chkpnt_fn=["model-000003", "model-000008"])),
+]
+
+
+@pytest.mark.parametrize("name,entry,overrides,extra", DRIVERS, ids=[d[0] for d in DRIVERS])
+def test_driver_equals_the_reference_run(tmp_path, monkeypatch, capsys, name, entry, overrides, extra):
+    """batch booking, validation split, learning-rate switches, checkpoint names, final evaluation: the same model calls in the
+    same order on the same rows, and the same log lines, as the reference's own driver produced with this stub model"""
+    import importlib
+    import logging
+    import pickle
+    import types
+    mod = importlib.import_module("clairvoyante_b200." + name)
+    X = G["feed/train_nobed_x"].astype(np.float32)
+    Y = G["feed/train_nobed_y"]
+    pos = G["feed/train_nobed_pos"].astype("S")
+    total = int(G["feed/train_nobed_total"])
+    bs = P.bloscBlockSize
+    bin_fn = str(tmp_path / "train.bin")
+    with open(bin_fn, "wb") as fh:
+        for obj in (total, [U.pack_array(X[i:i + bs]) for i in range(0, total, bs)], [U.pack_array(Y[i:i + bs]) for i in range(0, total, bs)],
+                    [U.pack_array(pos[i:i + bs]) for i in range(0, total, bs)]):
+            pickle.dump(obj, fh)
+    for k, v in overrides.items():
+        monkeypatch.setattr(P, k, v)
+    msgs = []
+
+    class Collect(logging.Handler):
+        def emit(self, record):
+            msgs.append(record.getMessage())
+
+    h = Collect()
+    logging.getLogger().addHandler(h)
+    old_level = logging.getLogger().level
+    logging.getLogger().setLevel(logging.INFO)
+    try:
+        m = _StubTrainer()
+        kw = dict(bin_fn=bin_fn, tensor_fn=None, var_fn=None, bed_fn=None, chkpnt_fn=None, learning_rate=1e-3, lambd=1e-3,
+                  ochk_prefix=str(tmp_path / "model"), olog_dir=None, v2=False, v3=True, slim=False)
+        kw.update(extra)
+        capsys.readouterr()
+        getattr(mod, entry)(types.SimpleNamespace(**kw), m, U)
+        err = capsys.readouterr().err
+    finally:
+        logging.getLogger().removeHandler(h)
+        logging.getLogger().setLevel(old_level)
+    assert [repr(c) for c in m.calls] == [str(c) for c in G[name + "/calls"]]
+    got = [x for x in msgs if "time elapsed" not in x] + [l for l in err.split("\n") if l and l not in msgs]
+    assert got == [str(x) for x in G[name + "/log"]]
+
+
+# ---------------------------------------------------------------- GetTruth, PairWithNonVariants, callVarBamParallel --------
+@pytest.mark.parametrize("tag,extra", [("all", []), ("region", ["--ctgStart", "400", "--ctgEnd", "1500"])])
+def test_gettruth_equals_the_reference_run(tmp_path, tag, extra):
+    vfn = str(tmp_path / "truth.vcf")
+    open(vfn, "w").write(str(G["gettruth/vcf"]))
+    r = subprocess.run([sys.executable, "-m", "clairvoyante_b200.GetTruth", "--vcf_fn", vfn, "--ctgName", "ctg"] + extra, cwd=ROOT,
+                       capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    want = str(G["gettruth/" + tag])
+    assert want.count("\n") > 20 and r.stdout.decode() == want
+
+
+@pytest.mark.parametrize("tag,amp", [("nobed", 2), ("bed", 1)])
+def test_pairwithnonvariants_equals_the_reference_run(tmp_path, tag, amp):
+    import gzip
+    import random
+    import types
+    from clairvoyante_b200 import PairWithNonVariants as PW
+    lines = [l for l in G["feed/tensor_text"].tobytes().decode().split("\n") if l]
+    tv, tc, bed, outfn = (str(tmp_path / n) for n in ("tensor_var", "tensor_can", "pair.bed", "tensor_pair"))
+    open(tv, "w").write("".join(l + "\n" for l in lines[:int(G["pair/n_var"])]))
+    open(tc, "w").write("".join(l + "\n" for l in lines[int(G["pair/n_can_from"]):]))
+    open(bed, "w").write("ctg\t0\t1200\nctg\t1500\t700000\n")
+    random.seed(12345)                       # the generator seeded the reference's (otherwise unseeded) sampler the same way
+    PW.Pair(types.SimpleNamespace(tensor_can_fn=tc, tensor_var_fn=tv, bed_fn=bed if tag == "bed" else None, output_fn=outfn, amp=amp,
+                                  seed=None))
+    got = gzip.open(outfn, "rt").read()
+    assert [" ".join(l.split()[:2]) for l in got.split("\n") if l] == [str(p) for p in G["pair/%s_positions" % tag]]
+    assert hashlib.sha256(got.encode()).hexdigest() == str(G["pair/%s_sha256" % tag])
+
+
+def _options(cmd):
+    tok, o, i = cmd.split(), {}, 0
+    while i < len(tok):
+        if tok[i].startswith("--"):
+            if i + 1 < len(tok) and not tok[i + 1].startswith("--"):
+                o[tok[i]] = tok[i + 1]
+                i += 2
+                continue
+            o[tok[i]] = True
+        i += 1
+    return o
+
+
+@pytest.mark.parametrize("tag", ["default", "bed_qual", "allcontigs"])
+def test_callvarbamparallel_chunks_equal_the_reference_run(tmp_path, tag):
+    tmp = str(tmp_path)
+    fa = os.path.join(tmp, "genome.fa")
+    for fn in (fa, os.path.join(tmp, "aln.bam"), os.path.join(tmp, "model.meta"), os.path.join(tmp, "model.index")):
+        open(fn, "w").write("x\n")
+    open(fa + ".fai", "w").write("chr1\t25000000\t6\t60\t61\nchr2\t10000001\t7\t60\t61\nchrUn_x\t5000\t8\t60\t61\n21\t9999999\t9\t60\t61\n")
+    open(os.path.join(tmp, "chunks.bed"), "w").write("chr1\t10000000\t10000001\nchr1\t19999999\t20000500\n21\t5\t500\n")
+    extra = [str(a).replace("TMP", tmp) for a in G["parallel/%s_args" % tag]]
+    extra = [os.path.join(tmp, "chunks.bed") if a.endswith("chunks.bed") else a for a in extra]
+    r = subprocess.run([sys.executable, "-m", "clairvoyante_b200.callVarBamParallel", "--chkpnt_fn", os.path.join(tmp, "model"), "--ref_fn", fa,
+                        "--bam_fn", os.path.join(tmp, "aln.bam"), "--pypy", "python", "--samtools", "python", "--output_prefix", "out/calls"]
+                       + extra, cwd=ROOT, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    got = [_options(c.replace(tmp, "TMP")) for c in r.stdout.decode().split("\n") if c]
+    want = [_options(c) for c in str(G["parallel/" + tag]).split("\n") if c]
+    assert len(got) == len(want) and len(want) >= 4
+    same = ["--chkpnt_fn", "--ref_fn", "--bam_fn", "--bed_fn", "--ctgName", "--ctgStart", "--ctgEnd", "--call_fn", "--sampleName", "--qual",
+            "--considerleftedge"]
+    for g, w in zip(got, want):
+        assert [g.get(k) for k in same] == [w.get(k) for k in same]
+        assert float(g["--threshold"]) == float(w["--threshold"]) and float(g["--minCoverage"]) == float(w["--minCoverage"])
