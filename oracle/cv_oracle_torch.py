@@ -82,7 +82,7 @@ def loss_and_grads(weights, x, y, variant="v3", l2_lambda=0.0, dtype=torch.float
         fw = dict(fw, drop4_mask=torch.tensor(fw["drop4_mask"], dtype=dtype))
     l = loss(W, xt, yt, variant, l2_lambda, **fw)
     l.backward()
-    return float(l), {k: v.grad.numpy() for k, v in W.items()}
+    return float(l.detach()), {k: v.grad.numpy() for k, v in W.items()}
 
 
 def tf_adam_step(var, grad, m, v, t, lr, beta1=0.9, beta2=0.999, eps=1e-8):
