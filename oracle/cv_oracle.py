@@ -14,7 +14,14 @@ oracle is (a) the activation/parameter shapes recorded in
 jupyter_nb/visualization.ipynb:112-121,475-739 (checked in
 tests/test_oracle.py), (b) a second, independent restatement on torch-CPU
 (cv_oracle_torch.py: F.conv2d / F.max_pool2d in NCHW) that must agree with
-this one, and (c) hand-computed padding cases for TF `SAME` semantics.
+this one, (c) hand-computed padding cases for TF `SAME` semantics, and (d) the
+reference's OWN graph code -- clairvoyante_v3.py, clairvoyante_v3_slim.py,
+selu.py, unmodified -- executed at fixture-generation time on a stand-in for the
+TensorFlow-1.x API (tests/golden/tf1_stand_in.py, op kernels on torch float64):
+tests/golden/reference_graph.npz holds its predict / getLoss / train results and
+tests/test_reference_graph_cpu.py requires this oracle to reproduce them to
+rounding.  (d) ties the wiring, formulas and feeds to the reference's source;
+TensorFlow's own kernels remain restated, hence still "unpinned" for those.
 
 Reference anchors (all paths relative to /root/reference):
   graph v3      clairvoyante/clairvoyante_v3.py:54-138

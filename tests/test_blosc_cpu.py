@@ -203,3 +203,74 @@ def test_pack_array_blosc_is_what_the_reference_writes(tmp_path):
     assert total == 500 and np.array_equal(U.unpack_array(xb[0]), x) and np.array_equal(U.unpack_array(pb[0]), pos)
     X, n, end = U.DecompressArray(xb, 0, 500, 500)
     assert n == 500 and end == 1 and np.array_equal(X, x)
+
+
+# ---- the LZ4 layer against the real liblz4 (through pyarrow's "lz4_raw" codec = LZ4_compress_default / LZ4_decompress_safe) ----
+def _liblz4():
+    pa = pytest.importorskip("pyarrow")
+    if not pa.Codec.is_available("lz4_raw"):
+        pytest.skip("pyarrow built without lz4")
+    return pa.Codec("lz4_raw")
+
+
+def _streams(frame):
+    """(uncompressed size, payload) of every split stream of a codec-1 frame, by the container rules of blosc_frame.cpp"""
+    flags, typesize = frame[2], frame[3]
+    nbytes, blocksize, _ = struct.unpack("<III", frame[4:16])
+    if flags & 0x02 or nbytes == 0:
+        return
+    nblocks = (nbytes + blocksize - 1) // blocksize
+    for b in range(nblocks):
+        bsize = nbytes % blocksize if (b == nblocks - 1 and nbytes % blocksize) else blocksize
+        leftover = bsize != blocksize
+        nsplits = typesize if (not (flags & 0x10) and typesize <= 16 and blocksize // typesize >= 128 and not leftover) else 1
+        off = struct.unpack("<i", frame[16 + 4 * b:20 + 4 * b])[0]
+        for _ in range(nsplits):
+            c = struct.unpack("<i", frame[off:off + 4])[0]
+            yield b, bsize // nsplits, frame[off + 4:off + 4 + c]
+            off += 4 + c
+
+
+def _payloads():
+    rng = np.random.default_rng(7)
+    x = synth.make_sites(600, 3)
+    return [x.tobytes(), BW.py2_pickle_ndarray(x[:500]), np.repeat(rng.standard_normal(2000), 37).astype(np.float64).tobytes(),
+            (b"ACGT" * 70000) + b"xyz", rng.integers(0, 3, 300000, dtype=np.uint8).tobytes(), bytes(100000),
+            np.arange(50000, dtype=np.int32).tobytes()]
+
+
+def test_decoder_reads_streams_written_by_the_real_liblz4(monkeypatch):
+    """frames assembled by the test-side container writer around streams compressed by liblz4 itself -- what python-blosc
+    (codec lz4 / lz4hc: both emit the LZ4 block format) puts into the reference's .bin"""
+    codec = _liblz4()
+    monkeypatch.setattr(BW, "lz4_compress", lambda part: codec.compress(bytes(part), asbytes=True) if len(part) else b"\x00")
+    for data in _payloads():
+        for typesize, shuffle in ((4, True), (4, False), (8, True), (1, False)):
+            frame = BW.blosc_compress(data, typesize, 256 * 1024 - (256 * 1024) % typesize, do_shuffle=shuffle)
+            assert _decompress(frame) == data
+
+
+def test_real_liblz4_decodes_the_streams_of_the_native_encoder():
+    """every LZ4 stream cvb_blosc_compress writes is a valid LZ4 block for LZ4_decompress_safe and yields the (shuffled) bytes
+    the container says it holds -- i.e. python-blosc in the reference's interpreter can read a `tensor2Bin --blosc` file"""
+    codec = _liblz4()
+    checked = 0
+    for data in _payloads():
+        for typesize, shuffle in ((4, 1), (4, 0), (8, 1), (1, 0)):
+            frame = _native_compress(data, typesize, shuffle)
+            blocks = {}
+            for b, size, payload in _streams(frame):
+                raw = payload if len(payload) == size else codec.decompress(payload, decompressed_size=size, asbytes=True)
+                assert len(raw) == size
+                blocks[b] = blocks.get(b, b"") + raw
+                checked += len(payload) != size
+            if blocks:
+                out = b""
+                for b in sorted(blocks):
+                    blk = blocks[b]
+                    if frame[2] & 0x01 and typesize > 1:       # undo the byte shuffle of this block
+                        ne = len(blk) // typesize
+                        blk = np.frombuffer(blk[:ne * typesize], np.uint8).reshape(typesize, ne).T.copy().tobytes() + blk[ne * typesize:]
+                    out += blk
+                assert out == data
+    assert checked > 50
