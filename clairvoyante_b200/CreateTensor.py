@@ -15,7 +15,6 @@ yields exactly what utils_v2.GetTensor yields for the rows this module would hav
 import argparse
 import ctypes
 import gzip
-import re
 import shlex
 import shutil
 import subprocess
@@ -231,49 +230,31 @@ def _load_candidates(args):
     return out
 
 
-_CIGAR_OP = re.compile(rb"(\d+)([MIDNSHP=X])")
-
-
 class _SamTextView(object):
     """What `samtools view -F 2308 <file> ctg[:start-end]` (reference CreateTensor.py:134-136) prints, for a SAM TEXT file:
     header lines are dropped, records of other contigs, unmapped / secondary / supplementary records (flag & 2308) and
-    records that do not overlap the 1-based inclusive region are skipped.  File-like: read() hands out filtered chunks."""
+    records that do not overlap the 1-based inclusive region are skipped (native: cvb_sam_view, csrc/sam_view.cpp).
+    File-like: read() hands out filtered chunks."""
 
     def __init__(self, fh, ctgName, start=None, end=None):
-        self.fh, self.ctg, self.start, self.end, self.carry = fh, ctgName.encode(), start, end, b""
-
-    def _keep(self, line):
-        if line[:1] == b"@":
-            return False
-        f = line.split(b"\t", 6)
-        if len(f) < 6:
-            return bool(line.strip())                  # malformed: let the native stage count it
-        try:
-            if int(f[1]) & 2308 or f[2] != self.ctg:
-                return False
-            if self.start is None:
-                return True
-            lo = int(f[3])
-        except ValueError:
-            return True
-        if lo > self.end:
-            return False
-        if lo >= self.start:
-            return True
-        span = sum(int(n) for n, op in _CIGAR_OP.findall(f[5]) if op in b"MDN=X")
-        return lo + max(span, 1) - 1 >= self.start
+        self.fh, self.ctg, self.carry = fh, ctgName.encode(), b""
+        self.start, self.end = (-1, -1) if start is None or end is None else (int(start), int(end))
+        self.lib = _lib.load()
 
     def read(self, size=8 << 20):
         while True:
             b = self.fh.read(size)
-            if not b:
-                last, self.carry = self.carry, b""
-                return last if last and self._keep(last) else b""
-            lines = (self.carry + b).split(b"\n")
-            self.carry = lines.pop()
-            out = [ln for ln in lines if self._keep(ln)]
-            if out:
-                return b"\n".join(out) + b"\n"
+            final = not b
+            data = self.carry + b if self.carry else b
+            if final and not data:
+                return b""
+            out = np.empty(len(data) + 1, np.uint8)             # (no zero fill, unlike ctypes.create_string_buffer)
+            n, used = ctypes.c_int64(), ctypes.c_int64()
+            _lib.check(self.lib.cvb_sam_view(data, len(data), 1 if final else 0, self.ctg, 2308, self.start, self.end,
+                                             out.ctypes.data, ctypes.byref(n), ctypes.byref(used)))
+            self.carry = data[used.value:]
+            if n.value or final:
+                return out[:n.value].tobytes()
 
     def close(self):
         self.fh.close()

@@ -197,6 +197,14 @@ int cvb_candidates_take(cvb_candidates* c, char* text, int64_t text_cap, int64_t
                         int64_t* n_pos);
 int cvb_candidates_stats(const cvb_candidates* c, int64_t stats[4]);
 
+/* `samtools view -F <flag_mask> <file> ctg[:start-end]` for SAM TEXT (CreateTensor.py:134-136, ExtractVariantCandidates.py:
+ * 107-109 run it with -F 2308): copies the complete lines of in[0, len) that samtools would print to out (capacity len + 1)
+ * -- header lines, other contigs, records with flag & flag_mask and records that do not overlap the 1-based inclusive region
+ * [start, end] are dropped; start < 0 = no region.  A trailing line without '\n' is processed only if final_chunk != 0;
+ * *consumed = bytes of `in` that were processed (feed the rest again with the next chunk).  Host code. */
+int cvb_sam_view(const char* in, int64_t len, int final_chunk, const char* ctg_name, int flag_mask, int64_t start, int64_t end,
+                 char* out, int64_t* out_len, int64_t* consumed);
+
 /* pinned host memory helpers for the batch feed (utils_v2.GetTensor replacement) */
 int cvb_alloc_pinned(int64_t bytes, void** out);
 int cvb_free_pinned(void* p);

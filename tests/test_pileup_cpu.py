@@ -178,3 +178,53 @@ def test_golden_alignment_fixture():
     centers, x, _ = run_native(sam, ref, pos)
     assert np.array_equal(centers, g["centers"]) and np.array_equal(x, g["tensors"].astype(np.float32))
     assert [w[0] for w in want] == g["centers"].tolist() and all(np.array_equal(w[1], x[i]) for i, w in enumerate(want))
+
+
+def test_sam_text_view_equals_samtools_view_semantics():
+    """cvb_sam_view (what the command lines apply to .sam text instead of `samtools view -F 2308 file ctg:start-end`):
+    header / contig / flag / region-overlap filter, any chunking, against a line-by-line Python statement of the rule"""
+    import io
+    import re
+    rng = np.random.default_rng(11)
+    ref, sam, _ = synth_alignments(rng, ref_len=3000, n_reads=500)
+    rows = sam.split("\n")[:-1]
+    out = []
+    for i, r in enumerate(rows):
+        f = r.split("\t")
+        if not r.startswith("@"):
+            f[1] = str([0, 16, 4, 256, 2048, 1024, 83, 2064][i % 8])
+            if i % 17 == 0:
+                f[2] = "ctg2"
+        out.append("\t".join(f))
+    out.insert(40, "")
+    out.insert(90, "short\trow")
+    text = "\n".join(out)                                   # (no trailing newline: the last record must still come through)
+
+    def want(a, b):
+        keep = []
+        for line in text.split("\n"):
+            if line.startswith("@") or not line.strip():
+                continue
+            f = line.split("\t")
+            if len(f) < 6:
+                keep.append(line)
+                continue
+            if int(f[1]) & 2308 or f[2] != "ctg":
+                continue
+            lo = int(f[3])
+            hi = lo + max(sum(int(k) for k, op in re.findall(r"(\d+)([MIDNSHP=X])", f[5]) if op in "MDN=X"), 1) - 1
+            if a is not None and (hi < a or lo > b):
+                continue
+            keep.append(line)
+        return "".join(k + "\n" for k in keep).encode()
+
+    for a, b in ((None, None), (1, 3000), (700, 1500), (2990, 5000), (5000, 6000)):
+        for size in (1 << 20, 977, 64):
+            v = CT._SamTextView(io.BytesIO(text.encode()), "ctg", a, b)
+            got = b""
+            while True:
+                c = v.read(size)
+                if not c:
+                    break
+                got += c
+            assert got == want(a, b), (a, b, size)

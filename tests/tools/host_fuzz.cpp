@@ -217,6 +217,30 @@ void fuzz_alignments() {
   const bool intact = rnd_below(3) == 0;
   if (!intact) mutate(v);
 
+  {  // samtools-view filter on text: chunked, exact-size buffers, with and without a region
+    const bool region = rnd_below(2);
+    const int64_t a = region ? rnd_below(ref_len) : -1, b = region ? a + rnd_below(600) : -1;
+    std::vector<uint8_t> pending;
+    int64_t off = 0, kept = 0;
+    const int64_t n = (int64_t)v.size();
+    while (off < n || !pending.empty()) {
+      int64_t len = 1 + rnd_below(rnd_below(3) ? 3000 : 50);
+      if (len > n - off) len = n - off;
+      pending.insert(pending.end(), v.begin() + off, v.begin() + off + len);
+      off += len;
+      const int fin = off >= n;
+      std::vector<uint8_t> in(pending);  // exact-size heap copies
+      std::vector<char> out(in.size() + 1);
+      int64_t on = -1, used = -1;
+      if (cvb_sam_view((const char*)in.data(), (int64_t)in.size(), fin, "ctg", 2308, a, b, out.data(), &on, &used)) die("sam_view failed");
+      if (on < 0 || on > (int64_t)in.size() + 1 || used < 0 || used > (int64_t)in.size()) die("sam_view: counts outside their ranges");
+      if (fin && used != (int64_t)in.size()) die("sam_view left input behind on the final chunk");
+      kept += on;
+      pending.erase(pending.begin(), pending.begin() + used);
+      if (fin) break;
+    }
+    if (kept > n + 1) die("sam_view produced more than it was given");
+  }
   {  // candidates
     std::vector<int64_t> bb, be;
     if (rnd_below(2)) {
