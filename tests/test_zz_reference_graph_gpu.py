@@ -34,6 +34,8 @@ def test_predict_getloss_and_first_train_loss(tag, variant):
     assert np.abs(out - G[tag + "/predict"]).max() <= 2e-4
     want = float(G[tag + "/getloss"])
     assert abs(float(m.getLoss(X, Y)) - want) <= 2e-5 * abs(want) + 1e-3
+    m.init(seed=1)                                     # (Adam slots and step zeroed, as in tests/test_train_gpu.py)
+    m.setWeights(I.init_weights(variant, seed=0))
     loss, _ = m.train(X, Y)
     want = float(G[tag + "/train_losses"][0])
     assert abs(float(loss) - want) <= 3e-5 * abs(want) + 1e-3
