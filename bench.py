@@ -301,6 +301,7 @@ def main():
         kern[k]["pipe"] = "tcgen05 (3x split-fp16)" if (tensor and k in tc_kernels) else "fp32 SIMT"
     roofline = dict(kernel=dom, bound=r_bound, achieved=kern[dom]["tflops"], peak=r_peak, unit="TFLOP/s",
                     frac=kern[dom]["tflops"] / r_peak, peak_source=r_src,
+                    issued_frac=(3.0 if on_tensor else 1.0) * kern[dom]["tflops"] / r_peak,   # tensor-pipe occupancy: MMAs issued / peak
                     algorithmic_flops_per_launch=fl[dom] * sites_per_launch, ms_per_launch=kern[dom]["ms_per_launch"],
                     traffic=traffic, kernels=kern,
                     whole_pass=dict(tflops=value / world * fl["total"] / 1e12, frac_fp32_nominal=value / world * fl["total"] / 1e12 / FP32_NOMINAL_TFLOPS),
