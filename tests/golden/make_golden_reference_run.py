@@ -591,6 +591,58 @@ def run_small_scripts(fx, tmp):
     return out
 
 
+# ------------------------------------------------------------------------------- the whole calling pipeline (callVarBam.py)
+PIPELINES = [   # (tag, scenario, callVarBam options)
+    ("plain", "defaults", {}),
+    ("region_bed_qual", "region_bed_filters", dict(ctgStart=150, ctgEnd=1900, bed=True, threshold=0.1, minCoverage=6, qual=30, dcov=5)),
+    ("vcf_sites", "defaults", dict(vcf=True, ctgStart=300, ctgEnd=1400)),
+]
+
+
+def run_pipelines(fx, tmp, evc, ct):
+    """ExtractVariantCandidates | CreateTensor | callVar exactly as callVarBam.py:113-131 chains them (same per-stage options),
+    each stage the reference's own code, the model a probability table"""
+    out = {}
+    utils = load_reference("utils_v2", ref_dir=CV_DIR)
+    cv = load_reference("callVar", ref_dir=CV_DIR)
+    cv.param.predictBatchSize = 100
+    gt = load_reference("GetTruth")
+    table = probability_table(4000, 17)
+    out["pipeline/probabilities"] = table
+    vfn = os.path.join(tmp, "sites.vcf")
+    open(vfn, "w").write(str(fx["gettruth/vcf"]))
+    for tag, sc, o in PIPELINES:
+        fa, samfn, bedfn = (os.path.join(tmp, "pl_" + tag + e) for e in (".fa", ".sam", ".bed"))
+        ref = str(fx[sc + "/ref"])
+        open(fa, "w").write(">ctg\n" + "".join(ref[i:i + 70] + "\n" for i in range(0, len(ref), 70)))
+        open(fa + ".fai", "w").write("ctg\t%d\t5\t70\t71\n" % len(ref))
+        open(samfn, "w").write(str(fx[sc + "/sam"]))
+        rng_args = ["--ctgStart", str(o["ctgStart"]), "--ctgEnd", str(o["ctgEnd"])] if "ctgStart" in o else []
+        if o.get("vcf"):
+            cand = run_main(gt, ["--vcf_fn", vfn, "--ctgName", "ctg"] + rng_args)
+        else:
+            argv = ["--bam_fn", samfn, "--ref_fn", fa]
+            if o.get("bed"):
+                open(bedfn, "w").write(str(fx[sc + "/bed"]))
+                argv += ["--bed_fn", bedfn]
+            argv += ["--ctgName", "ctg"] + rng_args + ["--threshold", str(o.get("threshold", 0.125)), "--minCoverage", str(o.get("minCoverage", 4)),
+                                                         "--samtools", "samtools"]
+            cand = run_main(evc, argv)
+        tens = run_main(ct, ["--bam_fn", samfn, "--ref_fn", fa, "--ctgName", "ctg"] + rng_args + ["--considerleftedge", "--samtools", "samtools",
+                             "--dcov", str(o.get("dcov", 250))], stdin_text=cand)
+        tfn, vcf_out = os.path.join(tmp, "pl_" + tag + ".tensors"), os.path.join(tmp, "pl_" + tag + ".vcf")
+        open(tfn, "w").write(tens)
+        args = types.SimpleNamespace(v2=False, v3=True, slim=False, tensor_fn=tfn, call_fn=vcf_out, sampleName="SAMPLE", threads=None,
+                                     qual=o.get("qual"), showRef=False, ref_fn=fa)
+        cv.Test(args, StubModel(table[:sum(1 for l in tens.split("\n") if l and l.split()[2][16].upper() in "ACGT")]), utils)
+        import gc
+        gc.collect()
+        out["pipeline/%s_vcf" % tag] = np.array(open(vcf_out).read())
+        print("pipeline %-16s %4d candidates, %4d tensors, %4d VCF records" % (
+            tag, cand.count("\n"), tens.count("\n"), sum(1 for l in open(vcf_out) if not l.startswith("#"))))
+    return out
+
+
 def main():
     order27 = py27_dict_order(["A", "C", "G", "T", "I", "D", "N"])
     print("CPython 2.7 iteration order of the counter literal:", " ".join(order27))
@@ -636,6 +688,7 @@ def main():
         fixture.update(feed_and_callvar("".join(all_tensor_text), tmp))
         fixture.update(run_drivers(fixture, tmp))
         fixture.update(run_small_scripts(fixture, tmp))
+        fixture.update(run_pipelines(fixture, tmp, evc27, ct))
     fixture["scenarios"] = np.array(names)
     np.savez_compressed(os.path.join(HERE, "reference_run.npz"), **fixture)
     print("written", os.path.join(HERE, "reference_run.npz"))

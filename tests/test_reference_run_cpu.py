@@ -394,3 +394,37 @@ def test_callvarbamparallel_chunks_equal_the_reference_run(tmp_path, tag):
     for g, w in zip(got, want):
         assert [g.get(k) for k in same] == [w.get(k) for k in same]
         assert float(g["--threshold"]) == float(w["--threshold"]) and float(g["--minCoverage"]) == float(w["--minCoverage"])
+
+
+# ---------------------------------------------------------------- the whole calling pipeline --------------------------------
+PIPELINES = [   # as in tests/golden/make_golden_reference_run.py
+    ("plain", "defaults", {}),
+    ("region_bed_qual", "region_bed_filters", dict(ctgStart=150, ctgEnd=1900, bed=True, threshold=0.1, minCoverage=6, qual=30, dcov=5)),
+    ("vcf_sites", "defaults", dict(vcf=True, ctgStart=300, ctgEnd=1400)),
+]
+
+
+@pytest.mark.parametrize("tag,sc,o", PIPELINES, ids=[p[0] for p in PIPELINES])
+def test_callvarbam_equals_the_reference_pipeline(tmp_path, monkeypatch, tag, sc, o):
+    """alignments -> VCF in one process (native candidates, native pile-up, callVar.Test) against the VCF that the reference's
+    three stages, chained with the options callVarBam.py:113-131 gives them, wrote with the same probability table as model"""
+    import types
+    from clairvoyante_b200 import callVarBam as CB
+    fa, samfn, bedfn, vfn, out = (str(tmp_path / n) for n in ("ref.fa", "aln.sam", "conf.bed", "sites.vcf", "calls.vcf"))
+    ref = str(G[sc + "/ref"])
+    open(fa, "w").write(">ctg\n" + "".join(ref[i:i + 70] + "\n" for i in range(0, len(ref), 70)))
+    open(fa + ".fai", "w").write("ctg\t%d\t5\t70\t71\n" % len(ref))
+    open(samfn, "w").write(str(G[sc + "/sam"]))
+    if o.get("bed"):
+        open(bedfn, "w").write(str(G[sc + "/bed"]))
+    if o.get("vcf"):
+        open(vfn, "w").write(str(G["gettruth/vcf"]))
+    monkeypatch.setattr(P, "predictBatchSize", 100)
+    args = types.SimpleNamespace(chkpnt_fn=None, ref_fn=fa, bed_fn=bedfn if o.get("bed") else None, bam_fn=samfn, call_fn=out,
+                                 vcf_fn=vfn if o.get("vcf") else None, threshold=o.get("threshold", 0.125),
+                                 minCoverage=o.get("minCoverage", 4), qual=o.get("qual"), sampleName="SAMPLE", ctgName="ctg",
+                                 ctgStart=o.get("ctgStart"), ctgEnd=o.get("ctgEnd"), considerleftedge=True, dcov=o.get("dcov", 250),
+                                 samtools="samtools-is-not-installed", pypy="pypy", v3=True, v2=False, slim=False, threads=None, delay=0)
+    CB.Run(args, model=_TableModel(G["pipeline/probabilities"]))
+    want = str(G["pipeline/%s_vcf" % tag])
+    assert want.count("\n") > 30 and open(out).read() == want
