@@ -168,3 +168,36 @@ extern "C" int cvb_parse_tensor_text(const char* buf, int64_t len, int final_chu
   *kept = k;
   return 0;
 }
+
+// "chrom:pos:SEQ\n" (SEQ upper-cased, utils_v2.py:38,42) for every KEPT line of a cvb_parse_tensor_text result: the position
+// strings GetTensor yields, assembled here because building them row by row in Python was the slowest part of the feed.
+extern "C" int64_t cvb_tensor_text_positions(const char* buf, const int64_t* meta, int64_t lines, char* out, int64_t cap) {
+  if (lines < 0 || (lines > 0 && (!buf || !meta || !out))) {
+    cvb_internal_set_error("cvb_tensor_text_positions: bad argument");
+    return -1;
+  }
+  const LineMeta* M = reinterpret_cast<const LineMeta*>(meta);
+  char* o = out;
+  char* const oe = out + cap;
+  for (int64_t i = 0; i < lines; ++i) {
+    const LineMeta& m = M[i];
+    if (m.status != CVB_LINE_KEPT) continue;
+    if (m.chrom_len + m.pos_len + m.seq_len + 3 > oe - o) {
+      cvb_internal_set_error("cvb_tensor_text_positions: output buffer too small");
+      return -1;
+    }
+    memcpy(o, buf + m.chrom_off, (size_t)m.chrom_len);
+    o += m.chrom_len;
+    *o++ = ':';
+    memcpy(o, buf + m.pos_off, (size_t)m.pos_len);
+    o += m.pos_len;
+    *o++ = ':';
+    const char* s = buf + m.seq_off;
+    for (int64_t k = 0; k < m.seq_len; ++k) {
+      const char ch = s[k];
+      *o++ = (ch >= 'a' && ch <= 'z') ? (char)(ch - 32) : ch;
+    }
+    *o++ = '\n';
+  }
+  return o - out;
+}

@@ -20,6 +20,7 @@ import bisect
 import ctypes
 import gc
 import io
+import os
 import pickle
 import random
 import shlex
@@ -74,6 +75,13 @@ def _open_bytes(fn):
     """binary twin of _open_text for the native parser"""
     if fn == "PIPE":
         return None, sys.stdin.buffer
+    try:                                   # `gzip -fdc` passes a file that is not gzip through unchanged: read it directly
+        with open(fn, "rb") as probe:
+            plain = probe.read(2) != b"\x1f\x8b"
+        if plain and os.path.isfile(fn):
+            return None, open(fn, "rb", buffering=0)
+    except OSError:
+        pass                               # (let gzip report the problem like the reference would)
     proc = subprocess.Popen(shlex.split("gzip -fdc %s" % fn), stdout=subprocess.PIPE, bufsize=1 << 20)
     try:                                   # 1 MB pipe instead of 64 KB: fewer wake-ups per 32 MB read (Linux only)
         import fcntl
@@ -86,10 +94,44 @@ def _open_bytes(fn):
 _READ_BYTES = 32 << 20        # ~12k rows of ~2.7 KB per read
 
 
+def _read_ahead(fb, size):
+    """chunks of `fb` read on a helper thread, one ahead of the consumer (the read releases the GIL, so the next 32 MB arrive
+    while the current ones are parsed); yields b"" for ever once the stream has ended"""
+    import queue
+    import threading
+    q = queue.Queue(maxsize=2)
+
+    def pump():
+        try:
+            while True:
+                b = fb.read(size)
+                q.put(b)
+                if not b:
+                    return
+        except Exception as e:            # surfaced in the consumer
+            q.put(e)
+
+    threading.Thread(target=pump, daemon=True).start()
+    while True:
+        b = q.get()
+        if isinstance(b, Exception):
+            raise b
+        if not b:
+            break
+        yield b
+    while True:
+        yield b""
+
+
+_PARSE_LINES = 16384          # lines handed to the parser per call, whatever the batch size: enough work for every host thread
+
+
 def _native_rows(tensor_fn, num, threads=0):
     """Drives cvb_parse_tensor_text (csrc/text_feed.cpp) over the stream.  Yields (rows, recs) with rows a fresh
     float32 (k, 528) array (k <= num, channel 0 already subtracted, utils_v2.py:46) and recs the k
-    (chrom, pos, SEQ) string triples of those rows.  Every yield but the last has k == num."""
+    "chrom:pos:SEQ" strings of those rows (cvb_tensor_text_positions).  Every yield but the last has k == num.
+    The parser is called on up to _PARSE_LINES lines at a time and the batches are cut from its output, so that a
+    1000-row batch (param.predictBatchSize) does not limit it to 1000 lines of work per call."""
     lib = _lib.load()
     proc, fb = _open_bytes(tensor_fn)
     width = _site_floats()
@@ -97,42 +139,55 @@ def _native_rows(tensor_fn, num, threads=0):
         raise NotImplementedError("the native parser is compiled for (33,4,4) tensors")
     n_lines, n_kept, n_used = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
     buf, off, eof = b"", 0, False
-    rows = np.empty((num, width), dtype=np.float32)
-    meta = np.empty((max(num, 1), 10), dtype=np.int64)
+    chunks = _read_ahead(fb, _READ_BYTES)
+    stage = np.empty((_PARSE_LINES, width), dtype=np.float32)
+    meta = np.empty((_PARSE_LINES, 10), dtype=np.int64)
+    ptxt = np.empty(1, np.uint8)
+    want = num if num > 0 else _PARSE_LINES
+    rows = np.empty((want, width), dtype=np.float32)
     recs, c = [], 0
     while True:
         base = ctypes.cast(ctypes.c_char_p(buf), ctypes.c_void_p).value or 0
-        _lib.check(lib.cvb_parse_tensor_text(base + off, len(buf) - off, 1 if eof else 0, num - c, threads,
-                                             rows[c:].ctypes.data, meta.ctypes.data,
+        _lib.check(lib.cvb_parse_tensor_text(base + off, len(buf) - off, 1 if eof else 0, _PARSE_LINES, threads,
+                                             stage.ctypes.data, meta.ctypes.data,
                                              ctypes.byref(n_lines), ctypes.byref(n_kept), ctypes.byref(n_used)))
-        nl = n_lines.value
+        nl, k = n_lines.value, n_kept.value
         if nl:
-            st = meta[:nl, 0]
-            for i in np.nonzero(st == 2)[0]:            # CVB_LINE_MALFORMED (reference message, utils_v2.py:35)
+            for i in np.nonzero(meta[:nl, 0] == 2)[0]:   # CVB_LINE_MALFORMED (reference message, utils_v2.py:35)
                 a, l = int(meta[i, 1]) + off, int(meta[i, 2])
                 print("UnpackATensorRecord Failure", buf[a:a + l].decode("ascii", "replace"), file=sys.stderr)
-            for i in np.nonzero(st == 0)[0]:            # CVB_LINE_KEPT
-                m = meta[i]
-                recs.append((buf[off + m[3]:off + m[3] + m[4]].decode("ascii", "replace"),
-                             buf[off + m[5]:off + m[5] + m[6]].decode("ascii", "replace"),
-                             buf[off + m[7]:off + m[7] + m[8]].decode("ascii", "replace").upper()))
-            c += n_kept.value
+            if k:                                        # "chrom:pos:SEQ" of the kept rows, assembled natively
+                if len(ptxt) < n_used.value + 16:
+                    ptxt = np.empty(n_used.value + 16, np.uint8)
+                pn = lib.cvb_tensor_text_positions(base + off, meta.ctypes.data, nl, ptxt.ctypes.data, len(ptxt))
+                if pn < 0:
+                    _lib.check(1)
+                names = ptxt[:pn].tobytes().decode("ascii", "replace").split("\n")
+                s0 = 0
+                while s0 < k:                            # cut the batches out of this parse
+                    if num <= 0 and c == len(rows):      # (num <= 0: one batch with everything)
+                        rows = np.concatenate([rows, np.empty_like(rows)])
+                    take = min(len(rows) - c, k - s0)
+                    rows[c:c + take] = stage[s0:s0 + take]
+                    recs += names[s0:s0 + take]
+                    c += take
+                    s0 += take
+                    if num > 0 and c == num:
+                        yield rows, recs
+                        rows = np.empty((num, width), dtype=np.float32)   # fresh storage: the consumer still holds the batch
+                        recs, c = [], 0
             off += n_used.value
-        if c == num and num > 0:
-            yield rows, recs
-            rows = np.empty((num, width), dtype=np.float32)   # fresh storage: the consumer still holds the batch
-            recs, c = [], 0
-            continue
         if nl == 0 or off >= len(buf):
             if eof:
                 break
-            chunk = fb.read(_READ_BYTES)
+            chunk = next(chunks)
             if chunk:
                 buf, off = buf[off:] + chunk, 0
             else:
                 eof = True                               # one more pass: a last line without '\n'
-    if proc is not None:
+    if fb is not sys.stdin.buffer:
         fb.close()
+    if proc is not None:
         proc.wait()
     yield rows[:c], recs
 
@@ -150,12 +205,12 @@ def GetTensor(tensor_fn, num, threads=0):
         rows, recs = prev
         total += len(recs)
         print("Processed %d tensors" % total, file=sys.stderr)
-        yield 0, len(recs), rows.reshape(-1, h, 4, param.matrixNum), [":".join(r) for r in recs]
+        yield 0, len(recs), rows.reshape(-1, h, 4, param.matrixNum), recs
         prev = cur
     rows, recs = prev
     total += len(recs)
     print("Processed %d tensors" % total, file=sys.stderr)
-    yield 1, len(recs), rows.reshape(-1, h, 4, param.matrixNum), [":".join(r) for r in recs]
+    yield 1, len(recs), rows.reshape(-1, h, 4, param.matrixNum), recs
 
 
 # ------------------------------------------------------------------------------------------------
@@ -482,7 +537,8 @@ def GetTrainingArray(tensor_fn, var_fn, bed_fn, shuffle=True, container="cvbz"):
     h, centre = 2 * param.flankingBaseNum + 1, param.flankingBaseNum
     total = 0
     for rows, recs in _native_rows(tensor_fn, 4096):
-        for r, (chrom, coord, seq) in zip(rows.reshape(-1, h, 4, param.matrixNum), recs):
+        for r, rec in zip(rows.reshape(-1, h, 4, param.matrixNum), recs):
+            chrom, coord, seq = rec.rsplit(":", 2)
             if regions is not None and (chrom not in regions or not regions.hit(chrom, int(coord))):
                 continue
             key = chrom + ":" + coord

@@ -131,6 +131,11 @@ enum { CVB_LINE_KEPT = 0, CVB_LINE_SKIPPED = 1, CVB_LINE_MALFORMED = 2, CVB_LINE
 int cvb_parse_tensor_text(const char* buf, int64_t len, int final_chunk, int64_t max_lines, int threads, float* x,
                           int64_t* meta, int64_t* lines, int64_t* kept, int64_t* consumed);
 
+/* the position strings utils_v2.GetTensor yields (utils_v2.py:38-42), for the KEPT lines of a cvb_parse_tensor_text result
+ * (same buf, its meta, its *lines): "chrom:pos:SEQ\n" each, SEQ upper-cased.  Returns the bytes written to out[0, cap) or -1
+ * (cap = the consumed byte count of that parse is always enough). */
+int64_t cvb_tensor_text_positions(const char* buf, const int64_t* meta, int64_t lines, char* out, int64_t cap);
+
 /* CRC-32C (Castagnoli) of data[0,n) continuing from `crc` (0 to start): the checksum TensorFlow's checkpoint bundles
  * carry per tensor and per index block (tf.train.Saver, clairvoyante_v3.py:243-251).  Host code. */
 uint32_t cvb_crc32c(uint32_t crc, const void* data, int64_t n);
