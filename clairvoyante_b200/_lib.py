@@ -94,6 +94,7 @@ SIGNATURES = {
     "cvb_candidates_take": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp, c_i64, ctypes.POINTER(c_i64)]),
     "cvb_candidates_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64)]),
     "cvb_tensor_text_positions": (c_i64, [c_vp, c_vp, c_i64, c_vp, c_i64]),
+    "cvb_vcf_records": (c_i64, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_vp, c_i64]),
     "cvb_sam_view": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, c_i64, c_i64, c_vp,
                                     ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "cvb_blosc_compress_bound": (c_i64, [c_i64]),

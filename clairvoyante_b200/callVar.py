@@ -2,8 +2,8 @@
 clairvoyante/callVar.py with the same command line (callVar.py:223-254) and the same VCF text.
 
   Run / Test    callVar.py:21-47, 180-216   three-way overlap: parse batch k+2 | predict batch k+1 | format batch k
-  Output        callVar.py:50-153           per-site decisions; the argmax / QUAL / DP / AF arithmetic is done on
-                                            whole batches with NumPy, strings only for the emitted records
+  Output        callVar.py:50-153           per-site decisions and the record text: one native pass over the batch
+                                            (cvb_vcf_records, csrc/vcf_text.cpp)
   PrintVCFHeader callVar.py:156-178
 """
 import argparse
@@ -11,12 +11,11 @@ import logging
 import os
 import sys
 import time
-from math import log
 from threading import Thread
 
 import numpy as np
 
-from . import param
+from . import _lib, param
 
 logging.basicConfig(format='%(message)s', level=logging.INFO)
 num2base = "ACGT"
@@ -46,101 +45,27 @@ def Run(args):
     Test(args, m, utils)
 
 
-def _top2(a):
-    s = np.sort(a, axis=1)
-    return s[:, -1], s[:, -2]
-
-
 def Output(args, call_fh, num, XBatch, posBatch, base, z, t, l):
+    """callVar.py:50-153.  The per-site record logic runs in the C library (cvb_vcf_records, csrc/vcf_text.cpp: one pass over the
+    batch instead of a Python loop per site); oracle/callvar_output.py is its scalar restatement."""
     if num != len(base):
         sys.exit("Inconsistent shape between input tensor and output predictions %d/%d" % (num, len(base)))
     if num == 0:
         return
-    F = param.flankingBaseNum
-    varTypes = np.argmax(t, axis=1)
-    emit = np.flatnonzero((varTypes != 0) | bool(args.showRef))
-    if emit.size == 0:
-        return
-    zyg = np.argmax(z, axis=1)
-    vlen = np.argmax(l, axis=1)
-    t1, t2 = _top2(t); z1, z2 = _top2(z); l1, l2 = _top2(l)
-    # float32 products, float64 ratio and log, truncation toward zero -- as in callVar.py:72
-    ratio = ((t2 * z2 * l2).astype(np.float64) + 1e-300) / ((t1 * z1 * l1).astype(np.float64) + 1e-300)
-    order = np.argsort(base, axis=1, kind="stable")[:, ::-1]          # ties: higher index first, like argsort()[::-1]
-    # python sum() over float32 rows accumulates left to right in float32 (callVar.py:88-89)
-    dp = np.zeros(num, np.float32)
-    for src in (XBatch[:, F, :, 0], XBatch[:, F + 1, :, 1], XBatch[:, F + 1, :, 2], XBatch[:, F, :, 3]):
-        s = np.zeros(num, np.float32)
-        for k in range(4):
-            s = s + src[:, k]
-        dp = dp + s
-    ins_cov = XBatch[:, F + 1, :, 1].sum(axis=1, dtype=np.float32)
-    del_cov = XBatch[:, F + 1, :, 2].sum(axis=1, dtype=np.float32)
-    out = []
-    for j in emit:
-        if dp[j] == 0:
-            continue
-        varType, varLength = int(varTypes[j]), int(vlen[j])
-        chromosome, coordination, refSeq = posBatch[j].split(":")
-        coordination = int(coordination)
-        qual = int(-4.343 * log(ratio[j]))
-        filt = "."
-        if args.qual is not None:
-            filt = "PASS" if qual >= args.qual else "LowQual"
-        refBase = refSeq[F]; altBase = ""; inferred = 0; info = []; af = 0.0
-        if varType <= 1:                                   # REF or SNP
-            if varType == 1:
-                b1, b2 = num2base[order[j, 0]], num2base[order[j, 1]]
-                altBase = b1 if b1 != refBase else b2
-            else:
-                altBase = refBase
-            af = XBatch[j, F, base2num[altBase], 3] / dp[j]
-        elif varType == 2:                                 # INS
-            if varLength == 0:
-                varLength = 1
-            af = ins_cov[j] / dp[j]
-            if varLength != maxVarLength:
-                for k in range(F + 1, F + varLength + 1):
-                    altBase += num2base[int(np.argmax(XBatch[j, k, :, 1]))]
-            else:
-                for k in range(F + 1, 2 * F + 1):
-                    ref_t, ins_t = XBatch[j, k, :, 0], XBatch[j, k, :, 1]
-                    if k < (F + maxVarLength) or sum(ins_t) >= (inferIndelLengthMinimumAF * sum(ref_t)):
-                        inferred += 1
-                        altBase += num2base[int(np.argmax(ins_t))]
-                    else:
-                        break
-            if inferred >= F:
-                altBase = "<INS>"
-                info.append("SVTYPE=INS")
-            else:
-                altBase = refBase + altBase
-        else:                                              # DEL
-            if varLength == 0:
-                varLength = 1
-            af = del_cov[j] / dp[j]
-            if varLength == maxVarLength:
-                for k in range(F + 1, 2 * F + 1):
-                    if k < (F + maxVarLength) or sum(XBatch[j, k, :, 2]) >= (inferIndelLengthMinimumAF * sum(XBatch[j, k, :, 0])):
-                        inferred += 1
-                    else:
-                        break
-            if inferred >= F:
-                altBase = "<DEL>"
-                info.append("SVTYPE=DEL")
-            elif varLength != maxVarLength:
-                refBase = refSeq[F:F + varLength + 1]
-                altBase = refSeq[F]
-            else:
-                refBase = refSeq[F:F + inferred + 1]
-                altBase = refSeq[F]
-        if 0 < inferred < F:
-            info.append("LENGUESS=%d" % inferred)
-        gt = "0/0" if varType == 0 else ("0/1" if zyg[j] == 0 else "1/1")
-        out.append("%s\t%d\t.\t%s\t%s\t%d\t%s\t%s\tGT:GQ:DP:AF\t%s:%d:%d:%.4f" %
-                   (chromosome, coordination, refBase, altBase, qual, filt, ";".join(info) if info else ".", gt, qual, dp[j], af))
-    if out:
-        call_fh.write("\n".join(out) + "\n")
+    lib = _lib.load()
+    x = np.ascontiguousarray(XBatch, dtype=np.float32)
+    heads = [np.ascontiguousarray(h, dtype=np.float32) for h in (base, z, t, l)]
+    if x.shape[1:] != (2 * param.flankingBaseNum + 1, 4, param.matrixNum) or [h.shape[1] for h in heads] != [4, 2, 4, 6]:
+        sys.exit("Output: unexpected tensor or prediction shape")
+    pos = "\n".join(posBatch).encode("ascii", "replace")
+    out = np.empty(len(pos) + 256 * num + 64, np.uint8)
+    n = lib.cvb_vcf_records(x.ctypes.data, pos, len(pos), heads[0].ctypes.data, heads[1].ctypes.data, heads[2].ctypes.data,
+                            heads[3].ctypes.data, num, 1 if args.showRef else 0, -1 if args.qual is None else int(args.qual),
+                            out.ctypes.data, len(out))
+    if n < 0:
+        _lib.check(1)
+    if n:
+        call_fh.write(out[:n].tobytes().decode("ascii", "replace"))
 
 
 def PrintVCFHeader(args, call_fh):

@@ -202,6 +202,14 @@ int cvb_candidates_take(cvb_candidates* c, char* text, int64_t text_cap, int64_t
                         int64_t* n_pos);
 int cvb_candidates_stats(const cvb_candidates* c, int64_t stats[4]);
 
+/* ---- VCF records of one batch of calls: the per-site loop of `Output` (clairvoyante/callVar.py:58-153) --------------------
+ * x (n,33,4,4) the batch as GetTensor yields it; pos = its n position strings "chrom:pos:SEQ" separated by '\n';
+ * base (n,4), z (n,2), t (n,4), l (n,6) the four head outputs; show_ref as --showRef; qual_cut = --qual or -1.
+ * Writes the records (one line each, sites without a record skipped) to out[0, cap) and returns the byte count, -1 on error
+ * (cap >= pos_len + 256 * n is always enough).  Host code. */
+int64_t cvb_vcf_records(const float* x, const char* pos, int64_t pos_len, const float* base, const float* z, const float* t,
+                        const float* l, int64_t n, int show_ref, int qual_cut, char* out, int64_t cap);
+
 /* `samtools view -F <flag_mask> <file> ctg[:start-end]` for SAM TEXT (CreateTensor.py:134-136, ExtractVariantCandidates.py:
  * 107-109 run it with -F 2308): copies the complete lines of in[0, len) that samtools would print to out (capacity len + 1)
  * -- header lines, other contigs, records with flag & flag_mask and records that do not overlap the 1-based inclusive region

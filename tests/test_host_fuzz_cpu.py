@@ -9,7 +9,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "clairvoyante_b200", "csrc")
-STAGES = ["blosc_frame.cpp", "text_feed.cpp", "pileup.cpp", "candidates.cpp", "crc32c.cpp", "sam_view.cpp"]
+STAGES = ["blosc_frame.cpp", "text_feed.cpp", "pileup.cpp", "candidates.cpp", "crc32c.cpp", "sam_view.cpp", "vcf_text.cpp"]
 
 
 @pytest.fixture(scope="module")

@@ -1,7 +1,7 @@
 // host_fuzz.cpp -- memory-safety harness for the host-side C++ stages of libcvb200 (no CUDA, no GPU).
 //
 // Built by tests/test_host_fuzz_cpu.py with -fsanitize=address,undefined from the stage sources where they lie
-// (blosc_frame.cpp, text_feed.cpp, pileup.cpp, candidates.cpp, crc32c.cpp) and run with a fixed seed: valid inputs,
+// (blosc_frame.cpp, text_feed.cpp, pileup.cpp, candidates.cpp, crc32c.cpp, sam_view.cpp, vcf_text.cpp) and run with a fixed seed: valid inputs,
 // then the same inputs with bytes flipped / cut / duplicated.  The checks are "returns, leaks nothing, touches nothing
 // outside its buffers" plus the round trips that must still hold (blosc encode -> decode).
 //   host_fuzz <seed> <iterations>
@@ -300,6 +300,36 @@ void fuzz_alignments() {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------- VCF records
+void fuzz_vcf() {
+  const int64_t n = rnd_below(40);
+  std::vector<float> x((size_t)n * 528), base((size_t)n * 4), z((size_t)n * 2), t((size_t)n * 4), l((size_t)n * 6);
+  for (auto& v : x) v = rnd_below(6) == 0 ? (float)rnd_below(60) : 0.f;
+  auto fill = [](std::vector<float>& a) {
+    for (auto& v : a) v = (float)rnd_below(1000) / 1000.f;
+    for (size_t i = 0; i + 1 < a.size(); i += 7) a[i + 1] = a[i];  // ties
+  };
+  fill(base); fill(z); fill(t); fill(l);
+  std::string pos;
+  for (int64_t j = 0; j < n; ++j) {
+    pos += (rnd_below(9) ? "chr1" : "HLA:A*01") + std::string(":") + std::to_string(rnd_below(1000000)) + ":";
+    for (int k = 0; k < 33; ++k) pos += "ACGTN"[rnd_below(k == 16 ? 4 : 5)];
+    if (j + 1 < n || rnd_below(2)) pos += "\n";
+  }
+  std::vector<uint8_t> pv(pos.begin(), pos.end());
+  const bool intact = rnd_below(2);
+  if (!intact) mutate(pv);
+  const int64_t cap = (int64_t)pv.size() + 256 * n + 64;
+  std::vector<char> out((size_t)cap);
+  const int64_t w = cvb_vcf_records(x.data(), (const char*)pv.data(), (int64_t)pv.size(), base.data(), z.data(), t.data(), l.data(), n,
+                                    (int)rnd_below(2), rnd_below(2) ? -1 : (int)rnd_below(300), out.data(), cap);
+  if (w > cap) die("vcf_records overran");
+  if (intact && w < 0) die("vcf_records refused well-formed input");
+  if (n > 3 && cvb_vcf_records(x.data(), (const char*)pv.data(), (int64_t)pv.size(), base.data(), z.data(), t.data(), l.data(), n, 1, -1,
+                               out.data(), 50) > 50)
+    die("vcf_records ignored its capacity");
+}
+
 void fuzz_crc() {
   const int64_t n = rnd_below(5000);
   std::vector<uint8_t> v((size_t)n);
@@ -321,6 +351,7 @@ int main(int argc, char** argv) {
     if (!*only || !strcmp(only, "text")) fuzz_text();
     if (!*only || !strcmp(only, "aln")) fuzz_alignments();
     if (!*only || !strcmp(only, "crc")) fuzz_crc();
+    if (!*only || !strcmp(only, "vcf")) fuzz_vcf();
   }
   if (strcmp(cvb_crc32c(0, "123456789", 9) == 0xE3069283u ? "ok" : "bad", "ok")) die("crc32c known answer");
   printf("host_fuzz: %d iterations clean\n", iters);
