@@ -51,3 +51,20 @@ def test_pair_with_non_variants(tmp_path):
     a.bed_fn = None                                             # without BED the chr1:900 and chr2 rows are usable too
     a.amp = 100
     assert PairWithNonVariants.Pair(a) == (2, 8)
+
+
+def test_submodule_invocator(tmp_path):
+    """python -m clairvoyante_b200 <Submodule> ... (reference clairvoyante.py) reaches the submodule's main()"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    vcf = tmp_path / "t.vcf"
+    vcf.write_text("#h\nctg\t10\t.\tA\tC\t50\tPASS\t.\tGT\t0/1\nctg\t20\t.\tAT\tA\t50\tPASS\t.\tGT\t1|1\n")
+    r = subprocess.run([sys.executable, "-m", "clairvoyante_b200", "GetTruth", "--vcf_fn", str(vcf), "--ctgName", "ctg"], cwd=root,
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == "ctg 10 A C 0 1\nctg 20 AT A 1 1\n", r.stderr
+    r = subprocess.run([sys.executable, "-m", "clairvoyante_b200"], cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0 and "callVarBam" in r.stdout
+    r = subprocess.run([sys.executable, "-m", "clairvoyante_b200", "getEmbedding"], cwd=root, capture_output=True, text=True)
+    assert r.returncode != 0 and "outside the scope" in r.stderr
