@@ -155,6 +155,16 @@ void fuzz_text() {
         for (int f = 3; f < 9; f += 2)
           if (m[f] < 0 || m[f + 1] < 0 || m[f] + m[f + 1] > (int64_t)exact.size() - off) die("text parser: field span outside the buffer");
     }
+    {  // the position strings of the kept rows: capacity = the consumed bytes, as the Python side sizes it
+      std::vector<char> names((size_t)consumed + 16);
+      const int64_t w = cvb_tensor_text_positions((const char*)exact.data() + off, meta.data(), lines, names.data(), (int64_t)names.size());
+      if (w < 0 || w > (int64_t)names.size()) die("tensor_text_positions: capacity rule violated");
+      int64_t nl = 0;
+      for (int64_t i = 0; i < w; ++i) nl += names[(size_t)i] == '\n';
+      if (nl != kept) die("tensor_text_positions: one line per kept row expected");
+      if (kept > 0 && cvb_tensor_text_positions((const char*)exact.data() + off, meta.data(), lines, names.data(), 3) >= 0)
+        die("tensor_text_positions ignored its capacity");
+    }
     if (consumed == 0) break;
     off += consumed;
   }
