@@ -104,6 +104,8 @@ struct cvb_model {
   int tc_merged = 1;
   int tc_cluster = 1;  // 2-CTA clusters with weight multicast in the conv tensor kernels (needs tc_merged)
   int tc_slab = 1;     // slab-mode conv kernels (conv_tc_slab.cuh): A loaded once per (tile, w'), re-used across kh
+  int slim_fc4_tc = 0; // CVB_SLIM_FC4_TC=1: v3_slim inference FC4 as a split-bf16 tcgen05 GEMM (opt-in until run on a B200)
+  uint16_t *d_p3s = nullptr, *d_w4ts = nullptr;  // its operands: planes of the conv3 output / of fc4/kernel^T
   int tc_resident = 0; // CVB_CONV_RESIDENT bit mask: 1 = conv3, 2 = conv2 keep their taps in shared memory (ConvSlabCfg RES;
                        // opt-in until it has been timed and parity-checked on a B200)
   CUtensorMap map_c2slab, map_c3slab;
@@ -224,6 +226,7 @@ extern "C" int cvb_destroy(cvb_model* m) {
   cudaFree(m->d_params); cudaFree(m->d_m); cudaFree(m->d_v); cudaFree(m->d_grad);
   cudaFree(m->d_p2); cudaFree(m->d_p3); cudaFree(m->d_h4); cudaFree(m->d_h5);
   cudaFree(m->d_w3b_hi); cudaFree(m->d_p1); cudaFree(m->d_w2b_hi); cudaFree(m->d_h4s); cudaFree(m->d_wtail);
+  cudaFree(m->d_p3s); cudaFree(m->d_w4ts);
   cudaFree(m->d_w4t_hi); cudaFree(m->d_w4t_lo); cudaFree(m->d_absmax); cudaFree(m->d_inv_scale);
   for (int i = 0; i < cvb_model::NSLOT; ++i) {
     cudaFree(m->d_x[i]); cudaFree(m->d_x16[i]); cudaFree(m->d_out[i]); cudaFree(m->d_lg[i]);
@@ -494,6 +497,12 @@ static int tc_setup_slim(cvb_model* m) {
                           tc::SlimConv3SlabRes::SMEM_BYTES));
   const char* er = getenv("CVB_CONV_RESIDENT");
   m->tc_resident = er ? atoi(er) : 0;
+  const char* ef = getenv("CVB_SLIM_FC4_TC");
+  m->slim_fc4_tc = ef && ef[0] == '1';
+  if (m->slim_fc4_tc) {
+    CK(cudaMalloc(&m->d_p3s, (size_t)m->alloc_sites * 4224 * 2 * 2));
+    CK(cudaMalloc(&m->d_w4ts, (size_t)36 * 4224 * 2 * 2));
+  }
   CK(cudaFuncSetAttribute(tc::k_conv_tc<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tc::k_conv_tc<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   m->tc_ready = true;
@@ -501,10 +510,14 @@ static int tc_setup_slim(cvb_model* m) {
   return 0;
 }
 
+static int slim_fc4_tc_weights(cvb_model* m, cudaStream_t st);   // (defined with the generic GEMM helpers below)
+static int slim_fc4_tc_forward(cvb_model* m, int64_t n, cudaStream_t st);
+
 // (re)build the split fp16 copy of fc4/kernel on `st` if the fp32 master changed
 static int tc_refresh_weights(cvb_model* m, cudaStream_t st) {
   if (!m->tc_weights_dirty) return 0;
   if (m->variant == CVB_V3_SLIM) {
+    if (m->slim_fc4_tc && slim_fc4_tc_weights(m, st)) return 1;
     using C = tc::SlimConv3Tc;
     CK(cudaMemsetAsync(m->d_absmax + 1, 0, 4, st));
     tc::k_absmax<<<32, 256, 0, st>>>(m->var("conv3/kernel"), 5 * 4 * 16 * 32, m->d_absmax + 1);
@@ -835,7 +848,10 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
     }
-    {
+    if (tensor && m->slim_fc4_tc) {
+      if (slim_fc4_tc_forward(m, n, st)) return 1;
+      if (prof_mark(m, st)) return 1;
+    } else {
       using F = FcCfg<36, 9, 4, 28, 8>;
       auto k = k_fc4<F>;
       CK(set_smem(k, F::SMEM_BYTES));
@@ -1196,6 +1212,24 @@ static int split_transpose_bf16(const float* src, int64_t R, int C, int64_t ld_s
   tc::k_split_transpose_bf16<<<dim3((unsigned)((C + 31) / 32), (unsigned)((R + 63) / 64)), dim3(32, 8), 0, st>>>(
       src, R, C, ld_src, bf(dst), bf(dst + plane), ld_dst, row_shift);
   CK(cudaGetLastError());
+  return 0;
+}
+
+// v3_slim inference FC4 on tcgen05 (opt-in, CVB_SLIM_FC4_TC=1; written without a GPU at hand -- tools/ab_resident.py-style A/B
+// first): the fp32 conv3 output [n][4224] is split into bf16 hi/lo planes and multiplied with the split-bf16 transpose of
+// fc4/kernel by the generic GEMM of the training path (N = 36 in one 48-column tile, K-chunked, bias + SELU epilogue) -- the same
+// two launches train_forward_slim uses.
+static int slim_fc4_tc_weights(cvb_model* m, cudaStream_t st) {
+  if (split_transpose_bf16(m->var("fc4/kernel"), 4224, 36, 36, m->d_w4ts, 36 * 4224, 4224, st)) return 1;
+  m->launches += 1;
+  return 0;
+}
+static int slim_fc4_tc_forward(cvb_model* m, int64_t n, cudaStream_t st) {
+  if (split_rows_bf16(m->d_p3, n, 4224, m->d_p3s, m->alloc_sites * 4224, st)) return 1;
+  if (launch_gemm_tc<48, true, tc::GEMM_EPI_BIAS_SELU>(m, m->d_p3s, m->alloc_sites * 4224, 4224, m->d_w4ts, 36 * 4224, 4224, (int)n, 36, 4224,
+                                                       m->d_h4, 36, m->var("fc4/bias"), st))
+    return 1;
+  m->launches += 1;
   return 0;
 }
 

@@ -10,6 +10,11 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 variant, setting = sys.argv[1], sys.argv[2]
 os.environ["CVB_CONV_RESIDENT"] = setting
+extra = sys.argv[3] if len(sys.argv) > 3 else ""          # further opt-in switches, e.g. CVB_SLIM_FC4_TC=1 (not bit-identical:
+for kv in filter(None, extra.split(",")):                 # bf16x3 GEMM instead of fp32 SIMT -- max |diff| is reported)
+    k, v = kv.split("=")
+    os.environ[k] = v
+tag = setting + ("_" + extra.replace("=", "").replace(",", "_") if extra else "")
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 from clairvoyante_b200 import initializers as I, synth  # noqa: E402
@@ -24,9 +29,10 @@ m.setWeights(I.init_weights(variant, 0))
 chunk = 18944 if variant == "v3" else 33152
 x = synth.make_sites(chunk + 1234, 1)          # one full chunk and a ragged one
 _, logits = m.predictLogits(x)
-np.save("gpurun_out/ab_resident_%s_%s.npy" % (variant, setting), logits)
+np.save("gpurun_out/ab_resident_%s_%s.npy" % (variant, tag), logits)
 ref_fn = "gpurun_out/ab_resident_%s_0.npy" % variant
-same = bool(np.array_equal(np.load(ref_fn), logits)) if setting != "0" and os.path.exists(ref_fn) else None
+same = bool(np.array_equal(np.load(ref_fn), logits)) if tag != "0" and os.path.exists(ref_fn) else None
+maxdiff = float(np.abs(np.load(ref_fn) - logits).max()) if tag != "0" and os.path.exists(ref_fn) else None
 
 N = chunk * 8
 xd = torch.from_numpy(x[:chunk]).cuda().repeat(8, 1, 1, 1).contiguous()
@@ -39,8 +45,8 @@ m.profileBegin()
 for _ in range(4):
     m.predictDevice(xd.data_ptr(), N, od.data_ptr(), None, st)
 pr = m.profileRead()
-out = {"variant": variant, "CVB_CONV_RESIDENT": setting, "bit_identical_to_default": same,
+out = {"variant": variant, "CVB_CONV_RESIDENT": setting, "extra": extra, "bit_identical_to_default": same, "max_abs_logit_diff": maxdiff,
        "ms_per_chunk": {k: round(v[0] / max(v[1], 1), 4) for k, v in pr.items()}}
 print(json.dumps(out))
-json.dump(out, open("gpurun_out/ab_resident_%s_%s.json" % (variant, setting), "w"))
+json.dump(out, open("gpurun_out/ab_resident_%s_%s.json" % (variant, tag), "w"))
 m.close()
