@@ -15,6 +15,7 @@ yields exactly what utils_v2.GetTensor yields for the rows this module would hav
 import argparse
 import ctypes
 import gzip
+import os
 import shlex
 import shutil
 import subprocess
@@ -31,7 +32,9 @@ _ACGT = frozenset("ACGT")
 class Pileup(object):
     """thin handle over cvb_pileup_* (one contig / region)"""
 
-    def __init__(self, ref_seq, candidates, ref_start=None, minMQ=0, dcov=250, minCoverage=0, considerleftedge=True):
+    def __init__(self, ref_seq, candidates, ref_start=None, minMQ=0, dcov=250, minCoverage=0, considerleftedge=True, threads=None):
+        """threads: host threads for the CIGAR walks of a feed() call (None = CVB_HOST_THREADS or up to 16 cores);
+        the result does not depend on it"""
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
         ref = ref_seq.encode("ascii", "replace") if isinstance(ref_seq, str) else bytes(ref_seq)
@@ -39,6 +42,9 @@ class Pileup(object):
         _lib.check(self._lib.cvb_pileup_create(ref, len(ref), int(ref_start or 0), cand.ctypes.data, cand.size,
                                                int(minMQ), int(dcov), int(minCoverage), 1 if considerleftedge else 0,
                                                ctypes.byref(self._h)))
+        if threads is None:
+            threads = int(os.environ.get("CVB_HOST_THREADS", 0)) or min(16, os.cpu_count() or 1)
+        _lib.check(self._lib.cvb_pileup_set_threads(self._h, int(threads)))
 
     def feed(self, sam_bytes, final=False):
         b = sam_bytes.encode("ascii", "replace") if isinstance(sam_bytes, str) else sam_bytes

@@ -79,6 +79,7 @@ SIGNATURES = {
     "cvb_pileup_create": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_int, ctypes.POINTER(c_vp)]),
     "cvb_pileup_destroy": (ctypes.c_int, [c_vp]),
+    "cvb_pileup_set_threads": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "cvb_pileup_feed": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int]),
     "cvb_pileup_ready": (c_i64, [c_vp]),
     "cvb_pileup_take": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, ctypes.POINTER(c_i64)]),

@@ -166,6 +166,9 @@ typedef struct cvb_pileup cvb_pileup;
 int cvb_pileup_create(const char* ref_seq, int64_t ref_len, int64_t ref_start, const int64_t* cand_pos, int64_t n_cand,
                       int min_mq, int dcov, int min_coverage, int consider_left_edge, cvb_pileup** out);
 int cvb_pileup_destroy(cvb_pileup* p);
+/* host threads for the CIGAR walks of one cvb_pileup_feed call (default 1): each thread owns a contiguous range of the
+ * candidate list; results (tensors, their order, the statistics) are identical for every thread count */
+int cvb_pileup_set_threads(cvb_pileup* p, int threads);
 int cvb_pileup_feed(cvb_pileup* p, const char* sam, int64_t len, int final_chunk);
 int64_t cvb_pileup_ready(const cvb_pileup* p);
 int cvb_pileup_take(cvb_pileup* p, int64_t max_sites, float* x, int64_t* center, int64_t* n_out);

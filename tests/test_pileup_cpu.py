@@ -228,3 +228,24 @@ def test_sam_text_view_equals_samtools_view_semantics():
                     break
                 got += c
             assert got == want(a, b), (a, b, size)
+
+
+@pytest.mark.parametrize("seed", [0, 5, 9])
+@pytest.mark.parametrize("opts", [dict(), dict(dcov=2, minCoverage=3), dict(considerleftedge=False, minMQ=10)])
+def test_thread_count_does_not_change_the_result(seed, opts):
+    """the CIGAR walks of a feed call may run on several threads (cvb_pileup_set_threads): same tensors, same order, same
+    statistics for every thread count -- on sorted input, on unsorted / damaged input, for whole and chunked feeds"""
+    rng = np.random.default_rng(seed)
+    ref, sam, _ = synth_alignments(rng, ref_len=6000, n_reads=1500, dup_pos=0.3)
+    cands = sorted(set(int(c) for c in rng.integers(1, 6000, size=900)))          # dense: every ~7 bases
+    rows = sam.split("\n")
+    shuffled = rows[:2] + [rows[i] for i in rng.permutation(np.arange(2, len(rows) - 1))[:400]]
+    for text, chunk in ((sam, None), (sam, 20000), ("\n".join(shuffled) + "\n", None)):
+        want = None
+        for threads in (1, 2, 3, 8):
+            c, x, st = run_native(text, ref, cands, None, chunk, threads=threads, **opts)
+            if want is None:
+                want = (c, x, st)
+                assert len(c) > 20
+            else:
+                assert np.array_equal(c, want[0]) and np.array_equal(x, want[1]) and st == want[2], (threads, chunk)

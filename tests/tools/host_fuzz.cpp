@@ -204,6 +204,12 @@ std::string sam_rows(const std::string& ref, int reads, const char* ctg, bool so
 void feed_chunks(const std::vector<uint8_t>& sam, int (*feed)(void*, const char*, int64_t, int), void* h) {
   int64_t off = 0;
   const int64_t n = (int64_t)sam.size();
+  if (n > 0 && rnd_below(3) == 0) {  // everything in one call (the path that may use several threads)
+    std::vector<uint8_t> whole(sam);
+    feed(h, (const char*)whole.data(), n, 0);
+    feed(h, nullptr, 0, 1);
+    return;
+  }
   while (off < n) {
     int64_t len = 1 + rnd_below(rnd_below(3) ? 4000 : 40);
     if (len > n - off) len = n - off;
@@ -222,7 +228,7 @@ void fuzz_alignments() {
   const std::string ref = make_ref(ref_len);
   const int64_t ref_start = rnd_below(3) ? 0 : rnd_below(100);
   const bool sorted = rnd_below(4) != 0;
-  std::string sam = sam_rows(ref, 5 + (int)rnd_below(120), "ctg", sorted);
+  std::string sam = sam_rows(ref, 5 + (int)rnd_below(rnd_below(3) ? 120 : 500), "ctg", sorted);
   std::vector<uint8_t> v(sam.begin(), sam.end());
   const bool intact = rnd_below(3) == 0;
   if (!intact) mutate(v);
@@ -284,6 +290,7 @@ void fuzz_alignments() {
     if (cvb_pileup_create(ref.data(), ref_len, ref_start, cand.empty() ? nullptr : cand.data(), (int64_t)cand.size(), (int)rnd_below(30),
                           (int)rnd_below(3) ? 1000 : 3, (int)rnd_below(5), (int)rnd_below(2), &h))
       return;  // (a refused configuration is fine)
+    cvb_pileup_set_threads(h, 1 + (int)rnd_below(4));
     feed_chunks(v, feed_pileup, h);
     const int64_t ready = cvb_pileup_ready(h);
     if (ready < 0 || (sorted && intact && ready > (int64_t)cand.size()))  // (unsorted input can re-open a centre, as in the reference)
