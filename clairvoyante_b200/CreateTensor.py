@@ -48,6 +48,9 @@ class Pileup(object):
 
     def feed(self, sam_bytes, final=False):
         b = sam_bytes.encode("ascii", "replace") if isinstance(sam_bytes, str) else sam_bytes
+        if isinstance(b, np.ndarray):                     # (uint8 buffer from _SamTextView: no copy)
+            _lib.check(self._lib.cvb_pileup_feed(self._h, b.ctypes.data, b.size, 1 if final else 0))
+            return
         _lib.check(self._lib.cvb_pileup_feed(self._h, b, len(b), 1 if final else 0))
 
     def ready(self):
@@ -84,9 +87,10 @@ def _chunks(sam_source, size=8 << 20):
     if isinstance(sam_source, (bytes, str)):
         yield sam_source
     elif hasattr(sam_source, "read"):
+        read = getattr(sam_source, "read_array", None) or sam_source.read     # (_SamTextView: uint8 buffers, no copy)
         while True:
-            b = sam_source.read(size)
-            if not b:
+            b = read(size)
+            if len(b) == 0:
                 break
             yield b
     else:
@@ -248,19 +252,23 @@ class _SamTextView(object):
         self.lib = _lib.load()
 
     def read(self, size=8 << 20):
+        return self.read_array(size).tobytes()
+
+    def read_array(self, size=8 << 20):
+        """like read(), but hands out the uint8 buffer the filter wrote (no copy; empty at the end of the stream)"""
         while True:
             b = self.fh.read(size)
             final = not b
             data = self.carry + b if self.carry else b
             if final and not data:
-                return b""
+                return np.empty(0, np.uint8)
             out = np.empty(len(data) + 1, np.uint8)             # (no zero fill, unlike ctypes.create_string_buffer)
             n, used = ctypes.c_int64(), ctypes.c_int64()
             _lib.check(self.lib.cvb_sam_view(data, len(data), 1 if final else 0, self.ctg, 2308, self.start, self.end,
                                              out.ctypes.data, ctypes.byref(n), ctypes.byref(used)))
             self.carry = data[used.value:]
             if n.value or final:
-                return out[:n.value].tobytes()
+                return out[:n.value]
 
     def close(self):
         self.fh.close()

@@ -22,7 +22,8 @@ class Candidates(object):
     """thin handle over cvb_candidates_* (one contig / region)"""
 
     def __init__(self, ctgName, ref_seq, ref_start=None, ctgStart=None, ctgEnd=None, bed=None, minMQ=0, minCoverage=4,
-                 threshold=0.125, outputProb=None, seed=0):
+                 threshold=0.125, outputProb=None, seed=0, threads=None):
+        """threads: host threads per feed() call (None = CVB_HOST_THREADS or up to 16 cores); the result does not depend on it"""
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
         ref = ref_seq.encode("ascii", "replace") if isinstance(ref_seq, str) else bytes(ref_seq)
@@ -39,9 +40,15 @@ class Candidates(object):
             bb.ctypes.data if nb > 0 else None, be.ctypes.data if nb > 0 else None, nb, int(minMQ), float(minCoverage),
             float(threshold), -1.0 if outputProb is None else float(outputProb), int(seed) & 0xFFFFFFFFFFFFFFFF,
             ctypes.byref(self._h)))
+        if threads is None:
+            threads = int(os.environ.get("CVB_HOST_THREADS", 0)) or min(16, os.cpu_count() or 1)
+        _lib.check(self._lib.cvb_candidates_set_threads(self._h, int(threads)))
 
     def feed(self, sam_bytes, final=False):
         b = sam_bytes.encode("ascii", "replace") if isinstance(sam_bytes, str) else sam_bytes
+        if isinstance(b, np.ndarray):                     # (uint8 buffer from _SamTextView: no copy)
+            _lib.check(self._lib.cvb_candidates_feed(self._h, b.ctypes.data, b.size, 1 if final else 0))
+            return
         _lib.check(self._lib.cvb_candidates_feed(self._h, b, len(b), 1 if final else 0))
 
     def take(self):

@@ -89,6 +89,7 @@ SIGNATURES = {
                                              ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_uint64,
                                              ctypes.POINTER(c_vp)]),
     "cvb_candidates_destroy": (ctypes.c_int, [c_vp]),
+    "cvb_candidates_set_threads": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "cvb_candidates_feed": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int]),
     "cvb_candidates_pending_bytes": (c_i64, [c_vp]),
     "cvb_candidates_pending": (c_i64, [c_vp]),

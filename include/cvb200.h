@@ -198,6 +198,9 @@ int cvb_candidates_create(const char* ctg_name, const char* ref_seq, int64_t ref
                           int64_t ctg_end, const int64_t* bed_begin, const int64_t* bed_end, int64_t n_bed, int min_mq,
                           double min_coverage, double threshold, double output_prob, uint64_t seed, cvb_candidates** out);
 int cvb_candidates_destroy(cvb_candidates* c);
+/* host threads per cvb_candidates_feed call (default 1): rows are tokenised in parallel and the counting is split by reference
+ * position; rows, their order and the statistics are identical for every thread count */
+int cvb_candidates_set_threads(cvb_candidates* c, int threads);
 int cvb_candidates_feed(cvb_candidates* c, const char* sam, int64_t len, int final_chunk);
 int64_t cvb_candidates_pending_bytes(const cvb_candidates* c);
 int64_t cvb_candidates_pending(const cvb_candidates* c);

@@ -156,3 +156,27 @@ def test_mutated_sam_rows_never_crash_and_still_agree():
         assert [int(v) for v in cc] == [w[0] for w in want] and all(np.array_equal(x[i], w[1]) for i, w in enumerate(want)), it
         rows, _, _ = run_native(sam2, "ctg", ref, None, minCoverage=0)
         assert rows == O.make_candidates(sam2, "ctg", ref, None, minCoverage=0), it
+
+
+@pytest.mark.parametrize("seed", [1, 4, 8])
+@pytest.mark.parametrize("opts", [dict(), dict(minMQ=20, threshold=0.05, minCoverage=2),
+                                  dict(ctgStart=801, ctgEnd=5000, bed=[(500, 2500), (3000, 3001), (3500, 9000)])])
+def test_thread_count_does_not_change_the_result(seed, opts):
+    """several host threads per feed call (cvb_candidates_set_threads: rows tokenised in parallel, counting split by position):
+    same rows, same order, same statistics as the serial loop -- sorted input, shuffled input, whole and chunked feeds"""
+    rng = np.random.default_rng(seed)
+    ref, sam, _ = synth_alignments(rng, ref_len=7000, n_reads=3000, dup_pos=0.3)
+    sam = with_extras(sam, rng)
+    rows = sam.split("\n")
+    head = [r for r in rows if r.startswith("@")]
+    body = [r for r in rows if r and not r.startswith("@")]
+    shuffled = "\n".join(head + [body[i] for i in rng.permutation(len(body))[:1500]]) + "\n"
+    for text, chunk in ((sam, None), (sam, 300000), (shuffled, None)):
+        want = None
+        for threads in (1, 2, 3, 8):
+            got = run_native(text, "ctg", ref, None, chunk, threads=threads, **opts)
+            if want is None:
+                want = got
+                assert len(got[0]) > 50
+            else:
+                assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2], (threads, chunk)

@@ -228,7 +228,7 @@ void fuzz_alignments() {
   const std::string ref = make_ref(ref_len);
   const int64_t ref_start = rnd_below(3) ? 0 : rnd_below(100);
   const bool sorted = rnd_below(4) != 0;
-  std::string sam = sam_rows(ref, 5 + (int)rnd_below(rnd_below(3) ? 120 : 500), "ctg", sorted);
+  std::string sam = sam_rows(ref, 5 + (int)rnd_below(rnd_below(3) ? 120 : (rnd_below(2) ? 500 : 1500)), "ctg", sorted);
   std::vector<uint8_t> v(sam.begin(), sam.end());
   const bool intact = rnd_below(3) == 0;
   if (!intact) mutate(v);
@@ -269,6 +269,7 @@ void fuzz_alignments() {
                               bb.empty() ? nullptr : bb.data(), bb.empty() ? nullptr : be.data(), (int64_t)bb.size(), (int)rnd_below(30),
                               (double)(1 + rnd_below(6)), 0.05 + 0.1 * (double)rnd_below(5), rnd_below(2) ? 0.0 : 0.3, rnd(), &c))
       die("candidates_create failed");
+    cvb_candidates_set_threads(c, 1 + (int)rnd_below(4));
     feed_chunks(v, feed_cand, c);
     const int64_t bytes = cvb_candidates_pending_bytes(c), np = cvb_candidates_pending(c);
     if (bytes < 0 || np < 0) die("candidates: negative pending counts");
