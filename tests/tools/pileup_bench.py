@@ -50,12 +50,27 @@ def main():
     best = None
     for _ in range(3):
         t = time.perf_counter()
-        p = CT.Pileup(ref, cands)
+        p = CT.Pileup(ref, cands, threads=1)
         p.feed(b, final=True)
         c, x = p.take()
         dt = time.perf_counter() - t
         p.close()
         best = dt if best is None else min(best, dt)
+    nt = min(16, os.cpu_count() or 1)
+    best_mt = None
+    for _ in range(3):
+        t = time.perf_counter()
+        p = CT.Pileup(ref, cands, threads=nt)
+        for i in range(0, len(b), 8 << 20):
+            p.feed(b[i:i + (8 << 20)])
+        p.feed(b"", final=True)
+        cm, xm = p.take()
+        dt = time.perf_counter() - t
+        p.close()
+        best_mt = dt if best_mt is None else min(best_mt, dt)
+    assert np.array_equal(cm, c) and np.array_equal(xm, x)
+    out["native_threads"] = dict(seconds=round(best_mt, 4), sites_per_s=round(len(c) / best_mt), reads_per_s=round(n_reads / best_mt),
+                                 threads=nt)
     out["native"] = dict(seconds=round(best, 4), sites=len(c), sites_per_s=round(len(c) / best), reads_per_s=round(n_reads / best),
                          sam_mb_per_s=round(len(b) / best / 1e6, 1), threads=1)
     rows = 0
@@ -79,12 +94,23 @@ def main():
     best = None
     for _ in range(3):
         t = time.perf_counter()
-        c = EVC.Candidates("ctg", ref)
+        c = EVC.Candidates("ctg", ref, threads=1)
         c.feed(b, final=True)
         text, pos = c.take()
         dt = time.perf_counter() - t
         c.close()
         best = dt if best is None else min(best, dt)
+    best_mt = None
+    for _ in range(3):
+        t = time.perf_counter()
+        c = EVC.Candidates("ctg", ref, threads=nt)
+        c.feed(b, final=True)
+        text_mt, pos_mt = c.take()
+        dt = time.perf_counter() - t
+        c.close()
+        best_mt = dt if best_mt is None else min(best_mt, dt)
+    assert text_mt == text
+    out["candidates_native_threads"] = dict(seconds=round(best_mt, 4), reads_per_s=round(n_reads / best_mt), threads=nt)
     t = time.perf_counter()
     w = OC.make_candidates(sub, "ctg", ref)
     dt = time.perf_counter() - t
