@@ -39,21 +39,47 @@ def _vcf_positions(vcf_fn, ctgName, ctgStart, ctgEnd):
     return out
 
 
+class _ChunkCache(object):
+    """keeps the alignment text of pass 1 for pass 2 while it fits (CVB_SAM_CACHE_MB, default 2048): the reference decodes the
+    BAM twice (one `samtools view` per stage, callVarBam.py:113-126); here the second decode is skipped when memory allows"""
+
+    def __init__(self):
+        self.limit = int(os.environ.get("CVB_SAM_CACHE_MB", 2048)) << 20
+        self.chunks, self.bytes, self.complete = [], 0, False
+
+    def tee(self, chunks):
+        keep = self.limit > 0
+        for b in chunks:
+            if keep:
+                self.bytes += len(b)
+                if self.bytes > self.limit:
+                    keep, self.chunks = False, []
+                else:
+                    self.chunks.append(b)
+            yield b
+        self.complete = keep
+
+
 class _AlignmentFeed(object):
     """stands where callVar.Test expects `utils`: GetTensor(tensor_fn, num) yields (endFlag, n, X, pos)"""
 
-    def __init__(self, args, ref_seq, ref_start, positions):
-        self.args, self.ref_seq, self.ref_start, self.positions = args, ref_seq, ref_start, positions
+    def __init__(self, args, ref_seq, ref_start, positions, cache=None):
+        self.args, self.ref_seq, self.ref_start, self.positions, self.cache = args, ref_seq, ref_start, positions, cache
 
     def GetTensor(self, tensor_fn, num):
         a = self.args
-        proc, sam = CT._open_alignments(a)
+        if self.cache is not None and self.cache.complete:
+            proc, sam, source = None, None, iter(self.cache.chunks)
+        else:
+            proc, sam = CT._open_alignments(a)
+            source = sam
         try:
-            for item in CT.GetTensorFromAlignments(sam, self.ref_seq, self.positions, a.ctgName, num, self.ref_start,
+            for item in CT.GetTensorFromAlignments(source, self.ref_seq, self.positions, a.ctgName, num, self.ref_start,
                                                    dcov=a.dcov, considerleftedge=a.considerleftedge):
                 yield item
         finally:
-            sam.close()
+            if sam is not None:
+                sam.close()
             if proc is not None:
                 proc.wait()
 
@@ -70,13 +96,15 @@ def Run(args, model=None):
     if args.vcf_fn is None:
         bed = EVC._load_bed(args.bed_fn, args.ctgName) if args.bed_fn is not None else None
         proc, sam = CT._open_alignments(args)
-        pos = [p for _, p in EVC.extract_candidates(sam, args.ctgName, ref_seq, ref_start, ctgStart=args.ctgStart, ctgEnd=args.ctgEnd,
+        cache = _ChunkCache()
+        pos = [p for _, p in EVC.extract_candidates(cache.tee(CT._chunks(sam)), args.ctgName, ref_seq, ref_start, ctgStart=args.ctgStart, ctgEnd=args.ctgEnd,
                                                     bed=bed, minCoverage=args.minCoverage, threshold=args.threshold)]
         sam.close()
         if proc is not None:
             proc.wait()
         positions = np.concatenate(pos) if pos else np.empty((0,), np.int64)
     else:
+        cache = None
         positions = np.asarray(_vcf_positions(args.vcf_fn, args.ctgName, args.ctgStart, args.ctgEnd), np.int64)
     if args.ctgStart is not None:                                # CreateTensor's own candidate filter (CreateTensor.py:70-71)
         positions = positions[(positions >= args.ctgStart) & (positions <= args.ctgEnd)]
@@ -91,7 +119,7 @@ def Run(args, model=None):
         model.restoreParameters(os.path.abspath(args.chkpnt_fn))
     cv_args = types.SimpleNamespace(tensor_fn="(alignments)", call_fn=args.call_fn, qual=args.qual, sampleName=args.sampleName,
                                     showRef=False, ref_fn=args.ref_fn if os.path.isfile(args.ref_fn + ".fai") else None)
-    callVar.Test(cv_args, model, _AlignmentFeed(args, ref_seq, ref_start, positions))
+    callVar.Test(cv_args, model, _AlignmentFeed(args, ref_seq, ref_start, positions, cache))
     return len(positions)
 
 
