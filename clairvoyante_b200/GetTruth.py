@@ -12,30 +12,29 @@ import subprocess
 import sys
 
 
+def _genotype(sample_field):
+    """allele indices of the GT sub-field, ascending: '1|0' -> (0, 1), './1' -> (0, 1)"""
+    a, b = (int(x) for x in sample_field.split(":")[0].replace("/", "|").replace(".", "0").split("|"))
+    return (a, b) if a < b else (b, a)
+
+
 def truth_rows(lines, ctgName, ctgStart=None, ctgEnd=None):
     """ctgStart is the value the reference compares with (its --ctgStart + 1, :35-36)"""
-    for row in lines:
-        row = row.strip().split()
-        if not row or row[0][0] == "#":
+    bounded = ctgStart is not None and ctgEnd is not None
+    for line in lines:
+        f = line.strip().split()
+        if not f or f[0][0] == "#" or f[0] != ctgName:
             continue
-        if row[0] != ctgName:
+        if bounded and not ctgStart <= int(f[1]) <= ctgEnd:
             continue
-        if ctgStart is not None and ctgEnd is not None:
-            if int(row[1]) < ctgStart or int(row[1]) > ctgEnd:
-                continue
-        last = row[-1]
-        varType = last.split(":")[0].replace("/", "|").replace(".", "0").split("|")
-        p1, p2 = varType
-        p1, p2 = int(p1), int(p2)
-        p1, p2 = (p1, p2) if p1 < p2 else (p2, p1)
-        if p1 == 1 and p2 == 2 and row[4].find(",") != -1:
-            p1, p2 = 0, 1
-            shortestLen, shortestGT = 99, ""
-            for i in row[4].split(","):
-                if len(i) < shortestLen:
-                    shortestLen, shortestGT = len(i), i
-            row[4] = shortestGT
-        yield " ".join([row[0], row[1], row[3], row[4], str(p1), str(p2)])
+        g1, g2 = _genotype(f[-1])
+        alt = f[4]
+        if (g1, g2) == (1, 2) and "," in alt:       # two ALT alleles: reported as 0/1 with the shortest one (first of equals; :67-77)
+            g1, g2 = 0, 1
+            alt = min(alt.split(","), key=lambda s: 99 if len(s) >= 99 else len(s))
+            if len(alt) >= 99:
+                alt = ""
+        yield " ".join((f[0], f[1], f[3], alt, str(g1), str(g2)))
 
 
 def OutputVariant(args):
@@ -63,16 +62,13 @@ def OutputVariant(args):
 
 def main():
     parser = argparse.ArgumentParser(description="Extract variant type and allele from a Truth dataset")
-    parser.add_argument('--vcf_fn', type=str, default="input.vcf", help="Truth vcf file input, default: %(default)s")
-    parser.add_argument('--var_fn', type=str, default="PIPE", help="Truth variants output, use PIPE for standard output, default: %(default)s")
-    parser.add_argument('--ctgName', type=str, default="chr17", help="The name of sequence to be processed, default: %(default)s")
-    parser.add_argument('--ctgStart', type=int, default=None, help="The 1-bsae starting position of the sequence to be processed")
-    parser.add_argument('--ctgEnd', type=int, default=None, help="The inclusive ending position of the sequence to be processed")
-    args = parser.parse_args()
-    if len(sys.argv[1:]) == 0:
-        parser.print_help()
-        sys.exit(1)
-    OutputVariant(args)
+    parser.add_argument('--vcf_fn', type=str, default="input.vcf", help="Truth VCF, default: %(default)s")
+    parser.add_argument('--var_fn', type=str, default="PIPE", help="Output (PIPE = standard output), default: %(default)s")
+    parser.add_argument('--ctgName', type=str, default="chr17", help="Contig to extract, default: %(default)s")
+    parser.add_argument('--ctgStart', type=int, default=None, help="First position of the region (as the reference takes it)")
+    parser.add_argument('--ctgEnd', type=int, default=None, help="Last position of the region, inclusive")
+    from . import _driver as D
+    OutputVariant(D.parse(parser))
 
 
 if __name__ == "__main__":

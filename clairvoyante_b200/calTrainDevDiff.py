@@ -1,94 +1,55 @@
-"""calTrainDevDiff -- mean training-set and validation-set loss of a list of checkpoints; Python-3 counterpart of reference
-clairvoyante/calTrainDevDiff.py (same command line, :80-110).  One `getLossNoRT` per batch of predictBatchSize runs on a
-thread while the next batch is decompressed (:55-72); like the reference, a batch's loss is booked as "validation" when the
-dataset pointer AFTER fetching the following batch has reached validationStart (:70-71)."""
+"""calTrainDevDiff -- mean training-set and validation-set loss of a list of checkpoints; counterpart of reference
+clairvoyante/calTrainDevDiff.py (same options, :80-110).  One getLossNoRT per batch of predictBatchSize, overlapped with the
+next fetch (:55-72).  Kept from the reference: a batch's loss counts as "validation" when the reader -- which already
+stands behind the batch being evaluated -- has reached validationStart (:70-71); the batch before the split is shortened to
+end on it, the batches behind it are aligned to multiples of predictBatchSize (:61-64); the last batch is evaluated after
+the loop (:73-76)."""
 import argparse
-import os
 import sys
-from threading import Thread
 
-from . import param
+from . import _driver as D, param
 
 
 def Run(args):
-    if args.v2:
-        sys.exit("clairvoyante_b200 implements the v3 / v3_slim networks only (--v2 is out of scope)")
-    from . import utils_v2 as utils
-    if args.slim:
-        from . import clairvoyante_v3_slim as cv
-    else:
-        from . import clairvoyante_v3 as cv
-    utils.SetupEnv()
-    m = cv.Clairvoyante()
-    m.init()
+    m, utils = D.new_model(args)
     CalcAll(args, m, utils)
 
 
 def CalcAll(args, m, utils):
-    if args.bin_fn is not None:
-        total, XBlocks, YBlocks, _ = utils.load_bin(args.bin_fn)
-    else:
-        total, XBlocks, YBlocks, _ = utils.GetTrainingArray(args.tensor_fn, args.var_fn, args.bed_fn)
-    trainingTotal = int(total * param.trainingDatasetPercentage)
-    validationStart = trainingTotal + 1
-    numValItems = total - validationStart
+    data = D.TrainingSet(args, utils)
+
+    def rows_after(at):
+        size = param.predictBatchSize
+        if at < data.validationStart and data.validationStart - at < size:
+            return data.validationStart - at
+        if at >= data.validationStart and at % size != 0:
+            return size - at % size
+        return size
+
     results = []
-    for n in args.chkpnt_fn:
-        m.restoreParameters(os.path.abspath(n))
-        datasetPtr = 0
-        trainingLost = validationLost = 0
-        predictBatchSize = param.predictBatchSize
-        XBatch, XNum, _ = utils.DecompressArray(XBlocks, datasetPtr, predictBatchSize, total)
-        YBatch, YNum, _ = utils.DecompressArray(YBlocks, datasetPtr, predictBatchSize, total)
-        datasetPtr += XNum
-        while True:
-            worker = Thread(target=m.getLossNoRT, args=(XBatch, YBatch))
-            worker.start()
-            predictBatchSize = param.predictBatchSize
-            if datasetPtr < validationStart and (validationStart - datasetPtr) < predictBatchSize:
-                predictBatchSize = validationStart - datasetPtr
-            elif datasetPtr >= validationStart and (datasetPtr % predictBatchSize) != 0:
-                predictBatchSize = predictBatchSize - (datasetPtr % predictBatchSize)
-            XBatch2, XNum2, XEndFlag2 = utils.DecompressArray(XBlocks, datasetPtr, predictBatchSize, total)
-            YBatch2, YNum2, YEndFlag2 = utils.DecompressArray(YBlocks, datasetPtr, predictBatchSize, total)
-            if XNum2 != YNum2 or XEndFlag2 != YEndFlag2:
-                sys.exit("Inconsistency between decompressed arrays: %d/%d" % (XNum2, YNum2))
-            worker.join()
-            XBatch, YBatch = XBatch2, YBatch2
-            if datasetPtr >= validationStart:
-                validationLost += m.getLossLossRTVal
-            else:
-                trainingLost += m.getLossLossRTVal
-            if XEndFlag2 != 0:
-                m.getLossNoRT(XBatch, YBatch)
-                if datasetPtr >= validationStart:
-                    validationLost += m.getLossLossRTVal
-                else:
-                    trainingLost += m.getLossLossRTVal
-                print("%s\t%.10f\t%.10f" % (n, trainingLost / trainingTotal, validationLost / numValItems), file=sys.stderr)
-                results.append((n, trainingLost / trainingTotal, validationLost / numValItems))
-                break
-            datasetPtr += XNum2
+    for name in args.chkpnt_fn:
+        m.restoreParameters(D.absolute(name))
+        sums = {True: 0, False: 0}                 # keyed by "counts as validation"
+        w = D.Walk(data, param.predictBatchSize, rows_after, lambda at: m.getLossNoRT)
+        for at, _method in w:
+            sums[at >= data.validationStart] += m.getLossLossRTVal
+        X, Y, at = w.tail
+        m.getLossNoRT(X, Y)
+        # (the reference tests the pointer BEFORE it moves past the last batch, :75)
+        last_at = at - len(X)
+        sums[last_at >= data.validationStart] += m.getLossLossRTVal
+        line = (name, sums[False] / data.trainingTotal, sums[True] / data.numValItems)
+        print("%s\t%.10f\t%.10f" % line, file=sys.stderr)
+        results.append(line)
     return results
 
 
 def main():
     parser = argparse.ArgumentParser(description="Calculate the loss different between training dataset and validation dataset")
-    parser.add_argument('--bin_fn', type=str, default=None,
-                        help="Binary tensor input generated by tensor2Bin.py, tensor_fn, var_fn and bed_fn will be ignored")
-    parser.add_argument('--tensor_fn', type=str, default="vartensors", help="Tensor input")
-    parser.add_argument('--var_fn', type=str, default="truthvars", help="Truth variants list input")
-    parser.add_argument('--bed_fn', type=str, default=None, help="High confident genome regions input in the BED format")
-    parser.add_argument('--chkpnt_fn', nargs='+', type=str, default=None, help="Input a list of checkpoint for calculation")
-    parser.add_argument('--v3', type=param.str2bool, nargs='?', const=True, default=True, help="Use Clairvoyante version 3")
-    parser.add_argument('--v2', type=param.str2bool, nargs='?', const=True, default=False, help="Use Clairvoyante version 2")
-    parser.add_argument('--slim', type=param.str2bool, nargs='?', const=True, default=False,
-                        help="Train using the slim version of Clairvoyante, optional")
-    args = parser.parse_args()
-    if len(sys.argv[1:]) == 0:
-        parser.print_help()
-        sys.exit(1)
-    Run(args)
+    D.dataset_options(parser)
+    parser.add_argument('--chkpnt_fn', nargs='+', type=str, default=None, help="Checkpoints to evaluate")
+    D.variant_options(parser)
+    Run(D.parse(parser))
 
 
 if __name__ == "__main__":

@@ -1,100 +1,89 @@
 """callVarBamParallel -- print one callVarBam command per genome chunk; counterpart of reference
-clairvoyante/callVarBamParallel.py with the same command line (:92-145) and the same chunking (:66-89): contigs of the
-`.fai` index (major contigs unless --includingAllContigs) cut into --refChunkSize pieces, chunks without BED coverage
-skipped.  The printed commands run `python -m clairvoyante_b200.callVarBam`, one process per chunk on one GPU each
-(`CVB_DEVICE` / `CUDA_VISIBLE_DEVICES` select it): sites are independent, no collective."""
+clairvoyante/callVarBamParallel.py (same options, :92-145; same chunking, :66-89): the contigs of the `.fai` index (the
+major ones unless --includingAllContigs) are cut into --refChunkSize pieces and pieces without BED coverage are left out.
+The commands run `python -m clairvoyante_b200.callVarBam`, one process per chunk on one GPU each (`CVB_DEVICE` /
+`CUDA_VISIBLE_DEVICES` select it): sites are independent, there is no collective."""
 import argparse
 import gzip
 import os
 import sys
 
-from . import param
+from . import _driver as D, param
 
-majorContigs = {"chr" + str(a) for a in list(range(0, 23)) + ["X", "Y"]}.union({str(a) for a in list(range(0, 23)) + ["X", "Y"]})
+_NUMBERED = [str(i) for i in range(23)] + ["X", "Y"]
+majorContigs = set(_NUMBERED) | {"chr" + c for c in _NUMBERED}
 
 
-def _check(fn, sfx=""):
-    if not os.path.isfile(fn + sfx):
-        sys.exit("Error: %s not found" % (fn + sfx))
+def _existing(fn, suffix=""):
+    if not os.path.isfile(fn + suffix):
+        sys.exit("Error: %s not found" % (fn + suffix))
     return os.path.abspath(fn)
 
 
+def _bed_intervals(bed_fn):
+    """{contig: [(begin, end)]} with the reference's end - 1 and never-empty rule (:56-60)"""
+    covered = {}
+    with (gzip.open if bed_fn.endswith(".gz") else open)(bed_fn, "rt") as f:
+        for fields in (line.split() for line in f):
+            if len(fields) >= 3:
+                lo, hi = int(fields[1]), int(fields[2]) - 1
+                covered.setdefault(fields[0], []).append((lo, hi + 1 if hi == lo else hi))
+    return covered
+
+
+def _chunks(fai_fn, size, every_contig):
+    """(contig, start, end) pieces in index order"""
+    with open(fai_fn) as fai:
+        for fields in (line.strip().split("\t") for line in fai):
+            if not every_contig and fields[0] not in majorContigs:
+                continue
+            length = int(fields[1])
+            for start in range(0, length, size):
+                yield fields[0], start, min(start + size, length)
+
+
 def commands(args):
-    chkpnt_fn = os.path.abspath(args.chkpnt_fn)
-    bam_fn, ref_fn = _check(args.bam_fn), _check(args.ref_fn)
-    fai_fn = _check(args.ref_fn, ".fai") + ".fai"
-    bed_fn = _check(args.bed_fn) if args.bed_fn is not None else None
-    tree = {}
-    if bed_fn is not None:                                              # :51-64
-        opener = gzip.open if bed_fn.endswith(".gz") else open
-        with opener(bed_fn, "rt") as f:
-            for row in f:
-                row = row.strip().split()
-                if len(row) < 3:
-                    continue
-                begin, end = int(row[1]), int(row[2]) - 1
-                if end == begin:
-                    end += 1
-                tree.setdefault(row[0], []).append((begin, end))
-    tail = " ".join(x for x in ("--vcf_fn %s" % _check(args.vcf_fn) if args.vcf_fn is not None else "",
-                                "--considerleftedge" if args.considerleftedge else "",
-                                "--qual %d" % args.qual if args.qual else "", "--slim" if args.slim else "") if x)
-    out = []
-    for line in open(fai_fn):                                            # :66-89
-        fields = line.strip().split("\t")
-        chromName = fields[0]
-        if not args.includingAllContigs and str(chromName) not in majorContigs:
+    model = os.path.abspath(args.chkpnt_fn)
+    bam, ref = _existing(args.bam_fn), _existing(args.ref_fn)
+    _existing(args.ref_fn, ".fai")
+    bed = _existing(args.bed_fn) if args.bed_fn is not None else None
+    covered = _bed_intervals(bed) if bed else None
+    extras = [("--vcf_fn %s" % _existing(args.vcf_fn)) if args.vcf_fn is not None else "", "--considerleftedge" if args.considerleftedge else "",
+              ("--qual %d" % args.qual) if args.qual else "", "--slim" if args.slim else ""]
+    lines = []
+    for contig, start, end in _chunks(ref + ".fai", args.refChunkSize, args.includingAllContigs):
+        if covered is not None and not any(lo < end and hi > start for lo, hi in covered.get(contig, ())):   # tree.search(start, end) empty
             continue
-        regionStart, chromLength = 0, int(fields[1])
-        while regionStart < chromLength:
-            start, end = regionStart, min(regionStart + args.refChunkSize, chromLength)
-            output_fn = "%s.%s_%d_%d.vcf" % (args.output_prefix, chromName, regionStart, end)
-            bed_part = ""
-            if bed_fn is not None:
-                if not any(b < end and e > start for b, e in tree.get(chromName, [])):   # len(tree.search(start, end)) == 0
-                    regionStart = end
-                    continue
-                bed_part = "--bed_fn %s " % bed_fn
-            out.append("python -m clairvoyante_b200.callVarBam --chkpnt_fn %s --ref_fn %s --bam_fn %s %s--ctgName %s --ctgStart %d "
-                       "--ctgEnd %d --call_fn %s --threshold %f --minCoverage %f --samtools %s --sampleName %s %s"
-                       % (chkpnt_fn, ref_fn, bam_fn, bed_part, chromName, regionStart, end, output_fn, args.threshold,
-                          args.minCoverage, args.samtools, args.sampleName, tail))
-            regionStart = end
-    return [c.rstrip() for c in out]
+        opts = ["--chkpnt_fn", model, "--ref_fn", ref, "--bam_fn", bam] + (["--bed_fn", bed] if bed else []) + [
+            "--ctgName", contig, "--ctgStart", str(start), "--ctgEnd", str(end),
+            "--call_fn", "%s.%s_%d_%d.vcf" % (args.output_prefix, contig, start, end), "--threshold", "%f" % args.threshold,
+            "--minCoverage", "%f" % args.minCoverage, "--samtools", args.samtools, "--sampleName", args.sampleName]
+        lines.append(" ".join(["python -m clairvoyante_b200.callVarBam"] + opts + [x for x in extras if x]))
+    return lines
 
 
 def main():
-    parser = argparse.ArgumentParser(
-        description="Create commands for calling variants in parallel using a trained Clairvoyante model and a BAM file")
-    parser.add_argument('--chkpnt_fn', type=str, default=None, help="Input a Clairvoyante model")
-    parser.add_argument('--ref_fn', type=str, default="ref.fa", help="Reference fasta file input, default: %(default)s")
-    parser.add_argument('--bed_fn', type=str, default=None, help="Call variant only in these regions, optional, default: whole genome")
-    parser.add_argument('--refChunkSize', type=int, default=10000000,
-                        help="Divide job with smaller genome chunk size for parallelism, default: %(default)s")
-    parser.add_argument('--bam_fn', type=str, default="bam.bam", help="BAM file input, default: %(default)s")
-    parser.add_argument('--vcf_fn', type=str, default=None, help="Candidate sites VCF file input, optional")
-    parser.add_argument('--output_prefix', type=str, default=None, help="Output prefix")
-    parser.add_argument('--includingAllContigs', type=param.str2bool, nargs='?', const=True, default=False,
-                        help="Call variants on all contigs, default: chr{1..22,X,Y} and {1..22,X,Y}")
-    parser.add_argument('--tensorflowThreads', type=int, default=4, help="(ignored: no TensorFlow)")
-    parser.add_argument('--threshold', type=float, default=0.2,
-                        help="Minimum allele frequence of the 1st non-reference allele for a site to be considered as a condidate "
-                             "site, default: %(default)f")
-    parser.add_argument('--minCoverage', type=float, default=4, help="Minimum coverage required to call a variant, default: %(default)d")
-    parser.add_argument('--qual', type=int, default=None,
-                        help="If set, variant with equal or higher quality will be marked PASS, or LowQual otherwise, optional")
-    parser.add_argument('--sampleName', type=str, default="SAMPLE", help="Define the sample name to be shown in the VCF file")
-    parser.add_argument('--considerleftedge', type=param.str2bool, nargs='?', const=True, default=True,
-                        help="Count the left-most base-pairs of a read for coverage, default: %(default)s")
-    parser.add_argument('--samtools', type=str, default="samtools", help="Path to the 'samtools', default: %(default)s")
-    parser.add_argument('--pypy', type=str, default="pypy", help="(ignored)")
-    parser.add_argument('--delay', type=int, default=10, help="(ignored)")
-    parser.add_argument('--slim', type=param.str2bool, nargs='?', const=True, default=False, help="Use the slim model")
-    args = parser.parse_args()
-    if len(sys.argv[1:]) == 0:
-        parser.print_help()
-        sys.exit(1)
-    print("\n".join(commands(args)))
+    parser = argparse.ArgumentParser(description="Create commands for calling variants in parallel using a trained Clairvoyante model and a BAM file")
+    add = parser.add_argument
+    add('--chkpnt_fn', type=str, default=None, help="Model checkpoint")
+    add('--ref_fn', type=str, default="ref.fa", help="Reference FASTA (with .fai), default: %(default)s")
+    add('--bed_fn', type=str, default=None, help="Only chunks touching these regions, optional")
+    add('--refChunkSize', type=int, default=10000000, help="Chunk length, default: %(default)s")
+    add('--bam_fn', type=str, default="bam.bam", help="Alignments, default: %(default)s")
+    add('--vcf_fn', type=str, default=None, help="Candidate sites VCF passed on to callVarBam, optional")
+    add('--output_prefix', type=str, default=None, help="Prefix of the per-chunk VCF names")
+    add('--includingAllContigs', type=param.str2bool, nargs='?', const=True, default=False, help="All contigs of the index, not only 1-22, X, Y")
+    add('--tensorflowThreads', type=int, default=4, help="(ignored: no TensorFlow)")
+    add('--threshold', type=float, default=0.2, help="Candidate allele-frequency threshold, default: %(default)f")
+    add('--minCoverage', type=float, default=4, help="Candidate minimum coverage, default: %(default)d")
+    add('--qual', type=int, default=None, help="PASS / LowQual cut, optional")
+    add('--sampleName', type=str, default="SAMPLE", help="Sample column of the VCF")
+    add('--considerleftedge', type=param.str2bool, nargs='?', const=True, default=True, help="Passed on to callVarBam, default: %(default)s")
+    add('--samtools', type=str, default="samtools", help="samtools executable, default: %(default)s")
+    add('--pypy', type=str, default="pypy", help="(ignored)")
+    add('--delay', type=int, default=10, help="(ignored)")
+    add('--slim', type=param.str2bool, nargs='?', const=True, default=False, help="slim network")
+    print("\n".join(commands(D.parse(parser))))
 
 
 if __name__ == "__main__":

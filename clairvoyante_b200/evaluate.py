@@ -10,24 +10,15 @@ import time
 
 import numpy as np
 
-from . import param
+from . import _driver as D, param
 
 logging.basicConfig(format='%(message)s', level=logging.INFO)
 
 
 def Run(args):
     logging.info("Loading model ...")
-    if args.v2:
-        sys.exit("clairvoyante_b200 implements the v3 / v3_slim networks only (--v2 is out of scope)")
-    from . import utils_v2 as utils
-    if args.slim:
-        from . import clairvoyante_v3_slim as cv
-    else:
-        from . import clairvoyante_v3 as cv
-    utils.SetupEnv()
-    m = cv.Clairvoyante()
-    m.init()
-    m.restoreParameters(os.path.abspath(args.chkpnt_fn))
+    m, utils = D.new_model(args)
+    m.restoreParameters(D.absolute(args.chkpnt_fn))
     Test(args, m, utils)
 
 
@@ -84,21 +75,10 @@ def Test(args, m, utils):
 
 def main():
     parser = argparse.ArgumentParser(description="Evaluate trained Clairvoyante model")
-    parser.add_argument('--bin_fn', type=str, default=None,
-                        help="Binary tensor input generated by tensor2Bin.py, tensor_fn, var_fn and bed_fn will be ignored")
-    parser.add_argument('--tensor_fn', type=str, default="vartensors", help="Tensor input")
-    parser.add_argument('--var_fn', type=str, default="truthvars", help="Truth variants list input")
-    parser.add_argument('--bed_fn', type=str, default=None, help="High confident genome regions input in the BED format")
-    parser.add_argument('--chkpnt_fn', type=str, default=None, help="Input a checkpoint for testing")
-    parser.add_argument('--v3', type=param.str2bool, nargs='?', const=True, default=True, help="Use Clairvoyante version 3")
-    parser.add_argument('--v2', type=param.str2bool, nargs='?', const=True, default=False, help="Use Clairvoyante version 2")
-    parser.add_argument('--slim', type=param.str2bool, nargs='?', const=True, default=False,
-                        help="Train using the slim version of Clairvoyante, optional")
-    args = parser.parse_args()
-    if len(sys.argv[1:]) == 0:
-        parser.print_help()
-        sys.exit(1)
-    Run(args)
+    D.dataset_options(parser)
+    parser.add_argument('--chkpnt_fn', type=str, default=None, help="Checkpoint to evaluate")
+    D.variant_options(parser)
+    Run(D.parse(parser))
 
 
 if __name__ == "__main__":

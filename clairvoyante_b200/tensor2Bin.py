@@ -5,9 +5,8 @@ i.e. what the reference itself writes, so that the file also loads in the refere
 import argparse
 import logging
 import pickle
-import sys
 
-from . import param
+from . import _driver as D, param
 
 logging.basicConfig(format='%(message)s', level=logging.INFO)
 
@@ -29,19 +28,11 @@ def Run(args):
 
 def main():
     parser = argparse.ArgumentParser(description="Generate a binary format input tensor")
-    parser.add_argument('--tensor_fn', type=str, default="vartensors", help="Tensor input")
-    parser.add_argument('--var_fn', type=str, default="truthvars", help="Truth variants list input")
-    parser.add_argument('--bed_fn', type=str, default=None, help="High confident genome regions input in the BED format")
-    parser.add_argument('--bin_fn', type=str, default=None, help="Output a binary tensor file")
+    D.dataset_options(parser)                    # here --bin_fn names the OUTPUT
     parser.add_argument('--blosc', type=param.str2bool, nargs='?', const=True, default=False,
                         help="Shuffled frames + protocol-2 outer pickles, exactly like the reference (default: unshuffled frames)")
-    parser.add_argument('--v3', type=param.str2bool, nargs='?', const=True, default=True, help="Use Clairvoyante version 3")
-    parser.add_argument('--v2', type=param.str2bool, nargs='?', const=True, default=False, help="Use Clairvoyante version 2")
-    args = parser.parse_args()
-    if len(sys.argv[1:]) == 0:
-        parser.print_help()
-        sys.exit(1)
-    Run(args)
+    D.variant_options(parser)
+    Run(D.parse(parser))
 
 
 if __name__ == "__main__":

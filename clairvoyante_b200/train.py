@@ -11,31 +11,20 @@ the same command line (train.py:225-259) and the same schedule:
 """
 import argparse
 import logging
-import os
-import sys
 import time
-from threading import Thread
 
 import numpy as np
 
-from . import param
+from . import _driver as D, param
 
 logging.basicConfig(format='%(message)s', level=logging.INFO)
 
 
 def Run(args):
-    if args.v2:
-        sys.exit("clairvoyante_b200 implements the v3 / v3_slim networks only (--v2 is out of scope)")
-    from . import utils_v2 as utils
-    if args.slim:
-        from . import clairvoyante_v3_slim as cv
-    else:
-        from . import clairvoyante_v3 as cv
-    utils.SetupEnv()
-    m = cv.Clairvoyante()
-    m.init()
+    logging.info("Initializing model ...")
+    m, utils = D.new_model(args)
     if args.chkpnt_fn is not None:
-        m.restoreParameters(os.path.abspath(args.chkpnt_fn))
+        m.restoreParameters(D.absolute(args.chkpnt_fn))
     TrainAll(args, m, utils)
 
 
@@ -69,63 +58,19 @@ def _confusion(pred, truth, k):
 
 def TrainAll(args, m, utils):
     logging.info("Loading the training dataset ...")
-    if args.bin_fn is not None:
-        total, XBlocks, YBlocks, posBlocks = utils.load_bin(args.bin_fn)       # noqa: F841  (positions kept for format parity)
-    else:
-        total, XBlocks, YBlocks, posBlocks = utils.GetTrainingArray(args.tensor_fn, args.var_fn, args.bed_fn)
-    logging.info("The size of training dataset: {}".format(total))
-
-    summaryWriter = m.summaryFileWriter(args.olog_dir) if args.olog_dir is not None else None
-
-    logging.info("Start training ...")
-    logging.info("Learning rate: %.2e" % m.setLearningRate(args.learning_rate))
-    logging.info("L2 regularization lambda: %.2e" % m.setL2RegularizationLambda(args.lambd))
+    data = D.TrainingSet(args, utils)
+    total, XBlocks, YBlocks = data.total, data.X, data.Y
+    summaryWriter = D.announce_training(args, m, data)
 
     validationLosses = []
     trainingStart = time.time()
-    trainingTotal = int(total * param.trainingDatasetPercentage)
-    validationStart = trainingTotal + 1
-    numValItems = total - validationStart
     switchesLeft = param.maxLearningRateSwitch
     sinceSwitch = 0
-    epoch = 1 if args.chkpnt_fn is None else int(args.chkpnt_fn[-param.parameterOutputPlaceHolder:]) + 1
-
-    def fetch(ptr, size):
-        X, nx, ex = utils.DecompressArray(XBlocks, ptr, size, total)
-        Y, ny, ey = utils.DecompressArray(YBlocks, ptr, size, total)
-        if nx != ny or ex != ey:
-            sys.exit("Inconsistency between decompressed arrays: %d/%d" % (nx, ny))
-        return X, Y, nx, ex
-
-    while epoch < param.maxEpoch:
-        epochStart = time.time()
-        trainLossSum = validationLossSum = 0
-        XBatch, YBatch, got, _ = fetch(0, param.trainBatchSize)
-        ptr = got
-        while True:
-            training = ptr < validationStart
-            worker = Thread(target=m.trainNoRT if training else m.getLossNoRT, args=(XBatch, YBatch))
-            worker.start()
-            XNext, YNext, got, endFlag = fetch(ptr, next_batch_size(ptr, validationStart))   # overlaps the model call
-            worker.join()
-            XBatch, YBatch = XNext, YNext
-            if training:
-                trainLossSum += m.trainLossRTVal
-                if summaryWriter is not None:
-                    summaryWriter.add_summary(m.trainSummaryRTVal, epoch)
-            else:
-                validationLossSum += m.getLossLossRTVal
-            ptr += got
-            if endFlag != 0:
-                break
-        validationLossSum += m.getLoss(XBatch, YBatch)
-        logging.info(" ".join([str(epoch), "Training loss:", str(trainLossSum / trainingTotal), "Validation loss: ",
-                               str(validationLossSum / numValItems)]))
-        logging.info("Epoch time elapsed: %.2f s" % (time.time() - epochStart))
+    for epoch in range(D.first_epoch(args), param.maxEpoch):
+        _, validationLossSum = D.train_validate_epoch(m, data, epoch, summaryWriter)
         validationLosses.append((validationLossSum, epoch))
         if args.ochk_prefix is not None:
-            path = "%s-%%0%dd" % (args.ochk_prefix, param.parameterOutputPlaceHolder)
-            m.saveParameters(os.path.abspath(path % epoch))
+            m.saveParameters(D.absolute(D.checkpoint_name(args.ochk_prefix, epoch)))
         sinceSwitch += 1
         if sinceSwitch >= 6 and switch_needed([v for v, _ in validationLosses]):
             switchesLeft -= 1
@@ -134,7 +79,6 @@ def TrainAll(args, m, utils):
             logging.info("New learning rate: %.2e" % m.setLearningRate())
             logging.info("New L2 regularization lambda: %.2e" % m.setL2RegularizationLambda())
             sinceSwitch = 0
-        epoch += 1
 
     logging.info("Training time elapsed: %.2f s" % (time.time() - trainingStart))
     best = sorted(validationLosses)[0][1] if validationLosses else 0
@@ -170,27 +114,10 @@ def TrainAll(args, m, utils):
 
 def main():
     parser = argparse.ArgumentParser(description="Train Clairvoyante")
-    parser.add_argument('--bin_fn', type=str, default=None,
-                        help="Binary tensor input generated by tensor2Bin.py, tensor_fn, var_fn and bed_fn will be ignored")
-    parser.add_argument('--tensor_fn', type=str, default="vartensors", help="Tensor input")
-    parser.add_argument('--var_fn', type=str, default="truthvars", help="Truth variants list input")
-    parser.add_argument('--bed_fn', type=str, default=None, help="High confident genome regions input in the BED format")
-    parser.add_argument('--chkpnt_fn', type=str, default=None, help="Input a checkpoint for testing or continue training")
-    parser.add_argument('--learning_rate', type=float, default=param.initialLearningRate,
-                        help="Set the initial learning rate, default: %(default)s")
-    parser.add_argument('--lambd', type=float, default=param.l2RegularizationLambda,
-                        help="Set the l2 regularization lambda, default: %(default)s")
-    parser.add_argument('--ochk_prefix', type=str, default=None, help="Prefix for checkpoint outputs at each learning rate change, optional")
-    parser.add_argument('--olog_dir', type=str, default=None, help="Directory for tensorboard log outputs, optional")
-    parser.add_argument('--v3', type=param.str2bool, nargs='?', const=True, default=True, help="Use Clairvoyante version 3")
-    parser.add_argument('--v2', type=param.str2bool, nargs='?', const=True, default=False, help="Use Clairvoyante version 2")
-    parser.add_argument('--slim', type=param.str2bool, nargs='?', const=True, default=False,
-                        help="Train using the slim version of Clairvoyante, optional")
-    args = parser.parse_args()
-    if len(sys.argv[1:]) == 0:
-        parser.print_help()
-        sys.exit(1)
-    Run(args)
+    D.dataset_options(parser)
+    D.optimiser_options(parser)
+    D.variant_options(parser)
+    Run(D.parse(parser))
 
 
 if __name__ == "__main__":

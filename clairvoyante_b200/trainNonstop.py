@@ -1,118 +1,43 @@
-"""trainNonstop -- train at a fixed learning rate, one checkpoint per epoch, until maxEpoch; Python-3 counterpart of
-reference clairvoyante/trainNonstop.py with the same command line (trainNonstop.py:131-170).  The epoch loop is train.py's
-(first 90 % trains in batches of trainBatchSize while the next batch is decompressed, the rest validates in batches of
-predictBatchSize; trainNonstop.py:78-124) without the learning-rate schedule; `--ochk_prefix` is mandatory (:31-32)."""
+"""trainNonstop -- train at a fixed learning rate, one checkpoint per epoch, until maxEpoch; counterpart of reference
+clairvoyante/trainNonstop.py (same options, :131-170): train.py's epoch (first 90 % trains, the rest validates; :78-124)
+without the learning-rate schedule.  `--ochk_prefix` is mandatory (:31-32)."""
 import argparse
 import logging
-import os
 import sys
 import time
-from threading import Thread
 
-from . import param
-from .train import next_batch_size
+from . import _driver as D, param
 
 logging.basicConfig(format='%(message)s', level=logging.INFO)
 
 
 def Run(args):
     logging.info("Initializing model ...")
-    if args.v2:
-        sys.exit("clairvoyante_b200 implements the v3 / v3_slim networks only (--v2 is out of scope)")
-    from . import utils_v2 as utils
-    if args.slim:
-        from . import clairvoyante_v3_slim as cv
-    else:
-        from . import clairvoyante_v3 as cv
-    utils.SetupEnv()
-    m = cv.Clairvoyante()
-    m.init()
+    m, utils = D.new_model(args)
     if args.ochk_prefix is None:
         sys.exit("--chk_prefix must be defined in nonstop training mode")
     if args.chkpnt_fn is not None:
-        m.restoreParameters(os.path.abspath(args.chkpnt_fn))
+        m.restoreParameters(D.absolute(args.chkpnt_fn))
     TrainAll(args, m, utils)
 
 
 def TrainAll(args, m, utils):
     logging.info("Loading the training dataset ...")
-    if args.bin_fn is not None:
-        total, XBlocks, YBlocks, _ = utils.load_bin(args.bin_fn)
-    else:
-        total, XBlocks, YBlocks, _ = utils.GetTrainingArray(args.tensor_fn, args.var_fn, args.bed_fn)
-    logging.info("The size of training dataset: {}".format(total))
-    summaryWriter = m.summaryFileWriter(args.olog_dir) if args.olog_dir is not None else None
-    logging.info("Start training ...")
-    logging.info("Learning rate: %.2e" % m.setLearningRate(args.learning_rate))
-    logging.info("L2 regularization lambda: %.2e" % m.setL2RegularizationLambda(args.lambd))
-
-    trainingStart = time.time()
-    trainingTotal = int(total * param.trainingDatasetPercentage)
-    validationStart = trainingTotal + 1
-    numValItems = total - validationStart
-    epoch = 1 if args.chkpnt_fn is None else int(args.chkpnt_fn[-param.parameterOutputPlaceHolder:]) + 1
-
-    def fetch(ptr, size):
-        X, nx, ex = utils.DecompressArray(XBlocks, ptr, size, total)
-        Y, ny, ey = utils.DecompressArray(YBlocks, ptr, size, total)
-        if nx != ny or ex != ey:
-            sys.exit("Inconsistency between decompressed arrays: %d/%d" % (nx, ny))
-        return X, Y, nx, ex
-
-    while epoch < param.maxEpoch:
-        epochStart = time.time()
-        trainLossSum = validationLossSum = 0
-        XBatch, YBatch, got, _ = fetch(0, param.trainBatchSize)
-        ptr = got
-        while True:
-            training = ptr < validationStart
-            worker = Thread(target=m.trainNoRT if training else m.getLossNoRT, args=(XBatch, YBatch))
-            worker.start()
-            XNext, YNext, got, endFlag = fetch(ptr, next_batch_size(ptr, validationStart))   # overlaps the model call
-            worker.join()
-            XBatch, YBatch = XNext, YNext
-            if training:
-                trainLossSum += m.trainLossRTVal
-                if summaryWriter is not None:
-                    summaryWriter.add_summary(m.trainSummaryRTVal, epoch)
-            else:
-                validationLossSum += m.getLossLossRTVal
-            ptr += got
-            if endFlag != 0:
-                break
-        validationLossSum += m.getLoss(XBatch, YBatch)
-        logging.info(" ".join([str(epoch), "Training loss:", str(trainLossSum / trainingTotal), "Validation loss: ",
-                               str(validationLossSum / numValItems)]))
-        logging.info("Epoch time elapsed: %.2f s" % (time.time() - epochStart))
-        path = "%s-%%0%dd" % (args.ochk_prefix, param.parameterOutputPlaceHolder)
-        m.saveParameters(os.path.abspath(path % epoch))
-        epoch += 1
-    logging.info("Training time elapsed: %.2f s" % (time.time() - trainingStart))
+    data = D.TrainingSet(args, utils)
+    writer = D.announce_training(args, m, data)
+    began = time.time()
+    for epoch in range(D.first_epoch(args), param.maxEpoch):
+        D.train_validate_epoch(m, data, epoch, writer)
+        m.saveParameters(D.absolute(D.checkpoint_name(args.ochk_prefix, epoch)))
+    logging.info("Training time elapsed: %.2f s" % (time.time() - began))
 
 
 def main():
     parser = argparse.ArgumentParser(description="Train Clairvoyante Nonstop")
-    parser.add_argument('--bin_fn', type=str, default=None,
-                        help="Binary tensor input generated by tensor2Bin.py, tensor_fn, var_fn and bed_fn will be ignored")
-    parser.add_argument('--tensor_fn', type=str, default="vartensors", help="Tensor input")
-    parser.add_argument('--var_fn', type=str, default="truthvars", help="Truth variants list input")
-    parser.add_argument('--bed_fn', type=str, default=None, help="High confident genome regions input in the BED format")
-    parser.add_argument('--chkpnt_fn', type=str, default=None, help="Input a checkpoint for testing or continue training")
-    parser.add_argument('--learning_rate', type=float, default=param.initialLearningRate,
-                        help="Set the initial learning rate, default: %(default)s")
-    parser.add_argument('--lambd', type=float, default=param.l2RegularizationLambda,
-                        help="Set the l2 regularization lambda, default: %(default)s")
-    parser.add_argument('--ochk_prefix', type=str, default=None, help="Prefix for checkpoint outputs at each learning rate change, optional")
-    parser.add_argument('--olog_dir', type=str, default=None, help="Directory for tensorboard log outputs, optional")
-    parser.add_argument('--v3', type=param.str2bool, nargs='?', const=True, default=True, help="Use Clairvoyante version 3")
-    parser.add_argument('--v2', type=param.str2bool, nargs='?', const=True, default=False, help="Use Clairvoyante version 2")
-    parser.add_argument('--slim', type=param.str2bool, nargs='?', const=True, default=False,
-                        help="Train using the slim version of Clairvoyante, optional")
-    args = parser.parse_args()
-    if len(sys.argv[1:]) == 0:
-        parser.print_help()
-        sys.exit(1)
-    Run(args)
+    D.dataset_options(parser)
+    D.optimiser_options(parser)
+    D.variant_options(parser)
+    Run(D.parse(parser))
 
 
 if __name__ == "__main__":

@@ -1,108 +1,51 @@
-"""trainWithoutValidationNonstop -- train on the WHOLE set at a fixed learning rate, a checkpoint per epoch, until maxEpoch;
-Python-3 counterpart of reference clairvoyante/trainWithoutValidationNonstop.py (same command line, :113-152).
-Reference behaviour kept: the batch fetched together with the end-of-data flag is not trained in that epoch (:93-105:
-the epoch is closed as soon as DecompressArray reports the end), i.e. the last partial batch of every epoch is skipped."""
+"""trainWithoutValidationNonstop -- every row trains, fixed learning rate, one checkpoint per epoch until maxEpoch;
+counterpart of reference clairvoyante/trainWithoutValidationNonstop.py (same options).  Kept from the reference: all batches
+are trainBatchSize rows, the LAST batch of an epoch is fetched but never trained on (the loop ends when the reader hits the
+end, :95-104), the epoch mean divides by the whole set, and the checkpoint path is used as given (not made absolute)."""
 import argparse
 import logging
-import os
 import sys
 import time
-from threading import Thread
 
-from . import param
+from . import _driver as D, param
 
 logging.basicConfig(format='%(message)s', level=logging.INFO)
 
 
 def Run(args):
     logging.info("Initializing model ...")
-    if args.v2:
-        sys.exit("clairvoyante_b200 implements the v3 / v3_slim networks only (--v2 is out of scope)")
-    from . import utils_v2 as utils
-    if args.slim:
-        from . import clairvoyante_v3_slim as cv
-    else:
-        from . import clairvoyante_v3 as cv
-    utils.SetupEnv()
-    m = cv.Clairvoyante()
-    m.init()
+    m, utils = D.new_model(args)
     if args.ochk_prefix is None:
         sys.exit("--chk_prefix must be defined in nonstop training mode")
     if args.chkpnt_fn is not None:
-        m.restoreParameters(os.path.abspath(args.chkpnt_fn))
+        m.restoreParameters(D.absolute(args.chkpnt_fn))
     TrainAll(args, m, utils)
 
 
 def TrainAll(args, m, utils):
     logging.info("Loading the training dataset ...")
-    if args.bin_fn is not None:
-        total, XBlocks, YBlocks, _ = utils.load_bin(args.bin_fn)
-    else:
-        total, XBlocks, YBlocks, _ = utils.GetTrainingArray(args.tensor_fn, args.var_fn, args.bed_fn)
-    logging.info("The size of training dataset: {}".format(total))
-    summaryWriter = m.summaryFileWriter(args.olog_dir) if args.olog_dir is not None else None
-    logging.info("Start training ...")
-    logging.info("Learning rate: %.2e" % m.setLearningRate(args.learning_rate))
-    logging.info("L2 regularization lambda: %.2e" % m.setL2RegularizationLambda(args.lambd))
-    trainingStart = time.time()
-    batchSize = param.trainBatchSize
-    epoch = 1 if args.chkpnt_fn is None else int(args.chkpnt_fn[-param.parameterOutputPlaceHolder:]) + 1
-
-    def fetch(ptr):
-        X, nx, ex = utils.DecompressArray(XBlocks, ptr, batchSize, total)
-        Y, ny, ey = utils.DecompressArray(YBlocks, ptr, batchSize, total)
-        if nx != ny or ex != ey:
-            sys.exit("Inconsistency between decompressed arrays: %d/%d" % (nx, ny))
-        return X, Y, nx, ex
-
-    while epoch < param.maxEpoch:
-        epochStart = time.time()
-        trainLossSum = 0
-        XBatch, YBatch, got, _ = fetch(0)
-        ptr = got
-        while True:
-            worker = Thread(target=m.trainNoRT, args=(XBatch, YBatch))
-            worker.start()
-            XNext, YNext, got, endFlag = fetch(ptr)              # overlaps the model call
-            worker.join()
-            XBatch, YBatch = XNext, YNext
-            trainLossSum += m.trainLossRTVal
-            if summaryWriter is not None:
-                summaryWriter.add_summary(m.trainSummaryRTVal, epoch)
-            ptr += got
-            if endFlag != 0:
-                break
-        logging.info(" ".join([str(epoch), "Training loss:", str(trainLossSum / total)]))
-        logging.info("Epoch time elapsed: %.2f s" % (time.time() - epochStart))
-        path = "%s-%%0%dd" % (args.ochk_prefix, param.parameterOutputPlaceHolder)
-        m.saveParameters(path % epoch)
-        epoch += 1
-    logging.info("Training time elapsed: %.2f s" % (time.time() - trainingStart))
+    data = D.TrainingSet(args, utils)
+    writer = D.announce_training(args, m, data)
+    began = time.time()
+    for epoch in range(D.first_epoch(args), param.maxEpoch):
+        epoch_began = time.time()
+        loss_sum = 0
+        for _at, _method in D.Walk(data, param.trainBatchSize, lambda at: param.trainBatchSize, lambda at: m.trainNoRT):
+            loss_sum += m.trainLossRTVal
+            if writer is not None:
+                writer.add_summary(m.trainSummaryRTVal, epoch)
+        logging.info(" ".join([str(epoch), "Training loss:", str(loss_sum / data.total)]))
+        logging.info("Epoch time elapsed: %.2f s" % (time.time() - epoch_began))
+        m.saveParameters(D.checkpoint_name(args.ochk_prefix, epoch))
+    logging.info("Training time elapsed: %.2f s" % (time.time() - began))
 
 
 def main():
-    parser = argparse.ArgumentParser(description="Train Clairvoyante Nonstop")
-    parser.add_argument('--bin_fn', type=str, default=None,
-                        help="Binary tensor input generated by tensor2Bin.py, tensor_fn, var_fn and bed_fn will be ignored")
-    parser.add_argument('--tensor_fn', type=str, default="vartensors", help="Tensor input")
-    parser.add_argument('--var_fn', type=str, default="truthvars", help="Truth variants list input")
-    parser.add_argument('--bed_fn', type=str, default=None, help="High confident genome regions input in the BED format")
-    parser.add_argument('--chkpnt_fn', type=str, default=None, help="Input a checkpoint for testing or continue training")
-    parser.add_argument('--learning_rate', type=float, default=param.initialLearningRate,
-                        help="Set the initial learning rate, default: %(default)s")
-    parser.add_argument('--lambd', type=float, default=param.l2RegularizationLambda,
-                        help="Set the l2 regularization lambda, default: %(default)s")
-    parser.add_argument('--ochk_prefix', type=str, default=None, help="Prefix for checkpoint outputs at each learning rate change, optional")
-    parser.add_argument('--olog_dir', type=str, default=None, help="Directory for tensorboard log outputs, optional")
-    parser.add_argument('--v3', type=param.str2bool, nargs='?', const=True, default=True, help="Use Clairvoyante version 3")
-    parser.add_argument('--v2', type=param.str2bool, nargs='?', const=True, default=False, help="Use Clairvoyante version 2")
-    parser.add_argument('--slim', type=param.str2bool, nargs='?', const=True, default=False,
-                        help="Train using the slim version of Clairvoyante, optional")
-    args = parser.parse_args()
-    if len(sys.argv[1:]) == 0:
-        parser.print_help()
-        sys.exit(1)
-    Run(args)
+    parser = argparse.ArgumentParser(description="Train Clairvoyante Nonstop without validation")
+    D.dataset_options(parser)
+    D.optimiser_options(parser)
+    D.variant_options(parser)
+    Run(D.parse(parser))
 
 
 if __name__ == "__main__":
