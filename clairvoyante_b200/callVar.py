@@ -118,26 +118,19 @@ def Test(args, m, utils):
 
 
 def main():
+    from . import _driver as D
     parser = argparse.ArgumentParser(description="Call variants using a trained Clairvoyante model and tensors of candididate variants")
-    parser.add_argument('--tensor_fn', type=str, default="PIPE", help="Tensor input, use PIPE for standard input")
-    parser.add_argument('--chkpnt_fn', type=str, default=None, help="Input a checkpoint for testing or continue training")
-    parser.add_argument('--call_fn', type=str, default=None, help="Output variant predictions")
-    parser.add_argument('--qual', type=int, default=None,
-                        help="If set, variant with equal or higher quality will be marked PASS, or LowQual otherwise, optional")
-    parser.add_argument('--sampleName', type=str, default="SAMPLE", help="Define the sample name to be shown in the VCF file")
-    parser.add_argument('--showRef', type=param.str2bool, nargs='?', const=True, default=False, help="Show reference calls, optional")
-    parser.add_argument('--ref_fn', type=str, default=None,
-                        help="Reference fasta file input, optional, print contig tags in the VCF header if set")
-    parser.add_argument('--threads', type=int, default=None, help="Number of threads, optional")
-    parser.add_argument('--v3', type=param.str2bool, nargs='?', const=True, default=True, help="Use Clairvoyante version 3")
-    parser.add_argument('--v2', type=param.str2bool, nargs='?', const=True, default=False, help="Use Clairvoyante version 2")
-    parser.add_argument('--slim', type=param.str2bool, nargs='?', const=True, default=False,
-                        help="Train using the slim version of Clairvoyante, optional")
-    args = parser.parse_args()
-    if len(sys.argv[1:]) == 0:
-        parser.print_help()
-        sys.exit(1)
-    Run(args)
+    add = parser.add_argument
+    add('--tensor_fn', type=str, default="PIPE", help="Tensor text (PIPE = standard input)")
+    add('--chkpnt_fn', type=str, default=None, help="Model checkpoint")
+    add('--call_fn', type=str, default=None, help="VCF to write")
+    add('--qual', type=int, default=None, help="Mark records PASS at or above this quality, LowQual below; optional")
+    add('--sampleName', type=str, default="SAMPLE", help="Sample column of the VCF")
+    add('--showRef', type=param.str2bool, nargs='?', const=True, default=False, help="Also write reference calls")
+    add('--ref_fn', type=str, default=None, help="Reference FASTA: its .fai supplies the ##contig header lines, optional")
+    add('--threads', type=int, default=None, help="Accepted for compatibility (TensorFlow's thread count in the reference)")
+    D.variant_options(parser)
+    Run(D.parse(parser))
 
 
 if __name__ == "__main__":
