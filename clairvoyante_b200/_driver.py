@@ -83,12 +83,16 @@ class TrainingSet(object):
         return X, Y, nx, ex
 
     def rows_wanted(self, at):
-        """size of the batch that starts at row `at` when an epoch trains and validates (train.py:95-102): full training
-        batches up to the split, then prediction-sized batches aligned to multiples of predictBatchSize"""
-        if at < self.validationStart:
-            return min(param.trainBatchSize, self.validationStart - at)
-        off = at % param.predictBatchSize
-        return param.predictBatchSize - off if off else param.predictBatchSize
+        return rows_wanted(at, self.validationStart)
+
+
+def rows_wanted(at, validationStart):
+    """size of the batch that starts at row `at` when an epoch trains and validates (train.py:95-102): full training
+    batches up to the split, then prediction-sized batches aligned to multiples of predictBatchSize"""
+    if at < validationStart:
+        return min(param.trainBatchSize, validationStart - at)
+    off = at % param.predictBatchSize
+    return param.predictBatchSize - off if off else param.predictBatchSize
 
 
 class Walk(object):

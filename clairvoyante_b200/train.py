@@ -30,11 +30,7 @@ def Run(args):
 
 def next_batch_size(ptr, validationStart):
     """rows to fetch at dataset position `ptr` (train.py:95-102)"""
-    if ptr < validationStart:
-        return min(param.trainBatchSize, validationStart - ptr) if (validationStart - ptr) < param.trainBatchSize else param.trainBatchSize
-    if ptr % param.predictBatchSize != 0:
-        return param.predictBatchSize - (ptr % param.predictBatchSize)
-    return param.predictBatchSize
+    return D.rows_wanted(ptr, validationStart)
 
 
 def switch_needed(losses):
