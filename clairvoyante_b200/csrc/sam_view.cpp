@@ -10,6 +10,10 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
+#include <thread>
+#include <vector>
+
 #include "../../include/cvb200.h"
 
 void cvb_internal_set_error(const char* msg);  // cvb200.cu
@@ -87,21 +91,63 @@ extern "C" int cvb_sam_view(const char* in, int64_t len, int final_chunk, const 
     return 1;
   }
   const size_t ctg_len = strlen(ctg_name);
-  const char* p = in;
-  const char* const e = in + len;
-  char* o = out;
-  while (p < e) {
-    const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(e - p)));
-    if (!nl && !final_chunk) break;
-    const char* le = nl ? nl : e;
-    if (keep_line(p, le, ctg_name, ctg_len, flag_mask, start, end)) {
-      memcpy(o, p, (size_t)(le - p));
-      o += le - p;
-      *o++ = '\n';  // (out needs len + 1 bytes when the final line has no newline)
+  // filter [p, e) (whole lines, except possibly the last) into o; returns the end of what was written
+  auto run = [&](const char* p, const char* e, bool last_may_lack_newline, char* o, const char** stopped) -> char* {
+    while (p < e) {
+      const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(e - p)));
+      if (!nl && !last_may_lack_newline) break;
+      const char* le = nl ? nl : e;
+      if (keep_line(p, le, ctg_name, ctg_len, flag_mask, start, end)) {
+        memcpy(o, p, (size_t)(le - p));
+        o += le - p;
+        *o++ = '\n';  // (out needs len + 1 bytes when the final line has no newline)
+      }
+      p = nl ? nl + 1 : e;
     }
-    p = nl ? nl + 1 : e;
+    *stopped = p;
+    return o;
+  };
+  const char* const e = in + len;
+  int T = (int)std::min<int64_t>(std::min<unsigned>(std::thread::hardware_concurrency(), 8u), len >> 21);  // >= 2 MB per thread
+  if (T < 2) {
+    const char* stopped = in;
+    char* o = run(in, e, final_chunk != 0, out, &stopped);
+    *out_len = o - out;
+    *consumed = stopped - in;
+    return 0;
+  }
+  // cut at line starts; every part writes to the same offset of `out` it has in `in` (output never exceeds input), then the
+  // parts are moved together
+  std::vector<const char*> cut((size_t)T + 1);
+  cut[0] = in;
+  cut[(size_t)T] = e;
+  for (int t = 1; t < T; ++t) {
+    const char* guess = in + len * t / T;
+    if (guess < cut[(size_t)t - 1]) guess = cut[(size_t)t - 1];
+    const char* nl = static_cast<const char*>(memchr(guess, '\n', (size_t)(e - guess)));
+    cut[(size_t)t] = nl ? nl + 1 : e;
+  }
+  while (T > 1 && cut[(size_t)T - 1] >= e) --T;  // (no line start left for the trailing parts: the part before them reaches the end)
+  cut[(size_t)T] = e;
+  std::vector<char*> wrote((size_t)T);
+  std::vector<const char*> stopped((size_t)T);
+  auto work = [&](int t) {
+    const bool is_last = t == T - 1;
+    wrote[(size_t)t] = run(cut[(size_t)t], cut[(size_t)t + 1], is_last ? final_chunk != 0 : true, out + (cut[(size_t)t] - in),
+                           &stopped[(size_t)t]);
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
+  char* o = wrote[0];
+  for (int t = 1; t < T; ++t) {
+    char* b = out + (cut[(size_t)t] - in);
+    const size_t n = (size_t)(wrote[(size_t)t] - b);
+    memmove(o, b, n);
+    o += n;
   }
   *out_len = o - out;
-  *consumed = p - in;
+  *consumed = stopped[(size_t)T - 1] - in;
   return 0;
 }

@@ -249,3 +249,35 @@ def test_thread_count_does_not_change_the_result(seed, opts):
                 assert len(c) > 20
             else:
                 assert np.array_equal(c, want[0]) and np.array_equal(x, want[1]) and st == want[2], (threads, chunk)
+
+
+def test_sam_text_view_large_chunks_use_threads_and_agree_with_small_chunks():
+    """chunks of several MB are filtered on more than one thread (cut at line starts, compacted afterwards): same bytes as
+    the same text filtered in small, single-threaded chunks -- with and without a final newline, with a region"""
+    import io
+    rng = np.random.default_rng(12)
+    ref, sam, _ = synth_alignments(rng, ref_len=3000, n_reads=800)
+    rows = [r for r in sam.split("\n") if r]
+    body = []
+    for k in range(80):                                    # ~10 MB, flags / contigs varied
+        for i, r in enumerate(rows):
+            f = r.split("\t")
+            if not r.startswith("@"):
+                f[1] = str([0, 16, 4, 256, 0, 0, 2048, 0][(i + k) % 8])
+                if (i + k) % 19 == 0:
+                    f[2] = "ctg2"
+            body.append("\t".join(f))
+    for tail in ("\n", "", "\nr_last\t0\tctg\t100\t60\t50M\t*\t0\t0\t" + "A" * 50 + "\t*"):
+        text = ("\n".join(body) + tail).encode()
+        assert len(text) > 8 << 20
+        for region in ((None, None), (500, 1800)):
+            def filtered(size):
+                v = CT._SamTextView(io.BytesIO(text), "ctg", *region)
+                out = []
+                while True:
+                    c = v.read(size)
+                    if not c:
+                        return b"".join(out)
+                    out.append(c)
+            small, big = filtered(100000), filtered(1 << 30)
+            assert small == big and len(small) > 1 << 20
