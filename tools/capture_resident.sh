@@ -8,4 +8,7 @@ for v in v3 slim; do
     timeout 90 python tools/ab_resident.py $v $s 2>&1 | tail -2 || echo "{\"variant\": \"$v\", \"CVB_CONV_RESIDENT\": \"$s\", \"failed\": true}"
   done
   [ "$v" = slim ] && { timeout 90 python tools/ab_resident.py slim 0 CVB_SLIM_FC4_TC=1 2>&1 | tail -2 || echo "{\"variant\": \"slim\", \"extra\": \"CVB_SLIM_FC4_TC=1\", \"failed\": true}"; }
+  for s in 0 4; do
+    timeout 120 python tools/ab_resident_train.py $v $s 2>&1 | tail -1 || echo "{\"variant\": \"$v\", \"train\": true, \"CVB_CONV_RESIDENT\": \"$s\", \"failed\": true}"
+  done
 done | tee gpurun_out/ab_resident.log
