@@ -404,8 +404,9 @@ PIPELINES = [   # as in tests/golden/make_golden_reference_run.py
 ]
 
 
+@pytest.mark.parametrize("cache_mb", ["2048", "0"], ids=["text-kept-for-pass-2", "two-passes-over-the-file"])
 @pytest.mark.parametrize("tag,sc,o", PIPELINES, ids=[p[0] for p in PIPELINES])
-def test_callvarbam_equals_the_reference_pipeline(tmp_path, monkeypatch, tag, sc, o):
+def test_callvarbam_equals_the_reference_pipeline(tmp_path, monkeypatch, tag, sc, o, cache_mb):
     """alignments -> VCF in one process (native candidates, native pile-up, callVar.Test) against the VCF that the reference's
     three stages, chained with the options callVarBam.py:113-131 gives them, wrote with the same probability table as model"""
     import types
@@ -420,6 +421,7 @@ def test_callvarbam_equals_the_reference_pipeline(tmp_path, monkeypatch, tag, sc
     if o.get("vcf"):
         open(vfn, "w").write(str(G["gettruth/vcf"]))
     monkeypatch.setattr(P, "predictBatchSize", 100)
+    monkeypatch.setenv("CVB_SAM_CACHE_MB", cache_mb)
     args = types.SimpleNamespace(chkpnt_fn=None, ref_fn=fa, bed_fn=bedfn if o.get("bed") else None, bam_fn=samfn, call_fn=out,
                                  vcf_fn=vfn if o.get("vcf") else None, threshold=o.get("threshold", 0.125),
                                  minCoverage=o.get("minCoverage", 4), qual=o.get("qual"), sampleName="SAMPLE", ctgName="ctg",
