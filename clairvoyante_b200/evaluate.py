@@ -4,8 +4,6 @@ with the same command line (evaluate.py:113-140) and the same report: top-1 / to
 in batches of predictBatchSize (:55-74)."""
 import argparse
 import logging
-import os
-import sys
 import time
 
 import numpy as np
