@@ -161,13 +161,24 @@ def GetTensorFromAlignments(sam_source, ref_seq, candidates, ctgName, num, ref_s
             c += k
             i0 += k
             if c == num:
-                X[..., 1:] -= X[..., 0:1]
-                yield 0, c, X, pos
+                yield 0, c, _subtracted_with_counts(X), pos
                 X = np.empty((num, h, 4, param.matrixNum), np.float32)
                 pos, c = [], 0
-    X = X[:c]
+    yield 1, c, _subtracted_with_counts(X[:c]), pos
+
+
+def _subtracted_with_counts(X):
+    """raw pile-up counts -> the batch GetTensor would yield (channels 1..3 relative to channel 0, utils_v2.py:46), as a
+    CountBatch that keeps the raw counts as uint8 / int16 for the narrow host->device feed (cvb_predict_host_counts_*)"""
+    from . import utils_v2
+    narrow = os.environ.get("CVB_FEED", "counts") != "fp32"
+    counts = utils_v2.pack_counts(X, subtracted=False) if narrow and len(X) else None
     X[..., 1:] -= X[..., 0:1]
-    yield 1, c, X, pos
+    if counts is None:
+        return X
+    out = X.view(utils_v2.CountBatch)
+    out.counts = counts
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -175,9 +186,9 @@ def GetTensorFromAlignments(sam_source, ref_seq, candidates, ctgName, num, ref_s
 # ------------------------------------------------------------------------------------------------
 def _read_fasta_contig(ref_fn, ctgName, start=None, end=None):
     """plain FASTA reader used when samtools is absent: bases [start, end] (1-based, inclusive) of contig ctgName"""
-    opener = gzip.open if ref_fn.endswith(".gz") else open
+    from .utils_v2 import open_maybe_gzip
     seq, on = [], False
-    with opener(ref_fn, "rt") as f:
+    with open_maybe_gzip(ref_fn) as f:
         for line in f:
             if line.startswith(">"):
                 if on:
@@ -220,10 +231,9 @@ def _load_candidates(args):
     """GetCandidate (:61-83): positions of this contig inside [ctgStart, ctgEnd]"""
     if args.can_fn == "PIPE":
         fo = sys.stdin
-    elif args.can_fn.endswith(".gz"):
-        fo = gzip.open(args.can_fn, "rt")
-    else:
-        fo = open(args.can_fn, "rt")
+    else:                      # gzip or plain by content: the reference reads with `gzip -fdc` and its own stages write
+        from .utils_v2 import open_maybe_gzip    # gzip under suffix-less names (ExtractVariantCandidates.py, GetTruth.py)
+        fo = open_maybe_gzip(args.can_fn)
     out = []
     for row in fo:
         row = row.split()
@@ -277,7 +287,8 @@ class _SamTextView(object):
 def _open_alignments(args):
     fn = args.bam_fn
     if fn.endswith(".sam") or fn.endswith(".sam.gz"):
-        fh = gzip.open(fn, "rb") if fn.endswith(".gz") else open(fn, "rb")
+        from .utils_v2 import open_maybe_gzip
+        fh = open_maybe_gzip(fn, "rb")
         return None, _SamTextView(fh, args.ctgName, args.ctgStart, args.ctgEnd if args.ctgStart is not None else None)
     if not shutil.which(args.samtools):
         sys.exit("samtools not found: pass a .sam / .sam.gz text file as --bam_fn or install samtools")

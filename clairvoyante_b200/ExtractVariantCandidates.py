@@ -99,9 +99,9 @@ def extract_candidates(sam_source, ctgName, ref_seq, ref_start=None, **opts):
 
 def _load_bed(bed_fn, ctgName):
     """:89-105 -- half-open intervals of this contig as the reference builds them"""
-    opener = gzip.open if bed_fn.endswith(".gz") else open
+    from .utils_v2 import open_maybe_gzip
     out, seen = [], set()
-    with opener(bed_fn, "rt") as f:
+    with open_maybe_gzip(bed_fn) as f:
         for row in f:
             row = row.strip().split()
             if len(row) < 3:

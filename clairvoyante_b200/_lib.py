@@ -58,21 +58,32 @@ SIGNATURES = {
     "cvb_num_parameters": (c_i64, [c_vp]),
     "cvb_set_variable": (ctypes.c_int, [c_vp, ctypes.c_char_p, ctypes.c_int, c_vp, c_i64]),
     "cvb_get_variable": (ctypes.c_int, [c_vp, ctypes.c_char_p, ctypes.c_int, c_vp, c_i64]),
+    "cvb_init_weights": (ctypes.c_int, [c_vp, ctypes.c_uint64]),
     "cvb_set_step": (ctypes.c_int, [c_vp, c_i64]),
     "cvb_get_step": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64)]),
     "cvb_set_compute_mode": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "cvb_predict_host": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cvb_predict_host_f16": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cvb_predict_device": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "cvb_predict_device_x": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp]),
+    "cvb_predict_host_counts_i16": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cvb_predict_host_counts_u8": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cvb_loss_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "cvb_train_step_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_float, ctypes.c_float,
                                            ctypes.c_float, ctypes.c_uint64, ctypes.c_int, c_vp]),
+    "cvb_set_dropout_fc5": (ctypes.c_int, [c_vp, ctypes.c_float]),
     "cvb_set_train_mode": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "cvb_grad_buffer": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64)]),
+    "cvb_nccl_unique_id": (ctypes.c_int, [c_vp]),
+    "cvb_allreduce_init": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int]),
+    "cvb_allreduce_attach": (ctypes.c_int, [c_vp, c_vp]),
+    "cvb_allreduce_gradients": (ctypes.c_int, [c_vp]),
     "cvb_get_gradient": (ctypes.c_int, [c_vp, ctypes.c_char_p, c_vp, c_i64]),
     "cvb_apply_adam": (ctypes.c_int, [c_vp, ctypes.c_float, ctypes.c_float, c_vp]),
     "cvb_parse_tensor_text": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, c_i64, ctypes.c_int, c_vp, c_vp,
                                              ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
+    "cvb_pack_counts": (ctypes.c_int, [c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_vp, c_vp,
+                                       ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "cvb_blosc_info": (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
                                       ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "cvb_blosc_decompress": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64, ctypes.POINTER(c_i64)]),

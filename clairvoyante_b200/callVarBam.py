@@ -25,9 +25,9 @@ from . import CreateTensor as CT, ExtractVariantCandidates as EVC, callVar, para
 def _vcf_positions(vcf_fn, ctgName, ctgStart, ctgEnd):
     """candidate sites from a VCF (the reference runs dataPrepScripts/GetTruth.py:47-58 for this): rows of this contig
     inside [ctgStart, ctgEnd] (ctgStart already the 1-based value)"""
-    opener = gzip.open if vcf_fn.endswith(".gz") else open
+    from .utils_v2 import open_maybe_gzip
     out = []
-    with opener(vcf_fn, "rt") as f:
+    with open_maybe_gzip(vcf_fn) as f:
         for row in f:
             row = row.strip().split()
             if not row or row[0][0] == "#" or row[0] != ctgName:

@@ -23,7 +23,8 @@ def _existing(fn, suffix=""):
 def _bed_intervals(bed_fn):
     """{contig: [(begin, end)]} with the reference's end - 1 and never-empty rule (:56-60)"""
     covered = {}
-    with (gzip.open if bed_fn.endswith(".gz") else open)(bed_fn, "rt") as f:
+    from .utils_v2 import open_maybe_gzip
+    with open_maybe_gzip(bed_fn) as f:
         for fields in (line.split() for line in f):
             if len(fields) >= 3:
                 lo, hi = int(fields[1]), int(fields[2]) - 1

@@ -61,6 +61,28 @@ __device__ __forceinline__ void st_global_256(void* p, const void* src8x32) {
                "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+// Where a site's 16 head outputs go: interleaved [n][16] (cvb_predict_device's out16), or -- base != nullptr -- the four
+// per-head arrays base [n][4], zygosity [n][2], varType [n][4], indelLength [n][6] that the reference's predict() returns
+// (clairvoyante_v3.py:257-267), so that the host path needs no de-interleave pass after the D2H copy.
+struct OutDst {
+  float* out16;
+  float *base, *zyg, *vtype, *ilen;
+};
+__host__ __device__ inline OutDst out_interleaved(float* out16) { return OutDst{out16, nullptr, nullptr, nullptr, nullptr}; }
+__device__ __forceinline__ void store_out16(const OutDst& d, int64_t site, const float (&v)[16]) {
+  if (d.base) {
+    *reinterpret_cast<float4*>(d.base + site * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float2*>(d.zyg + site * 2) = make_float2(v[4], v[5]);
+    *reinterpret_cast<float4*>(d.vtype + site * 4) = make_float4(v[6], v[7], v[8], v[9]);
+    float2* l = reinterpret_cast<float2*>(d.ilen + site * 6);
+    l[0] = make_float2(v[10], v[11]); l[1] = make_float2(v[12], v[13]); l[2] = make_float2(v[14], v[15]);
+  } else {
+    float4* o = reinterpret_cast<float4*>(d.out16 + site * 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  }
+}
+
 __device__ __forceinline__ float4 max4(float4 a, float4 b) {
   return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }

@@ -3,6 +3,7 @@
 #include "../../include/cvb200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -73,7 +74,8 @@ struct cvb_model {
   // transfer after the host has seen D2H(c-1), so every host wake-up and de-interleave shows up as a PCIe bubble.
   static constexpr int NSLOT = 4;
   float *d_x[NSLOT] = {}, *d_out[NSLOT] = {}, *d_lg[NSLOT] = {};
-  __half* d_x16[NSLOT] = {};  // fp16 input slots (cvb_predict_host_f16)
+  __half* d_x16[NSLOT] = {};  // narrow input slots (fp16 values, int16 / uint8 raw counts: cvb_predict_host_f16 / _counts_*)
+  float* d_xw = nullptr;      // fp32 scratch of one chunk for the front kernels that cannot read a narrow feed themselves
   float *h_x[NSLOT] = {}, *h_out[NSLOT] = {}, *h_lg[NSLOT] = {};
   cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t e_h2d[NSLOT], e_comp[NSLOT], e_d2h[NSLOT];
@@ -120,6 +122,10 @@ struct cvb_model {
   size_t prof_used = 0;
   TrainWork* train = nullptr;
   int train_mode = CVB_TRAIN_BF16X3;  // arithmetic of the FC4 contractions in a training step (v3)
+  void* nccl_comm = nullptr;  // data-parallel training: gradient all-reduce on s_comp inside cvb_train_step_host / cvb_apply_adam
+  bool nccl_owned = false;
+  int nccl_ranks = 1;
+  float drop5 = 0.f, drop5_now = 0.f;  // dropoutRateFC5 (cvb_set_dropout_fc5) / the rate of the pass being run (0 in getLoss)
   const float* var(const char* n) const {
     for (auto& v : vars)
       if (v.name == n) return d_params + v.offset;
@@ -172,6 +178,51 @@ static void build_vars(cvb_model* m) {
   }
 }
 
+// ------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen of the libnccl.so.2 the process already holds, e.g. torch's): the library has no
+// link-time dependency on it.  Prototypes restated from nccl.h (ncclFloat32 = 7, ncclSum = 0).
+// ------------------------------------------------------------------------------------
+struct NcclId { char internal[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*CommCount)(void*, int*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  if (api.lib) return &api;
+  const char* names[] = {getenv("CVB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* nm : names)
+    if (nm && *nm && (h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
+  if (!h) { fail("NCCL not found (dlopen libnccl.so.2: %s); set CVB_NCCL_LIB", dlerror()); return nullptr; }
+  api.GetUniqueId = (int (*)(NcclId*))dlsym(h, "ncclGetUniqueId");
+  api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+  api.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  api.CommCount = (int (*)(void*, int*))dlsym(h, "ncclCommCount");
+  api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+  api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.CommCount) {
+    fail("libnccl lacks an expected symbol");
+    return nullptr;
+  }
+  api.lib = h;
+  return &api;
+}
+#define NK(api, call)                                                                                              \
+  do {                                                                                                             \
+    int r_ = (call);                                                                                               \
+    if (r_ != 0) return fail("%s:%d %s -> NCCL error %d (%s)", __FILE__, __LINE__, #call, r_,                      \
+                             (api)->GetErrorString ? (api)->GetErrorString(r_) : "?");                             \
+  } while (0)
+
+static void nccl_release(cvb_model* m);
+static int allreduce_gradients(cvb_model* m, cudaStream_t st);
+
 extern "C" int cvb_create(int variant, int device, cvb_model** out) {
   if (!out) return fail("cvb_create: out is NULL");
   if (variant != CVB_V3 && variant != CVB_V3_SLIM) return fail("cvb_create: unknown variant %d", variant);
@@ -222,6 +273,7 @@ extern "C" int cvb_destroy(cvb_model* m) {
   cudaSetDevice(m->device);
   cudaDeviceSynchronize();
   train_work_free(m->train);
+  nccl_release(m);
   for (auto e : m->prof_events) cudaEventDestroy(e);
   cudaFree(m->d_params); cudaFree(m->d_m); cudaFree(m->d_v); cudaFree(m->d_grad);
   cudaFree(m->d_p2); cudaFree(m->d_p3); cudaFree(m->d_h4); cudaFree(m->d_h5);
@@ -229,6 +281,7 @@ extern "C" int cvb_destroy(cvb_model* m) {
   cudaFree(m->d_p3s); cudaFree(m->d_w4ts);
   cudaFree(m->d_w4t_hi); cudaFree(m->d_w4t_lo); cudaFree(m->d_absmax); cudaFree(m->d_inv_scale);
   for (int i = 0; i < cvb_model::NSLOT; ++i) {
+    if (i == 0) cudaFree(m->d_xw);
     cudaFree(m->d_x[i]); cudaFree(m->d_x16[i]); cudaFree(m->d_out[i]); cudaFree(m->d_lg[i]);
     cudaFreeHost(m->h_x[i]); cudaFreeHost(m->h_out[i]); cudaFreeHost(m->h_lg[i]);
     if (m->events) { cudaEventDestroy(m->e_h2d[i]); cudaEventDestroy(m->e_comp[i]); cudaEventDestroy(m->e_d2h[i]); }
@@ -284,6 +337,52 @@ extern "C" int cvb_get_variable(cvb_model* m, const char* name, int slot, float*
   CK(cudaMemcpy(host, base + v->offset, (size_t)n * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
+// init_op (clairvoyante_v3.py:177-178): the reference's initialisers, drawn on the host from a counter-based stream --
+// conv* / fc4 / fc5 kernels: tf.contrib.layers.variance_scaling_initializer(factor=2.0, mode='FAN_IN', uniform=False)
+// (clairvoyante_v3.py:57,72,87,106,116) = normal with stddev sqrt(1.3 * 2 / fan_in), redrawn outside +-2 sigma; head kernels:
+// tf.layers.dense's default glorot_uniform (:125-135); biases zero.  Also zeroes the Adam slots and the step counter.
+// (The reference is unseeded; the Python twin initializers.init_weights uses NumPy's generator, so the two streams differ.)
+static inline uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+extern "C" int cvb_init_weights(cvb_model* m, uint64_t seed) {
+  if (!m) return fail("cvb_init_weights: NULL model");
+  CK(cudaSetDevice(m->device));
+  std::vector<float> h((size_t)m->nparams, 0.f);
+  uint64_t ctr = 0;
+  const uint64_t key = mix64(seed + 0x9E3779B97F4A7C15ull);
+  auto uni = [&]() { return (double)(mix64(key + (++ctr) * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0); };  // [0,1)
+  for (auto& v : m->vars) {
+    if (v.name.find("bias") != std::string::npos) continue;
+    float* w = h.data() + v.offset;
+    const int64_t fan_out = v.dims[v.ndim - 1], fan_in = v.numel / fan_out;
+    if (v.name[0] == 'Y') {
+      const double limit = sqrt(6.0 / (double)(fan_in + fan_out));
+      for (int64_t i = 0; i < v.numel; ++i) w[i] = (float)((2.0 * uni() - 1.0) * limit);
+    } else {
+      const double sd = sqrt(1.3 * 2.0 / (double)fan_in);
+      for (int64_t i = 0; i < v.numel; ++i) {
+        double z;
+        do {  // Box-Muller, redrawn outside two standard deviations (tf.truncated_normal)
+          const double u1 = 1.0 - uni(), u2 = uni();
+          z = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+        } while (fabs(z) > 2.0);
+        w[i] = (float)(z * sd);
+      }
+    }
+  }
+  CK(cudaStreamSynchronize(m->s_comp));
+  const size_t pb = (size_t)m->nparams * 4;
+  CK(cudaMemcpy(m->d_params, h.data(), pb, cudaMemcpyHostToDevice));
+  CK(cudaMemset(m->d_m, 0, pb));
+  CK(cudaMemset(m->d_v, 0, pb));
+  m->step = 0;
+  m->tc_weights_dirty = true;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------
 // tensor-core path setup: TMA descriptors (driver entry point fetched through the runtime,
 // so the library has no link-time dependency on libcuda) and pre-split FC4 weights
@@ -414,7 +513,7 @@ static int tc_setup(cvb_model* m) {
     CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::Conv3Slab>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Conv3Slab::SMEM_BYTES));
     CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::Conv3SlabRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Conv3SlabRes::SMEM_BYTES));
     const char* er = getenv("CVB_CONV_RESIDENT");
-    m->tc_resident = er ? atoi(er) : 0;
+    m->tc_resident = er ? atoi(er) : 1;  // conv3's taps stay in shared memory (measured -8 %, bit-identical); conv2: no gain
     if (m->tc_merged && make_conv_merged_maps<C>(p2_hi, m->p2_rows, m->d_w3b_hi, CU_TENSOR_MAP_SWIZZLE_64B, &m->map_c3a4,
                                                  &m->map_c3b2, &m->map_c3b3, &m->map_c3b4, &m->map_c3h2, &m->map_c3h3,
                                                  &m->map_c3h4)) {
@@ -589,6 +688,12 @@ extern "C" int cvb_set_train_mode(cvb_model* m, int mode) {
   m->train_mode = mode;
   return 0;
 }
+extern "C" int cvb_set_dropout_fc5(cvb_model* m, float rate) {
+  if (!m) return fail("NULL model");
+  if (!(rate >= 0.f && rate < 1.f)) return fail("cvb_set_dropout_fc5: rate %g outside [0,1)", rate);
+  m->drop5 = rate;
+  return 0;
+}
 extern "C" int64_t cvb_kernel_launches(const cvb_model* m) { return m ? m->launches : 0; }
 
 // ------------------------------------------------------------------------------------
@@ -652,12 +757,6 @@ static int launch_conv_tc(cvb_model* m, int resident, int64_t n, cudaStream_t st
   return 0;
 }
 
-// fp16 candidate tensors (counts are integers, |x| <= 250: exact in fp16) widened to the fp32 layout the front kernels read
-__global__ void k_half_to_float(const __half2* __restrict__ in, float2* __restrict__ out, int64_t n2) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = __half22float2(in[i]);
-}
-
 static int prof_mark(cvb_model* m, cudaStream_t st) {
   if (!m->profiling) return 0;
   if (m->prof_used == m->prof_events.size()) {
@@ -669,11 +768,34 @@ static int prof_mark(cvb_model* m, cudaStream_t st) {
   return 0;
 }
 
-static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, float* logits16, cudaStream_t st) {
+// narrow feed -> fp32 scratch (only for the front kernels that do not widen on their own)
+static int widen_chunk(cvb_model* m, const void* xin, int kind, int64_t n, cudaStream_t st) {
+  if (!m->d_xw) CK(cudaMalloc(&m->d_xw, (size_t)m->alloc_sites * 528 * 4));
+  const int64_t npos = n * 132;
+  const int g = (int)std::min<int64_t>((npos + 255) / 256, (int64_t)m->num_sms * 16);
+  float4* o = reinterpret_cast<float4*>(m->d_xw);
+  if (kind == X_F16) k_widen<X_F16><<<g, 256, 0, st>>>(xin, o, npos);
+  else if (kind == X_I16) k_widen<X_I16><<<g, 256, 0, st>>>(xin, o, npos);
+  else k_widen<X_U8><<<g, 256, 0, st>>>(xin, o, npos);
+  CK(cudaGetLastError());
+  m->launches += 1;
+  return 0;
+}
+
+// one chunk (n <= CHUNK) of the forward pass on `st`; xin holds elements of `kind` (X_F32 .. X_U8)
+static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, OutDst out16, float* logits16, cudaStream_t st) {
   if (n <= 0) return 0;
   const int sms = m->num_sms;
   const bool tensor = m->compute_mode == CVB_COMPUTE_FP16X3;
   if (tensor && tc_refresh_weights(m, st)) return 1;
+  static const bool c1_reg = !(getenv("CVB_C1_REG") && getenv("CVB_C1_REG")[0] == '0');
+  const bool fused_feed = m->variant == CVB_V3 && tensor && m->tc_conv2 && c1_reg;  // k_v3_c1_reg<KIND> widens on its own
+  if (kind != X_F32 && !fused_feed) {
+    if (widen_chunk(m, xin, kind, n, st)) return 1;
+    xin = m->d_xw;
+    kind = X_F32;
+  }
+  const float* x = static_cast<const float*>(xin);
   if (prof_mark(m, st)) return 1;
   if (m->variant == CVB_V3) {
     {
@@ -685,10 +807,14 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
         auto k1 = k_v3_c1<7>;
         CK(set_smem(k1, C1K::SMEM_BYTES));
         const size_t p1_halves = (size_t)m->p1_rows * 64;
-        static const bool c1_reg = !(getenv("CVB_C1_REG") && getenv("CVB_C1_REG")[0] == '0');
         if (c1_reg) {
-          k_v3_c1_reg<<<(unsigned)((n * 16 + 127) / 128), 128, 0, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->d_p1,
-                                                                       m->d_p1 + p1_halves);
+          const unsigned g1 = (unsigned)((n * 16 + 127) / 128);
+          const float *w1 = m->var("conv1/kernel"), *b1 = m->var("conv1/bias");
+          __half *phi = m->d_p1, *plo = m->d_p1 + p1_halves;
+          if (kind == X_F32) k_v3_c1_reg<X_F32><<<g1, 128, 0, st>>>(xin, n, w1, b1, phi, plo);
+          else if (kind == X_F16) k_v3_c1_reg<X_F16><<<g1, 128, 0, st>>>(xin, n, w1, b1, phi, plo);
+          else if (kind == X_I16) k_v3_c1_reg<X_I16><<<g1, 128, 0, st>>>(xin, n, w1, b1, phi, plo);
+          else k_v3_c1_reg<X_U8><<<g1, 128, 0, st>>>(xin, n, w1, b1, phi, plo);
         } else {
           int g1 = (int)std::min<int64_t>((n + 6) / 7, 2 * sms);
           k1<<<g1, 256, C1K::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->d_p1, m->d_p1 + p1_halves);
@@ -871,19 +997,29 @@ static int forward_chunk(cvb_model* m, const float* x, int64_t n, float* out16, 
   return 0;
 }
 
-extern "C" int cvb_predict_device(cvb_model* m, const float* x, int64_t n, float* out16, float* logits16, void* stream) {
+static const int kXBytes[4] = {4, 2, 2, 1};  // element size of CVB_X_F32 / F16 / I16 / U8
+
+extern "C" int cvb_predict_device_x(cvb_model* m, const void* x, int x_kind, int64_t n, float* out16, float* logits16, void* stream) {
   if (!m) return fail("cvb_predict_device: NULL model");
   if (n < 0) return fail("cvb_predict_device: negative n");
+  if (x_kind < 0 || x_kind > 3) return fail("cvb_predict_device: unknown element kind %d", x_kind);
   if (n == 0) return 0;
   if (!x || !out16) return fail("cvb_predict_device: NULL buffer");
+  if ((uintptr_t)x & 15) return fail("cvb_predict_device: x must be 16-byte aligned");
   CK(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t CHUNK = m->CHUNK;
+  const char* xb = static_cast<const char*>(x);
   for (int64_t s = 0; s < n; s += CHUNK) {
     int64_t c = std::min<int64_t>(CHUNK, n - s);
-    if (forward_chunk(m, x + s * 528, c, out16 + s * 16, logits16 ? logits16 + s * 16 : nullptr, st)) return 1;
+    if (forward_chunk(m, xb + (size_t)s * 528 * kXBytes[x_kind], x_kind, c, out_interleaved(out16 + s * 16),
+                      logits16 ? logits16 + s * 16 : nullptr, st))
+      return 1;
   }
   return 0;
+}
+extern "C" int cvb_predict_device(cvb_model* m, const float* x, int64_t n, float* out16, float* logits16, void* stream) {
+  return cvb_predict_device_x(m, x, X_F32, n, out16, logits16, stream);
 }
 
 static int ensure_host_slots(cvb_model* m) {
@@ -914,22 +1050,35 @@ static void advise_hugepages(void* p, size_t bytes) {
   if (e > a) madvise((void*)a, e - a, MADV_HUGEPAGE);
 }
 
-static int predict_host_impl(cvb_model* m, const void* xv, bool half_in, int64_t n, float* base, float* zygosity, float* var_type,
+static int predict_host_impl(cvb_model* m, const void* xv, int kind, int64_t n, float* base, float* zygosity, float* var_type,
                              float* indel_length, float* logits16);
 
 extern "C" int cvb_predict_host(cvb_model* m, const float* x, int64_t n, float* base, float* zygosity, float* var_type,
                                 float* indel_length, float* logits16) {
-  return predict_host_impl(m, x, false, n, base, zygosity, var_type, indel_length, logits16);
+  return predict_host_impl(m, x, X_F32, n, base, zygosity, var_type, indel_length, logits16);
 }
 extern "C" int cvb_predict_host_f16(cvb_model* m, const uint16_t* x, int64_t n, float* base, float* zygosity, float* var_type,
                                     float* indel_length, float* logits16) {
-  return predict_host_impl(m, x, true, n, base, zygosity, var_type, indel_length, logits16);
+  return predict_host_impl(m, x, X_F16, n, base, zygosity, var_type, indel_length, logits16);
+}
+extern "C" int cvb_predict_host_counts_i16(cvb_model* m, const int16_t* counts, int64_t n, float* base, float* zygosity,
+                                           float* var_type, float* indel_length, float* logits16) {
+  return predict_host_impl(m, counts, X_I16, n, base, zygosity, var_type, indel_length, logits16);
+}
+extern "C" int cvb_predict_host_counts_u8(cvb_model* m, const uint8_t* counts, int64_t n, float* base, float* zygosity,
+                                          float* var_type, float* indel_length, float* logits16) {
+  return predict_host_impl(m, counts, X_U8, n, base, zygosity, var_type, indel_length, logits16);
 }
 
-static int predict_host_impl(cvb_model* m, const void* xv, bool half_in, int64_t n, float* base, float* zygosity, float* var_type,
+// The device writes a chunk's results as four per-head blocks [cap*4 | cap*2 | cap*4 | cap*6] floats (OutDst), so the way
+// back is four plain copies per chunk: straight into the caller's arrays when those are pinned, through the pinned staging
+// slot and four memcpy otherwise -- no per-site de-interleave on the host.
+static const int kHeadW[4] = {4, 2, 4, 6};
+
+static int predict_host_impl(cvb_model* m, const void* xv, int kind, int64_t n, float* base, float* zygosity, float* var_type,
                              float* indel_length, float* logits16) {
   const char* x = static_cast<const char*>(xv);
-  const size_t esz = half_in ? 2 : 4;
+  const size_t esz = (size_t)kXBytes[kind];
   if (!m) return fail("cvb_predict_host: NULL model");
   if (n < 0) return fail("cvb_predict_host: negative n");
   if (n == 0) return 0;
@@ -941,8 +1090,11 @@ static int predict_host_impl(cvb_model* m, const void* xv, bool half_in, int64_t
     advise_hugepages(var_type, (size_t)n * 16); advise_hugepages(indel_length, (size_t)n * 24);
     if (logits16) advise_hugepages(logits16, (size_t)n * 64);
   }
+  float* const heads[4] = {base, zygosity, var_type, indel_length};
   const bool pinned_in = is_pinned(x);
-  const int64_t CHUNK = m->CHUNK;
+  const bool pinned_out = is_pinned(base) && is_pinned(zygosity) && is_pinned(var_type) && is_pinned(indel_length) &&
+                          (!logits16 || is_pinned(logits16));
+  const int64_t CHUNK = m->CHUNK, cap = m->alloc_sites;
   const int64_t nchunks = (n + CHUNK - 1) / CHUNK;
   // software pipeline over chunks: the host enqueues H2D(c), kernels(c), D2H(c) and only then collects chunk c-LAG, so
   // the copy engines always have LAG chunks of work queued ahead of the host
@@ -957,23 +1109,24 @@ static int predict_host_impl(cvb_model* m, const void* xv, bool half_in, int64_t
         memcpy(m->h_x[sl], src, (size_t)cn * 528 * esz);
         src = reinterpret_cast<const char*>(m->h_x[sl]);
       }
-      if (c >= NS) CK(cudaStreamWaitEvent(m->s_h2d, m->e_comp[sl], 0));  // d_x[sl] / d_x16[sl] consumed
-      CK(cudaMemcpyAsync(half_in ? (void*)m->d_x16[sl] : (void*)m->d_x[sl], src, (size_t)cn * 528 * esz, cudaMemcpyHostToDevice,
-                         m->s_h2d));
+      void* dx = kind == X_F32 ? (void*)m->d_x[sl] : (void*)m->d_x16[sl];
+      if (c >= NS) CK(cudaStreamWaitEvent(m->s_h2d, m->e_comp[sl], 0));  // the slot's input buffer has been consumed
+      CK(cudaMemcpyAsync(dx, src, (size_t)cn * 528 * esz, cudaMemcpyHostToDevice, m->s_h2d));
       CK(cudaEventRecord(m->e_h2d[sl], m->s_h2d));
       CK(cudaStreamWaitEvent(m->s_comp, m->e_h2d[sl], 0));
       if (c >= NS) CK(cudaStreamWaitEvent(m->s_comp, m->e_d2h[sl], 0));  // d_out[sl] drained
-      if (half_in) {
-        k_half_to_float<<<m->num_sms * 8, 256, 0, m->s_comp>>>(reinterpret_cast<const __half2*>(m->d_x16[sl]),
-                                                              reinterpret_cast<float2*>(m->d_x[sl]), cn * 264);
-        CK(cudaGetLastError());
-        m->launches += 1;
-      }
-      if (forward_chunk(m, m->d_x[sl], cn, m->d_out[sl], logits16 ? m->d_lg[sl] : nullptr, m->s_comp)) return 1;
+      float* o = m->d_out[sl];
+      const OutDst dst{nullptr, o, o + cap * 4, o + cap * 6, o + cap * 10};
+      if (forward_chunk(m, dx, kind, cn, dst, logits16 ? m->d_lg[sl] : nullptr, m->s_comp)) return 1;
       CK(cudaEventRecord(m->e_comp[sl], m->s_comp));
       CK(cudaStreamWaitEvent(m->s_d2h, m->e_comp[sl], 0));
-      CK(cudaMemcpyAsync(m->h_out[sl], m->d_out[sl], (size_t)cn * 64, cudaMemcpyDeviceToHost, m->s_d2h));
-      if (logits16) CK(cudaMemcpyAsync(m->h_lg[sl], m->d_lg[sl], (size_t)cn * 64, cudaMemcpyDeviceToHost, m->s_d2h));
+      int64_t off = 0;
+      for (int h = 0; h < 4; off += cap * kHeadW[h], ++h) {
+        float* to = pinned_out ? heads[h] + s0 * kHeadW[h] : m->h_out[sl] + off;
+        CK(cudaMemcpyAsync(to, o + off, (size_t)cn * kHeadW[h] * 4, cudaMemcpyDeviceToHost, m->s_d2h));
+      }
+      if (logits16)
+        CK(cudaMemcpyAsync(pinned_out ? logits16 + s0 * 16 : m->h_lg[sl], m->d_lg[sl], (size_t)cn * 64, cudaMemcpyDeviceToHost, m->s_d2h));
       CK(cudaEventRecord(m->e_d2h[sl], m->s_d2h));
     }
     if (c >= LAG) {
@@ -981,13 +1134,12 @@ static int predict_host_impl(cvb_model* m, const void* xv, bool half_in, int64_t
       const int sl = (int)(p % NS);
       const int64_t s0 = p * CHUNK, cn = std::min<int64_t>(CHUNK, n - s0);
       CK(cudaEventSynchronize(m->e_d2h[sl]));
-      // de-interleave [base4 | zyg2 | type4 | len6] into the four arrays the reference's predict() returns
-      const float* o = m->h_out[sl];
-      float* pb = base + s0 * 4; float* pz = zygosity + s0 * 2; float* pt = var_type + s0 * 4; float* pl = indel_length + s0 * 6;
-      for (int64_t i = 0; i < cn; ++i, o += 16, pb += 4, pz += 2, pt += 4, pl += 6) {
-        memcpy(pb, o, 16); memcpy(pz, o + 4, 8); memcpy(pt, o + 6, 16); memcpy(pl, o + 10, 24);
+      if (!pinned_out) {
+        int64_t off = 0;
+        for (int h = 0; h < 4; off += cap * kHeadW[h], ++h)
+          memcpy(heads[h] + s0 * kHeadW[h], m->h_out[sl] + off, (size_t)cn * kHeadW[h] * 4);
+        if (logits16) memcpy(logits16 + s0 * 16, m->h_lg[sl], (size_t)cn * 64);
       }
-      if (logits16) memcpy(logits16 + s0 * 16, m->h_lg[sl], (size_t)cn * 64);
     }
   }
   return 0;
@@ -1335,6 +1487,20 @@ static int launch_conv_keep(cvb_model* m, const float* in, int64_t nc, const flo
   return 0;
 }
 
+// dropout5 (clairvoyante_v3.py:121): h5 -> d5 under the FC5 stream of the step's seed; returns what the heads read
+static const uint64_t kSeed5 = 0x5D5D5D5D5D5D5D5Dull;
+static int train_dropout5(cvb_model* m, int64_t nc, int n5, uint64_t seed, int64_t site0, cudaStream_t st, const float** h5in) {
+  TrainWork* w = m->train;
+  *h5in = w->h5;
+  if (m->drop5_now <= 0.f) return 0;
+  if (!w->d5) CK(cudaMalloc(&w->d5, (size_t)w->cap * 168 * 4));
+  k_dropout_fwd<<<gsz(nc * n5), 256, 0, st>>>(w->h5, w->d5, nc * n5, site0 * n5, seed ^ kSeed5, drop_const(m->drop5_now));
+  CK(cudaGetLastError());
+  m->launches += 1;
+  *h5in = w->d5;
+  return 0;
+}
+
 static int train_forward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t seed, int64_t index0, cudaStream_t st) {
   TrainWork* w = m->train;
   if (launch_conv_keep<ConvCfg<4, 8, 1, 33, 12, 8, 8>>(m, w->x, nc, m->var("conv1/kernel"), m->var("conv1/bias"), w->c1, true, st)) return 1;
@@ -1369,7 +1535,9 @@ static int train_forward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t se
     d4 = w->d4;
   }
   k_dense_small<true><<<gsz(nc * 18), 256, 0, st>>>(d4, 36, 36, m->var("fc5/kernel"), 18, m->var("fc5/bias"), w->h5, 18, nc);
-  k_heads<36, 18><<<(int)((nc + 15) / 16), 256, 0, st>>>(d4, w->h5, nc, head_ptrs(m), w->out16, w->logits);
+  const float* h5in;
+  if (train_dropout5(m, nc, 18, seed, index0 / 36, st, &h5in)) return 1;
+  k_heads<36, 18><<<(int)((nc + 15) / 16), 256, 0, st>>>(d4, h5in, nc, head_ptrs(m), out_interleaved(w->out16), w->logits);
   CK(cudaGetLastError());
   m->launches += 8 + (drop4 > 0.f ? 1 : 0);
   return 0;
@@ -1385,7 +1553,8 @@ static int train_backward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t s
   CK(cudaMemsetAsync(w->tmpb, 0, 36 * 16 * 4, st));
   CK(cudaMemsetAsync(w->tmph, 0, 24 * 16 * 4, st));
   k_gemm_tn<<<dim3(1, 1), 256, 0, st>>>(d4, 36, w->dlog, 16, w->tmpb, 16, 36, 16, nc);
-  k_gemm_tn<<<dim3(1, 1), 256, 0, st>>>(w->h5, 18, w->dlog, 16, w->tmph, 16, 18, 16, nc);
+  const float* h5in = m->drop5_now > 0.f ? w->d5 : w->h5;
+  k_gemm_tn<<<dim3(1, 1), 256, 0, st>>>(h5in, 18, w->dlog, 16, w->tmph, 16, 18, 16, nc);
   HeadG hg{gvar(m, "YBaseChangeSigmoid/kernel"), gvar(m, "YZygosityFC/kernel"), gvar(m, "YVarTypeFC/kernel"),
            gvar(m, "YIndelLengthFC/kernel")};
   k_scatter_heads<<<1, 256, 0, st>>>(w->tmpb, w->tmph, 36, 18, hg);
@@ -1395,7 +1564,8 @@ static int train_backward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t s
   k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->dlog + 10, nc, 16, 6, gvar(m, "YIndelLengthFC/bias"));
   HeadW hw{m->var("YBaseChangeSigmoid/kernel"), m->var("YZygosityFC/kernel"), m->var("YVarTypeFC/kernel"),
            m->var("YIndelLengthFC/kernel")};
-  k_heads_bwd<<<gsz(nc * (36 + 18)), 256, 0, st>>>(w->dlog, w->h5, nc, 36, 18, hw, w->g4, w->g5, 24);
+  k_heads_bwd<<<gsz(nc * (36 + 18)), 256, 0, st>>>(w->dlog, w->h5, nc, 36, 18, hw, w->g4, w->g5, 24, m->drop5_now > 0.f ? 1 : 0,
+                                                   seed ^ kSeed5, index0 / 36 * 18, drop_const(m->drop5_now));
   // FC5
   k_gemm_tn<<<dim3(1, 1), 256, 0, st>>>(d4, 36, w->g5, 24, gvar(m, "fc5/kernel"), 18, 36, 18, nc);
   k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->g5, nc, 24, 18, gvar(m, "fc5/bias"));
@@ -1537,7 +1707,9 @@ static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, i
                                                                     168);
     CK(cudaGetLastError());
   }
-  k_heads<336, 168><<<(int)((nc + 15) / 16), 256, 0, st>>>(d4, w->h5, nc, head_ptrs(m), w->out16, w->logits);
+  const float* h5in;
+  if (train_dropout5(m, nc, 168, seed, index0 / 336, st, &h5in)) return 1;
+  k_heads<336, 168><<<(int)((nc + 15) / 16), 256, 0, st>>>(d4, h5in, nc, head_ptrs(m), out_interleaved(w->out16), w->logits);
   CK(cudaGetLastError());
   m->launches += 9 + (drop4 > 0.f ? 1 : 0);
   return 0;
@@ -1558,14 +1730,16 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
   k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->dlog + 10, nc, 16, 6, gvar(m, "YIndelLengthFC/bias"));
   HeadW hw{m->var("YBaseChangeSigmoid/kernel"), m->var("YZygosityFC/kernel"), m->var("YVarTypeFC/kernel"),
            m->var("YIndelLengthFC/kernel")};
-  k_heads_bwd<<<gsz(nc * (336 + 168)), 256, 0, st>>>(w->dlog, w->h5, nc, 336, 168, hw, w->g4, w->g5, 176);
+  const float* h5in = m->drop5_now > 0.f ? w->d5 : w->h5;  // what the three softmax heads read
+  k_heads_bwd<<<gsz(nc * (336 + 168)), 256, 0, st>>>(w->dlog, w->h5, nc, 336, 168, hw, w->g4, w->g5, 176, m->drop5_now > 0.f ? 1 : 0,
+                                                     seed ^ kSeed5, index0 / 336 * 168, drop_const(m->drop5_now));
   if (tcm) {
     // weight gradients of FC5 and the four heads as two tcgen05 contractions over K = sites:
     //   tmp5 [336][184] = d4^T . [g5 | dlog]   (cols 0..167 -> fc5/kernel, 168..171 -> base head: its input is dropout4)
     //   tmph [168][16]  = h5^T . dlog          (cols 4..15 -> zygosity / varType / indelLength heads)
     const int64_t ldt = w->ldt;
     if (split_transpose_bf16(d4, nc, 336, 336, w->d4t, 336 * ldt, ldt, st)) return 1;
-    if (split_transpose_bf16(w->h5, nc, 168, 168, w->h5t, 168 * ldt, ldt, st)) return 1;
+    if (split_transpose_bf16(h5in, nc, 168, 168, w->h5t, 168 * ldt, ldt, st)) return 1;
     if (split_transpose_bf16(w->g5, nc, 168, 176, w->gct, 184 * ldt, ldt, st)) return 1;
     if (split_transpose_bf16(w->dlog, nc, 16, 16, w->gct + 168 * ldt, 184 * ldt, ldt, st)) return 1;
     // 3 and 2 output tiles only: K (= sites) is split over the SMs and the slices meet in fp32 atomics
@@ -1586,7 +1760,7 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
     CK(cudaMemsetAsync(w->tmpb, 0, 336 * 16 * 4, st));
     CK(cudaMemsetAsync(w->tmph, 0, 168 * 16 * 4, st));
     k_gemm_tn<<<dim3((336 + 63) / 64, 1), 256, 0, st>>>(d4, 336, w->dlog, 16, w->tmpb, 16, 336, 16, nc);
-    k_gemm_tn<<<dim3((168 + 63) / 64, 1), 256, 0, st>>>(w->h5, 168, w->dlog, 16, w->tmph, 16, 168, 16, nc);
+    k_gemm_tn<<<dim3((168 + 63) / 64, 1), 256, 0, st>>>(h5in, 168, w->dlog, 16, w->tmph, 16, 168, 16, nc);
     k_scatter_heads<<<(336 * 4 + 255) / 256, 256, 0, st>>>(w->tmpb, w->tmph, 336, 168, hg);
     k_gemm_tn<<<dim3((336 + 63) / 64, (168 + 63) / 64), 256, 0, st>>>(d4, 336, w->g5, 176, gvar(m, "fc5/kernel"), 168, 336, 168, nc);
   }
@@ -1762,6 +1936,7 @@ static int train_pass(cvb_model* m, const float* x, const float* y, int64_t n, f
   if (ensure_train_work(m)) return 1;
   TrainWork* w = m->train;
   cudaStream_t st = m->s_comp;
+  m->drop5_now = backward ? m->drop5 : 0.f;  // phase = False in getLoss (clairvoyante_v3.py:207-216)
   CK(cudaMemsetAsync(w->loss, 0, 16 * 4, st));
   if (backward) CK(cudaMemsetAsync(m->d_grad, 0, (size_t)(m->nparams + 16) * 4, st));
   if (train_prepare_weights(m, st, backward)) return 1;
@@ -1804,18 +1979,31 @@ extern "C" int cvb_loss_host(cvb_model* m, const float* x, const float* y, int64
   return 0;
 }
 
-static const char* kKernels[] = {"conv1/kernel", "conv2/kernel", "conv3/kernel", "fc4/kernel", "fc5/kernel",
-                                 "YBaseChangeSigmoid/kernel", "YZygosityFC/kernel", "YVarTypeFC/kernel", "YIndelLengthFC/kernel"};
-
-// loss6 = [total, loss1, loss2, loss3, loss4, lossL2] from the (possibly all-reduced) sums at d_grad[nparams..+4)
-static int finish_losses(cvb_model* m, float l2, float* loss6) {
+// finishes a step on the compute stream: one k_adam_flat launch (Adam on all 18 variables + sum of squares of the
+// pre-update kernels), then loss6 = [total, loss1, loss2, loss3, loss4, lossL2] from the (possibly all-reduced) sums at
+// d_grad[nparams..+4) -- one launch and one host synchronisation where the first version had 27 launches and two.
+extern "C" int cvb_apply_adam(cvb_model* m, float lr, float l2, float* loss6) {
+  if (!m) return fail("cvb_apply_adam: NULL model");
+  if (!m->train) return fail("cvb_apply_adam: no gradients (call cvb_train_step_host first)");
+  CK(cudaSetDevice(m->device));
   cudaStream_t st = m->s_comp;
   TrainWork* w = m->train;
+  m->step += 1;
+  const double b1 = 0.9, b2 = 0.999;
+  const float lr_t = (float)(lr * sqrt(1.0 - pow(b2, (double)m->step)) / (1.0 - pow(b1, (double)m->step)));
+  BiasRanges br;
+  br.n = 0;
+  for (auto& v : m->vars)
+    if (v.name.find("bias") != std::string::npos) {  // clairvoyante_v3.py:150
+      br.lo[br.n] = v.offset / 4;
+      br.hi[br.n] = (v.offset + (v.numel + 3) / 4 * 4) / 4;
+      ++br.n;
+    }
   CK(cudaMemsetAsync(w->loss + 8, 0, 4, st));
-  for (const char* k : kKernels) {
-    const VarInfo* v = m->info(k);
-    k_sumsq<<<gsz(v->numel), 256, 0, st>>>(m->d_params + v->offset, v->numel, w->loss + 8);
-  }
+  const int64_t n4 = m->nparams / 4;
+  k_adam_flat<<<gsz(n4), 256, 0, st>>>(reinterpret_cast<float4*>(m->d_params), reinterpret_cast<float4*>(m->d_m),
+                                       reinterpret_cast<float4*>(m->d_v), reinterpret_cast<const float4*>(m->d_grad), n4, lr_t,
+                                       (float)b1, (float)b2, 1e-8f, l2, br, w->loss + 8);
   CK(cudaGetLastError());
   float l[5];
   CK(cudaMemcpyAsync(l, m->d_grad + m->nparams, 16, cudaMemcpyDeviceToHost, st));
@@ -1826,27 +2014,7 @@ static int finish_losses(cvb_model* m, float l2, float* loss6) {
     for (int i = 0; i < 4; ++i) loss6[1 + i] = l[i];
     loss6[0] = l[0] + l[1] + l[2] + l[3] + loss6[5];
   }
-  m->launches += 9;
-  return 0;
-}
-
-extern "C" int cvb_apply_adam(cvb_model* m, float lr, float l2, float* loss6) {
-  if (!m) return fail("cvb_apply_adam: NULL model");
-  if (!m->train) return fail("cvb_apply_adam: no gradients (call cvb_train_step_host first)");
-  CK(cudaSetDevice(m->device));
-  if (finish_losses(m, l2, loss6)) return 1;  // session.run fetches the loss of the pre-update weights
-  cudaStream_t st = m->s_comp;
-  m->step += 1;
-  const double b1 = 0.9, b2 = 0.999;
-  const float lr_t = (float)(lr * sqrt(1.0 - pow(b2, (double)m->step)) / (1.0 - pow(b1, (double)m->step)));
-  for (auto& v : m->vars) {
-    const bool is_kernel = v.name.find("bias") == std::string::npos;  // clairvoyante_v3.py:150
-    k_adam<<<gsz(v.numel), 256, 0, st>>>(m->d_params + v.offset, m->d_m + v.offset, m->d_v + v.offset, m->d_grad + v.offset, v.numel,
-                                         lr_t, (float)b1, (float)b2, 1e-8f, is_kernel ? l2 : 0.f);
-  }
-  CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(st));
-  m->launches += (int64_t)m->vars.size();
+  m->launches += 1;
   m->tc_weights_dirty = true;
   return 0;
 }
@@ -1861,7 +2029,10 @@ extern "C" int cvb_train_step_host(cvb_model* m, const float* x, const float* y,
   if (train_pass(m, x, y, n, drop4, dropout_seed, true)) return 1;
   // loss sums ride at the tail of the gradient buffer so that one all-reduce covers both
   CK(cudaMemcpyAsync(m->d_grad + m->nparams, m->train->loss, 16, cudaMemcpyDeviceToDevice, m->s_comp));
-  if (apply_update) return cvb_apply_adam(m, lr, l2, loss6);
+  if (apply_update) {
+    if (allreduce_gradients(m, m->s_comp)) return 1;  // data-parallel: this rank's shard -> the global batch's sums
+    return cvb_apply_adam(m, lr, l2, loss6);
+  }
   CK(cudaStreamSynchronize(m->s_comp));
   return 0;
 }
@@ -1872,6 +2043,66 @@ extern "C" int cvb_grad_buffer(cvb_model* m, void** dev_ptr, int64_t* numel) {
   *numel = m->nparams + 4;  // gradients (16-byte aligned slots per variable) followed by the four loss sums
   return 0;
 }
+// ---- data-parallel training: the SUM all-reduce of [gradients | 4 loss sums] runs inside the library, on the compute
+// stream, between the backward pass and the optimiser kernel -- no host synchronisation and nothing on another stream
+// (the first version reduced through torch.distributed on torch's stream and had to synchronise the host before Adam).
+static void nccl_release(cvb_model* m) {
+  if (m->nccl_comm && m->nccl_owned) {
+    NcclApi* a = nccl_api();
+    if (a) a->CommDestroy(m->nccl_comm);
+  }
+  m->nccl_comm = nullptr;
+  m->nccl_owned = false;
+  m->nccl_ranks = 1;
+}
+extern "C" int cvb_nccl_unique_id(void* id128) {
+  if (!id128) return fail("cvb_nccl_unique_id: NULL argument");
+  NcclApi* a = nccl_api();
+  if (!a) return 1;
+  NK(a, a->GetUniqueId(static_cast<NcclId*>(id128)));
+  return 0;
+}
+extern "C" int cvb_allreduce_init(cvb_model* m, const void* id128, int nranks, int rank) {
+  if (!m || !id128) return fail("cvb_allreduce_init: NULL argument");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail("cvb_allreduce_init: rank %d of %d", rank, nranks);
+  NcclApi* a = nccl_api();
+  if (!a) return 1;
+  CK(cudaSetDevice(m->device));
+  nccl_release(m);
+  NcclId id;
+  memcpy(&id, id128, sizeof(id));
+  void* comm = nullptr;
+  NK(a, a->CommInitRank(&comm, nranks, id, rank));
+  m->nccl_comm = comm;
+  m->nccl_owned = true;
+  m->nccl_ranks = nranks;
+  return 0;
+}
+extern "C" int cvb_allreduce_attach(cvb_model* m, void* nccl_comm) {
+  if (!m) return fail("cvb_allreduce_attach: NULL model");
+  nccl_release(m);
+  if (!nccl_comm) return 0;
+  NcclApi* a = nccl_api();
+  if (!a) return 1;
+  int n = 0;
+  NK(a, a->CommCount(nccl_comm, &n));
+  m->nccl_comm = nccl_comm;
+  m->nccl_ranks = n;
+  return 0;
+}
+static int allreduce_gradients(cvb_model* m, cudaStream_t st) {
+  if (!m->nccl_comm || m->nccl_ranks < 2) return 0;
+  NcclApi* a = nccl_api();
+  if (!a) return 1;
+  NK(a, a->AllReduce(m->d_grad, m->d_grad, (size_t)(m->nparams + 4), 7 /* ncclFloat32 */, 0 /* ncclSum */, m->nccl_comm, st));
+  return 0;
+}
+extern "C" int cvb_allreduce_gradients(cvb_model* m) {
+  if (!m) return fail("cvb_allreduce_gradients: NULL model");
+  CK(cudaSetDevice(m->device));
+  return allreduce_gradients(m, m->s_comp);
+}
+
 extern "C" int cvb_get_gradient(cvb_model* m, const char* name, float* host, int64_t n) {
   if (!m || !name || !host) return fail("cvb_get_gradient: NULL argument");
   const VarInfo* v = m->info(name);

@@ -217,8 +217,41 @@ __device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
 __device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
   asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
 }
+// Input element kinds of the candidate tensors (include/cvb200.h CVB_X_*): fp32 / fp16 values that are already
+// channel-subtracted, or RAW int16 / uint8 counts (CreateTensor's alnCode) whose channels 1..3 are made relative to channel 0
+// here, on the device (utils_v2.py:46), while the position's four channels are widened to fp32.
+enum { X_F32 = 0, X_F16 = 1, X_I16 = 2, X_U8 = 3 };
+template <int KIND> struct XElem { static constexpr int BYTES = KIND == X_F32 ? 4 : (KIND == X_U8 ? 1 : 2); };
+// one (site, row, base) position = 4 consecutive channels -> fp32
+template <int KIND>
+__device__ __forceinline__ float4 widen_pos4(const void* __restrict__ p) {
+  if constexpr (KIND == X_F32) {
+    return *reinterpret_cast<const float4*>(p);
+  } else if constexpr (KIND == X_F16) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  } else if constexpr (KIND == X_I16) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    const float c0 = (float)(short)(v.x & 0xffff), c1 = (float)(short)(v.x >> 16), c2 = (float)(short)(v.y & 0xffff), c3 = (float)(short)(v.y >> 16);
+    return make_float4(c0, c1 - c0, c2 - c0, c3 - c0);
+  } else {
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
+    const float c0 = (float)(v & 0xff), c1 = (float)((v >> 8) & 0xff), c2 = (float)((v >> 16) & 0xff), c3 = (float)(v >> 24);
+    return make_float4(c0, c1 - c0, c2 - c0, c3 - c0);
+  }
+}
+// stand-alone widening pass for the front kernels that only read fp32 (everything except k_v3_c1_reg)
+template <int KIND>
+__global__ void k_widen(const void* __restrict__ in, float4* __restrict__ out, int64_t npos) {
+  const char* src = static_cast<const char*>(in);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npos; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = widen_pos4<KIND>(src + i * (4 * XElem<KIND>::BYTES));
+}
+
+template <int KIND>
 __global__ void __launch_bounds__(128)
-k_v3_c1_reg(const float* __restrict__ x, int64_t n, const float* __restrict__ w1g, const float* __restrict__ b1g,
+k_v3_c1_reg(const void* __restrict__ xv, int64_t n, const float* __restrict__ w1g, const float* __restrict__ b1g,
             __half* __restrict__ p1_hi, __half* __restrict__ p1_lo) {
   const int64_t gt = (int64_t)blockIdx.x * 128 + threadIdx.x;
   const int64_t site = gt >> 4;
@@ -247,12 +280,28 @@ k_v3_c1_reg(const float* __restrict__ x, int64_t n, const float* __restrict__ w1
   {
     const int lane = threadIdx.x & 31;
     const int64_t wsite0 = (gt >> 5) * 2;  // first site of this warp
-    const float* src = x + wsite0 * 528;
-    const int nchunk = (wsite0 + 1 < n) ? 264 : 132;
-    for (int c = lane; c < nchunk; c += 32) cp_async16(xs + c * 4, src + c * 4);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncwarp();
+    const int nsite = (wsite0 + 1 < n) ? 2 : 1;
+    if constexpr (KIND == X_F32) {
+      const float* src = static_cast<const float*>(xv) + wsite0 * 528;
+      for (int c = lane; c < nsite * 132; c += 32) cp_async16(xs + c * 4, src + c * 4);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncwarp();
+    } else {
+      // narrow feed: the raw bytes of the warp's two sites are staged the same way, then every lane widens its share of
+      // the (row, base) positions into the fp32 tile the row loop reads (raw counts: channel 0 subtracted here)
+      constexpr int EB = XElem<KIND>::BYTES;
+      __shared__ __align__(16) unsigned char raw_all[4][2 * 528 * EB];
+      unsigned char* raw = raw_all[threadIdx.x >> 5];
+      const unsigned char* src = static_cast<const unsigned char*>(xv) + wsite0 * (528 * EB);
+      for (int c = lane; c < nsite * (33 * EB); c += 32) cp_async16(raw + c * 16, src + c * 16);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncwarp();
+      for (int c = lane; c < nsite * 132; c += 32)
+        *reinterpret_cast<float4*>(xs + c * 4) = widen_pos4<KIND>(raw + c * (4 * EB));
+      __syncwarp();
+    }
   }
   if (site >= n) return;  // odd tail: the second half-warp has no site
   const ulonglong2* xp = reinterpret_cast<const ulonglong2*>(xs + ((gt >> 4) & 1) * 528);
@@ -608,7 +657,7 @@ struct HeadPtrs {
 // ------------------------------------------------------------------------------------
 template <int N4, int N5>
 __global__ void __launch_bounds__(256)
-k_heads(const float* __restrict__ h4, const float* __restrict__ h5, int64_t n, HeadPtrs hp, float* __restrict__ out16,
+k_heads(const float* __restrict__ h4, const float* __restrict__ h5, int64_t n, HeadPtrs hp, OutDst out16,
         float* __restrict__ logits16) {
   __shared__ float lg[16 * 16];
   const int tid = threadIdx.x;
@@ -669,9 +718,7 @@ k_heads(const float* __restrict__ h4, const float* __restrict__ h5, int64_t n, H
         for (int k = a; k < b; ++k) ov[k] *= inv;
       };
       sm(4, 6); sm(6, 10); sm(10, 16);
-      float4* d = reinterpret_cast<float4*>(out16 + st * 16);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) d[k] = make_float4(ov[4 * k], ov[4 * k + 1], ov[4 * k + 2], ov[4 * k + 3]);
+      store_out16(out16, st, ov);
       if (logits16) {
         float4* dl = reinterpret_cast<float4*>(logits16 + st * 16);
 #pragma unroll
@@ -683,7 +730,7 @@ k_heads(const float* __restrict__ h4, const float* __restrict__ h5, int64_t n, H
 
 template <int N4, int N5, int TS>
 __global__ void __launch_bounds__(256, 2)
-k_tail(const float* __restrict__ h4, int64_t n, HeadPtrs hp, float* __restrict__ out16, float* __restrict__ logits16) {
+k_tail(const float* __restrict__ h4, int64_t n, HeadPtrs hp, OutDst out16, float* __restrict__ logits16) {
   constexpr int L4 = N4 + 4, L5 = N5 + 4;
   __shared__ __align__(16) float h4s[TS * L4];
   __shared__ __align__(16) float h5s[TS * L5];
@@ -753,9 +800,7 @@ k_tail(const float* __restrict__ h4, int64_t n, HeadPtrs hp, float* __restrict__
       for (int k = a; k < b; ++k) o[k] *= inv;
     };
     sm(4, 6); sm(6, 10); sm(10, 16);
-    float4* d = reinterpret_cast<float4*>(out16 + (site0 + tid) * 16);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) d[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+    store_out16(out16, site0 + tid, o);
     if (logits16) {
       float4* dl = reinterpret_cast<float4*>(logits16 + (site0 + tid) * 16);
 #pragma unroll

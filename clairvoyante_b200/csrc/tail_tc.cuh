@@ -56,7 +56,7 @@ struct TailHeads { const float *b5, *bb, *wz, *bz, *wt, *bt, *wl, *bl; };
 __global__ void __launch_bounds__(TailTc::THREADS, 1)
 k_tail_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
           const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, int64_t n,
-          TailHeads hp, const float* __restrict__ inv_scale, float* __restrict__ out16, float* __restrict__ logits16) {
+          TailHeads hp, const float* __restrict__ inv_scale, OutDst out16, float* __restrict__ logits16) {
   using F = TailTc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -212,9 +212,7 @@ k_tail_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
 #pragma unroll
         for (int k = 10; k < 16; ++k) ov[k] *= inv;
       }
-      float4* d = reinterpret_cast<float4*>(out16 + site * 16);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) d[k] = make_float4(ov[4 * k], ov[4 * k + 1], ov[4 * k + 2], ov[4 * k + 3]);
+      store_out16(out16, site, ov);
       if (logits16) {
         float4* dl = reinterpret_cast<float4*>(logits16 + site * 16);
 #pragma unroll

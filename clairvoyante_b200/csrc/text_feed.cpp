@@ -201,3 +201,48 @@ extern "C" int64_t cvb_tensor_text_positions(const char* buf, const int64_t* met
   }
   return o - out;
 }
+
+// Narrow feed (cvb_predict_host_counts_i16 / _u8): fp32 candidate tensors -> the RAW counts they were built from, as int16
+// (and, when the caller asks, uint8).  x holds n_pos (row, base) positions of 4 channels; subtracted != 0 means channels
+// 1..3 are already relative to channel 0 (what GetTensor yields, utils_v2.py:46) and the raw count is x_i + x_0.  The
+// conversion is only valid for tensors of non-negative integers: *exact = 0 if any value is not an integer in [0, 32767]
+// (the caller then keeps the fp32 feed), *max_count = the largest count seen (<= 255: the uint8 buffer is usable).
+extern "C" int cvb_pack_counts(const float* x, int64_t n_pos, int subtracted, int threads, int16_t* out_i16, uint8_t* out_u8,
+                               int* max_count, int* exact) {
+  if (n_pos < 0 || (n_pos > 0 && (!x || !out_i16))) return fail("cvb_pack_counts: bad argument");
+  int T = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(T, 64), n_pos / 65536));
+  std::vector<int> tmax((size_t)T, 0), tok((size_t)T, 1);
+  auto work = [&](int t, int64_t a, int64_t b) {
+    int mx = 0, ok = 1;
+    for (int64_t i = a; i < b; ++i) {
+      const float* p = x + 4 * i;
+      const float c0 = p[0];
+      const float v[4] = {c0, subtracted ? p[1] + c0 : p[1], subtracted ? p[2] + c0 : p[2], subtracted ? p[3] + c0 : p[3]};
+      for (int k = 0; k < 4; ++k) {
+        const float f = v[k];
+        const int c = (f >= 0.f && f <= 32767.f) ? (int)f : -1;
+        if (c < 0 || (float)c != f) { ok = 0; out_i16[4 * i + k] = 0; if (out_u8) out_u8[4 * i + k] = 0; continue; }
+        mx = c > mx ? c : mx;
+        out_i16[4 * i + k] = (int16_t)c;
+        if (out_u8) out_u8[4 * i + k] = (uint8_t)(c > 255 ? 255 : c);
+      }
+    }
+    tmax[(size_t)t] = mx;
+    tok[(size_t)t] = ok;
+  };
+  if (T == 1) {
+    work(0, 0, n_pos);
+  } else {
+    std::vector<std::thread> pool;
+    const int64_t per = (n_pos + T - 1) / T;
+    for (int t = 1; t < T; ++t) pool.emplace_back(work, t, std::min(n_pos, t * per), std::min(n_pos, (t + 1) * per));
+    work(0, 0, std::min(n_pos, per));
+    for (auto& th : pool) th.join();
+  }
+  int mx = 0, ok = 1;
+  for (int t = 0; t < T; ++t) { mx = std::max(mx, tmax[(size_t)t]); ok &= tok[(size_t)t]; }
+  if (max_count) *max_count = mx;
+  if (exact) *exact = ok;
+  return 0;
+}

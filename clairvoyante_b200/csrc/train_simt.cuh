@@ -22,6 +22,7 @@ struct TrainWork {
   cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};  // slot uploaded / slot's compute finished
   float *c1 = nullptr, *p1p = nullptr, *c2 = nullptr, *p2p = nullptr, *c3 = nullptr, *p3 = nullptr;
   float *h4 = nullptr, *d4 = nullptr, *h5 = nullptr, *logits = nullptr, *out16 = nullptr;
+  float* d5 = nullptr;  // dropout5 (dropoutRateFC5 != 0 only; its own allocation)
   float *dlog = nullptr, *g5 = nullptr, *g4 = nullptr, *g4b = nullptr, *gp3 = nullptr, *g3p = nullptr, *gp2 = nullptr;
   float *g2p = nullptr, *gp1 = nullptr, *g1 = nullptr;
   float *w3t = nullptr, *w2t = nullptr, *w4t = nullptr, *w5t = nullptr, *tmpb = nullptr, *tmph = nullptr;
@@ -51,6 +52,7 @@ static inline void train_work_free(TrainWork* w) {
   cudaFree(w->all);
   cudaFree(w->all16);
   cudaFree(w->amax);
+  cudaFree(w->d5);
   for (int i = 0; i < 2; ++i) {
     if (w->ev_up[i]) cudaEventDestroy(w->ev_up[i]);
     if (w->ev_done[i]) cudaEventDestroy(w->ev_done[i]);
@@ -286,8 +288,10 @@ __global__ void k_loss_grad(const float* __restrict__ logits16, const float* __r
 
 // ---- back through the heads: g5 = (dlog[4:16] . W_{z,t,l}^T) * selu'(h5);  g4 = dlog[0:4] . Wb^T
 struct HeadW { const float *wb, *wz, *wt, *wl; };
+// use_drop5: the heads read dropout5 = a * (h5 * mask + alpha * (1 - mask)) + b (clairvoyante_v3.py:121): d dropout5 / d h5 = a * mask
 __global__ void k_heads_bwd(const float* __restrict__ dlog, const float* __restrict__ h5, int64_t n, int N4, int N5, HeadW w,
-                            float* __restrict__ g4, float* __restrict__ g5, int ld5) {
+                            float* __restrict__ g4, float* __restrict__ g5, int ld5, int use_drop5, uint64_t seed5,
+                            int64_t index0_5, DropConst dc5) {
   const int64_t total = n * (N4 + N5);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t s = i / (N4 + N5);
@@ -303,6 +307,7 @@ __global__ void k_heads_bwd(const float* __restrict__ dlog, const float* __restr
       for (int o = 0; o < 4; ++o) a += d[6 + o] * w.wt[kk * 4 + o];
 #pragma unroll
       for (int o = 0; o < 6; ++o) a += d[10 + o] * w.wl[kk * 6 + o];
+      if (use_drop5) a *= dc5.a * floorf(dc5.keep + hash_uniform(seed5, (uint64_t)(index0_5 + s * N5 + kk)));
       g5[s * ld5 + kk] = a * selu_grad_from_out(h5[s * N5 + kk]);
     }
   }
@@ -559,27 +564,34 @@ __global__ void k_scatter_conv_wgrad(const float* __restrict__ tmpw, float* __re
   dW[i] += a;
 }
 
-// ---- sum of squares (for lossL2 = lambda * sum 0.5 ||kernel||^2, tf.nn.l2_loss)
-__global__ void k_sumsq(const float* __restrict__ w, int64_t n, float* __restrict__ out) {
-  float a = 0.f;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a += w[i] * w[i];
-  for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-  if ((threadIdx.x & 31) == 0) atomicAdd(out, a);
-}
-
-// ---- TF-1.x Adam (python/training/adam.py): lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed on the host;
-//   g' = g + l2*w (d/dw of lambda*0.5*||w||^2; biases get l2 = 0);  m += (g'-m)(1-b1);  v += (g'^2-v)(1-b2);
-//   w -= lr_t * m / (sqrt(v) + eps)
-__global__ void k_adam(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
-                       int64_t n, float lr_t, float b1, float b2, float eps, float l2) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float gg = g[i] + l2 * w[i];
-    const float mm = m[i] + (gg - m[i]) * (1.f - b1);
-    const float vv = v[i] + (gg * gg - v[i]) * (1.f - b2);
-    m[i] = mm;
-    v[i] = vv;
-    w[i] -= lr_t * mm / (sqrtf(vv) + eps);
+// ---- the whole optimiser step in ONE launch over the flat parameter buffer (every variable starts on a 16-byte boundary
+// and is padded to a multiple of 4 floats with zeros, which Adam leaves at zero): TF-1.x Adam as above with l2 applied to
+// the kernels only (clairvoyante_v3.py:150: every variable whose name has no "bias"), and -- from the PRE-update weights,
+// which is what session.run's loss fetch sees -- the sum of squares of the kernels for lossL2.
+struct BiasRanges { int n; int64_t lo[12], hi[12]; };  // [lo, hi) float4 indices of the bias variables
+__global__ void __launch_bounds__(256)
+k_adam_flat(float4* __restrict__ w, float4* __restrict__ m, float4* __restrict__ v, const float4* __restrict__ g, int64_t n4,
+            float lr_t, float b1, float b2, float eps, float l2, BiasRanges br, float* __restrict__ sumsq) {
+  float ss = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    bool bias = false;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) bias |= k < br.n && i >= br.lo[k] && i < br.hi[k];
+    const float lam = bias ? 0.f : l2;
+    float4 W = w[i], M = m[i], V = v[i];
+    const float4 G = g[i];
+    if (!bias) ss += W.x * W.x + W.y * W.y + W.z * W.z + W.w * W.w;
+    auto upd = [&](float& ww, float& mm, float& vv, float gr) {
+      const float gg = gr + lam * ww;
+      mm = mm + (gg - mm) * (1.f - b1);
+      vv = vv + (gg * gg - vv) * (1.f - b2);
+      ww -= lr_t * mm / (sqrtf(vv) + eps);
+    };
+    upd(W.x, M.x, V.x, G.x); upd(W.y, M.y, V.y, G.y); upd(W.z, M.z, V.z, G.z); upd(W.w, M.w, V.w, G.w);
+    w[i] = W; m[i] = M; v[i] = V;
   }
+  for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  if ((threadIdx.x & 31) == 0 && ss != 0.f) atomicAdd(sumsq, ss);
 }
 
 }  // namespace cvb

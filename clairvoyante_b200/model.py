@@ -68,8 +68,6 @@ class ClairvoyanteBase(object):
         self.trainLossRTVal = None; self.trainSummaryRTVal = None; self.getLossLossRTVal = None
         self.predictBaseRTVal = None; self.predictZygosityRTVal = None
         self.predictVarTypeRTVal = None; self.predictIndelLengthRTVal = None
-        if dropoutRateFC5 != 0.0:
-            raise NotImplementedError("dropoutRateFC5 != 0 is not supported (reference default param.py:22 is 0.0)")
         self._lib = _lib.load()
         self.device = _default_device() if device is None else int(device)
         h = ctypes.c_void_p()
@@ -86,6 +84,9 @@ class ClairvoyanteBase(object):
         # CVB_TRAIN=fp32 selects the all-SIMT kernels, CVB_TRAIN=bf16 plain bf16 operands
         self.trainMode = None
         self.setTrainMode(os.environ.get("CVB_TRAIN", "bf16x3"))
+        if not 0.0 <= float(dropoutRateFC5) < 1.0:
+            raise ValueError("dropoutRateFC5 must be in [0, 1)")
+        _lib.check(self._lib.cvb_set_dropout_fc5(self._h, float(dropoutRateFC5)))
         self._dropout_calls = 0
         self._seed = int.from_bytes(os.urandom(8), "little")   # reference dropout is unseeded (selu.py:55)
 
@@ -93,13 +94,8 @@ class ClairvoyanteBase(object):
     def init(self, seed=None):
         """init_op (clairvoyante_v3.py:177-178): reference initialisers, zero Adam slots, step 0."""
         if seed is None:
-            seed = int.from_bytes(os.urandom(4), "little")
-        self.setWeights(initializers.init_weights(self.VARIANT, seed))
-        for name, shape in initializers.variable_shapes(self.VARIANT):
-            z = np.zeros(shape, np.float32)
-            self._set(name, 1, z)
-            self._set(name, 2, z)
-        _lib.check(self._lib.cvb_set_step(self._h, 0))
+            seed = int.from_bytes(os.urandom(8), "little")
+        _lib.check(self._lib.cvb_init_weights(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -230,18 +226,25 @@ class ClairvoyanteBase(object):
 
     # ---- inference (clairvoyante_v3.py:257-280) --------------------------------------------
     def _predict(self, XArray, want_logits=False):
-        half = isinstance(XArray, np.ndarray) and XArray.dtype == np.float16     # fp16 feed: half the PCIe bytes (cvb200.h)
-        if half:
+        # narrow feeds (cvb200.h): a CountBatch's raw uint8 / int16 counts (utils_v2.GetTensor attaches them), an explicit
+        # uint8 / int16 array of RAW counts, or float16 values -- a quarter / a half of the host->device bytes, same bits out
+        counts = getattr(XArray, "counts", None)
+        if counts is not None and counts.shape[0] == XArray.shape[0]:
+            XArray = counts
+        fn = None
+        if isinstance(XArray, np.ndarray) and XArray.dtype in (np.float16, np.int16, np.uint8):
+            fn = {np.dtype(np.float16): self._lib.cvb_predict_host_f16, np.dtype(np.int16): self._lib.cvb_predict_host_counts_i16,
+                  np.dtype(np.uint8): self._lib.cvb_predict_host_counts_u8}[XArray.dtype]
             x = np.ascontiguousarray(XArray)
             n = x.shape[0] if x.ndim > 0 else 0
             if x.size != n * int(np.prod(self.inputShape)):
                 raise ValueError("expected shape (N,33,4,4), got %s" % (x.shape,))
         else:
             x, n = _f32c(XArray, self.inputShape)
+            fn = self._lib.cvb_predict_host
         base = np.empty((n, 4), np.float32); z = np.empty((n, 2), np.float32)
         t = np.empty((n, 4), np.float32); l = np.empty((n, 6), np.float32)
         lg = np.empty((n, 16), np.float32) if want_logits else None
-        fn = self._lib.cvb_predict_host_f16 if half else self._lib.cvb_predict_host
         _lib.check(fn(self._h, x.ctypes.data, n, base.ctypes.data, z.ctypes.data, t.ctypes.data,
                       l.ctypes.data, lg.ctypes.data if want_logits else None))
         return base, z, t, l, lg
@@ -263,6 +266,12 @@ class ClairvoyanteBase(object):
     def predictDevice(self, x_ptr, n, out16_ptr, logits16_ptr=None, stream=None):
         """Device-resident batch (pointers from e.g. torch.Tensor.data_ptr()); asynchronous."""
         _lib.check(self._lib.cvb_predict_device(self._h, x_ptr, n, out16_ptr, logits16_ptr, stream))
+
+    X_KINDS = {"f32": 0, "f16": 1, "i16": 2, "u8": 3}
+
+    def predictDeviceX(self, x_ptr, kind, n, out16_ptr, logits16_ptr=None, stream=None):
+        """predictDevice for a device buffer of fp16 values ('f16') or RAW int16 / uint8 counts ('i16', 'u8')"""
+        _lib.check(self._lib.cvb_predict_device_x(self._h, x_ptr, self.X_KINDS[kind], n, out16_ptr, logits16_ptr, stream))
 
     def debugRead(self, which, n_sites):
         """Intermediate of the last device pass: 'p2' | 'p3' | 'h4' (test aid)."""

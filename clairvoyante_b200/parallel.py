@@ -41,29 +41,51 @@ class _CudaBuffer(object):
 
 
 class DataParallelTrainer(object):
-    """train(X, Y) on the global batch: every rank takes its shard, gradients + loss sums are all-reduced (SUM) in
-    one call over NVLink/NCCL, then every rank applies the identical Adam step."""
+    """train(X, Y) on the global batch: every rank takes its shard, gradients + loss sums are all-reduced (SUM) over
+    NVLink/NCCL, then every rank applies the identical Adam step.
 
-    def __init__(self, model, dist=None):
-        import torch
-        self._torch = torch
+    The reduction runs INSIDE the library (cvb_allreduce_init, include/cvb200.h): ncclAllReduce on the library's compute
+    stream between the backward pass and the optimiser kernel, one C call per step, no host synchronisation in between.
+    torch.distributed only carries the 128-byte ncclUniqueId to the other ranks when the trainer is built.  On a backend
+    without NCCL (the gloo CPU tests) or with in_library=False the first version's route is used: torch.distributed
+    all_reduce on the exposed gradient buffer."""
+
+    def __init__(self, model, dist=None, in_library=True):
         self.m = model
         self.dist = dist
         self.rank = dist.get_rank() if dist is not None else 0
         self.world = dist.get_world_size() if dist is not None else 1
-        ptr, numel = ctypes.c_void_p(), ctypes.c_int64()
+        self.in_library = False
+        self.grad = None
+        if dist is None or self.world == 1:
+            return
+        lib = model._lib
         from . import _lib
-        _lib.check(model._lib.cvb_grad_buffer(model._h, ctypes.byref(ptr), ctypes.byref(numel)))
-        self.grad = torch.as_tensor(_CudaBuffer(ptr.value, numel.value), device="cuda:%d" % model.device)
+        if in_library and dist.get_backend() == "nccl":
+            uid = ctypes.create_string_buffer(128)
+            if self.rank == 0:
+                _lib.check(lib.cvb_nccl_unique_id(uid))
+            box = [uid.raw]
+            dist.broadcast_object_list(box, src=0)
+            _lib.check(lib.cvb_allreduce_init(model._h, box[0], self.world, self.rank))
+            self.in_library = True
+        else:
+            import torch
+            self._torch = torch
+            ptr, numel = ctypes.c_void_p(), ctypes.c_int64()
+            _lib.check(lib.cvb_grad_buffer(model._h, ctypes.byref(ptr), ctypes.byref(numel)))
+            self.grad = torch.as_tensor(_CudaBuffer(ptr.value, numel.value), device="cuda:%d" % model.device)
 
     def train(self, X, Y, seed):
         lo, hi = shard_range(len(X), self.rank, self.world)
         # the dropout stream is indexed by (seed, element); give every rank a distinct, reproducible stream
-        self.m._train_step(X[lo:hi], Y[lo:hi], apply_update=0, seed=(seed + 0x51ED270B * self.rank) & 0xFFFFFFFFFFFFFFFF)
-        if self.dist is not None and self.world > 1:
-            self.dist.all_reduce(self.grad, op=self.dist.ReduceOp.SUM)
-            if self.grad.is_cuda:
-                # NCCL enqueues the reduction on torch's stream and returns; the optimizer kernels run on the library's
-                # own (non-blocking) stream, so the reduced gradients must be complete before applyAdam reads them
-                self._torch.cuda.current_stream(self.grad.device).synchronize()
+        seed = (seed + 0x51ED270B * self.rank) & 0xFFFFFFFFFFFFFFFF
+        if self.in_library or self.world == 1:
+            return self.m._train_step(X[lo:hi], Y[lo:hi], apply_update=1, seed=seed)
+        self.m._train_step(X[lo:hi], Y[lo:hi], apply_update=0, seed=seed)
+        self.dist.all_reduce(self.grad, op=self.dist.ReduceOp.SUM)
+        if self.grad.is_cuda:
+            # NCCL enqueues the reduction on torch's stream and returns; the optimizer kernels run on the library's
+            # own (non-blocking) stream, so the reduced gradients must be complete before applyAdam reads them
+            self._torch.cuda.current_stream(self.grad.device).synchronize()
         return self.m.applyAdam()

@@ -11,7 +11,8 @@ SITE_FLOATS = 33 * 4 * 4
 _BLOCK = 8192          # sites per RNG block: site i depends only on (seed, i // _BLOCK)
 
 
-def _block(seed, b, n):
+def _block_raw(seed, b, n):
+    """Raw CreateTensor counts (before utils_v2.py:46's channel subtraction): non-negative integers <= 250 + 0.3*250."""
     rng = np.random.default_rng([seed, b])
     H = 33
     d = np.minimum(rng.poisson(40.0, (n, H)), 250).astype(np.float32)          # depth per position
@@ -34,23 +35,88 @@ def _block(seed, b, n):
     dele = np.floor(d * 0.3 * rng.random((n, H))) * (rng.random((n, H)) < 0.02)
     x[..., 2] = x[..., 0]
     x[ii, hh, ref, 2] += dele
+    return x
+
+
+def _block(seed, b, n):
+    x = _block_raw(seed, b, n)
     # utils_v2.py:46 -- subtract the reference channel from the other three
     x[..., 1:4] -= x[..., 0:1]
     return x
 
 
-def make_sites(n, seed=0, start=0):
-    """Sites [start, start+n) of the infinite seeded stream."""
-    out = np.empty((n, 33, 4, 4), np.float32)
+def _stream(block_fn, n, seed, start, dtype):
+    out = np.empty((n, 33, 4, 4), dtype)
     i = 0
     while i < n:
         g = start + i
         b, off = divmod(g, _BLOCK)
-        blk = _block(seed, b, _BLOCK)
+        blk = block_fn(seed, b, _BLOCK)
         take = min(n - i, _BLOCK - off)
         out[i:i + take] = blk[off:off + take]
         i += take
     return out
+
+
+def make_sites(n, seed=0, start=0):
+    """Sites [start, start+n) of the infinite seeded stream."""
+    return _stream(_block, n, seed, start, np.float32)
+
+
+def make_counts(n, seed=0, start=0):
+    """The same sites as RAW counts, int16 (what CreateTensor.py:56 prints, before utils_v2.py:46):
+    make_counts(...) with channels 1..3 minus channel 0, as float32, equals make_sites(...) exactly."""
+    return _stream(_block_raw, n, seed, start, np.int16)
+
+
+def make_labeled_sites(n, seed=0):
+    """(x, y): sites whose CENTRE row (position 16) carries an implanted genotype and the (N,16) labels that describe it
+    (encoding of utils_v2.py:78-121,141-148), so that a network can actually learn the mapping -- used to produce
+    trained-like weights (tests/golden/make_trained_weights.py) and by the training bench.  2/3 non-variant, 1/6 0/1,
+    1/6 1/1; variants are SNP / INS / DEL with equal odds, indel length 1..5 shown as counts on the following rows."""
+    x = _stream(_block_raw, n, seed, 0, np.float32)
+    rng = np.random.default_rng([seed, 0x5EED])
+    y = np.zeros((n, 16), np.float32)
+    c = 16
+    i = np.arange(n)
+    d = np.maximum(x[:, c, :, 0].sum(1), 8.0)                      # depth at the centre
+    ref = x[:, c, :, 0].argmax(1)
+    kind = rng.integers(0, 6, n)                                   # 0..3 non-variant, 4 het, 5 hom
+    vt = rng.integers(0, 3, n)                                     # 0 SNP, 1 INS, 2 DEL
+    alt = (ref + rng.integers(1, 4, n)) % 4
+    vlen = rng.integers(1, 6, n)
+    frac = np.where(kind == 4, 0.35 + 0.3 * rng.random(n), 0.85 + 0.15 * rng.random(n))
+    moved = np.floor(d * frac).astype(np.float32)
+    # clean centre: every channel shows the reference base at full depth
+    x[:, c] = 0.0
+    for ch in range(4):
+        x[i, c, ref, ch] = d
+    var = kind >= 4
+    snp = var & (vt == 0)
+    x[i[snp], c, ref[snp], 3] -= moved[snp]; x[i[snp], c, alt[snp], 3] += moved[snp]
+    x[i[snp], c, ref[snp], 1] -= moved[snp]; x[i[snp], c, alt[snp], 1] += moved[snp]
+    for k, chn in ((1, 1), (2, 2)):                                # insertions on channel 1, deletions on channel 2
+        sel = var & (vt == k)
+        for L in range(1, 6):
+            s = sel & (vlen >= L)
+            rows = c + L - 1 if k == 1 else c + L
+            base = rng.integers(0, 4, n) if k == 1 else x[:, rows, :, 0].argmax(1)
+            x[i[s], rows, base[s], chn] += moved[s]
+    x[..., 1:4] -= x[..., 0:1]
+    nv = ~var
+    y[i[nv], ref[nv]] = 1.0; y[nv, 5] = 1.0; y[nv, 6] = 1.0; y[nv, 10] = 1.0           # utils_v2.py:142-147
+    het, hom = kind == 4, kind == 5
+    y[i[het], ref[het]] = 0.5                                                            # utils_v2.py:90-96
+    hs = het & snp
+    y[i[hs], alt[hs]] = 0.5
+    y[het, 4] = 1.0
+    ho = hom & snp                                                                       # utils_v2.py:98-103
+    y[i[ho], alt[ho]] = 1.0
+    y[hom, 5] = 1.0
+    y[i[var], np.where(vt == 0, 7, np.where(vt == 1, 8, 9))[var]] = 1.0
+    L = np.where(vt == 0, 0, vlen)
+    y[i[var], np.where(L > 4, 15, 10 + L)[var]] = 1.0
+    return x, y
 
 
 def make_labels(n, seed=0):

@@ -54,6 +54,15 @@ def _open_text(fn):
     return proc, io.TextIOWrapper(proc.stdout, encoding="ascii", errors="replace")
 
 
+def open_maybe_gzip(fn, mode="rt"):
+    """plain or gzip file by its two magic bytes, whatever its name: what the reference's `gzip -fdc` readers accept
+    (its own stages write gzip under suffix-less names, e.g. PrepDataBeforeDemo.sh's can_chr21_sampled)"""
+    import gzip
+    with open(fn, "rb") as probe:
+        packed = probe.read(2) == b"\x1f\x8b"
+    return gzip.open(fn, mode) if packed else open(fn, mode)
+
+
 def _close_text(proc, fh):
     if proc is not None:
         fh.close()
@@ -123,6 +132,40 @@ def _read_ahead(fb, size):
         yield b""
 
 
+class CountBatch(np.ndarray):
+    """A float32 batch exactly as GetTensor yields it (channel 0 subtracted, utils_v2.py:46) that also carries `.counts`:
+    the same sites as RAW uint8 / int16 counts for the narrow host->device feed (cvb_predict_host_counts_*, a quarter / a
+    half of the bytes; the first device kernel redoes the subtraction).  The attribute belongs to this very object --
+    slices and views do not inherit it -- so code that treats the batch as a plain ndarray is unaffected."""
+    counts = None
+
+    def __array_finalize__(self, obj):
+        self.counts = None
+
+
+def pack_counts(x, subtracted=True, threads=0):
+    """raw counts behind the float32 tensors `x` ((n,33,4,4) or (n,528)) as a uint8 array (every count <= 255) or an int16
+    one, same shape; None when `x` is not a tensor of non-negative integer counts (then only the fp32 feed is exact).
+    subtracted=True: x is what GetTensor yields; False: x is CreateTensor's raw alnCode."""
+    lib = _lib.load()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    i16 = np.empty(x.shape, np.int16)
+    u8 = np.empty(x.shape, np.uint8)
+    mx, ok = ctypes.c_int(), ctypes.c_int()
+    _lib.check(lib.cvb_pack_counts(x.ctypes.data, x.size // 4, 1 if subtracted else 0, threads, i16.ctypes.data, u8.ctypes.data,
+                                   ctypes.byref(mx), ctypes.byref(ok)))
+    if not ok.value:
+        return None
+    return u8 if mx.value <= 255 else i16
+
+
+def with_counts(x, subtracted=True, raw=None):
+    """`x` (float32, subtracted) as a CountBatch whose `.counts` holds the narrow copy (None if the values are not counts)"""
+    out = np.asarray(x).view(CountBatch)
+    out.counts = pack_counts(raw if raw is not None else x, subtracted=subtracted and raw is None)
+    return out
+
+
 _PARSE_LINES = 16384          # lines handed to the parser per call, whatever the batch size: enough work for every host thread
 
 
@@ -146,6 +189,10 @@ def _native_rows(tensor_fn, num, threads=0):
     want = num if num > 0 else _PARSE_LINES
     rows = np.empty((want, width), dtype=np.float32)
     recs, c = [], 0
+    narrow = os.environ.get("CVB_FEED", "counts") != "fp32"          # also hand out the batch as raw uint8 / int16 counts
+    cstage = np.empty((_PARSE_LINES, width), np.int16) if narrow else None
+    crows = np.empty((want, width), np.int16) if narrow else None
+    cmax, mx, ok = 0, ctypes.c_int(), ctypes.c_int()
     while True:
         base = ctypes.cast(ctypes.c_char_p(buf), ctypes.c_void_p).value or 0
         _lib.check(lib.cvb_parse_tensor_text(base + off, len(buf) - off, 1 if eof else 0, _PARSE_LINES, threads,
@@ -163,19 +210,31 @@ def _native_rows(tensor_fn, num, threads=0):
                 if pn < 0:
                     _lib.check(1)
                 names = ptxt[:pn].tobytes().decode("ascii", "replace").split("\n")
+                if narrow:                               # packed once per parse, on every host thread
+                    _lib.check(lib.cvb_pack_counts(stage.ctypes.data, k * (width // 4), 1, threads, cstage.ctypes.data, None,
+                                                   ctypes.byref(mx), ctypes.byref(ok)))
+                    if not ok.value:
+                        narrow = False                   # not a stream of integer counts: fp32 feed from here on
+                    cmax = max(cmax, mx.value)
                 s0 = 0
                 while s0 < k:                            # cut the batches out of this parse
                     if num <= 0 and c == len(rows):      # (num <= 0: one batch with everything)
                         rows = np.concatenate([rows, np.empty_like(rows)])
                     take = min(len(rows) - c, k - s0)
                     rows[c:c + take] = stage[s0:s0 + take]
+                    if narrow:
+                        if num <= 0 and len(crows) < len(rows):
+                            crows = np.concatenate([crows, np.empty((len(rows) - len(crows), width), np.int16)])
+                        crows[c:c + take] = cstage[s0:s0 + take]
                     recs += names[s0:s0 + take]
                     c += take
                     s0 += take
                     if num > 0 and c == num:
-                        yield rows, recs
+                        yield _attach_counts(rows, crows if narrow else None, cmax), recs
                         rows = np.empty((num, width), dtype=np.float32)   # fresh storage: the consumer still holds the batch
-                        recs, c = [], 0
+                        if narrow:
+                            crows = np.empty((num, width), np.int16)
+                        recs, c, cmax = [], 0, 0
             off += n_used.value
         if nl == 0 or off >= len(buf):
             if eof:
@@ -189,7 +248,24 @@ def _native_rows(tensor_fn, num, threads=0):
         fb.close()
     if proc is not None:
         proc.wait()
-    yield rows[:c], recs
+    yield _attach_counts(rows[:c], crows[:c] if narrow else None, cmax), recs
+
+
+def _attach_counts(rows, counts, cmax):
+    if counts is None:
+        return rows
+    out = rows.view(CountBatch)
+    out.counts = counts.astype(np.uint8) if cmax <= 255 else counts
+    return out
+
+
+def _as_sites(rows, h):
+    """(k,528) rows -> (k,33,4,4), keeping the narrow copy a CountBatch carries"""
+    x = rows.reshape(-1, h, 4, param.matrixNum)
+    c = getattr(rows, "counts", None)
+    if c is not None:
+        x.counts = c.reshape(x.shape)
+    return x
 
 
 def GetTensor(tensor_fn, num, threads=0):
@@ -205,12 +281,12 @@ def GetTensor(tensor_fn, num, threads=0):
         rows, recs = prev
         total += len(recs)
         print("Processed %d tensors" % total, file=sys.stderr)
-        yield 0, len(recs), rows.reshape(-1, h, 4, param.matrixNum), recs
+        yield 0, len(recs), _as_sites(rows, h), recs
         prev = cur
     rows, recs = prev
     total += len(recs)
     print("Processed %d tensors" % total, file=sys.stderr)
-    yield 1, len(recs), rows.reshape(-1, h, 4, param.matrixNum), recs
+    yield 1, len(recs), _as_sites(rows, h), recs
 
 
 # ------------------------------------------------------------------------------------------------

@@ -61,6 +61,11 @@ int64_t cvb_num_parameters(const cvb_model* m);
 int cvb_set_variable(cvb_model* m, const char* name, int slot, const float* host, int64_t n);
 /* replaces saveParameters (clairvoyante_v3.py:243): download one variable */
 int cvb_get_variable(cvb_model* m, const char* name, int slot, float* host, int64_t n);
+/* replaces init() = session.run(tf.global_variables_initializer()) (clairvoyante_v3.py:177-178): draws every variable
+ * from the reference's initialisers -- variance-scaling truncated normal (factor 2, FAN_IN) for conv1-3 / fc4 / fc5
+ * kernels (:57,72,87,106,116), glorot-uniform for the four head kernels (:125-135), zero biases -- with a seeded
+ * counter-based generator, zeroes the Adam slots and the step counter.  The reference is unseeded. */
+int cvb_init_weights(cvb_model* m, uint64_t seed);
 /* Adam step counter t (TF keeps beta1_power/beta2_power; t is their exponent) */
 int cvb_set_step(cvb_model* m, int64_t t);
 int cvb_get_step(const cvb_model* m, int64_t* t);
@@ -78,11 +83,25 @@ int cvb_predict_host(cvb_model* m, const float* x, int64_t n, float* base /*n,4*
  * first device step widens them to the fp32 layout of cvb_predict_host; results are then bit-identical to it. */
 int cvb_predict_host_f16(cvb_model* m, const uint16_t* x, int64_t n, float* base, float* zygosity, float* var_type,
                          float* indel_length, float* logits16);
+/* the narrow feed (utils_v2.py:46 fused into the first device kernel): RAW CreateTensor counts -- the
+ * non-negative integers of dataPrepScripts/CreateTensor.py:23-52 (`alnCode`), (n,33,4,4) C-contiguous, channel 0 NOT yet
+ * subtracted -- as int16 (a half of the fp32 bytes on the host->device link) or uint8 (a quarter; the caller guarantees
+ * every count <= 255, e.g. utils_v2.pack_counts checks it).  The first kernel widens each (row, base) position to fp32
+ * and makes channels 1..3 relative to channel 0, exactly what GetTensor does on the host for the fp32 entry point
+ * (integers: no rounding anywhere), so results are bit-identical to cvb_predict_host on the subtracted fp32 tensors. */
+int cvb_predict_host_counts_i16(cvb_model* m, const int16_t* counts, int64_t n, float* base, float* zygosity,
+                                float* var_type, float* indel_length, float* logits16);
+int cvb_predict_host_counts_u8(cvb_model* m, const uint8_t* counts, int64_t n, float* base, float* zygosity,
+                               float* var_type, float* indel_length, float* logits16);
+/* element kinds of a candidate-tensor buffer */
+enum { CVB_X_F32 = 0, CVB_X_F16 = 1, CVB_X_I16_COUNTS = 2, CVB_X_U8_COUNTS = 3 };
 /* same computation on DEVICE buffers (x, out16, logits16 are device pointers on the
  * handle's device); enqueued on `stream` (a cudaStream_t; NULL = the CUDA legacy default
  * stream, exactly as in the runtime API) and NOT synchronised.                                                  */
 int cvb_predict_device(cvb_model* m, const float* x, int64_t n, float* out16, float* logits16,
                        void* stream);
+/* cvb_predict_device for a device buffer of any element kind (CVB_X_*; x 16-byte aligned) */
+int cvb_predict_device_x(cvb_model* m, const void* x, int x_kind, int64_t n, float* out16, float* logits16, void* stream);
 
 /* replaces getLoss/getLossNoRT (clairvoyante_v3.py:207-227): forward with phase=False,
  * lambda=0; returns the SUM-over-batch loss (clairvoyante_v3.py:140-152).
@@ -98,6 +117,11 @@ int cvb_loss_host(cvb_model* m, const float* x, const float* y, int64_t n, float
 int cvb_train_step_host(cvb_model* m, const float* x, const float* y, int64_t n,
                         float lr, float l2, float drop4, uint64_t dropout_seed,
                         int apply_update, float* loss6);
+/* dropoutRateFC5 (clairvoyante_v3.py:121, selu.py:34-69, param.py:22; default 0): SELU dropout on FC5's output, which
+ * feeds the zygosity / varType / indelLength heads, in every following cvb_train_step_host.  Its keep mask comes from the
+ * same counter-based stream as FC4's (train_simt.cuh hash_uniform; host twin dropout_rng.py) under
+ * dropout_seed ^ 0x5D5D5D5D5D5D5D5D, element index = site * N5 + unit. */
+int cvb_set_dropout_fc5(cvb_model* m, float rate);
 /* arithmetic of the large contractions of cvb_train_step_host / cvb_loss_host (train.py's model.train / getLoss path,
  * clairvoyante_v3.py:174,183-227).  FP32: fp32 SIMT kernels throughout.  BF16X3 (default): FC4 forward, data gradient and
  * weight gradient on tcgen05 with split-bf16 operands (x = hi + lo, three products, fp32 accumulate: ~2^-16 relative per
@@ -108,6 +132,21 @@ int cvb_set_train_mode(cvb_model* m, int mode);
 /* device pointer + element count of the flat fp32 gradient buffer (all 18 variables in
  * cvb_variable_info order, followed by 5 loss terms) for an external all-reduce     */
 int cvb_grad_buffer(cvb_model* m, void** dev_ptr, int64_t* numel);
+/* ---- data-parallel training (train.py over several GPUs): one process per GPU, every rank steps on its shard
+ * of the global batch, and because the loss is a SUM over the batch (clairvoyante_v3.py:140-151) one SUM all-reduce of
+ * [gradients | 4 loss sums] gives every rank the global step.  With a communicator attached the library issues that
+ * ncclAllReduce itself, on its compute stream, inside cvb_train_step_host(apply_update = 1) between the backward pass and
+ * the optimiser kernel -- no host synchronisation, nothing on a foreign stream.  NCCL is bound at run time (dlopen of
+ * libnccl.so.2, or $CVB_NCCL_LIB): libcvb200.so does not link against it.
+ *   cvb_nccl_unique_id : rank 0 draws the 128-byte ncclUniqueId and hands it to the other ranks by any means
+ *                        (torch.distributed broadcast, MPI, a file)
+ *   cvb_allreduce_init : every rank: ncclCommInitRank on the handle's device; the communicator belongs to the handle
+ *   cvb_allreduce_attach : use an EXISTING ncclComm_t (owned by the caller; NULL detaches)
+ *   cvb_allreduce_gradients : the reduction alone, for callers that drive apply_update = 0 / cvb_apply_adam themselves */
+int cvb_nccl_unique_id(void* id128);
+int cvb_allreduce_init(cvb_model* m, const void* id128, int nranks, int rank);
+int cvb_allreduce_attach(cvb_model* m, void* nccl_comm);
+int cvb_allreduce_gradients(cvb_model* m);
 /* download gradients of one variable (testing) */
 int cvb_get_gradient(cvb_model* m, const char* name, float* host, int64_t n);
 /* finishes a step: loss6 (may be NULL) = [total, base, zygosity, varType, indelLength, lossL2] computed from the
@@ -135,6 +174,14 @@ int cvb_parse_tensor_text(const char* buf, int64_t len, int final_chunk, int64_t
  * (same buf, its meta, its *lines): "chrom:pos:SEQ\n" each, SEQ upper-cased.  Returns the bytes written to out[0, cap) or -1
  * (cap = the consumed byte count of that parse is always enough). */
 int64_t cvb_tensor_text_positions(const char* buf, const int64_t* meta, int64_t lines, char* out, int64_t cap);
+
+/* fp32 candidate tensors -> the raw counts behind them for the narrow feed (cvb_predict_host_counts_*).  x = n_pos
+ * positions of 4 channels ((n,33,4,4) has 132 n positions); subtracted != 0: channels 1..3 are relative to channel 0 as
+ * GetTensor yields them (utils_v2.py:46), raw = x_i + x_0.  out_i16 always, out_u8 (may be NULL) saturating at 255.
+ * *exact = 1 iff every count is an integer in [0, 32767] (otherwise keep the fp32 feed); *max_count <= 255 means the uint8
+ * buffer is exact too.  Host code, threads <= 0: hardware concurrency. */
+int cvb_pack_counts(const float* x, int64_t n_pos, int subtracted, int threads, int16_t* out_i16, uint8_t* out_u8,
+                    int* max_count, int* exact);
 
 /* CRC-32C (Castagnoli) of data[0,n) continuing from `crc` (0 to start): the checksum TensorFlow's checkpoint bundles
  * carry per tensor and per index block (tf.train.Saver, clairvoyante_v3.py:243-251).  Host code. */

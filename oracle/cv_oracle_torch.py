@@ -31,8 +31,20 @@ def to_torch(weights, dtype=torch.float32, requires_grad=False):
     return {k: torch.tensor(v, dtype=dtype, requires_grad=requires_grad) for k, v in weights.items()}
 
 
-def forward(W, x, variant="v3", drop4_rate=0.0, drop4_mask=None):
-    """W: dict name->torch tensor (TF layouts: HWIO / [in,out]); x: (N,33,4,4) NHWC tensor."""
+def _dropout_selu(t, rate, mask):
+    # selu.py:34-69 with the keep mask given (fixedPointMean 0, fixedPointVar 1)
+    keep = 1.0 - rate
+    al = O.DROPOUT_ALPHA
+    a_ = math.sqrt(1.0 / (keep * ((1.0 - keep) * al * al + 1.0)))
+    b_ = -a_ * ((1.0 - keep) * al)
+    return a_ * (t * mask + al * (1.0 - mask)) + b_
+
+
+def forward(W, x, variant="v3", drop4_rate=0.0, drop4_mask=None, head_act=True, drop5_rate=0.0, drop5_mask=None):
+    """W: dict name->torch tensor (TF layouts: HWIO / [in,out]); x: (N,33,4,4) NHWC tensor.
+    head_act=False is NOT the reference graph: it drops the SELU of the three softmax heads (clairvoyante_v3.py:128-137) and
+    exists only for the warm-up phase of tests/golden/make_trained_weights.py (a head whose two pre-activations are both far
+    below zero sits at SELU's floor with a vanishing gradient and never recovers)."""
     spec = O.VARIANTS[variant]
     a = x.reshape(-1, O.H_IN, O.W_IN, O.C_IN).permute(0, 3, 1, 2)      # NCHW
     for i, (kh, cout, pool) in enumerate(spec["convs"], 1):
@@ -53,10 +65,13 @@ def forward(W, x, variant="v3", drop4_rate=0.0, drop4_mask=None):
         b_ = -a_ * ((1.0 - keep) * al)
         d4 = a_ * (fc4 * drop4_mask + al * (1.0 - drop4_mask)) + b_
     fc5 = selu(d4 @ W["fc5/kernel"] + W["fc5/bias"])
+    if drop5_rate > 0.0:                                               # dropout5 feeds the three softmax heads
+        fc5 = _dropout_selu(fc5, drop5_rate, drop5_mask)               # (clairvoyante_v3.py:121,128-135)
     base_logit = d4 @ W["YBaseChangeSigmoid/kernel"] + W["YBaseChangeSigmoid/bias"]
-    zl = selu(fc5 @ W["YZygosityFC/kernel"] + W["YZygosityFC/bias"]) + 1e-10
-    tl = selu(fc5 @ W["YVarTypeFC/kernel"] + W["YVarTypeFC/bias"]) + 1e-10
-    ll = selu(fc5 @ W["YIndelLengthFC/kernel"] + W["YIndelLengthFC/bias"]) + 1e-10
+    hact = selu if head_act else (lambda t: t)
+    zl = hact(fc5 @ W["YZygosityFC/kernel"] + W["YZygosityFC/bias"]) + 1e-10
+    tl = hact(fc5 @ W["YVarTypeFC/kernel"] + W["YVarTypeFC/bias"]) + 1e-10
+    ll = hact(fc5 @ W["YIndelLengthFC/kernel"] + W["YIndelLengthFC/bias"]) + 1e-10
     return dict(base=torch.sigmoid(base_logit), zygosity=torch.softmax(zl, 1),
                 varType=torch.softmax(tl, 1), indelLength=torch.softmax(ll, 1),
                 logits=torch.cat([base_logit, zl, tl, ll], 1))
@@ -78,8 +93,9 @@ def loss_and_grads(weights, x, y, variant="v3", l2_lambda=0.0, dtype=torch.float
     W = to_torch(weights, dtype, requires_grad=True)
     xt = torch.tensor(x, dtype=dtype)
     yt = torch.tensor(y, dtype=dtype)
-    if fw.get("drop4_mask") is not None:
-        fw = dict(fw, drop4_mask=torch.tensor(fw["drop4_mask"], dtype=dtype))
+    for k in ("drop4_mask", "drop5_mask"):
+        if fw.get(k) is not None:
+            fw = dict(fw, **{k: torch.tensor(fw[k], dtype=dtype)})
     l = loss(W, xt, yt, variant, l2_lambda, **fw)
     l.backward()
     return float(l.detach()), {k: v.grad.numpy() for k, v in W.items()}

@@ -71,6 +71,63 @@ def test_gradients_match_autograd(variant, rate, mode):
     m.close()
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("mode", ["bf16x3", "fp32"])
+@pytest.mark.parametrize("n", [300, 5121 + 77])
+def test_fc5_dropout_gradients_match_autograd(variant, mode, n):
+    """dropoutRateFC5 != 0 (clairvoyante_v3.py:121; param.py:22 defaults to 0 but the kwarg accepts any rate): SELU dropout
+    on FC5's output, which feeds the zygosity / varType / indelLength heads, together with FC4's; masks replayed on the host
+    (two micro-chunks at n = 5198: the counters run over the whole batch); getLoss stays dropout-free (phase = False)"""
+    N5 = {"v3": 168, "v3_slim": 18}
+    W = I.init_weights(variant, 15)
+    x, y = synth.make_sites(n, 16), synth.make_labels(n, 16)
+    m = _model(W, variant, dropoutRateFC4=0.5, dropoutRateFC5=0.25)
+    m.setTrainMode(mode)
+    seed = 0x77AA55
+    plain = float(m.getLoss(x, y))
+    loss, _ = m._train_step(x, y, apply_update=0, seed=seed)
+    g = m.getGradients()
+    m4 = dropout_rng.keep_mask(seed, n, 0.5, width=N4[variant])
+    m5 = dropout_rng.keep_mask(seed ^ 0x5D5D5D5D5D5D5D5D, n, 0.25, width=N5[variant])
+    ref_loss, ref_g = OT.loss_and_grads(W, x, y, variant, 0.0, drop4_rate=0.5, drop4_mask=m4, drop5_rate=0.25, drop5_mask=m5)
+    assert abs(float(m.getLoss(x, y)) - plain) <= 1e-6 * abs(plain)
+    for name in sorted(ref_g):
+        assert _relerr(g[name], ref_g[name]) < GRAD_TOL[mode], name
+    m.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_native_init_draws_the_reference_initialisers(variant):
+    """cvb_init_weights (init(), clairvoyante_v3.py:177-178): truncated normal with stddev sqrt(2.6 / fan_in) cut at two sigma
+    for conv / fc4 / fc5 kernels, glorot-uniform heads, zero biases, zero Adam slots and step; seeded and repeatable"""
+    m = _model(I.init_weights(variant, 0), variant)
+    m.train(synth.make_sites(64, 1), synth.make_labels(64, 1))          # leaves non-zero slots and step 1 behind
+    m.init(seed=123)
+    W = m.getWeights()
+    assert m.getStep() == 0
+    for name, shape in I.variable_shapes(variant):
+        w = W[name]
+        assert w.shape == tuple(shape)
+        assert not m._get(name, 1, shape).any() and not m._get(name, 2, shape).any()
+        if name.endswith("bias"):
+            assert not w.any()
+        elif name.startswith("Y"):
+            lim = np.sqrt(6.0 / (shape[0] + shape[1]))
+            assert np.abs(w).max() <= lim and (w.size < 100 or np.abs(w).max() > 0.8 * lim)
+        else:
+            sd = np.sqrt(2.6 / np.prod(shape[:-1]))
+            assert np.abs(w).max() <= 2.0 * sd * (1 + 1e-6)
+            if w.size >= 2000:                                           # std of a normal truncated at 2 sigma = 0.8796 sigma
+                assert abs(w.std() / sd - 0.8796) < 0.05 and abs(w.mean()) < 0.1 * sd
+    m2 = _model(I.init_weights(variant, 0), variant)
+    m2.init(seed=123)
+    W2 = m2.getWeights()
+    assert all(np.array_equal(W[k], W2[k]) for k in W)
+    m2.init(seed=124)
+    assert not np.array_equal(m2.getWeights()["fc4/kernel"], W["fc4/kernel"])
+    m.close(); m2.close()
+
+
 @pytest.mark.parametrize("variant,n", [("v3", 1), ("v3", 37), ("v3", 129), ("v3", 5121), ("v3_slim", 37), ("v3_slim", 5121)])
 def test_tensor_and_simt_training_paths_agree(variant, n):
     """the tcgen05 contractions (split bf16) against the fp32 SIMT kernels on ragged batch sizes: K = sites of the

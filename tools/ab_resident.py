@@ -25,7 +25,7 @@ else:
 
 os.makedirs("gpurun_out", exist_ok=True)
 m = cv.Clairvoyante()
-m.setWeights(I.init_weights(variant, 0))
+m.setWeights(I.init_weights("v3" if variant == "v3" else "v3_slim", 0))
 chunk = 18944 if variant == "v3" else 33152
 x = synth.make_sites(chunk + 1234, 1)          # one full chunk and a ragged one
 _, logits = m.predictLogits(x)

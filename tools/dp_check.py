@@ -1,27 +1,66 @@
-"""2-rank NCCL check of parallel.DataParallelTrainer: DP step on a global batch == single-GPU step on the same batch
-(dropout off), and sharded predict == single-GPU predict.  torchrun --nproc-per-node 2 tools/dp_check.py"""
-import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch, torch.distributed as dist
-from clairvoyante_b200 import clairvoyante_v3 as cv, initializers as I, parallel, synth
+"""2-rank (or more) NCCL check of parallel.DataParallelTrainer: a data-parallel step on a global batch == the single-GPU step
+on the same batch (dropout off), through the in-library ncclAllReduce (cvb_allreduce_init) and through the torch.distributed
+route, two steps each; and sharded predict == single-GPU predict.
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/dp_check.py [variant]
+(tests/test_dp_gpu.py runs this when the box has two GPUs)"""
+import os
+import sys
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+from clairvoyante_b200 import initializers as I, parallel, synth  # noqa: E402
+
+variant = sys.argv[1] if len(sys.argv) > 1 else "v3"
+if variant == "v3":
+    from clairvoyante_b200 import clairvoyante_v3 as cv
+else:
+    from clairvoyante_b200 import clairvoyante_v3_slim as cv
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-W = I.init_weights("v3", 2)
-x, y = synth.make_sites(10000, 1), synth.make_labels(10000, 1)
-m = cv.Clairvoyante(dropoutRateFC4=0.0, device=local); m.init(seed=1); m.setWeights(W)
-tr = parallel.DataParallelTrainer(m, dist)
-loss, _ = tr.train(x, y, seed=5)
-ref = cv.Clairvoyante(dropoutRateFC4=0.0, device=local); ref.init(seed=1); ref.setWeights(W)
-lref, _ = ref.train(x, y)
-wa, wb = m.getWeights(), ref.getWeights()
-err = max(float(np.abs(wa[k] - wb[k]).max()) for k in wa)
-def gather(loc):
-    out = [None] * world; dist.all_gather_object(out, loc); return out
-full = parallel.predict_sharded(m, x[:5001], rank, world, gather)
-single = m.predict(x[:5001])
-same = all(np.array_equal(a, b) for a, b in zip(full, single))
-print("rank %d: DP loss %.4f single %.4f | max |w_dp - w_single| = %.3g | sharded predict == single: %s" % (rank, loss, lref, err, same), flush=True)
-assert abs(loss - lref) <= 1e-5 * abs(lref) and err < 2e-6 and same
+W = I.init_weights(variant, 2)
+n = 10000                                                            # the reference's trainBatchSize (param.py:13)
+x, y = synth.make_sites(n, 1), synth.make_labels(n, 1)
+
+
+def fresh():
+    m = cv.Clairvoyante(dropoutRateFC4=0.0, device=local)
+    m.init(seed=1)
+    m.setWeights(W)
+    return m
+
+
+ref = fresh()
+lref = [float(ref.train(x, y)[0]) for _ in range(2)]
+wref = ref.getWeights()
+for in_library in (True, False):
+    m = fresh()
+    tr = parallel.DataParallelTrainer(m, dist, in_library=in_library)
+    assert tr.in_library == in_library
+    ldp = [float(tr.train(x, y, seed=5)[0]) for _ in range(2)]
+    w = m.getWeights()
+    err = max(float(np.abs(w[k] - wref[k]).max()) for k in w)
+    print("rank %d in_library=%s: DP losses %s single %s | max |w_dp - w_single| after 2 steps = %.3g"
+          % (rank, in_library, ldp, lref, err), flush=True)
+    assert all(abs(a - b) <= 1e-5 * abs(b) for a, b in zip(ldp, lref)) and err < 5e-6
+    # every rank holds the same weights bit for bit (identical reduced gradients, identical Adam)
+    ck = torch.tensor([float(np.sum([w[k].astype(np.float64).sum() for k in w]))], device="cuda", dtype=torch.float64)
+    lo, hi = ck.clone(), ck.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert float(lo) == float(hi)
+    if in_library:
+        def gather(loc):
+            out = [None] * world
+            dist.all_gather_object(out, loc)
+            return out
+        full = parallel.predict_sharded(m, x[:5001], rank, world, gather)
+        single = m.predict(x[:5001])
+        assert all(np.array_equal(a, b) for a, b in zip(full, single))
+    m.close()
+ref.close()
+dist.barrier()
+if rank == 0:
+    print("dp_check ok: %s, %d ranks" % (variant, world), flush=True)
 dist.destroy_process_group()
