@@ -184,6 +184,163 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def source_hash():
+    from clairvoyante_b200 import _lib
+    return _lib.source_hash()
+
+
+def load_traffic(variant, kernel):
+    """ncu DRAM bytes per launch of `kernel` from profiles/traffic.json -- only if that file was captured from THIS build
+    (it records the hash of csrc/ + include/ that tools/capture_round.sh saw); a stale file reads as null + a note"""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tp):
+        return None, "profiles/traffic.json absent"
+    d = json.load(open(tp))
+    if d.get("source_hash") != source_hash():
+        return None, "profiles/traffic.json is from another build (source_hash %s != %s): re-run tools/capture_round.sh" % (
+            d.get("source_hash"), source_hash())
+    return d.get(variant, {}).get(kernel), "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, build %s" % d["source_hash"]
+
+
+def inference_leg(args, cv, variant, W, local, rank, world, barrier, max_over_ranks, steps, warmup, full):
+    """device-resident pass + per-kernel timing + the two e2e feeds for one variant; `full` adds roofline detail"""
+    import torch
+    from clairvoyante_b200 import synth, utils_v2
+    m = cv.Clairvoyante(device=local)
+    if args.compute != "auto":
+        m.setComputeMode(args.compute)
+    m.setWeights(W)
+    tensor = m.computeMode == "fp16x3"
+    n = args.sites
+    pool_n = min(65536, n)
+    pool = synth.make_sites(pool_n, seed=1000 + rank)
+    reps = (n + pool_n - 1) // pool_n
+    xd = torch.from_numpy(pool).cuda().repeat(reps, 1, 1, 1)[:n].contiguous()      # 8.45 GB for 4M sites >> 126 MB L2
+    od = torch.empty((n, 16), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        m.predictDevice(xd.data_ptr(), n, od.data_ptr(), None, stream)
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    l0 = m.kernelLaunches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = m.kernelLaunches() - l0
+    clk = clocks.stop()
+    value = world * n * steps / (ms / 1e3)
+    out = dict(value=value, ms_per_step=ms / steps, launches=launches, clocks=clk, tensor=tensor, n=n, pool_n=pool_n)
+
+    # ---- per-kernel durations, live, CUDA events on the launching stream (separate short pass so
+    #      the event records do not sit inside the headline timing)
+    m.profileBegin()
+    for _ in range(2):
+        step()
+    prof = m.profileRead()
+    fl = dict(FLOPS_PER_SITE[variant])
+    conv2_separate = prof["conv2"][0] > 0.01 * prof["front"][0]      # tcgen05 conv2 runs as its own kernel
+    fl["front"] = fl["conv1"] if conv2_separate else fl["conv1"] + fl["conv2"]
+    if not conv2_separate:
+        prof.pop("conv2")
+    kern = {}
+    for k, (tms, cnt) in prof.items():
+        kern[k] = dict(ms_per_launch=tms / max(cnt, 1), launches=cnt, share=tms / max(sum(v[0] for v in prof.values()), 1e-9),
+                       tflops=fl[k] * (2 * n) / (tms / 1e3) / 1e12)
+    out["kernels"], out["flops"] = kern, fl
+    del xd, od
+    torch.cuda.empty_cache()
+
+    # ---- e2e: public API, pinned HOST input, H2D of every input byte + D2H of every result inside the timed region.
+    # One e2e step = the same `ne` sites, fed as predict() calls of at most 1 Mi sites from a pinned buffer (keeps the
+    # pinned footprint per rank small -- 8 ranks share one host).  Two feeds:
+    #   counts : the batch as the repo's own producers hand it out (utils_v2.GetTensor / CreateTensor.GetTensorFromAlignments
+    #            yield a CountBatch: float32 tensors + the raw uint8 / int16 counts) -> cvb_predict_host_counts_*: a quarter of
+    #            the fp32 bytes cross the link, the first kernel widens and subtracts the reference channel (utils_v2.py:46)
+    #   fp32   : a caller that only holds the channel-subtracted float32 tensors (the reference's own callers)
+    ne = args.e2e_sites or n
+    call_n = min(ne, 1 << 20)
+    ncalls = (ne + call_n - 1) // call_n
+    ne = ncalls * call_n
+    raw = synth.make_counts(pool_n, seed=1000 + rank)
+    packed = utils_v2.pack_counts(raw.astype(np.float32), subtracted=False)
+    assert packed is not None and np.array_equal(packed.astype(np.int16), raw)
+    feeds = {}
+    for name, dtype in (("counts", packed.dtype), ("fp32", np.float32)):
+        xh = torch.empty((call_n, 33, 4, 4), dtype=getattr(torch, np.dtype(dtype).name)).pin_memory()
+        xh_np = xh.numpy()
+        src = packed if name == "counts" else pool
+        for i in range(0, call_n, pool_n):
+            k = min(pool_n, call_n - i)
+            xh_np[i:i + k] = src[:k]
+        checksum = 0.0
+        for _ in range(2):
+            m.predict(xh_np)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            for _c in range(ncalls):
+                base, z, t, l = m.predict(xh_np)
+                checksum += float(t[0, 0])
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        feeds[name] = dict(value=world * ne * steps / dt, unit="sites/s", h2d_bytes_per_step=world * ne * 528 * xh_np.itemsize,
+                           d2h_bytes_per_step=world * ne * 16 * 4, ms_per_step=dt / steps * 1e3, checksum=checksum,
+                           input_dtype=str(xh_np.dtype))
+        del xh, xh_np
+    e2e = dict(feeds["counts"])
+    e2e.update(sites_per_step=world * ne, sites_per_gpu_per_step=ne, calls_per_step=ncalls,
+               api="Clairvoyante.predict(X) on a pinned NumPy batch of RAW %s counts (what utils_v2.GetTensor / "
+                   "CreateTensor.GetTensorFromAlignments attach to every batch), %d sites per call; four per-head float32 "
+                   "arrays come back" % (feeds["counts"]["input_dtype"], call_n),
+               fp32_input=dict(feeds["fp32"], api="Clairvoyante.predict(X) on pinned channel-subtracted float32 X"))
+    out["e2e"] = e2e
+    m.close()
+    return out
+
+
+def train_leg(args, cv, W, local, rank, world, dist, barrier, max_over_ranks):
+    """BASELINE configs[3] / README.md:307-319: v3 training, fwd + loss + bwd + Adam per step through the public API
+    (Clairvoyante.train at N = 1, parallel.DataParallelTrainer -- NCCL all-reduce inside the library -- at N > 1) on the
+    reference's trainBatchSize = 10,000 tensors GLOBAL (strong scaling) and on 10,000 per GPU (weak); host arrays, H2D inside"""
+    import torch
+    from clairvoyante_b200 import parallel, synth
+    m = cv.Clairvoyante(device=local)
+    m.init(seed=1)
+    m.setWeights(W)
+    tr = parallel.DataParallelTrainer(m, dist if world > 1 else None)
+    res = {}
+    for label, total in (("global_batch_10000", 10000), ("per_gpu_batch_10000", 10000 * world)):
+        if world == 1 and label == "per_gpu_batch_10000":
+            res[label] = res["global_batch_10000"]
+            continue
+        x, y = synth.make_labeled_sites(total, seed=77)
+        for _ in range(3):
+            tr.train(x, y, seed=1)
+        barrier()
+        l0 = m.kernelLaunches()
+        steps = 10
+        t0 = time.perf_counter()
+        for i in range(steps):
+            loss, _ = tr.train(x, y, seed=2 + i)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        res[label] = dict(value=total * steps / dt, unit="tensors/s", ms_per_step=dt / steps * 1e3, global_batch=total,
+                          per_gpu_batch=total // world, launches_per_step=(m.kernelLaunches() - l0) / steps, loss_per_tensor=float(loss) / total)
+    m.close()
+    return dict(metric="training tensors/sec (fwd + loss + bwd + TF-Adam per step, clairvoyante_v3, dropout 0.5, lambda 1e-3)",
+                api="Clairvoyante.train(X, Y)" if world == 1 else "parallel.DataParallelTrainer.train (cvb_allreduce_init: ncclAllReduce on the library's stream)",
+                dtype="bf16x3 on tcgen05 (split-bf16 operands, fp32 accumulate, fp32 master weights)", data="synthetic labelled sites",
+                reference_published="README.md:307-319: 90 s per 11 M tensors on a V100 (122 k/s), ~3.8 k/s on 28 Xeon cores", **res)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -197,6 +354,7 @@ def main():
     ap.add_argument("--compute", default="auto", choices=["auto", "fp32", "fp16x3"],
                     help="arithmetic path: fp16x3 = conv3/FC4 on tcgen05 with split-fp16 operands + fp32 accumulate "
                          "(fp32-equivalent, logits within 1e-3 of fp64); fp32 = all-SIMT fp32")
+    ap.add_argument("--no-extra", action="store_true", help="headline only: skip the v3_slim and training blocks")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -226,67 +384,15 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    from clairvoyante_b200 import initializers, synth
-    if args.variant == "v3":
-        from clairvoyante_b200 import clairvoyante_v3 as cv
-    else:
-        from clairvoyante_b200 import clairvoyante_v3_slim as cv
+    from clairvoyante_b200 import initializers
+    from clairvoyante_b200 import clairvoyante_v3 as cv3, clairvoyante_v3_slim as cvs
+    cv = cv3 if args.variant == "v3" else cvs
     W = initializers.init_weights(args.variant, seed=0)
-    m = cv.Clairvoyante(device=local)
-    if args.compute != "auto":
-        m.setComputeMode(args.compute)
-    m.setWeights(W)
-    tensor = m.computeMode == "fp16x3"
-
-    # ---- synthetic inputs: 65,536 unique seeded sites (rank-distinct), tiled to --sites in HBM
-    n = args.sites
-    pool_n = min(65536, n)
-    pool = synth.make_sites(pool_n, seed=1000 + rank)
-    reps = (n + pool_n - 1) // pool_n
-    xd = torch.from_numpy(pool).cuda().repeat(reps, 1, 1, 1)[:n].contiguous()      # 8.45 GB for 4M sites >> 126 MB L2
-    od = torch.empty((n, 16), dtype=torch.float32, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
-
-    def step():
-        m.predictDevice(xd.data_ptr(), n, od.data_ptr(), None, stream)
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    clocks = ClockSampler(local)
-    l0 = m.kernelLaunches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = m.kernelLaunches() - l0
-    clk = clocks.stop()
-    value = world * n * args.steps / (ms / 1e3)
-
-    # ---- per-kernel durations, live, CUDA events on the launching stream (separate short pass so
-    #      the event records do not sit inside the headline timing)
-    m.profileBegin()
-    for _ in range(2):
-        step()
-    prof = m.profileRead()
-    fl = dict(FLOPS_PER_SITE[args.variant])
-    conv2_separate = prof["conv2"][0] > 0.01 * prof["front"][0]      # tcgen05 conv2 runs as its own kernel
-    fl["front"] = fl["conv1"] if conv2_separate else fl["conv1"] + fl["conv2"]
-    if not conv2_separate:
-        prof.pop("conv2")
-    kern = {}
-    for k, (tms, cnt) in prof.items():
-        kern[k] = dict(ms_per_launch=tms / max(cnt, 1), launches=cnt, share=tms / max(sum(v[0] for v in prof.values()), 1e-9),
-                       tflops=fl[k] * (2 * n) / (tms / 1e3) / 1e12)
+    r = inference_leg(args, cv, args.variant, W, local, rank, world, barrier, max_over_ranks, args.steps, args.warmup, True)
+    tensor, n, kern, fl, value = r["tensor"], r["n"], r["kernels"], r["flops"], r["value"]
     dom = max(kern, key=lambda k: kern[k]["share"])
     pk = peaks()
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.variant, {}).get(dom)
+    traffic, traffic_note = load_traffic(args.variant, dom)
     sites_per_launch = 2 * n / max(kern[dom]["launches"], 1)
     tc_kernels = ("conv2", "conv3", "fc4", "tail") if args.variant == "v3" else ("conv3",)   # slim: only conv3 is on tcgen05
     on_tensor = tensor and dom in tc_kernels
@@ -303,62 +409,23 @@ def main():
                     frac=kern[dom]["tflops"] / r_peak, peak_source=r_src,
                     issued_frac=(3.0 if on_tensor else 1.0) * kern[dom]["tflops"] / r_peak,   # tensor-pipe occupancy: MMAs issued / peak
                     algorithmic_flops_per_launch=fl[dom] * sites_per_launch, ms_per_launch=kern[dom]["ms_per_launch"],
-                    traffic=traffic, kernels=kern,
+                    traffic=traffic, traffic_source=traffic_note, kernels=kern,
                     whole_pass=dict(tflops=value / world * fl["total"] / 1e12, frac_fp32_nominal=value / world * fl["total"] / 1e12 / FP32_NOMINAL_TFLOPS),
                     hbm=dict(achieved_gbs=value / world * HBM_BYTES_PER_SITE / 1e9, peak_gbs=pk["hbm_gbs"],
                              frac=value / world * HBM_BYTES_PER_SITE / 1e9 / pk["hbm_gbs"], peak_source=pk["source"],
                              note="not the binding bound: 3,708 FLOP per algorithmic HBM byte"))
 
-    # ---- e2e: public API, pinned host input, H2D + D2H inside the timed region
-    # One e2e step = the same `ne` sites, fed as predict() calls of at most 1 Mi sites from a pinned buffer (keeps the
-    # pinned footprint at 2.2 GB per rank -- 8 ranks share one host -- while every input byte of the step still
-    # crosses PCIe inside the timed region).
-    ne = args.e2e_sites or n
-    call_n = min(ne, 1 << 20)
-    ncalls = (ne + call_n - 1) // call_n
-    del xd, od
-    torch.cuda.empty_cache()
-    xh = torch.empty((call_n, 33, 4, 4), dtype=torch.float32).pin_memory()
-    xh_np = xh.numpy()
-    for i in range(0, call_n, pool_n):
-        k = min(pool_n, call_n - i)
-        xh_np[i:i + k] = pool[:k]
-    checksum = 0.0
-    for _ in range(2):
-        m.predict(xh_np)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        for _c in range(ncalls):
-            base, z, t, l = m.predict(xh_np)
-            checksum += float(t[0, 0])
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    dt = max_over_ranks(dt)
-    ne = ncalls * call_n
-    e2e_value = world * ne * args.steps / dt
-    e2e = dict(value=e2e_value, unit="sites/s", h2d_bytes_per_step=world * ne * 528 * 4, d2h_bytes_per_step=world * ne * 16 * 4,
-               sites_per_step=world * ne, sites_per_gpu_per_step=ne, calls_per_step=ncalls, ms_per_step=dt / args.steps * 1e3,
-               api="Clairvoyante.predict(X) on pinned NumPy X, %d sites per call" % call_n)
-
-    # the same step with the caller holding the count tensors as fp16 (BASELINE configs[2] "fp16 I/O"): half the H2D bytes,
-    # bit-identical outputs (tests/test_forward_gpu.py); reported beside e2e, not instead of it
-    xh16 = torch.empty((call_n, 33, 4, 4), dtype=torch.float16).pin_memory()
-    xh16_np = xh16.numpy()
-    xh16_np[...] = xh_np
-    del xh, xh_np
-    for _ in range(2):
-        m.predict(xh16_np)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        for _c in range(ncalls):
-            base, z, t, l = m.predict(xh16_np)
-    torch.cuda.synchronize()
-    dt16 = max_over_ranks(time.perf_counter() - t0)
-    e2e["fp16_input"] = dict(value=world * ne * args.steps / dt16, unit="sites/s", h2d_bytes_per_step=world * ne * 528 * 2,
-                             ms_per_step=dt16 / args.steps * 1e3, api="Clairvoyante.predict(X.astype(float16)), pinned")
-    del xh16, xh16_np
+    slim = train = None
+    if not args.no_extra:
+        if args.variant == "v3":
+            # BASELINE configs[2]: v3_slim, site list sharded 1 -> N GPUs, recorded at every N the driver runs
+            s = inference_leg(args, cvs, "v3_slim", initializers.init_weights("v3_slim", seed=0), local, rank, world, barrier,
+                              max_over_ranks, max(2, args.steps // 2), 2, False)
+            slim = dict(metric=METRIC, value=s["value"], unit="sites/s", ms_per_step=s["ms_per_step"], sites_per_gpu_per_step=s["n"],
+                        vs_v3=s["value"] / value, e2e=s["e2e"], gpu_launches=s["launches"],
+                        kernels={k: dict(ms_per_launch=v["ms_per_launch"], share=v["share"]) for k, v in s["kernels"].items()},
+                        config="configs[2]: v3_slim inference, %d sites per GPU, site-list sharded, no collective" % s["n"])
+            train = train_leg(args, cv3, W, local, rank, world, dist, barrier, max_over_ranks)
 
     cpu = None
     if rank == 0 and world == 1:
@@ -368,19 +435,19 @@ def main():
                           % (nsamp, thr))
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit="sites/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f32 (3x split-fp16 on tcgen05, f32 accumulate)" if tensor else "f32",
                     data="synthetic",
                     config=dict(workload="configs[1]: 4M synthetic (33,4,4) candidate sites, clairvoyante_%s forward, fp32" % args.variant,
-                                sites_per_gpu_per_step=n, unique_sites=pool_n, parallelism="site-list sharding, no collective",
+                                sites_per_gpu_per_step=n, unique_sites=r["pool_n"], parallelism="site-list sharding, no collective",
                                 l2="inputs (%.2f GB/GPU) exceed the 126 MB L2; no flush needed" % (n * 2112 / 1e9),
                                 weights="reference initialisers, seed 0",
                                 compute_mode=(("fp32-equivalent: %s on tcgen05 with 3x split-fp16 operands and fp32 accumulate, "
                                                "rest fp32 SIMT" % ("conv2+conv3+FC4+FC5/heads" if args.variant == "v3" else "conv3"))
                                               if tensor else "fp32 SIMT")),
-                    clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu, checksum=checksum)
+                    clocks=r["clocks"], e2e=r["e2e"], gpu_launches=r["launches"], roofline=roofline, cpu_baseline=cpu,
+                    slim=slim, train=train, build=source_hash())
         print(json.dumps(line))
-    m.close()
     if world > 1:
         dist.destroy_process_group()
 

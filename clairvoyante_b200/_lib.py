@@ -21,6 +21,17 @@ def sources():
         [os.path.join(INCLUDE, "cvb200.h")]
 
 
+def source_hash():
+    """12 hex digits over the library's sources (csrc/ + include/): names the build that a profile / traffic file belongs to"""
+    import hashlib
+    h = hashlib.sha256()
+    for fn in sources():
+        h.update(os.path.basename(fn).encode())
+        with open(fn, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:12]
+
+
 def build(force=False, verbose=False):
     """nvcc cross-compiles for sm_100a without a GPU (a few seconds)."""
     if not force and os.path.exists(LIB_PATH):

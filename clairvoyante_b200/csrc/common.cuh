@@ -83,6 +83,14 @@ __device__ __forceinline__ void store_out16(const OutDst& d, int64_t site, const
   }
 }
 
+// Programmatic dependent launch (the forward chain c1 -> conv2 -> conv3 -> FC4 -> tail is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization): pdl_wait() blocks until the preceding kernel of the stream has
+// completed and its writes are visible -- it is a no-op for a kernel launched the ordinary way; everything before it
+// (barrier init, TMEM allocation, descriptor prefetch, resident weight loads) overlaps the predecessor's last wave.
+// pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled once every CTA of this grid has issued it or exited.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 __device__ __forceinline__ float4 max4(float4 a, float4 b) {
   return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }

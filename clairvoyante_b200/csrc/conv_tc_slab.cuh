@@ -33,20 +33,29 @@ namespace tc {
 // column w rises by one), i.e. a descriptor start address advanced by whole COUT-row blocks -- a multiple of the swizzle
 // period for every layer here.  KH boxes are loaded once instead of 4 KH boxes per tile: conv3 ingests 70 KB of
 // activations per tile instead of 70 KB + 221 KB of weights.  SB is ignored.
-template <class F, int SA_, int SB_, int NCB_ = 4, bool RES_ = false>
+// BC = true (inference launches): the layer's bias arrives BY VALUE in the kernel parameters (BiasParam), i.e. in the
+// constant bank, and the epilogue's FFMA reads it as a c[0x0][..] operand -- the column -> channel map is a compile-time
+// function of the unrolled column index -- instead of one shared-memory load per four columns.  The training launches keep
+// the shared-memory copy: their bias changes every step and their launch parameters are frozen inside CUDA graphs.
+struct BiasParam { float v[64]; };
+template <class F, int SA_, int SB_, int NCB_ = 4, bool RES_ = false, bool BC_ = false, int EPI_ = 1>
 struct ConvSlabCfg {
   static constexpr int SA = SA_, SB = RES_ ? 1 : SB_, NCB = NCB_;
-  static constexpr bool RES = RES_;
+  static constexpr bool RES = RES_, BC = BC_;
+  static constexpr int EPI = EPI_;  // EXPERIMENT: 0 = round-1 pooling code for POOL != 4
   static constexpr int CB = F::NOUT / NCB;
   static constexpr int EPI_WARPS = 4 * NCB;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static_assert(F::NOUT % NCB == 0 && CB % 16 == 0 && THREADS <= 1024 && NCB <= 14, "epilogue column blocks");
+  static_assert(!BC_ || (CB % F::COUT == 0 && F::COUT <= 64), "constant-bank bias: column block = whole channel groups");
   static constexpr int SLAB_ROWS = ((128 + F::KH - 1 + 7) / 8) * 8;
   static constexpr int TILE_STEP = 129 - F::POOL;
   static constexpr int A_PLANE = SLAB_ROWS * F::ROW_BYTES;
   static constexpr int A_SLOT = 2 * A_PLANE;
   static constexpr int B_SLOT = 2 * F::NOUT * F::ROW_BYTES;
-  static constexpr int XCH_FLOATS = F::POOL > 1 ? 2 * NCB * 4 * (F::POOL - 1) * CB : 4;
+  // exchange block of one (accumulator buffer, column block): 4 quadrants x (POOL-1) published rows
+  static constexpr int XROWS = 4 * (F::POOL - 1);
+  static constexpr int XCH_FLOATS = F::POOL > 1 ? 2 * NCB * XROWS * CB : 4;
   static constexpr int W_BYTES = RES ? F::KH * B_SLOT : SB * B_SLOT;  // resident taps [kh][plane][4 * COUT rows], or the weight ring
   static constexpr int RING_BYTES = SA * A_SLOT + W_BYTES;
   static_assert(!RES || (F::COUT * F::ROW_BYTES) % (8 * F::ROW_BYTES) == 0, "tap blocks start on a swizzle period");
@@ -55,16 +64,46 @@ struct ConvSlabCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "does not fit in shared memory");
 };
 
-using Conv2Slab = ConvSlabCfg<Conv2Tc, 8, 16>;  // two tiles of operands in flight
+using Conv2Slab = ConvSlabCfg<Conv2Tc, 8, 16, 4, false, true>;  // two tiles of operands in flight
 using Conv3Slab = ConvSlabCfg<Conv3Tc, 3, 6>;  // (NCB = 6, 24 warps x 32 columns, measured no faster: 0.203 vs 0.199 ms)
 using SlimConv3Slab = ConvSlabCfg<SlimConv3Tc, 4, 8>;
 // resident-weight variants (CVB_CONV_RESIDENT=1): the shared memory the weight ring held goes to deeper activation rings
 using Conv2SlabRes = ConvSlabCfg<Conv2Tc, 12, 0, 4, true>;
-using Conv3SlabRes = ConvSlabCfg<Conv3Tc, 6, 0, 4, true>;
-using SlimConv3SlabRes = ConvSlabCfg<SlimConv3Tc, 8, 0, 4, true>;
+using Conv3SlabRes = ConvSlabCfg<Conv3Tc, 6, 0, 4, true, true>;
+using Conv3SlabResV0 = ConvSlabCfg<Conv3Tc, 6, 0, 4, true, false, 0>;  // EXPERIMENT variants (CVB_C3_VARIANT)
+using Conv3SlabResV1 = ConvSlabCfg<Conv3Tc, 6, 0, 4, true, true, 0>;
+using SlimConv3SlabRes = ConvSlabCfg<SlimConv3Tc, 8, 0, 4, true, true>;
 
+// 128-bit shared-memory load executed only by the lanes with pred != 0; the others get {d, d, d, d} and cost no
+// shared-memory wavefront (these kernels are bound by the shared-memory pipe -- tensor-core operand fetch, shuffles -- so a
+// load that all 32 lanes execute for the sake of two of them is four wavefronts too many; measured: +7 % on conv3)
+// (not volatile: the compiler may schedule these loads freely -- all of a tile's neighbour loads in flight at once -- and
+// what keeps them below the named barrier that publishes the rows is a data dependency: the address includes the token that
+// named_bar_sync_tok returns)
+__device__ __forceinline__ float4 lds128_if(const float* p, bool pred, float d) {
+  float4 r;
+  asm(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "setp.ne.b32 P1, %5, 0;\n\t"
+      "mov.f32 %0, %6;\n\t"
+      "mov.f32 %1, %6;\n\t"
+      "mov.f32 %2, %6;\n\t"
+      "mov.f32 %3, %6;\n\t"
+      "@P1 ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t"
+      "}\n"
+      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+      : "r"(smem_u32(p)), "r"((int)pred), "f"(d));
+  return r;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+// the same barrier, returning 0 as a value the compiler cannot see through: add it to an address to order a load after it
+__device__ __forceinline__ int named_bar_sync_tok(int id, int nthreads) {
+  int tok;
+  asm volatile("bar.sync %1, %2;\n\tmov.u32 %0, 0;\n" : "=r"(tok) : "r"(id), "r"(nthreads) : "memory");
+  return tok;
 }
 
 template <class F, class S>
@@ -73,7 +112,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
             const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ CUtensorMap map_b3,
             const __grid_constant__ CUtensorMap map_b4,  // 3-D (k, row, plane), box {BK, nb*COUT, 2}
             int64_t n, const float* __restrict__ bias, const float* __restrict__ inv_scale, __half* __restrict__ out_hi,
-            __half* __restrict__ out_lo, int ablate) {
+            __half* __restrict__ out_lo, int ablate, const __grid_constant__ BiasParam bias_c) {
   // ablate (timing experiments only, results are wrong): 1 = epilogue skips pooling/SELU/stores, 2 = no MMAs issued,
   // 4 = weight boxes are not loaded, 8 = activation slabs are not loaded, 16 = no global stores, 32 = no pooling
   extern __shared__ uint8_t smem_raw[];
@@ -95,7 +134,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
   static_assert((2 * S::SA + 2 * S::SB + 5) * 8 + 8 <= 512, "barrier block");
 
   __shared__ float bias_s[F::COUT];
-  if (threadIdx.x < F::COUT) bias_s[threadIdx.x] = F::ACT ? bias[threadIdx.x] : 0.f;
+  if (!S::BC && threadIdx.x < F::COUT) bias_s[threadIdx.x] = F::ACT ? bias[threadIdx.x] : 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t total_rows = n * F::RPS;
   const int64_t ntiles = (total_rows + S::TILE_STEP - 1) / S::TILE_STEP;
@@ -125,6 +164,8 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
         for (int kh = 0; kh < F::KH; ++kh)
           tma_load_3d(b_ring + kh * S::B_SLOT, &map_b4, w_full, (3 - F::PADL) * F::CIN, kh * F::NOUT, 0);
       }
+      pdl_wait();  // the activations are the previous kernel's output (the resident taps above are not)
+      pdl_launch_dependents();
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int r0 = (int)(tile * S::TILE_STEP);
         for (int i = 0; i < 4; ++i, ++ia) {
@@ -236,44 +277,46 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
       if (lane == 0) mbar_arrive(&acc_empty[buf]);  // the accumulator is in registers: let the next tile's MMAs start
       if (ablate & 1) continue;
       if (F::POOL > 1 && !(ablate & 32)) {
-        float* xb = xch + ((size_t)(buf * S::NCB + wblk) * 4) * (F::POOL - 1) * CB;  // [q][POOL-1][CB]
+        // Branch-free pooling.  v[r + d] for d < POOL comes from a warp shuffle; for the last POOL-1 lanes of a quadrant the
+        // shuffle runs off the warp (and returns the lane's own value, harmless under max) and the missing rows are the
+        // first rows of the NEXT quadrant, published through shared memory and read by those lanes alone through a
+        // predicated load whose default is -inf (lds128_if) -- no select and no divergence (the first version's ternaries
+        // compiled to BSSY / BSYNC / WARPSYNC sequences in the POOL = 4 kernel), and no wavefront spent on the other lanes.
+        float* xb = xch + (size_t)(buf * S::NCB + wblk) * S::XROWS * CB;
         if (lane < F::POOL - 1) {
           float* d = xb + (q * (F::POOL - 1) + lane) * CB;
 #pragma unroll
           for (int j = 0; j < CB; j += 4) *reinterpret_cast<float4*>(d + j) = make_float4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
         }
-        named_bar_sync(1 + wblk, 128);  // the four quadrant warps of this column block
-        // rows 0..POOL-2 of the next quadrant (unused for q = 3); read as 128-bit vectors, one group of 4 channels at a time,
-        // by the last POOL-1 lanes only (a scalar predicated load per channel cost 3 x COUT warp instructions per tile)
-        const float4* nx = reinterpret_cast<const float4*>(xb + ((q + 1) & 3) * (F::POOL - 1) * CB);
-        constexpr int C4 = CB / 4;
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int tok = named_bar_sync_tok(1 + wblk, 128);  // the four quadrant warps of this column block
+        const int nq = ((q + 1) & 3) * (F::POOL - 1) * CB + tok;         // first published row of the next quadrant
         if (F::POOL == 4) {
-          // tree: m2[r] = max(v[r], v[r+1]); m4[r] = max(m2[r], m2[r+2]) -- two shuffles per channel instead of three
-          // (the shuffle pipe, one warp instruction per clock per SM, is a measurable part of this epilogue)
+          // tree: m2[r] = max(v[r], v[r+1]); m4[r] = max(m2[r], m2[r+2]) -- two shuffles per channel instead of three.
+          // outside rows: lane 31 needs v[32] for m2; lanes 30 / 31 need m2[32] = max(v[32], v[33]) / m2[33] = max(v[33], v[34])
+          const float* p1 = xb + nq;
+          const float* pa = xb + nq + (lane >= 30 ? (lane - 30) * CB : 0);
+          const float* pb = xb + nq + (lane >= 30 ? (lane - 29) * CB : 0);
 #pragma unroll
-          for (int g = 0; g < C4; ++g) {
-            const float4 n0 = lane == 31 ? nx[g] : z4;                                   // v[32] for lane 31
-            const float4 na = lane >= 30 ? nx[(lane - 30) * C4 + g] : z4;                // m2[lane + 2] = max(v[lane+2], v[lane+3])
-            const float4 nb2 = lane >= 30 ? nx[(lane - 29) * C4 + g] : z4;
-            const float n0v[4] = {n0.x, n0.y, n0.z, n0.w};
+          for (int g = 0; g < CB / 4; ++g) {
+            const float4 n1 = lds128_if(p1 + 4 * g, lane == 31, -INFINITY), na = lds128_if(pa + 4 * g, lane >= 30, -INFINITY),
+                         nb2 = lds128_if(pb + 4 * g, lane >= 30, -INFINITY);
+            const float n1v[4] = {n1.x, n1.y, n1.z, n1.w};
             const float m2n[4] = {fmaxf(na.x, nb2.x), fmaxf(na.y, nb2.y), fmaxf(na.z, nb2.z), fmaxf(na.w, nb2.w)};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int j = 4 * g + e;
               const float v = raw[j];
-              float t1 = __shfl_down_sync(0xffffffffu, v, 1);
-              if (lane == 31) t1 = n0v[e];
-              const float m2 = fmaxf(v, t1);
-              float t2 = __shfl_down_sync(0xffffffffu, m2, 2);
-              if (lane >= 30) t2 = m2n[e];
-              raw[j] = fmaxf(m2, t2);
+              const float m2 = fmaxf(fmaxf(v, __shfl_down_sync(0xffffffffu, v, 1)), n1v[e]);
+              raw[j] = fmaxf(fmaxf(m2, __shfl_down_sync(0xffffffffu, m2, 2)), m2n[e]);
             }
           }
-        } else {
+        } else if (S::EPI == 0) {
+          const float4* nx = reinterpret_cast<const float4*>(xb + ((q + 1) & 3) * (F::POOL - 1) * CB);
+          constexpr int C4 = CB / 4;
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int g = 0; g < C4; ++g) {
-            float nv[F::POOL > 1 ? F::POOL - 1 : 1][4];  // nv[d-1] = v[lane + d] for the lanes whose window leaves the quadrant
+            float nv[F::POOL > 1 ? F::POOL - 1 : 1][4];
 #pragma unroll
             for (int d = 1; d < F::POOL; ++d) {
               const float4 t = lane + d >= 32 ? nx[(lane + d - 32) * C4 + g] : z4;
@@ -290,6 +333,28 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
                 if (lane + d >= 32) t = nv[d - 1][e];
                 mx = fmaxf(mx, t);
               }
+              raw[j] = mx;
+            }
+          }
+        } else {
+          const float* pd[F::POOL > 1 ? F::POOL - 1 : 1];
+#pragma unroll
+          for (int d = 1; d < F::POOL; ++d) pd[d - 1] = xb + nq + (lane + d >= 32 ? (lane + d - 32) * CB : 0);
+#pragma unroll
+          for (int g = 0; g < CB / 4; ++g) {
+            float nv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int d = 1; d < F::POOL; ++d) {
+              const float4 t = lds128_if(pd[d - 1] + 4 * g, lane + d >= 32, -INFINITY);
+              nv[0] = fmaxf(nv[0], t.x); nv[1] = fmaxf(nv[1], t.y); nv[2] = fmaxf(nv[2], t.z); nv[3] = fmaxf(nv[3], t.w);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * g + e;
+              const float v = raw[j];
+              float mx = fmaxf(v, nv[e]);
+#pragma unroll
+              for (int d = 1; d < F::POOL; ++d) mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, v, d));
               raw[j] = mx;  // max over rows r .. r+POOL-1 (pooling raw accumulators before SELU is exact, see conv_tc.cuh)
             }
           }
@@ -298,9 +363,14 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
 #pragma unroll
       for (int cc = 0; cc < CB; cc += 16) {
         float pv[16];
-        const float* b16 = bias_s + (wblk * CB + cc) % F::COUT;  // channel of accumulator column c is c mod COUT (16 | CB, COUT)
+        // channel of accumulator column c is c mod COUT (16 | CB, COUT); CB is a multiple of COUT or equal to it in every
+        // configuration, so the channel of (wblk * CB + cc + j) does not depend on wblk: a constant-bank offset when BC
+        const float* b16 = bias_s + (wblk * CB + cc) % F::COUT;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pv[j] = F::ACT ? selu_f(fmaf(raw[cc + j], isc, b16[j])) : raw[cc + j] * isc;
+        for (int j = 0; j < 16; ++j) {
+          const float bj = S::BC ? bias_c.v[(cc + j) % F::COUT] : b16[j];
+          pv[j] = F::ACT ? selu_f(fmaf(raw[cc + j], isc, bj)) : raw[cc + j] * isc;
+        }
         if (F::OUT_F32) {
           if (store) {  // 64 B per thread: two full-sector 256-bit stores
             float* d = reinterpret_cast<float*>(out_hi) + o + cc;

@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -60,6 +61,8 @@ struct VarInfo {
 // sites per device pass: bounds the intermediates and makes k_fc4's grid exactly one wave
 // (M-tile 96 sites x #SMs for v3; 224 x #SMs for slim)
 
+static const int64_t kFc4SplitSites = 18 * 128;  // largest batch whose FC4 is split over K (36 CTAs x 4 slices = one wave)
+
 struct cvb_model {
   int variant = 0, device = 0, compute_mode = CVB_COMPUTE_FP32, num_sms = 148;
   int64_t CHUNK = 96 * 148;
@@ -75,6 +78,7 @@ struct cvb_model {
   static constexpr int NSLOT = 4;
   float *d_x[NSLOT] = {}, *d_out[NSLOT] = {}, *d_lg[NSLOT] = {};
   __half* d_x16[NSLOT] = {};  // narrow input slots (fp16 values, int16 / uint8 raw counts: cvb_predict_host_f16 / _counts_*)
+  float* d_fc4ws = nullptr;   // split-K FC4 of small batches: per-chunk partial sums [36][kFc4SplitSites][352]
   float* d_xw = nullptr;      // fp32 scratch of one chunk for the front kernels that cannot read a narrow feed themselves
   float *h_x[NSLOT] = {}, *h_out[NSLOT] = {}, *h_lg[NSLOT] = {};
   cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
@@ -88,6 +92,8 @@ struct cvb_model {
   bool tc_ready = false, tc_weights_dirty = true;
   CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
   CUtensorMap map_bh_hi, map_bh_lo;  // FC4 weights with NH/2-row boxes (cluster multicast)
+  CUtensorMap map_b80_hi, map_b80_lo;  // ... with 80-row boxes (k_fc4_both's second N-half: 160 rows per stage)
+  int tc_fc4_both = 1;                 // large batches: k_fc4_both (128 sites x all 336 outputs per CTA)
   CUtensorMap map_ah_hi, map_ah_lo;  // FC4 activations with BM/2-row boxes (4-CTA clusters)
   int tc_fc4_cluster = 1;
   // conv3 on tensor cores: B = rearranged conv3 weights [3*192][128], A = p2 hi/lo [sites*28][128]
@@ -108,6 +114,7 @@ struct cvb_model {
   int tc_slab = 1;     // slab-mode conv kernels (conv_tc_slab.cuh): A loaded once per (tile, w'), re-used across kh
   int slim_fc4_tc = 0; // CVB_SLIM_FC4_TC=1: v3_slim inference FC4 as a split-bf16 tcgen05 GEMM (opt-in until run on a B200)
   uint16_t *d_p3s = nullptr, *d_w4ts = nullptr;  // its operands: planes of the conv3 output / of fc4/kernel^T
+  tc::BiasParam hb2 = {}, hb3 = {};  // host copies of conv2/bias, conv3/bias: passed by value to the inference conv kernels
   int tc_resident = 0; // CVB_CONV_RESIDENT bit mask: 1 = conv3, 2 = conv2 keep their taps in shared memory (ConvSlabCfg RES;
                        // opt-in until it has been timed and parity-checked on a B200)
   CUtensorMap map_c2slab, map_c3slab;
@@ -281,7 +288,7 @@ extern "C" int cvb_destroy(cvb_model* m) {
   cudaFree(m->d_p3s); cudaFree(m->d_w4ts);
   cudaFree(m->d_w4t_hi); cudaFree(m->d_w4t_lo); cudaFree(m->d_absmax); cudaFree(m->d_inv_scale);
   for (int i = 0; i < cvb_model::NSLOT; ++i) {
-    if (i == 0) cudaFree(m->d_xw);
+    if (i == 0) { cudaFree(m->d_xw); cudaFree(m->d_fc4ws); }
     cudaFree(m->d_x[i]); cudaFree(m->d_x16[i]); cudaFree(m->d_out[i]); cudaFree(m->d_lg[i]);
     cudaFreeHost(m->h_x[i]); cudaFreeHost(m->h_out[i]); cudaFreeHost(m->h_lg[i]);
     if (m->events) { cudaEventDestroy(m->e_h2d[i]); cudaEventDestroy(m->e_comp[i]); cudaEventDestroy(m->e_d2h[i]); }
@@ -479,6 +486,13 @@ static int tc_setup(cvb_model* m) {
   if (make_map_f16(&m->map_b_lo, m->d_w4t_lo, F::N, K, F::BK, F::NH, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   if (make_map_f16(&m->map_bh_hi, m->d_w4t_hi, F::N, K, F::BK, F::NH / 2, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   if (make_map_f16(&m->map_bh_lo, m->d_w4t_lo, F::N, K, F::BK, F::NH / 2, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  if (make_map_f16(&m->map_b80_hi, m->d_w4t_hi, F::N, K, F::BK, tc::Fc4Both::N1 / 2, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  if (make_map_f16(&m->map_b80_lo, m->d_w4t_lo, F::N, K, F::BK, tc::Fc4Both::N1 / 2, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  CK(cudaFuncSetAttribute(tc::k_fc4_both, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Fc4Both::SMEM_BYTES));
+  {
+    const char* e = getenv("CVB_FC4_BOTH");
+    m->tc_fc4_both = e && e[0] == '1';  // EXPERIMENT: slower than the two-wave kernel so far (register spills in the epilogue)
+  }
   CK(cudaFuncSetAttribute(tc::k_fc4_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tc::k_fc4_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tc::k_fc4_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
@@ -595,7 +609,7 @@ static int tc_setup_slim(cvb_model* m) {
   CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::SlimConv3SlabRes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           tc::SlimConv3SlabRes::SMEM_BYTES));
   const char* er = getenv("CVB_CONV_RESIDENT");
-  m->tc_resident = er ? atoi(er) : 0;
+  m->tc_resident = er ? atoi(er) : 1;  // measured on B200: 0.317 -> 0.207 ms per 33,152-site chunk, bit-identical
   const char* ef = getenv("CVB_SLIM_FC4_TC");
   m->slim_fc4_tc = ef && ef[0] == '1';
   if (m->slim_fc4_tc) {
@@ -615,6 +629,13 @@ static int slim_fc4_tc_forward(cvb_model* m, int64_t n, cudaStream_t st);
 // (re)build the split fp16 copy of fc4/kernel on `st` if the fp32 master changed
 static int tc_refresh_weights(cvb_model* m, cudaStream_t st) {
   if (!m->tc_weights_dirty) return 0;
+  {  // host copies of the conv biases for the by-value kernel parameter (BiasParam); weights change rarely on this path
+    const VarInfo* b2 = m->info("conv2/bias");
+    const VarInfo* b3 = m->info("conv3/bias");
+    CK(cudaMemcpyAsync(m->hb2.v, m->d_params + b2->offset, (size_t)b2->numel * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(m->hb3.v, m->d_params + b3->offset, (size_t)b3->numel * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
   if (m->variant == CVB_V3_SLIM) {
     if (m->slim_fc4_tc && slim_fc4_tc_weights(m, st)) return 1;
     using C = tc::SlimConv3Tc;
@@ -679,6 +700,10 @@ extern "C" int cvb_set_compute_mode(cvb_model* m, int mode) {
   }
   m->compute_mode = mode;
   m->CHUNK = (int64_t)m->num_sms * (m->variant == CVB_V3 ? (mode == CVB_COMPUTE_FP32 ? 96 : 128) : 224);
+  if (const char* e = getenv("CVB_CHUNK_PER_SM")) {  // experiment: sites per SM per launch (FC4 runs 2 CTAs per 128 sites)
+    const int v = atoi(e);
+    if (v >= 32 && v <= 224) m->CHUNK = (int64_t)m->num_sms * v;
+  }
   return 0;
 }
 extern "C" int cvb_set_train_mode(cvb_model* m, int mode) {
@@ -699,6 +724,38 @@ extern "C" int64_t cvb_kernel_launches(const cvb_model* m) { return m ? m->launc
 // ------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------
+// cudaLaunchKernelEx with the two launch attributes this library uses: a cluster shape and programmatic dependent launch
+// (the kernel may be scheduled while its predecessor in the stream is still in its last wave; it calls pdl_wait() before it
+// touches the predecessor's output, common.cuh)
+template <class... P, class... A>
+static cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, int cluster_y,
+                            bool pdl, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (cluster_x * cluster_y > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = cluster_x; at[na].val.clusterDim.y = cluster_y; at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+static bool use_pdl(const cvb_model* m) {
+  static const bool on = !(getenv("CVB_PDL") && getenv("CVB_PDL")[0] == '0');
+  return on && !m->profiling;  // (event records between the kernels would serialise them anyway)
+}
+
 template <class K>
 static cudaError_t set_smem(K kernel, int bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -721,15 +778,33 @@ static int launch_conv_tc(cvb_model* m, int resident, int64_t n, cudaStream_t st
                           const CUtensorMap& a_lo,
                           const CUtensorMap& b_hi, const CUtensorMap& b_lo, const CUtensorMap& a4, const CUtensorMap& b2,
                           const CUtensorMap& b3, const CUtensorMap& b4, const CUtensorMap& h2, const CUtensorMap& h3,
-                          const CUtensorMap& h4, const float* bias, const float* inv_scale, __half* out_hi, __half* out_lo) {
+                          const CUtensorMap& h4, const float* bias, const tc::BiasParam& bc, const float* inv_scale, __half* out_hi,
+                          __half* out_lo) {
   if (m->tc_slab && slab) {
     const int64_t st_tiles = (n * T::RPS + S::TILE_STEP - 1) / S::TILE_STEP;
     const int g = (int)std::min<int64_t>(st_tiles, m->num_sms);
     static const int ablate = getenv("CVB_ABLATE") ? atoi(getenv("CVB_ABLATE")) : 0;  // timing experiments only
+    static const int c3v = getenv("CVB_C3_VARIANT") ? atoi(getenv("CVB_C3_VARIANT")) : -1;  // EXPERIMENT
+    if constexpr (std::is_same<SR, tc::Conv3SlabRes>::value) {
+      if (resident && c3v == 0) {
+        CK(set_smem(tc::k_conv_slab<T, tc::Conv3SlabResV0>, tc::Conv3SlabResV0::SMEM_BYTES));
+        CK(launch_k(tc::k_conv_slab<T, tc::Conv3SlabResV0>, dim3(g), dim3(SR::THREADS), tc::Conv3SlabResV0::SMEM_BYTES, st, 1, 1,
+                    use_pdl(m), *slab, b2, b3, b4, n, bias, inv_scale, out_hi, out_lo, ablate, bc));
+        return 0;
+      }
+      if (resident && c3v == 1) {
+        CK(set_smem(tc::k_conv_slab<T, tc::Conv3SlabResV1>, tc::Conv3SlabResV1::SMEM_BYTES));
+        CK(launch_k(tc::k_conv_slab<T, tc::Conv3SlabResV1>, dim3(g), dim3(SR::THREADS), tc::Conv3SlabResV1::SMEM_BYTES, st, 1, 1,
+                    use_pdl(m), *slab, b2, b3, b4, n, bias, inv_scale, out_hi, out_lo, ablate, bc));
+        return 0;
+      }
+    }
     if (resident)
-      tc::k_conv_slab<T, SR><<<g, SR::THREADS, SR::SMEM_BYTES, st>>>(*slab, b2, b3, b4, n, bias, inv_scale, out_hi, out_lo, ablate);
+      CK(launch_k(tc::k_conv_slab<T, SR>, dim3(g), dim3(SR::THREADS), SR::SMEM_BYTES, st, 1, 1, use_pdl(m), *slab, b2, b3, b4, n, bias,
+                  inv_scale, out_hi, out_lo, ablate, bc));
     else
-      tc::k_conv_slab<T, S><<<g, S::THREADS, S::SMEM_BYTES, st>>>(*slab, b2, b3, b4, n, bias, inv_scale, out_hi, out_lo, ablate);
+      CK(launch_k(tc::k_conv_slab<T, S>, dim3(g), dim3(S::THREADS), S::SMEM_BYTES, st, 1, 1, use_pdl(m), *slab, b2, b3, b4, n, bias,
+                  inv_scale, out_hi, out_lo, ablate, bc));
     CK(cudaGetLastError());
     return 0;
   }
@@ -824,7 +899,7 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
         using T = tc::Conv2Tc;
         __half* p2_hi = reinterpret_cast<__half*>(m->d_p2);
         if (launch_conv_tc<T, tc::Conv2Slab, tc::Conv2SlabRes>(m, m->tc_resident & 2, n, st, &m->map_c2slab, m->map_c2a_hi, m->map_c2a_lo, m->map_c2b_hi, m->map_c2b_lo, m->map_c2a4, m->map_c2b2,
-                              m->map_c2b3, m->map_c2b4, m->map_c2h2, m->map_c2h3, m->map_c2h4, m->var("conv2/bias"),
+                              m->map_c2b3, m->map_c2b4, m->map_c2h2, m->map_c2h3, m->map_c2h4, m->var("conv2/bias"), m->hb2,
                               m->d_inv_scale + 2, p2_hi, p2_hi + m->p2_rows * 128))
           return 1;
         m->launches += 1;
@@ -857,7 +932,7 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
         __half* p3_hi = reinterpret_cast<__half*>(m->d_p3);
         if (launch_conv_tc<T, tc::Conv3Slab, tc::Conv3SlabRes>(m, m->tc_resident & 1, n, st, &m->map_c3slab, m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo,
                                              m->map_c3a4, m->map_c3b2, m->map_c3b3, m->map_c3b4, m->map_c3h2, m->map_c3h3,
-                                             m->map_c3h4, m->var("conv3/bias"), m->d_inv_scale + 1, p3_hi,
+                                             m->map_c3h4, m->var("conv3/bias"), m->hb3, m->d_inv_scale + 1, p3_hi,
                                              p3_hi + m->alloc_sites * 4608))
           return 1;
       } else if (tensor) {
@@ -878,30 +953,50 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
       const unsigned tiles4 = (unsigned)((n + F::BM - 1) / F::BM);
       __half* h4hi = m->tc_tail ? m->d_h4s : nullptr;
       __half* h4lo = m->tc_tail ? m->d_h4s + (size_t)m->alloc_sites * 336 : nullptr;
-      if (m->tc_fc4_cluster >= 2 && tiles4 >= 2) {
+      // small batches: split the 36 K-chunks over gridDim.z so that ~every SM streams a slice of W4 (k_fc4_tc, `ws`)
+      static const bool split_ok = !(getenv("CVB_FC4_SPLITK") && getenv("CVB_FC4_SPLITK")[0] == '0');
+      unsigned ksplit = 1;
+      if (split_ok) {
+        const unsigned ctas = 2 * ((tiles4 + 1) & ~1u);
+        for (unsigned k : {36u, 18u, 12u, 9u, 6u, 4u, 3u, 2u})
+          if ((int64_t)n <= kFc4SplitSites && ctas * k <= (unsigned)sms + 4) { ksplit = k; break; }
+      }
+      float* ws = nullptr;
+      const int64_t ws_plane = (int64_t)kFc4SplitSites * 2 * F::NH;
+      if (ksplit > 1) {
+        if (!m->d_fc4ws) CK(cudaMalloc(&m->d_fc4ws, (size_t)36 * ws_plane * 4));
+        ws = m->d_fc4ws;
+      }
+      if (ksplit == 1 && m->tc_fc4_both) {
+        using G = tc::Fc4Both;
+        // pairs of site tiles share the weight operand; a padding tile stores nothing
+        CK(launch_k(tc::k_fc4_both, dim3((tiles4 + 1) & ~1u), dim3(G::THREADS), G::SMEM_BYTES, st, 2, 1, use_pdl(m), m->map_a_hi,
+                    m->map_a_lo, m->map_bh_hi, m->map_bh_lo, m->map_b80_hi, m->map_b80_lo, n, 4608, m->var("fc4/bias"),
+                    (const float*)m->d_inv_scale, m->d_h4, h4hi, h4lo));
+      } else if (m->tc_fc4_cluster >= 2 && tiles4 >= 2) {
         const bool cl4 = m->tc_fc4_cluster >= 4;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2, (tiles4 + 1) & ~1u);  // pairs of site tiles; a padding tile loads zeros and stores nothing
-        cfg.blockDim = dim3(F::THREADS);
-        cfg.dynamicSmemBytes = F::SMEM_BYTES;
-        cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = cl4 ? 2 : 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
+        const dim3 g4(2, (tiles4 + 1) & ~1u, ksplit);  // pairs of site tiles; a padding tile loads zeros and stores nothing
         if (cl4)
-          CK(cudaLaunchKernelEx(&cfg, tc::k_fc4_tc<4>, m->map_ah_hi, m->map_ah_lo, m->map_bh_hi, m->map_bh_lo, n, 4608,
-                                m->var("fc4/bias"), (const float*)m->d_inv_scale, m->d_h4, h4hi, h4lo));
+          CK(launch_k(tc::k_fc4_tc<4>, g4, dim3(F::THREADS), F::SMEM_BYTES, st, 2, 2, use_pdl(m), m->map_ah_hi, m->map_ah_lo,
+                      m->map_bh_hi, m->map_bh_lo, n, 4608, m->var("fc4/bias"), (const float*)m->d_inv_scale, m->d_h4, h4hi, h4lo, ws,
+                      ws_plane));
         else
-          CK(cudaLaunchKernelEx(&cfg, tc::k_fc4_tc<2>, m->map_a_hi, m->map_a_lo, m->map_bh_hi, m->map_bh_lo, n, 4608,
-                                m->var("fc4/bias"), (const float*)m->d_inv_scale, m->d_h4, h4hi, h4lo));
+          CK(launch_k(tc::k_fc4_tc<2>, g4, dim3(F::THREADS), F::SMEM_BYTES, st, 1, 2, use_pdl(m), m->map_a_hi, m->map_a_lo,
+                      m->map_bh_hi, m->map_bh_lo, n, 4608, m->var("fc4/bias"), (const float*)m->d_inv_scale, m->d_h4, h4hi, h4lo, ws,
+                      ws_plane));
       } else {
-        tc::k_fc4_tc<1><<<dim3(2, tiles4), F::THREADS, F::SMEM_BYTES, st>>>(m->map_a_hi, m->map_a_lo, m->map_b_hi, m->map_b_lo, n,
-                                                                            4608, m->var("fc4/bias"), m->d_inv_scale, m->d_h4,
-                                                                            h4hi, h4lo);
+        tc::k_fc4_tc<1><<<dim3(2, tiles4, ksplit), F::THREADS, F::SMEM_BYTES, st>>>(m->map_a_hi, m->map_a_lo, m->map_b_hi, m->map_b_lo, n,
+                                                                                    4608, m->var("fc4/bias"), m->d_inv_scale, m->d_h4,
+                                                                                    h4hi, h4lo, ws, ws_plane);
       }
       CK(cudaGetLastError());
+      if (ws) {
+        CK(launch_k(tc::k_fc4_reduce, dim3((unsigned)std::min<int64_t>((n * 84 + 127) / 128, (int64_t)sms * 8)), dim3(128), 0, st, 1, 1,
+                    use_pdl(m), (const float*)ws, ws_plane, 4608 / F::KCH, n, m->var("fc4/bias"), (const float*)m->d_inv_scale, m->d_h4,
+                    h4hi, h4lo));
+        CK(cudaGetLastError());
+        m->launches += 1;
+      }
       if (prof_mark(m, st)) return 1;
     } else {
       using F = FcCfg<336, 21, 16, 12, 8>;
@@ -917,9 +1012,8 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
       tc::TailHeads th{m->var("fc5/bias"), m->var("YBaseChangeSigmoid/bias"), m->var("YZygosityFC/kernel"), m->var("YZygosityFC/bias"),
                        m->var("YVarTypeFC/kernel"), m->var("YVarTypeFC/bias"), m->var("YIndelLengthFC/kernel"),
                        m->var("YIndelLengthFC/bias")};
-      tc::k_tail_tc<<<(int)((n + T::BM - 1) / T::BM), T::THREADS, T::SMEM_BYTES, st>>>(m->map_ta_hi, m->map_ta_lo, m->map_tb_hi,
-                                                                                        m->map_tb_lo, n, th, m->d_inv_scale + 3, out16,
-                                                                                        logits16);
+      CK(launch_k(tc::k_tail_tc, dim3((unsigned)((n + T::BM - 1) / T::BM)), dim3(T::THREADS), T::SMEM_BYTES, st, 1, 1, use_pdl(m),
+                  m->map_ta_hi, m->map_ta_lo, m->map_tb_hi, m->map_tb_lo, n, th, (const float*)(m->d_inv_scale + 3), out16, logits16));
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
       m->launches -= 1;  // one fused kernel instead of FC5 + heads (the common "+= 5" below counts two)
@@ -959,7 +1053,7 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
       using T = tc::SlimConv3Tc;
       if (launch_conv_tc<T, tc::SlimConv3Slab, tc::SlimConv3SlabRes>(m, m->tc_resident & 1, n, st, &m->map_c3slab, m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo,
                                                m->map_c3a4, m->map_c3b2, m->map_c3b3,
-                            m->map_c3b4, m->map_c3h2, m->map_c3h3, m->map_c3h4, m->var("conv3/bias"), m->d_inv_scale + 1,
+                            m->map_c3b4, m->map_c3h2, m->map_c3h3, m->map_c3h4, m->var("conv3/bias"), m->hb3, m->d_inv_scale + 1,
                             reinterpret_cast<__half*>(m->d_p3), nullptr))
         return 1;
       if (prof_mark(m, st)) return 1;
@@ -1096,6 +1190,38 @@ static int predict_host_impl(cvb_model* m, const void* xv, int kind, int64_t n, 
                           (!logits16 || is_pinned(logits16));
   const int64_t CHUNK = m->CHUNK, cap = m->alloc_sites;
   const int64_t nchunks = (n + CHUNK - 1) / CHUNK;
+  if (nchunks == 1) {
+    // One chunk -- every call of the reference's drivers (predictBatchSize = 1000, callVar.py:184): nothing to pipeline, so
+    // the copy in, the kernels and the copy out go down ONE stream with no events in between, the four head blocks are packed
+    // back to back ([4 | 2 | 4 | 6] x np floats, np = n rounded up to 4 for the vector stores) and come back in one copy.
+    cudaStream_t st = m->s_comp;
+    const char* src = x;
+    if (!pinned_in) {
+      memcpy(m->h_x[0], src, (size_t)n * 528 * esz);
+      src = reinterpret_cast<const char*>(m->h_x[0]);
+    }
+    void* dx = kind == X_F32 ? (void*)m->d_x[0] : (void*)m->d_x16[0];
+    CK(cudaMemcpyAsync(dx, src, (size_t)n * 528 * esz, cudaMemcpyHostToDevice, st));
+    const int64_t np = (n + 3) & ~(int64_t)3;
+    float* o = m->d_out[0];
+    const OutDst dst{nullptr, o, o + np * 4, o + np * 6, o + np * 10};
+    if (forward_chunk(m, dx, kind, n, dst, logits16 ? m->d_lg[0] : nullptr, st)) return 1;
+    if (pinned_out) {
+      int64_t off = 0;
+      for (int h = 0; h < 4; off += np * kHeadW[h], ++h)
+        CK(cudaMemcpyAsync(heads[h], o + off, (size_t)n * kHeadW[h] * 4, cudaMemcpyDeviceToHost, st));
+      if (logits16) CK(cudaMemcpyAsync(logits16, m->d_lg[0], (size_t)n * 64, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      return 0;
+    }
+    CK(cudaMemcpyAsync(m->h_out[0], o, (size_t)np * 64, cudaMemcpyDeviceToHost, st));
+    if (logits16) CK(cudaMemcpyAsync(m->h_lg[0], m->d_lg[0], (size_t)n * 64, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int64_t off = 0;
+    for (int h = 0; h < 4; off += np * kHeadW[h], ++h) memcpy(heads[h], m->h_out[0] + off, (size_t)n * kHeadW[h] * 4);
+    if (logits16) memcpy(logits16, m->h_lg[0], (size_t)n * 64);
+    return 0;
+  }
   // software pipeline over chunks: the host enqueues H2D(c), kernels(c), D2H(c) and only then collects chunk c-LAG, so
   // the copy engines always have LAG chunks of work queued ahead of the host
   constexpr int NS = cvb_model::NSLOT, LAG = NS - 1;
@@ -1213,6 +1339,9 @@ static int ensure_train_work(cvb_model* m) {
   if (m->train) return 0;
   TrainWork* w = new TrainWork();
   w->cap = TRAIN_CHUNK;
+  CK(cudaMalloc(&w->seedbuf, 16));
+  CK(cudaMemset(w->seedbuf, 0, 16));
+  w->graphs_on = !(getenv("CVB_TRAIN_GRAPH") && getenv("CVB_TRAIN_GRAPH")[0] == '0');
   for (int i = 0; i < 2; ++i) {
     CK(cudaEventCreateWithFlags(&w->ev_up[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&w->ev_done[i], cudaEventDisableTiming));
@@ -1422,6 +1551,8 @@ using Conv2D = tc::ConvTcCfg<30, 2, 32, 16, 29, 1, 29, 0, 4, true, 2, false, tru
 // v3_slim conv3 (5x4, 16 -> 32, rows padded 2 + 33 + 2): forward = the inference configuration; data gradient 32 -> 16
 using SlimConv3D = tc::ConvTcCfg<37, 5, 32, 16, 33, 1, 33, 0, 4, true, 2, false, true>;  // g3h [.][37][128] -> gp2 [.][33][64]
 using SlimConv3DS = tc::ConvSlabCfg<SlimConv3D, 3, 6>;
+using SlimConv3FS = tc::ConvSlabCfg<tc::SlimConv3Tc, 4, 8>;             // the inference geometry with the bias read from memory
+using SlimConv3FR = tc::ConvSlabCfg<tc::SlimConv3Tc, 8, 0, 4, true>;
 using Conv2FS = tc::ConvSlabCfg<Conv2F, 4, 8>;
 using Conv3FS = tc::ConvSlabCfg<Conv3F, 3, 6>;
 using Conv3DS = tc::ConvSlabCfg<Conv3D, 3, 3>;
@@ -1457,11 +1588,11 @@ static int launch_train_conv(cvb_model* m, const uint16_t* act, int64_t act_plan
   if (resident) {
     auto k = tc::k_conv_slab<F, SR>;
     CK(set_smem(k, SR::SMEM_BYTES));
-    k<<<grid, SR::THREADS, SR::SMEM_BYTES, st>>>(ma, mb[0], mb[1], mb[2], nc, bias, inv_scale, reinterpret_cast<__half*>(out), nullptr, 0);
+    k<<<grid, SR::THREADS, SR::SMEM_BYTES, st>>>(ma, mb[0], mb[1], mb[2], nc, bias, inv_scale, reinterpret_cast<__half*>(out), nullptr, 0, tc::BiasParam{});
   } else {
     auto k = tc::k_conv_slab<F, S>;
     CK(set_smem(k, S::SMEM_BYTES));
-    k<<<grid, S::THREADS, S::SMEM_BYTES, st>>>(ma, mb[0], mb[1], mb[2], nc, bias, inv_scale, reinterpret_cast<__half*>(out), nullptr, 0);
+    k<<<grid, S::THREADS, S::SMEM_BYTES, st>>>(ma, mb[0], mb[1], mb[2], nc, bias, inv_scale, reinterpret_cast<__half*>(out), nullptr, 0, tc::BiasParam{});
   }
   CK(cudaGetLastError());
   m->launches += 1;
@@ -1494,7 +1625,7 @@ static int train_dropout5(cvb_model* m, int64_t nc, int n5, uint64_t seed, int64
   *h5in = w->h5;
   if (m->drop5_now <= 0.f) return 0;
   if (!w->d5) CK(cudaMalloc(&w->d5, (size_t)w->cap * 168 * 4));
-  k_dropout_fwd<<<gsz(nc * n5), 256, 0, st>>>(w->h5, w->d5, nc * n5, site0 * n5, seed ^ kSeed5, drop_const(m->drop5_now));
+  k_dropout_fwd<<<gsz(nc * n5), 256, 0, st>>>(w->h5, w->d5, nc * n5, site0 * n5, SeedRef{w->seedbuf, kSeed5}, drop_const(m->drop5_now));
   CK(cudaGetLastError());
   m->launches += 1;
   *h5in = w->d5;
@@ -1513,7 +1644,7 @@ static int train_forward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t se
   if (stc) {
     // conv3 on the tcgen05 slab kernel (the inference configuration already keeps every SELU output: no pooling in slim),
     // FC4 = c3 [sites][4224] . W4 as a split-bf16 GEMM (N = 36 in one 48-column tile)
-    if (launch_train_conv<tc::SlimConv3Tc, tc::SlimConv3Slab, tc::SlimConv3SlabRes>(m, w->p2h, w->cap * 37 * 64, w->wf3, nc, m->var("conv3/bias"), w->fsc + 1,
+    if (launch_train_conv<tc::SlimConv3Tc, trc::SlimConv3FS, trc::SlimConv3FR>(m, w->p2h, w->cap * 37 * 64, w->wf3, nc, m->var("conv3/bias"), w->fsc + 1,
                                                               w->c3, st))
       return 1;
     if (split_rows_bf16(w->c3, nc, 4224, w->p3s, w->cap * 4224, st)) return 1;
@@ -1531,7 +1662,7 @@ static int train_forward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t se
   }
   const float* d4 = w->h4;
   if (drop4 > 0.f) {
-    k_dropout_fwd<<<gsz(nc * 36), 256, 0, st>>>(w->h4, w->d4, nc * 36, index0, seed, drop_const(drop4));
+    k_dropout_fwd<<<gsz(nc * 36), 256, 0, st>>>(w->h4, w->d4, nc * 36, index0, SeedRef{w->seedbuf, 0}, drop_const(drop4));
     d4 = w->d4;
   }
   k_dense_small<true><<<gsz(nc * 18), 256, 0, st>>>(d4, 36, 36, m->var("fc5/kernel"), 18, m->var("fc5/bias"), w->h5, 18, nc);
@@ -1565,12 +1696,12 @@ static int train_backward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t s
   HeadW hw{m->var("YBaseChangeSigmoid/kernel"), m->var("YZygosityFC/kernel"), m->var("YVarTypeFC/kernel"),
            m->var("YIndelLengthFC/kernel")};
   k_heads_bwd<<<gsz(nc * (36 + 18)), 256, 0, st>>>(w->dlog, w->h5, nc, 36, 18, hw, w->g4, w->g5, 24, m->drop5_now > 0.f ? 1 : 0,
-                                                   seed ^ kSeed5, index0 / 36 * 18, drop_const(m->drop5_now));
+                                                   SeedRef{w->seedbuf, kSeed5}, index0 / 36 * 18, drop_const(m->drop5_now));
   // FC5
   k_gemm_tn<<<dim3(1, 1), 256, 0, st>>>(d4, 36, w->g5, 24, gvar(m, "fc5/kernel"), 18, 36, 18, nc);
   k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->g5, nc, 24, 18, gvar(m, "fc5/bias"));
   k_dense_bwd_small<<<gsz(nc * 36), 256, 0, st>>>(w->g5, 24, 18, m->var("fc5/kernel"), 36, w->g4b, 36, nc);
-  k_fc4_bwd_elem<<<gsz(nc * 36), 256, 0, st>>>(w->g4, w->g4b, w->h4, nc * 36, index0, seed, drop_const(drop4), drop4 > 0.f ? 1 : 0);
+  k_fc4_bwd_elem<<<gsz(nc * 36), 256, 0, st>>>(w->g4, w->g4b, w->h4, nc * 36, index0, SeedRef{w->seedbuf, 0}, drop_const(drop4), drop4 > 0.f ? 1 : 0);
   // FC4
   const bool stc = w->slim_tc && m->train_mode != CVB_TRAIN_FP32;
   k_colsum<<<dim3(2, 32), 256, 0, st>>>(w->g4, nc, 36, 36, gvar(m, "fc4/bias"));
@@ -1689,7 +1820,7 @@ static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, i
   }
   const float* d4 = w->h4;
   if (drop4 > 0.f) {
-    k_dropout_fwd<<<gsz(nc * 336), 256, 0, st>>>(w->h4, w->d4, nc * 336, index0, seed, drop_const(drop4));
+    k_dropout_fwd<<<gsz(nc * 336), 256, 0, st>>>(w->h4, w->d4, nc * 336, index0, SeedRef{w->seedbuf, 0}, drop_const(drop4));
     d4 = w->d4;
   }
   if (tcm) {
@@ -1732,7 +1863,7 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
            m->var("YIndelLengthFC/kernel")};
   const float* h5in = m->drop5_now > 0.f ? w->d5 : w->h5;  // what the three softmax heads read
   k_heads_bwd<<<gsz(nc * (336 + 168)), 256, 0, st>>>(w->dlog, w->h5, nc, 336, 168, hw, w->g4, w->g5, 176, m->drop5_now > 0.f ? 1 : 0,
-                                                     seed ^ kSeed5, index0 / 336 * 168, drop_const(m->drop5_now));
+                                                     SeedRef{w->seedbuf, kSeed5}, index0 / 336 * 168, drop_const(m->drop5_now));
   if (tcm) {
     // weight gradients of FC5 and the four heads as two tcgen05 contractions over K = sites:
     //   tmp5 [336][184] = d4^T . [g5 | dlog]   (cols 0..167 -> fc5/kernel, 168..171 -> base head: its input is dropout4)
@@ -1779,7 +1910,7 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
     k<<<(int)((nc + F::M - 1) / F::M), 256, F::SMEM_BYTES, st>>>(w->g5, nc, 176, w->w5t, nullptr, w->g4b, 336, 336);
     CK(cudaGetLastError());
   }
-  k_fc4_bwd_elem<<<gsz(nc * 336), 256, 0, st>>>(w->g4, w->g4b, w->h4, nc * 336, index0, seed, drop_const(drop4), drop4 > 0.f ? 1 : 0);
+  k_fc4_bwd_elem<<<gsz(nc * 336), 256, 0, st>>>(w->g4, w->g4b, w->h4, nc * 336, index0, SeedRef{w->seedbuf, 0}, drop_const(drop4), drop4 > 0.f ? 1 : 0);
   // FC4
   k_colsum<<<dim3((336 + 31) / 32, 32), 256, 0, st>>>(w->g4, nc, 336, 336, gvar(m, "fc4/bias"));
   if (m->train_mode != CVB_TRAIN_FP32) {
@@ -1931,15 +2062,64 @@ static int train_prepare_weights(cvb_model* m, cudaStream_t st, bool backward) {
   return 0;
 }
 
+// Runs `body` (a fixed sequence of launches on `st`) through a CUDA graph: the first use of a key runs eagerly (lazy
+// allocations, function attributes), the second is captured and instantiated, every later one is a single cudaGraphLaunch.
+// A training step is ~60 launches per micro-chunk of a few microseconds each; at the data-parallel shard sizes (1,250 tensors
+// per GPU at the reference's batch of 10,000 on 8 GPUs) the step was bound by launch overhead, not by the kernels.
+// What varies between steps is kept out of the launch parameters: the dropout seed is read from device memory (SeedRef),
+// the upload slot and the batch offset of the chunk are part of the key.
+template <class Body>
+static int run_captured(cvb_model* m, uint64_t key, cudaStream_t st, Body body) {
+  TrainWork* w = m->train;
+  if (!w->graphs_on) return body();
+  TrainWork::GraphEntry& e = w->graphs[key];
+  if (e.exec) {
+    CK(cudaGraphLaunch(e.exec, st));
+    m->launches += e.launches;
+    return 0;
+  }
+  if (e.uses++ == 0) return body();
+  const int64_t l0 = m->launches;
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    w->graphs_on = false;
+    return body();
+  }
+  const int rc = body();
+  cudaGraph_t g = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &g);
+  if (rc || ce != cudaSuccess || !g || cudaGraphInstantiate(&e.exec, g, 0) != cudaSuccess) {
+    cudaGetLastError();  // something in the sequence cannot be captured on this driver: eager launches from now on
+    if (g) cudaGraphDestroy(g);
+    e.exec = nullptr;
+    w->graphs_on = false;
+    m->launches = l0;
+    return body();
+  }
+  cudaGraphDestroy(g);
+  e.launches = m->launches - l0;
+  CK(cudaGraphLaunch(e.exec, st));
+  return 0;
+}
+static inline uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
 // forward + loss (+ backward) over a host batch in micro-chunks; loss terms accumulate in train->loss[0..3]
 static int train_pass(cvb_model* m, const float* x, const float* y, int64_t n, float drop4, uint64_t seed, bool backward) {
   if (ensure_train_work(m)) return 1;
   TrainWork* w = m->train;
   cudaStream_t st = m->s_comp;
   m->drop5_now = backward ? m->drop5 : 0.f;  // phase = False in getLoss (clairvoyante_v3.py:207-216)
-  CK(cudaMemsetAsync(w->loss, 0, 16 * 4, st));
-  if (backward) CK(cudaMemsetAsync(m->d_grad, 0, (size_t)(m->nparams + 16) * 4, st));
-  if (train_prepare_weights(m, st, backward)) return 1;
+  CK(cudaMemcpyAsync(w->seedbuf, &seed, 8, cudaMemcpyHostToDevice, st));  // (pageable source: staged before the call returns)
+  // what a captured sequence depends on besides the chunk: pass kind, arithmetic, dropout rates (baked into DropConst)
+  const uint64_t cfg = (uint64_t)(backward ? 1 : 0) | ((uint64_t)m->train_mode << 1) | ((uint64_t)(fbits(drop4) >> 8) << 4) |
+                       ((uint64_t)(fbits(m->drop5_now) >> 8) << 28);
+  auto key_of = [&](int64_t ci, int64_t nc) { return cfg * 0x9E3779B97F4A7C15ull + (uint64_t)(ci + 1) * 1000003ull + (uint64_t)nc * 7919ull; };
+  if (run_captured(m, key_of(-1, 0), st, [&]() -> int {
+        CK(cudaMemsetAsync(w->loss, 0, 16 * 4, st));
+        if (backward) CK(cudaMemsetAsync(m->d_grad, 0, (size_t)(m->nparams + 16) * 4, st));
+        return train_prepare_weights(m, st, backward);
+      }))
+    return 1;
   // micro-chunks alternate between two upload slots: chunk c+1 is copied on the H2D stream (a pageable source blocks the
   // host inside cudaMemcpyAsync) while chunk c's kernels, already enqueued, run on the compute stream
   int64_t ci = 0;
@@ -1954,11 +2134,15 @@ static int train_pass(cvb_model* m, const float* x, const float* y, int64_t n, f
     w->x = w->xs[slot];
     w->y = w->ys[slot];
     const int64_t n4 = m->variant == CVB_V3 ? 336 : 36;  // dropout counter = flat index into the whole batch's FC4 output
-    if (train_forward(m, nc, drop4, seed, s0 * n4, st)) return 1;
-    k_loss_grad<<<gsz(nc, 128), 128, 0, st>>>(w->logits, w->out16, w->y, nc, backward ? w->dlog : nullptr, w->loss);
-    CK(cudaGetLastError());
-    m->launches += 1;
-    if (backward && train_backward(m, nc, drop4, seed, s0 * n4, st)) return 1;
+    if (run_captured(m, key_of(ci, nc), st, [&]() -> int {
+          if (train_forward(m, nc, drop4, seed, s0 * n4, st)) return 1;
+          k_loss_grad<<<gsz(nc, 128), 128, 0, st>>>(w->logits, w->out16, w->y, nc, backward ? w->dlog : nullptr, w->loss);
+          CK(cudaGetLastError());
+          m->launches += 1;
+          if (backward && train_backward(m, nc, drop4, seed, s0 * n4, st)) return 1;
+          return 0;
+        }))
+      return 1;
     CK(cudaEventRecord(w->ev_done[slot], st));
   }
   return 0;

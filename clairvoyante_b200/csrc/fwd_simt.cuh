@@ -256,6 +256,7 @@ k_v3_c1_reg(const void* __restrict__ xv, int64_t n, const float* __restrict__ w1
   const int64_t gt = (int64_t)blockIdx.x * 128 + threadIdx.x;
   const int64_t site = gt >> 4;
   const int w = (int)(gt & 15) >> 2, cq = (int)(gt & 3);
+  if (threadIdx.x == 0) pdl_launch_dependents();  // conv2's CTAs may set themselves up during this grid's last wave
   if ((gt >> 5) * 2 >= n) return;  // whole warp past the end
   unsigned long long wr[4][2][4];  // [w'][channel pair][co]: {W[kw][2cp][co], W[kw][2cp+1][co]}, kw = w' - w + 1
 #pragma unroll
@@ -336,6 +337,92 @@ k_v3_c1_reg(const void* __restrict__ xv, int64_t n, const float* __restrict__ w1
       *reinterpret_cast<uint2*>(ohi + (h - 4) * 64) = *reinterpret_cast<const uint2*>(hi);
       *reinterpret_cast<uint2*>(olo + (h - 4) * 64) = *reinterpret_cast<const uint2*>(lo);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// k_slim_c1_reg: v3_slim's conv1 (clairvoyante_v3_slim.py:54-61: 1x4, 4 -> 8, SELU, no pooling) in the style of k_v3_c1_reg
+// -- registers only -- for the tensor-core conv2: 8 threads per site, thread (w, cq) owns output column w, channels
+// 4cq..4cq+3 and writes p1 [site][35][4*8] (rows 0 and 34 are conv2's zero SAME padding and are never written) as fp16
+// hi / lo planes (LO = false: the hi plane only, plain-fp16 mode).  Input: any element kind (widen_pos4).
+// ------------------------------------------------------------------------------------
+template <int KIND, bool LO>
+__global__ void __launch_bounds__(64)
+k_slim_c1_reg(const void* __restrict__ xv, int64_t n, const float* __restrict__ w1g, const float* __restrict__ b1g,
+              __half* __restrict__ p1_hi, __half* __restrict__ p1_lo) {
+  const int64_t gt = (int64_t)blockIdx.x * 64 + threadIdx.x;  // 64-thread blocks: 2 warps x 4 sites of staging fit the static limit
+  const int64_t site = gt >> 3;
+  const int w = (int)(gt & 7) >> 1, cq = (int)(gt & 1);
+  const int64_t wsite0 = (gt >> 5) * 4;  // first of this warp's four sites
+  if (wsite0 >= n) return;
+  unsigned long long wr[4][2][4];  // [w'][channel pair][co]: {W[kw][2cp][co], W[kw][2cp+1][co]}, kw = w' - w + 1
+#pragma unroll
+  for (int wp = 0; wp < 4; ++wp) {
+    const int kw = wp - w + 1;
+    const bool valid = kw >= 0 && kw <= 3;
+#pragma unroll
+    for (int cp = 0; cp < 2; ++cp)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kwc = valid ? kw : 0;
+        const float a = __ldg(w1g + (kwc * 4 + 2 * cp) * 8 + 4 * cq + j);
+        const float b = __ldg(w1g + (kwc * 4 + 2 * cp + 1) * 8 + 4 * cq + j);
+        wr[wp][cp][j] = valid ? pack_f32x2(a, b) : 0ull;
+      }
+  }
+  const float4 bias = __ldg(reinterpret_cast<const float4*>(b1g) + cq);
+  __shared__ __align__(16) float xs_all[2][4 * 528];
+  float* xs = xs_all[threadIdx.x >> 5];
+  {
+    const int lane = threadIdx.x & 31;
+    const int nsite = (int)(n - wsite0 < 4 ? n - wsite0 : 4);
+    constexpr int EB = XElem<KIND>::BYTES;
+    if constexpr (KIND == X_F32) {
+      const float* src = static_cast<const float*>(xv) + wsite0 * 528;
+      for (int c = lane; c < nsite * 132; c += 32) cp_async16(xs + c * 4, src + c * 4);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncwarp();
+    } else {
+      __shared__ __align__(16) unsigned char raw_all[2][4 * 528 * EB];
+      unsigned char* raw = raw_all[threadIdx.x >> 5];
+      const unsigned char* src = static_cast<const unsigned char*>(xv) + wsite0 * (528 * EB);
+      for (int c = lane; c < nsite * (33 * EB); c += 32) cp_async16(raw + c * 16, src + c * 16);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncwarp();
+      for (int c = lane; c < nsite * 132; c += 32)
+        *reinterpret_cast<float4*>(xs + c * 4) = widen_pos4<KIND>(raw + c * (4 * EB));
+      __syncwarp();
+    }
+  }
+  if (site >= n) return;
+  const ulonglong2* xp = reinterpret_cast<const ulonglong2*>(xs + ((gt >> 3) & 3) * 528);
+  __half* ohi = p1_hi + site * (35 * 32) + 32 + w * 8 + cq * 4;  // row 1 = conv1 row 0
+  __half* olo = p1_lo + site * (35 * 32) + 32 + w * 8 + cq * 4;
+#pragma unroll 3
+  for (int h = 0; h < 33; ++h) {
+    ulonglong2 xa[4];
+#pragma unroll
+    for (int wp = 0; wp < 4; ++wp) xa[wp] = xp[h * 4 + wp];
+    unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+    for (int wp = 0; wp < 4; ++wp)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ffma2(acc[j], xa[wp].x, wr[wp][0][j]);
+        ffma2(acc[j], xa[wp].y, wr[wp][1][j]);
+      }
+    float y[4];
+    const float bb[4] = {bias.x, bias.y, bias.z, bias.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      y[j] = selu_f(__uint_as_float((unsigned)acc[j]) + __uint_as_float((unsigned)(acc[j] >> 32)) + bb[j]);
+    __half2 hi[2], lo[2];
+    tc::split_f16x2(y[0], y[1], hi[0], lo[0]);
+    tc::split_f16x2(y[2], y[3], hi[1], lo[1]);
+    *reinterpret_cast<uint2*>(ohi + h * 32) = *reinterpret_cast<const uint2*>(hi);
+    if (LO) *reinterpret_cast<uint2*>(olo + h * 32) = *reinterpret_cast<const uint2*>(lo);
   }
 }
 

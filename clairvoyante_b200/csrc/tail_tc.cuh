@@ -99,6 +99,7 @@ k_tail_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
 
   if (warp == 0) {
     if (elect_one()) {
+      pdl_wait();
       for (int kb = 0; kb < F::NKB; ++kb) {
         const int s = kb % F::STAGES;
         const uint32_t ph = (kb / F::STAGES) & 1;

@@ -7,6 +7,7 @@
 // Data-gradient convolutions reuse k_conv_layer with flipped/transposed weights (k_flip_conv_weights),
 // ACT=false and pad-left 2; weight gradients are k_conv_wgrad (convs) and k_gemm_tn (dense layers).
 #pragma once
+#include <map>
 #include "conv_simt.cuh"
 #include "tc_common.cuh"
 
@@ -23,6 +24,11 @@ struct TrainWork {
   float *c1 = nullptr, *p1p = nullptr, *c2 = nullptr, *p2p = nullptr, *c3 = nullptr, *p3 = nullptr;
   float *h4 = nullptr, *d4 = nullptr, *h5 = nullptr, *logits = nullptr, *out16 = nullptr;
   float* d5 = nullptr;  // dropout5 (dropoutRateFC5 != 0 only; its own allocation)
+  uint64_t* seedbuf = nullptr;  // the step's dropout seed (see SeedRef)
+  // captured micro-chunk / prologue launch sequences (cvb200.cu run_captured): key -> executable graph
+  struct GraphEntry { int uses = 0; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+  std::map<uint64_t, GraphEntry> graphs;
+  bool graphs_on = true;
   float *dlog = nullptr, *g5 = nullptr, *g4 = nullptr, *g4b = nullptr, *gp3 = nullptr, *g3p = nullptr, *gp2 = nullptr;
   float *g2p = nullptr, *gp1 = nullptr, *g1 = nullptr;
   float *w3t = nullptr, *w2t = nullptr, *w4t = nullptr, *w5t = nullptr, *tmpb = nullptr, *tmph = nullptr;
@@ -53,6 +59,9 @@ static inline void train_work_free(TrainWork* w) {
   cudaFree(w->all16);
   cudaFree(w->amax);
   cudaFree(w->d5);
+  cudaFree(w->seedbuf);
+  for (auto& kv : w->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (int i = 0; i < 2; ++i) {
     if (w->ev_up[i]) cudaEventDestroy(w->ev_up[i]);
     if (w->ev_done[i]) cudaEventDestroy(w->ev_done[i]);
@@ -68,6 +77,13 @@ __host__ __device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t i
   z = z ^ (z >> 31);
   return (float)(z >> 40) * (1.0f / 16777216.0f);
 }
+// The dropout seed of the step lives in device memory (TrainWork::seedbuf) and the kernels read it through this reference,
+// so that the launch parameters of a micro-chunk do not change from step to step and its captured CUDA graph can be replayed.
+struct SeedRef {
+  const uint64_t* p;
+  uint64_t mix;  // 0 for FC4's stream, kSeed5 for FC5's
+  __device__ __forceinline__ uint64_t get() const { return *p ^ mix; }
+};
 // SELU-dropout constants for keep probability `keep` (selu.py:59-62; fixedPointMean 0, fixedPointVar 1)
 struct DropConst { float keep, a, b, alpha; };
 static inline DropConst drop_const(float rate) {
@@ -238,7 +254,8 @@ k_conv1_wgrad(const float* __restrict__ x, const float* __restrict__ g, int64_t 
 
 // ---- SELU dropout forward on FC4's output (selu.py:54-62): d4 = a*(h4*mask + alpha*(1-mask)) + b
 __global__ void k_dropout_fwd(const float* __restrict__ h4, float* __restrict__ d4, int64_t total, int64_t index0,
-                              uint64_t seed, DropConst dc) {
+                              SeedRef seedr, DropConst dc) {
+  const uint64_t seed = seedr.get();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const float u = hash_uniform(seed, (uint64_t)(index0 + i));
     const float mask = floorf(dc.keep + u);  // 1 with probability keep
@@ -290,8 +307,9 @@ __global__ void k_loss_grad(const float* __restrict__ logits16, const float* __r
 struct HeadW { const float *wb, *wz, *wt, *wl; };
 // use_drop5: the heads read dropout5 = a * (h5 * mask + alpha * (1 - mask)) + b (clairvoyante_v3.py:121): d dropout5 / d h5 = a * mask
 __global__ void k_heads_bwd(const float* __restrict__ dlog, const float* __restrict__ h5, int64_t n, int N4, int N5, HeadW w,
-                            float* __restrict__ g4, float* __restrict__ g5, int ld5, int use_drop5, uint64_t seed5,
+                            float* __restrict__ g4, float* __restrict__ g5, int ld5, int use_drop5, SeedRef seedr5,
                             int64_t index0_5, DropConst dc5) {
+  const uint64_t seed5 = use_drop5 ? seedr5.get() : 0;
   const int64_t total = n * (N4 + N5);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t s = i / (N4 + N5);
@@ -315,7 +333,8 @@ __global__ void k_heads_bwd(const float* __restrict__ dlog, const float* __restr
 
 // ---- dpre4 = (g4 + g4b) * d(dropout)/d(h4) * selu'(h4)   (d4 = a*h4*mask + ...: derivative a*mask)
 __global__ void k_fc4_bwd_elem(float* __restrict__ g4, const float* __restrict__ g4b, const float* __restrict__ h4,
-                               int64_t total, int64_t index0, uint64_t seed, DropConst dc, int use_dropout) {
+                               int64_t total, int64_t index0, SeedRef seedr, DropConst dc, int use_dropout) {
+  const uint64_t seed = use_dropout ? seedr.get() : 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     float f = 1.f;
     if (use_dropout) f = dc.a * floorf(dc.keep + hash_uniform(seed, (uint64_t)(index0 + i)));

@@ -23,7 +23,9 @@ def vcf_line(x, pos, base, z, t, l, show_ref=False, qual_cut=None):
     zyg = int(np.argmax(z)); var_len = int(np.argmax(l))           # :62-64
     chrom, coord, ref_seq = pos.split(":")                         # :66
     st, sz, sl = np.sort(t)[::-1], np.sort(z)[::-1], np.sort(l)[::-1]
-    qual = int(-4.343 * log((st[1] * sz[1] * sl[1] + 1e-300) / (st[0] * sz[0] * sl[0] + 1e-300)))   # :72
+    # :72 -- under the reference's NumPy 1.x the products stay in the inputs' dtype (float32 from TensorFlow) and adding the
+    # Python float promotes to float64; NumPy 2 (NEP 50) would keep float32 + 1e-300 = float32, hence the explicit float64
+    qual = int(-4.343 * log((np.float64(st[1] * sz[1] * sl[1]) + 1e-300) / (np.float64(st[0] * sz[0] * sl[0]) + 1e-300)))
     filt = "."
     if qual_cut is not None:
         filt = "PASS" if qual >= qual_cut else "LowQual"            # :75-79
