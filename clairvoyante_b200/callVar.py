@@ -100,15 +100,28 @@ def Test(args, m, utils):
     m.predictNoRT(cur[2])
     preds = (m.predictBaseRTVal, m.predictZygosityRTVal, m.predictVarTypeRTVal, m.predictIndelLengthRTVal)
     nxt = next(gen) if cur[0] == 0 else None
+    failed = []
+
+    def guarded(fn, *a):
+        # an exception (or sys.exit) on a worker thread would otherwise end only that thread: the VCF would silently miss a
+        # batch and the process would still exit 0
+        try:
+            fn(*a)
+        except BaseException as e:          # noqa: B902 -- SystemExit included
+            failed.append(e)
+
     while True:
-        workers = [Thread(target=Output, args=(args, call_fh, cur[1], cur[2], cur[3]) + preds)]
+        workers = [Thread(target=guarded, args=(Output, args, call_fh, cur[1], cur[2], cur[3]) + preds)]
         if nxt is not None:
-            workers.append(Thread(target=m.predictNoRT, args=(nxt[2],)))
+            workers.append(Thread(target=guarded, args=(m.predictNoRT, nxt[2])))
         for w in workers:
             w.start()
         after = next(gen) if (nxt is not None and nxt[0] == 0) else None    # main thread parses meanwhile
         for w in workers:
             w.join()
+        if failed:
+            call_fh.close()
+            raise failed[0]
         if nxt is None:
             break
         cur, nxt = nxt, after

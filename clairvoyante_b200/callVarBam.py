@@ -117,7 +117,7 @@ def Run(args, model=None):
         model = cv.Clairvoyante()
         model.init()
         model.restoreParameters(os.path.abspath(args.chkpnt_fn))
-    cv_args = types.SimpleNamespace(tensor_fn="(alignments)", call_fn=args.call_fn, qual=args.qual, sampleName=args.sampleName,
+    cv_args = types.SimpleNamespace(tensor_fn="(alignments)", call_fn=args.call_fn, qual=args.qual or None, sampleName=args.sampleName,
                                     showRef=False, ref_fn=args.ref_fn if os.path.isfile(args.ref_fn + ".fai") else None)
     callVar.Test(cv_args, model, _AlignmentFeed(args, ref_seq, ref_start, positions, cache))
     return len(positions)

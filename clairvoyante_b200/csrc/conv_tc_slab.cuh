@@ -42,12 +42,12 @@ template <class F, int SA_, int SB_, int NCB_ = 4, bool RES_ = false, bool BC_ =
 struct ConvSlabCfg {
   static constexpr int SA = SA_, SB = RES_ ? 1 : SB_, NCB = NCB_;
   static constexpr bool RES = RES_, BC = BC_;
-  static constexpr int EPI = EPI_;  // EXPERIMENT: 0 = round-1 pooling code for POOL != 4
+  static constexpr int EPI = EPI_;  // pooling code for POOL != 4: 0 = selects on compiler-predicated loads, 1 = lds128_if
   static constexpr int CB = F::NOUT / NCB;
   static constexpr int EPI_WARPS = 4 * NCB;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static_assert(F::NOUT % NCB == 0 && CB % 16 == 0 && THREADS <= 1024 && NCB <= 14, "epilogue column blocks");
-  static_assert(!BC_ || (CB % F::COUT == 0 && F::COUT <= 64), "constant-bank bias: column block = whole channel groups");
+  static_assert(!BC_ || (CB % F::BIAS_MOD == 0 && F::BIAS_MOD <= 64), "constant-bank bias: column block = whole channel groups");
   static constexpr int SLAB_ROWS = ((128 + F::KH - 1 + 7) / 8) * 8;
   static constexpr int TILE_STEP = 129 - F::POOL;
   static constexpr int A_PLANE = SLAB_ROWS * F::ROW_BYTES;
@@ -65,14 +65,17 @@ struct ConvSlabCfg {
 };
 
 using Conv2Slab = ConvSlabCfg<Conv2Tc, 8, 16, 4, false, true>;  // two tiles of operands in flight
-using Conv3Slab = ConvSlabCfg<Conv3Tc, 3, 6>;  // (NCB = 6, 24 warps x 32 columns, measured no faster: 0.203 vs 0.199 ms)
+using Conv3Slab = ConvSlabCfg<Conv3Tc, 3, 6, 4, false, false, 0>;  // (NCB = 6, 24 warps x 32 columns, measured no faster: 0.203 vs 0.199 ms)
 using SlimConv3Slab = ConvSlabCfg<SlimConv3Tc, 4, 8>;
 // resident-weight variants (CVB_CONV_RESIDENT=1): the shared memory the weight ring held goes to deeper activation rings
 using Conv2SlabRes = ConvSlabCfg<Conv2Tc, 12, 0, 4, true>;
-using Conv3SlabRes = ConvSlabCfg<Conv3Tc, 6, 0, 4, true, true>;
-using Conv3SlabResV0 = ConvSlabCfg<Conv3Tc, 6, 0, 4, true, false, 0>;  // EXPERIMENT variants (CVB_C3_VARIANT)
-using Conv3SlabResV1 = ConvSlabCfg<Conv3Tc, 6, 0, 4, true, true, 0>;
+// conv3 keeps the first pooling code and the shared-memory bias (EPI 0, BC off): measured per 18,944-site launch 0.167 ms
+// against 0.175 with the constant-bank bias and 0.189 with the predicated-load pooling that helps conv2 (0.139 -> 0.127)
+using Conv3SlabRes = ConvSlabCfg<Conv3Tc, 6, 0, 4, true, false, 0>;
 using SlimConv3SlabRes = ConvSlabCfg<SlimConv3Tc, 8, 0, 4, true, true>;
+// v3_slim tensor pipeline: dense conv2 (NOUT = 64: 4 x 16 columns per epilogue warp), conv3 with fp16 planes out
+using SlimConv2SlabRes = ConvSlabCfg<SlimConv2Tc, 8, 0, 4, true, true>;
+using SlimConv3HSlabRes = ConvSlabCfg<SlimConv3TcH, 8, 0, 4, true, true>;
 
 // 128-bit shared-memory load executed only by the lanes with pred != 0; the others get {d, d, d, d} and cost no
 // shared-memory wavefront (these kernels are bound by the shared-memory pipe -- tensor-core operand fetch, shuffles -- so a
@@ -115,6 +118,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
             __half* __restrict__ out_lo, int ablate, const __grid_constant__ BiasParam bias_c) {
   // ablate (timing experiments only, results are wrong): 1 = epilogue skips pooling/SELU/stores, 2 = no MMAs issued,
   // 4 = weight boxes are not loaded, 8 = activation slabs are not loaded, 16 = no global stores, 32 = no pooling
+  // bit 64 is NOT an ablation: plain-fp16 mode (one MMA term, the lo output plane is not written)
   extern __shared__ uint8_t smem_raw[];
   // aligned by OFFSET from the extern array, so that the compiler still knows these are shared-memory addresses (a pointer
   // rebuilt from an integer is generic: the exchange-buffer traffic below was compiled to LD.E / ST.E)
@@ -133,8 +137,8 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
   float* xch = reinterpret_cast<float*>(smem + S::RING_BYTES + 512);
   static_assert((2 * S::SA + 2 * S::SB + 5) * 8 + 8 <= 512, "barrier block");
 
-  __shared__ float bias_s[F::COUT];
-  if (!S::BC && threadIdx.x < F::COUT) bias_s[threadIdx.x] = F::ACT ? bias[threadIdx.x] : 0.f;
+  __shared__ float bias_s[F::BIAS_MOD];
+  if (!S::BC && threadIdx.x < F::BIAS_MOD) bias_s[threadIdx.x] = F::ACT ? bias[threadIdx.x] : 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t total_rows = n * F::RPS;
   const int64_t ntiles = (total_rows + S::TILE_STEP - 1) / S::TILE_STEP;
@@ -162,13 +166,13 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
       if (S::RES) {  // all taps once: per kh the {BK, 4 * COUT, 2} box of the input column that reaches every output column
         mbar_arrive_expect_tx(w_full, F::KH * S::B_SLOT);
         for (int kh = 0; kh < F::KH; ++kh)
-          tma_load_3d(b_ring + kh * S::B_SLOT, &map_b4, w_full, (3 - F::PADL) * F::CIN, kh * F::NOUT, 0);
+          tma_load_3d(b_ring + kh * S::B_SLOT, &map_b4, w_full, F::RES_K0, kh * F::NOUT, 0);
       }
       pdl_wait();  // the activations are the previous kernel's output (the resident taps above are not)
       pdl_launch_dependents();
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int r0 = (int)(tile * S::TILE_STEP);
-        for (int i = 0; i < 4; ++i, ++ia) {
+        for (int i = 0; i < F::NWP; ++i, ++ia) {
           const int wp = wp_of(i);
           const int wl = F::wlo(wp), nb = F::whi(wp) - wl + 1;
           const int sa = ia % S::SA;
@@ -201,7 +205,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
         const int buf = tcount & 1;
         mbar_wait(&acc_empty[buf], ((tcount >> 1) & 1) ^ 1);
         tc_fence_after();
-        for (int i = 0; i < 4; ++i, ++ia) {
+        for (int i = 0; i < F::NWP; ++i, ++ia) {
           const int wp = wp_of(i);
           const int wl = F::wlo(wp), nb = F::whi(wp) - wl + 1;
           const uint32_t idesc = F::BF16 ? umma_idesc_bf16(128, nb * F::COUT) : umma_idesc_f16(128, nb * F::COUT);
@@ -214,7 +218,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
             const int sb = ib % S::SB;
             uint32_t b_hi, b_lo;
             if (S::RES) {  // tap blocks 3 - w' + wl - PADL .. of the resident copy: planes NOUT rows apart
-              b_hi = smem_u32(b_ring + kh * S::B_SLOT) + (3 - wp + wl - F::PADL) * (F::COUT * F::ROW_BYTES);
+              b_hi = smem_u32(b_ring + kh * S::B_SLOT) + F::res_block(wp) * (F::COUT * F::ROW_BYTES);
               b_lo = b_hi + F::NOUT * F::ROW_BYTES;
             } else {
               mbar_wait(&fullB[sb], (ib / S::SB) & 1);
@@ -231,9 +235,13 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
               const uint64_t dal = umma_desc(a_lo + ko, 16, F::SBO, F::LAYOUT);
               const uint64_t dbh = umma_desc(b_hi + ko, 16, F::SBO, F::LAYOUT);
               const uint64_t dbl = umma_desc(b_lo + ko, 16, F::SBO, F::LAYOUT);
-              umma_f16(tcol, dal, dbh, idesc, (uint32_t)((i | kh | ks) != 0));
-              umma_f16(tcol, dah, dbl, idesc, 1u);
-              umma_f16(tcol, dah, dbh, idesc, 1u);
+              if (ablate & 64) {  // plain fp16 (v3_slim "fp16" mode): the hi x hi term alone
+                umma_f16(tcol, dah, dbh, idesc, (uint32_t)((i | kh | ks) != 0));
+              } else {
+                umma_f16(tcol, dal, dbh, idesc, (uint32_t)((i | kh | ks) != 0));
+                umma_f16(tcol, dah, dbl, idesc, 1u);
+                umma_f16(tcol, dah, dbh, idesc, 1u);
+              }
             }
             if (!S::RES) umma_commit(&emptyB[sb]);
           }
@@ -365,10 +373,10 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
         float pv[16];
         // channel of accumulator column c is c mod COUT (16 | CB, COUT); CB is a multiple of COUT or equal to it in every
         // configuration, so the channel of (wblk * CB + cc + j) does not depend on wblk: a constant-bank offset when BC
-        const float* b16 = bias_s + (wblk * CB + cc) % F::COUT;
+        const float* b16 = bias_s + (wblk * CB + cc) % F::BIAS_MOD;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float bj = S::BC ? bias_c.v[(cc + j) % F::COUT] : b16[j];
+          const float bj = S::BC ? bias_c.v[(cc + j) % F::BIAS_MOD] : b16[j];
           pv[j] = F::ACT ? selu_f(fmaf(raw[cc + j], isc, bj)) : raw[cc + j] * isc;
         }
         if (F::OUT_F32) {
@@ -384,7 +392,7 @@ k_conv_slab(const __grid_constant__ CUtensorMap map_a,   // 3-D (k, row, plane),
           for (int j = 0; j < 8; ++j) split_f16x2(pv[2 * j], pv[2 * j + 1], hi[j], lo[j]);
           if (store) {  // 16 halves = one 32-byte sector per plane: one 256-bit store each
             st_global_256(out_hi + o + cc, hi);
-            st_global_256(out_lo + o + cc, lo);
+            if (!(ablate & 64)) st_global_256(out_lo + o + cc, lo);
           }
         }
       }

@@ -61,7 +61,7 @@ struct VarInfo {
 // sites per device pass: bounds the intermediates and makes k_fc4's grid exactly one wave
 // (M-tile 96 sites x #SMs for v3; 224 x #SMs for slim)
 
-static const int64_t kFc4SplitSites = 18 * 128;  // largest batch whose FC4 is split over K (36 CTAs x 4 slices = one wave)
+static const int64_t kFc4SplitSites = 48 * 128;  // largest batch whose FC4 is split over K (96 CTAs x 3 slices = two waves)
 
 struct cvb_model {
   int variant = 0, device = 0, compute_mode = CVB_COMPUTE_FP32, num_sms = 148;
@@ -78,7 +78,7 @@ struct cvb_model {
   static constexpr int NSLOT = 4;
   float *d_x[NSLOT] = {}, *d_out[NSLOT] = {}, *d_lg[NSLOT] = {};
   __half* d_x16[NSLOT] = {};  // narrow input slots (fp16 values, int16 / uint8 raw counts: cvb_predict_host_f16 / _counts_*)
-  float* d_fc4ws = nullptr;   // split-K FC4 of small batches: per-chunk partial sums [36][kFc4SplitSites][352]
+  float* d_fc4ws = nullptr;   // split-K FC4 of small batches: per-chunk partial sums [9][kFc4SplitSites][352]
   float* d_xw = nullptr;      // fp32 scratch of one chunk for the front kernels that cannot read a narrow feed themselves
   float *h_x[NSLOT] = {}, *h_out[NSLOT] = {}, *h_lg[NSLOT] = {};
   cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
@@ -92,8 +92,6 @@ struct cvb_model {
   bool tc_ready = false, tc_weights_dirty = true;
   CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
   CUtensorMap map_bh_hi, map_bh_lo;  // FC4 weights with NH/2-row boxes (cluster multicast)
-  CUtensorMap map_b80_hi, map_b80_lo;  // ... with 80-row boxes (k_fc4_both's second N-half: 160 rows per stage)
-  int tc_fc4_both = 1;                 // large batches: k_fc4_both (128 sites x all 336 outputs per CTA)
   CUtensorMap map_ah_hi, map_ah_lo;  // FC4 activations with BM/2-row boxes (4-CTA clusters)
   int tc_fc4_cluster = 1;
   // conv3 on tensor cores: B = rearranged conv3 weights [3*192][128], A = p2 hi/lo [sites*28][128]
@@ -112,6 +110,11 @@ struct cvb_model {
   int tc_merged = 1;
   int tc_cluster = 1;  // 2-CTA clusters with weight multicast in the conv tensor kernels (needs tc_merged)
   int tc_slab = 1;     // slab-mode conv kernels (conv_tc_slab.cuh): A loaded once per (tile, w'), re-used across kh
+  // v3_slim, every layer but conv1 on tcgen05 (CVB_SLIM_TC=0 keeps the first arrangement: SIMT front, fp32 conv3 output, SIMT FC4)
+  int slim_tc = 1;
+  __half *d_p1s = nullptr, *d_w2s = nullptr, *d_w4h = nullptr;  // p1 [rows][32] hi|lo; dense conv2 taps hi|lo; fc4/kernel^T [36][4224] hi|lo
+  int64_t p1s_rows = 0;
+  CUtensorMap map_s2slab, map_s2b;
   int slim_fc4_tc = 0; // CVB_SLIM_FC4_TC=1: v3_slim inference FC4 as a split-bf16 tcgen05 GEMM (opt-in until run on a B200)
   uint16_t *d_p3s = nullptr, *d_w4ts = nullptr;  // its operands: planes of the conv3 output / of fc4/kernel^T
   tc::BiasParam hb2 = {}, hb3 = {};  // host copies of conv2/bias, conv3/bias: passed by value to the inference conv kernels
@@ -285,7 +288,7 @@ extern "C" int cvb_destroy(cvb_model* m) {
   cudaFree(m->d_params); cudaFree(m->d_m); cudaFree(m->d_v); cudaFree(m->d_grad);
   cudaFree(m->d_p2); cudaFree(m->d_p3); cudaFree(m->d_h4); cudaFree(m->d_h5);
   cudaFree(m->d_w3b_hi); cudaFree(m->d_p1); cudaFree(m->d_w2b_hi); cudaFree(m->d_h4s); cudaFree(m->d_wtail);
-  cudaFree(m->d_p3s); cudaFree(m->d_w4ts);
+  cudaFree(m->d_p3s); cudaFree(m->d_w4ts); cudaFree(m->d_p1s); cudaFree(m->d_w2s); cudaFree(m->d_w4h);
   cudaFree(m->d_w4t_hi); cudaFree(m->d_w4t_lo); cudaFree(m->d_absmax); cudaFree(m->d_inv_scale);
   for (int i = 0; i < cvb_model::NSLOT; ++i) {
     if (i == 0) { cudaFree(m->d_xw); cudaFree(m->d_fc4ws); }
@@ -486,13 +489,6 @@ static int tc_setup(cvb_model* m) {
   if (make_map_f16(&m->map_b_lo, m->d_w4t_lo, F::N, K, F::BK, F::NH, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   if (make_map_f16(&m->map_bh_hi, m->d_w4t_hi, F::N, K, F::BK, F::NH / 2, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   if (make_map_f16(&m->map_bh_lo, m->d_w4t_lo, F::N, K, F::BK, F::NH / 2, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-  if (make_map_f16(&m->map_b80_hi, m->d_w4t_hi, F::N, K, F::BK, tc::Fc4Both::N1 / 2, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-  if (make_map_f16(&m->map_b80_lo, m->d_w4t_lo, F::N, K, F::BK, tc::Fc4Both::N1 / 2, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-  CK(cudaFuncSetAttribute(tc::k_fc4_both, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Fc4Both::SMEM_BYTES));
-  {
-    const char* e = getenv("CVB_FC4_BOTH");
-    m->tc_fc4_both = e && e[0] == '1';  // EXPERIMENT: slower than the two-wave kernel so far (register spills in the epilogue)
-  }
   CK(cudaFuncSetAttribute(tc::k_fc4_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tc::k_fc4_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tc::k_fc4_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
@@ -618,6 +614,29 @@ static int tc_setup_slim(cvb_model* m) {
   }
   CK(cudaFuncSetAttribute(tc::k_conv_tc<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tc::k_conv_tc<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  {
+    // conv2 as a dense row-shifted GEMM on p1 [site][35][32] (k_slim_c1_reg writes it), conv3 with fp16 hi / lo output planes,
+    // FC4 as a split-fp16 GEMM over those planes (gemm_tc.cuh)
+    const char* e = getenv("CVB_SLIM_TC");
+    m->slim_tc = !(e && e[0] == '0');
+    using C2 = tc::SlimConv2Tc;
+    using S2 = tc::SlimConv2SlabRes;
+    m->p1s_rows = m->alloc_sites * C2::RPS + 256;
+    const size_t p1_halves = (size_t)m->p1s_rows * C2::KROW;
+    CK(cudaMalloc(&m->d_p1s, p1_halves * 2 * 2));
+    CK(cudaMemset(m->d_p1s, 0, p1_halves * 2 * 2));  // rows 0 and 34 of every site stay zero (conv2's SAME padding)
+    const size_t w2_halves = (size_t)C2::B_ROWS_TOTAL * C2::KROW;
+    CK(cudaMalloc(&m->d_w2s, w2_halves * 2 * 2));
+    CK(cudaMalloc(&m->d_w4h, (size_t)36 * 4224 * 2 * 2));
+    if (make_slab_map<C2, S2>(m->d_p1s, m->p1s_rows, CU_TENSOR_MAP_SWIZZLE_64B, &m->map_s2slab)) return 1;
+    const uint64_t bd[3] = {(uint64_t)C2::KROW, (uint64_t)C2::B_ROWS_TOTAL, 2};
+    const uint64_t bs[2] = {(uint64_t)C2::KROW * 2, (uint64_t)C2::B_ROWS_TOTAL * C2::KROW * 2};
+    const uint32_t bb[3] = {(uint32_t)C2::BK, (uint32_t)C2::NOUT, 2};
+    if (make_map_nd(&m->map_s2b, m->d_w2s, 3, bd, bs, bb, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    CK(cudaFuncSetAttribute(tc::k_conv_slab<C2, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tc::k_conv_slab<tc::SlimConv3TcH, tc::SlimConv3HSlabRes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            tc::SlimConv3HSlabRes::SMEM_BYTES));
+  }
   m->tc_ready = true;
   m->tc_weights_dirty = true;
   return 0;
@@ -645,6 +664,19 @@ static int tc_refresh_weights(cvb_model* m, cudaStream_t st) {
                                                                                         m->d_w3b_hi, m->d_w3b_lo, m->d_inv_scale + 1);
     CK(cudaGetLastError());
     m->launches += 2;
+    if (m->slim_tc) {
+      using C2 = tc::SlimConv2Tc;
+      CK(cudaMemsetAsync(m->d_absmax + 2, 0, 4, st));
+      tc::k_absmax<<<16, 256, 0, st>>>(m->var("conv2/kernel"), 3 * 4 * 8 * 16, m->d_absmax + 2);
+      tc::k_prep_conv_weights_dense<C2, 8, 16><<<(C2::B_ROWS_TOTAL * C2::KROW + 255) / 256, 256, 0, st>>>(
+          m->var("conv2/kernel"), m->d_absmax + 2, m->d_w2s, m->d_w2s + (size_t)C2::B_ROWS_TOTAL * C2::KROW, m->d_inv_scale + 2);
+      CK(cudaMemsetAsync(m->d_absmax, 0, 4, st));
+      tc::k_absmax<<<64, 256, 0, st>>>(m->var("fc4/kernel"), (int64_t)4224 * 36, m->d_absmax);
+      tc::k_prep_fc_weights<<<dim3(4224 / 32, 2), dim3(32, 8), 0, st>>>(m->var("fc4/kernel"), 4224, 36, m->d_absmax, m->d_w4h,
+                                                                        m->d_w4h + (size_t)36 * 4224, m->d_inv_scale);
+      CK(cudaGetLastError());
+      m->launches += 4;
+    }
     m->tc_weights_dirty = false;
     return 0;
   }
@@ -689,11 +721,14 @@ extern "C" int cvb_set_step(cvb_model* m, int64_t t) { if (!m) return fail("NULL
 extern "C" int cvb_get_step(const cvb_model* m, int64_t* t) { if (!m || !t) return fail("NULL argument"); *t = m->step; return 0; }
 extern "C" int cvb_set_compute_mode(cvb_model* m, int mode) {
   if (!m) return fail("NULL model");
-  if (mode != CVB_COMPUTE_FP32 && mode != CVB_COMPUTE_FP16X3)
+  if (mode != CVB_COMPUTE_FP32 && mode != CVB_COMPUTE_FP16X3 && mode != CVB_COMPUTE_FP16)
     return fail("cvb_set_compute_mode: unknown mode %d", mode);
+  if (mode == CVB_COMPUTE_FP16 && m->variant != CVB_V3_SLIM)
+    return fail("cvb_set_compute_mode: plain fp16 (BASELINE configs[2]) is implemented for v3_slim");
   CK(cudaSetDevice(m->device));
-  if (mode == CVB_COMPUTE_FP16X3 && (m->variant == CVB_V3 ? tc_setup(m) : tc_setup_slim(m))) return 1;
-  if (mode != m->compute_mode) {
+  if (mode != CVB_COMPUTE_FP32 && (m->variant == CVB_V3 ? tc_setup(m) : tc_setup_slim(m))) return 1;
+  if (mode == CVB_COMPUTE_FP16 && !m->slim_tc) return fail("cvb_set_compute_mode: fp16 needs the tensor pipeline (CVB_SLIM_TC=0 is set)");
+  if ((mode == CVB_COMPUTE_FP32) != (m->compute_mode == CVB_COMPUTE_FP32)) {
     // p2's zero padding rows sit at different byte offsets in the fp32 and the fp16 hi/lo layouts
     CK(cudaDeviceSynchronize());
     CK(cudaMemset(m->d_p2, 0, m->p2_bytes));
@@ -784,21 +819,6 @@ static int launch_conv_tc(cvb_model* m, int resident, int64_t n, cudaStream_t st
     const int64_t st_tiles = (n * T::RPS + S::TILE_STEP - 1) / S::TILE_STEP;
     const int g = (int)std::min<int64_t>(st_tiles, m->num_sms);
     static const int ablate = getenv("CVB_ABLATE") ? atoi(getenv("CVB_ABLATE")) : 0;  // timing experiments only
-    static const int c3v = getenv("CVB_C3_VARIANT") ? atoi(getenv("CVB_C3_VARIANT")) : -1;  // EXPERIMENT
-    if constexpr (std::is_same<SR, tc::Conv3SlabRes>::value) {
-      if (resident && c3v == 0) {
-        CK(set_smem(tc::k_conv_slab<T, tc::Conv3SlabResV0>, tc::Conv3SlabResV0::SMEM_BYTES));
-        CK(launch_k(tc::k_conv_slab<T, tc::Conv3SlabResV0>, dim3(g), dim3(SR::THREADS), tc::Conv3SlabResV0::SMEM_BYTES, st, 1, 1,
-                    use_pdl(m), *slab, b2, b3, b4, n, bias, inv_scale, out_hi, out_lo, ablate, bc));
-        return 0;
-      }
-      if (resident && c3v == 1) {
-        CK(set_smem(tc::k_conv_slab<T, tc::Conv3SlabResV1>, tc::Conv3SlabResV1::SMEM_BYTES));
-        CK(launch_k(tc::k_conv_slab<T, tc::Conv3SlabResV1>, dim3(g), dim3(SR::THREADS), tc::Conv3SlabResV1::SMEM_BYTES, st, 1, 1,
-                    use_pdl(m), *slab, b2, b3, b4, n, bias, inv_scale, out_hi, out_lo, ablate, bc));
-        return 0;
-      }
-    }
     if (resident)
       CK(launch_k(tc::k_conv_slab<T, SR>, dim3(g), dim3(SR::THREADS), SR::SMEM_BYTES, st, 1, 1, use_pdl(m), *slab, b2, b3, b4, n, bias,
                   inv_scale, out_hi, out_lo, ablate, bc));
@@ -843,6 +863,19 @@ static int prof_mark(cvb_model* m, cudaStream_t st) {
   return 0;
 }
 
+struct GemmExtra {  // batched / split-K launches, see tc::GemmArgs
+  int batches = 1, a_batch_rows = 0, a_kshift0 = 0, a_kshift_per_batch = 0;
+  int64_t c_batch_stride = 0;
+  int kslices = 1;
+  int f16 = 0, terms = 0;  // fp16 operands; terms 0 = what the training mode says (3, or 1 for CVB_TRAIN_BF16)
+  const float* inv_scale = nullptr;
+  bool pdl = false;
+};
+template <int BN, bool CHUNKED, int EPI, bool MN = false>
+static int launch_gemm_tc(cvb_model* m, const uint16_t* a, int64_t a_plane, int64_t lda, const uint16_t* b, int64_t b_plane,
+                          int64_t ldb, int M, int N, int K, float* C, int64_t ldc, const float* bias, cudaStream_t st,
+                          const GemmExtra& ex = GemmExtra());
+
 // narrow feed -> fp32 scratch (only for the front kernels that do not widen on their own)
 static int widen_chunk(cvb_model* m, const void* xin, int kind, int64_t n, cudaStream_t st) {
   if (!m->d_xw) CK(cudaMalloc(&m->d_xw, (size_t)m->alloc_sites * 528 * 4));
@@ -861,10 +894,11 @@ static int widen_chunk(cvb_model* m, const void* xin, int kind, int64_t n, cudaS
 static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, OutDst out16, float* logits16, cudaStream_t st) {
   if (n <= 0) return 0;
   const int sms = m->num_sms;
-  const bool tensor = m->compute_mode == CVB_COMPUTE_FP16X3;
+  const bool tensor = m->compute_mode != CVB_COMPUTE_FP32;
   if (tensor && tc_refresh_weights(m, st)) return 1;
   static const bool c1_reg = !(getenv("CVB_C1_REG") && getenv("CVB_C1_REG")[0] == '0');
-  const bool fused_feed = m->variant == CVB_V3 && tensor && m->tc_conv2 && c1_reg;  // k_v3_c1_reg<KIND> widens on its own
+  // k_v3_c1_reg<KIND> / k_slim_c1_reg<KIND> widen a narrow feed on their own
+  const bool fused_feed = tensor && (m->variant == CVB_V3 ? (m->tc_conv2 && c1_reg) : (m->slim_tc != 0));
   if (kind != X_F32 && !fused_feed) {
     if (widen_chunk(m, xin, kind, n, st)) return 1;
     xin = m->d_xw;
@@ -953,27 +987,21 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
       const unsigned tiles4 = (unsigned)((n + F::BM - 1) / F::BM);
       __half* h4hi = m->tc_tail ? m->d_h4s : nullptr;
       __half* h4lo = m->tc_tail ? m->d_h4s + (size_t)m->alloc_sites * 336 : nullptr;
-      // small batches: split the 36 K-chunks over gridDim.z so that ~every SM streams a slice of W4 (k_fc4_tc, `ws`)
+      // small batches: split the 9 K-chunks over gridDim.z so that ~every SM streams a slice of W4 (k_fc4_tc, `ws`)
       static const bool split_ok = !(getenv("CVB_FC4_SPLITK") && getenv("CVB_FC4_SPLITK")[0] == '0');
       unsigned ksplit = 1;
       if (split_ok) {
         const unsigned ctas = 2 * ((tiles4 + 1) & ~1u);
-        for (unsigned k : {36u, 18u, 12u, 9u, 6u, 4u, 3u, 2u})
-          if ((int64_t)n <= kFc4SplitSites && ctas * k <= (unsigned)sms + 4) { ksplit = k; break; }
+        for (unsigned k : {9u, 3u})
+          if ((int64_t)n <= kFc4SplitSites && ctas * k <= 2 * (unsigned)sms) { ksplit = k; break; }
       }
       float* ws = nullptr;
       const int64_t ws_plane = (int64_t)kFc4SplitSites * 2 * F::NH;
       if (ksplit > 1) {
-        if (!m->d_fc4ws) CK(cudaMalloc(&m->d_fc4ws, (size_t)36 * ws_plane * 4));
+        if (!m->d_fc4ws) CK(cudaMalloc(&m->d_fc4ws, (size_t)(4608 / F::KCH) * ws_plane * 4));
         ws = m->d_fc4ws;
       }
-      if (ksplit == 1 && m->tc_fc4_both) {
-        using G = tc::Fc4Both;
-        // pairs of site tiles share the weight operand; a padding tile stores nothing
-        CK(launch_k(tc::k_fc4_both, dim3((tiles4 + 1) & ~1u), dim3(G::THREADS), G::SMEM_BYTES, st, 2, 1, use_pdl(m), m->map_a_hi,
-                    m->map_a_lo, m->map_bh_hi, m->map_bh_lo, m->map_b80_hi, m->map_b80_lo, n, 4608, m->var("fc4/bias"),
-                    (const float*)m->d_inv_scale, m->d_h4, h4hi, h4lo));
-      } else if (m->tc_fc4_cluster >= 2 && tiles4 >= 2) {
+      if (m->tc_fc4_cluster >= 2 && tiles4 >= 2) {
         const bool cl4 = m->tc_fc4_cluster >= 4;
         const dim3 g4(2, (tiles4 + 1) & ~1u, ksplit);  // pairs of site tiles; a padding tile loads zeros and stores nothing
         if (cl4)
@@ -1028,6 +1056,63 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
     }
+    m->launches += 5;
+  } else if (tensor && m->slim_tc) {
+    // ---- v3_slim on the tensor path: conv1 (SIMT, registers) -> conv2 (dense row-shifted GEMM) -> conv3 -> FC4 (GEMM) -> tail
+    const bool hi_only = m->compute_mode == CVB_COMPUTE_FP16;  // plain fp16: one MMA term, hi planes only
+    using C2 = tc::SlimConv2Tc;
+    using C3 = tc::SlimConv3TcH;
+    {
+      const unsigned g1 = (unsigned)((n * 8 + 63) / 64);
+      const float *w1 = m->var("conv1/kernel"), *b1 = m->var("conv1/bias");
+      __half *phi = m->d_p1s, *plo = m->d_p1s + (size_t)m->p1s_rows * C2::KROW;
+#define CVB_SLIM_C1(KIND)                                                                                  \
+  do {                                                                                                     \
+    if (hi_only) k_slim_c1_reg<KIND, false><<<g1, 64, 0, st>>>(xin, n, w1, b1, phi, plo);                  \
+    else k_slim_c1_reg<KIND, true><<<g1, 64, 0, st>>>(xin, n, w1, b1, phi, plo);                           \
+  } while (0)
+      if (kind == X_F32) CVB_SLIM_C1(X_F32);
+      else if (kind == X_F16) CVB_SLIM_C1(X_F16);
+      else if (kind == X_I16) CVB_SLIM_C1(X_I16);
+      else CVB_SLIM_C1(X_U8);
+#undef CVB_SLIM_C1
+      CK(cudaGetLastError());
+      if (prof_mark(m, st)) return 1;
+    }
+    const int hi_flag = hi_only ? 64 : 0;  // k_conv_slab: only the hi x hi term, no lo plane written
+    {
+      using S2 = tc::SlimConv2SlabRes;
+      const int64_t tiles = (n * C2::RPS + S2::TILE_STEP - 1) / S2::TILE_STEP;
+      __half* p2_hi = reinterpret_cast<__half*>(m->d_p2);
+      CK(launch_k(tc::k_conv_slab<C2, S2>, dim3((unsigned)std::min<int64_t>(tiles, sms)), dim3(S2::THREADS), S2::SMEM_BYTES, st, 1, 1,
+                  use_pdl(m), m->map_s2slab, m->map_s2b, m->map_s2b, m->map_s2b, n, m->var("conv2/bias"),
+                  (const float*)(m->d_inv_scale + 2), p2_hi, p2_hi + m->p2_rows * 64, hi_flag, m->hb2));
+      if (prof_mark(m, st)) return 1;
+    }
+    {
+      using S3 = tc::SlimConv3HSlabRes;
+      const int64_t tiles = (n * C3::RPS + S3::TILE_STEP - 1) / S3::TILE_STEP;
+      __half* p3_hi = reinterpret_cast<__half*>(m->d_p3);
+      CK(launch_k(tc::k_conv_slab<C3, S3>, dim3((unsigned)std::min<int64_t>(tiles, sms)), dim3(S3::THREADS), S3::SMEM_BYTES, st, 1, 1,
+                  use_pdl(m), m->map_c3slab, m->map_c3b2, m->map_c3b3, m->map_c3b4, n, m->var("conv3/bias"),
+                  (const float*)(m->d_inv_scale + 1), p3_hi, p3_hi + m->alloc_sites * 4224, hi_flag, m->hb3));
+      if (prof_mark(m, st)) return 1;
+    }
+    {
+      GemmExtra ex;
+      ex.f16 = 1;
+      ex.terms = hi_only ? 1 : 3;
+      ex.inv_scale = m->d_inv_scale;
+      ex.pdl = use_pdl(m);
+      if (launch_gemm_tc<48, true, tc::GEMM_EPI_BIAS_SELU>(m, reinterpret_cast<const uint16_t*>(m->d_p3), m->alloc_sites * 4224, 4224,
+                                                           reinterpret_cast<const uint16_t*>(m->d_w4h), 36 * 4224, 4224, (int)n, 36, 4224,
+                                                           m->d_h4, 36, m->var("fc4/bias"), st, ex))
+        return 1;
+      if (prof_mark(m, st)) return 1;
+    }
+    k_tail<36, 18, 16><<<(int)((n + 15) / 16), 256, 0, st>>>(m->d_h4, n, head_ptrs(m), out16, logits16);
+    CK(cudaGetLastError());
+    if (prof_mark(m, st)) return 1;
     m->launches += 5;
   } else {
     {
@@ -1432,17 +1517,12 @@ static inline int gsz(int64_t total, int block = 256) { return (int)std::min<int
 // ---- tensor-core FC4 contractions of the training path (gemm_tc.cuh) ------------------------------------------------
 // C[M][N] (op)= A[M][K] . B[N][K]^T ; a / b point at the hi plane, the lo plane follows `a_plane` / `b_plane` elements later;
 // lda / ldb = row pitch in elements (multiple of 8: TMA strides are 16-byte granular)
-struct GemmExtra {  // batched / split-K launches, see tc::GemmArgs
-  int batches = 1, a_batch_rows = 0, a_kshift0 = 0, a_kshift_per_batch = 0;
-  int64_t c_batch_stride = 0;
-  int kslices = 1;
-};
 // MN = false: a [M][K], b [N][K] (K-major; lda / ldb = row pitch).  MN = true: a [K][M], b [K][N] (transposed operands read in
 // place as MN-major tiles; lda / ldb = pitch of a K row).
-template <int BN, bool CHUNKED, int EPI, bool MN = false>
+template <int BN, bool CHUNKED, int EPI, bool MN>
 static int launch_gemm_tc(cvb_model* m, const uint16_t* a, int64_t a_plane, int64_t lda, const uint16_t* b, int64_t b_plane,
                           int64_t ldb, int M, int N, int K, float* C, int64_t ldc, const float* bias, cudaStream_t st,
-                          const GemmExtra& ex = GemmExtra()) {
+                          const GemmExtra& ex) {
   using G = tc::GemmTc<BN, MN>;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   const uint64_t sa[1] = {(uint64_t)lda * 2}, sb[1] = {(uint64_t)ldb * 2};
@@ -1465,7 +1545,9 @@ static int launch_gemm_tc(cvb_model* m, const uint16_t* a, int64_t a_plane, int6
   CK(set_smem(k, G::SMEM_BYTES));
   tc::GemmArgs g;
   g.M = M; g.N = N; g.K = K;
-  g.terms = m->train_mode == CVB_TRAIN_BF16 ? 1 : 3;
+  g.terms = ex.terms ? ex.terms : (m->train_mode == CVB_TRAIN_BF16 ? 1 : 3);
+  g.f16 = ex.f16;
+  g.inv_scale = ex.inv_scale;
   g.C = C; g.ldc = ldc; g.bias = bias;
   g.m_tiles = (M + G::BM - 1) / G::BM;
   g.a_batch_rows = ex.a_batch_rows; g.c_batch_stride = ex.c_batch_stride;
@@ -1474,7 +1556,7 @@ static int launch_gemm_tc(cvb_model* m, const uint16_t* a, int64_t a_plane, int6
   g.kb_per_slice = (nkb + ex.kslices - 1) / ex.kslices;
   const int kslices = (nkb + g.kb_per_slice - 1) / g.kb_per_slice;  // no empty slice
   const dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)(g.m_tiles * ex.batches), (unsigned)kslices);
-  k<<<grid, G::THREADS, G::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, g);
+  CK(launch_k(k, grid, dim3(G::THREADS), G::SMEM_BYTES, st, 1, 1, ex.pdl, ma_hi, ma_lo, mb_hi, mb_lo, g));
   CK(cudaGetLastError());
   return 0;
 }

@@ -22,7 +22,7 @@ namespace tc {
 struct Fc4Tc {
   // CTA = 128 sites x one N-half (176 columns; the second half has 160 real + 16 zero-filled).
   static constexpr int BM = 128, N = 336, NH = 176, BK = 32, STAGES = 5;
-  static constexpr int KCH = 128;                          // K per from-zero accumulation chunk (36 chunks; shared by k_fc4_both)
+  static constexpr int KCH = 512;                          // K per from-zero accumulation chunk (9 chunks)
   static constexpr int ROW_BYTES = BK * 2;                // 64 B = one SWIZZLE_64B atom row
   static constexpr int A_BYTES = BM * ROW_BYTES;          // 8192
   static constexpr int B_BYTES = NH * ROW_BYTES;          // 11264
@@ -91,7 +91,7 @@ k_fc4_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ C
          const float* __restrict__ bias, const float* __restrict__ inv_scale, float* __restrict__ out,
          __half* __restrict__ out_hi, __half* __restrict__ out_lo, float* __restrict__ ws, int64_t ws_plane) {
   // out_hi / out_lo (optional): h4 again as split fp16 [n][336], the A operand of the fused tail (tail_tc.cuh)
-  // ws != nullptr: split-K launch for small batches (gridDim.z slices of the 36 K-chunks): a call of 1,000 sites -- the
+  // ws != nullptr: split-K launch for small batches (gridDim.z slices of the 9 K-chunks): a call of 1,000 sites -- the
   // reference's predictBatchSize, callVar.py:184 -- has only 8 site tiles, i.e. 16 CTAs each streaming all of W4 (6.2 MB) on
   // its own while 132 SMs idle.  Every CTA then handles nchunks / gridDim.z chunks and its epilogue stores each chunk's raw
   // partial sums to ws[chunk][site][2 * NH]; k_fc4_reduce adds them IN CHUNK ORDER and applies the epilogue, which is the
@@ -275,230 +275,6 @@ k_fc4_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ C
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, F::TMEM_COLS);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------------------
-// k_fc4_both: the large-batch FC4.  One CTA = 128 sites x ALL 336 outputs, so the activation tile is read from L2 once instead
-// of once per N-half (k_fc4_tc is bound by operand ingest: ~1.2 GB of L2 -> shared-memory traffic per 18,944-site launch, of
-// which the second read of A is 350 MB), and a 148-tile launch is one wave of 148 CTAs instead of two waves of 296.
-//
-// Schedule per K-chunk c (KCH = 128 = 4 K-blocks of 32): step (c, h0) multiplies the chunk's four A blocks with the first 176
-// rows of W4^T, step (c, h1) multiplies THE SAME A blocks (still in shared memory) with the other 160 rows.  Every step
-// accumulates from zero (fc4 rounding note above) into its own TMEM buffer: h0 steps alternate between columns [0,176) and
-// [336,512), h1 steps use [176,336) -- 512 columns in all; an h1 buffer is drained during the following h0 step.
-// Warp roles (576 threads): warp 0 TMA producer, warp 1 MMA issuer, 16 epilogue warps = 4 TMEM lane quadrants x {h0 columns
-// [0,96), h0 [96,176), h1 [0,80), h1 [80,160)}: each drains its slice of every finished step into at most 96 fp32 sums per
-// thread (one CTA-wide set of 176-wide sums per thread would need more registers than 576 threads leave).
-// Rings: 6 A slots (a chunk's 4 blocks + 2 of the next), 5 B slots.
-// Launched as 2-CTA clusters along the site-tile axis that share the weight operand (each CTA loads half of a B stage's rows
-// and multicasts them, as in k_fc4_tc<2>).  Per-chunk partial sums, their order of addition and the epilogue arithmetic are
-// those of k_fc4_tc / k_fc4_reduce: the three routes are bit-identical.
-struct Fc4Both {
-  using F = Fc4Tc;
-  static constexpr int N0 = 176, N1 = 160;                 // 336 = 176 + 160, both multiples of 16 (UMMA N for M = 128)
-  static constexpr int SA = 6, SB = 5, KBC = F::KCH / F::BK;  // K-blocks per chunk
-  static constexpr int A_SLOT = 2 * F::A_BYTES;            // hi | lo, 16 KB
-  static constexpr int B_PLANE = N0 * F::ROW_BYTES;        // 11264
-  static constexpr int B_SLOT = 2 * B_PLANE;
-  static constexpr int RING_BYTES = SA * A_SLOT + SB * B_SLOT;
-  static constexpr int SMEM_BYTES = RING_BYTES + 1024 + 512;
-  static constexpr int THREADS = 64 + 16 * 32;
-  static constexpr int TMEM_COLS = 512;
-  static constexpr int P0 = 96;                            // h0 columns [0,96) | [96,176); h1 columns [0,80) | [80,160)
-  static constexpr int P1 = 80;
-  static_assert(SA >= KBC + 1, "a chunk's A blocks stay resident across both N-halves");
-  static_assert(SMEM_BYTES <= 227 * 1024, "does not fit in shared memory");
-  __host__ __device__ static constexpr uint32_t tcol(int c, int h) { return h ? 176u : ((c & 1) ? 336u : 0u); }
-};
-
-__global__ void __launch_bounds__(Fc4Both::THREADS, 1)
-k_fc4_both(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-           const __grid_constant__ CUtensorMap map_b0_hi, const __grid_constant__ CUtensorMap map_b0_lo,  // boxes of 88 rows
-           const __grid_constant__ CUtensorMap map_b1_hi, const __grid_constant__ CUtensorMap map_b1_lo,  // boxes of 80 rows
-           int64_t n, int K, const float* __restrict__ bias, const float* __restrict__ inv_scale, float* __restrict__ out,
-           __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
-  using F = Fc4Tc;
-  using G = Fc4Both;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* a_ring = smem;
-  uint8_t* b_ring = smem + G::SA * G::A_SLOT;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::RING_BYTES);
-  uint64_t* fullA = bars;
-  uint64_t* emptyA = fullA + G::SA;
-  uint64_t* fullB = emptyA + G::SA;
-  uint64_t* emptyB = fullB + G::SB;
-  uint64_t* acc_full = emptyB + G::SB;  // [3] by TMEM buffer: 0 = h0 even chunks, 1 = h1, 2 = h0 odd chunks
-  uint64_t* acc_empty = acc_full + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 3);
-  static_assert((2 * G::SA + 2 * G::SB + 6) * 8 + 8 <= 512, "barrier block");
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t site0 = (int64_t)blockIdx.x * F::BM;
-  const int nchunks = K / F::KCH;
-  const uint32_t ty = cluster_ctarank();  // which of the pair's two site tiles
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
-    tma_prefetch_desc(&map_b0_hi); tma_prefetch_desc(&map_b0_lo);
-    tma_prefetch_desc(&map_b1_hi); tma_prefetch_desc(&map_b1_lo);
-    for (int s = 0; s < G::SA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
-    for (int s = 0; s < G::SB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 2); }  // both CTAs of the pair release a B slot
-    for (int b = 0; b < 3; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }  // 4 quadrants x 2 column parts
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, G::TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  auto buf_of = [](int c, int h) { return h ? 1 : ((c & 1) ? 2 : 0); };
-  auto uses_before = [](int c, int h) { return (uint32_t)(h ? c : (c >> 1)); };  // earlier steps that targeted the same buffer
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (elect_one()) {
-      uint32_t ia = 0, ib = 0;
-      pdl_wait();
-      pdl_launch_dependents();
-      for (int c = 0; c < nchunks; ++c) {
-        for (int h = 0; h < 2; ++h) {
-          for (int j = 0; j < G::KBC; ++j, ++ib) {
-            const int k0 = (c * G::KBC + j) * F::BK;
-            if (h == 0) {
-              const int sa = ia % G::SA;
-              mbar_wait(&emptyA[sa], ((ia / G::SA) & 1) ^ 1);
-              mbar_arrive_expect_tx(&fullA[sa], G::A_SLOT);
-              tma_load_2d(a_ring + sa * G::A_SLOT, &map_a_hi, &fullA[sa], k0, (int)site0);
-              tma_load_2d(a_ring + sa * G::A_SLOT + F::A_BYTES, &map_a_lo, &fullA[sa], k0, (int)site0);
-              ++ia;
-            }
-            const int sb = ib % G::SB;
-            mbar_wait(&emptyB[sb], ((ib / G::SB) & 1) ^ 1);
-            uint8_t* bs = b_ring + sb * G::B_SLOT;
-            const int rows = h ? G::N1 : G::N0, hr = rows / 2;  // this CTA loads rows [ty * hr, +hr) of the stage for the pair
-            mbar_arrive_expect_tx(&fullB[sb], 2 * rows * F::ROW_BYTES);
-            tma_load_2d_mc(bs + ty * (hr * F::ROW_BYTES), h ? &map_b1_hi : &map_b0_hi, &fullB[sb], k0, h * G::N0 + (int)ty * hr,
-                           (uint16_t)3);
-            tma_load_2d_mc(bs + G::B_PLANE + ty * (hr * F::ROW_BYTES), h ? &map_b1_lo : &map_b0_lo, &fullB[sb], k0,
-                           h * G::N0 + (int)ty * hr, (uint16_t)3);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      uint32_t ib = 0;
-      for (int c = 0; c < nchunks; ++c) {
-        for (int h = 0; h < 2; ++h) {
-          const int buf = buf_of(c, h);
-          mbar_wait(&acc_empty[buf], (uses_before(c, h) & 1) ^ 1);  // the epilogue has drained this buffer
-          tc_fence_after();
-          const uint32_t tcol = tmem_base + G::tcol(c, h);
-          const uint32_t idesc = h ? umma_idesc_f16(F::BM, G::N1) : umma_idesc_f16(F::BM, G::N0);
-          for (int j = 0; j < G::KBC; ++j, ++ib) {
-            const uint32_t ia = (uint32_t)(c * G::KBC + j);
-            const int sa = ia % G::SA, sb = ib % G::SB;
-            if (h == 0) mbar_wait(&fullA[sa], (ia / G::SA) & 1);
-            mbar_wait(&fullB[sb], (ib / G::SB) & 1);
-            tc_fence_after();
-            const uint32_t a_hi = smem_u32(a_ring + sa * G::A_SLOT), a_lo = a_hi + F::A_BYTES;
-            const uint32_t b_hi = smem_u32(b_ring + sb * G::B_SLOT), b_lo = b_hi + G::B_PLANE;
-#pragma unroll
-            for (int ks = 0; ks < F::BK / 16; ++ks) {
-              const uint32_t ko = ks * 32;
-              const uint64_t dah = umma_desc(a_hi + ko, 16, F::SBO, F::LAYOUT);
-              const uint64_t dal = umma_desc(a_lo + ko, 16, F::SBO, F::LAYOUT);
-              const uint64_t dbh = umma_desc(b_hi + ko, 16, F::SBO, F::LAYOUT);
-              const uint64_t dbl = umma_desc(b_lo + ko, 16, F::SBO, F::LAYOUT);
-              umma_f16(tcol, dal, dbh, idesc, (uint32_t)((j | ks) != 0));  // small terms first (as k_fc4_tc)
-              umma_f16(tcol, dah, dbl, idesc, 1u);
-              umma_f16(tcol, dah, dbh, idesc, 1u);
-            }
-            umma_commit_mc(&emptyB[sb], (uint16_t)3);
-            if (h == 1) umma_commit(&emptyA[sa]);  // both halves have read this A block
-          }
-          umma_commit(&acc_full[buf]);
-        }
-      }
-    }
-  } else {
-    // ===================== epilogue (warps 2..17) =====================
-    const int q = warp & 3;
-    const int grp = (warp - 2) >> 2;          // 0: h0 cols [0,96)  1: h0 [96,176)  2: h1 [0,80)  3: h1 [80,160)
-    const int h = grp >> 1;
-    const int c0 = (grp & 1) ? (h ? G::P1 : G::P0) : 0;             // first column of this warp's part inside its N-half
-    const int ncol = (grp & 1) ? G::P1 : (h ? G::P1 : G::P0);       // 96 or 80
-    const int row = q * 32 + lane;
-    const int64_t site = site0 + row;
-    float sum[G::P0];
-#pragma unroll
-    for (int i = 0; i < G::P0; ++i) sum[i] = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-      const int buf = buf_of(c, h);
-      mbar_wait(&acc_full[buf], uses_before(c, h) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + G::tcol(c, h) + c0;
-      {
-        // two batches of loads, each under one wait (the TMEM round trip is paid twice per step, not six times), and the
-        // buffer is handed back to the MMA warp as soon as its last column is in registers
-        uint32_t r[3][16];
-#pragma unroll
-        for (int b = 0; b < 3; ++b) tmem_ld16(taddr + b * 16, r[b]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int b = 0; b < 3; ++b)
-#pragma unroll
-          for (int j = 0; j < 16; ++j) sum[b * 16 + j] += __uint_as_float(r[b][j]);
-#pragma unroll
-        for (int b = 0; b < 3; ++b)
-          if (48 + b * 16 < ncol) tmem_ld16(taddr + 48 + b * 16, r[b]);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
-#pragma unroll
-        for (int b = 0; b < 3; ++b)
-          if (48 + b * 16 < ncol) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) sum[48 + b * 16 + j] += __uint_as_float(r[b][j]);
-          }
-      }
-    }
-    const float isc = inv_scale[0];
-    const int col0 = h * G::N0 + c0;
-    if (site < n) {
-      float* dst = out + site * F::N + col0;
-#pragma unroll
-      for (int cc = 0; cc < G::P0; cc += 4) {
-        if (cc < ncol) {
-          const float4 bv = *reinterpret_cast<const float4*>(bias + col0 + cc);
-          float4 v;
-          v.x = selu_f(fmaf(sum[cc + 0], isc, bv.x));
-          v.y = selu_f(fmaf(sum[cc + 1], isc, bv.y));
-          v.z = selu_f(fmaf(sum[cc + 2], isc, bv.z));
-          v.w = selu_f(fmaf(sum[cc + 3], isc, bv.w));
-          *reinterpret_cast<float4*>(dst + cc) = v;
-          if (out_hi) {
-            __half2 hi[2], lo[2];
-            split_f16x2(v.x, v.y, hi[0], lo[0]);
-            split_f16x2(v.z, v.w, hi[1], lo[1]);
-            *reinterpret_cast<uint2*>(out_hi + site * F::N + col0 + cc) = *reinterpret_cast<const uint2*>(hi);
-            *reinterpret_cast<uint2*>(out_lo + site * F::N + col0 + cc) = *reinterpret_cast<const uint2*>(lo);
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, G::TMEM_COLS);
   }
 }
 

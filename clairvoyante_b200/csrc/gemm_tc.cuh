@@ -43,6 +43,8 @@ struct GemmArgs {
   int64_t c_batch_stride;
   int kb_per_slice;
   int a_kshift0, a_kshift_per_batch;  // MN only
+  int f16;                 // operands are (split) fp16 instead of bf16: the inference FC4 of v3_slim
+  const float* inv_scale;  // GEMM_EPI_BIAS_SELU: accumulator * inv_scale[0] + bias (power-of-two pre-scaled fp16 weights); may be NULL
 };
 
 template <int BN_, bool MN_ = false>
@@ -160,6 +162,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
 
   if (warp == 0) {
     if (elect_one()) {
+      pdl_wait();
       const uint32_t bytes = split ? G::STAGE_BYTES : G::A_BYTES + G::B_BYTES;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % G::STAGES;
@@ -192,7 +195,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(G::BM, BN) | (MN ? (1u << 15) | (1u << 16) : 0u);  // a_major, b_major = MN
+      const uint32_t idesc = (g.f16 ? umma_idesc_f16(G::BM, BN) : umma_idesc_bf16(G::BM, BN)) |
+                             (MN ? (1u << 15) | (1u << 16) : 0u);  // a_major, b_major = MN
       int kb = 0;
       for (int c = 0; c < nchunks; ++c) {
         const int buf = c & 1;
@@ -235,6 +239,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
     float* crow = C + (int64_t)row * ldc + n0;
+    const float isc = (EPI == GEMM_EPI_BIAS_SELU && g.inv_scale) ? g.inv_scale[0] : 1.f;
     auto emit = [&](int cc, const float (&v)[16]) {  // 16 consecutive columns starting at n0 + cc
       if (row >= M) return;
 #pragma unroll
@@ -244,7 +249,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
         float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         if (EPI == GEMM_EPI_BIAS_SELU) {
           const float4 b = *reinterpret_cast<const float4*>(bias + col);
-          o.x = selu_f(o.x + b.x); o.y = selu_f(o.y + b.y); o.z = selu_f(o.z + b.z); o.w = selu_f(o.w + b.w);
+          o.x = selu_f(fmaf(o.x, isc, b.x)); o.y = selu_f(fmaf(o.y, isc, b.y));
+          o.z = selu_f(fmaf(o.z, isc, b.z)); o.w = selu_f(fmaf(o.w, isc, b.w));
         } else if (EPI == GEMM_EPI_ACCUM) {
           const float4 p = *reinterpret_cast<const float4*>(crow + cc + j);
           o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;

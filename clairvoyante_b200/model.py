@@ -17,7 +17,7 @@ import numpy as np
 from . import _lib, tf_bundle, initializers, param
 
 _VARIANT_ID = {"v3": 0, "v3_slim": 1}
-COMPUTE_MODES = {"fp32": 0, "fp16x3": 1}
+COMPUTE_MODES = {"fp32": 0, "fp16x3": 1, "fp16": 2}
 TRAIN_MODES = {"fp32": 0, "bf16x3": 1, "bf16": 2}
 
 
@@ -167,6 +167,13 @@ class ClairvoyanteBase(object):
                                         beta2_power=np.float32(0.999 ** (t.value + 1))))
         d["step"] = np.int64(t.value)
         np.savez(self._ckpt_path(fn), **d)
+        # the reference's callVarBam.py / callVarBamParallel.py test for `<prefix>.meta` before they restore (CheckFileExist
+        # with sfx='.meta'); tf.train.Saver().restore itself reads only .index / .data, so an empty graph-less .meta and the
+        # usual `checkpoint` state file are enough for a checkpoint written here to pass those entry points
+        if not os.path.exists(fn + ".meta"):
+            open(fn + ".meta", "wb").close()
+        with open(os.path.join(os.path.dirname(os.path.abspath(fn)), "checkpoint"), "w") as f:
+            f.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (os.path.basename(fn), os.path.basename(fn)))
 
     def getStep(self):
         """number of Adam updates applied so far (what TF keeps as beta1_power / beta2_power)"""

@@ -664,11 +664,17 @@ def DecompressArray(array, start, num, maximum):
         num = maximum - start
         endFlag = 1
     bs = param.bloscBlockSize
+    if num <= 0:
+        # start == maximum (a set whose size is a multiple of the block size, asked for its tail): the reference decodes the
+        # always-present trailing block and returns an empty slice of it (utils_v2.py:196-207)
+        blk = unpack_array(array[min(start // bs, len(array) - 1)]) if len(array) else np.empty((0,), np.float32)
+        return blk[:0], 0, 1
     first, last = start // bs, (start + num - 1) // bs
-    if last - first >= 2:
+    head = unpack_array(array[first]) if last - first >= 2 else None
+    if head is not None and head.dtype.kind not in "SUO":
+        # (byte-string blocks -- the position keys -- differ in width from block to block: np.concatenate below widens them)
         # a training batch spans 20 blocks: decode them on the pool (the C decoder and zlib drop the GIL) and let every worker
         # copy its rows straight into the batch -- decode and the 21 MB gather both run in parallel
-        head = unpack_array(array[first])
         out = np.empty((num,) + head.shape[1:], head.dtype)
 
         def place(i, a=None):
@@ -683,7 +689,7 @@ def DecompressArray(array, start, num, maximum):
         for f in futures:
             f.result()
         return out, num, endFlag
-    parts = [unpack_array(array[i]) for i in range(first, last + 1)]
+    parts = [head if (i == first and head is not None) else unpack_array(array[i]) for i in range(first, last + 1)]
     out = np.concatenate(parts) if len(parts) > 1 else parts[0]
     left = start % bs
     if left != 0 or num % bs != 0:

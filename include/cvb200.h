@@ -38,8 +38,11 @@ enum { CVB_V3 = 0, CVB_V3_SLIM = 1 };
 /* arithmetic mode of the forward pass */
 enum {
   CVB_COMPUTE_FP32 = 0,   /* fp32 SIMT everywhere (bit-faithful op order per layer) */
-  CVB_COMPUTE_FP16X3 = 1  /* conv2/conv3/FC4/FC5+heads on tcgen05 with split-fp16 (hi+lo) operands, fp32 accumulate:
+  CVB_COMPUTE_FP16X3 = 1, /* conv2/conv3/FC4/FC5+heads on tcgen05 with split-fp16 (hi+lo) operands, fp32 accumulate:
                              fp32-equivalent (logits within 1e-3 of fp64), the default */
+  CVB_COMPUTE_FP16 = 2    /* v3_slim only (BASELINE configs[2] "v3_slim inference, fp16"): the same tensor pipeline with plain
+                             fp16 operands -- one MMA term instead of three, activations kept as one fp16 plane, fp32
+                             accumulate; logits within 2e-3 * max(1, max |logit|) of fp64 (tests/test_forward_gpu.py) */
 };
 
 const char* cvb_last_error(void);

@@ -19,7 +19,18 @@ TOL = 1e-3
 
 
 # (variant, compute mode): every parity test runs on each arithmetic path the library ships
-CASES = [("v3", "fp16x3"), ("v3", "fp32"), ("v3_slim", "fp16x3"), ("v3_slim", "fp32")]
+CASES = [("v3", "fp16x3"), ("v3", "fp32"), ("v3_slim", "fp16x3"), ("v3_slim", "fp32"), ("v3_slim", "fp16")]
+# "fp16" = BASELINE configs[2] (v3_slim, plain fp16 operands: one MMA term, activations stored as one fp16 plane, fp32
+# accumulate).  Its stated tolerance: |logit - oracle_fp64| <= 2e-3 * max(1, max |logit|) -- fp16's 2^-11 relative rounding on
+# every activation and weight through five layers (measured: 5e-4 of the largest logit); the fp32-equivalent modes keep the
+# 1e-3 absolute bar of north_star.
+FP16_REL = 2e-3
+
+
+def _tol(mode, ref_logits):
+    if mode != "fp16" or not len(ref_logits):
+        return TOL
+    return FP16_REL * max(1.0, float(np.abs(ref_logits).max()))
 
 
 def _model(variant, W, mode=None, **kw):
@@ -43,9 +54,10 @@ def _check(variant, W, x, m=None, tol=TOL, mode=None):
     r16 = O.out16(ref)
     assert out16.shape == (len(x), 16) and out16.dtype == np.float32
     if len(x):
+        tol = _tol(mode, ref["logits"]) if tol == TOL else tol
         err = np.abs(lg - ref["logits"]).max()
         assert err <= tol, "max |logit - oracle| = %g" % err
-        assert np.abs(out16 - r16).max() <= 2e-4
+        assert np.abs(out16 - r16).max() <= (2e-4 if mode != "fp16" else 0.25 * tol + 2e-4)
         # argmax per head; a site is exempt only if the oracle's own top-2 margin is below the tolerance
         for a, b in ((0, 4), (4, 6), (6, 10), (10, 16)):
             rl = ref["logits"][:, a:b]
@@ -75,8 +87,9 @@ def test_golden_fixture(variant, mode):
     x = synth.make_sites(int(d["n"]), int(d["data_seed"]))
     m = _model(variant, W, mode)
     out16, lg = m.predictLogits(x)
-    assert np.abs(lg - d["logits"]).max() <= TOL
-    assert np.abs(out16 - d["out16"]).max() <= 2e-4
+    tol = _tol(mode, d["logits"])
+    assert np.abs(lg - d["logits"]).max() <= tol
+    assert np.abs(out16 - d["out16"]).max() <= (2e-4 if mode != "fp16" else 0.25 * tol + 2e-4)
     m.close()
 
 
@@ -112,7 +125,7 @@ def test_multi_chunk_and_pinned_paths(variant, mode):
     # oracle on a sample (fp64 NumPy on 33k sites would take a while)
     idx = np.r_[0:64, 9472 - 32:9472 + 32, 14208 - 32:14208 + 32, n - 64:n]
     ref = O.forward(W, x[idx], variant)
-    assert np.abs(l_page[idx] - ref["logits"]).max() <= TOL
+    assert np.abs(l_page[idx] - ref["logits"]).max() <= _tol(mode, ref["logits"])
     # sharding: contiguous site ranges concatenated in order == single pass
     parts = [m.predictLogits(x[a:b])[0] for a, b in ((0, 10000), (10000, 20001), (20001, n))]
     assert np.array_equal(np.concatenate(parts), o_page)
@@ -180,6 +193,21 @@ def test_stage_intermediates_v3(mode):
     assert np.abs(p3 - L["pool3"]).max() <= 3e-4
     h4 = m.debugRead("h4", 300)
     assert np.abs(h4 - L["fc4"]).max() <= 5e-4
+    m.close()
+
+
+def test_slim_modes_switch_and_report_their_error():
+    """v3_slim: fp32 SIMT, fp16x3 and plain fp16 share buffers; switching back and forth must not leak stale rows; prints the
+    measured logit error of each arithmetic (the fp16 figure is what its stated tolerance is judged against)"""
+    W = I.init_weights("v3_slim", 8)
+    x = synth.make_sites(700, 9)
+    ref = O.forward(W, x, "v3_slim")["logits"]
+    m = _model("v3_slim", W, "fp32")
+    for mode in ("fp16x3", "fp16", "fp32", "fp16", "fp16x3"):
+        m.setComputeMode(mode)
+        err = np.abs(m.predictLogits(x)[1] - ref).max()
+        print("v3_slim %s: max |logit - oracle| = %.3g (max |logit| %.3g)" % (mode, err, np.abs(ref).max()))
+        assert err <= _tol(mode, ref)
     m.close()
 
 
