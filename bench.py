@@ -370,7 +370,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"          # rank 0 prints ONE JSON line on stdout:
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner (printed at WARN too) goes to stderr
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 

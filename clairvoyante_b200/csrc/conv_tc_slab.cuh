@@ -68,7 +68,6 @@ using Conv2Slab = ConvSlabCfg<Conv2Tc, 8, 16, 4, false, true>;  // two tiles of 
 using Conv3Slab = ConvSlabCfg<Conv3Tc, 3, 6, 4, false, false, 0>;  // (NCB = 6, 24 warps x 32 columns, measured no faster: 0.203 vs 0.199 ms)
 using SlimConv3Slab = ConvSlabCfg<SlimConv3Tc, 4, 8>;
 // resident-weight variants (CVB_CONV_RESIDENT=1): the shared memory the weight ring held goes to deeper activation rings
-using Conv2SlabRes = ConvSlabCfg<Conv2Tc, 12, 0, 4, true>;
 // conv3 keeps the first pooling code and the shared-memory bias (EPI 0, BC off): measured per 18,944-site launch 0.167 ms
 // against 0.175 with the constant-bank bias and 0.189 with the predicated-load pooling that helps conv2 (0.139 -> 0.127)
 using Conv3SlabRes = ConvSlabCfg<Conv3Tc, 6, 0, 4, true, false, 0>;

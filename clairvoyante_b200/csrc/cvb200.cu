@@ -110,16 +110,12 @@ struct cvb_model {
   int tc_merged = 1;
   int tc_cluster = 1;  // 2-CTA clusters with weight multicast in the conv tensor kernels (needs tc_merged)
   int tc_slab = 1;     // slab-mode conv kernels (conv_tc_slab.cuh): A loaded once per (tile, w'), re-used across kh
-  // v3_slim, every layer but conv1 on tcgen05 (CVB_SLIM_TC=0 keeps the first arrangement: SIMT front, fp32 conv3 output, SIMT FC4)
-  int slim_tc = 1;
+  // v3_slim tensor path: every layer but conv1 and the tail on tcgen05
   __half *d_p1s = nullptr, *d_w2s = nullptr, *d_w4h = nullptr;  // p1 [rows][32] hi|lo; dense conv2 taps hi|lo; fc4/kernel^T [36][4224] hi|lo
   int64_t p1s_rows = 0;
   CUtensorMap map_s2slab, map_s2b;
-  int slim_fc4_tc = 0; // CVB_SLIM_FC4_TC=1: v3_slim inference FC4 as a split-bf16 tcgen05 GEMM (opt-in until run on a B200)
-  uint16_t *d_p3s = nullptr, *d_w4ts = nullptr;  // its operands: planes of the conv3 output / of fc4/kernel^T
   tc::BiasParam hb2 = {}, hb3 = {};  // host copies of conv2/bias, conv3/bias: passed by value to the inference conv kernels
-  int tc_resident = 0; // CVB_CONV_RESIDENT bit mask: 1 = conv3, 2 = conv2 keep their taps in shared memory (ConvSlabCfg RES;
-                       // opt-in until it has been timed and parity-checked on a B200)
+  int tc_resident = 1; // CVB_CONV_RESIDENT=0: conv3 / slim conv3 stream their taps through the ring instead (ConvSlabCfg RES)
   CUtensorMap map_c2slab, map_c3slab;
   CUtensorMap map_c2h2, map_c2h3, map_c2h4, map_c3h2, map_c3h3, map_c3h4;
   // fused tail (FC5 + heads) on tensor cores: A = h4 hi/lo [sites][336], B = [W5 | Wb]^T [176][336]
@@ -288,7 +284,7 @@ extern "C" int cvb_destroy(cvb_model* m) {
   cudaFree(m->d_params); cudaFree(m->d_m); cudaFree(m->d_v); cudaFree(m->d_grad);
   cudaFree(m->d_p2); cudaFree(m->d_p3); cudaFree(m->d_h4); cudaFree(m->d_h5);
   cudaFree(m->d_w3b_hi); cudaFree(m->d_p1); cudaFree(m->d_w2b_hi); cudaFree(m->d_h4s); cudaFree(m->d_wtail);
-  cudaFree(m->d_p3s); cudaFree(m->d_w4ts); cudaFree(m->d_p1s); cudaFree(m->d_w2s); cudaFree(m->d_w4h);
+  cudaFree(m->d_p1s); cudaFree(m->d_w2s); cudaFree(m->d_w4h);
   cudaFree(m->d_w4t_hi); cudaFree(m->d_w4t_lo); cudaFree(m->d_absmax); cudaFree(m->d_inv_scale);
   for (int i = 0; i < cvb_model::NSLOT; ++i) {
     if (i == 0) { cudaFree(m->d_xw); cudaFree(m->d_fc4ws); }
@@ -549,7 +545,6 @@ static int tc_setup(cvb_model* m) {
     m->tc_conv2 = m->tc_conv3 && !(e && e[0] == '0');
     if (make_slab_map<C, tc::Conv2Slab>(m->d_p1, m->p1_rows, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c2slab)) return 1;
     CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::Conv2Slab>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Conv2Slab::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::Conv2SlabRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Conv2SlabRes::SMEM_BYTES));
     if (m->tc_merged && make_conv_merged_maps<C>(m->d_p1, m->p1_rows, m->d_w2b_hi, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c2a4,
                                                  &m->map_c2b2, &m->map_c2b3, &m->map_c2b4, &m->map_c2h2, &m->map_c2h3,
                                                  &m->map_c2h4))
@@ -606,19 +601,11 @@ static int tc_setup_slim(cvb_model* m) {
                           tc::SlimConv3SlabRes::SMEM_BYTES));
   const char* er = getenv("CVB_CONV_RESIDENT");
   m->tc_resident = er ? atoi(er) : 1;  // measured on B200: 0.317 -> 0.207 ms per 33,152-site chunk, bit-identical
-  const char* ef = getenv("CVB_SLIM_FC4_TC");
-  m->slim_fc4_tc = ef && ef[0] == '1';
-  if (m->slim_fc4_tc) {
-    CK(cudaMalloc(&m->d_p3s, (size_t)m->alloc_sites * 4224 * 2 * 2));
-    CK(cudaMalloc(&m->d_w4ts, (size_t)36 * 4224 * 2 * 2));
-  }
   CK(cudaFuncSetAttribute(tc::k_conv_tc<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tc::k_conv_tc<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   {
     // conv2 as a dense row-shifted GEMM on p1 [site][35][32] (k_slim_c1_reg writes it), conv3 with fp16 hi / lo output planes,
     // FC4 as a split-fp16 GEMM over those planes (gemm_tc.cuh)
-    const char* e = getenv("CVB_SLIM_TC");
-    m->slim_tc = !(e && e[0] == '0');
     using C2 = tc::SlimConv2Tc;
     using S2 = tc::SlimConv2SlabRes;
     m->p1s_rows = m->alloc_sites * C2::RPS + 256;
@@ -642,9 +629,6 @@ static int tc_setup_slim(cvb_model* m) {
   return 0;
 }
 
-static int slim_fc4_tc_weights(cvb_model* m, cudaStream_t st);   // (defined with the generic GEMM helpers below)
-static int slim_fc4_tc_forward(cvb_model* m, int64_t n, cudaStream_t st);
-
 // (re)build the split fp16 copy of fc4/kernel on `st` if the fp32 master changed
 static int tc_refresh_weights(cvb_model* m, cudaStream_t st) {
   if (!m->tc_weights_dirty) return 0;
@@ -656,7 +640,6 @@ static int tc_refresh_weights(cvb_model* m, cudaStream_t st) {
     CK(cudaStreamSynchronize(st));
   }
   if (m->variant == CVB_V3_SLIM) {
-    if (m->slim_fc4_tc && slim_fc4_tc_weights(m, st)) return 1;
     using C = tc::SlimConv3Tc;
     CK(cudaMemsetAsync(m->d_absmax + 1, 0, 4, st));
     tc::k_absmax<<<32, 256, 0, st>>>(m->var("conv3/kernel"), 5 * 4 * 16 * 32, m->d_absmax + 1);
@@ -664,7 +647,7 @@ static int tc_refresh_weights(cvb_model* m, cudaStream_t st) {
                                                                                         m->d_w3b_hi, m->d_w3b_lo, m->d_inv_scale + 1);
     CK(cudaGetLastError());
     m->launches += 2;
-    if (m->slim_tc) {
+    {
       using C2 = tc::SlimConv2Tc;
       CK(cudaMemsetAsync(m->d_absmax + 2, 0, 4, st));
       tc::k_absmax<<<16, 256, 0, st>>>(m->var("conv2/kernel"), 3 * 4 * 8 * 16, m->d_absmax + 2);
@@ -727,7 +710,6 @@ extern "C" int cvb_set_compute_mode(cvb_model* m, int mode) {
     return fail("cvb_set_compute_mode: plain fp16 (BASELINE configs[2]) is implemented for v3_slim");
   CK(cudaSetDevice(m->device));
   if (mode != CVB_COMPUTE_FP32 && (m->variant == CVB_V3 ? tc_setup(m) : tc_setup_slim(m))) return 1;
-  if (mode == CVB_COMPUTE_FP16 && !m->slim_tc) return fail("cvb_set_compute_mode: fp16 needs the tensor pipeline (CVB_SLIM_TC=0 is set)");
   if ((mode == CVB_COMPUTE_FP32) != (m->compute_mode == CVB_COMPUTE_FP32)) {
     // p2's zero padding rows sit at different byte offsets in the fp32 and the fp16 hi/lo layouts
     CK(cudaDeviceSynchronize());
@@ -898,7 +880,7 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
   if (tensor && tc_refresh_weights(m, st)) return 1;
   static const bool c1_reg = !(getenv("CVB_C1_REG") && getenv("CVB_C1_REG")[0] == '0');
   // k_v3_c1_reg<KIND> / k_slim_c1_reg<KIND> widen a narrow feed on their own
-  const bool fused_feed = tensor && (m->variant == CVB_V3 ? (m->tc_conv2 && c1_reg) : (m->slim_tc != 0));
+  const bool fused_feed = tensor && (m->variant == CVB_V3 ? (m->tc_conv2 && c1_reg) : true);
   if (kind != X_F32 && !fused_feed) {
     if (widen_chunk(m, xin, kind, n, st)) return 1;
     xin = m->d_xw;
@@ -932,7 +914,7 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
         if (prof_mark(m, st)) return 1;  // kind 0 = SIMT front (conv1+pool1 here), kind 1 = tcgen05 conv2
         using T = tc::Conv2Tc;
         __half* p2_hi = reinterpret_cast<__half*>(m->d_p2);
-        if (launch_conv_tc<T, tc::Conv2Slab, tc::Conv2SlabRes>(m, m->tc_resident & 2, n, st, &m->map_c2slab, m->map_c2a_hi, m->map_c2a_lo, m->map_c2b_hi, m->map_c2b_lo, m->map_c2a4, m->map_c2b2,
+        if (launch_conv_tc<T, tc::Conv2Slab, tc::Conv2Slab>(m, 0, n, st, &m->map_c2slab, m->map_c2a_hi, m->map_c2a_lo, m->map_c2b_hi, m->map_c2b_lo, m->map_c2a4, m->map_c2b2,
                               m->map_c2b3, m->map_c2b4, m->map_c2h2, m->map_c2h3, m->map_c2h4, m->var("conv2/bias"), m->hb2,
                               m->d_inv_scale + 2, p2_hi, p2_hi + m->p2_rows * 128))
           return 1;
@@ -1057,7 +1039,7 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
       if (prof_mark(m, st)) return 1;
     }
     m->launches += 5;
-  } else if (tensor && m->slim_tc) {
+  } else if (tensor) {
     // ---- v3_slim on the tensor path: conv1 (SIMT, registers) -> conv2 (dense row-shifted GEMM) -> conv3 -> FC4 (GEMM) -> tail
     const bool hi_only = m->compute_mode == CVB_COMPUTE_FP16;  // plain fp16: one MMA term, hi planes only
     using C2 = tc::SlimConv2Tc;
@@ -1115,34 +1097,20 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
     if (prof_mark(m, st)) return 1;
     m->launches += 5;
   } else {
+    // ---- v3_slim, fp32 SIMT kernels (CVB_COMPUTE_FP32)
     {
       using F = FrontSlim<6>;
       int64_t tiles = (n + 5) / 6;
       int grid = (int)std::min<int64_t>(tiles, 4 * sms);
-      if (tensor) {
-        auto k = k_slim_front<6, true>;
-        CK(set_smem(k, F::SMEM_BYTES));
-        k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
-                                            m->var("conv2/bias"), m->d_p2, reinterpret_cast<__half*>(m->d_p2) + m->p2_rows * 64);
-      } else {
-        auto k = k_slim_front<6, false>;
-        CK(set_smem(k, F::SMEM_BYTES));
-        k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
-                                            m->var("conv2/bias"), m->d_p2, nullptr);
-      }
+      auto k = k_slim_front<6, false>;
+      CK(set_smem(k, F::SMEM_BYTES));
+      k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
+                                          m->var("conv2/bias"), m->d_p2, nullptr);
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
       if (prof_mark(m, st)) return 1;  // (no separate conv2 kernel)
     }
-    if (tensor) {
-      using T = tc::SlimConv3Tc;
-      if (launch_conv_tc<T, tc::SlimConv3Slab, tc::SlimConv3SlabRes>(m, m->tc_resident & 1, n, st, &m->map_c3slab, m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo,
-                                               m->map_c3a4, m->map_c3b2, m->map_c3b3,
-                            m->map_c3b4, m->map_c3h2, m->map_c3h3, m->map_c3h4, m->var("conv3/bias"), m->hb3, m->d_inv_scale + 1,
-                            reinterpret_cast<__half*>(m->d_p3), nullptr))
-        return 1;
-      if (prof_mark(m, st)) return 1;
-    } else {
+    {
       using C = ConvCfg<16, 32, 5, 33, 3, 8, 8>;
       using L = ConvLayerSmem<C, 1>;
       auto k = k_conv_layer<C, 1, 256, false>;
@@ -1153,10 +1121,7 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
     }
-    if (tensor && m->slim_fc4_tc) {
-      if (slim_fc4_tc_forward(m, n, st)) return 1;
-      if (prof_mark(m, st)) return 1;
-    } else {
+    {
       using F = FcCfg<36, 9, 4, 28, 8>;
       auto k = k_fc4<F>;
       CK(set_smem(k, F::SMEM_BYTES));
@@ -1271,7 +1236,8 @@ static int predict_host_impl(cvb_model* m, const void* xv, int kind, int64_t n, 
   }
   float* const heads[4] = {base, zygosity, var_type, indel_length};
   const bool pinned_in = is_pinned(x);
-  const bool pinned_out = is_pinned(base) && is_pinned(zygosity) && is_pinned(var_type) && is_pinned(indel_length) &&
+  // (a caller that pins its outputs pins its input too: skipping five pointer queries is worth 5-8 us on a 1,000-site call)
+  const bool pinned_out = pinned_in && is_pinned(base) && is_pinned(zygosity) && is_pinned(var_type) && is_pinned(indel_length) &&
                           (!logits16 || is_pinned(logits16));
   const int64_t CHUNK = m->CHUNK, cap = m->alloc_sites;
   const int64_t nchunks = (n + CHUNK - 1) / CHUNK;
@@ -1280,13 +1246,20 @@ static int predict_host_impl(cvb_model* m, const void* xv, int kind, int64_t n, 
     // the copy in, the kernels and the copy out go down ONE stream with no events in between, the four head blocks are packed
     // back to back ([4 | 2 | 4 | 6] x np floats, np = n rounded up to 4 for the vector stores) and come back in one copy.
     cudaStream_t st = m->s_comp;
-    const char* src = x;
-    if (!pinned_in) {
-      memcpy(m->h_x[0], src, (size_t)n * 528 * esz);
-      src = reinterpret_cast<const char*>(m->h_x[0]);
-    }
     void* dx = kind == X_F32 ? (void*)m->d_x[0] : (void*)m->d_x16[0];
-    CK(cudaMemcpyAsync(dx, src, (size_t)n * 528 * esz, cudaMemcpyHostToDevice, st));
+    const size_t bytes = (size_t)n * 528 * esz;
+    if (pinned_in) {
+      CK(cudaMemcpyAsync(dx, x, bytes, cudaMemcpyHostToDevice, st));
+    } else {
+      // pageable input: staged through the pinned slot in four pieces, each on its way to the device while the next is copied
+      char* hs = reinterpret_cast<char*>(m->h_x[0]);
+      const size_t piece = ((bytes / 4) + 4095) & ~(size_t)4095;
+      for (size_t o = 0; o < bytes; o += piece) {
+        const size_t len = std::min(piece, bytes - o);
+        memcpy(hs + o, x + o, len);
+        CK(cudaMemcpyAsync(static_cast<char*>(dx) + o, hs + o, len, cudaMemcpyHostToDevice, st));
+      }
+    }
     const int64_t np = (n + 3) & ~(int64_t)3;
     float* o = m->d_out[0];
     const OutDst dst{nullptr, o, o + np * 4, o + np * 6, o + np * 10};
@@ -1578,24 +1551,6 @@ static int split_transpose_bf16(const float* src, int64_t R, int C, int64_t ld_s
   return 0;
 }
 
-// v3_slim inference FC4 on tcgen05 (opt-in, CVB_SLIM_FC4_TC=1; written without a GPU at hand -- tools/ab_resident.py-style A/B
-// first): the fp32 conv3 output [n][4224] is split into bf16 hi/lo planes and multiplied with the split-bf16 transpose of
-// fc4/kernel by the generic GEMM of the training path (N = 36 in one 48-column tile, K-chunked, bias + SELU epilogue) -- the same
-// two launches train_forward_slim uses.
-static int slim_fc4_tc_weights(cvb_model* m, cudaStream_t st) {
-  if (split_transpose_bf16(m->var("fc4/kernel"), 4224, 36, 36, m->d_w4ts, 36 * 4224, 4224, st)) return 1;
-  m->launches += 1;
-  return 0;
-}
-static int slim_fc4_tc_forward(cvb_model* m, int64_t n, cudaStream_t st) {
-  if (split_rows_bf16(m->d_p3, n, 4224, m->d_p3s, m->alloc_sites * 4224, st)) return 1;
-  if (launch_gemm_tc<48, true, tc::GEMM_EPI_BIAS_SELU>(m, m->d_p3s, m->alloc_sites * 4224, 4224, m->d_w4ts, 36 * 4224, 4224, (int)n, 36, 4224,
-                                                       m->d_h4, 36, m->var("fc4/bias"), st))
-    return 1;
-  m->launches += 1;
-  return 0;
-}
-
 // Conv weight gradient on tcgen05 (training_op, clairvoyante_v3.py:174, for conv2 / conv3):
 //   dW[kh][kw][c][co] = sum_R in[R - 1 + kh][(w', c)] * g[R][(w, co)],   w' = w + kw - 1,
 // over the flattened (site, row) index R of the padded layouts (g stored one row down, its pad rows are zero, so terms that
@@ -1633,22 +1588,15 @@ using Conv2D = tc::ConvTcCfg<30, 2, 32, 16, 29, 1, 29, 0, 4, true, 2, false, tru
 // v3_slim conv3 (5x4, 16 -> 32, rows padded 2 + 33 + 2): forward = the inference configuration; data gradient 32 -> 16
 using SlimConv3D = tc::ConvTcCfg<37, 5, 32, 16, 33, 1, 33, 0, 4, true, 2, false, true>;  // g3h [.][37][128] -> gp2 [.][33][64]
 using SlimConv3DS = tc::ConvSlabCfg<SlimConv3D, 3, 6>;
-using SlimConv3FS = tc::ConvSlabCfg<tc::SlimConv3Tc, 4, 8>;             // the inference geometry with the bias read from memory
-using SlimConv3FR = tc::ConvSlabCfg<tc::SlimConv3Tc, 8, 0, 4, true>;
+using SlimConv3FS = tc::ConvSlabCfg<tc::SlimConv3Tc, 4, 8>;             // the inference geometry, fp32 output, bias read from memory
 using Conv2FS = tc::ConvSlabCfg<Conv2F, 4, 8>;
 using Conv3FS = tc::ConvSlabCfg<Conv3F, 3, 6>;
 using Conv3DS = tc::ConvSlabCfg<Conv3D, 3, 3>;
 using Conv2DS = tc::ConvSlabCfg<Conv2D, 3, 6>;
-// resident-weight variants (CVB_CONV_RESIDENT bit 4, see ConvSlabCfg)
-using SlimConv3DR = tc::ConvSlabCfg<SlimConv3D, 6, 0, 4, true>;
-using Conv2FR = tc::ConvSlabCfg<Conv2F, 8, 0, 4, true>;
-using Conv3FR = tc::ConvSlabCfg<Conv3F, 6, 0, 4, true>;
-using Conv3DR = tc::ConvSlabCfg<Conv3D, 3, 0, 4, true>;
-using Conv2DR = tc::ConvSlabCfg<Conv2D, 6, 0, 4, true>;
 }  // namespace trc
 
 // act: hi plane [rows = nc * RPS][KROW], lo plane act_plane elements later; wts: B [KH * NOUT][KROW] hi then lo plane
-template <class F, class S, class SR>
+template <class F, class S>
 static int launch_train_conv(cvb_model* m, const uint16_t* act, int64_t act_plane, const uint16_t* wts, int64_t nc, const float* bias,
                              const float* inv_scale, float* out, cudaStream_t st) {
   const CUtensorMapSwizzle sw = F::ROW_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -1666,16 +1614,11 @@ static int launch_train_conv(cvb_model* m, const uint16_t* act, int64_t act_plan
   }
   const int64_t tiles = (nc * F::RPS + S::TILE_STEP - 1) / S::TILE_STEP;
   const int grid = (int)std::min<int64_t>(tiles, m->num_sms);
-  static const int resident = getenv("CVB_CONV_RESIDENT") ? atoi(getenv("CVB_CONV_RESIDENT")) & 4 : 0;
-  if (resident) {
-    auto k = tc::k_conv_slab<F, SR>;
-    CK(set_smem(k, SR::SMEM_BYTES));
-    k<<<grid, SR::THREADS, SR::SMEM_BYTES, st>>>(ma, mb[0], mb[1], mb[2], nc, bias, inv_scale, reinterpret_cast<__half*>(out), nullptr, 0, tc::BiasParam{});
-  } else {
-    auto k = tc::k_conv_slab<F, S>;
-    CK(set_smem(k, S::SMEM_BYTES));
-    k<<<grid, S::THREADS, S::SMEM_BYTES, st>>>(ma, mb[0], mb[1], mb[2], nc, bias, inv_scale, reinterpret_cast<__half*>(out), nullptr, 0, tc::BiasParam{});
-  }
+  // (weights through the ring: keeping the taps resident was measured on these launches too -- 3.27 -> 3.25 ms per
+  //  10,000-tensor step, inside the noise -- and not kept)
+  auto k = tc::k_conv_slab<F, S>;
+  CK(set_smem(k, S::SMEM_BYTES));
+  k<<<grid, S::THREADS, S::SMEM_BYTES, st>>>(ma, mb[0], mb[1], mb[2], nc, bias, inv_scale, reinterpret_cast<__half*>(out), nullptr, 0, tc::BiasParam{});
   CK(cudaGetLastError());
   m->launches += 1;
   return 0;
@@ -1726,7 +1669,7 @@ static int train_forward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t se
   if (stc) {
     // conv3 on the tcgen05 slab kernel (the inference configuration already keeps every SELU output: no pooling in slim),
     // FC4 = c3 [sites][4224] . W4 as a split-bf16 GEMM (N = 36 in one 48-column tile)
-    if (launch_train_conv<tc::SlimConv3Tc, trc::SlimConv3FS, trc::SlimConv3FR>(m, w->p2h, w->cap * 37 * 64, w->wf3, nc, m->var("conv3/bias"), w->fsc + 1,
+    if (launch_train_conv<tc::SlimConv3Tc, trc::SlimConv3FS>(m, w->p2h, w->cap * 37 * 64, w->wf3, nc, m->var("conv3/bias"), w->fsc + 1,
                                                               w->c3, st))
       return 1;
     if (split_rows_bf16(w->c3, nc, 4224, w->p3s, w->cap * 4224, st)) return 1;
@@ -1803,7 +1746,7 @@ static int train_backward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t s
                                                                         bf(w->g3h), bf(w->g3h) + w->cap * 37 * 128);
     if (launch_conv_wgrad_tc<16, 32, 5, 32, -2>(m, w->p2b, w->cap * 37 * 64, w->g3h, w->cap * 37 * 128, nc * 37, gvar(m, "conv3/kernel"), st))
       return 1;
-    if (launch_train_conv<trc::SlimConv3D, trc::SlimConv3DS, trc::SlimConv3DR>(m, w->g3h, w->cap * 37 * 128, w->wd3, nc, nullptr, w->fsc + 2, w->gp2, st))
+    if (launch_train_conv<trc::SlimConv3D, trc::SlimConv3DS>(m, w->g3h, w->cap * 37 * 128, w->wd3, nc, nullptr, w->fsc + 2, w->gp2, st))
       return 1;
   } else {
   k_gemm_tn<<<dim3(4224 / 64, 1), 256, 0, st>>>(w->c3, 4224, w->g4, 36, gvar(m, "fc4/kernel"), 36, 4224, 36, nc);
@@ -1855,11 +1798,11 @@ static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, i
                                                      tcm ? bf(w->p1b) + w->cap * 30 * 64 : nullptr);
   }
   if (tcm) {
-    if (launch_train_conv<trc::Conv2F, trc::Conv2FS, trc::Conv2FR>(m, w->p1h, w->cap * 30 * 64, w->wf2, nc, m->var("conv2/bias"), w->fsc + 0, w->c2, st))
+    if (launch_train_conv<trc::Conv2F, trc::Conv2FS>(m, w->p1h, w->cap * 30 * 64, w->wf2, nc, m->var("conv2/bias"), w->fsc + 0, w->c2, st))
       return 1;
     k_pool_fwd<4><<<gsz(nc * 26 * 32), 256, 0, st>>>(w->c2, nc, 29, 128, w->p2p, 28, 1, hp(w->p2h), hp(w->p2h) + w->cap * 28 * 128,
                                                      bf(w->p2b), bf(w->p2b) + w->cap * 28 * 128);
-    if (launch_train_conv<trc::Conv3F, trc::Conv3FS, trc::Conv3FR>(m, w->p2h, w->cap * 28 * 128, w->wf3, nc, m->var("conv3/bias"), w->fsc + 1, w->c3, st))
+    if (launch_train_conv<trc::Conv3F, trc::Conv3FS>(m, w->p2h, w->cap * 28 * 128, w->wf3, nc, m->var("conv3/bias"), w->fsc + 1, w->c3, st))
       return 1;
     // pool3 also writes p3 as the split-bf16 A operand of the FC4 forward GEMM
     k_pool_fwd<3, true><<<gsz(nc * 24 * 48), 256, 0, st>>>(w->c3, nc, 26, 192, w->p3, 24, 0, hp(w->p3s), hp(w->p3s) + w->cap * 4608);
@@ -2034,7 +1977,7 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
       CK(cudaGetLastError());
     }
     if (tcm) {
-      if (launch_train_conv<trc::Conv3D, trc::Conv3DS, trc::Conv3DR>(m, w->g3h, w->cap * 28 * 256, w->wd3, nc, nullptr, w->fsc + 2, w->gp2, st)) return 1;
+      if (launch_train_conv<trc::Conv3D, trc::Conv3DS>(m, w->g3h, w->cap * 28 * 256, w->wd3, nc, nullptr, w->fsc + 2, w->gp2, st)) return 1;
     } else {
       using C = ConvCfg<48, 32, 3, 26, 3, 8, 8, 2>;
       using L = ConvLayerSmem<C, 1>;
@@ -2060,7 +2003,7 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
       CK(cudaGetLastError());
     }
     if (tcm) {
-      if (launch_train_conv<trc::Conv2D, trc::Conv2DS, trc::Conv2DR>(m, w->g2h, w->cap * 30 * 128, w->wd2, nc, nullptr, w->fsc + 2, w->gp1, st)) return 1;
+      if (launch_train_conv<trc::Conv2D, trc::Conv2DS>(m, w->g2h, w->cap * 30 * 128, w->wd2, nc, nullptr, w->fsc + 2, w->gp1, st)) return 1;
     } else {
       using C = ConvCfg<32, 16, 2, 29, 4, 8, 8, 2>;
       using L = ConvLayerSmem<C, 1>;
