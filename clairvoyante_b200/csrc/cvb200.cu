@@ -768,9 +768,10 @@ static cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t 
   cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
 }
-static bool use_pdl(const cvb_model* m) {
+static bool use_pdl(const cvb_model* m, int which = 0) {
   static const bool on = !(getenv("CVB_PDL") && getenv("CVB_PDL")[0] == '0');
-  return on && !m->profiling;  // (event records between the kernels would serialise them anyway)
+  static const int off_mask = getenv("CVB_PDL_OFF") ? atoi(getenv("CVB_PDL_OFF")) : 0;  // diagnosis: 1 conv2, 2 conv3, 4 fc4, 8 after fc4
+  return on && !(off_mask & which) && !m->profiling;  // (event records between the kernels would serialise them anyway)
 }
 
 template <class K>
@@ -1067,7 +1068,7 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
       const int64_t tiles = (n * C2::RPS + S2::TILE_STEP - 1) / S2::TILE_STEP;
       __half* p2_hi = reinterpret_cast<__half*>(m->d_p2);
       CK(launch_k(tc::k_conv_slab<C2, S2>, dim3((unsigned)std::min<int64_t>(tiles, sms)), dim3(S2::THREADS), S2::SMEM_BYTES, st, 1, 1,
-                  use_pdl(m), m->map_s2slab, m->map_s2b, m->map_s2b, m->map_s2b, n, m->var("conv2/bias"),
+                  use_pdl(m, 1), m->map_s2slab, m->map_s2b, m->map_s2b, m->map_s2b, n, m->var("conv2/bias"),
                   (const float*)(m->d_inv_scale + 2), p2_hi, p2_hi + m->p2_rows * 64, hi_flag, m->hb2));
       if (prof_mark(m, st)) return 1;
     }
@@ -1076,7 +1077,7 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
       const int64_t tiles = (n * C3::RPS + S3::TILE_STEP - 1) / S3::TILE_STEP;
       __half* p3_hi = reinterpret_cast<__half*>(m->d_p3);
       CK(launch_k(tc::k_conv_slab<C3, S3>, dim3((unsigned)std::min<int64_t>(tiles, sms)), dim3(S3::THREADS), S3::SMEM_BYTES, st, 1, 1,
-                  use_pdl(m), m->map_c3slab, m->map_c3b2, m->map_c3b3, m->map_c3b4, n, m->var("conv3/bias"),
+                  use_pdl(m, 2), m->map_c3slab, m->map_c3b2, m->map_c3b3, m->map_c3b4, n, m->var("conv3/bias"),
                   (const float*)(m->d_inv_scale + 1), p3_hi, p3_hi + m->alloc_sites * 4224, hi_flag, m->hb3));
       if (prof_mark(m, st)) return 1;
     }
@@ -1085,7 +1086,10 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
       ex.f16 = 1;
       ex.terms = hi_only ? 1 : 3;
       ex.inv_scale = m->d_inv_scale;
-      ex.pdl = use_pdl(m);
+      // (launched the ordinary way: as a programmatic dependent of conv3 this 8-CTA GEMM took 37 us longer whenever
+      //  conv3 had 2..7 CTAs with a single tile -- 999 <= n <= 1016, the reference's batch size among them -- and saved 4 us
+      //  otherwise; measured with tools/small_n_probe.py)
+      ex.pdl = false;
       if (launch_gemm_tc<48, true, tc::GEMM_EPI_BIAS_SELU>(m, reinterpret_cast<const uint16_t*>(m->d_p3), m->alloc_sites * 4224, 4224,
                                                            reinterpret_cast<const uint16_t*>(m->d_w4h), 36 * 4224, 4224, (int)n, 36, 4224,
                                                            m->d_h4, 36, m->var("fc4/bias"), st, ex))

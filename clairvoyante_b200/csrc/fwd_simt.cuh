@@ -354,6 +354,7 @@ k_slim_c1_reg(const void* __restrict__ xv, int64_t n, const float* __restrict__ 
   const int64_t site = gt >> 3;
   const int w = (int)(gt & 7) >> 1, cq = (int)(gt & 1);
   const int64_t wsite0 = (gt >> 5) * 4;  // first of this warp's four sites
+  if (threadIdx.x == 0) pdl_launch_dependents();  // conv2's CTAs may set themselves up during this grid's last wave
   if (wsite0 >= n) return;
   unsigned long long wr[4][2][4];  // [w'][channel pair][co]: {W[kw][2cp][co], W[kw][2cp+1][co]}, kw = w' - w + 1
 #pragma unroll

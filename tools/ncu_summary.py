@@ -71,5 +71,39 @@ def main(rep, launches):
         print()
 
 
+# kernel name fragments -> (variant, bench kernel kind) for profiles/traffic.json
+KINDS = [("k_v3_c1_reg", ("v3", "front")), ("ConvTcCfg<(int)30, (int)2", ("v3", "conv2")), ("ConvTcCfg<(int)28, (int)3", ("v3", "conv3")),
+         ("k_fc4_tc", ("v3", "fc4")), ("k_tail_tc", ("v3", "tail")), ("k_slim_c1_reg", ("v3_slim", "front")),
+         ("ConvTcCfg<(int)35, (int)3", ("v3_slim", "conv2")), ("ConvTcCfg<(int)37, (int)5", ("v3_slim", "conv3")),
+         ("k_gemm_tc<(int)48", ("v3_slim", "fc4")), ("k_tail<", ("v3_slim", "tail"))]
+
+
+def traffic(rep, out_fn, source_hash):
+    """profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch of every forward kernel in an
+    `ncu --set full` report (the LARGEST launch of each kernel = a full chunk), stamped with the hash of the build"""
+    import json
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(io.StringIO(out)))
+    hdr, units = r[0], r[1]
+    ir, iw, it, ik = (hdr.index(k) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "Kernel Name"))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    res = {"source_hash": source_hash, "report": rep, "v3": {}, "v3_slim": {}, "_detail": {}}
+    for row in r[2:]:
+        for frag, (variant, kind) in KINDS:
+            if frag in row[ik]:
+                b = float(row[ir]) * scale[units[ir]] + float(row[iw]) * scale[units[iw]]
+                if b > res[variant].get(kind, 0):
+                    res[variant][kind] = b
+                    res["_detail"]["%s/%s" % (variant, kind)] = dict(dram_read=float(row[ir]) * scale[units[ir]],
+                                                                     dram_write=float(row[iw]) * scale[units[iw]],
+                                                                     duration=row[it] + " " + units[it])
+                break
+    json.dump(res, open(out_fn, "w"), indent=1)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
+    if len(sys.argv) > 2 and sys.argv[1] == "--traffic":      # ncu_summary.py --traffic <rep> <out.json> <source_hash>
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
