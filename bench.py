@@ -312,7 +312,7 @@ def train_leg(args, cv, W, local, rank, world, dist, barrier, max_over_ranks):
     (Clairvoyante.train at N = 1, parallel.DataParallelTrainer -- NCCL all-reduce inside the library -- at N > 1) on the
     reference's trainBatchSize = 10,000 tensors GLOBAL (strong scaling) and on 10,000 per GPU (weak); host arrays, H2D inside"""
     import torch
-    from clairvoyante_b200 import parallel, synth
+    from clairvoyante_b200 import parallel, synth, utils_v2
     m = cv.Clairvoyante(device=local)
     m.init(seed=1)
     m.setWeights(W)
@@ -323,6 +323,7 @@ def train_leg(args, cv, W, local, rank, world, dist, barrier, max_over_ranks):
             res[label] = res["global_batch_10000"]
             continue
         x, y = synth.make_labeled_sites(total, seed=77)
+        x = utils_v2.with_counts(x)      # what the training drivers hand over (_driver.TrainingSet.fetch): float32 + raw counts
         for _ in range(3):
             tr.train(x, y, seed=1)
         barrier()

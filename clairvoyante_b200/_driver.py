@@ -5,6 +5,8 @@ reference's command lines, log lines and model-call sequences -- tests/test_refe
 reference's own drivers did with a stub model -- but are written on top of this module instead of five copies of one loop."""
 import logging
 import os
+
+import numpy as np
 import sys
 import time
 from threading import Thread
@@ -80,6 +82,11 @@ class TrainingSet(object):
         Y, ny, ey = self.utils.DecompressArray(self.Y, at, rows, self.total)
         if nx != ny or ex != ey:
             sys.exit("Inconsistency between decompressed arrays: %d/%d" % (nx, ny))
+        # the batch also carries its raw counts (uint8 / int16) for the narrow host->device feed of train / getLoss
+        # (cvb_train_step_host_x); packed natively on the reader's side of the train / fetch overlap
+        pack = getattr(self.utils, "with_counts", None)
+        if pack is not None and nx and os.environ.get("CVB_FEED", "counts") != "fp32" and getattr(X, "dtype", None) == np.float32:
+            X = pack(X)
         return X, Y, nx, ex
 
     def rows_wanted(self, at):

@@ -83,6 +83,9 @@ SIGNATURES = {
     "cvb_train_step_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_float, ctypes.c_float,
                                            ctypes.c_float, ctypes.c_uint64, ctypes.c_int, c_vp]),
     "cvb_set_dropout_fc5": (ctypes.c_int, [c_vp, ctypes.c_float]),
+    "cvb_loss_host_x": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_vp, c_i64, c_vp]),
+    "cvb_train_step_host_x": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_vp, c_i64, ctypes.c_float, ctypes.c_float,
+                                             ctypes.c_float, ctypes.c_uint64, ctypes.c_int, c_vp]),
     "cvb_set_train_mode": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "cvb_grad_buffer": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64)]),
     "cvb_nccl_unique_id": (ctypes.c_int, [c_vp]),

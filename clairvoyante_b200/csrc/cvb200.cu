@@ -2133,15 +2133,20 @@ static int run_captured(cvb_model* m, uint64_t key, cudaStream_t st, Body body) 
 static inline uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
 // forward + loss (+ backward) over a host batch in micro-chunks; loss terms accumulate in train->loss[0..3]
-static int train_pass(cvb_model* m, const float* x, const float* y, int64_t n, float drop4, uint64_t seed, bool backward) {
+static int train_pass(cvb_model* m, const void* xv, int kind, const float* y, int64_t n, float drop4, uint64_t seed, bool backward) {
   if (ensure_train_work(m)) return 1;
   TrainWork* w = m->train;
   cudaStream_t st = m->s_comp;
+  const char* x = static_cast<const char*>(xv);
+  const size_t esz = (size_t)kXBytes[kind];
+  if (kind != X_F32 && !w->xn[0]) {  // narrow upload slots (raw counts / fp16 values), widened on the device per micro-chunk
+    for (int i = 0; i < 2; ++i) CK(cudaMalloc(&w->xn[i], (size_t)w->cap * 528 * 2));
+  }
   m->drop5_now = backward ? m->drop5 : 0.f;  // phase = False in getLoss (clairvoyante_v3.py:207-216)
   CK(cudaMemcpyAsync(w->seedbuf, &seed, 8, cudaMemcpyHostToDevice, st));  // (pageable source: staged before the call returns)
   // what a captured sequence depends on besides the chunk: pass kind, arithmetic, dropout rates (baked into DropConst)
   const uint64_t cfg = (uint64_t)(backward ? 1 : 0) | ((uint64_t)m->train_mode << 1) | ((uint64_t)(fbits(drop4) >> 8) << 4) |
-                       ((uint64_t)(fbits(m->drop5_now) >> 8) << 28);
+                       ((uint64_t)(fbits(m->drop5_now) >> 8) << 28) | ((uint64_t)kind << 52);
   auto key_of = [&](int64_t ci, int64_t nc) { return cfg * 0x9E3779B97F4A7C15ull + (uint64_t)(ci + 1) * 1000003ull + (uint64_t)nc * 7919ull; };
   if (run_captured(m, key_of(-1, 0), st, [&]() -> int {
         CK(cudaMemsetAsync(w->loss, 0, 16 * 4, st));
@@ -2156,7 +2161,8 @@ static int train_pass(cvb_model* m, const float* x, const float* y, int64_t n, f
     const int64_t nc = std::min<int64_t>(w->cap, n - s0);
     const int slot = (int)(ci & 1);
     if (ci >= 2) CK(cudaStreamWaitEvent(m->s_h2d, w->ev_done[slot], 0));
-    CK(cudaMemcpyAsync(w->xs[slot], x + s0 * 528, (size_t)nc * 528 * 4, cudaMemcpyHostToDevice, m->s_h2d));
+    void* xdst = kind == X_F32 ? (void*)w->xs[slot] : w->xn[slot];
+    CK(cudaMemcpyAsync(xdst, x + (size_t)s0 * 528 * esz, (size_t)nc * 528 * esz, cudaMemcpyHostToDevice, m->s_h2d));
     CK(cudaMemcpyAsync(w->ys[slot], y + s0 * 16, (size_t)nc * 16 * 4, cudaMemcpyHostToDevice, m->s_h2d));
     CK(cudaEventRecord(w->ev_up[slot], m->s_h2d));
     CK(cudaStreamWaitEvent(st, w->ev_up[slot], 0));
@@ -2164,6 +2170,16 @@ static int train_pass(cvb_model* m, const float* x, const float* y, int64_t n, f
     w->y = w->ys[slot];
     const int64_t n4 = m->variant == CVB_V3 ? 336 : 36;  // dropout counter = flat index into the whole batch's FC4 output
     if (run_captured(m, key_of(ci, nc), st, [&]() -> int {
+          if (kind != X_F32) {  // counts -> the fp32 tensors the layers read, channel 0 subtracted (utils_v2.py:46)
+            const int64_t npos = nc * 132;
+            const int g = (int)std::min<int64_t>((npos + 255) / 256, (int64_t)m->num_sms * 16);
+            float4* o = reinterpret_cast<float4*>(w->xs[slot]);
+            if (kind == X_F16) k_widen<X_F16><<<g, 256, 0, st>>>(w->xn[slot], o, npos);
+            else if (kind == X_I16) k_widen<X_I16><<<g, 256, 0, st>>>(w->xn[slot], o, npos);
+            else k_widen<X_U8><<<g, 256, 0, st>>>(w->xn[slot], o, npos);
+            CK(cudaGetLastError());
+            m->launches += 1;
+          }
           if (train_forward(m, nc, drop4, seed, s0 * n4, st)) return 1;
           k_loss_grad<<<gsz(nc, 128), 128, 0, st>>>(w->logits, w->out16, w->y, nc, backward ? w->dlog : nullptr, w->loss);
           CK(cudaGetLastError());
@@ -2178,13 +2194,17 @@ static int train_pass(cvb_model* m, const float* x, const float* y, int64_t n, f
 }
 
 extern "C" int cvb_loss_host(cvb_model* m, const float* x, const float* y, int64_t n, float* loss) {
+  return cvb_loss_host_x(m, x, X_F32, y, n, loss);
+}
+extern "C" int cvb_loss_host_x(cvb_model* m, const void* x, int x_kind, const float* y, int64_t n, float* loss) {
   if (!m || !loss) return fail("cvb_loss_host: NULL argument");
   if (n < 0) return fail("cvb_loss_host: negative n");
+  if (x_kind < 0 || x_kind > 3) return fail("cvb_loss_host: unknown element kind %d", x_kind);
   *loss = 0.f;
   if (n == 0) return 0;
   if (!x || !y) return fail("cvb_loss_host: NULL buffer");
   CK(cudaSetDevice(m->device));
-  if (train_pass(m, x, y, n, 0.f, 0, false)) return 1;
+  if (train_pass(m, x, x_kind, y, n, 0.f, 0, false)) return 1;
   float l[4];
   CK(cudaMemcpyAsync(l, m->train->loss, 16, cudaMemcpyDeviceToHost, m->s_comp));
   CK(cudaStreamSynchronize(m->s_comp));
@@ -2234,12 +2254,17 @@ extern "C" int cvb_apply_adam(cvb_model* m, float lr, float l2, float* loss6) {
 
 extern "C" int cvb_train_step_host(cvb_model* m, const float* x, const float* y, int64_t n, float lr, float l2, float drop4,
                                    uint64_t dropout_seed, int apply_update, float* loss6) {
+  return cvb_train_step_host_x(m, x, X_F32, y, n, lr, l2, drop4, dropout_seed, apply_update, loss6);
+}
+extern "C" int cvb_train_step_host_x(cvb_model* m, const void* x, int x_kind, const float* y, int64_t n, float lr, float l2,
+                                     float drop4, uint64_t dropout_seed, int apply_update, float* loss6) {
   if (!m) return fail("cvb_train_step_host: NULL model");
+  if (x_kind < 0 || x_kind > 3) return fail("cvb_train_step_host: unknown element kind %d", x_kind);
   if (n <= 0) return fail("cvb_train_step_host: empty batch");
   if (!x || !y) return fail("cvb_train_step_host: NULL buffer");
   if (drop4 < 0.f || drop4 >= 1.f) return fail("cvb_train_step_host: dropout rate %g outside [0,1)", drop4);
   CK(cudaSetDevice(m->device));
-  if (train_pass(m, x, y, n, drop4, dropout_seed, true)) return 1;
+  if (train_pass(m, x, x_kind, y, n, drop4, dropout_seed, true)) return 1;
   // loss sums ride at the tail of the gradient buffer so that one all-reduce covers both
   CK(cudaMemcpyAsync(m->d_grad + m->nparams, m->train->loss, 16, cudaMemcpyDeviceToDevice, m->s_comp));
   if (apply_update) {

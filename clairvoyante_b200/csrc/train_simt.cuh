@@ -20,6 +20,7 @@ struct TrainWork {
   bool slim_tc = false;  // v3_slim: conv3 + FC4 of the training step on tcgen05
   float *x = nullptr, *y = nullptr;  // the micro-chunk being computed: one of the two upload slots below
   float *xs[2] = {nullptr, nullptr}, *ys[2] = {nullptr, nullptr};
+  void* xn[2] = {nullptr, nullptr};  // narrow upload slots (raw uint8 / int16 counts, fp16 values): own allocations
   cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};  // slot uploaded / slot's compute finished
   float *c1 = nullptr, *p1p = nullptr, *c2 = nullptr, *p2p = nullptr, *c3 = nullptr, *p3 = nullptr;
   float *h4 = nullptr, *d4 = nullptr, *h5 = nullptr, *logits = nullptr, *out16 = nullptr;
@@ -59,6 +60,8 @@ static inline void train_work_free(TrainWork* w) {
   cudaFree(w->all16);
   cudaFree(w->amax);
   cudaFree(w->d5);
+  cudaFree(w->xn[0]);
+  cudaFree(w->xn[1]);
   cudaFree(w->seedbuf);
   for (auto& kv : w->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);

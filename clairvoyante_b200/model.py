@@ -302,13 +302,30 @@ class ClairvoyanteBase(object):
         return int(self._lib.cvb_kernel_launches(self._h))
 
     # ---- loss / training (clairvoyante_v3.py:183-227) --------------------------------------
+    _X_KIND = {np.dtype(np.float32): 0, np.dtype(np.float16): 1, np.dtype(np.int16): 2, np.dtype(np.uint8): 3}
+
+    def _x_arg(self, X):
+        """(contiguous array, element kind, n): a CountBatch's raw counts or an explicit uint8 / int16 / float16 array travel
+        narrow (cvb200.h CVB_X_*), anything else as float32"""
+        counts = getattr(X, "counts", None)
+        if counts is not None and counts.shape[0] == X.shape[0]:
+            X = counts
+        if isinstance(X, np.ndarray) and X.dtype in (np.float16, np.int16, np.uint8):
+            x = np.ascontiguousarray(X)
+            n = x.shape[0] if x.ndim > 0 else 0
+            if x.size != n * int(np.prod(self.inputShape)):
+                raise ValueError("expected shape (N,33,4,4), got %s" % (x.shape,))
+            return x, self._X_KIND[x.dtype], n
+        x, n = _f32c(X, self.inputShape)
+        return x, 0, n
+
     def getLoss(self, batchX, batchY):
-        x, n = _f32c(batchX, self.inputShape)
+        x, kind, n = self._x_arg(batchX)
         y, ny = _f32c(batchY, (16,))
         if n != ny:
             raise ValueError("X/Y batch mismatch %d/%d" % (n, ny))
         loss = ctypes.c_float()
-        _lib.check(self._lib.cvb_loss_host(self._h, x.ctypes.data, y.ctypes.data, n, ctypes.byref(loss)))
+        _lib.check(self._lib.cvb_loss_host_x(self._h, x.ctypes.data, kind, y.ctypes.data, n, ctypes.byref(loss)))
         return np.float32(loss.value)
 
     def getLossNoRT(self, batchX, batchY):
@@ -316,7 +333,7 @@ class ClairvoyanteBase(object):
         self.getLossLossRTVal = self.getLoss(batchX, batchY)
 
     def _train_step(self, batchX, batchY, apply_update=1, seed=None):
-        x, n = _f32c(batchX, self.inputShape)
+        x, kind, n = self._x_arg(batchX)
         y, ny = _f32c(batchY, (16,))
         if n != ny:
             raise ValueError("X/Y batch mismatch %d/%d" % (n, ny))
@@ -324,9 +341,9 @@ class ClairvoyanteBase(object):
             self._dropout_calls += 1
             seed = (self._seed + self._dropout_calls * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
         l5 = (ctypes.c_float * 8)()
-        _lib.check(self._lib.cvb_train_step_host(self._h, x.ctypes.data, y.ctypes.data, n,
-                                                 self.learningRateVal, self.l2RegularizationLambdaVal,
-                                                 self.dropoutRateFC4Val, seed, apply_update, l5))
+        _lib.check(self._lib.cvb_train_step_host_x(self._h, x.ctypes.data, kind, y.ctypes.data, n,
+                                                   self.learningRateVal, self.l2RegularizationLambdaVal,
+                                                   self.dropoutRateFC4Val, seed, apply_update, l5))
         summary = dict(learning_rate=float(self.learningRateVal), l2Lambda=float(self.l2RegularizationLambdaVal),
                        loss=float(l5[0]), loss1=float(l5[1]), loss2=float(l5[2]), loss3=float(l5[3]),
                        loss4=float(l5[4]), lossL2=float(l5[5]))

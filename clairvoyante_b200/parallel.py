@@ -76,13 +76,23 @@ class DataParallelTrainer(object):
             _lib.check(lib.cvb_grad_buffer(model._h, ctypes.byref(ptr), ctypes.byref(numel)))
             self.grad = torch.as_tensor(_CudaBuffer(ptr.value, numel.value), device="cuda:%d" % model.device)
 
+    @staticmethod
+    def _shard(X, lo, hi):
+        """rows [lo, hi) of a batch; a CountBatch keeps its raw counts (slices of it alone would drop them)"""
+        c = getattr(X, "counts", None)
+        xs = X[lo:hi]
+        if c is not None and hasattr(xs, "counts"):
+            xs.counts = c[lo:hi]
+        return xs
+
     def train(self, X, Y, seed):
         lo, hi = shard_range(len(X), self.rank, self.world)
+        X = self._shard(X, 0, len(X))      # (view; keeps the caller's object untouched)
         # the dropout stream is indexed by (seed, element); give every rank a distinct, reproducible stream
         seed = (seed + 0x51ED270B * self.rank) & 0xFFFFFFFFFFFFFFFF
         if self.in_library or self.world == 1:
-            return self.m._train_step(X[lo:hi], Y[lo:hi], apply_update=1, seed=seed)
-        self.m._train_step(X[lo:hi], Y[lo:hi], apply_update=0, seed=seed)
+            return self.m._train_step(self._shard(X, lo, hi), Y[lo:hi], apply_update=1, seed=seed)
+        self.m._train_step(self._shard(X, lo, hi), Y[lo:hi], apply_update=0, seed=seed)
         self.dist.all_reduce(self.grad, op=self.dist.ReduceOp.SUM)
         if self.grad.is_cuda:
             # NCCL enqueues the reduction on torch's stream and returns; the optimizer kernels run on the library's

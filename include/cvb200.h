@@ -125,6 +125,12 @@ int cvb_train_step_host(cvb_model* m, const float* x, const float* y, int64_t n,
  * same counter-based stream as FC4's (train_simt.cuh hash_uniform; host twin dropout_rng.py) under
  * dropout_seed ^ 0x5D5D5D5D5D5D5D5D, element index = site * N5 + unit. */
 int cvb_set_dropout_fc5(cvb_model* m, float rate);
+/* the same two calls for a batch held as fp16 values or as RAW int16 / uint8 counts (CVB_X_*; see cvb_predict_host_counts_*):
+ * a half / a quarter of the bytes cross the host->device link and every micro-chunk is widened -- raw counts get
+ * x[...,1:4] -= x[...,0:1], utils_v2.py:46 -- on the device; losses and gradients are bit-identical to the float32 call */
+int cvb_loss_host_x(cvb_model* m, const void* x, int x_kind, const float* y, int64_t n, float* loss);
+int cvb_train_step_host_x(cvb_model* m, const void* x, int x_kind, const float* y, int64_t n, float lr, float l2, float drop4,
+                          uint64_t dropout_seed, int apply_update, float* loss6);
 /* arithmetic of the large contractions of cvb_train_step_host / cvb_loss_host (train.py's model.train / getLoss path,
  * clairvoyante_v3.py:174,183-227).  FP32: fp32 SIMT kernels throughout.  BF16X3 (default): FC4 forward, data gradient and
  * weight gradient on tcgen05 with split-bf16 operands (x = hi + lo, three products, fp32 accumulate: ~2^-16 relative per

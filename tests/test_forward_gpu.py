@@ -270,3 +270,41 @@ def test_error_paths():
     with pytest.raises(ValueError):
         m.setWeights({k: (v if k != "fc4/bias" else v[:5]) for k, v in W.items()})
     m.close()
+
+
+@pytest.mark.parametrize("variant", ["v3", "v3_slim"])
+def test_c_abi_pinned_buffers_and_device_feeds(variant):
+    """the routes `Clairvoyante.predict` never takes: the C ABI called with PINNED input and output buffers (results are copied
+    device -> caller directly, single-chunk and pipelined paths), and cvb_predict_device_x on device buffers of raw uint8 /
+    int16 counts and fp16 values -- all bit-identical to the ordinary call"""
+    import ctypes
+    import torch
+    from clairvoyante_b200 import _lib, utils_v2 as U
+    W = I.init_weights(variant, 3)
+    m = _model(variant, W)
+    lib = _lib.load()
+    for n in (777, 40000):
+        x = synth.make_sites(n, 21)
+        cnt = U.pack_counts(x)
+        ref_o, ref_l = m.predictLogits(x)
+        xin = torch.from_numpy(cnt).pin_memory()
+        outs = [torch.empty((n, k), dtype=torch.float32).pin_memory() for k in (4, 2, 4, 6, 16)]
+        _lib.check(lib.cvb_predict_host_counts_u8(m._h, xin.data_ptr(), n, *[o.data_ptr() for o in outs]))
+        got = torch.cat(outs[:4], 1).numpy()
+        assert np.array_equal(got, ref_o) and np.array_equal(outs[4].numpy(), ref_l)
+        st = torch.cuda.current_stream().cuda_stream
+        for kind, arr in (("u8", cnt), ("i16", cnt.astype(np.int16)), ("f16", x.astype(np.float16)), ("f32", x)):
+            xd = torch.from_numpy(arr).cuda()
+            od = torch.empty((n, 16), dtype=torch.float32, device="cuda")
+            ld = torch.empty((n, 16), dtype=torch.float32, device="cuda")
+            torch.cuda.synchronize()
+            m.predictDeviceX(xd.data_ptr(), kind, n, od.data_ptr(), ld.data_ptr(), st)
+            torch.cuda.synchronize()
+            assert np.array_equal(od.cpu().numpy(), ref_o) and np.array_equal(ld.cpu().numpy(), ref_l), kind
+    # error behaviour of the new entry points
+    assert lib.cvb_predict_device_x(m._h, 16, 7, 1, 16, None, None) != 0          # unknown element kind
+    assert lib.cvb_allreduce_attach(m._h, None) == 0 and lib.cvb_allreduce_gradients(m._h) == 0   # no communicator: no-ops
+    if variant == "v3":
+        with pytest.raises(RuntimeError):
+            m.setComputeMode("fp16")                                                # plain fp16 is a v3_slim mode
+    m.close()

@@ -97,6 +97,41 @@ def test_fc5_dropout_gradients_match_autograd(variant, mode, n):
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
+def test_count_feed_trains_bit_identically(variant):
+    """cvb_train_step_host_x / cvb_loss_host_x: a batch that arrives as raw uint8 / int16 counts (a CountBatch, or the explicit
+    arrays) is widened per micro-chunk on the device; loss and -- with every split-K sum forced into one order by a single
+    micro-chunk and fp32 SIMT kernels -- gradients are the float32 call's, bit for bit; on the tensor path (atomics) they agree
+    to rounding.  Two micro-chunks, ragged sizes."""
+    from clairvoyante_b200 import utils_v2 as U
+    W = I.init_weights(variant, 11)
+    n = 5120 + 333
+    x, y = synth.make_labeled_sites(n, 12)
+    cnt = U.pack_counts(x)
+    assert cnt is not None and cnt.dtype == np.uint8
+    m = _model(W, variant, dropoutRateFC4=0.5)
+    ref_loss = float(m.getLoss(x, y))
+    for feed in (U.with_counts(x), cnt, cnt.astype(np.int16), x.astype(np.float16)):
+        assert float(m.getLoss(feed, y)) == ref_loss
+    m.setTrainMode("fp32")
+    l0, _ = m._train_step(x[:3000], y[:3000], apply_update=0, seed=5)
+    g0 = m.getGradients()
+    l1, _ = m._train_step(U.with_counts(x[:3000]), y[:3000], apply_update=0, seed=5)
+    g1 = m.getGradients()
+    assert float(l0) == float(l1)
+    for k in g0:
+        assert _relerr(g1[k], g0[k]) < 1e-5, k          # (fp32 atomics in the weight-gradient sums: order, not values, may differ)
+    m.setTrainMode("bf16x3")
+    l2, _ = m._train_step(x, y, apply_update=0, seed=6)
+    g2 = m.getGradients()
+    l3, _ = m._train_step(cnt, y, apply_update=0, seed=6)
+    g3 = m.getGradients()
+    assert abs(float(l2) - float(l3)) <= 1e-6 * abs(float(l2))
+    for k in g2:
+        assert _relerr(g3[k], g2[k]) < 1e-4, k
+    m.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_native_init_draws_the_reference_initialisers(variant):
     """cvb_init_weights (init(), clairvoyante_v3.py:177-178): truncated normal with stddev sqrt(2.6 / fan_in) cut at two sigma
     for conv / fc4 / fc5 kernels, glorot-uniform heads, zero biases, zero Adam slots and step; seeded and repeatable"""
