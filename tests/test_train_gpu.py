@@ -97,11 +97,11 @@ def test_fc5_dropout_gradients_match_autograd(variant, mode, n):
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
-def test_count_feed_trains_bit_identically(variant):
+def test_count_feed_trains_identically(variant):
     """cvb_train_step_host_x / cvb_loss_host_x: a batch that arrives as raw uint8 / int16 counts (a CountBatch, or the explicit
-    arrays) is widened per micro-chunk on the device; loss and -- with every split-K sum forced into one order by a single
-    micro-chunk and fp32 SIMT kernels -- gradients are the float32 call's, bit for bit; on the tensor path (atomics) they agree
-    to rounding.  Two micro-chunks, ragged sizes."""
+    arrays) is widened per micro-chunk on the device to exactly the float32 tensors of the ordinary call; losses and gradients
+    agree to the rounding of their fp32 atomic sums (whose order varies from run to run on either feed).  Two micro-chunks,
+    ragged sizes, both arithmetic paths."""
     from clairvoyante_b200 import utils_v2 as U
     W = I.init_weights(variant, 11)
     n = 5120 + 333
@@ -111,13 +111,13 @@ def test_count_feed_trains_bit_identically(variant):
     m = _model(W, variant, dropoutRateFC4=0.5)
     ref_loss = float(m.getLoss(x, y))
     for feed in (U.with_counts(x), cnt, cnt.astype(np.int16), x.astype(np.float16)):
-        assert float(m.getLoss(feed, y)) == ref_loss
+        assert abs(float(m.getLoss(feed, y)) - ref_loss) <= 1e-6 * abs(ref_loss)   # (per-site terms meet in fp32 atomics)
     m.setTrainMode("fp32")
     l0, _ = m._train_step(x[:3000], y[:3000], apply_update=0, seed=5)
     g0 = m.getGradients()
     l1, _ = m._train_step(U.with_counts(x[:3000]), y[:3000], apply_update=0, seed=5)
     g1 = m.getGradients()
-    assert float(l0) == float(l1)
+    assert abs(float(l0) - float(l1)) <= 1e-6 * abs(float(l0))
     for k in g0:
         assert _relerr(g1[k], g0[k]) < 1e-5, k          # (fp32 atomics in the weight-gradient sums: order, not values, may differ)
     m.setTrainMode("bf16x3")

@@ -9,7 +9,8 @@ out = {}
 for n in (1250, 2500, 5000, 10000):
     x, y = synth.make_labeled_sites(n, 3)
     xp = torch.from_numpy(x).pin_memory().numpy(); yp = torch.from_numpy(y).pin_memory().numpy()
-    for name, (a, b) in (("pageable", (x, y)), ("pinned", (xp, yp))):
+    from clairvoyante_b200 import utils_v2
+    for name, (a, b) in (("pageable", (x, y)), ("pinned", (xp, yp)), ("counts_pageable", (utils_v2.with_counts(x), y))):
         for _ in range(4):
             m.train(a, b)
         t0 = time.perf_counter()
