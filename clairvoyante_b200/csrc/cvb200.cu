@@ -82,6 +82,8 @@ struct cvb_model {
   float* d_xw = nullptr;      // fp32 scratch of one chunk for the front kernels that cannot read a narrow feed themselves
   float *h_x[NSLOT] = {}, *h_out[NSLOT] = {}, *h_lg[NSLOT] = {};
   cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  cudaStream_t s_aux = nullptr;  // second branch of the backward pass: weight gradients run beside the data-gradient chain
+  cudaEvent_t e_fork = nullptr, e_join = nullptr;
   cudaEvent_t e_h2d[NSLOT], e_comp[NSLOT], e_d2h[NSLOT];
   bool events = false;
   int64_t launches = 0;
@@ -264,6 +266,9 @@ extern "C" int cvb_create(int variant, int device, cvb_model** out) {
   CK(cudaStreamCreateWithFlags(&m->s_comp, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&m->s_h2d, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&m->s_aux, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&m->e_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&m->e_join, cudaEventDisableTiming));
   for (int i = 0; i < cvb_model::NSLOT; ++i) {
     CK(cudaEventCreateWithFlags(&m->e_h2d[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&m->e_comp[i], cudaEventDisableTiming));
@@ -295,6 +300,9 @@ extern "C" int cvb_destroy(cvb_model* m) {
   if (m->s_comp) cudaStreamDestroy(m->s_comp);
   if (m->s_h2d) cudaStreamDestroy(m->s_h2d);
   if (m->s_d2h) cudaStreamDestroy(m->s_d2h);
+  if (m->s_aux) cudaStreamDestroy(m->s_aux);
+  if (m->e_fork) cudaEventDestroy(m->e_fork);
+  if (m->e_join) cudaEventDestroy(m->e_join);
   delete m;
   return 0;
 }
@@ -1705,8 +1713,28 @@ static int train_forward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t se
 
 static float* gvar(cvb_model* m, const char* name) { return m->d_grad + m->info(name)->offset; }
 
+// The weight gradients (split-K GEMMs + atomics, ~190 us of a 680 us step at 1,250 tensors) do not feed anything later in
+// the backward pass: they run on a second stream, forked from `st` wherever their operands are complete and joined at the
+// end of the micro-chunk, so that in the captured graph they are a parallel branch beside the data-gradient chain
+// (pool-backward -> dgrad conv -> ...).  CVB_TRAIN_AUX=0 keeps everything on one stream.
+static cudaStream_t bwd_fork(cvb_model* m, cudaStream_t st, bool tensor_path, bool* forked) {
+  static const bool aux_on = !(getenv("CVB_TRAIN_AUX") && getenv("CVB_TRAIN_AUX")[0] == '0');
+  if (!aux_on || !tensor_path) return st;
+  cudaEventRecord(m->e_fork, st);
+  cudaStreamWaitEvent(m->s_aux, m->e_fork, 0);
+  *forked = true;
+  return m->s_aux;
+}
+static int bwd_join(cvb_model* m, cudaStream_t st, bool forked) {
+  if (!forked) return 0;  // the branch rejoins before the chunk ends (and before the next chunk reuses its operands)
+  CK(cudaEventRecord(m->e_join, m->s_aux));
+  CK(cudaStreamWaitEvent(st, m->e_join, 0));
+  return 0;
+}
+
 static int train_backward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t seed, int64_t index0, cudaStream_t st) {
   TrainWork* w = m->train;
+  bool forked = false;
   const int sms = m->num_sms;
   const float* d4 = drop4 > 0.f ? w->d4 : w->h4;
   // heads
@@ -1741,14 +1769,15 @@ static int train_backward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t s
     GemmExtra k4;
     k4.kslices = 4;
     if (launch_gemm_tc<64, true, tc::GEMM_EPI_ATOMIC, true>(m, w->p3s, w->cap * 4224, 4224, w->g4s, w->cap * 40, 40, 4224, 36, (int)nc,
-                                                            gvar(m, "fc4/kernel"), 36, nullptr, st, k4))
+                                                            gvar(m, "fc4/kernel"), 36, nullptr, bwd_fork(m, st, true, &forked), k4))
       return 1;
     if (launch_gemm_tc<192, false, tc::GEMM_EPI_STORE>(m, w->g4s, w->cap * 40, 40, w->w4s, 4224 * 40, 40, (int)nc, 4224, 36, w->gp3, 4224,
                                                        nullptr, st))
       return 1;
     k_pool_bwd_selu<1, 128, 256, 32><<<gsz(nc * 33 * 32), 256, 0, st>>>(w->gp3, w->c3, nc, 33, w->g3p, 37, 2, gvar(m, "conv3/bias"),
                                                                         bf(w->g3h), bf(w->g3h) + w->cap * 37 * 128);
-    if (launch_conv_wgrad_tc<16, 32, 5, 32, -2>(m, w->p2b, w->cap * 37 * 64, w->g3h, w->cap * 37 * 128, nc * 37, gvar(m, "conv3/kernel"), st))
+    if (launch_conv_wgrad_tc<16, 32, 5, 32, -2>(m, w->p2b, w->cap * 37 * 64, w->g3h, w->cap * 37 * 128, nc * 37, gvar(m, "conv3/kernel"),
+                                                bwd_fork(m, st, true, &forked)))
       return 1;
     if (launch_train_conv<trc::SlimConv3D, trc::SlimConv3DS>(m, w->g3h, w->cap * 37 * 128, w->wd3, nc, nullptr, w->fsc + 2, w->gp2, st))
       return 1;
@@ -1780,6 +1809,7 @@ static int train_backward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t s
   k_pool_bwd_selu<1, 32, 256><<<gsz(nc * 33 * 8), 256, 0, st>>>(w->gp1, w->c1, nc, 33, w->g1, 33, 0, gvar(m, "conv1/bias"));
   k_conv1_wgrad<8, 4><<<(int)std::min<int64_t>((nc + 3) / 4, 4 * sms), 128, 0, st>>>(w->x, w->g1, nc, gvar(m, "conv1/kernel"));
   CK(cudaGetLastError());
+  if (bwd_join(m, st, forked)) return 1;
   m->launches += 24;
   return 0;
 }
@@ -1835,9 +1865,22 @@ static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, i
   }
   if (m->train_mode != CVB_TRAIN_FP32) {
     // FC4 on tcgen05: p3 -> split bf16 (K-major), B = W4^T prepared once per step (train_prepare_weights)
-    if (launch_gemm_tc<176, true, tc::GEMM_EPI_BIAS_SELU>(m, w->p3s, w->cap * 4608, 4608, w->w4ts, 336 * 4608, 4608, (int)nc, 336,
-                                                          4608, w->h4, 336, m->var("fc4/bias"), st))
+    if (nc <= 2560) {
+      // few site tiles (a data-parallel shard of the reference's 10,000-tensor batch on 8 GPUs is 1,250 tensors = 20 CTAs,
+      // each streaming all of W4: 64 us): K split six ways into fp32 atomics, bias + SELU in a second pass
+      CK(cudaMemsetAsync(w->h4, 0, (size_t)nc * 336 * 4, st));
+      GemmExtra k6;
+      k6.kslices = 6;
+      if (launch_gemm_tc<176, true, tc::GEMM_EPI_ATOMIC>(m, w->p3s, w->cap * 4608, 4608, w->w4ts, 336 * 4608, 4608, (int)nc, 336, 4608,
+                                                         w->h4, 336, nullptr, st, k6))
+        return 1;
+      k_bias_selu<<<gsz(nc * 84), 256, 0, st>>>(w->h4, m->var("fc4/bias"), nc * 84, 84);
+      CK(cudaGetLastError());
+      m->launches += 2;
+    } else if (launch_gemm_tc<176, true, tc::GEMM_EPI_BIAS_SELU>(m, w->p3s, w->cap * 4608, 4608, w->w4ts, 336 * 4608, 4608, (int)nc,
+                                                                 336, 4608, w->h4, 336, m->var("fc4/bias"), st)) {
       return 1;
+    }
     m->launches += 1;
   } else {
     using F = FcCfg<336, 21, 16, 12, 8>;
@@ -1882,6 +1925,8 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
   const float* d4 = drop4 > 0.f ? w->d4 : w->h4;
   // heads: bias gradients; heads -> g4 (base branch), g5 (x selu')
   const bool tcm = m->train_mode != CVB_TRAIN_FP32;
+  bool forked = false;
+  auto fork = [&]() { return bwd_fork(m, st, tcm, &forked); };
   HeadG hg{gvar(m, "YBaseChangeSigmoid/kernel"), gvar(m, "YZygosityFC/kernel"), gvar(m, "YVarTypeFC/kernel"),
            gvar(m, "YIndelLengthFC/kernel")};
   k_colsum<<<dim3(1, 64), 256, 0, st>>>(w->dlog + 0, nc, 16, 4, gvar(m, "YBaseChangeSigmoid/bias"));
@@ -1898,23 +1943,24 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
     //   tmp5 [336][184] = d4^T . [g5 | dlog]   (cols 0..167 -> fc5/kernel, 168..171 -> base head: its input is dropout4)
     //   tmph [168][16]  = h5^T . dlog          (cols 4..15 -> zygosity / varType / indelLength heads)
     const int64_t ldt = w->ldt;
-    if (split_transpose_bf16(d4, nc, 336, 336, w->d4t, 336 * ldt, ldt, st)) return 1;
-    if (split_transpose_bf16(h5in, nc, 168, 168, w->h5t, 168 * ldt, ldt, st)) return 1;
-    if (split_transpose_bf16(w->g5, nc, 168, 176, w->gct, 184 * ldt, ldt, st)) return 1;
-    if (split_transpose_bf16(w->dlog, nc, 16, 16, w->gct + 168 * ldt, 184 * ldt, ldt, st)) return 1;
+    cudaStream_t sw = fork();
+    if (split_transpose_bf16(d4, nc, 336, 336, w->d4t, 336 * ldt, ldt, sw)) return 1;
+    if (split_transpose_bf16(h5in, nc, 168, 168, w->h5t, 168 * ldt, ldt, sw)) return 1;
+    if (split_transpose_bf16(w->g5, nc, 168, 176, w->gct, 184 * ldt, ldt, sw)) return 1;
+    if (split_transpose_bf16(w->dlog, nc, 16, 16, w->gct + 168 * ldt, 184 * ldt, ldt, sw)) return 1;
     // 3 and 2 output tiles only: K (= sites) is split over the SMs and the slices meet in fp32 atomics
-    CK(cudaMemsetAsync(w->tmp5, 0, 336 * 184 * 4, st));
-    CK(cudaMemsetAsync(w->tmph, 0, 168 * 16 * 4, st));
+    CK(cudaMemsetAsync(w->tmp5, 0, 336 * 184 * 4, sw));
+    CK(cudaMemsetAsync(w->tmph, 0, 168 * 16 * 4, sw));
     GemmExtra sk;
     sk.kslices = std::max(1, m->num_sms / 3);
     if (launch_gemm_tc<192, true, tc::GEMM_EPI_ATOMIC>(m, w->d4t, 336 * ldt, ldt, w->gct, 184 * ldt, ldt, 336, 184, (int)nc, w->tmp5,
-                                                       184, nullptr, st, sk))
+                                                       184, nullptr, sw, sk))
       return 1;
     sk.kslices = std::max(1, m->num_sms / 4);
     if (launch_gemm_tc<16, true, tc::GEMM_EPI_ATOMIC>(m, w->h5t, 168 * ldt, ldt, w->gct + 168 * ldt, 184 * ldt, ldt, 168, 16,
-                                                      (int)nc, w->tmph, 16, nullptr, st, sk))
+                                                      (int)nc, w->tmph, 16, nullptr, sw, sk))
       return 1;
-    k_scatter_fc5_heads<<<(336 * 168 + 255) / 256, 256, 0, st>>>(w->tmp5, w->tmph, gvar(m, "fc5/kernel"), hg);
+    k_scatter_fc5_heads<<<(336 * 168 + 255) / 256, 256, 0, sw>>>(w->tmp5, w->tmph, gvar(m, "fc5/kernel"), hg);
     CK(cudaGetLastError());
   } else {
     CK(cudaMemsetAsync(w->tmpb, 0, 336 * 16 * 4, st));
@@ -1949,7 +1995,7 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
     GemmExtra k2;
     k2.kslices = 2;  // 72 output tiles x 2 K slices = 144 CTAs; the gradient buffer was zeroed at the start of the step
     if (launch_gemm_tc<192, true, tc::GEMM_EPI_ATOMIC, true>(m, w->p3s, w->cap * 4608, 4608, w->g4s, w->cap * 336, 336, 4608, 336,
-                                                             (int)nc, gvar(m, "fc4/kernel"), 336, nullptr, st, k2))
+                                                             (int)nc, gvar(m, "fc4/kernel"), 336, nullptr, fork(), k2))
       return 1;
     // data gradient  gp3 [sites][4608] = dpre4 . W4^T      (B = W4 as stored: [4608][336] is K-major for K = 336)
     if (launch_gemm_tc<192, false, tc::GEMM_EPI_STORE>(m, w->g4s, w->cap * 336, 336, w->w4s, 4608 * 336, 336, (int)nc, 4608, 336,
@@ -1971,7 +2017,8 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
                                                                             tcm ? bf(w->g3h) + w->cap * 28 * 256 : nullptr);
   {
     if (tcm) {
-      if (launch_conv_wgrad_tc<32, 48, 3, 64>(m, w->p2b, w->cap * 28 * 128, w->g3h, w->cap * 28 * 256, nc * 28, gvar(m, "conv3/kernel"), st))
+      if (launch_conv_wgrad_tc<32, 48, 3, 64>(m, w->p2b, w->cap * 28 * 128, w->g3h, w->cap * 28 * 256, nc * 28, gvar(m, "conv3/kernel"),
+                                              fork()))
         return 1;
     } else {
       using W = WgradCfg<32, 48, 3, 26, 4, 12, 4>;
@@ -1997,7 +2044,8 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
                                                                        tcm ? bf(w->g2h) + w->cap * 30 * 128 : nullptr);
   {
     if (tcm) {
-      if (launch_conv_wgrad_tc<16, 32, 2, 32>(m, w->p1b, w->cap * 30 * 64, w->g2h, w->cap * 30 * 128, nc * 30, gvar(m, "conv2/kernel"), st))
+      if (launch_conv_wgrad_tc<16, 32, 2, 32>(m, w->p1b, w->cap * 30 * 64, w->g2h, w->cap * 30 * 128, nc * 30, gvar(m, "conv2/kernel"),
+                                              fork()))
         return 1;
     } else {
       using W = WgradCfg<16, 32, 2, 29, 4, 4, 4>;
@@ -2021,6 +2069,7 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
   k_pool_bwd_selu<5, 64, 256><<<gsz(nc * 33 * 16), 256, 0, st>>>(w->gp1, w->c1, nc, 33, w->g1, 33, 0, gvar(m, "conv1/bias"));
   k_conv1_wgrad<16, 4><<<(int)std::min<int64_t>((nc + 3) / 4, 4 * sms), 256, 0, st>>>(w->x, w->g1, nc, gvar(m, "conv1/kernel"));
   CK(cudaGetLastError());
+  if (bwd_join(m, st, forked)) return 1;
   m->launches += 24;
   return 0;
 }

@@ -586,6 +586,16 @@ __global__ void k_scatter_conv_wgrad(const float* __restrict__ tmpw, float* __re
   dW[i] += a;
 }
 
+// ---- h[i] = SELU(h[i] + bias[i % N]) in place: second half of a split-K FC4 forward (small micro-chunks)
+__global__ void k_bias_selu(float* __restrict__ h, const float* __restrict__ bias, int64_t total4, int N4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(h)[i];
+    const float4 b = reinterpret_cast<const float4*>(bias)[i % N4];
+    v.x = selu_f(v.x + b.x); v.y = selu_f(v.y + b.y); v.z = selu_f(v.z + b.z); v.w = selu_f(v.w + b.w);
+    reinterpret_cast<float4*>(h)[i] = v;
+  }
+}
+
 // ---- the whole optimiser step in ONE launch over the flat parameter buffer (every variable starts on a 16-byte boundary
 // and is padded to a multiple of 4 floats with zeros, which Adam leaves at zero): TF-1.x Adam as above with l2 applied to
 // the kernels only (clairvoyante_v3.py:150: every variable whose name has no "bias"), and -- from the PRE-update weights,

@@ -72,10 +72,17 @@ def main(rep, launches):
 
 
 # kernel name fragments -> (variant, bench kernel kind) for profiles/traffic.json
-KINDS = [("k_v3_c1_reg", ("v3", "front")), ("ConvTcCfg<(int)30, (int)2", ("v3", "conv2")), ("ConvTcCfg<(int)28, (int)3", ("v3", "conv3")),
+KINDS = [("k_v3_c1_reg", ("v3", "front")), ("k_conv_slab<ConvTcCfg<30, 2,", ("v3", "conv2")), ("k_conv_slab<ConvTcCfg<28, 3,", ("v3", "conv3")),
          ("k_fc4_tc", ("v3", "fc4")), ("k_tail_tc", ("v3", "tail")), ("k_slim_c1_reg", ("v3_slim", "front")),
-         ("ConvTcCfg<(int)35, (int)3", ("v3_slim", "conv2")), ("ConvTcCfg<(int)37, (int)5", ("v3_slim", "conv3")),
-         ("k_gemm_tc<(int)48", ("v3_slim", "fc4")), ("k_tail<", ("v3_slim", "tail"))]
+         ("k_conv_slab<ConvTcCfg<35, 3,", ("v3_slim", "conv2")), ("k_conv_slab<ConvTcCfg<37, 5,", ("v3_slim", "conv3")),
+         ("k_gemm_tc<48,", ("v3_slim", "fc4")), ("k_tail<", ("v3_slim", "tail"))]
+
+
+def _norm(name):
+    """kernel name as ncu prints it, without namespaces and C-style casts: `k_conv_slab<ConvTcCfg<30, 2, ...`"""
+    for t in ("(int)", "(bool)", "cvb::tc::", "cvb::", "tc::"):
+        name = name.replace(t, "")
+    return name
 
 
 def traffic(rep, out_fn, source_hash):
@@ -90,7 +97,7 @@ def traffic(rep, out_fn, source_hash):
     res = {"source_hash": source_hash, "report": rep, "v3": {}, "v3_slim": {}, "_detail": {}}
     for row in r[2:]:
         for frag, (variant, kind) in KINDS:
-            if frag in row[ik]:
+            if frag in _norm(row[ik]):
                 b = float(row[ir]) * scale[units[ir]] + float(row[iw]) * scale[units[iw]]
                 if b > res[variant].get(kind, 0):
                     res[variant][kind] = b
