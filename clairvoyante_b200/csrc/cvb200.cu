@@ -858,6 +858,7 @@ struct GemmExtra {  // batched / split-K launches, see tc::GemmArgs
   int batches = 1, a_batch_rows = 0, a_kshift0 = 0, a_kshift_per_batch = 0;
   int64_t c_batch_stride = 0;
   int kslices = 1;
+  int64_t c_slice_stride = 0;  // > 0: K slice z stores to C + z * c_slice_stride (no atomics)
   int f16 = 0, terms = 0;  // fp16 operands; terms 0 = what the training mode says (3, or 1 for CVB_TRAIN_BF16)
   const float* inv_scale = nullptr;
   bool pdl = false;
@@ -1533,6 +1534,7 @@ static int launch_gemm_tc(cvb_model* m, const uint16_t* a, int64_t a_plane, int6
   g.terms = ex.terms ? ex.terms : (m->train_mode == CVB_TRAIN_BF16 ? 1 : 3);
   g.f16 = ex.f16;
   g.inv_scale = ex.inv_scale;
+  g.c_slice_stride = ex.c_slice_stride;
   g.C = C; g.ldc = ldc; g.bias = bias;
   g.m_tiles = (M + G::BM - 1) / G::BM;
   g.a_batch_rows = ex.a_batch_rows; g.c_batch_stride = ex.c_batch_stride;
@@ -1867,14 +1869,15 @@ static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, i
     // FC4 on tcgen05: p3 -> split bf16 (K-major), B = W4^T prepared once per step (train_prepare_weights)
     if (nc <= 2560) {
       // few site tiles (a data-parallel shard of the reference's 10,000-tensor batch on 8 GPUs is 1,250 tensors = 20 CTAs,
-      // each streaming all of W4: 64 us): K split six ways into fp32 atomics, bias + SELU in a second pass
-      CK(cudaMemsetAsync(w->h4, 0, (size_t)nc * 336 * 4, st));
+      // each streaming all of W4: 64 us): K split six ways, every slice stores its partial sums (into gp3, a backward-pass
+      // buffer that is free here), and a second pass adds them in slice order + bias + SELU -- deterministic
       GemmExtra k6;
       k6.kslices = 6;
-      if (launch_gemm_tc<176, true, tc::GEMM_EPI_ATOMIC>(m, w->p3s, w->cap * 4608, 4608, w->w4ts, 336 * 4608, 4608, (int)nc, 336, 4608,
-                                                         w->h4, 336, nullptr, st, k6))
+      k6.c_slice_stride = nc * 336;
+      if (launch_gemm_tc<176, true, tc::GEMM_EPI_STORE>(m, w->p3s, w->cap * 4608, 4608, w->w4ts, 336 * 4608, 4608, (int)nc, 336, 4608,
+                                                        w->gp3, 336, nullptr, st, k6))
         return 1;
-      k_bias_selu<<<gsz(nc * 84), 256, 0, st>>>(w->h4, m->var("fc4/bias"), nc * 84, 84);
+      k_bias_selu<<<gsz(nc * 84), 256, 0, st>>>(w->gp3, nc * 336, 6, w->h4, m->var("fc4/bias"), nc * 84, 84);
       CK(cudaGetLastError());
       m->launches += 2;
     } else if (launch_gemm_tc<176, true, tc::GEMM_EPI_BIAS_SELU>(m, w->p3s, w->cap * 4608, 4608, w->w4ts, 336 * 4608, 4608, (int)nc,

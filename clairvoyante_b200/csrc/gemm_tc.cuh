@@ -43,6 +43,7 @@ struct GemmArgs {
   int64_t c_batch_stride;
   int kb_per_slice;
   int a_kshift0, a_kshift_per_batch;  // MN only
+  int64_t c_slice_stride;  // K slice z writes C + z * c_slice_stride (0: all slices share C, use GEMM_EPI_ATOMIC)
   int f16;                 // operands are (split) fp16 instead of bf16: the inference FC4 of v3_slim
   const float* inv_scale;  // GEMM_EPI_BIAS_SELU: accumulator * inv_scale[0] + bias (power-of-two pre-scaled fp16 weights); may be NULL
 };
@@ -137,7 +138,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
   const int batch = blockIdx.y / g.m_tiles;
   const int m0 = (blockIdx.y - batch * g.m_tiles) * G::BM, n0 = blockIdx.x * BN;
   const int am0 = m0 + batch * g.a_batch_rows;  // row of this tile in the A tensor
-  float* const C = g.C + batch * g.c_batch_stride;
+  float* const C = g.C + batch * g.c_batch_stride + (int64_t)blockIdx.z * g.c_slice_stride;
   const int64_t ldc = g.ldc;
   const float* const bias = g.bias;
   const int kb_begin = blockIdx.z * g.kb_per_slice;

@@ -586,10 +586,16 @@ __global__ void k_scatter_conv_wgrad(const float* __restrict__ tmpw, float* __re
   dW[i] += a;
 }
 
-// ---- h[i] = SELU(h[i] + bias[i % N]) in place: second half of a split-K FC4 forward (small micro-chunks)
-__global__ void k_bias_selu(float* __restrict__ h, const float* __restrict__ bias, int64_t total4, int N4) {
+// ---- h[i] = SELU(sum_z part[z][i] + bias[i % N]): second half of a split-K FC4 forward (small micro-chunks); the K
+//      slices are added in slice order, so the result does not depend on scheduling
+__global__ void k_bias_selu(const float* __restrict__ part, int64_t slice_stride, int nslices, float* __restrict__ h,
+                            const float* __restrict__ bias, int64_t total4, int N4) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 v = reinterpret_cast<float4*>(h)[i];
+    float4 v = reinterpret_cast<const float4*>(part)[i];
+    for (int z = 1; z < nslices; ++z) {
+      const float4 t = reinterpret_cast<const float4*>(part + z * slice_stride)[i];
+      v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
     const float4 b = reinterpret_cast<const float4*>(bias)[i % N4];
     v.x = selu_f(v.x + b.x); v.y = selu_f(v.y + b.y); v.z = selu_f(v.z + b.z); v.w = selu_f(v.w + b.w);
     reinterpret_cast<float4*>(h)[i] = v;
