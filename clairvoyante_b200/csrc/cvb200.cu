@@ -1105,7 +1105,7 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
         return 1;
       if (prof_mark(m, st)) return 1;
     }
-    k_tail<36, 18, 16><<<(int)((n + 15) / 16), 256, 0, st>>>(m->d_h4, n, head_ptrs(m), out16, logits16);
+    k_tail_site<36, 18><<<(int)((n + 127) / 128), 128, 0, st>>>(m->d_h4, n, head_ptrs(m), out16, logits16);
     CK(cudaGetLastError());
     if (prof_mark(m, st)) return 1;
     m->launches += 5;
@@ -1144,8 +1144,7 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
       if (prof_mark(m, st)) return 1;
     }
     {
-      int grid = (int)((n + 15) / 16);
-      k_tail<36, 18, 16><<<grid, 256, 0, st>>>(m->d_h4, n, head_ptrs(m), out16, logits16);
+      k_tail_site<36, 18><<<(int)((n + 127) / 128), 128, 0, st>>>(m->d_h4, n, head_ptrs(m), out16, logits16);
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
     }

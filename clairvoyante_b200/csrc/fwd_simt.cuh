@@ -897,4 +897,90 @@ k_tail(const float* __restrict__ h4, int64_t n, HeadPtrs hp, OutDst out16, float
   }
 }
 
+// ------------------------------------------------------------------------------------
+// k_tail_site: the same layers for a SMALL FC4 width (v3_slim: 36 -> 18 -> heads), one site per thread.  k_tail gives FC5
+// one thread per output column -- 18 of a block's 256 threads for slim -- and cost 0.034 ms per 33,152-site chunk for ~1,000
+// MACs per site; here every thread keeps its site's 36 inputs in registers and reads the weights from shared memory as
+// warp-wide broadcasts.  Every accumulator adds its terms in the same (ascending k) order as k_tail: results are bit-identical.
+// ------------------------------------------------------------------------------------
+template <int N4, int N5>
+__global__ void __launch_bounds__(128)
+k_tail_site(const float* __restrict__ h4, int64_t n, HeadPtrs hp, OutDst out16, float* __restrict__ logits16) {
+  static_assert(N4 % 4 == 0 && N4 <= 64 && N5 <= 32, "small tails only");
+  constexpr int L5 = (N5 + 3) / 4 * 4;  // fc5/kernel rows padded to whole float4
+  __shared__ __align__(16) float w5s[N4 * L5];
+  __shared__ __align__(16) float wbs[N4 * 4];
+  __shared__ __align__(16) float whs[N5 * 12];  // per h5 unit: zygosity 2 | varType 4 | indelLength 6
+  __shared__ float b5s[L5], bhs[16];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < N4 * L5; i += 128) {
+    const int k = i / L5, j = i - k * L5;
+    w5s[i] = j < N5 ? hp.w5[k * N5 + j] : 0.f;
+  }
+  for (int i = tid; i < N4 * 4; i += 128) wbs[i] = hp.wb[i];
+  for (int i = tid; i < N5 * 12; i += 128) {
+    const int k = i / 12, o = i - k * 12;
+    whs[i] = o < 2 ? hp.wz[k * 2 + o] : (o < 6 ? hp.wt[k * 4 + (o - 2)] : hp.wl[k * 6 + (o - 6)]);
+  }
+  if (tid < L5) b5s[tid] = tid < N5 ? hp.b5[tid] : 0.f;
+  if (tid < 16) bhs[tid] = tid < 4 ? hp.bb[tid] : (tid < 6 ? hp.bz[tid - 4] : (tid < 10 ? hp.bt[tid - 6] : hp.bl[tid - 10]));
+  __syncthreads();
+  const int64_t site = (int64_t)blockIdx.x * 128 + tid;
+  if (site >= n) return;
+  float h[N4];
+#pragma unroll
+  for (int q = 0; q < N4 / 4; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(h4 + site * N4 + q * 4);
+    h[4 * q] = v.x; h[4 * q + 1] = v.y; h[4 * q + 2] = v.z; h[4 * q + 3] = v.w;
+  }
+  float a5[L5], lg[16];
+#pragma unroll
+  for (int j = 0; j < L5; ++j) a5[j] = 0.f;
+#pragma unroll
+  for (int o = 0; o < 16; ++o) lg[o] = 0.f;
+#pragma unroll
+  for (int k = 0; k < N4; ++k) {
+#pragma unroll
+    for (int j4 = 0; j4 < L5 / 4; ++j4) {
+      const float4 w = *reinterpret_cast<const float4*>(w5s + k * L5 + 4 * j4);
+      a5[4 * j4] = fmaf(h[k], w.x, a5[4 * j4]);         a5[4 * j4 + 1] = fmaf(h[k], w.y, a5[4 * j4 + 1]);
+      a5[4 * j4 + 2] = fmaf(h[k], w.z, a5[4 * j4 + 2]); a5[4 * j4 + 3] = fmaf(h[k], w.w, a5[4 * j4 + 3]);
+    }
+    const float4 wb = *reinterpret_cast<const float4*>(wbs + k * 4);  // base change reads the FC4 branch (clairvoyante_v3.py:125)
+    lg[0] = fmaf(h[k], wb.x, lg[0]); lg[1] = fmaf(h[k], wb.y, lg[1]);
+    lg[2] = fmaf(h[k], wb.z, lg[2]); lg[3] = fmaf(h[k], wb.w, lg[3]);
+  }
+#pragma unroll
+  for (int o = 0; o < 4; ++o) lg[o] += bhs[o];
+#pragma unroll
+  for (int k = 0; k < N5; ++k) {
+    const float h5 = selu_f(a5[k] + b5s[k]);
+    const float4 wa = *reinterpret_cast<const float4*>(whs + k * 12), wc = *reinterpret_cast<const float4*>(whs + k * 12 + 4),
+                 wd = *reinterpret_cast<const float4*>(whs + k * 12 + 8);
+    lg[4] = fmaf(h5, wa.x, lg[4]);   lg[5] = fmaf(h5, wa.y, lg[5]);   lg[6] = fmaf(h5, wa.z, lg[6]);   lg[7] = fmaf(h5, wa.w, lg[7]);
+    lg[8] = fmaf(h5, wc.x, lg[8]);   lg[9] = fmaf(h5, wc.y, lg[9]);   lg[10] = fmaf(h5, wc.z, lg[10]); lg[11] = fmaf(h5, wc.w, lg[11]);
+    lg[12] = fmaf(h5, wd.x, lg[12]); lg[13] = fmaf(h5, wd.y, lg[13]); lg[14] = fmaf(h5, wd.z, lg[14]); lg[15] = fmaf(h5, wd.w, lg[15]);
+  }
+#pragma unroll
+  for (int o = 4; o < 16; ++o) lg[o] = selu_f(lg[o] + bhs[o]) + 1e-10f;  // clairvoyante_v3.py:127-128
+  float ov[16];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) ov[k] = 1.f / (1.f + __expf(-lg[k]));
+  auto sm = [&](int a, int b) {
+    float mx = lg[a];
+    for (int k = a + 1; k < b; ++k) mx = fmaxf(mx, lg[k]);
+    float sum = 0.f;
+    for (int k = a; k < b; ++k) { ov[k] = __expf(lg[k] - mx); sum += ov[k]; }
+    const float inv = 1.f / sum;
+    for (int k = a; k < b; ++k) ov[k] *= inv;
+  };
+  sm(4, 6); sm(6, 10); sm(10, 16);
+  store_out16(out16, site, ov);
+  if (logits16) {
+    float4* dl = reinterpret_cast<float4*>(logits16 + site * 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dl[k] = make_float4(lg[4 * k], lg[4 * k + 1], lg[4 * k + 2], lg[4 * k + 3]);
+  }
+}
+
 }  // namespace cvb

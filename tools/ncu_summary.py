@@ -75,7 +75,7 @@ def main(rep, launches):
 KINDS = [("k_v3_c1_reg", ("v3", "front")), ("k_conv_slab<ConvTcCfg<30, 2,", ("v3", "conv2")), ("k_conv_slab<ConvTcCfg<28, 3,", ("v3", "conv3")),
          ("k_fc4_tc", ("v3", "fc4")), ("k_tail_tc", ("v3", "tail")), ("k_slim_c1_reg", ("v3_slim", "front")),
          ("k_conv_slab<ConvTcCfg<35, 3,", ("v3_slim", "conv2")), ("k_conv_slab<ConvTcCfg<37, 5,", ("v3_slim", "conv3")),
-         ("k_gemm_tc<48,", ("v3_slim", "fc4")), ("k_tail<", ("v3_slim", "tail"))]
+         ("k_gemm_tc<48,", ("v3_slim", "fc4")), ("k_tail<", ("v3_slim", "tail")), ("k_tail_site<", ("v3_slim", "tail"))]
 
 
 def _norm(name):
