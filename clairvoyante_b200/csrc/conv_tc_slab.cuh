@@ -1,10 +1,10 @@
-// conv_tc_slab.cuh -- second-generation tcgen05 conv kernel: same math and epilogue contract as conv_tc.cuh
-// (row-shifted implicit GEMM, split-fp16 operands, bias + SELU + (POOL,1) max-pool, hi/lo or fp32 output), but the
-// activation operand is loaded ONCE per (tile, input column w') as a slab of 128 + KH - 1 rows and re-used for every kh
-// through row-shifted UMMA descriptors: tools/umma_shift_probe.cu shows that a K-major SWIZZLE_64B/32B descriptor whose
-// start address is advanced by whole rows reads rows (i + shift) with base_offset = 0 (the swizzle is a function of the
-// absolute shared-memory address).  conv_tc.cuh re-loads A for every kh: 196 KB of A per conv3 tile instead of 70 KB,
-// and the kernels are bound by operand ingest (profiles/r01_tensor_path.md).
+// conv_tc_slab.cuh -- the tcgen05 conv kernel (geometry and numerics: conv_tc.cuh): row-shifted implicit GEMM, split-fp16
+// operands, bias + SELU + (POOL,1) max-pool, hi/lo or fp32 output.  The activation operand is loaded ONCE per (tile, input
+// column w') as a slab of 128 + KH - 1 rows and re-used for every kh through row-shifted UMMA descriptors:
+// tools/umma_shift_probe.cu shows that a K-major SWIZZLE_64B/32B descriptor whose start address is advanced by whole rows
+// reads rows (i + shift) with base_offset = 0 (the swizzle is a function of the absolute shared-memory address).  (Round 1's
+// first kernel re-loaded A for every kh: 196 KB of A per conv3 tile instead of 70 KB; these kernels are bound by operand
+// ingest, profiles/r01_tensor_path.md.)
 //
 // Tile = 128 CONSECUTIVE flattened rows (TMEM lane = row); a tile owns TILE_STEP = 129 - POOL pooled rows.  The pooling
 // window of the last POOL-1 lanes of a TMEM quadrant reaches into the next quadrant, which another warp holds: every
@@ -65,13 +65,12 @@ struct ConvSlabCfg {
 };
 
 using Conv2Slab = ConvSlabCfg<Conv2Tc, 8, 16, 4, false, true>;  // two tiles of operands in flight
-using Conv3Slab = ConvSlabCfg<Conv3Tc, 3, 6, 4, false, false, 0>;  // (NCB = 6, 24 warps x 32 columns, measured no faster: 0.203 vs 0.199 ms)
-using SlimConv3Slab = ConvSlabCfg<SlimConv3Tc, 4, 8>;
-// resident-weight variants (CVB_CONV_RESIDENT=1): the shared memory the weight ring held goes to deeper activation rings
+// resident-weight variants: the shared memory the weight ring held goes to deeper activation rings (measured: conv3
+// 0.188 -> 0.173 ms per 18,944 sites, v3_slim conv3 0.317 -> 0.207 ms per 33,152, bit-identical; conv2: no gain, stays on the ring)
+// (conv3 with NCB = 6, 24 warps x 32 columns, measured no faster: 0.203 vs 0.199 ms)
 // conv3 keeps the first pooling code and the shared-memory bias (EPI 0, BC off): measured per 18,944-site launch 0.167 ms
 // against 0.175 with the constant-bank bias and 0.189 with the predicated-load pooling that helps conv2 (0.139 -> 0.127)
 using Conv3SlabRes = ConvSlabCfg<Conv3Tc, 6, 0, 4, true, false, 0>;
-using SlimConv3SlabRes = ConvSlabCfg<SlimConv3Tc, 8, 0, 4, true, true>;
 // v3_slim tensor pipeline: dense conv2 (NOUT = 64: 4 x 16 columns per epilogue warp), conv3 with fp16 planes out
 using SlimConv2SlabRes = ConvSlabCfg<SlimConv2Tc, 8, 0, 4, true, true>;
 using SlimConv3HSlabRes = ConvSlabCfg<SlimConv3TcH, 8, 0, 4, true, true>;

@@ -94,36 +94,23 @@ struct cvb_model {
   bool tc_ready = false, tc_weights_dirty = true;
   CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
   CUtensorMap map_bh_hi, map_bh_lo;  // FC4 weights with NH/2-row boxes (cluster multicast)
-  CUtensorMap map_ah_hi, map_ah_lo;  // FC4 activations with BM/2-row boxes (4-CTA clusters)
-  int tc_fc4_cluster = 1;
   // conv3 on tensor cores: B = rearranged conv3 weights [3*192][128], A = p2 hi/lo [sites*28][128]
   __half *d_w3b_hi = nullptr, *d_w3b_lo = nullptr;
-  CUtensorMap map_c3a_hi, map_c3a_lo, map_c3b_hi, map_c3b_lo;
-  bool tc_conv3 = true;
-  // conv2 on tensor cores: A = p1 hi/lo [sites*30][64] (written by k_v3_c1), B = rearranged conv2 weights [2*128][64]
+  // conv2 on tensor cores: A = p1 hi/lo [sites*30][64] (written by k_v3_c1_reg), B = rearranged conv2 weights [2*128][64]
   __half *d_p1 = nullptr, *d_w2b_hi = nullptr, *d_w2b_lo = nullptr;
-  CUtensorMap map_c2a_hi, map_c2a_lo, map_c2b_hi, map_c2b_lo;
-  bool tc_conv2 = true;
-  // rows per fp16 plane of p1 / p2 (sites*RPS + slack, a multiple of the consumer's quadrant step so that the
-  // merged 4-D TMA view's plane stride is a multiple of its quadrant stride); lo plane = hi plane + rows*KROW
+  // rows per fp16 plane of p1 / p2 (sites*RPS + slack); lo plane = hi plane + rows*KROW
   int64_t p1_rows = 0, p2_rows = 0;
   size_t p2_bytes = 0;
-  CUtensorMap map_c2a4, map_c2b2, map_c2b3, map_c2b4, map_c3a4, map_c3b2, map_c3b3, map_c3b4;
-  int tc_merged = 1;
-  int tc_cluster = 1;  // 2-CTA clusters with weight multicast in the conv tensor kernels (needs tc_merged)
-  int tc_slab = 1;     // slab-mode conv kernels (conv_tc_slab.cuh): A loaded once per (tile, w'), re-used across kh
+  CUtensorMap map_c2b2, map_c2b3, map_c2b4, map_c3b2, map_c3b3, map_c3b4;  // weight boxes of 2, 3, 4 output columns, hi + lo planes
   // v3_slim tensor path: every layer but conv1 and the tail on tcgen05
   __half *d_p1s = nullptr, *d_w2s = nullptr, *d_w4h = nullptr;  // p1 [rows][32] hi|lo; dense conv2 taps hi|lo; fc4/kernel^T [36][4224] hi|lo
   int64_t p1s_rows = 0;
   CUtensorMap map_s2slab, map_s2b;
   tc::BiasParam hb2 = {}, hb3 = {};  // host copies of conv2/bias, conv3/bias: passed by value to the inference conv kernels
-  int tc_resident = 1; // CVB_CONV_RESIDENT=0: conv3 / slim conv3 stream their taps through the ring instead (ConvSlabCfg RES)
   CUtensorMap map_c2slab, map_c3slab;
-  CUtensorMap map_c2h2, map_c2h3, map_c2h4, map_c3h2, map_c3h3, map_c3h4;
   // fused tail (FC5 + heads) on tensor cores: A = h4 hi/lo [sites][336], B = [W5 | Wb]^T [176][336]
   __half *d_h4s = nullptr, *d_wtail = nullptr;
   CUtensorMap map_ta_hi, map_ta_lo, map_tb_hi, map_tb_lo;
-  bool tc_tail = true;
   int64_t alloc_sites = 0;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;  // 6 per chunk: start, after SIMT front, conv2(tc), conv3, fc4, tail
@@ -445,25 +432,16 @@ static int make_map_nd(CUtensorMap* map, void* base, int rank, const uint64_t* d
   return 0;
 }
 
-// merged views for k_conv_tc (conv_tc.cuh): activation planes at `act`, `rows` rows per plane; weights planes at `wts`
+// weight views for k_conv_slab: 3-D (k, row, plane) over the prepared taps at `wts` (hi plane then lo plane), one box
+// {BK, nb*COUT, 2} per number nb of output columns an input column feeds
 template <class C>
-static int make_conv_merged_maps(void* act, int64_t rows, void* wts, CUtensorMapSwizzle sw, CUtensorMap* a4, CUtensorMap* b2,
-                                 CUtensorMap* b3, CUtensorMap* b4, CUtensorMap* h2, CUtensorMap* h3, CUtensorMap* h4) {
-  const uint64_t rext = C::QROWS + C::KH - 1;
-  const uint64_t Q = (uint64_t)(rows - rext) / C::QSTEP + 1;
-  const uint64_t ad[4] = {(uint64_t)C::KROW, rext, Q, 2};
-  const uint64_t as[3] = {(uint64_t)C::KROW * 2, (uint64_t)C::QSTEP * C::KROW * 2, (uint64_t)rows * C::KROW * 2};
-  const uint32_t ab[4] = {(uint32_t)C::BK, 32, 4, 2};
-  if (make_map_nd(a4, act, 4, ad, as, ab, sw)) return 1;
+static int make_conv_weight_maps(void* wts, CUtensorMapSwizzle sw, CUtensorMap* b2, CUtensorMap* b3, CUtensorMap* b4) {
   const uint64_t bd[3] = {(uint64_t)C::KROW, (uint64_t)C::B_ROWS_TOTAL, 2};
   const uint64_t bs[2] = {(uint64_t)C::KROW * 2, (uint64_t)C::B_ROWS_TOTAL * C::KROW * 2};
   CUtensorMap* bm[3] = {b2, b3, b4};
-  CUtensorMap* hm[3] = {h2, h3, h4};
   for (int nb = 2; nb <= 4; ++nb) {
     const uint32_t bb[3] = {(uint32_t)C::BK, (uint32_t)(nb * C::COUT), 2};
     if (make_map_nd(bm[nb - 2], wts, 3, bd, bs, bb, sw)) return 1;
-    const uint32_t hb[3] = {(uint32_t)C::BK, (uint32_t)(nb * C::COUT / 2), 1};  // one plane, half the rows (cluster multicast)
-    if (make_map_nd(hm[nb - 2], wts, 3, bd, bs, hb, sw)) return 1;
   }
   return 0;
 }
@@ -495,75 +473,26 @@ static int tc_setup(cvb_model* m) {
   if (make_map_f16(&m->map_bh_lo, m->d_w4t_lo, F::N, K, F::BK, F::NH / 2, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   CK(cudaFuncSetAttribute(tc::k_fc4_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
   CK(cudaFuncSetAttribute(tc::k_fc4_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(tc::k_fc4_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
-  if (make_map_f16(&m->map_ah_hi, a_hi, (uint64_t)m->alloc_sites, K, F::BK, F::BM / 2, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-  if (make_map_f16(&m->map_ah_lo, a_lo, (uint64_t)m->alloc_sites, K, F::BK, F::BM / 2, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-  {
-    const char* e = getenv("CVB_TC_FC4_CLUSTER");  // 0 = no clusters, 2 (default) = weight multicast, 4 = weights + activations
-    m->tc_fc4_cluster = e ? atoi(e) : 2;  // 4 measured slower (0.242 vs 0.180 ms): lock-step of four CTAs, 4 KB boxes
-  }
   {
     using C = tc::Conv3Tc;
+    using S = tc::Conv3SlabRes;
     CK(cudaMalloc(&m->d_w3b_hi, (size_t)C::B_ROWS_TOTAL * C::KROW * 2 * 2));  // hi plane then lo plane
     m->d_w3b_lo = m->d_w3b_hi + (size_t)C::B_ROWS_TOTAL * C::KROW;
-    __half* p2_hi = reinterpret_cast<__half*>(m->d_p2);
-    __half* p2_lo = p2_hi + m->p2_rows * C::KROW;
-    const uint64_t rows = (uint64_t)m->alloc_sites * C::RPS;
-    if (make_map_f16(&m->map_c3a_hi, p2_hi, rows, C::KROW, C::BK, C::QROWS, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-    if (make_map_f16(&m->map_c3a_lo, p2_lo, rows, C::KROW, C::BK, C::QROWS, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-    if (make_map_f16(&m->map_c3b_hi, m->d_w3b_hi, C::B_ROWS_TOTAL, C::KROW, C::BK, C::COUT, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-    if (make_map_f16(&m->map_c3b_lo, m->d_w3b_lo, C::B_ROWS_TOTAL, C::KROW, C::BK, C::COUT, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
-    CK(cudaFuncSetAttribute(tc::k_conv_tc<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(tc::k_conv_tc<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    const char* e = getenv("CVB_TC_CONV3");
-    m->tc_conv3 = !(e && e[0] == '0');
-    const char* em = getenv("CVB_TC_MERGED");
-    m->tc_merged = !(em && em[0] == '0');
-    const char* ec = getenv("CVB_TC_CLUSTER");
-    m->tc_cluster = !(ec && ec[0] == '0');
-    const char* es = getenv("CVB_TC_SLAB");
-    m->tc_slab = !(es && es[0] == '0');
-    if (make_slab_map<C, tc::Conv3Slab>(p2_hi, m->p2_rows, CU_TENSOR_MAP_SWIZZLE_64B, &m->map_c3slab)) return 1;
-    CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::Conv3Slab>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Conv3Slab::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::Conv3SlabRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Conv3SlabRes::SMEM_BYTES));
-    const char* er = getenv("CVB_CONV_RESIDENT");
-    m->tc_resident = er ? atoi(er) : 1;  // conv3's taps stay in shared memory (measured -8 %, bit-identical); conv2: no gain
-    if (m->tc_merged && make_conv_merged_maps<C>(p2_hi, m->p2_rows, m->d_w3b_hi, CU_TENSOR_MAP_SWIZZLE_64B, &m->map_c3a4,
-                                                 &m->map_c3b2, &m->map_c3b3, &m->map_c3b4, &m->map_c3h2, &m->map_c3h3,
-                                                 &m->map_c3h4)) {
-      m->tc_merged = 0;  // overlapping-window view rejected by this driver: fall back to per-quadrant boxes
-      m->map_c3a4 = m->map_c3a_hi; m->map_c3b2 = m->map_c3b3 = m->map_c3b4 = m->map_c3b_hi;
-    }
+    if (make_slab_map<C, S>(m->d_p2, m->p2_rows, CU_TENSOR_MAP_SWIZZLE_64B, &m->map_c3slab)) return 1;
+    if (make_conv_weight_maps<C>(m->d_w3b_hi, CU_TENSOR_MAP_SWIZZLE_64B, &m->map_c3b2, &m->map_c3b3, &m->map_c3b4)) return 1;
+    CK(cudaFuncSetAttribute(tc::k_conv_slab<C, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
   }
   {
     using C = tc::Conv2Tc;
+    using S = tc::Conv2Slab;
     const size_t p1_halves = (size_t)m->p1_rows * C::KROW;
     CK(cudaMalloc(&m->d_p1, p1_halves * 2 * 2));
     CK(cudaMemset(m->d_p1, 0, p1_halves * 2 * 2));  // row 29 of every site stays zero (conv2's bottom SAME pad)
     CK(cudaMalloc(&m->d_w2b_hi, (size_t)C::B_ROWS_TOTAL * C::KROW * 2 * 2));  // hi plane then lo plane
     m->d_w2b_lo = m->d_w2b_hi + (size_t)C::B_ROWS_TOTAL * C::KROW;
-    const uint64_t rows = (uint64_t)m->alloc_sites * C::RPS;
-    if (make_map_f16(&m->map_c2a_hi, m->d_p1, rows, C::KROW, C::BK, C::QROWS, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
-    if (make_map_f16(&m->map_c2a_lo, m->d_p1 + p1_halves, rows, C::KROW, C::BK, C::QROWS, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
-    if (make_map_f16(&m->map_c2b_hi, m->d_w2b_hi, C::B_ROWS_TOTAL, C::KROW, C::BK, C::COUT, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
-    if (make_map_f16(&m->map_c2b_lo, m->d_w2b_lo, C::B_ROWS_TOTAL, C::KROW, C::BK, C::COUT, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
-    CK(cudaFuncSetAttribute(tc::k_conv_tc<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(tc::k_conv_tc<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    const char* e = getenv("CVB_TC_CONV2");
-    m->tc_conv2 = m->tc_conv3 && !(e && e[0] == '0');
-    if (make_slab_map<C, tc::Conv2Slab>(m->d_p1, m->p1_rows, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c2slab)) return 1;
-    CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::Conv2Slab>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Conv2Slab::SMEM_BYTES));
-    if (m->tc_merged && make_conv_merged_maps<C>(m->d_p1, m->p1_rows, m->d_w2b_hi, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c2a4,
-                                                 &m->map_c2b2, &m->map_c2b3, &m->map_c2b4, &m->map_c2h2, &m->map_c2h3,
-                                                 &m->map_c2h4))
-      m->tc_merged = 0;
-    if (!m->tc_merged) {
-      m->tc_cluster = 0;
-      m->tc_slab = 0;  // the slab kernels use the merged weight boxes
-      m->map_c2h2 = m->map_c2h3 = m->map_c2h4 = m->map_c3h2 = m->map_c3h3 = m->map_c3h4 = m->map_c2b_hi;
-      m->map_c2a4 = m->map_c2a_hi; m->map_c2b2 = m->map_c2b3 = m->map_c2b4 = m->map_c2b_hi;
-      m->map_c3a4 = m->map_c3a_hi; m->map_c3b2 = m->map_c3b3 = m->map_c3b4 = m->map_c3b_hi;
-    }
+    if (make_slab_map<C, S>(m->d_p1, m->p1_rows, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c2slab)) return 1;
+    if (make_conv_weight_maps<C>(m->d_w2b_hi, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c2b2, &m->map_c2b3, &m->map_c2b4)) return 1;
+    CK(cudaFuncSetAttribute(tc::k_conv_slab<C, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
   }
   {
     using T = tc::TailTc;
@@ -575,42 +504,22 @@ static int tc_setup(cvb_model* m) {
     if (make_map_f16(&m->map_tb_hi, m->d_wtail, T::NB, T::N4, T::BK, T::NB, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     if (make_map_f16(&m->map_tb_lo, m->d_wtail + (size_t)T::NB * T::N4, T::NB, T::N4, T::BK, T::NB, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
     CK(cudaFuncSetAttribute(tc::k_tail_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
-    const char* e = getenv("CVB_TC_TAIL");
-    m->tc_tail = !(e && e[0] == '0');
   }
   m->tc_ready = true;
   m->tc_weights_dirty = true;
   return 0;
 }
 
-// v3_slim: only conv3 (78 % of its FLOPs) runs on tcgen05; conv1+conv2 stay in the SIMT front kernel (which then writes
-// p2 as fp16 hi/lo planes), FC4/FC5/heads stay SIMT and read conv3's fp32 output.
+// v3_slim: conv1 SIMT (registers), conv2 / conv3 / FC4 on tcgen05, tail SIMT
 static int tc_setup_slim(cvb_model* m) {
   if (m->tc_ready) return 0;
-  using C = tc::SlimConv3Tc;
+  using C = tc::SlimConv3TcH;
   CK(cudaMalloc(&m->d_absmax, 16));
   CK(cudaMalloc(&m->d_inv_scale, 16));
   CK(cudaMalloc(&m->d_w3b_hi, (size_t)C::B_ROWS_TOTAL * C::KROW * 2 * 2));
   m->d_w3b_lo = m->d_w3b_hi + (size_t)C::B_ROWS_TOTAL * C::KROW;
-  if (make_conv_merged_maps<C>(m->d_p2, m->p2_rows, m->d_w3b_hi, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c3a4, &m->map_c3b2, &m->map_c3b3,
-                               &m->map_c3b4, &m->map_c3h2, &m->map_c3h3, &m->map_c3h4))
-    return 1;
-  m->map_c3a_hi = m->map_c3a_lo = m->map_c3a4;  // the per-quadrant 2-D maps are not used in merged mode
-  m->map_c3b_hi = m->map_c3b_lo = m->map_c3b2;
-  m->tc_merged = 1;
-  const char* ec = getenv("CVB_TC_CLUSTER");
-  m->tc_cluster = !(ec && ec[0] == '0');
-  const char* es = getenv("CVB_TC_SLAB");
-  m->tc_slab = !(es && es[0] == '0');
-  if (make_slab_map<C, tc::SlimConv3Slab>(m->d_p2, m->p2_rows, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c3slab)) return 1;
-  CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::SlimConv3Slab>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          tc::SlimConv3Slab::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(tc::k_conv_slab<C, tc::SlimConv3SlabRes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          tc::SlimConv3SlabRes::SMEM_BYTES));
-  const char* er = getenv("CVB_CONV_RESIDENT");
-  m->tc_resident = er ? atoi(er) : 1;  // measured on B200: 0.317 -> 0.207 ms per 33,152-site chunk, bit-identical
-  CK(cudaFuncSetAttribute(tc::k_conv_tc<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(tc::k_conv_tc<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  if (make_conv_weight_maps<C>(m->d_w3b_hi, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c3b2, &m->map_c3b3, &m->map_c3b4)) return 1;
+  if (make_slab_map<C, tc::SlimConv3HSlabRes>(m->d_p2, m->p2_rows, CU_TENSOR_MAP_SWIZZLE_32B, &m->map_c3slab)) return 1;
   {
     // conv2 as a dense row-shifted GEMM on p1 [site][35][32] (k_slim_c1_reg writes it), conv3 with fp16 hi / lo output planes,
     // FC4 as a split-fp16 GEMM over those planes (gemm_tc.cuh)
@@ -725,10 +634,6 @@ extern "C" int cvb_set_compute_mode(cvb_model* m, int mode) {
   }
   m->compute_mode = mode;
   m->CHUNK = (int64_t)m->num_sms * (m->variant == CVB_V3 ? (mode == CVB_COMPUTE_FP32 ? 96 : 128) : 224);
-  if (const char* e = getenv("CVB_CHUNK_PER_SM")) {  // experiment: sites per SM per launch (FC4 runs 2 CTAs per 128 sites)
-    const int v = atoi(e);
-    if (v >= 32 && v <= 224) m->CHUNK = (int64_t)m->num_sms * v;
-  }
   return 0;
 }
 extern "C" int cvb_set_train_mode(cvb_model* m, int mode) {
@@ -797,48 +702,15 @@ static HeadPtrs head_ptrs(const cvb_model* m) {
   return h;
 }
 
-// one chunk (n <= CHUNK) of the forward pass on `st`
-// launches k_conv_tc<T> either plainly or as 2-CTA clusters (weight multicast)
-template <class T, class S, class SR>
-static int launch_conv_tc(cvb_model* m, int resident, int64_t n, cudaStream_t st, const CUtensorMap* slab, const CUtensorMap& a_hi,
-                          const CUtensorMap& a_lo,
-                          const CUtensorMap& b_hi, const CUtensorMap& b_lo, const CUtensorMap& a4, const CUtensorMap& b2,
-                          const CUtensorMap& b3, const CUtensorMap& b4, const CUtensorMap& h2, const CUtensorMap& h3,
-                          const CUtensorMap& h4, const float* bias, const tc::BiasParam& bc, const float* inv_scale, __half* out_hi,
-                          __half* out_lo) {
-  if (m->tc_slab && slab) {
-    const int64_t st_tiles = (n * T::RPS + S::TILE_STEP - 1) / S::TILE_STEP;
-    const int g = (int)std::min<int64_t>(st_tiles, m->num_sms);
-    static const int ablate = getenv("CVB_ABLATE") ? atoi(getenv("CVB_ABLATE")) : 0;  // timing experiments only
-    if (resident)
-      CK(launch_k(tc::k_conv_slab<T, SR>, dim3(g), dim3(SR::THREADS), SR::SMEM_BYTES, st, 1, 1, use_pdl(m), *slab, b2, b3, b4, n, bias,
-                  inv_scale, out_hi, out_lo, ablate, bc));
-    else
-      CK(launch_k(tc::k_conv_slab<T, S>, dim3(g), dim3(S::THREADS), S::SMEM_BYTES, st, 1, 1, use_pdl(m), *slab, b2, b3, b4, n, bias,
-                  inv_scale, out_hi, out_lo, ablate, bc));
-    CK(cudaGetLastError());
-    return 0;
-  }
-  const int64_t tiles = (n * T::RPS + T::TILE_STEP - 1) / T::TILE_STEP;
-  int grid = (int)std::min<int64_t>(tiles, m->num_sms);
-  if (m->tc_cluster && m->tc_merged && grid >= 2) {
-    grid &= ~1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(T::THREADS);
-    cfg.dynamicSmemBytes = T::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, tc::k_conv_tc<T, true>, a_hi, a_lo, b_hi, b_lo, a4, b2, b3, b4, h2, h3, h4, 1, n, bias, inv_scale,
-                          out_hi, out_lo));
-  } else {
-    tc::k_conv_tc<T, false><<<grid, T::THREADS, T::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, a4, b2, b3, b4, h2, h3, h4, m->tc_merged, n,
-                                                                      bias, inv_scale, out_hi, out_lo);
-  }
+// one persistent launch of k_conv_slab<T, S> over n sites (inference: bias by value where S::BC says so)
+template <class T, class S>
+static int launch_conv_slab(cvb_model* m, int64_t n, cudaStream_t st, bool pdl, const CUtensorMap& slab, const CUtensorMap& b2,
+                            const CUtensorMap& b3, const CUtensorMap& b4, const float* bias, const tc::BiasParam& bc,
+                            const float* inv_scale, __half* out_hi, __half* out_lo, int flags = 0) {
+  static const int ablate = getenv("CVB_ABLATE") ? atoi(getenv("CVB_ABLATE")) : 0;  // timing experiments only (tools/ablate.py)
+  const int64_t tiles = (n * T::RPS + S::TILE_STEP - 1) / S::TILE_STEP;
+  CK(launch_k(tc::k_conv_slab<T, S>, dim3((unsigned)std::min<int64_t>(tiles, m->num_sms)), dim3(S::THREADS), S::SMEM_BYTES, st, 1, 1,
+              pdl, slab, b2, b3, b4, n, bias, inv_scale, out_hi, out_lo, ablate | flags, bc));
   CK(cudaGetLastError());
   return 0;
 }
@@ -888,122 +760,64 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
   const int sms = m->num_sms;
   const bool tensor = m->compute_mode != CVB_COMPUTE_FP32;
   if (tensor && tc_refresh_weights(m, st)) return 1;
-  static const bool c1_reg = !(getenv("CVB_C1_REG") && getenv("CVB_C1_REG")[0] == '0');
-  // k_v3_c1_reg<KIND> / k_slim_c1_reg<KIND> widen a narrow feed on their own
-  const bool fused_feed = tensor && (m->variant == CVB_V3 ? (m->tc_conv2 && c1_reg) : true);
-  if (kind != X_F32 && !fused_feed) {
+  // k_v3_c1_reg<KIND> / k_slim_c1_reg<KIND> (tensor path) widen a narrow feed on their own
+  if (kind != X_F32 && !tensor) {
     if (widen_chunk(m, xin, kind, n, st)) return 1;
     xin = m->d_xw;
     kind = X_F32;
   }
   const float* x = static_cast<const float*>(xin);
   if (prof_mark(m, st)) return 1;
-  if (m->variant == CVB_V3) {
+  if (m->variant == CVB_V3 && tensor) {
+    // ---- v3 on the tensor path: conv1 (SIMT, registers) -> conv2 -> conv3 (row-shifted implicit GEMMs) -> FC4 -> fused tail
     {
-      using F = FrontV3<4>;
-      int64_t tiles = (n + 3) / 4;
-      int grid = (int)std::min<int64_t>(tiles, 2 * sms);
-      if (tensor && m->tc_conv2) {
-        using C1K = C1Only<7>;
-        auto k1 = k_v3_c1<7>;
-        CK(set_smem(k1, C1K::SMEM_BYTES));
-        const size_t p1_halves = (size_t)m->p1_rows * 64;
-        if (c1_reg) {
-          const unsigned g1 = (unsigned)((n * 16 + 127) / 128);
-          const float *w1 = m->var("conv1/kernel"), *b1 = m->var("conv1/bias");
-          __half *phi = m->d_p1, *plo = m->d_p1 + p1_halves;
-          if (kind == X_F32) k_v3_c1_reg<X_F32><<<g1, 128, 0, st>>>(xin, n, w1, b1, phi, plo);
-          else if (kind == X_F16) k_v3_c1_reg<X_F16><<<g1, 128, 0, st>>>(xin, n, w1, b1, phi, plo);
-          else if (kind == X_I16) k_v3_c1_reg<X_I16><<<g1, 128, 0, st>>>(xin, n, w1, b1, phi, plo);
-          else k_v3_c1_reg<X_U8><<<g1, 128, 0, st>>>(xin, n, w1, b1, phi, plo);
-        } else {
-          int g1 = (int)std::min<int64_t>((n + 6) / 7, 2 * sms);
-          k1<<<g1, 256, C1K::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->d_p1, m->d_p1 + p1_halves);
-        }
-        CK(cudaGetLastError());
-        if (prof_mark(m, st)) return 1;  // kind 0 = SIMT front (conv1+pool1 here), kind 1 = tcgen05 conv2
-        using T = tc::Conv2Tc;
-        __half* p2_hi = reinterpret_cast<__half*>(m->d_p2);
-        if (launch_conv_tc<T, tc::Conv2Slab, tc::Conv2Slab>(m, 0, n, st, &m->map_c2slab, m->map_c2a_hi, m->map_c2a_lo, m->map_c2b_hi, m->map_c2b_lo, m->map_c2a4, m->map_c2b2,
-                              m->map_c2b3, m->map_c2b4, m->map_c2h2, m->map_c2h3, m->map_c2h4, m->var("conv2/bias"), m->hb2,
-                              m->d_inv_scale + 2, p2_hi, p2_hi + m->p2_rows * 128))
-          return 1;
-        m->launches += 1;
-      } else if (tensor && m->tc_conv3) {
-        auto k = k_v3_front<4, true>;
-        CK(set_smem(k, F::SMEM_BYTES));
-        k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
-                                            m->var("conv2/bias"), m->d_p2,
-                                            reinterpret_cast<__half*>(m->d_p2) + m->p2_rows * 128);
-        CK(cudaGetLastError());
-        if (prof_mark(m, st)) return 1;  // fused SIMT front = kind 0; kind 1 (tcgen05 conv2) stays empty
-      } else {
-        auto k = k_v3_front<4, false>;
-        CK(set_smem(k, F::SMEM_BYTES));
-        k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
-                                            m->var("conv2/bias"), m->d_p2, nullptr);
-        CK(cudaGetLastError());
-        if (prof_mark(m, st)) return 1;
-      }
+      using T = tc::Conv2Tc;
+      const size_t p1_halves = (size_t)m->p1_rows * T::KROW;
+      const unsigned g1 = (unsigned)((n * 16 + 127) / 128);
+      const float *w1 = m->var("conv1/kernel"), *b1 = m->var("conv1/bias");
+      __half *phi = m->d_p1, *plo = m->d_p1 + p1_halves;
+      if (kind == X_F32) k_v3_c1_reg<X_F32><<<g1, 128, 0, st>>>(xin, n, w1, b1, phi, plo);
+      else if (kind == X_F16) k_v3_c1_reg<X_F16><<<g1, 128, 0, st>>>(xin, n, w1, b1, phi, plo);
+      else if (kind == X_I16) k_v3_c1_reg<X_I16><<<g1, 128, 0, st>>>(xin, n, w1, b1, phi, plo);
+      else k_v3_c1_reg<X_U8><<<g1, 128, 0, st>>>(xin, n, w1, b1, phi, plo);
       CK(cudaGetLastError());
+      if (prof_mark(m, st)) return 1;
+      __half* p2_hi = reinterpret_cast<__half*>(m->d_p2);
+      if (launch_conv_slab<T, tc::Conv2Slab>(m, n, st, use_pdl(m, 1), m->map_c2slab, m->map_c2b2, m->map_c2b3, m->map_c2b4,
+                                             m->var("conv2/bias"), m->hb2, m->d_inv_scale + 2, p2_hi, p2_hi + m->p2_rows * 128))
+        return 1;
       if (prof_mark(m, st)) return 1;
     }
     {
-      using C = ConvCfg<32, 48, 3, 26, 3, 8, 8>;
-      using L = ConvLayerSmem<C, 3>;
-      int64_t tiles = (n + C::S - 1) / C::S;
-      int grid = (int)std::min<int64_t>(tiles, sms);
-      if (tensor && m->tc_conv3) {
-        using T = tc::Conv3Tc;
-        __half* p3_hi = reinterpret_cast<__half*>(m->d_p3);
-        if (launch_conv_tc<T, tc::Conv3Slab, tc::Conv3SlabRes>(m, m->tc_resident & 1, n, st, &m->map_c3slab, m->map_c3a_hi, m->map_c3a_lo, m->map_c3b_hi, m->map_c3b_lo,
-                                             m->map_c3a4, m->map_c3b2, m->map_c3b3, m->map_c3b4, m->map_c3h2, m->map_c3h3,
-                                             m->map_c3h4, m->var("conv3/bias"), m->hb3, m->d_inv_scale + 1, p3_hi,
-                                             p3_hi + m->alloc_sites * 4608))
-          return 1;
-      } else if (tensor) {
-        auto k = k_conv_layer<C, 3, 256, true>;
-        CK(set_smem(k, L::SMEM_BYTES));
-        k<<<grid, 256, L::SMEM_BYTES, st>>>(m->d_p2, n, m->var("conv3/kernel"), m->var("conv3/bias"), m->d_p3,
-                                            reinterpret_cast<__half*>(m->d_p3) + m->alloc_sites * 4608);
-      } else {
-        auto k = k_conv_layer<C, 3, 256, false>;
-        CK(set_smem(k, L::SMEM_BYTES));
-        k<<<grid, 256, L::SMEM_BYTES, st>>>(m->d_p2, n, m->var("conv3/kernel"), m->var("conv3/bias"), m->d_p3, nullptr);
-      }
-      CK(cudaGetLastError());
+      using T = tc::Conv3Tc;
+      __half* p3_hi = reinterpret_cast<__half*>(m->d_p3);
+      if (launch_conv_slab<T, tc::Conv3SlabRes>(m, n, st, use_pdl(m, 2), m->map_c3slab, m->map_c3b2, m->map_c3b3, m->map_c3b4,
+                                                m->var("conv3/bias"), m->hb3, m->d_inv_scale + 1, p3_hi,
+                                                p3_hi + m->alloc_sites * 4608))
+        return 1;
       if (prof_mark(m, st)) return 1;
     }
-    if (tensor) {
+    {
       using F = tc::Fc4Tc;
       const unsigned tiles4 = (unsigned)((n + F::BM - 1) / F::BM);
-      __half* h4hi = m->tc_tail ? m->d_h4s : nullptr;
-      __half* h4lo = m->tc_tail ? m->d_h4s + (size_t)m->alloc_sites * 336 : nullptr;
+      __half* h4hi = m->d_h4s;  // fp16 hi / lo planes of h4 = the A operand of the fused tail
+      __half* h4lo = m->d_h4s + (size_t)m->alloc_sites * 336;
       // small batches: split the 9 K-chunks over gridDim.z so that ~every SM streams a slice of W4 (k_fc4_tc, `ws`)
-      static const bool split_ok = !(getenv("CVB_FC4_SPLITK") && getenv("CVB_FC4_SPLITK")[0] == '0');
       unsigned ksplit = 1;
-      if (split_ok) {
-        const unsigned ctas = 2 * ((tiles4 + 1) & ~1u);
-        for (unsigned k : {9u, 3u})
-          if ((int64_t)n <= kFc4SplitSites && ctas * k <= 2 * (unsigned)sms) { ksplit = k; break; }
-      }
+      const unsigned ctas = 2 * ((tiles4 + 1) & ~1u);
+      for (unsigned k : {9u, 3u})
+        if ((int64_t)n <= kFc4SplitSites && ctas * k <= 2 * (unsigned)sms) { ksplit = k; break; }
       float* ws = nullptr;
       const int64_t ws_plane = (int64_t)kFc4SplitSites * 2 * F::NH;
       if (ksplit > 1) {
         if (!m->d_fc4ws) CK(cudaMalloc(&m->d_fc4ws, (size_t)(4608 / F::KCH) * ws_plane * 4));
         ws = m->d_fc4ws;
       }
-      if (m->tc_fc4_cluster >= 2 && tiles4 >= 2) {
-        const bool cl4 = m->tc_fc4_cluster >= 4;
-        const dim3 g4(2, (tiles4 + 1) & ~1u, ksplit);  // pairs of site tiles; a padding tile loads zeros and stores nothing
-        if (cl4)
-          CK(launch_k(tc::k_fc4_tc<4>, g4, dim3(F::THREADS), F::SMEM_BYTES, st, 2, 2, use_pdl(m), m->map_ah_hi, m->map_ah_lo,
-                      m->map_bh_hi, m->map_bh_lo, n, 4608, m->var("fc4/bias"), (const float*)m->d_inv_scale, m->d_h4, h4hi, h4lo, ws,
-                      ws_plane));
-        else
-          CK(launch_k(tc::k_fc4_tc<2>, g4, dim3(F::THREADS), F::SMEM_BYTES, st, 1, 2, use_pdl(m), m->map_a_hi, m->map_a_lo,
-                      m->map_bh_hi, m->map_bh_lo, n, 4608, m->var("fc4/bias"), (const float*)m->d_inv_scale, m->d_h4, h4hi, h4lo, ws,
-                      ws_plane));
+      if (tiles4 >= 2) {  // pairs of site tiles share every weight box (2-CTA multicast); a padding tile loads zeros and stores nothing
+        const dim3 g4(2, (tiles4 + 1) & ~1u, ksplit);
+        CK(launch_k(tc::k_fc4_tc<2>, g4, dim3(F::THREADS), F::SMEM_BYTES, st, 1, 2, use_pdl(m, 4), m->map_a_hi, m->map_a_lo,
+                    m->map_bh_hi, m->map_bh_lo, n, 4608, m->var("fc4/bias"), (const float*)m->d_inv_scale, m->d_h4, h4hi, h4lo, ws,
+                    ws_plane));
       } else {
         tc::k_fc4_tc<1><<<dim3(2, tiles4, ksplit), F::THREADS, F::SMEM_BYTES, st>>>(m->map_a_hi, m->map_a_lo, m->map_b_hi, m->map_b_lo, n,
                                                                                     4608, m->var("fc4/bias"), m->d_inv_scale, m->d_h4,
@@ -1018,7 +832,42 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
         m->launches += 1;
       }
       if (prof_mark(m, st)) return 1;
-    } else {
+    }
+    {
+      using T = tc::TailTc;
+      tc::TailHeads th{m->var("fc5/bias"), m->var("YBaseChangeSigmoid/bias"), m->var("YZygosityFC/kernel"), m->var("YZygosityFC/bias"),
+                       m->var("YVarTypeFC/kernel"), m->var("YVarTypeFC/bias"), m->var("YIndelLengthFC/kernel"),
+                       m->var("YIndelLengthFC/bias")};
+      CK(launch_k(tc::k_tail_tc, dim3((unsigned)((n + T::BM - 1) / T::BM)), dim3(T::THREADS), T::SMEM_BYTES, st, 1, 1, use_pdl(m, 8),
+                  m->map_ta_hi, m->map_ta_lo, m->map_tb_hi, m->map_tb_lo, n, th, (const float*)(m->d_inv_scale + 3), out16, logits16));
+      CK(cudaGetLastError());
+      if (prof_mark(m, st)) return 1;
+    }
+    m->launches += 5;  // c1, conv2, conv3, FC4, tail
+  } else if (m->variant == CVB_V3) {
+    // ---- v3, fp32 SIMT kernels (CVB_COMPUTE_FP32)
+    {
+      using F = FrontV3<4>;
+      auto k = k_v3_front<4>;
+      CK(set_smem(k, F::SMEM_BYTES));
+      const int grid = (int)std::min<int64_t>((n + 3) / 4, 2 * sms);
+      k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
+                                          m->var("conv2/bias"), m->d_p2);
+      CK(cudaGetLastError());
+      if (prof_mark(m, st)) return 1;
+      if (prof_mark(m, st)) return 1;  // (no separate conv2 kernel)
+    }
+    {
+      using C = ConvCfg<32, 48, 3, 26, 3, 8, 8>;
+      using L = ConvLayerSmem<C, 3>;
+      auto k = k_conv_layer<C, 3, 256>;
+      CK(set_smem(k, L::SMEM_BYTES));
+      const int grid = (int)std::min<int64_t>((n + C::S - 1) / C::S, sms);
+      k<<<grid, 256, L::SMEM_BYTES, st>>>(m->d_p2, n, m->var("conv3/kernel"), m->var("conv3/bias"), m->d_p3);
+      CK(cudaGetLastError());
+      if (prof_mark(m, st)) return 1;
+    }
+    {
       using F = FcCfg<336, 21, 16, 12, 8>;
       auto k = k_fc4<F>;
       CK(set_smem(k, F::SMEM_BYTES));
@@ -1027,17 +876,7 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
     }
-    if (tensor && m->tc_tail) {
-      using T = tc::TailTc;
-      tc::TailHeads th{m->var("fc5/bias"), m->var("YBaseChangeSigmoid/bias"), m->var("YZygosityFC/kernel"), m->var("YZygosityFC/bias"),
-                       m->var("YVarTypeFC/kernel"), m->var("YVarTypeFC/bias"), m->var("YIndelLengthFC/kernel"),
-                       m->var("YIndelLengthFC/bias")};
-      CK(launch_k(tc::k_tail_tc, dim3((unsigned)((n + T::BM - 1) / T::BM)), dim3(T::THREADS), T::SMEM_BYTES, st, 1, 1, use_pdl(m),
-                  m->map_ta_hi, m->map_ta_lo, m->map_tb_hi, m->map_tb_lo, n, th, (const float*)(m->d_inv_scale + 3), out16, logits16));
-      CK(cudaGetLastError());
-      if (prof_mark(m, st)) return 1;
-      m->launches -= 1;  // one fused kernel instead of FC5 + heads (the common "+= 5" below counts two)
-    } else {
+    {
       using F5 = FcCfg<168, 21, 8, 12, 8>;  // FC5: h5 = SELU(h4 @ W5 + b5), same SGEMM as the fp32 FC4
       auto k = k_fc4<F5>;
       CK(set_smem(k, F5::SMEM_BYTES));
@@ -1048,7 +887,7 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
     }
-    m->launches += 5;
+    m->launches += 5;  // front, conv3, FC4, FC5, heads
   } else if (tensor) {
     // ---- v3_slim on the tensor path: conv1 (SIMT, registers) -> conv2 (dense row-shifted GEMM) -> conv3 -> FC4 (GEMM) -> tail
     const bool hi_only = m->compute_mode == CVB_COMPUTE_FP16;  // plain fp16: one MMA term, hi planes only
@@ -1073,21 +912,19 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
     }
     const int hi_flag = hi_only ? 64 : 0;  // k_conv_slab: only the hi x hi term, no lo plane written
     {
-      using S2 = tc::SlimConv2SlabRes;
-      const int64_t tiles = (n * C2::RPS + S2::TILE_STEP - 1) / S2::TILE_STEP;
       __half* p2_hi = reinterpret_cast<__half*>(m->d_p2);
-      CK(launch_k(tc::k_conv_slab<C2, S2>, dim3((unsigned)std::min<int64_t>(tiles, sms)), dim3(S2::THREADS), S2::SMEM_BYTES, st, 1, 1,
-                  use_pdl(m, 1), m->map_s2slab, m->map_s2b, m->map_s2b, m->map_s2b, n, m->var("conv2/bias"),
-                  (const float*)(m->d_inv_scale + 2), p2_hi, p2_hi + m->p2_rows * 64, hi_flag, m->hb2));
+      if (launch_conv_slab<C2, tc::SlimConv2SlabRes>(m, n, st, use_pdl(m, 1), m->map_s2slab, m->map_s2b, m->map_s2b, m->map_s2b,
+                                                     m->var("conv2/bias"), m->hb2, m->d_inv_scale + 2, p2_hi,
+                                                     p2_hi + m->p2_rows * 64, hi_flag))
+        return 1;
       if (prof_mark(m, st)) return 1;
     }
     {
-      using S3 = tc::SlimConv3HSlabRes;
-      const int64_t tiles = (n * C3::RPS + S3::TILE_STEP - 1) / S3::TILE_STEP;
       __half* p3_hi = reinterpret_cast<__half*>(m->d_p3);
-      CK(launch_k(tc::k_conv_slab<C3, S3>, dim3((unsigned)std::min<int64_t>(tiles, sms)), dim3(S3::THREADS), S3::SMEM_BYTES, st, 1, 1,
-                  use_pdl(m, 2), m->map_c3slab, m->map_c3b2, m->map_c3b3, m->map_c3b4, n, m->var("conv3/bias"),
-                  (const float*)(m->d_inv_scale + 1), p3_hi, p3_hi + m->alloc_sites * 4224, hi_flag, m->hb3));
+      if (launch_conv_slab<C3, tc::SlimConv3HSlabRes>(m, n, st, use_pdl(m, 2), m->map_c3slab, m->map_c3b2, m->map_c3b3, m->map_c3b4,
+                                                      m->var("conv3/bias"), m->hb3, m->d_inv_scale + 1, p3_hi,
+                                                      p3_hi + m->alloc_sites * 4224, hi_flag))
+        return 1;
       if (prof_mark(m, st)) return 1;
     }
     {
@@ -1115,10 +952,10 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
       using F = FrontSlim<6>;
       int64_t tiles = (n + 5) / 6;
       int grid = (int)std::min<int64_t>(tiles, 4 * sms);
-      auto k = k_slim_front<6, false>;
+      auto k = k_slim_front<6>;
       CK(set_smem(k, F::SMEM_BYTES));
       k<<<grid, 256, F::SMEM_BYTES, st>>>(x, n, m->var("conv1/kernel"), m->var("conv1/bias"), m->var("conv2/kernel"),
-                                          m->var("conv2/bias"), m->d_p2, nullptr);
+                                          m->var("conv2/bias"), m->d_p2);
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
       if (prof_mark(m, st)) return 1;  // (no separate conv2 kernel)
@@ -1126,11 +963,11 @@ static int forward_chunk(cvb_model* m, const void* xin, int kind, int64_t n, Out
     {
       using C = ConvCfg<16, 32, 5, 33, 3, 8, 8>;
       using L = ConvLayerSmem<C, 1>;
-      auto k = k_conv_layer<C, 1, 256, false>;
+      auto k = k_conv_layer<C, 1, 256>;
       CK(set_smem(k, L::SMEM_BYTES));
       int64_t tiles = (n + C::S - 1) / C::S;
       int grid = (int)std::min<int64_t>(tiles, sms);
-      k<<<grid, 256, L::SMEM_BYTES, st>>>(m->d_p2, n, m->var("conv3/kernel"), m->var("conv3/bias"), m->d_p3, nullptr);
+      k<<<grid, 256, L::SMEM_BYTES, st>>>(m->d_p2, n, m->var("conv3/kernel"), m->var("conv3/bias"), m->d_p3);
       CK(cudaGetLastError());
       if (prof_mark(m, st)) return 1;
     }
@@ -1437,9 +1274,7 @@ static int ensure_train_work(cvb_model* m) {
     for (auto& it : slim_items) { *it.p = w->all + off; off += (it.n + 63) / 64 * 64; }
     w->p3 = w->c3;
     {
-      // tensor-core conv3 + FC4 of the v3_slim step (CVB_TRAIN_SLIM_TC=0 keeps the SIMT kernels): operand planes [hi | lo]
-      const char* e = getenv("CVB_TRAIN_SLIM_TC");
-      w->slim_tc = e ? atoi(e) != 0 : true;
+      // tensor-core conv3 + FC4 of the v3_slim step (CVB_TRAIN_FP32 keeps the SIMT kernels): operand planes [hi | lo]
       struct Item16 { uint16_t** p; int64_t n; };
       Item16 it16[] = {{&w->p2h, 2 * c * 37 * 64}, {&w->p2b, 2 * c * 37 * 64}, {&w->g3h, 2 * c * 37 * 128}, {&w->p3s, 2 * c * 4224},
                        {&w->g4s, 2 * c * 40}, {&w->w4s, 2 * 4224 * 40}, {&w->w4ts, 2 * 36 * 4224}, {&w->wf3, 2 * 5 * 128 * 64},
@@ -1644,13 +1479,13 @@ static int launch_conv_keep(cvb_model* m, const float* in, int64_t nc, const flo
   using L = ConvLayerSmem<C, 1>;
   const int grid = (int)std::min<int64_t>((nc + C::S - 1) / C::S, 2 * m->num_sms);
   if (act) {
-    auto k = k_conv_layer<C, 1, 256, false, true>;
+    auto k = k_conv_layer<C, 1, 256, true>;
     CK(set_smem(k, L::SMEM_BYTES));
-    k<<<grid, 256, L::SMEM_BYTES, st>>>(in, nc, wg, bg, out, nullptr);
+    k<<<grid, 256, L::SMEM_BYTES, st>>>(in, nc, wg, bg, out);
   } else {
-    auto k = k_conv_layer<C, 1, 256, false, false>;
+    auto k = k_conv_layer<C, 1, 256, false>;
     CK(set_smem(k, L::SMEM_BYTES));
-    k<<<grid, 256, L::SMEM_BYTES, st>>>(in, nc, wg, bg, out, nullptr);
+    k<<<grid, 256, L::SMEM_BYTES, st>>>(in, nc, wg, bg, out);
   }
   CK(cudaGetLastError());
   return 0;
@@ -1675,7 +1510,7 @@ static int train_forward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t se
   if (launch_conv_keep<ConvCfg<4, 8, 1, 33, 12, 8, 8>>(m, w->x, nc, m->var("conv1/kernel"), m->var("conv1/bias"), w->c1, true, st)) return 1;
   k_pool_fwd<1><<<gsz(nc * 33 * 8), 256, 0, st>>>(w->c1, nc, 33, 32, w->p1p, 35, 1, nullptr, nullptr);
   if (launch_conv_keep<ConvCfg<8, 16, 3, 33, 6, 8, 8>>(m, w->p1p, nc, m->var("conv2/kernel"), m->var("conv2/bias"), w->c2, true, st)) return 1;
-  const bool stc = w->slim_tc && m->train_mode != CVB_TRAIN_FP32;
+  const bool stc = m->train_mode != CVB_TRAIN_FP32;
   k_pool_fwd<1><<<gsz(nc * 33 * 16), 256, 0, st>>>(w->c2, nc, 33, 64, w->p2p, 37, 2, stc ? hp(w->p2h) : nullptr,
                                                    stc ? hp(w->p2h) + w->cap * 37 * 64 : nullptr, stc ? bf(w->p2b) : nullptr,
                                                    stc ? bf(w->p2b) + w->cap * 37 * 64 : nullptr);
@@ -1761,7 +1596,7 @@ static int train_backward_slim(cvb_model* m, int64_t nc, float drop4, uint64_t s
   k_dense_bwd_small<<<gsz(nc * 36), 256, 0, st>>>(w->g5, 24, 18, m->var("fc5/kernel"), 36, w->g4b, 36, nc);
   k_fc4_bwd_elem<<<gsz(nc * 36), 256, 0, st>>>(w->g4, w->g4b, w->h4, nc * 36, index0, SeedRef{w->seedbuf, 0}, drop_const(drop4), drop4 > 0.f ? 1 : 0);
   // FC4
-  const bool stc = w->slim_tc && m->train_mode != CVB_TRAIN_FP32;
+  const bool stc = m->train_mode != CVB_TRAIN_FP32;
   k_colsum<<<dim3(2, 32), 256, 0, st>>>(w->g4, nc, 36, 36, gvar(m, "fc4/bias"));
   if (stc) {
     // dpre4 [sites][36] as split bf16 with rows padded to 40 (TMA strides are 16-byte granular); weight gradient reads
@@ -1823,10 +1658,10 @@ static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, i
   {
     using C = ConvCfg<4, 16, 1, 33, 6, 8, 8>;
     using L = ConvLayerSmem<C, 1>;
-    auto k = k_conv_layer<C, 1, 256, false, true>;
+    auto k = k_conv_layer<C, 1, 256, true>;
     CK(set_smem(k, L::SMEM_BYTES));
     k<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, 2 * sms), 256, L::SMEM_BYTES, st>>>(w->x, nc, m->var("conv1/kernel"),
-                                                                                          m->var("conv1/bias"), w->c1, nullptr);
+                                                                                          m->var("conv1/bias"), w->c1);
     CK(cudaGetLastError());
     k_pool_fwd<5><<<gsz(nc * 29 * 16), 256, 0, st>>>(w->c1, nc, 33, 64, w->p1p, 30, 0, tcm ? hp(w->p1h) : nullptr,
                                                      tcm ? hp(w->p1h) + w->cap * 30 * 64 : nullptr, tcm ? bf(w->p1b) : nullptr,
@@ -1846,20 +1681,20 @@ static int train_forward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, i
     {
       using C = ConvCfg<16, 32, 2, 29, 4, 8, 8>;
       using L = ConvLayerSmem<C, 1>;
-      auto k = k_conv_layer<C, 1, 256, false, true>;
+      auto k = k_conv_layer<C, 1, 256, true>;
       CK(set_smem(k, L::SMEM_BYTES));
       k<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->p1p, nc, m->var("conv2/kernel"),
-                                                                                        m->var("conv2/bias"), w->c2, nullptr);
+                                                                                        m->var("conv2/bias"), w->c2);
       CK(cudaGetLastError());
       k_pool_fwd<4><<<gsz(nc * 26 * 32), 256, 0, st>>>(w->c2, nc, 29, 128, w->p2p, 28, 1, nullptr, nullptr);
     }
     {
       using C = ConvCfg<32, 48, 3, 26, 3, 8, 8>;
       using L = ConvLayerSmem<C, 1>;
-      auto k = k_conv_layer<C, 1, 256, false, true>;
+      auto k = k_conv_layer<C, 1, 256, true>;
       CK(set_smem(k, L::SMEM_BYTES));
       k<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->p2p, nc, m->var("conv3/kernel"),
-                                                                                        m->var("conv3/bias"), w->c3, nullptr);
+                                                                                        m->var("conv3/bias"), w->c3);
       CK(cudaGetLastError());
       k_pool_fwd<3><<<gsz(nc * 24 * 48), 256, 0, st>>>(w->c3, nc, 26, 192, w->p3, 24, 0, nullptr, nullptr);
     }
@@ -2034,9 +1869,9 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
     } else {
       using C = ConvCfg<48, 32, 3, 26, 3, 8, 8, 2>;
       using L = ConvLayerSmem<C, 1>;
-      auto kd = k_conv_layer<C, 1, 256, false, false>;
+      auto kd = k_conv_layer<C, 1, 256, false>;
       CK(set_smem(kd, L::SMEM_BYTES));
-      kd<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->g3p, nc, w->w3t, nullptr, w->gp2, nullptr);
+      kd<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->g3p, nc, w->w3t, nullptr, w->gp2);
       CK(cudaGetLastError());
     }
   }
@@ -2061,9 +1896,9 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
     } else {
       using C = ConvCfg<32, 16, 2, 29, 4, 8, 8, 2>;
       using L = ConvLayerSmem<C, 1>;
-      auto kd = k_conv_layer<C, 1, 256, false, false>;
+      auto kd = k_conv_layer<C, 1, 256, false>;
       CK(set_smem(kd, L::SMEM_BYTES));
-      kd<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->g2p, nc, w->w2t, nullptr, w->gp1, nullptr);
+      kd<<<(int)std::min<int64_t>((nc + C::S - 1) / C::S, sms), 256, L::SMEM_BYTES, st>>>(w->g2p, nc, w->w2t, nullptr, w->gp1);
       CK(cudaGetLastError());
     }
   }
@@ -2079,7 +1914,7 @@ static int train_backward(cvb_model* m, int64_t nc, float drop4, uint64_t seed, 
 static int train_prepare_weights(cvb_model* m, cudaStream_t st, bool backward) {
   TrainWork* w = m->train;
   if (m->variant != CVB_V3) {
-    const bool stc = w->slim_tc && m->train_mode != CVB_TRAIN_FP32;
+    const bool stc = m->train_mode != CVB_TRAIN_FP32;
     if (stc) {  // forward operands (getLoss included): conv3 weights rearranged + scaled fp16, W4^T [36][4224] split bf16
       using F3 = tc::SlimConv3Tc;
       CK(cudaMemsetAsync(w->amax, 0, 8, st));

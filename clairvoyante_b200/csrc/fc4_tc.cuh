@@ -80,10 +80,8 @@ __global__ void k_prep_fc_weights(const float* __restrict__ w, int K, int N, con
 // CL = 2: clusters of 2 CTAs along the site-tile axis (same N-half): the pair shares the weight operand, each CTA
 // loads half of its rows per stage and TMA-multicasts them to both (this kernel is bound by operand ingest: 1.66 GB of
 // TMA traffic per 18,944-site launch, 58 % of it weights).  map_b_* then carry boxes of NH/2 rows.
-// CL = 4: clusters of 2 x 2 CTAs = (both N-halves) x (two site tiles).  Additionally the two CTAs of one site tile share
-// the activation operand: each loads 64 of its 128 rows (map_a_* carry boxes of BM/2 rows) and multicasts them to its
-// sibling.  Per CTA and stage: 8 + 11 KB leave L2 instead of 16 + 11 KB.  A slot is refilled once the CTA itself and the
-// two CTAs it multicasts into have released it (empty barrier count 3).
+// (Clusters of 2 x 2 CTAs that also multicast the activation operand between the two N-halves were measured slower,
+// 0.212 vs 0.158 ms: four CTAs in lock-step on 4 KB boxes -- profiles/r02_ab_log.md -- and are gone.)
 template <int CL>
 __global__ void __launch_bounds__(Fc4Tc::THREADS, 1)
 k_fc4_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -97,8 +95,8 @@ k_fc4_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ C
   // partial sums to ws[chunk][site][2 * NH]; k_fc4_reduce adds them IN CHUNK ORDER and applies the epilogue, which is the
   // very sequence of fp32 additions the unsplit kernel performs in registers: results are bit-identical for every batch size.
   using F = Fc4Tc;
-  constexpr bool CL2 = CL >= 2;  // weights shared along the site-tile axis
-  constexpr bool CL4 = CL == 4;  // activations shared between the two N-halves as well
+  static_assert(CL == 1 || CL == 2, "one CTA, or a pair of site tiles sharing the weight boxes");
+  constexpr bool CL2 = CL == 2;  // weights shared along the site-tile axis
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F::STAGES * F::STAGE_BYTES);
@@ -122,7 +120,7 @@ k_fc4_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
     tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
-    for (int s = 0; s < F::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL4 ? 3 : (CL2 ? 2 : 1)); }
+    for (int s = 0; s < F::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL2 ? 2 : 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
     fence_barrier_init();
   }
@@ -132,12 +130,9 @@ k_fc4_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ C
   if (CL2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t crank = CL2 ? cluster_ctarank() : 0;
-  const uint32_t ty = CL4 ? crank >> 1 : crank;  // which of the cluster's two site tiles
+  const uint32_t ty = CL2 ? cluster_ctarank() : 0;  // which of the cluster's two site tiles
   // CTAs whose ring slots this CTA's loads land in / whose MMAs must have released a slot before it is refilled
-  const uint16_t mask_b = CL4 ? (uint16_t)((1u << half) | (1u << (half + 2))) : (uint16_t)3;
-  const uint16_t mask_a = (uint16_t)(3u << (2 * ty));
-  const uint16_t mask_rel = CL4 ? (uint16_t)((1u << crank) | (1u << (crank ^ 1)) | (1u << (crank ^ 2))) : (uint16_t)3;
+  const uint16_t mask_b = 3, mask_rel = 3;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -151,14 +146,8 @@ k_fc4_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ C
         uint8_t* st = smem + s * F::STAGE_BYTES;
         mbar_arrive_expect_tx(&full[s], F::STAGE_BYTES);
         const int k0 = (kb0 + kb) * F::BK;
-        if (CL4) {
-          constexpr int HA = F::BM / 2;  // 64 rows = 8 swizzle atoms
-          tma_load_2d_mc(st + half * (HA * F::ROW_BYTES), &map_a_hi, &full[s], k0, (int)site0 + half * HA, mask_a);
-          tma_load_2d_mc(st + F::A_BYTES + half * (HA * F::ROW_BYTES), &map_a_lo, &full[s], k0, (int)site0 + half * HA, mask_a);
-        } else {
-          tma_load_2d(st, &map_a_hi, &full[s], k0, (int)site0);
-          tma_load_2d(st + F::A_BYTES, &map_a_lo, &full[s], k0, (int)site0);
-        }
+        tma_load_2d(st, &map_a_hi, &full[s], k0, (int)site0);
+        tma_load_2d(st + F::A_BYTES, &map_a_lo, &full[s], k0, (int)site0);
         if (CL2) {
           constexpr int HR = F::NH / 2;  // 88 rows = 11 swizzle atoms
           tma_load_2d_mc(st + 2 * F::A_BYTES + ty * (HR * F::ROW_BYTES), &map_b_hi, &full[s], k0, half * F::NH + (int)ty * HR, mask_b);

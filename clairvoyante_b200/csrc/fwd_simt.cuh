@@ -41,13 +41,10 @@ struct FrontV3 {
   static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
 };
 
-// SPLIT = true: p2 is written as two fp16 tensors (hi at p2, lo at p2_lo), same [n][28][128] shape,
-// hi + lo ~= value: the A operand of the tensor-core conv3 (conv3_tc.cuh).
-template <int S, bool SPLIT>
+template <int S>
 __global__ void __launch_bounds__(256, 2)
 k_v3_front(const float* __restrict__ x, int64_t n, const float* __restrict__ w1g, const float* __restrict__ b1g,
-           const float* __restrict__ w2g, const float* __restrict__ b2g, float* __restrict__ p2,
-           void* __restrict__ p2_lo) {
+           const float* __restrict__ w2g, const float* __restrict__ b2g, float* __restrict__ p2) {
   using F = FrontV3<S>;
   using C1 = typename F::C1;
   using C2 = typename F::C2;
@@ -121,90 +118,15 @@ k_v3_front(const float* __restrict__ x, int64_t n, const float* __restrict__ w1g
 #pragma unroll
       for (int j = 1; j < 4; ++j) v = max4(v, *reinterpret_cast<const float4*>(src + j * F::C2S_RS));
       const int64_t o = ((site0 + s) * 28 + 1 + h) * 128 + q * 4;
-      if constexpr (SPLIT) {
-        __half hi[4], lo[4];
-        tc::split_f16(v.x, hi[0], lo[0]); tc::split_f16(v.y, hi[1], lo[1]);
-        tc::split_f16(v.z, hi[2], lo[2]); tc::split_f16(v.w, hi[3], lo[3]);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p2) + o) = *reinterpret_cast<const uint2*>(hi);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p2_lo) + o) = *reinterpret_cast<const uint2*>(lo);
-      } else {
-        *reinterpret_cast<float4*>(p2 + o) = v;
-      }
+      *reinterpret_cast<float4*>(p2 + o) = v;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------
-// k_v3_c1 (tensor path): x -> conv1+SELU -> pool1 -> p1 as fp16 hi/lo [n][30][64] (row 29 is the
-// zero SAME-padding row of conv2 and is never written), the A operand of the tcgen05 conv2.
-// ------------------------------------------------------------------------------------
-template <int S>
-struct C1Only {
-  using C1 = ConvCfg<4, 16, 1, 33, S, 8, 8>;
-  static_assert(C1::THREADS <= 256, "tile does not fit the CTA");
-  static constexpr int C1S_RS = 68;
-  static constexpr int W1 = 0;
-  static constexpr int B1 = W1 + C1::W_FLOATS;
-  static constexpr int XS = B1 + 16;
-  static constexpr int C1S = XS + C1::IN_FLOATS;
-  static constexpr int SMEM_FLOATS = C1S + S * 33 * C1S_RS;
-  static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
-};
-
-template <int S>
-__global__ void __launch_bounds__(256, 2)
-k_v3_c1(const float* __restrict__ x, int64_t n, const float* __restrict__ w1g, const float* __restrict__ b1g,
-        __half* __restrict__ p1_hi, __half* __restrict__ p1_lo) {
-  using F = C1Only<S>;
-  using C1 = typename F::C1;
-  extern __shared__ __align__(16) float smem[];
-  const int tid = threadIdx.x;
-  float* w1s = smem + F::W1;
-  float* b1s = smem + F::B1;
-  float* xs = smem + F::XS;
-  float* c1s = smem + F::C1S;
-  for (int i = tid; i < C1::W_FLOATS; i += 256) w1s[i] = w1g[i];
-  if (tid < 16) b1s[tid] = b1g[tid];
-  const ConvThread<C1> th1(tid);
-  const int64_t ntiles = (n + S - 1) / S;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t site0 = tile * S;
-    __syncthreads();
-    for (int i = tid; i < S * 33 * 4; i += 256) {
-      int s = i / 132, r = i - s * 132;
-      int h = r >> 2, q = r & 3;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (site0 + s < n) v = ldg_stream(reinterpret_cast<const float4*>(x + (site0 + s) * 528) + r);
-      *reinterpret_cast<float4*>(xs + (s * C1::ROWS + h) * C1::RS + q * 4) = v;
-    }
-    __syncthreads();
-    {
-      float acc[C1::TM][C1::TN];
-      conv_compute<C1>(xs, w1s, th1, acc);
-      conv_store_selu_smem<C1, 33, F::C1S_RS, 0>(acc, b1s, th1, c1s);
-    }
-    __syncthreads();
-    // pool1 (5,1) -> global p1[site][h<29][64] as hi/lo halves
-    for (int i = tid; i < S * 29 * 16; i += 256) {
-      int s = i / (29 * 16), r = i - s * (29 * 16);
-      int h = r >> 4, q = r & 15;
-      if (site0 + s >= n) continue;
-      const float* src = c1s + (s * 33 + h) * F::C1S_RS + q * 4;
-      float4 v = *reinterpret_cast<const float4*>(src);
-#pragma unroll
-      for (int j = 1; j < 5; ++j) v = max4(v, *reinterpret_cast<const float4*>(src + j * F::C1S_RS));
-      const int64_t o = ((site0 + s) * 30 + h) * 64 + q * 4;
-      __half hi[4], lo[4];
-      tc::split_f16(v.x, hi[0], lo[0]); tc::split_f16(v.y, hi[1], lo[1]);
-      tc::split_f16(v.z, hi[2], lo[2]); tc::split_f16(v.w, hi[3], lo[3]);
-      *reinterpret_cast<uint2*>(p1_hi + o) = *reinterpret_cast<const uint2*>(hi);
-      *reinterpret_cast<uint2*>(p1_lo + o) = *reinterpret_cast<const uint2*>(lo);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------
-// k_v3_c1_reg: the same layer (clairvoyante_v3.py:54-66: conv1 1x4, 4 -> 16, SELU, pool1 (5,1)) with everything in
+// k_v3_c1_reg (tensor path): x -> conv1 + SELU -> pool1 -> p1 as fp16 hi / lo planes [n][30][64], the A operand of the tcgen05
+// conv2 (row 29 is conv2's zero SAME-padding row and is never written).  clairvoyante_v3.py:54-66: conv1 1x4, 4 -> 16, SELU,
+// pool1 (5,1), with everything in
 // registers -- no shared memory, no barriers.  16 threads per site: thread (w, cq) owns output column w, channels
 // 4cq..4cq+3, keeps its 4 x 4 x 4 weights in registers (zero where the SAME padding cuts the tap), walks the site's 33 rows,
 // and pools with a 5-deep register ring (max of raw sums, then bias + SELU: SELU is monotonic).  The 16 x values of a row
@@ -447,11 +369,10 @@ struct FrontSlim {
   static constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
 };
 
-// SPLIT = true: p2 as two fp16 planes (hi at p2, lo at p2_lo) for the tcgen05 slim conv3
-template <int S, bool SPLIT>
+template <int S>
 __global__ void __launch_bounds__(256, 2)
 k_slim_front(const float* __restrict__ x, int64_t n, const float* __restrict__ w1g, const float* __restrict__ b1g,
-             const float* __restrict__ w2g, const float* __restrict__ b2g, float* __restrict__ p2, void* __restrict__ p2_lo) {
+             const float* __restrict__ w2g, const float* __restrict__ b2g, float* __restrict__ p2) {
   using F = FrontSlim<S>;
   using C1 = typename F::C1;
   using C2 = typename F::C2;
@@ -496,19 +417,7 @@ k_slim_front(const float* __restrict__ x, int64_t n, const float* __restrict__ w
       float acc[C2::TM][C2::TN];
       conv_compute<C2>(c1s, w2s, th2, acc);
       int nsites = (int)((n - site0) < S ? (n - site0) : S);
-      if constexpr (SPLIT) {
-        auto split4 = [](float a, float b, float c, float d, void* hi, void* lo, int64_t o) {
-          __half2 h[2], l[2];
-          tc::split_f16x2(a, b, h[0], l[0]);
-          tc::split_f16x2(c, d, h[1], l[1]);
-          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(hi) + o) = *reinterpret_cast<const uint2*>(h);
-          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(lo) + o) = *reinterpret_cast<const uint2*>(l);
-        };
-        conv_store_selu_global_split<C2, 37, 64, 2>(acc, b2s, th2, reinterpret_cast<__half*>(p2) + site0 * (37 * 64),
-                                                    reinterpret_cast<__half*>(p2_lo) + site0 * (37 * 64), nsites, split4);
-      } else {
-        conv_store_selu_global<C2, 37, 64, 2>(acc, b2s, th2, p2 + site0 * (37 * 64), nsites);
-      }
+      conv_store_selu_global<C2, 37, 64, 2>(acc, b2s, th2, p2 + site0 * (37 * 64), nsites);
     }
   }
 }
@@ -545,14 +454,11 @@ __device__ __forceinline__ void conv_tile_load_async(float* __restrict__ buf, co
   }
 }
 
-// SPLIT = false: out is fp32 [n][HP][4*COUT].
-// SPLIT = true : out is reinterpreted as two fp16 tensors of the same shape, hi at out and lo at
-//                out_lo, with hi + lo ~= value (operands of the split-fp16 tensor-core FC4, fc4_tc.cuh).
-// ACT = false: no bias / activation (data-gradient convolutions of the training path)
-template <class C, int POOL, int NTHREADS, bool SPLIT, bool ACT = true>
+// out is fp32 [n][HP][4*COUT].  ACT = false: no bias / activation (data-gradient convolutions of the training path)
+template <class C, int POOL, int NTHREADS, bool ACT = true>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_conv_layer(const float* __restrict__ in, int64_t n, const float* __restrict__ wg, const float* __restrict__ bg,
-             float* __restrict__ out, void* __restrict__ out_lo) {
+             float* __restrict__ out) {
   using L = ConvLayerSmem<C, POOL>;
   static_assert(C::THREADS <= NTHREADS, "tile does not fit the CTA");
   extern __shared__ __align__(16) float smem[];
@@ -590,15 +496,7 @@ k_conv_layer(const float* __restrict__ in, int64_t n, const float* __restrict__ 
 #pragma unroll
       for (int j = 1; j < POOL; ++j) v = max4(v, *reinterpret_cast<const float4*>(src + j * L::ORS));
       const int64_t o = ((site0 + s) * L::HP + h) * (4 * C::COUT) + q * 4;
-      if constexpr (SPLIT) {
-        __half hi[4], lo[4];
-        tc::split_f16(v.x, hi[0], lo[0]); tc::split_f16(v.y, hi[1], lo[1]);
-        tc::split_f16(v.z, hi[2], lo[2]); tc::split_f16(v.w, hi[3], lo[3]);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + o) = *reinterpret_cast<const uint2*>(hi);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out_lo) + o) = *reinterpret_cast<const uint2*>(lo);
-      } else {
-        *reinterpret_cast<float4*>(out + o) = v;
-      }
+      *reinterpret_cast<float4*>(out + o) = v;
     }
     __syncthreads();  // pooled reads done before the next-next tile load lands in `cur`
   }
@@ -816,92 +714,12 @@ k_heads(const float* __restrict__ h4, const float* __restrict__ h5, int64_t n, H
   }
 }
 
-template <int N4, int N5, int TS>
-__global__ void __launch_bounds__(256, 2)
-k_tail(const float* __restrict__ h4, int64_t n, HeadPtrs hp, OutDst out16, float* __restrict__ logits16) {
-  constexpr int L4 = N4 + 4, L5 = N5 + 4;
-  __shared__ __align__(16) float h4s[TS * L4];
-  __shared__ __align__(16) float h5s[TS * L5];
-  __shared__ float lg[TS * 16];
-  const int tid = threadIdx.x;
-  const int64_t site0 = (int64_t)blockIdx.x * TS;
-  for (int i = tid; i < TS * (N4 / 4); i += 256) {
-    int s = i / (N4 / 4), q = i - s * (N4 / 4);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (site0 + s < n) v = *reinterpret_cast<const float4*>(h4 + (site0 + s) * N4 + q * 4);
-    *reinterpret_cast<float4*>(h4s + s * L4 + q * 4) = v;
-  }
-  __syncthreads();
-  // FC5: thread j owns output column j for all TS sites
-  for (int j = tid; j < N5; j += 256) {
-    float acc[TS];
-#pragma unroll
-    for (int s = 0; s < TS; ++s) acc[s] = 0.f;
-    for (int k = 0; k < N4; k += 4) {
-      const float w0 = hp.w5[(k + 0) * N5 + j], w1 = hp.w5[(k + 1) * N5 + j];
-      const float w2 = hp.w5[(k + 2) * N5 + j], w3 = hp.w5[(k + 3) * N5 + j];
-#pragma unroll
-      for (int s = 0; s < TS; ++s) {
-        const float4 a = *reinterpret_cast<const float4*>(h4s + s * L4 + k);
-        acc[s] = fmaf(a.x, w0, acc[s]);
-        acc[s] = fmaf(a.y, w1, acc[s]);
-        acc[s] = fmaf(a.z, w2, acc[s]);
-        acc[s] = fmaf(a.w, w3, acc[s]);
-      }
-    }
-    const float b = hp.b5[j];
-#pragma unroll
-    for (int s = 0; s < TS; ++s) h5s[s * L5 + j] = selu_f(acc[s] + b);
-  }
-  __syncthreads();
-  // heads: 16 dot products per site
-  for (int i = tid; i < TS * 16; i += 256) {
-    const int s = i >> 4, o = i & 15;
-    float acc = 0.f;
-    if (o < 4) {  // base change: input is the FC4 branch (clairvoyante_v3.py:125)
-      for (int k = 0; k < N4; ++k) acc = fmaf(h4s[s * L4 + k], hp.wb[k * 4 + o], acc);
-      acc += hp.bb[o];
-    } else {
-      const float* w;
-      int ld, col;
-      float b;
-      if (o < 6) { w = hp.wz; ld = 2; col = o - 4; b = hp.bz[col]; }
-      else if (o < 10) { w = hp.wt; ld = 4; col = o - 6; b = hp.bt[col]; }
-      else { w = hp.wl; ld = 6; col = o - 10; b = hp.bl[col]; }
-      for (int k = 0; k < N5; ++k) acc = fmaf(h5s[s * L5 + k], w[k * ld + col], acc);
-      acc = selu_f(acc + b) + 1e-10f;  // clairvoyante_v3.py:127-128
-    }
-    lg[i] = acc;
-  }
-  __syncthreads();
-  if (tid < TS && site0 + tid < n) {
-    const float* l = lg + tid * 16;
-    float o[16];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) o[k] = 1.f / (1.f + __expf(-l[k]));
-    auto sm = [&](int a, int b) {
-      float m = l[a];
-      for (int k = a + 1; k < b; ++k) m = fmaxf(m, l[k]);
-      float sum = 0.f;
-      for (int k = a; k < b; ++k) { o[k] = __expf(l[k] - m); sum += o[k]; }
-      const float inv = 1.f / sum;
-      for (int k = a; k < b; ++k) o[k] *= inv;
-    };
-    sm(4, 6); sm(6, 10); sm(10, 16);
-    store_out16(out16, site0 + tid, o);
-    if (logits16) {
-      float4* dl = reinterpret_cast<float4*>(logits16 + (site0 + tid) * 16);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) dl[k] = make_float4(l[4 * k], l[4 * k + 1], l[4 * k + 2], l[4 * k + 3]);
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------
-// k_tail_site: the same layers for a SMALL FC4 width (v3_slim: 36 -> 18 -> heads), one site per thread.  k_tail gives FC5
-// one thread per output column -- 18 of a block's 256 threads for slim -- and cost 0.034 ms per 33,152-site chunk for ~1,000
-// MACs per site; here every thread keeps its site's 36 inputs in registers and reads the weights from shared memory as
-// warp-wide broadcasts.  Every accumulator adds its terms in the same (ascending k) order as k_tail: results are bit-identical.
+// k_tail_site: FC5 + the four heads (clairvoyante_v3_slim.py:96-118) for a SMALL FC4 width (v3_slim: 36 -> 18 -> 16 outputs),
+// one site per thread: the thread keeps its site's 36 inputs in registers and reads the weights from shared memory as
+// warp-wide broadcasts; every accumulator adds its terms in ascending k.  (The kernel this replaced gave FC5 one thread per
+// output column -- 18 of a block's 256 threads busy -- and took 0.034 ms per 33,152-site chunk for ~1,000 MACs per site;
+// this one takes 0.016 ms with bit-identical results.)
 // ------------------------------------------------------------------------------------
 template <int N4, int N5>
 __global__ void __launch_bounds__(128)

@@ -1,17 +1,17 @@
-"""A/B of the resident-weight conv kernels (ConvSlabCfg RES, conv_tc_slab.cuh) on one B200: for CVB_CONV_RESIDENT in
-0 (ring, default), 1 (conv3), 2 (conv2), 3 (both) and both variants, checks that the logits are BIT-IDENTICAL to the default
-path (the same MMAs in the same order on the same operands) and prints per-kernel ms per chunk.  Run each setting under its
-own timeout on the GPU box (tools/capture_resident.sh): a mis-programmed descriptor hangs the kernel, it does not fail.
-    python tools/ab_resident.py <variant: v3|slim> <setting>        # writes gpurun_out/ab_resident_<variant>_<setting>.npy/json"""
+"""A/B of one build against a saved baseline on one B200: per-kernel ms per chunk (cvb_profile_* events) and whether the logits
+are BIT-IDENTICAL to the run tagged "0" (same MMAs in the same order on the same operands), else the largest difference.
+Round 2 used it for every kernel experiment of profiles/r02_ab_log.md (then called ab_resident.py; its first subject, the
+CVB_CONV_RESIDENT switch, is gone: conv3 keeps its taps resident, conv2 streams them).  Run every setting under its own
+timeout on the GPU box: a mis-programmed descriptor hangs the kernel, it does not fail.
+    python tools/ab_kernels.py <variant: v3|slim> <tag> [ENV=VALUE,...]      # writes gpurun_out/ab_<variant>_<tag>.npy/json"""
 import json
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 variant, setting = sys.argv[1], sys.argv[2]
-os.environ["CVB_CONV_RESIDENT"] = setting
-extra = sys.argv[3] if len(sys.argv) > 3 else ""          # further opt-in switches, e.g. CVB_SLIM_FC4_TC=1 (not bit-identical:
-for kv in filter(None, extra.split(",")):                 # bf16x3 GEMM instead of fp32 SIMT -- max |diff| is reported)
+extra = sys.argv[3] if len(sys.argv) > 3 else ""          # diagnostic switches for this run, e.g. CVB_PDL=0,CVB_COMPUTE=fp16
+for kv in filter(None, extra.split(",")):
     k, v = kv.split("=")
     os.environ[k] = v
 tag = setting + ("_" + extra.replace("=", "").replace(",", "_") if extra else "")
@@ -29,8 +29,8 @@ m.setWeights(I.init_weights("v3" if variant == "v3" else "v3_slim", 0))
 chunk = 18944 if variant == "v3" else 33152
 x = synth.make_sites(chunk + 1234, 1)          # one full chunk and a ragged one
 _, logits = m.predictLogits(x)
-np.save("gpurun_out/ab_resident_%s_%s.npy" % (variant, tag), logits)
-ref_fn = "gpurun_out/ab_resident_%s_0.npy" % variant
+np.save("gpurun_out/ab_%s_%s.npy" % (variant, tag), logits)
+ref_fn = "gpurun_out/ab_%s_0.npy" % variant
 same = bool(np.array_equal(np.load(ref_fn), logits)) if tag != "0" and os.path.exists(ref_fn) else None
 maxdiff = float(np.abs(np.load(ref_fn) - logits).max()) if tag != "0" and os.path.exists(ref_fn) else None
 
@@ -45,8 +45,8 @@ m.profileBegin()
 for _ in range(4):
     m.predictDevice(xd.data_ptr(), N, od.data_ptr(), None, st)
 pr = m.profileRead()
-out = {"variant": variant, "CVB_CONV_RESIDENT": setting, "extra": extra, "bit_identical_to_default": same, "max_abs_logit_diff": maxdiff,
+out = {"variant": variant, "tag": setting, "extra": extra, "bit_identical_to_default": same, "max_abs_logit_diff": maxdiff,
        "ms_per_chunk": {k: round(v[0] / max(v[1], 1), 4) for k, v in pr.items()}}
 print(json.dumps(out))
-json.dump(out, open("gpurun_out/ab_resident_%s_%s.json" % (variant, tag), "w"))
+json.dump(out, open("gpurun_out/ab_%s_%s.json" % (variant, tag), "w"))
 m.close()
