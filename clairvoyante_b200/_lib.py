@@ -77,6 +77,8 @@ SIGNATURES = {
     "cvb_predict_host_f16": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cvb_predict_device": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "cvb_predict_device_x": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, c_vp, c_vp, c_vp]),
+    "cvb_predict_submit": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    "cvb_predict_collect": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cvb_predict_host_counts_i16": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cvb_predict_host_counts_u8": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cvb_loss_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),

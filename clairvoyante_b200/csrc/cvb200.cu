@@ -85,6 +85,11 @@ struct cvb_model {
   cudaStream_t s_aux = nullptr;  // second branch of the backward pass: weight gradients run beside the data-gradient chain
   cudaEvent_t e_fork = nullptr, e_join = nullptr;
   cudaEvent_t e_h2d[NSLOT], e_comp[NSLOT], e_d2h[NSLOT];
+  // cvb_predict_submit / cvb_predict_collect: one small batch per slot in flight
+  struct Ticket { bool busy = false; bool logits = false; int64_t n = 0; uint32_t gen = 0; };
+  Ticket tickets[NSLOT];
+  int next_slot = 0;
+  int tickets_out() const { int k = 0; for (auto& t : tickets) k += t.busy; return k; }
   bool events = false;
   int64_t launches = 0;
   // tensor-core path (CVB_COMPUTE_FP16X3): pre-split FC4 weights + TMA descriptors
@@ -316,6 +321,7 @@ static float* slot_ptr(cvb_model* m, int slot) {
 }
 extern "C" int cvb_set_variable(cvb_model* m, const char* name, int slot, const float* host, int64_t n) {
   if (!m || !name || !host) return fail("cvb_set_variable: NULL argument");
+  if (m->tickets_out()) return fail("cvb_set_variable: %d submitted batch(es) still in flight (cvb_predict_collect)", m->tickets_out());
   const VarInfo* v = m->info(name);
   if (!v) return fail("cvb_set_variable: no variable named '%s'", name);
   if (n != v->numel) return fail("cvb_set_variable: '%s' has %lld elements, got %lld", name, (long long)v->numel, (long long)n);
@@ -350,6 +356,7 @@ static inline uint64_t mix64(uint64_t z) {
 }
 extern "C" int cvb_init_weights(cvb_model* m, uint64_t seed) {
   if (!m) return fail("cvb_init_weights: NULL model");
+  if (m->tickets_out()) return fail("cvb_init_weights: %d submitted batch(es) still in flight (cvb_predict_collect)", m->tickets_out());
   CK(cudaSetDevice(m->device));
   std::vector<float> h((size_t)m->nparams, 0.f);
   uint64_t ctr = 0;
@@ -1076,6 +1083,7 @@ static int predict_host_impl(cvb_model* m, const void* xv, int kind, int64_t n, 
   if (n < 0) return fail("cvb_predict_host: negative n");
   if (n == 0) return 0;
   if (!x || !base || !zygosity || !var_type || !indel_length) return fail("cvb_predict_host: NULL buffer");
+  if (m->tickets_out()) return fail("cvb_predict_host: %d submitted batch(es) not collected yet (cvb_predict_collect)", m->tickets_out());
   CK(cudaSetDevice(m->device));
   if (ensure_host_slots(m)) return 1;
   if (n >= (1 << 18)) {
@@ -1175,6 +1183,82 @@ static int predict_host_impl(cvb_model* m, const void* xv, int kind, int64_t n, 
       }
     }
   }
+  return 0;
+}
+
+// ---- pipelined small batches: submit k+1 .. k+3 while k is on the device ---------------------------------------------------
+// A synchronous 1,000-site call (the reference's predictBatchSize) spends ~50 us staging 528 KB of pageable counts, ~73 us in
+// the five kernels and ~20 us coming back, one after the other.  With up to NSLOT batches in flight the staging copy of the
+// next batch and the copy-out of the previous one run on the host while the device works: the call rate becomes
+// max(host work, device chain) instead of their sum.  Each ticket owns one slot (device input / output buffers, pinned
+// staging buffers, three events); the kernels of consecutive tickets are serialised on s_comp, so the shared intermediates
+// (p1 .. h4) are safe.
+extern "C" int cvb_predict_submit(cvb_model* m, const void* xv, int x_kind, int64_t n, int want_logits, int* ticket) {
+  if (!m || !ticket) return fail("cvb_predict_submit: NULL argument");
+  if (x_kind < 0 || x_kind > 3) return fail("cvb_predict_submit: unknown element kind %d", x_kind);
+  if (n < 0) return fail("cvb_predict_submit: negative n");
+  if (n > 0 && !xv) return fail("cvb_predict_submit: NULL buffer");
+  if (n > m->CHUNK)
+    return fail("cvb_predict_submit: %lld sites exceed one device pass (%lld); use cvb_predict_host, which pipelines its chunks",
+                (long long)n, (long long)m->CHUNK);
+  const int sl = m->next_slot;
+  cvb_model::Ticket& t = m->tickets[sl];
+  if (t.busy) return fail("cvb_predict_submit: all %d slots are in flight; collect the oldest ticket first", cvb_model::NSLOT);
+  CK(cudaSetDevice(m->device));
+  if (ensure_host_slots(m)) return 1;
+  const char* x = static_cast<const char*>(xv);
+  const size_t bytes = (size_t)n * 528 * kXBytes[x_kind];
+  if (n > 0) {
+    void* dx = x_kind == X_F32 ? (void*)m->d_x[sl] : (void*)m->d_x16[sl];
+    // always staged (the caller's buffer is free again when this returns), in four pieces: each is on its way to the device
+    // while the next is copied
+    char* hs = reinterpret_cast<char*>(m->h_x[sl]);
+    const size_t piece = ((bytes / 4) + 4095) & ~(size_t)4095;
+    for (size_t o = 0; o < bytes; o += piece) {
+      const size_t len = std::min(piece, bytes - o);
+      memcpy(hs + o, x + o, len);
+      CK(cudaMemcpyAsync(static_cast<char*>(dx) + o, hs + o, len, cudaMemcpyHostToDevice, m->s_h2d));
+    }
+    CK(cudaEventRecord(m->e_h2d[sl], m->s_h2d));
+    CK(cudaStreamWaitEvent(m->s_comp, m->e_h2d[sl], 0));
+    const int64_t np = (n + 3) & ~(int64_t)3;
+    float* o = m->d_out[sl];
+    const OutDst dst{nullptr, o, o + np * 4, o + np * 6, o + np * 10};
+    if (forward_chunk(m, dx, x_kind, n, dst, want_logits ? m->d_lg[sl] : nullptr, m->s_comp)) return 1;
+    CK(cudaEventRecord(m->e_comp[sl], m->s_comp));
+    CK(cudaStreamWaitEvent(m->s_d2h, m->e_comp[sl], 0));
+    CK(cudaMemcpyAsync(m->h_out[sl], o, (size_t)np * 64, cudaMemcpyDeviceToHost, m->s_d2h));
+    if (want_logits) CK(cudaMemcpyAsync(m->h_lg[sl], m->d_lg[sl], (size_t)n * 64, cudaMemcpyDeviceToHost, m->s_d2h));
+    CK(cudaEventRecord(m->e_d2h[sl], m->s_d2h));
+  }
+  t.busy = true;
+  t.logits = want_logits != 0;
+  t.n = n;
+  t.gen = (t.gen + 1) & 0xffffff;
+  *ticket = (int)(t.gen << 4) | sl;
+  m->next_slot = (sl + 1) % cvb_model::NSLOT;
+  return 0;
+}
+
+extern "C" int cvb_predict_collect(cvb_model* m, int ticket, float* base, float* zygosity, float* var_type, float* indel_length,
+                                   float* logits16) {
+  if (!m) return fail("cvb_predict_collect: NULL model");
+  const int sl = ticket & 15;
+  if (ticket < 0 || sl >= cvb_model::NSLOT) return fail("cvb_predict_collect: bad ticket %d", ticket);
+  cvb_model::Ticket& t = m->tickets[sl];
+  if (!t.busy || (int)(t.gen << 4 | sl) != ticket) return fail("cvb_predict_collect: ticket %d is not in flight", ticket);
+  const int64_t n = t.n;
+  if (n > 0 && (!base || !zygosity || !var_type || !indel_length)) return fail("cvb_predict_collect: NULL buffer");
+  if (logits16 && !t.logits) return fail("cvb_predict_collect: ticket %d was submitted without logits", ticket);
+  t.busy = false;  // (also on a CUDA error below: the slot is not left blocked)
+  if (n == 0) return 0;
+  CK(cudaSetDevice(m->device));
+  CK(cudaEventSynchronize(m->e_d2h[sl]));
+  float* const heads[4] = {base, zygosity, var_type, indel_length};
+  const int64_t np = (n + 3) & ~(int64_t)3;
+  int64_t off = 0;
+  for (int h = 0; h < 4; off += np * kHeadW[h], ++h) memcpy(heads[h], m->h_out[sl] + off, (size_t)n * kHeadW[h] * 4);
+  if (logits16) memcpy(logits16, m->h_lg[sl], (size_t)n * 64);
   return 0;
 }
 
@@ -2104,6 +2188,7 @@ extern "C" int cvb_loss_host_x(cvb_model* m, const void* x, int x_kind, const fl
 extern "C" int cvb_apply_adam(cvb_model* m, float lr, float l2, float* loss6) {
   if (!m) return fail("cvb_apply_adam: NULL model");
   if (!m->train) return fail("cvb_apply_adam: no gradients (call cvb_train_step_host first)");
+  if (m->tickets_out()) return fail("cvb_apply_adam: %d submitted batch(es) still in flight (cvb_predict_collect)", m->tickets_out());
   CK(cudaSetDevice(m->device));
   cudaStream_t st = m->s_comp;
   TrainWork* w = m->train;
@@ -2147,6 +2232,7 @@ extern "C" int cvb_train_step_host_x(cvb_model* m, const void* x, int x_kind, co
   if (!m) return fail("cvb_train_step_host: NULL model");
   if (x_kind < 0 || x_kind > 3) return fail("cvb_train_step_host: unknown element kind %d", x_kind);
   if (n <= 0) return fail("cvb_train_step_host: empty batch");
+  if (m->tickets_out()) return fail("cvb_train_step_host: %d submitted batch(es) still in flight (cvb_predict_collect)", m->tickets_out());
   if (!x || !y) return fail("cvb_train_step_host: NULL buffer");
   if (drop4 < 0.f || drop4 >= 1.f) return fail("cvb_train_step_host: dropout rate %g outside [0,1)", drop4);
   CK(cudaSetDevice(m->device));

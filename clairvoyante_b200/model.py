@@ -265,6 +265,42 @@ class ClairvoyanteBase(object):
         self.predictBaseRTVal, self.predictZygosityRTVal, self.predictVarTypeRTVal, self.predictIndelLengthRTVal \
             = self.predict(XArray)
 
+    # ---- the same call in two halves: several small batches in flight (cvb_predict_submit / cvb_predict_collect) ----------
+    def predictSubmit(self, XArray, want_logits=False):
+        """Start predict(XArray) and return a ticket; XArray may be reused at once.  Up to four tickets may be outstanding;
+        predictCollect returns them in any order (they complete in submission order).  A batch must fit one device pass
+        (18,944 sites for v3, 33,152 for v3_slim) -- larger ones go through predict, which pipelines its own chunks."""
+        x, kind, n = self._x_arg(XArray)
+        t = ctypes.c_int()
+        _lib.check(self._lib.cvb_predict_submit(self._h, x.ctypes.data, kind, n, 1 if want_logits else 0, ctypes.byref(t)))
+        return (t.value, n, bool(want_logits))
+
+    def predictCollect(self, ticket):
+        """(base, zygosity, varType, indelLength[, logits16]) of a ticket from predictSubmit -- the arrays predict returns"""
+        t, n, want_logits = ticket
+        base = np.empty((n, 4), np.float32); z = np.empty((n, 2), np.float32)
+        v = np.empty((n, 4), np.float32); l = np.empty((n, 6), np.float32)
+        lg = np.empty((n, 16), np.float32) if want_logits else None
+        _lib.check(self._lib.cvb_predict_collect(self._h, t, base.ctypes.data, z.ctypes.data, v.ctypes.data, l.ctypes.data,
+                                                 lg.ctypes.data if want_logits else None))
+        return (base, z, v, l, lg) if want_logits else (base, z, v, l)
+
+    def predictStream(self, batches, depth=3):
+        """predict over an iterable of small batches with `depth` (<= 4) of them in flight: yields predict's four arrays per
+        batch, in order.  The staging copy of batch k+1 and the copy-out of batch k-1 overlap the kernels of batch k."""
+        depth = max(1, min(int(depth), 4))
+        pending = []
+        try:
+            for X in batches:
+                if len(pending) == depth:
+                    yield self.predictCollect(pending.pop(0))
+                pending.append(self.predictSubmit(X))
+            while pending:
+                yield self.predictCollect(pending.pop(0))
+        finally:                                   # a consumer that stops early must not leave tickets outstanding
+            while pending:
+                self.predictCollect(pending.pop(0))
+
     def predictLogits(self, XArray):
         """(out16, logits16): extension used by the parity tests (base head pre-sigmoid)."""
         base, z, t, l, lg = self._predict(XArray, want_logits=True)

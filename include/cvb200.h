@@ -98,6 +98,16 @@ int cvb_predict_host_counts_u8(cvb_model* m, const uint8_t* counts, int64_t n, f
                                float* var_type, float* indel_length, float* logits16);
 /* element kinds of a candidate-tensor buffer */
 enum { CVB_X_F32 = 0, CVB_X_F16 = 1, CVB_X_I16_COUNTS = 2, CVB_X_U8_COUNTS = 3 };
+/* The same call split in two, for drivers that keep several small batches in flight (the reference runs predictNoRT on a
+ * thread while it writes the previous batch, callVar.py:197-205): cvb_predict_submit copies x (n <= one device pass:
+ * 18,944 sites for v3, 33,152 for v3_slim; any CVB_X_* element kind) into a staging slot, enqueues the upload, the kernels
+ * and the download, and returns a ticket -- x may be reused at once; cvb_predict_collect waits for that ticket and fills
+ * the four arrays (and logits16 if the ticket was submitted with want_logits).  Up to 4 tickets may be outstanding; they
+ * complete in submission order; results are bit-identical to cvb_predict_host.  While a ticket is outstanding the
+ * synchronous predict / train / set_variable entry points return an error instead of racing with it.               */
+int cvb_predict_submit(cvb_model* m, const void* x, int x_kind, int64_t n, int want_logits, int* ticket);
+int cvb_predict_collect(cvb_model* m, int ticket, float* base, float* zygosity, float* var_type, float* indel_length,
+                        float* logits16);
 /* same computation on DEVICE buffers (x, out16, logits16 are device pointers on the
  * handle's device); enqueued on `stream` (a cudaStream_t; NULL = the CUDA legacy default
  * stream, exactly as in the runtime API) and NOT synchronised.                                                  */

@@ -308,3 +308,47 @@ def test_c_abi_pinned_buffers_and_device_feeds(variant):
         with pytest.raises(RuntimeError):
             m.setComputeMode("fp16")                                                # plain fp16 is a v3_slim mode
     m.close()
+
+
+@pytest.mark.parametrize("variant,mode", CASES)
+def test_submit_collect_pipeline_matches_predict(variant, mode):
+    """cvb_predict_submit / cvb_predict_collect: several small batches in flight give predict's bits, for every feed, in any
+    collection order; the slot limit, stale tickets and the synchronous entry points' refusal while tickets are out"""
+    from clairvoyante_b200 import utils_v2 as U
+    W = I.init_weights(variant, 3)
+    m = _model(variant, W, mode)
+    x = synth.make_sites(2400, 9)
+    cuts = [(0, 1000), (1000, 1001), (1001, 1334), (1334, 1334), (1334, 2334)]
+    feeds = [x[a:b] for a, b in cuts]
+    feeds[0] = U.with_counts(feeds[0])                       # CountBatch -> uint8 counts
+    feeds[2] = U.pack_counts(feeds[2]).astype(np.int16)      # explicit int16 counts
+    feeds[4] = feeds[4].astype(np.float16)                   # fp16 values
+    want = [m.predict(x[a:b]) for a, b in cuts]
+    tickets = [m.predictSubmit(f) for f in feeds[:4]]
+    with pytest.raises(RuntimeError, match="in flight"):
+        m.predictSubmit(feeds[4])                            # four slots
+    with pytest.raises(RuntimeError, match="not collected"):
+        m.predict(x[:10])
+    with pytest.raises(RuntimeError, match="in flight"):
+        m._set("fc4/bias", 0, W["fc4/bias"])
+    got = {}
+    for i in (2, 0, 3, 1):                                   # any order
+        got[i] = m.predictCollect(tickets[i])
+    with pytest.raises(RuntimeError, match="not in flight"):
+        m.predictCollect(tickets[0])
+    t4 = m.predictSubmit(feeds[4], want_logits=True)
+    got[4] = m.predictCollect(t4)
+    for i, w in enumerate(want):
+        for a, b in zip(w, got[i][:4]):
+            assert a.shape == b.shape and np.array_equal(a, b), (i, a.shape)
+    assert np.array_equal(got[4][4], m.predictLogits(x[1334:2334])[1])
+    with pytest.raises(RuntimeError, match="exceed one device pass"):
+        m.predictSubmit(np.zeros((40000, 33, 4, 4), np.uint8))
+    # the generator form, consumed to the end and abandoned half-way
+    outs = list(m.predictStream([x[i:i + 300] for i in range(0, 2400, 300)], depth=3))
+    assert np.array_equal(np.concatenate([o[2] for o in outs]), m.predict(x)[2])
+    g = m.predictStream([x[i:i + 300] for i in range(0, 2400, 300)], depth=4)
+    next(g)
+    g.close()
+    assert np.array_equal(m.predict(x[:300])[0], outs[0][0])  # nothing left outstanding
+    m.close()

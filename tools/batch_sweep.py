@@ -1,5 +1,6 @@
 """BASELINE.json configs[4]: batch-size sweep 256 -> 65536, v3 (and v3_slim) inference, 1 x B200: sites/s device-resident and
-through the host API (pageable float32 as the reference's callers hold it, and the repo's own CountBatch feed), per-kernel
+through the host API (pageable float32 as the reference's callers hold it, the repo's own CountBatch feed, and that feed with
+three batches in flight through predictSubmit / predictCollect), per-kernel
 duration at every batch, and the achieved fraction of the roofline per batch -- the dominant kernel's algorithmic TFLOP/s over
 the measured dense bf16 figure (the pass is compute-bound: 3,708 FLOP per algorithmic HBM byte), with the HBM view beside it.
 Writes gpurun_out/batch_sweep.json (kept as profiles/rNN_batch_sweep.json).    python tools/batch_sweep.py [variant ...]"""
@@ -55,6 +56,15 @@ for variant, mod in (("v3", cv), ("v3_slim", cvs)):
             for _ in range(k):
                 m.predict(arr)
             host[name] = b * k / (time.perf_counter() - t0)
+        if b <= 16384:      # the same feed with three batches in flight (predictSubmit / predictCollect)
+            arr = utils_v2.with_counts(pool[:b].copy())
+            k = max(8, reps // 2)
+            for _ in m.predictStream([arr] * 4, depth=3):
+                pass
+            t0 = time.perf_counter()
+            for _ in m.predictStream([arr] * k, depth=3):
+                pass
+            host["counts_pipelined"] = b * k / (time.perf_counter() - t0)
         dom = max(prof, key=prof.get)
         chunks = -(-b // 18944) if variant == "v3" else -(-b // 33152)
         fdom = fl["conv1"] + fl["conv2"] if (dom == "front" and "conv2" not in prof) else fl.get(dom, fl["conv1"])
@@ -65,9 +75,9 @@ for variant, mod in (("v3", cv), ("v3_slim", cvs)):
                                  dominant_frac=fdom * (b / chunks) / (prof[dom] / 1e3) / 1e12 / pk["bf16_tflops"],
                                  hbm_gbs=dev * HBM_BYTES_PER_SITE / 1e9, hbm_frac=dev * HBM_BYTES_PER_SITE / 1e9 / pk["hbm_gbs"]))
         rows.append(row)
-        print(variant, b, "device %.2f M/s (%.1f us/call)  host fp32 %.2f M/s  counts %.2f M/s  pass frac %.3f  %s" %
-              (dev / 1e6, 1e6 * b / dev, host["fp32_pageable"] / 1e6, host["counts"] / 1e6, row["roofline"]["pass_frac"],
-               row["kernel_us"]), flush=True)
+        print(variant, b, "device %.2f M/s (%.1f us/call)  host fp32 %.2f M/s  counts %.2f M/s  pipelined %.2f M/s  pass frac %.3f  %s" %
+              (dev / 1e6, 1e6 * b / dev, host["fp32_pageable"] / 1e6, host["counts"] / 1e6,
+               host.get("counts_pipelined", 0) / 1e6, row["roofline"]["pass_frac"], row["kernel_us"]), flush=True)
     res[variant] = rows
     m.close()
 json.dump(res, open("gpurun_out/batch_sweep.json", "w"), indent=1)
