@@ -343,6 +343,55 @@ def train_leg(args, cv, W, local, rank, world, dist, barrier, max_over_ranks):
                 reference_published="README.md:307-319: 90 s per 11 M tensors on a V100 (122 k/s), ~3.8 k/s on 28 Xeon cores", **res)
 
 
+def small_batch_leg(cv, W, local, batch=1000):
+    """BASELINE configs[4]'s left end, the reference drivers' real call pattern: predictBatchSize = 1000 sites per call
+    (param.py:12, callVar.py:184).  Device-resident calls, the synchronous host API on a pageable CountBatch, and the same
+    feed with three calls in flight (predictSubmit / predictCollect)."""
+    import time
+
+    import torch
+
+    from clairvoyante_b200 import synth, utils_v2
+    m = cv.Clairvoyante(device=local)
+    m.setWeights(W)
+    x = synth.make_sites(batch, 5)
+    feed = utils_v2.with_counts(x.copy())
+    xd = torch.from_numpy(x).cuda()
+    od = torch.empty((batch, 16), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    reps = 300
+    for _ in range(10):
+        m.predictDevice(xd.data_ptr(), batch, od.data_ptr(), None, st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(reps):
+        m.predictDevice(xd.data_ptr(), batch, od.data_ptr(), None, st)
+    e1.record()
+    torch.cuda.synchronize()
+    dev_us = e0.elapsed_time(e1) * 1e3 / reps
+    out = dict(batch=batch, config="configs[4] left end: %d sites per call (the reference's predictBatchSize)" % batch,
+               device=dict(value=batch / dev_us * 1e6, unit="sites/s", us_per_call=dev_us))
+    for name, arr in (("host_api_fp32_pageable", x), ("host_api_counts", feed)):
+        for _ in range(5):
+            m.predict(arr)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            m.predict(arr)
+        us = (time.perf_counter() - t0) * 1e6 / reps
+        out[name] = dict(value=batch / us * 1e6, unit="sites/s", us_per_call=us, api="Clairvoyante.predict, one call at a time")
+    for _ in m.predictStream([feed] * 8, depth=3):
+        pass
+    t0 = time.perf_counter()
+    for _ in m.predictStream([feed] * reps, depth=3):
+        pass
+    us = (time.perf_counter() - t0) * 1e6 / reps
+    out["host_api_counts_pipelined"] = dict(value=batch / us * 1e6, unit="sites/s", us_per_call=us,
+                                            api="Clairvoyante.predictStream (cvb_predict_submit / cvb_predict_collect), 3 calls in flight")
+    m.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -418,7 +467,9 @@ def main():
                              frac=value / world * HBM_BYTES_PER_SITE / 1e9 / pk["hbm_gbs"], peak_source=pk["source"],
                              note="not the binding bound: 3,708 FLOP per algorithmic HBM byte"))
 
-    slim = train = None
+    slim = train = small = None
+    if not args.no_extra and world == 1:
+        small = small_batch_leg(cv, W, local)
     if not args.no_extra:
         if args.variant == "v3":
             # BASELINE configs[2]: v3_slim, site list sharded 1 -> N GPUs, recorded at every N the driver runs -- in the
@@ -455,7 +506,7 @@ def main():
                                                "rest fp32 SIMT" % ("conv2+conv3+FC4+FC5/heads" if args.variant == "v3" else "conv2+conv3+FC4"))
                                               if tensor else "fp32 SIMT")),
                     clocks=r["clocks"], e2e=r["e2e"], gpu_launches=r["launches"], roofline=roofline, cpu_baseline=cpu,
-                    slim=slim, train=train, build=source_hash())
+                    slim=slim, train=train, small_batch=small, build=source_hash())
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
