@@ -46,12 +46,15 @@ for in_library in (True, False):
     err1 = max(float(np.abs(w[k] - wref1[k]).max()) for k in w)
     ldp.append(float(tr.train(x, y, seed=5)[0]))
     w = m.getWeights()
-    err = max(float(np.abs(w[k] - wref[k]).max()) for k in w)
-    print("rank %d in_library=%s: DP losses %s single %s | max |w_dp - w_single| after 1 step = %.3g, after 2 steps = %.3g"
-          % (rank, in_library, ldp, lref, err1, err), flush=True)
-    # shard sums meet in a different order than one GPU's atomics: gradients agree to rounding, and Adam's m / sqrt(v) turns
-    # a rounding-level difference of a near-zero gradient into a visible fraction of lr = 1e-3 from the second step on
-    assert all(abs(a - b) <= 1e-5 * abs(b) for a, b in zip(ldp, lref)) and err1 < 5e-6 and err < 2e-4
+    d2 = np.concatenate([np.abs(w[k] - wref[k]).ravel() for k in w])
+    err, q999 = float(d2.max()), float(np.quantile(d2, 0.999))
+    print("rank %d in_library=%s: DP losses %s single %s | max |w_dp - w_single| after 1 step = %.3g, after 2 steps = %.3g "
+          "(99.9 %% of the weights within %.3g)" % (rank, in_library, ldp, lref, err1, err, q999), flush=True)
+    # shard sums meet in a different order than one GPU's atomics: gradients agree to rounding, and from the second step on
+    # Adam's m / sqrt(v) turns a rounding-level difference of a near-zero gradient into a visible fraction of its step size
+    # lr = 1e-3 on that one weight (observed over repeated runs: 1e-5 .. 2e-4 on the worst weight): the first step is held to
+    # rounding, the second to "a handful of weights moved by less than one Adam step, the rest to rounding"
+    assert all(abs(a - b) <= 1e-5 * abs(b) for a, b in zip(ldp, lref)) and err1 < 5e-6 and err < 1e-3 and q999 < 1e-5
     # every rank holds the same weights bit for bit (identical reduced gradients, identical Adam)
     ck = torch.tensor([float(np.sum([w[k].astype(np.float64).sum() for k in w]))], device="cuda", dtype=torch.float64)
     lo, hi = ck.clone(), ck.clone()

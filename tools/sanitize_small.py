@@ -13,6 +13,12 @@ for variant, mod, modes in (("v3", cv, ("fp16x3", "fp32")), ("v3_slim", cvs, ("f
         for feed in (x, U.with_counts(x), U.pack_counts(x).astype(np.int16), x.astype(np.float16)):
             m.predict(feed)
         m.predict(synth.make_sites(1000, 2))
+        xs = synth.make_sites(1500, 3)                 # four tickets in flight, collected out of order, then the generator
+        t = [m.predictSubmit(U.with_counts(xs[i:i + 375])) for i in range(0, 1500, 375)]
+        for i in (1, 3, 0, 2):
+            m.predictCollect(t[i])
+        for _ in m.predictStream([xs[:500], xs[500:501], xs[501:]], depth=3):
+            pass
     m.train(x, y); m.train(x, y); m.train(x, y); m.getLoss(x, y)
     m.close()
     print(variant, "ok", flush=True)
