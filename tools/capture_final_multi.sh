@@ -8,5 +8,8 @@ if [ "$N" = "2" ]; then
   timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3 > gpurun_out/r02_tests_2gpu.log
   timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_small.py 2>&1 | tail -8 > gpurun_out/r02_sanitizer.log
   cat gpurun_out/r02_tests_2gpu.log gpurun_out/r02_sanitizer.log
+else
+  timeout 600 python -m pytest tests/test_dp_gpu.py -q 2>&1 | tail -3 > gpurun_out/r02_tests_dp_n$N.log
+  cat gpurun_out/r02_tests_dp_n$N.log
 fi
 bash tools/capture_r02_multi.sh $N
