@@ -12,7 +12,6 @@ so no tensor text is printed or parsed.  Alignments and reference come from `sam
 `--pypy`, `--threads` and `--delay` are accepted for command-line compatibility; there is nothing left for them to tune.
 """
 import argparse
-import gzip
 import os
 import sys
 import types

@@ -4,7 +4,6 @@ major ones unless --includingAllContigs) are cut into --refChunkSize pieces and 
 The commands run `python -m clairvoyante_b200.callVarBam`, one process per chunk on one GPU each (`CVB_DEVICE` /
 `CUDA_VISIBLE_DEVICES` select it): sites are independent, there is no collective."""
 import argparse
-import gzip
 import os
 import sys
 

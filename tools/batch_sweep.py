@@ -10,7 +10,6 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np  # noqa: E402
 import torch  # noqa: E402
 from bench import FLOPS_PER_SITE, HBM_BYTES_PER_SITE, peaks  # noqa: E402
 from clairvoyante_b200 import clairvoyante_v3 as cv, clairvoyante_v3_slim as cvs, initializers as I, synth, utils_v2  # noqa: E402

@@ -2,7 +2,7 @@
 process: run twice).   python tools/small_n_probe.py <variant>"""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from clairvoyante_b200 import clairvoyante_v3 as cv, clairvoyante_v3_slim as cvs, initializers as I, synth
 variant = sys.argv[1] if len(sys.argv) > 1 else "v3_slim"
 m = (cv if variant == "v3" else cvs).Clairvoyante()

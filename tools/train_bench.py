@@ -5,7 +5,6 @@ import os
 import sys
 import time
 
-import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from clairvoyante_b200 import param, synth   # noqa: E402

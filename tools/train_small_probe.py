@@ -2,7 +2,7 @@
 a data-parallel step at the reference's global batch of 10,000 on 8 GPUs is 1,250 tensors).  python tools/train_small_probe.py"""
 import os, sys, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from clairvoyante_b200 import clairvoyante_v3 as cv, synth
 m = cv.Clairvoyante(); m.init(seed=1)
 out = {}
