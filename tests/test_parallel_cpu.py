@@ -56,3 +56,41 @@ def test_sharded_predict_equals_single_process_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_predict_stream_keeps_depth_in_flight_and_drains_on_close():
+    """cpu: host logic of ClairvoyanteBase.predictStream (model.py) over a stand-in for the submit / collect pair: results in
+    submission order, never more than `depth` tickets outstanding, and none left when the consumer stops early"""
+    from clairvoyante_b200.model import ClairvoyanteBase
+
+    class Fake(object):
+        predictStream = ClairvoyanteBase.predictStream
+
+        def __init__(self):
+            self.out, self.peak, self.log = [], 0, []
+
+        def predictSubmit(self, X, want_logits=False):
+            self.out.append(X)
+            self.peak = max(self.peak, len(self.out))
+            self.log.append(("s", X))
+            return X
+
+        def predictCollect(self, t):
+            assert self.out[0] == t                     # oldest first
+            self.out.pop(0)
+            self.log.append(("c", t))
+            return (t, t * 10)
+
+    f = Fake()
+    assert list(f.predictStream(range(7), depth=3)) == [(i, i * 10) for i in range(7)]
+    assert f.peak == 3 and f.out == []
+    assert f.log[:5] == [("s", 0), ("s", 1), ("s", 2), ("c", 0), ("s", 3)]     # a collect only once `depth` are in flight
+    f = Fake()
+    assert list(f.predictStream(range(2), depth=9)) == [(0, 0), (1, 10)] and f.peak == 2      # depth is capped at 4 slots
+    f = Fake()
+    assert list(f.predictStream(range(9), depth=9)) and f.peak == 4
+    f = Fake()
+    g = f.predictStream(range(10), depth=4)
+    assert next(g) == (0, 0)
+    g.close()                                           # the consumer walks away: everything submitted is still collected
+    assert f.out == [] and [t for k, t in f.log if k == "s"] == [t for k, t in f.log if k == "c"]
