@@ -6,7 +6,7 @@ update).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs may import it; the product path
 (clairvoyante_b200/) never does and fails loudly without its CUDA library.
 
-PARITY UNPINNED: the reference's arithmetic lives in TensorFlow 1.12
+PARITY: forward pinned (e), training arithmetic UNPINNED.  The reference's arithmetic lives in TensorFlow 1.12
 (requirements.txt:1), which is not vendored under /root/reference and not
 installable here (no wheel, no network, Python-2 sources).  The reference ships
 no tests, no golden vectors and no weights.  What pins this
@@ -20,8 +20,16 @@ selu.py, unmodified -- executed at fixture-generation time on a stand-in for the
 TensorFlow-1.x API (tests/golden/tf1_stand_in.py, op kernels on torch float64):
 tests/golden/reference_graph.npz holds its predict / getLoss / train results and
 tests/test_reference_graph_cpu.py requires this oracle to reproduce them to
-rounding.  (d) ties the wiring, formulas and feeds to the reference's source;
-TensorFlow's own kernels remain restated, hence still "unpinned" for those.
+rounding.  (d) ties the wiring, formulas and feeds to the reference's source.
+(e) TensorFlow's FORWARD op semantics -- Conv2D SAME with even kernels, VALID
+max-pool, the NHWC flatten order, MatMul + BiasAdd, sigmoid / softmax -- are
+pinned against an independent executor of TensorFlow graphs: the forward
+GraphDef of both variants (tests/golden/tf_graphdef.py, TF's proto schemas)
+run by OpenCV's dnn TensorFlow importer; tests/golden/opencv_tf_forward.npz
+holds its outputs and tests/test_oracle_opencv_cpu.py requires this oracle to
+match them (6e-7 on the head outputs).  What remains restated from
+documentation, hence still "unpinned": the gradients of those ops and TF-1.x
+Adam (cv_oracle_torch.py: torch autograd + the documented update rule).
 
 Reference anchors (all paths relative to /root/reference):
   graph v3      clairvoyante/clairvoyante_v3.py:54-138

@@ -122,3 +122,34 @@ def test_argmax_identical_on_trained_weights(variant, mode):
     assert np.array_equal(np.concatenate([base, z, t, l], 1), out16)
     print("%s/%s: exempt (near-tie) fraction per head: %s" % (variant, mode, ["%.4f" % f for f in exempt_fractions(fx)]))
     m.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,mode", [("v3", "fp16x3"), ("v3", "fp32"), ("v3_slim", "fp16x3"), ("v3_slim", "fp32")])
+def test_cuda_matches_the_independent_tf_executor(variant, mode):
+    """The CUDA path against tests/golden/opencv_tf_forward.npz -- the forward GraphDef executed by OpenCV's TensorFlow
+    importer (tests/golden/tf_graphdef.py, make_golden_opencv.py), an implementation of TF's op semantics written by neither the
+    reference's authors nor this repo's: logits within north_star's 1e-3, outputs within 2e-4, argmax identical wherever the
+    fixture's top-2 margin exceeds 2e-3 -- with no oracle in the loop"""
+    from clairvoyante_b200 import initializers as I
+    if variant == "v3":
+        from clairvoyante_b200 import clairvoyante_v3 as cv
+    else:
+        from clairvoyante_b200 import clairvoyante_v3_slim as cv
+    with np.load(os.path.join(GOLD, "opencv_tf_forward.npz")) as z:
+        fx = {k: z[k] for k in z.files}
+    x, _ = synth.make_labeled_sites(int(fx["n"]), int(fx["data_seed"]))
+    m = cv.Clairvoyante()
+    m.setComputeMode(mode)
+    for tag in ("trained", "init"):
+        W = load_trained(variant)[0] if tag == "trained" else I.init_weights(variant, 4)
+        m.setWeights(W)
+        out16, lg = m.predictLogits(x)
+        want_lg, want = fx["%s_%s_logits" % (variant, tag)], fx["%s_%s_out16" % (variant, tag)]
+        assert np.abs(lg - want_lg).max() <= 1e-3, (tag, float(np.abs(lg - want_lg).max()))
+        assert np.abs(out16 - want).max() <= 2e-4, tag
+        for a, b in HEADS:
+            srt = np.sort(want_lg[:, a:b], 1)
+            clear = srt[:, -1] - srt[:, -2] > 2e-3
+            assert (lg[:, a:b].argmax(1) == want_lg[:, a:b].argmax(1))[clear].all(), (tag, a)
+    m.close()
