@@ -27,9 +27,11 @@ pinned against an independent executor of TensorFlow graphs: the forward
 GraphDef of both variants (tests/golden/tf_graphdef.py, TF's proto schemas)
 run by OpenCV's dnn TensorFlow importer; tests/golden/opencv_tf_forward.npz
 holds its outputs and tests/test_oracle_opencv_cpu.py requires this oracle to
-match them (6e-7 on the head outputs).  What remains restated from
-documentation, hence still "unpinned": the gradients of those ops and TF-1.x
-Adam (cv_oracle_torch.py: torch autograd + the documented update rule).
+match them (6e-7 on the head outputs).  Training: gradients are torch autograd
+of that forward function (cv_oracle_torch.py); TF-1.x Adam is restated from its
+documented update and cross-checked against torch.optim.Adam with epsilon moved
+to TensorFlow's position (tests/test_oracle.py) -- that placement of epsilon is
+the one thing still "unpinned".
 
 Reference anchors (all paths relative to /root/reference):
   graph v3      clairvoyante/clairvoyante_v3.py:54-138
