@@ -43,6 +43,13 @@ def main():
             ys = run_pb(pb, x, list(outs) + list(logits))
             out["%s_%s_out16" % (variant, tag)] = np.concatenate([y.reshape(N, -1) for y in ys[:4]], 1)
             out["%s_%s_logits" % (variant, tag)] = np.concatenate([y.reshape(N, -1) for y in ys[4:]], 1)
+    # the inputs and weights of reference_graph.npz (the reference's own predict() on the stand-in): same sites, seed-0 initialisers
+    with np.load(os.path.join(HERE, "reference_graph.npz")) as z:
+        xr = z["x"].astype(np.float32)
+    for variant in ("v3", "v3_slim"):
+        pb, outs, logits = forward_graph(I.init_weights(variant, 0), variant, len(xr))
+        ys = run_pb(pb, xr, list(outs))
+        out["%s_refgraph_out16" % variant] = np.concatenate([y.reshape(len(xr), -1) for y in ys], 1)
     rng = np.random.default_rng(SEED)
     for i, (kh, cin, cout, pool) in enumerate(LAYERS):
         k = rng.standard_normal((kh, 4, cin, cout)).astype(np.float32)

@@ -80,6 +80,23 @@ def test_forward_matches_the_tf_importer(fx, variant, tag):
         assert (ref["logits"][:, a:b].argmax(1) == lg[:, a:b].argmax(1))[clear].all()
 
 
+@pytest.mark.parametrize("tag,variant", [("v3", "v3"), ("slim", "v3_slim")])
+def test_tf_importer_equals_the_references_own_predict(fx, tag, variant):
+    """no oracle in this one: reference_graph.npz holds what the REFERENCE'S OWN clairvoyante_v3*.py / selu.py return from
+    predict() when executed on the TF stand-in (make_golden_reference_graph.py); OpenCV's TensorFlow importer, given the GraphDef
+    of tf_graphdef.py with the same weights and sites, must return the same 16 numbers per site -- the reference's wiring and an
+    independent implementation of TensorFlow's kernels meet"""
+    with np.load(os.path.join(GOLD, "reference_graph.npz")) as z:
+        want = z[tag + "/predict"]
+    got = fx["%s_refgraph_out16" % variant]
+    assert got.shape == want.shape == (256, 16)
+    assert np.abs(got - want).max() <= 2e-5          # fp32 arithmetic in OpenCV, |logit| up to ~60 with initialiser weights
+    for a, b in ((4, 6), (6, 10), (10, 16)):         # same call wherever the two leading probabilities are not a tie
+        srt = np.sort(want[:, a:b], 1)               # (initialiser weights leave most v3 zygosity logits at SELU's floor: 0.5 / 0.5)
+        clear = srt[:, -1] - srt[:, -2] > 1e-4
+        assert (got[:, a:b].argmax(1) == want[:, a:b].argmax(1))[clear].all()
+
+
 def test_fixture_is_what_opencv_computes_now(fx):
     """the committed fixture is reproducible: re-run the importer (skipped where cv2 is absent)"""
     cv2 = pytest.importorskip("cv2")
