@@ -109,4 +109,4 @@ def test_fixture_is_what_opencv_computes_now(fx):
         pb, outs, logits = forward_graph(_weights(variant, "trained"), variant, len(x))
         ys = M.run_pb(pb, x, list(outs) + list(logits))
         got = np.concatenate([y.reshape(len(x), -1) for y in ys[:4]], 1)
-        assert np.abs(got - fx["%s_trained_out16" % variant]).max() <= 1e-6
+        assert np.abs(got - fx["%s_trained_out16" % variant]).max() <= 5e-6      # (OpenCV dispatches on the host's vector ISA)
